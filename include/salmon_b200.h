@@ -1,0 +1,139 @@
+/*
+ * salmon_b200.h -- C ABI of libsalmon_b200.so (B200 / sm_100a).
+ *
+ * Drop-in boundary for Salmon's quantification hot path.
+ * The reference has no FFI layer; the seams are ordinary C++ calls.  Each entry
+ * point below names the reference call it replaces (file:line relative to
+ * COMBINE-lab/salmon v1.11.4).  Plain pointers and sizes only; all pointers are
+ * HOST pointers unless a name ends in _dev.  Return 0 on success, negative on
+ * error (message via sb_last_error()); sb_em_optimize returns 1 where the
+ * reference returns `false` ("Total alpha weight was too small").
+ *
+ * There is no CPU fallback: every compute entry point fails with
+ * SB_ERR_NO_DEVICE if no CUDA device is usable.
+ */
+#ifndef SALMON_B200_H
+#define SALMON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_OK 0
+#define SB_ERR_INVALID (-1)
+#define SB_ERR_NO_DEVICE (-2)
+#define SB_ERR_CUDA (-3)
+#define SB_ERR_NOMEM (-4)
+#define SB_ERR_NCCL (-5)
+#define SB_ERR_STATE (-6)
+
+/* ---- library ---------------------------------------------------------- */
+int sb_version(void);                 /* 10000*major + 100*minor + patch */
+const char* sb_last_error(void);      /* thread-local, never NULL */
+int sb_device_count(void);            /* number of usable CUDA devices (0 if none) */
+
+/* ---- equivalence classes ---------------------------------------------- */
+/* Host view of EquivalenceClassBuilder<TGValue>::eqVec() after finish()
+ * (include/salmon/internal/quant/EquivalenceClassBuilder.hpp:165-181,210-223):
+ * class c has transcripts tids[off[c]..off[c+1]) (sorted ascending, as
+ * TranscriptGroup keeps them), TGValue::weights in `weights` (normalised to sum
+ * 1 per class by finish()), TGValue::count in `counts`. */
+typedef struct sb_eq_csr {
+  uint64_t n_classes;
+  uint32_t n_txps;
+  const uint64_t* off;     /* [n_classes+1] */
+  const uint32_t* tids;    /* [off[n_classes]] */
+  const double* weights;   /* [off[n_classes]] */
+  const uint64_t* counts;  /* [n_classes] */
+} sb_eq_csr;
+
+/* ---- EM / VBEM optimiser ---------------------------------------------- */
+/* The SalmonOpts fields CollapsedEMOptimizer::optimize reads
+ * (src/inference/CollapsedEMOptimizer.cpp:743-773,785,791,805,817,862). */
+typedef struct sb_em_params {
+  int32_t use_vbem;             /* sopt.useVBOpt (default 1) */
+  int32_t per_txp_prior;        /* sopt.perTranscriptPrior (default 1) */
+  int32_t init_uniform;         /* sopt.initUniform */
+  int32_t eq_class_mode;        /* sopt.eqClassMode */
+  int32_t no_rich_eq;           /* sopt.noRichEqClasses */
+  int32_t no_length_correction; /* sopt.noLengthCorrection */
+  int32_t alt_init;             /* sopt.meta || sopt.alternativeInitMode */
+  int32_t reserved;
+  double vb_prior;              /* sopt.vbPrior (1e-2) */
+  double tol;                   /* relDiffTolerance (0.01) */
+  double num_required_frags;    /* sopt.numRequiredFragments (5e7) */
+  uint32_t min_iter;            /* 100 (:890); 50 for bootstraps (:411) */
+  uint32_t max_iter;            /* 10000 (pipeline/MappingPipelineStages.cpp:49) */
+} sb_em_params;
+
+typedef struct sb_em_stats {
+  uint32_t iters;
+  uint32_t converged;
+  double max_rel_diff;     /* of the last iteration */
+  double alpha_sum;        /* after truncation (:1004-1014) */
+  uint64_t n_degenerate;   /* markDegenerateClasses (:330-394) */
+  uint64_t n_multi_classes;/* valid classes with >1 transcript kept on device */
+  uint64_t nnz_multi;      /* their label entries */
+  uint32_t n_active_txps;  /* transcripts in >=1 such class */
+  uint32_t gpu_launches;   /* kernels this library launched in the last call */
+  float prepare_ms;        /* device time of sb_em_prepare (CUDA events) */
+  float run_ms;            /* device time of the iteration loop (CUDA events) */
+  float loop_kernel_ms;    /* device time of the persistent iteration kernel(s) only */
+  uint32_t loop_kernel_launches;
+} sb_em_stats;
+
+void sb_em_default_params(sb_em_params* p);
+
+typedef struct sb_em_ctx sb_em_ctx;
+
+/* One context per GPU (one process per GPU in multi-GPU runs). */
+sb_em_ctx* sb_em_create(int device);
+void sb_em_destroy(sb_em_ctx* ctx);
+
+/* Replaces `bool CollapsedEMOptimizer::optimize(ExpT&, SalmonOpts&, double tol,
+ * uint32_t maxIter)` (include/salmon/internal/inference/CollapsedEMOptimizer.hpp:22-28;
+ * src/inference/CollapsedEMOptimizer.cpp:732-1035).  Inputs per transcript are
+ * what optimize reads from Transcript: projectedCounts (:780), the effective
+ * length it would compute at :782-784, uniqueCount() (:790).  alpha_out[M]
+ * receives what :1031 stores with setSharedCount().  Host buffers in and out;
+ * this call = upload + prepare + run + download. */
+int sb_em_optimize(sb_em_ctx* ctx, const sb_eq_csr* eq, const sb_em_params* p,
+                   const double* projected_counts, const double* eff_len,
+                   const uint64_t* unique_counts, double* alpha_out,
+                   sb_em_stats* stats);
+
+/* The same call split into its stages, so that a caller (or bench.py) can keep
+ * the classes resident in HBM and time the stages separately. */
+int sb_em_upload(sb_em_ctx* ctx, const sb_eq_csr* eq,
+                 const double* projected_counts, const double* eff_len,
+                 const uint64_t* unique_counts);
+int sb_em_prepare(sb_em_ctx* ctx, const sb_em_params* p, sb_em_stats* stats);
+int sb_em_run(sb_em_ctx* ctx, sb_em_stats* stats);   /* re-runnable: restarts from the prepared state */
+int sb_em_download(sb_em_ctx* ctx, double* alpha_out, sb_em_stats* stats);
+
+/* Debug/parity taps (tests): combinedWeights (:862-870) and validity flags. */
+int sb_em_get_combined(sb_em_ctx* ctx, double* combined_out, uint8_t* valid_out);
+
+/* Tuning knobs (not part of the reference contract): kernel variant.
+ * key: "variant" (0 = multi-kernel per iteration, 1 = persistent cooperative),
+ *      "blocks_per_sm", "flush_l2_mb". */
+int sb_em_set_option(sb_em_ctx* ctx, const char* key, int64_t value);
+
+/* ---- multi-GPU: classes stay sharded per rank, alpha is all-reduced once per
+ * iteration (the only collective).  The caller provides
+ * the NCCL unique id (128 bytes, from sb_nccl_unique_id on rank 0, broadcast
+ * by whatever the host uses -- bench.py uses torch.distributed). */
+int sb_nccl_unique_id(void* out128);
+int sb_em_comm_init(sb_em_ctx* ctx, int rank, int nranks, const void* unique_id128);
+int sb_em_comm_destroy(sb_em_ctx* ctx);
+
+/* Write a buffer larger than L2 (bench hygiene between timed steps). */
+int sb_flush_l2(sb_em_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SALMON_B200_H */

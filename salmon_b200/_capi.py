@@ -1,0 +1,250 @@
+"""ctypes binding of libsalmon_b200.so (the C ABI in include/salmon_b200.h).
+
+Plumbing only: numpy arrays in, numpy arrays out.  There is no CPU fallback --
+if the shared library is missing or no CUDA device is usable, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsalmon_b200.so")
+
+SB_OK = 0
+
+
+class SalmonB200Error(RuntimeError):
+    pass
+
+
+class sb_eq_csr(C.Structure):
+    _fields_ = [
+        ("n_classes", C.c_uint64),
+        ("n_txps", C.c_uint32),
+        ("off", C.c_void_p),
+        ("tids", C.c_void_p),
+        ("weights", C.c_void_p),
+        ("counts", C.c_void_p),
+    ]
+
+
+class sb_em_params(C.Structure):
+    _fields_ = [
+        ("use_vbem", C.c_int32),
+        ("per_txp_prior", C.c_int32),
+        ("init_uniform", C.c_int32),
+        ("eq_class_mode", C.c_int32),
+        ("no_rich_eq", C.c_int32),
+        ("no_length_correction", C.c_int32),
+        ("alt_init", C.c_int32),
+        ("reserved", C.c_int32),
+        ("vb_prior", C.c_double),
+        ("tol", C.c_double),
+        ("num_required_frags", C.c_double),
+        ("min_iter", C.c_uint32),
+        ("max_iter", C.c_uint32),
+    ]
+
+
+class sb_em_stats(C.Structure):
+    _fields_ = [
+        ("iters", C.c_uint32),
+        ("converged", C.c_uint32),
+        ("max_rel_diff", C.c_double),
+        ("alpha_sum", C.c_double),
+        ("n_degenerate", C.c_uint64),
+        ("n_multi_classes", C.c_uint64),
+        ("nnz_multi", C.c_uint64),
+        ("n_active_txps", C.c_uint32),
+        ("gpu_launches", C.c_uint32),
+        ("prepare_ms", C.c_float),
+        ("run_ms", C.c_float),
+        ("loop_kernel_ms", C.c_float),
+        ("loop_kernel_launches", C.c_uint32),
+    ]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/salmon_b200.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "sb_version": (C.c_int, []),
+    "sb_last_error": (C.c_char_p, []),
+    "sb_device_count": (C.c_int, []),
+    "sb_em_default_params": (None, [C.POINTER(sb_em_params)]),
+    "sb_em_create": (_P, [C.c_int]),
+    "sb_em_destroy": (None, [_P]),
+    "sb_em_optimize": (C.c_int, [_P, C.POINTER(sb_eq_csr), C.POINTER(sb_em_params), _P, _P, _P, _P,
+                                 C.POINTER(sb_em_stats)]),
+    "sb_em_upload": (C.c_int, [_P, C.POINTER(sb_eq_csr), _P, _P, _P]),
+    "sb_em_prepare": (C.c_int, [_P, C.POINTER(sb_em_params), C.POINTER(sb_em_stats)]),
+    "sb_em_run": (C.c_int, [_P, C.POINTER(sb_em_stats)]),
+    "sb_em_download": (C.c_int, [_P, _P, C.POINTER(sb_em_stats)]),
+    "sb_em_get_combined": (C.c_int, [_P, _P, _P]),
+    "sb_em_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "sb_nccl_unique_id": (C.c_int, [_P]),
+    "sb_em_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "sb_em_comm_destroy": (C.c_int, [_P]),
+    "sb_flush_l2": (C.c_int, [_P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SalmonB200Error(
+                f"{LIB_PATH} not found: build it with `make` (or __graft_entry__.build()); "
+                "there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _check(rc, what):
+    if rc < 0:
+        raise SalmonB200Error(f"{what} failed ({rc}): {load().sb_last_error().decode()}")
+    return rc
+
+
+def default_params(**over) -> sb_em_params:
+    p = sb_em_params()
+    load().sb_em_default_params(C.byref(p))
+    for k, v in over.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+@dataclass
+class EqClasses:
+    """Host CSR view of EquivalenceClassBuilder::eqVec() (see sb_eq_csr)."""
+    n_txps: int
+    off: np.ndarray      # uint64 [C+1]
+    tids: np.ndarray     # uint32 [nnz]
+    weights: np.ndarray  # float64 [nnz]
+    counts: np.ndarray   # uint64 [C]
+
+    def __post_init__(self):
+        self.off = np.ascontiguousarray(self.off, dtype=np.uint64)
+        self.tids = np.ascontiguousarray(self.tids, dtype=np.uint32)
+        self.weights = np.ascontiguousarray(self.weights, dtype=np.float64)
+        self.counts = np.ascontiguousarray(self.counts, dtype=np.uint64)
+        assert self.off.shape[0] == self.counts.shape[0] + 1
+        assert self.tids.shape[0] == self.weights.shape[0] == int(self.off[-1])
+
+    @property
+    def n_classes(self):
+        return int(self.counts.shape[0])
+
+    @property
+    def nnz(self):
+        return int(self.tids.shape[0])
+
+    def as_struct(self) -> sb_eq_csr:
+        return sb_eq_csr(self.n_classes, self.n_txps, self.off.ctypes.data, self.tids.ctypes.data,
+                         self.weights.ctypes.data, self.counts.ctypes.data)
+
+
+class EMContext:
+    """Thin RAII wrapper around sb_em_ctx."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        self.h = self.lib.sb_em_create(device)
+        if not self.h:
+            raise SalmonB200Error("sb_em_create failed: " + self.lib.sb_last_error().decode())
+        self._keep = None
+        self.M = 0
+
+    def close(self):
+        if self.h:
+            self.lib.sb_em_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key: str, value: int):
+        _check(self.lib.sb_em_set_option(self.h, key.encode(), int(value)), "sb_em_set_option")
+
+    @staticmethod
+    def _txp_arrays(eq, projected, eff_len, unique):
+        projected = np.ascontiguousarray(projected, dtype=np.float64)
+        eff_len = np.ascontiguousarray(eff_len, dtype=np.float64)
+        unique = np.ascontiguousarray(unique, dtype=np.uint64)
+        assert projected.shape[0] == eff_len.shape[0] == unique.shape[0] == eq.n_txps
+        return projected, eff_len, unique
+
+    def optimize(self, eq: EqClasses, params: sb_em_params, projected, eff_len, unique):
+        """sb_em_optimize: host buffers in, host alpha out.  Returns (alpha, stats, ok)."""
+        projected, eff_len, unique = self._txp_arrays(eq, projected, eff_len, unique)
+        alpha = np.empty(eq.n_txps, dtype=np.float64)
+        st = sb_em_stats()
+        s = eq.as_struct()
+        rc = _check(self.lib.sb_em_optimize(self.h, C.byref(s), C.byref(params), projected.ctypes.data,
+                                            eff_len.ctypes.data, unique.ctypes.data, alpha.ctypes.data,
+                                            C.byref(st)), "sb_em_optimize")
+        self.M = eq.n_txps
+        return alpha, st, rc == 0
+
+    def upload(self, eq: EqClasses, projected, eff_len, unique):
+        projected, eff_len, unique = self._txp_arrays(eq, projected, eff_len, unique)
+        s = eq.as_struct()
+        _check(self.lib.sb_em_upload(self.h, C.byref(s), projected.ctypes.data, eff_len.ctypes.data,
+                                     unique.ctypes.data), "sb_em_upload")
+        self.M = eq.n_txps
+        self._nnz = eq.nnz
+        self._C = eq.n_classes
+
+    def prepare(self, params: sb_em_params) -> sb_em_stats:
+        st = sb_em_stats()
+        _check(self.lib.sb_em_prepare(self.h, C.byref(params), C.byref(st)), "sb_em_prepare")
+        return st
+
+    def run(self) -> sb_em_stats:
+        st = sb_em_stats()
+        _check(self.lib.sb_em_run(self.h, C.byref(st)), "sb_em_run")
+        return st
+
+    def download(self):
+        alpha = np.empty(self.M, dtype=np.float64)
+        st = sb_em_stats()
+        rc = _check(self.lib.sb_em_download(self.h, alpha.ctypes.data, C.byref(st)), "sb_em_download")
+        return alpha, st.alpha_sum, rc == 0
+
+    def get_combined(self):
+        cw = np.empty(self._nnz, dtype=np.float64)
+        valid = np.empty(self._C, dtype=np.uint8)
+        _check(self.lib.sb_em_get_combined(self.h, cw.ctypes.data, valid.ctypes.data), "sb_em_get_combined")
+        return cw, valid
+
+    def flush_l2(self):
+        _check(self.lib.sb_flush_l2(self.h), "sb_flush_l2")
+
+    def comm_init(self, rank: int, nranks: int, uid: bytes):
+        buf = C.create_string_buffer(uid, 128)
+        _check(self.lib.sb_em_comm_init(self.h, rank, nranks, buf), "sb_em_comm_init")
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(load().sb_nccl_unique_id(buf), "sb_nccl_unique_id")
+    return buf.raw

@@ -1,0 +1,49 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol that
+include/salmon_b200.h declares, and fails loudly (no CPU fallback) without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from salmon_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    inc = os.path.join(ROOT, "include")
+    for fn in os.listdir(inc):
+        if fn.endswith(".h"):
+            txt = open(os.path.join(inc, fn)).read()
+            txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+            names |= set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", txt))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    decl = declared_symbols()
+    assert len(decl) >= 15
+    for name in sorted(decl):
+        assert hasattr(lib, name), f"{name} declared in include/*.h but not exported"
+    # and the Python binding covers them all
+    assert decl <= set(_capi.SYMBOLS), sorted(decl - set(_capi.SYMBOLS))
+
+
+def test_version_and_params():
+    lib = _capi.load()
+    assert lib.sb_version() >= 100
+    p = _capi.default_params()
+    assert p.use_vbem == 1 and p.per_txp_prior == 1
+    assert p.vb_prior == 1e-2 and p.tol == 0.01 and p.min_iter == 100 and p.max_iter == 10000
+    assert p.num_required_frags == 5e7
+
+
+def test_no_cpu_fallback_without_gpu():
+    lib = _capi.load()
+    if lib.sb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_capi.SalmonB200Error, match="no CUDA device"):
+        _capi.EMContext(0)

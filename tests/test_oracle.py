@@ -1,0 +1,142 @@
+"""CPU tests of the oracle (oracle/em_oracle.c) against golden vectors and an
+independent pure-Python restatement.  No GPU needed."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from salmon_b200._capi import EqClasses, sb_em_params
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def mkparams(**kw):
+    d = dict(use_vbem=1, per_txp_prior=1, init_uniform=0, eq_class_mode=0, no_rich_eq=0,
+             no_length_correction=0, alt_init=0, vb_prior=1e-2, tol=0.01, num_required_frags=5e7,
+             min_iter=100, max_iter=10000)
+    d.update(kw)
+    return d
+
+
+def random_problem(rng, C, M, max_label=6, zero_frac=0.0):
+    sizes = rng.integers(1, max_label + 1, size=C)
+    sizes = np.minimum(sizes, M)
+    off = np.concatenate(([0], np.cumsum(sizes))).astype(np.uint64)
+    tids = np.concatenate([np.sort(rng.choice(M, size=s, replace=False)) for s in sizes]).astype(np.uint32)
+    w = rng.random(int(off[-1])) + 0.01
+    if zero_frac:
+        w[rng.random(w.shape[0]) < zero_frac] = 0.0
+    s = np.add.reduceat(w, off[:-1].astype(np.int64))
+    s[s == 0] = 1.0
+    w = w / np.repeat(s, sizes)
+    counts = rng.integers(1, 50, size=C).astype(np.uint64)
+    eq = EqClasses(M, off, tids, w, counts)
+    eff = rng.uniform(0.5, 3000.0, size=M)
+    cnt_e = np.repeat(counts.astype(np.float64), sizes)
+    proj = np.bincount(tids, weights=cnt_e * w, minlength=M)
+    uniq = np.bincount(tids[np.repeat(sizes == 1, sizes)], weights=counts[sizes == 1].astype(float),
+                       minlength=M).astype(np.uint64)
+    return eq, proj, eff, uniq
+
+
+def as_classes(eq):
+    out = []
+    for c in range(eq.n_classes):
+        b, e = int(eq.off[c]), int(eq.off[c + 1])
+        out.append((eq.tids[b:e].tolist(), eq.weights[b:e].tolist(), int(eq.counts[c])))
+    return out
+
+
+def test_digamma_golden(oracle):
+    import mpmath
+    mpmath.mp.dps = 40
+    rows = json.load(open(os.path.join(HERE, "golden", "digamma_golden.json")))["rows"]
+    assert len(rows) > 400
+    for r in rows:
+        x = float.fromhex(r["x"])
+        want = mpmath.mpf(r["digamma"])
+        got = oracle.digamma(x)
+        if abs(x - 1.4616321449683623) < 0.05:   # near the root: absolute
+            assert abs(got - want) < 4e-16
+        else:
+            assert abs((got - want) / want) < 2e-15, (x, got, want)
+
+
+def test_philox_kat(oracle):
+    # Known-answer vectors of Philox-4x32-10 (Random123 kat_vectors)
+    assert oracle.philox((0, 0, 0, 0), (0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = 0xffffffff
+    assert oracle.philox((f, f, f, f), (f, f)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert oracle.philox((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_tiny_hand_case(oracle):
+    # Two transcripts, one ambiguous class with equal weights + one unique class.
+    # EM fixed point: alpha0 = 10 + x, alpha1 = 10 - x ... checked against closed form:
+    # classes: {0}:count 10 ; {0,1}: count 10, weights .5/.5, equal effLen.
+    # plain EM: a0' = 10 + 10*a0/(a0+a1), a1' = 10*a1/(a0+a1)  -> converges to (20, 0).
+    eq = EqClasses(2, np.array([0, 1, 3]), np.array([0, 0, 1]), np.array([1.0, 0.5, 0.5]), np.array([10, 10]))
+    p = mkparams(use_vbem=0, min_iter=2000, max_iter=2000)
+    a, st = oracle.em_optimize(eq, np.array([15.0, 5.0]), np.array([100.0, 100.0]),
+                               np.array([10, 0], dtype=np.uint64), p)
+    assert st.iters == 2000 and st.ok == 1
+    assert abs(a.sum() - 20.0) < 1e-9
+    assert a[0] > 19.9 and a[1] < 0.1
+    # one-step closed form (use min_iter=max_iter=1): includes the +1.0 the reference's
+    # EM path carries on its first iteration (alphasPrime starts at 1.0, :812/:821).
+    p1 = mkparams(use_vbem=0, min_iter=1, max_iter=1)
+    a1, _ = oracle.em_optimize(eq, np.array([15.0, 5.0]), np.array([100.0, 100.0]),
+                               np.array([10, 0], dtype=np.uint64), p1)
+    tw = 20.0
+    frac = min(0.999, tw / 5e7)
+    a0 = [15.0 * frac + (tw / 2) * (1 - frac), 5.0 * frac + (tw / 2) * (1 - frac)]
+    want0 = 1.0 + 10 + 10 * a0[0] / (a0[0] + a0[1])
+    want1 = 1.0 + 10 * a0[1] / (a0[0] + a0[1])
+    assert abs(a1[0] - want0) < 1e-12 and abs(a1[1] - want1) < 1e-12
+
+
+@pytest.mark.parametrize("kw", [
+    dict(), dict(use_vbem=0), dict(per_txp_prior=0, vb_prior=1e-5), dict(init_uniform=1),
+    dict(eq_class_mode=1, init_uniform=1), dict(no_rich_eq=1), dict(alt_init=1),
+])
+def test_oracle_vs_python_restatement(oracle, kw):
+    import py_ref
+    rng = np.random.default_rng(5)
+    eq, proj, eff, uniq = random_problem(rng, C=60, M=25, zero_frac=0.05)
+    p = mkparams(min_iter=30, max_iter=200, **kw)
+    a, st, cw, valid = oracle.em_optimize(eq, proj, eff, uniq, p, want_combined=True)
+    pk = {k: p[k] for k in ("use_vbem", "per_txp_prior", "init_uniform", "eq_class_mode", "no_rich_eq",
+                            "alt_init", "vb_prior", "tol", "num_required_frags", "min_iter", "max_iter")}
+    ra, rit, rconv, rmax, rcomb, rvalid = py_ref.optimize(as_classes(eq), eq.n_txps, proj, eff, uniq, **pk)
+    assert st.iters == rit
+    assert bool(st.converged) == rconv
+    assert [bool(v) for v in valid] == rvalid
+    np.testing.assert_allclose(cw, np.concatenate(rcomb), rtol=1e-15, atol=0)
+    np.testing.assert_allclose(a, np.array(ra), rtol=1e-10, atol=1e-12)
+    assert abs(st.max_rel_diff - rmax) <= 1e-9 * max(1.0, abs(rmax))
+
+
+def test_mass_conservation_and_mt(oracle):
+    rng = np.random.default_rng(11)
+    eq, proj, eff, uniq = random_problem(rng, C=5000, M=800, max_label=12)
+    p = mkparams(min_iter=50, max_iter=50)
+    a, st = oracle.em_optimize(eq, proj, eff, uniq, p)
+    # every valid class hands out exactly its count
+    assert st.n_degenerate == 0
+    assert abs(a.sum() - float(eq.counts.sum())) / float(eq.counts.sum()) < 1e-9
+    a2, st2 = oracle.em_optimize(eq, proj, eff, uniq, p, mt=True, n_threads=4)
+    np.testing.assert_allclose(a2, a, rtol=1e-9, atol=1e-9)
+    t = oracle.tpm(a, eff)
+    assert abs(t.sum() - 1e6) < 1e-3
+
+
+def test_degenerate_classes_are_dropped(oracle):
+    # a class whose only members have zero combined weight is marked degenerate
+    eq = EqClasses(3, np.array([0, 2, 3]), np.array([0, 1, 2]), np.array([0.0, 0.0, 1.0]), np.array([7, 5]))
+    p = mkparams(min_iter=5, max_iter=5)
+    a, st = oracle.em_optimize(eq, np.array([1.0, 1.0, 5.0]), np.array([100.0, 100.0, 100.0]),
+                               np.zeros(3, dtype=np.uint64), p)
+    assert st.n_degenerate == 1
+    assert a[2] == 5.0 and a[0] == 0.0 and a[1] == 0.0

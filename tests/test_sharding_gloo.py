@@ -1,0 +1,59 @@
+"""world_size-2 gloo test (CPU) of the N>1 host logic: classes shard round-robin
+across ranks, each rank produces its partial alpha' for the same alpha, and the
+all-reduced sum equals the unsharded update."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_lib as O
+    from salmon_b200.synth import shard_classes, synth_eq
+    eq, proj, eff, uniq = synth_eq(seed=3, C=4000, M=900, total_count=100000)
+    sh = shard_classes(eq, rank, world)
+    # uid-style broadcast plumbing: rank 0 owns a 128-byte token, everyone must agree
+    tok = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        tok = torch.arange(128, dtype=torch.uint8)
+    dist.broadcast(tok, 0)
+    assert tok.tolist() == list(range(128))
+    rng = np.random.default_rng(0)
+    alpha = rng.random(eq.n_txps) * 10
+    prior = np.full(eq.n_txps, 1e-2)
+    sizes = (sh.off[1:] - sh.off[:-1]).astype(np.int64)
+    cw = sh.weights  # already normalised per class
+    valid = np.ones(sh.n_classes, dtype=np.uint8)
+    # EM step on the shard (theta = alpha): partial alpha'
+    part, _ = O.em_step(sh, cw, valid, prior, alpha, vbem=0)
+    t = torch.from_numpy(part.copy())
+    dist.all_reduce(t)
+    full, _ = O.em_step(eq, eq.weights, np.ones(eq.n_classes, dtype=np.uint8), prior, alpha, vbem=0)
+    ok = np.allclose(t.numpy(), full, rtol=1e-12, atol=1e-12)
+    cnt = torch.tensor([float(sh.counts.sum())], dtype=torch.float64)
+    dist.all_reduce(cnt)
+    ok = ok and cnt.item() == float(eq.counts.sum())
+    q.put((rank, bool(ok), int(sizes.sum())))
+    dist.destroy_process_group()
+
+
+def test_sharded_update_equals_unsharded():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+    assert all(ok for _, ok, _ in res), res
