@@ -27,31 +27,41 @@
 #include "common.cuh"
 #include "em_internal.h"
 
-namespace cg = cooperative_groups;
+#include "em_kernels.cuh"
 
 namespace sb {
 
 // ---------------------------------------------------------------------------
-// constants
+// kernel configurations: ring chunk (columns) x resident blocks per SM
 // ---------------------------------------------------------------------------
-constexpr int TILE = 2048;            // entries per tile window
-constexpr int LMAX = 256;             // rows longer than this take the block path
-constexpr int CAP = TILE + LMAX + 8;  // shared-memory entries per stage
-constexpr int STAGES = 2;
-constexpr int THREADS = 256;
-constexpr double DIGAMMA_MIN = 1e-10;     // CollapsedEMOptimizer.cpp:43
-constexpr double MIN_EQ_W = DBL_MIN;      // :40
-constexpr double ALPHA_CHECK_CUTOFF = 1e-2;  // :884
-
-struct SmemLayout {
-  // per stage: idx[CAP] u32 then w[CAP] f64 ; then barriers + scratch
-  static constexpr size_t idx_bytes = size_t(CAP) * 4;
-  static constexpr size_t w_bytes = size_t(CAP) * 8;
-  static constexpr size_t stage_bytes = idx_bytes + w_bytes;
-  static constexpr size_t bars_off = stage_bytes * STAGES;
-  static constexpr size_t scratch_off = bars_off + 64;
-  static constexpr size_t total = scratch_off + 64 * 8;
+struct KernelSet {
+  const char* name;
+  size_t smem;
+  const void* persistent;
+  void (*p1)(EmArgs);
+  void (*p2)(EmArgs, uint32_t);
+  void (*p2_partial)(EmArgs);
 };
+template <int CH, int MINB>
+static KernelSet make_set(const char* name) {
+  KernelSet k;
+  k.name = name;
+  k.smem = em_smem<CH>();
+  k.persistent = (const void*)k_em_persistent<CH, MINB>;
+  k.p1 = k_em_p1<CH, MINB>;
+  k.p2 = k_em_p2<CH, MINB>;
+  k.p2_partial = k_em_p2_partial<CH, MINB>;
+  return k;
+}
+constexpr int N_KERNEL_SETS = 6;
+static const KernelSet& kernel_set(int cfg) {
+  static const KernelSet sets[N_KERNEL_SETS] = {
+      make_set<8, 3>("ch8b3"),  make_set<16, 2>("ch16b2"), make_set<8, 4>("ch8b4"),
+      make_set<4, 4>("ch4b4"),  make_set<4, 3>("ch4b3"),   make_set<8, 2>("ch8b2"),
+  };
+  if (cfg < 0 || cfg >= N_KERNEL_SETS) cfg = 0;
+  return sets[cfg];
+}
 
 // ---------------------------------------------------------------------------
 // prepare kernels
@@ -83,14 +93,15 @@ __global__ void k_txp_init(uint32_t M, const double* __restrict__ projected,
 }
 
 // :830-873 combined weights, :330-394 degenerate marking, singleton folding.
-// One thread per class (one-time work).
-__global__ void k_class_combine(uint64_t C, const uint64_t* __restrict__ off,
+// One thread per class (one-time work).  sortkey = first transcript of a kept class.
+__global__ void k_class_combine(uint64_t C, uint32_t M, const uint64_t* __restrict__ off,
                                 const uint32_t* __restrict__ tids,
                                 const double* __restrict__ aux,
                                 const uint64_t* __restrict__ counts,
                                 const double* __restrict__ effLens,
                                 const double* __restrict__ alpha0, sb_em_params p,
                                 double* __restrict__ cw, uint64_t* __restrict__ packed,
+                                uint32_t* __restrict__ sortkey,
                                 double* __restrict__ single, uint8_t* __restrict__ valid,
                                 unsigned long long* __restrict__ n_degenerate) {
   uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -119,29 +130,52 @@ __global__ void k_class_combine(uint64_t C, const uint64_t* __restrict__ off,
   valid[c] = ok ? 1 : 0;
   uint64_t len = e - b;
   uint64_t pk = 0;
+  uint32_t key = M;  // dropped classes sort last
   if (!ok) {
     atomicAdd(n_degenerate, 1ull);
   } else if (len == 1) {
     atomicAdd(&single[tids[b]], count);  // integer-valued: order independent
   } else if (len > 1) {
     pk = (1ull << 32) | len;             // (class count, entry count)
+    key = tids[b];
   }
   packed[c] = pk;
+  sortkey[c] = key;
 }
 
-// Compact valid multi-transcript classes; histogram of transcript occurrences.
-__global__ void k_compact(uint64_t C, const uint64_t* __restrict__ off,
+// second-level key: (locality group, length bucket); dropped rows last
+__global__ void k_bucket_key(uint64_t n, const uint32_t* __restrict__ order,
+                             const uint64_t* __restrict__ packed, uint32_t* __restrict__ key,
+                             uint32_t* __restrict__ val) {
+  uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const uint64_t pk = packed[order ? order[p] : p];
+  const uint32_t len = (uint32_t)(pk & 0xffffffffu);
+  key[p] = pk ? ((uint32_t)(p / SELL_GROUP) << 9) | min(len, 511u) : 0xffffffffu;
+  val[p] = order ? order[p] : (uint32_t)p;
+}
+
+__global__ void k_gather_u64(uint64_t n, const uint32_t* __restrict__ order,
+                             const uint64_t* __restrict__ src, uint64_t* __restrict__ dst) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[order[i]];
+}
+
+// Compact the kept classes in their final order; histogram of transcript occurrences.
+__global__ void k_compact(uint64_t C, const uint32_t* __restrict__ order,
+                          const uint64_t* __restrict__ off,
                           const uint32_t* __restrict__ tids, const double* __restrict__ cw,
                           const uint64_t* __restrict__ counts,
-                          const uint64_t* __restrict__ packed,
+                          const uint64_t* __restrict__ packed_sorted,
                           const uint64_t* __restrict__ packed_scan,
                           uint32_t* __restrict__ m_off, uint32_t* __restrict__ m_idx,
                           double* __restrict__ m_w, double* __restrict__ m_cnt,
                           uint32_t* __restrict__ ent_cls, uint32_t* __restrict__ tcnt) {
-  uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  if (packed[c] == 0) return;
-  const uint64_t s = packed_scan[c];
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C) return;
+  if (packed_sorted[i] == 0) return;
+  const uint64_t c = order[i];
+  const uint64_t s = packed_scan[i];
   const uint32_t cid = (uint32_t)(s >> 32);
   uint32_t o = (uint32_t)(s & 0xffffffffu);
   m_off[cid] = o;
@@ -160,27 +194,42 @@ __global__ void k_iota(uint32_t n, uint32_t* __restrict__ v) {
   if (i < n) v[i] = i;
 }
 
-// per transcript: packed (active flag, occurrence count) for the row scan
+// per transcript: packed (active flag, occurrence count) for the rank scan
 __global__ void k_row_pack(uint32_t M, const uint32_t* __restrict__ tcnt,
                            uint64_t* __restrict__ packed) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < M) packed[i] = tcnt[i] ? ((1ull << 32) | tcnt[i]) : 0ull;
 }
-__global__ void k_row_fill(uint32_t M, const uint32_t* __restrict__ tcnt,
-                           const uint64_t* __restrict__ scan, uint32_t* __restrict__ t_off,
-                           uint32_t* __restrict__ row_tid, uint32_t* __restrict__ tid_row) {
+// rank space (active transcripts in ascending id): CSR offsets + id of each rank
+__global__ void k_rank_fill(uint32_t M, const uint32_t* __restrict__ tcnt,
+                            const uint64_t* __restrict__ scan, uint32_t* __restrict__ t_off,
+                            uint32_t* __restrict__ rank_tid, uint64_t* __restrict__ rank_packed) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
   if (tcnt[i]) {
-    uint32_t row = (uint32_t)(scan[i] >> 32);
-    t_off[row] = (uint32_t)(scan[i] & 0xffffffffu);
-    row_tid[row] = i;
-    tid_row[i] = row;
-  } else {
-    tid_row[i] = 0xffffffffu;
+    uint32_t rk = (uint32_t)(scan[i] >> 32);
+    t_off[rk] = (uint32_t)(scan[i] & 0xffffffffu);
+    rank_tid[rk] = i;
+    rank_packed[rk] = (1ull << 32) | tcnt[i];
   }
 }
-// transcript-major entries from the stable sort permutation
+// final rows: row r holds rank rowperm[r]; state vectors gathered into row space
+__global__ void k_row_fill(uint32_t R, const uint32_t* __restrict__ rowperm,
+                           const uint32_t* __restrict__ rank_tid, const double* __restrict__ prior,
+                           const double* __restrict__ base, const double* __restrict__ alpha0,
+                           uint32_t* __restrict__ row_tid, uint32_t* __restrict__ tid_row,
+                           double* __restrict__ r_prior, double* __restrict__ r_base,
+                           double* __restrict__ r_alpha0) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const uint32_t t = rank_tid[rowperm[r]];
+  row_tid[r] = t;
+  tid_row[t] = r;
+  r_prior[r] = prior[t];
+  r_base[r] = base[t];
+  r_alpha0[r] = alpha0[t];
+}
+// transcript-major CSR (rank order) from the stable sort permutation
 __global__ void k_gather_csc(uint32_t nnz, const uint32_t* __restrict__ perm,
                              const uint32_t* __restrict__ ent_cls,
                              const double* __restrict__ m_w, uint32_t* __restrict__ t_idx,
@@ -191,48 +240,90 @@ __global__ void k_gather_csc(uint32_t nnz, const uint32_t* __restrict__ perm,
   t_idx[k] = ent_cls[j];
   t_w[k] = m_w[j];
 }
-
-// tile k owns the rows whose first entry lies in [k*TILE, (k+1)*TILE).
-// desc = {row0, row1, ent0, ent1}: rows [row0,row1) with entries [ent0,ent1);
-// rows longer than LMAX are skipped by the tile pass (block path), and if the
-// last row of the tile is long the span stops at its first entry.
-__global__ void k_tiles(uint32_t n_rows, const uint32_t* __restrict__ off, uint32_t nnz,
-                        uint32_t n_tiles, uint4* __restrict__ desc) {
+__global__ void k_remap(uint32_t n, const uint32_t* __restrict__ src,
+                        const uint32_t* __restrict__ map, uint32_t* __restrict__ dst) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_tiles) return;
-  auto lower = [&](uint32_t target) {
-    uint32_t lo = 0, hi = n_rows;  // first row with off[row] >= target
-    while (lo < hi) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (off[mid] >= target) hi = mid; else lo = mid + 1;
-    }
-    return lo;
-  };
-  uint32_t r0 = lower(k * (uint32_t)TILE);
-  uint32_t r1 = (k + 1 == n_tiles) ? n_rows : lower((k + 1) * (uint32_t)TILE);
-  uint32_t e0 = (r0 < n_rows) ? off[r0] : nnz;
-  uint32_t e1 = off[r1];
-  if (r1 > r0) {
-    uint32_t lastlen = off[r1] - off[r1 - 1];
-    if (lastlen > (uint32_t)LMAX) e1 = off[r1 - 1];
-  } else {
-    e1 = e0;
-  }
-  desc[k] = make_uint4(r0, r1, e0, e1);
+  if (k < n) dst[k] = map[src[k]];
 }
-__global__ void k_long_rows(uint32_t n_rows, const uint32_t* __restrict__ off,
-                            uint32_t* __restrict__ list, uint32_t* __restrict__ n_long,
-                            uint32_t cap) {
-  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_rows) return;
-  if (off[r + 1] - off[r] > (uint32_t)LMAX) {
-    uint32_t pos = atomicAdd(n_long, 1u);
-    if (pos < cap) list[pos] = r;
+
+// ---- CSR -> SELL-32 -------------------------------------------------------------
+// one warp per slice: row lengths, slice width (= max non-long length)
+__global__ void k_sell_widths(uint32_t n_rows, uint32_t n_slices, const uint32_t* __restrict__ rowperm,
+                              const uint32_t* __restrict__ csr_off, uint16_t* __restrict__ len16,
+                              uint32_t* __restrict__ width, uint32_t* __restrict__ n_long) {
+  const uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= n_slices) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t row = s * 32 + lane;
+  uint32_t len = 0;
+  if (row < n_rows) {
+    const uint32_t cr = rowperm ? rowperm[row] : row;
+    len = csr_off[cr + 1] - csr_off[cr];
+    if (len > (uint32_t)LMAX) {
+      len16[row] = LEN_LONG;
+      atomicAdd(n_long, 1u);
+      len = 0;
+    } else {
+      len16[row] = (uint16_t)len;
+    }
   }
+  for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+  if (lane == 0) width[s] = len;
+}
+__global__ void k_sell_fill(uint32_t n_rows, uint32_t n_slices, const uint32_t* __restrict__ rowperm,
+                            const uint32_t* __restrict__ csr_off, const uint32_t* __restrict__ csr_idx,
+                            const double* __restrict__ csr_w, const uint32_t* __restrict__ slice_ptr,
+                            const uint16_t* __restrict__ len16, uint32_t pad_idx,
+                            uint32_t* __restrict__ s_idx, double* __restrict__ s_w,
+                            uint32_t* __restrict__ long_rows, uint32_t* __restrict__ long_cursor) {
+  const uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= n_slices) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t row = s * 32 + lane;
+  const size_t base = (size_t)slice_ptr[s] * 32 + lane;
+  const uint32_t width = slice_ptr[s + 1] - slice_ptr[s];
+  uint32_t n = 0;
+  if (row < n_rows) {
+    const uint32_t cr = rowperm ? rowperm[row] : row;
+    const uint32_t b = csr_off[cr], e = csr_off[cr + 1];
+    if (len16[row] == LEN_LONG) {
+      const uint32_t pos = atomicAdd(long_cursor, 1u);
+      long_rows[3 * pos] = row;
+      long_rows[3 * pos + 1] = b;
+      long_rows[3 * pos + 2] = e;
+    } else {
+      n = e - b;
+      for (uint32_t j = 0; j < n; ++j) {
+        s_idx[base + (size_t)j * 32] = csr_idx[b + j];
+        s_w[base + (size_t)j * 32] = csr_w[b + j];
+      }
+    }
+  }
+  // padding: weight 0 and a gather index that always reads 0.0 (slot one past the end)
+  for (uint32_t j = n; j < width; ++j) {
+    s_idx[base + (size_t)j * 32] = pad_idx;
+    s_w[base + (size_t)j * 32] = 0.0;
+  }
+}
+// contiguous, work-balanced slice ranges per warp: work(slice) = width + overhead
+__global__ void k_warp_ranges(uint32_t n_slices, const uint32_t* __restrict__ slice_ptr,
+                              uint32_t overhead, uint32_t n_warps, uint32_t* __restrict__ warp_begin) {
+  const uint32_t wid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wid > n_warps) return;
+  if (wid == n_warps || n_slices == 0) { warp_begin[wid] = n_slices; return; }
+  const uint64_t total = (uint64_t)slice_ptr[n_slices] + (uint64_t)overhead * n_slices;
+  const uint64_t target = total * wid / n_warps;
+  uint32_t lo = 0, hi = n_slices;  // first slice whose cumulative work (before it) >= target
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    uint64_t wk = (uint64_t)slice_ptr[mid] + (uint64_t)overhead * mid;
+    if (wk >= target) hi = mid; else lo = mid + 1;
+  }
+  warp_begin[wid] = lo;
 }
 
 // deterministic single-block reduction: out[0] = sum_i f(i)
-// mode 0: alpha[i]+prior[i] over all i ; mode 1: base[i]+prior[i] over inactive i
+// mode 0: a[i]+b[i] over all i ; mode 1: a[i]+b[i] over inactive i
 __global__ void k_sum1(uint32_t M, const double* __restrict__ a, const double* __restrict__ b,
                        const uint32_t* __restrict__ tid_row, int mode, double* __restrict__ out) {
   __shared__ double scratch[32];
@@ -245,12 +336,12 @@ __global__ void k_sum1(uint32_t M, const double* __restrict__ a, const double* _
   if (threadIdx.x == 0) out[0] = acc;
 }
 
-// theta for iteration 0 (exact logNorm) + bookkeeping for inactive transcripts.
-__global__ void k_theta0(uint32_t M, int vbem, const double* __restrict__ alpha0,
+// iteration-0 state (exact logNorm), in whatever index space the caller iterates in
+__global__ void k_theta0(uint32_t n, int vbem, const double* __restrict__ alpha0,
                          const double* __restrict__ prior, const double* __restrict__ sum0,
                          double* __restrict__ alpha, double* __restrict__ theta) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M) return;
+  if (i >= n) return;
   double a = alpha0[i];
   alpha[i] = a;
   if (vbem) {
@@ -262,290 +353,22 @@ __global__ void k_theta0(uint32_t M, int vbem, const double* __restrict__ alpha0
   }
 }
 
-// inactive transcripts (in no valid multi-transcript class): alpha after >=1
-// iteration is base (+1.0 after exactly one EM iteration, see em_internal.h).
-__global__ void k_finalize_inactive(uint32_t M, const uint32_t* __restrict__ tid_row,
-                                    const double* __restrict__ base, double bias,
-                                    double* __restrict__ alpha) {
+// row space -> transcript space.  Inactive transcripts (in no kept multi-transcript
+// class) hold base (+1.0 after exactly one EM iteration: alphasPrime starts at 1.0).
+__global__ void k_finalize(uint32_t M, const uint32_t* __restrict__ tid_row,
+                           const double* __restrict__ base, double bias,
+                           const double* __restrict__ r_alpha, double* __restrict__ alpha) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
-  if (tid_row[i] == 0xffffffffu) alpha[i] = base[i] + bias;
+  uint32_t r = tid_row[i];
+  alpha[i] = (r == 0xffffffffu) ? base[i] + bias : r_alpha[r];
 }
 
-// ---------------------------------------------------------------------------
-// iteration kernels
-// ---------------------------------------------------------------------------
-struct Block {
-  uint32_t* s_idx[STAGES];
-  double* s_w[STAGES];
-  uint64_t* bars;
-  double* scratch;
-  uint32_t uses[STAGES];
-};
-
-__device__ __forceinline__ void block_setup(Block& B, unsigned char* smem) {
-#pragma unroll
-  for (int s = 0; s < STAGES; ++s) {
-    B.s_w[s] = reinterpret_cast<double*>(smem + s * SmemLayout::stage_bytes);
-    B.s_idx[s] = reinterpret_cast<uint32_t*>(smem + s * SmemLayout::stage_bytes + SmemLayout::w_bytes);
-    B.uses[s] = 0;
-  }
-  B.bars = reinterpret_cast<uint64_t*>(smem + SmemLayout::bars_off);
-  B.scratch = reinterpret_cast<double*>(smem + SmemLayout::scratch_off);
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) mbar_init(&B.bars[s], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-}
-
-// issue the bulk loads of one tile into stage s (one elected thread)
-__device__ __forceinline__ void tile_issue(Block& B, int s, const uint4 d,
-                                           const uint32_t* __restrict__ idx,
-                                           const double* __restrict__ w) {
-  const uint32_t e0a = d.z & ~3u;
-  const uint32_t e1a = (d.w + 3u) & ~3u;
-  const uint32_t n = e1a - e0a;
-  if (n == 0) return;
-  fence_proxy_async();  // generic-proxy writes to this stage happen-before the async writes
-  mbar_arrive_expect_tx(&B.bars[s], n * 12u);
-  bulk_g2s(B.s_w[s], w + e0a, n * 8u, &B.bars[s]);
-  bulk_g2s(B.s_idx[s], idx + e0a, n * 4u, &B.bars[s]);
-}
-
-// PHASE 1: rows = classes, gather theta, out scale[row] = cnt[row]/denom
-// PHASE 2: rows = active transcripts, gather scale, epilogue per transcript
-struct P2Acc {
-  double sum;     // sum of (alpha' + prior) over my rows
-  double maxrel;  // max rel diff over my rows
-};
-
-struct EmArgs {
-  // class-major
-  const uint32_t* c_off; const uint32_t* c_idx; const double* c_w; const uint4* c_tiles;
-  const uint32_t* c_long; const double* c_cnt; double* scale;
-  uint32_t c_ntiles, c_nlong, c_nrows;
-  // transcript-major
-  const uint32_t* t_off; const uint32_t* t_idx; const double* t_w; const uint4* t_tiles;
-  const uint32_t* t_long; const uint32_t* row_tid;
-  uint32_t t_ntiles, t_nlong, t_nrows;
-  // per transcript state
-  double* alpha; double* theta; const double* prior; const double* base;
-  double* part_out;   // multi-GPU: partial sums per transcript row (no epilogue)
-  // reductions
-  double* sum_partial;            // [2][grid]
-  unsigned long long* maxrel;     // [2] (bit pattern of a non-negative double)
-  double inactive_sum; double sum0;
-  double tol;
-  uint32_t min_iter, max_iter;
-  int vbem;
-  uint32_t* out;                  // [0]=iters [1]=converged ; maxrel of last iter in maxrel
-};
-
-template <int PHASE>
-__device__ __forceinline__ void row_epilogue(const EmArgs& A, uint32_t row, double acc,
-                                             double logNorm, double bias, P2Acc& pa) {
-  if (PHASE == 1) {
-    A.scale[row] = (acc <= MIN_EQ_W) ? 0.0 : A.c_cnt[row] / acc;
-  } else if (PHASE == 3) {
-    // multi-GPU: this rank's share of alpha'_t; the update runs after the all-reduce
-    const uint32_t t = A.row_tid[row];
-    const double th = A.theta[t];
-    double na = A.base[t];
-    if (th > 0.0) na += th * acc;
-    A.part_out[t] = na;
-  } else {
-    const uint32_t t = A.row_tid[row];
-    const double th = A.theta[t];
-    const double pr = A.prior[t];
-    double na = A.base[t] + bias;
-    if (th > 0.0) na += th * acc;
-    const double old = A.alpha[t];
-    if (na > ALPHA_CHECK_CUTOFF) {
-      double rel = fabs(old - na) / na;
-      pa.maxrel = fmax(pa.maxrel, rel);
-    }
-    A.alpha[t] = na;
-    const double ap = na + pr;
-    pa.sum += ap;
-    if (A.vbem) {
-      A.theta[t] = (ap > DIGAMMA_MIN) ? exp(digamma_pos(ap) - logNorm) : 0.0;
-    } else {
-      A.theta[t] = na;
-    }
-  }
-}
-
-template <int PHASE>
-__device__ __forceinline__ void run_phase(const EmArgs& A, Block& B, uint32_t bid, uint32_t nblk,
-                                          double logNorm, double bias, P2Acc& pa) {
-  const uint32_t* __restrict__ off = (PHASE == 1) ? A.c_off : A.t_off;
-  const uint32_t* __restrict__ idx = (PHASE == 1) ? A.c_idx : A.t_idx;
-  const double* __restrict__ w = (PHASE == 1) ? A.c_w : A.t_w;
-  const uint4* __restrict__ tiles = (PHASE == 1) ? A.c_tiles : A.t_tiles;
-  // theta / scale are rewritten by other blocks inside the persistent kernel: plain
-  // (coherent) loads only -- never ld.global.nc / __restrict__ for these two.
-  const double* gsrc = (PHASE == 1) ? A.theta : A.scale;
-  const uint32_t ntiles = (PHASE == 1) ? A.c_ntiles : A.t_ntiles;
-  const uint32_t nlong = (PHASE == 1) ? A.c_nlong : A.t_nlong;
-  const uint32_t* __restrict__ longs = (PHASE == 1) ? A.c_long : A.t_long;
-  const bool em_nan_guard = (PHASE == 1) && !A.vbem;
-  (void)A.c_nrows;
-
-  const uint32_t n_my = (bid < ntiles) ? (ntiles - bid + nblk - 1) / nblk : 0;
-  // prologue: prefetch STAGES-1 tiles
-  if (threadIdx.x == 0) {
-    for (uint32_t i = 0; i < (uint32_t)(STAGES - 1) && i < n_my; ++i)
-      tile_issue(B, i % STAGES, tiles[bid + i * nblk], idx, w);
-  }
-  for (uint32_t i = 0; i < n_my; ++i) {
-    const int s = i % STAGES;
-    const uint4 d = tiles[bid + i * nblk];
-    if (threadIdx.x == 0 && i + STAGES - 1 < n_my)
-      tile_issue(B, (i + STAGES - 1) % STAGES, tiles[bid + (i + STAGES - 1) * nblk], idx, w);
-    const uint32_t e0a = d.z & ~3u;
-    const uint32_t n = ((d.w + 3u) & ~3u) - e0a;
-    if (n) {
-      mbar_wait(&B.bars[s], B.uses[s] & 1u);
-      ++B.uses[s];
-      uint32_t* sidx = B.s_idx[s];
-      double* sw = B.s_w[s];
-      // (1) gather * weight, in place
-      for (uint32_t k = threadIdx.x; k < n; k += THREADS) {
-        const double g = gsrc[sidx[k]];
-        double v = g * sw[k];
-        if (em_nan_guard && isnan(v)) v = 0.0;
-        sw[k] = v;
-      }
-      __syncthreads();
-      // (2) one thread per row: sequential sum in label order
-      for (uint32_t r = d.x + threadIdx.x; r < d.y; r += THREADS) {
-        const uint32_t b = off[r], e = off[r + 1];
-        if (e - b > (uint32_t)LMAX) continue;  // block path
-        double acc = 0.0;
-        for (uint32_t k = b - e0a; k < e - e0a; ++k) acc += sw[k];
-        row_epilogue<PHASE>(A, r, acc, logNorm, bias, pa);
-      }
-      __syncthreads();  // stage free for the next bulk load
-    } else {
-      // tile without short rows: only (possibly) empty span
-    }
-  }
-  // long rows: whole block per row, fixed-order tree reduction
-  for (uint32_t li = bid; li < nlong; li += nblk) {
-    const uint32_t r = longs[li];
-    const uint32_t b = off[r], e = off[r + 1];
-    double acc = 0.0;
-    for (uint32_t k = b + threadIdx.x; k < e; k += THREADS) {
-      double v = gsrc[idx[k]] * w[k];
-      if (em_nan_guard && isnan(v)) v = 0.0;
-      acc += v;
-    }
-    acc = block_reduce<false>(acc, B.scratch);
-    if (threadIdx.x == 0) row_epilogue<PHASE>(A, r, acc, logNorm, bias, pa);
-    __syncthreads();
-  }
-}
-
-// alphaSum of the iteration input, from the per-block partials of the previous P2
-__device__ __forceinline__ double sum_partials(const double* part, uint32_t n, double extra,
-                                               double* scratch) {
-  double acc = 0.0;
-  for (uint32_t i = threadIdx.x; i < n; i += THREADS) acc += part[i];
-  acc = block_reduce<false>(acc, scratch);
-  return acc + extra;
-}
-
-__global__ void __launch_bounds__(THREADS)
-k_em_persistent(const __grid_constant__ EmArgs A) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  cg::grid_group grid = cg::this_grid();
-  Block B;
-  block_setup(B, smem);
-  const uint32_t bid = blockIdx.x, nblk = gridDim.x;
-
-  uint32_t it = 0;
-  bool converged = false;
-  double logNorm = A.vbem ? digamma_pos(A.sum0) : 0.0;
-  while (it < A.min_iter || (it < A.max_iter && !converged)) {
-    const uint32_t par = it & 1u;
-    if (bid == 0 && threadIdx.x == 0) A.maxrel[par] = 0ull;
-    P2Acc pa{0.0, 0.0};
-    run_phase<1>(A, B, bid, nblk, 0.0, 0.0, pa);
-    grid.sync();
-    if (A.vbem && it > 0) {
-      // lagged logNorm: alphaSum of THIS iteration's input = partials written by the
-      // previous P2.  Any common factor in theta cancels in P1/P2.
-      double s = sum_partials(A.sum_partial + (size_t)(par ^ 1u) * nblk, nblk, A.inactive_sum,
-                              B.scratch);
-      logNorm = digamma_pos(s);
-    }
-    const double bias = (!A.vbem && it == 0) ? 1.0 : 0.0;  // alphasPrime starts at 1.0 (:812,:821)
-    run_phase<2>(A, B, bid, nblk, logNorm, bias, pa);
-    double bs = block_reduce<false>(pa.sum, B.scratch);
-    double bm = block_reduce<true>(pa.maxrel, B.scratch);
-    if (threadIdx.x == 0) {
-      A.sum_partial[(size_t)par * nblk + bid] = bs;
-      if (bm > 0.0) atomicMax(&A.maxrel[par], (unsigned long long)__double_as_longlong(bm));
-    }
-    grid.sync();
-    const double mr = __longlong_as_double((long long)A.maxrel[par]);
-    converged = !(mr > A.tol);
-    ++it;
-  }
-  if (bid == 0 && threadIdx.x == 0) {
-    A.out[0] = it;
-    A.out[1] = converged ? 1u : 0u;
-    A.out[2] = (it - 1) & 1u;  // parity slot holding the last maxrel
-  }
-}
-
-// multi-kernel variant ------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) k_em_p1(const __grid_constant__ EmArgs A) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  Block B;
-  block_setup(B, smem);
-  P2Acc pa{0.0, 0.0};
-  run_phase<1>(A, B, blockIdx.x, gridDim.x, 0.0, 0.0, pa);
-}
-// it_par: parity of this iteration; first: iteration 0 (exact sum0)
-__global__ void __launch_bounds__(THREADS)
-k_em_p2(const __grid_constant__ EmArgs A, uint32_t it, const uint32_t* __restrict__ done_flag) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  if (done_flag && *done_flag) return;
-  Block B;
-  block_setup(B, smem);
-  const uint32_t par = it & 1u;
-  double logNorm = 0.0;
-  if (A.vbem) {
-    if (it == 0) logNorm = digamma_pos(A.sum0);
-    else
-      logNorm = digamma_pos(sum_partials(A.sum_partial + (size_t)(par ^ 1u) * gridDim.x, gridDim.x,
-                                         A.inactive_sum, B.scratch));
-  }
-  const double bias = (!A.vbem && it == 0) ? 1.0 : 0.0;
-  P2Acc pa{0.0, 0.0};
-  run_phase<2>(A, B, blockIdx.x, gridDim.x, logNorm, bias, pa);
-  double bs = block_reduce<false>(pa.sum, B.scratch);
-  double bm = block_reduce<true>(pa.maxrel, B.scratch);
-  if (threadIdx.x == 0) {
-    A.sum_partial[(size_t)par * gridDim.x + blockIdx.x] = bs;
-    if (bm > 0.0) atomicMax(&A.maxrel[par], (unsigned long long)__double_as_longlong(bm));
-  }
-}
 __global__ void k_reset_maxrel(unsigned long long* maxrel, uint32_t par) { maxrel[par] = 0ull; }
 
-// multi-GPU: P2 without the per-transcript update (partial alpha' for the all-reduce)
-__global__ void __launch_bounds__(THREADS) k_em_p2_partial(const __grid_constant__ EmArgs A) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  Block B;
-  block_setup(B, smem);
-  P2Acc pa{0.0, 0.0};
-  run_phase<3>(A, B, blockIdx.x, gridDim.x, 0.0, 0.0, pa);
-}
 // multi-GPU: per-transcript update over ALL transcripts from the all-reduced alpha'.
 // Every rank computes the same values, so every rank takes the same decisions.
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(256)
 k_em_update(const __grid_constant__ EmArgs A, const double* __restrict__ red, uint32_t M,
             uint32_t it) {
   __shared__ double scratch[32];
@@ -554,11 +377,11 @@ k_em_update(const __grid_constant__ EmArgs A, const double* __restrict__ red, ui
   if (A.vbem) {
     if (it == 0) logNorm = digamma_pos(A.sum0);
     else logNorm = digamma_pos(sum_partials(A.sum_partial + (size_t)(par ^ 1u) * gridDim.x,
-                                            gridDim.x, 0.0, scratch));
+                                                 gridDim.x, 0.0, scratch));
   }
   const double bias = (!A.vbem && it == 0) ? 1.0 : 0.0;
   double sum = 0.0, mx = 0.0;
-  for (uint32_t t = blockIdx.x * THREADS + threadIdx.x; t < M; t += gridDim.x * THREADS) {
+  for (uint32_t t = blockIdx.x * 256 + threadIdx.x; t < M; t += gridDim.x * 256) {
     const double na = red[t] + bias;
     const double old = A.alpha[t];
     if (na > ALPHA_CHECK_CUTOFF) mx = fmax(mx, fabs(old - na) / na);
@@ -653,24 +476,36 @@ extern "C" sb_em_ctx* sb_em_create(int device) {
   return c;
 }
 
+static void free_sell(SellDev& m) {
+  void** ptrs[] = {(void**)&m.slice_ptr, (void**)&m.width, (void**)&m.len, (void**)&m.idx,
+                   (void**)&m.w, (void**)&m.warp_begin, (void**)&m.long_rows};
+  for (void** p : ptrs) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+}
 static void free_all(sb_em_ctx* c) {
   void** ptrs[] = {(void**)&c->d_off, (void**)&c->d_tids, (void**)&c->d_aux, (void**)&c->d_counts,
                    (void**)&c->d_projected, (void**)&c->d_eff_in, (void**)&c->d_unique,
                    (void**)&c->d_efflens, (void**)&c->d_prior, (void**)&c->d_alpha0,
                    (void**)&c->d_alpha, (void**)&c->d_theta, (void**)&c->d_base, (void**)&c->d_cw,
-                   (void**)&c->d_packed, (void**)&c->d_packed_scan, (void**)&c->d_valid,
-                   (void**)&c->d_scalars, (void**)&c->d_tcnt, (void**)&c->d_tid_row,
-                   (void**)&c->cm.off, (void**)&c->cm.idx, (void**)&c->cm.w, (void**)&c->cm.tiles,
-                   (void**)&c->cm.longs, (void**)&c->tm.off, (void**)&c->tm.idx, (void**)&c->tm.w,
-                   (void**)&c->tm.tiles, (void**)&c->tm.longs, (void**)&c->d_cnt, (void**)&c->d_scale,
-                   (void**)&c->d_ent_cls, (void**)&c->d_row_tid, (void**)&c->d_sort_keys,
-                   (void**)&c->d_sort_vals, (void**)&c->d_sort_keys2, (void**)&c->d_sort_vals2,
-                   (void**)&c->d_tmp, (void**)&c->d_sum_partial, (void**)&c->d_flush,
-                   (void**)&c->d_part, (void**)&c->d_part_red};
+                   (void**)&c->d_packed, (void**)&c->d_packed2, (void**)&c->d_packed_scan,
+                   (void**)&c->d_valid, (void**)&c->d_scalars, (void**)&c->d_tcnt,
+                   (void**)&c->d_tid_row, (void**)&c->m_off, (void**)&c->m_idx,
+                   (void**)&c->m_idx_state, (void**)&c->m_w, (void**)&c->t_off, (void**)&c->t_idx,
+                   (void**)&c->t_w, (void**)&c->d_cnt, (void**)&c->d_scale, (void**)&c->d_ent_cls,
+                   (void**)&c->d_row_tid, (void**)&c->d_rank_tid, (void**)&c->d_rowperm,
+                   (void**)&c->d_order, (void**)&c->d_sort_keys, (void**)&c->d_sort_vals,
+                   (void**)&c->d_sort_keys2, (void**)&c->d_sort_vals2, (void**)&c->d_tmp,
+                   (void**)&c->d_sum_partial, (void**)&c->d_flush, (void**)&c->d_part,
+                   (void**)&c->d_part_red, (void**)&c->r_alpha, (void**)&c->r_theta,
+                   (void**)&c->r_prior, (void**)&c->r_base, (void**)&c->r_alpha0};
   for (void** p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
   }
+  free_sell(c->cm);
+  free_sell(c->tm);
 }
 
 extern "C" void sb_em_destroy(sb_em_ctx* c) {
@@ -686,8 +521,13 @@ extern "C" void sb_em_destroy(sb_em_ctx* c) {
 extern "C" int sb_em_set_option(sb_em_ctx* c, const char* key, int64_t value) {
   if (!c || !key) { set_error("null argument"); return SB_ERR_INVALID; }
   if (!strcmp(key, "variant")) c->variant = (int)value;
-  else if (!strcmp(key, "blocks_per_sm")) c->blocks_per_sm = (int)value;
-  else if (!strcmp(key, "check_every")) c->check_every = (int)std::max<int64_t>(1, value);
+  else if (!strcmp(key, "blocks_per_sm")) { c->blocks_per_sm = (int)value; c->prepared = false; }
+  else if (!strcmp(key, "config")) {
+    if (value < 0 || value >= N_KERNEL_SETS) { set_error("config out of range"); return SB_ERR_INVALID; }
+    c->config = (int)value;
+    c->prepared = false;
+  } else if (!strcmp(key, "overhead_p1")) { c->ovh_p1 = (int)value; c->prepared = false; }
+  else if (!strcmp(key, "overhead_p2")) { c->ovh_p2 = (int)value; c->prepared = false; }
   else { set_error("unknown option '%s'", key); return SB_ERR_INVALID; }
   return SB_OK;
 }
@@ -742,28 +582,88 @@ extern "C" int sb_em_upload(sb_em_ctx* c, const sb_eq_csr* eq, const double* pro
 
 static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
-static int build_tiles(sb_em_ctx* c, SegMat& m, uint32_t* d_nlong_slot) {
-  cudaStream_t st = c->stream;
-  m.n_tiles = (m.nnz + TILE - 1) / TILE;
-  SB_TRY(dev_alloc(&m.tiles, (size_t)m.n_tiles));
-  if (m.n_tiles)
-    k_tiles<<<nblk(m.n_tiles, 128), 128, 0, st>>>(m.n_rows, m.off, m.nnz, m.n_tiles, m.tiles);
-  // long rows
-  uint32_t cap = m.nnz / (LMAX + 1) + 1;
-  SB_TRY(dev_alloc(&m.longs, (size_t)cap));
-  SB_CUDA(cudaMemsetAsync(d_nlong_slot, 0, 4, st));
-  if (m.n_rows)
-    k_long_rows<<<nblk(m.n_rows, 256), 256, 0, st>>>(m.n_rows, m.off, m.longs, d_nlong_slot, cap);
+static int bits_for(uint64_t n) {  // bits needed to represent values 0..n
+  int b = 1;
+  while (b < 32 && (1ull << b) <= n) ++b;
+  return b;
+}
+
+// stable sort of (key,val) u32 pairs through the context's scratch buffers;
+// result in d_sort_keys2 / d_sort_vals2
+static int sort_pairs(sb_em_ctx* c, uint32_t n, int end_bit) {
+  size_t tb = c->tmp_bytes;
+  SB_CUDA(cub::DeviceRadixSort::SortPairs(c->d_tmp, tb, c->d_sort_keys, c->d_sort_keys2,
+                                          c->d_sort_vals, c->d_sort_vals2, (int)n, 0, end_bit,
+                                          c->stream));
+  c->launches += 1 + 2 * ((end_bit + 7) / 8);
+  return SB_OK;
+}
+static int scan_u64(sb_em_ctx* c, const uint64_t* in, uint64_t* out, uint64_t n) {
+  size_t tb = c->tmp_bytes;
+  SB_CUDA(cub::DeviceScan::ExclusiveSum(c->d_tmp, tb, in, out, (int)n, c->stream));
   c->launches += 2;
-  SB_CUDA(cudaMemcpyAsync(&m.n_long, d_nlong_slot, 4, cudaMemcpyDeviceToHost, st));
+  return SB_OK;
+}
+
+// CSR (rows optionally permuted by rowperm) -> SELL-32 + long-row list + warp ranges
+static int build_sell(sb_em_ctx* c, SellDev& m, uint32_t n_rows, const uint32_t* rowperm,
+                      const uint32_t* csr_off, const uint32_t* csr_idx, const double* csr_w,
+                      uint32_t pad_idx, uint32_t overhead, uint32_t n_warps) {
+  cudaStream_t st = c->stream;
+  m.n_rows = n_rows;
+  m.n_slices = (n_rows + 31) / 32;
+  m.csr_idx = csr_idx;
+  m.csr_w = csr_w;
+  SB_TRY(dev_alloc(&m.len, (size_t)n_rows));
+  SB_TRY(dev_alloc(&m.width, (size_t)m.n_slices + 1));
+  SB_TRY(dev_alloc(&m.slice_ptr, (size_t)m.n_slices + 1));
+  SB_TRY(dev_alloc(&m.warp_begin, (size_t)n_warps + 1));
+  uint32_t* d_nlong = (uint32_t*)(c->d_scalars + 8);
+  SB_CUDA(cudaMemsetAsync(d_nlong, 0, 8, st));
+  SB_CUDA(cudaMemsetAsync(m.width, 0, ((size_t)m.n_slices + 1) * 4, st));
+  if (m.n_slices) {
+    k_sell_widths<<<nblk(m.n_slices, 8), 256, 0, st>>>(n_rows, m.n_slices, rowperm, csr_off, m.len,
+                                                       m.width, d_nlong);
+    c->launches++;
+  }
+  {
+    size_t tb = c->tmp_bytes;
+    SB_CUDA(cub::DeviceScan::ExclusiveSum(c->d_tmp, tb, m.width, m.slice_ptr, (int)(m.n_slices + 1), st));
+    c->launches += 2;
+  }
+  uint32_t ncols = 0;
+  SB_CUDA(cudaMemcpyAsync(&ncols, m.slice_ptr + m.n_slices, 4, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(&m.n_long, d_nlong, 4, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
+  m.n_cols = ncols;
+  SB_TRY(dev_alloc(&m.idx, (size_t)ncols * 32 + 32));
+  SB_TRY(dev_alloc(&m.w, (size_t)ncols * 32 + 32));
+  SB_TRY(dev_alloc(&m.long_rows, (size_t)3 * m.n_long + 3));
+  SB_CUDA(cudaMemsetAsync(m.idx, 0, ((size_t)ncols * 32 + 32) * 4, st));
+  SB_CUDA(cudaMemsetAsync(m.w, 0, ((size_t)ncols * 32 + 32) * 8, st));
+  if (m.n_slices) {
+    k_sell_fill<<<nblk(m.n_slices, 8), 256, 0, st>>>(n_rows, m.n_slices, rowperm, csr_off, csr_idx,
+                                                     csr_w, m.slice_ptr, m.len, pad_idx, m.idx,
+                                                     m.w, m.long_rows, d_nlong + 1);
+    c->launches++;
+  }
+  k_warp_ranges<<<nblk(n_warps + 1, 256), 256, 0, st>>>(m.n_slices, m.slice_ptr, overhead, n_warps,
+                                                        m.warp_begin);
+  c->launches++;
   if (m.n_long > 1) {
-    // deterministic order of the list itself is irrelevant to results (each long row is
-    // reduced independently with a fixed tree) but keep it sorted for reproducible timing.
-    std::vector<uint32_t> h(m.n_long);
-    SB_CUDA(cudaMemcpy(h.data(), m.longs, (size_t)m.n_long * 4, cudaMemcpyDeviceToHost));
-    std::sort(h.begin(), h.end());
-    SB_CUDA(cudaMemcpy(m.longs, h.data(), (size_t)m.n_long * 4, cudaMemcpyHostToDevice));
+    // every long row is reduced independently with a fixed tree: list order does not
+    // affect results; sorted anyway so that block assignment is reproducible.
+    std::vector<uint32_t> h((size_t)3 * m.n_long);
+    SB_CUDA(cudaMemcpyAsync(h.data(), m.long_rows, h.size() * 4, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    std::vector<uint32_t> ord(m.n_long);
+    for (uint32_t i = 0; i < m.n_long; ++i) ord[i] = i;
+    std::sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) { return h[3 * x] < h[3 * y]; });
+    std::vector<uint32_t> h2(h.size());
+    for (uint32_t i = 0; i < m.n_long; ++i)
+      for (int k = 0; k < 3; ++k) h2[3 * i + k] = h[3 * ord[i] + k];
+    SB_CUDA(cudaMemcpyAsync(m.long_rows, h2.data(), h2.size() * 4, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaStreamSynchronize(st));
   }
   return SB_OK;
 }
@@ -778,98 +678,122 @@ extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* s
   const uint64_t C = c->C;
   const uint32_t M = c->M;
   const uint64_t nnz = c->nnz;
+  const bool row_space = c->nranks <= 1;
   SB_CUDA(cudaEventRecord(c->ev[0], st));
 
+  // launch geometry first: the slice ranges are cut for this grid
+  int occ = 0;
+  const KernelSet& ks = kernel_set(c->config);
+  SB_CUDA(cudaFuncSetAttribute(ks.persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
+  SB_CUDA(cudaFuncSetAttribute((const void*)ks.p1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
+  SB_CUDA(cudaFuncSetAttribute((const void*)ks.p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
+  SB_CUDA(cudaFuncSetAttribute((const void*)ks.p2_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
+  SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ks.persistent, EM_THREADS, ks.smem));
+  if (occ < 1) { set_error("persistent EM kernel does not fit on an SM"); return SB_ERR_CUDA; }
+  if (c->blocks_per_sm > 0) occ = std::min(occ, c->blocks_per_sm);
+  c->grid = (uint32_t)(occ * c->n_sm);
+  c->occ = occ;
+  const uint32_t n_warps = c->grid * (EM_THREADS / 32);
+
+  const uint64_t NP = std::max<uint64_t>(C, M) + 1;
+  const uint64_t NS = std::max<uint64_t>(std::max<uint64_t>(C, nnz), (uint64_t)M) + 1;
   SB_TRY(dev_alloc(&c->d_efflens, M));
   SB_TRY(dev_alloc(&c->d_prior, M));
   SB_TRY(dev_alloc(&c->d_alpha0, M));
   SB_TRY(dev_alloc(&c->d_alpha, M));
-  SB_TRY(dev_alloc(&c->d_theta, M));
+  SB_TRY(dev_alloc(&c->d_theta, (size_t)M + 4));
+  SB_CUDA(cudaMemsetAsync(c->d_theta, 0, ((size_t)M + 4) * 8, st));
   SB_TRY(dev_alloc(&c->d_base, M));
   SB_TRY(dev_alloc(&c->d_cw, nnz));
-  SB_TRY(dev_alloc(&c->d_packed, std::max<uint64_t>(C, M) + 1));
-  SB_TRY(dev_alloc(&c->d_packed_scan, std::max<uint64_t>(C, M) + 1));
+  SB_TRY(dev_alloc(&c->d_packed, NP));
+  SB_TRY(dev_alloc(&c->d_packed2, NP));
+  SB_TRY(dev_alloc(&c->d_packed_scan, NP));
   SB_TRY(dev_alloc(&c->d_valid, C));
   SB_TRY(dev_alloc(&c->d_scalars, 64));
   SB_TRY(dev_alloc(&c->d_tcnt, M));
   SB_TRY(dev_alloc(&c->d_tid_row, M));
+  SB_TRY(dev_alloc(&c->d_sort_keys, NS));
+  SB_TRY(dev_alloc(&c->d_sort_vals, NS));
+  SB_TRY(dev_alloc(&c->d_sort_keys2, NS));
+  SB_TRY(dev_alloc(&c->d_sort_vals2, NS));
+  SB_TRY(dev_alloc(&c->d_order, NS));
   SB_CUDA(cudaMemsetAsync(c->d_base, 0, (size_t)M * 8, st));
   SB_CUDA(cudaMemsetAsync(c->d_scalars, 0, 64 * 8, st));
   SB_CUDA(cudaMemsetAsync(c->d_tcnt, 0, (size_t)M * 4, st));
-  SB_CUDA(cudaMemsetAsync(c->d_packed + std::max<uint64_t>(C, M), 0, 8, st));
+  SB_CUDA(cudaMemsetAsync(c->d_tid_row, 0xff, (size_t)M * 4, st));
+
+  // scratch for cub
+  size_t t1 = 0, t2 = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, t1, c->d_packed, c->d_packed_scan, (int)NP, st);
+  {
+    uint32_t* k = nullptr; uint32_t* v = nullptr;
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, k, k, v, v, (int)NS, 0, 32, st);
+  }
+  size_t need = std::max(t1, t2);
+  if (need > c->tmp_bytes) {
+    SB_TRY(dev_alloc((unsigned char**)&c->d_tmp, need));
+    c->tmp_bytes = need;
+  }
 
   k_txp_init<<<nblk(M, 256), 256, 0, st>>>(M, c->d_projected, c->d_eff_in, c->d_unique, *p,
                                             c->total_weight, c->d_efflens, c->d_prior, c->d_alpha0);
   c->launches++;
   unsigned long long* d_ndeg = (unsigned long long*)(c->d_scalars + 0);
   if (C) {
-    k_class_combine<<<nblk(C, 128), 128, 0, st>>>(C, c->d_off, c->d_tids, c->d_aux, c->d_counts,
+    k_class_combine<<<nblk(C, 128), 128, 0, st>>>(C, M, c->d_off, c->d_tids, c->d_aux, c->d_counts,
                                                    c->d_efflens, c->d_alpha0, *p, c->d_cw,
-                                                   c->d_packed, c->d_base, c->d_valid, d_ndeg);
+                                                   c->d_packed, c->d_sort_keys, c->d_base,
+                                                   c->d_valid, d_ndeg);
+    // (1) locality order: classes by first transcript id
+    k_iota<<<nblk(C, 256), 256, 0, st>>>((uint32_t)C, c->d_sort_vals);
+    c->launches += 2;
+    SB_TRY(sort_pairs(c, (uint32_t)C, bits_for(M)));
+    SB_CUDA(cudaMemcpyAsync(c->d_order, c->d_sort_vals2, C * 4, cudaMemcpyDeviceToDevice, st));
+    // (2) inside groups of SELL_GROUP classes, bucket by label length
+    k_bucket_key<<<nblk(C, 256), 256, 0, st>>>(C, c->d_order, c->d_packed, c->d_sort_keys, c->d_sort_vals);
+    c->launches++;
+    SB_TRY(sort_pairs(c, (uint32_t)C, 32));
+    SB_CUDA(cudaMemcpyAsync(c->d_order, c->d_sort_vals2, C * 4, cudaMemcpyDeviceToDevice, st));
+    k_gather_u64<<<nblk(C, 256), 256, 0, st>>>(C, c->d_order, c->d_packed, c->d_packed2);
     c->launches++;
   }
-  // scan (class count, entry count) packed into one u64
-  size_t tmp_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->d_packed, c->d_packed_scan, (int)(C + 1), st);
-  size_t sort_tmp = 0;
-  {
-    uint32_t* k = nullptr; uint32_t* v = nullptr;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, k, k, v, v, (int)std::max<uint64_t>(nnz, 1), 0, 32, st);
-  }
-  size_t scan_m = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, scan_m, c->d_packed, c->d_packed_scan, (int)(M + 1), st);
-  size_t need = std::max(std::max(tmp_bytes, sort_tmp), scan_m);
-  if (need > c->tmp_bytes) {
-    SB_TRY(dev_alloc((unsigned char**)&c->d_tmp, need));
-    c->tmp_bytes = need;
-  }
-  SB_CUDA(cub::DeviceScan::ExclusiveSum(c->d_tmp, need, c->d_packed, c->d_packed_scan, (int)(C + 1), st));
-  c->launches += 2;
+  SB_CUDA(cudaMemsetAsync(c->d_packed2 + C, 0, 8, st));
+  SB_TRY(scan_u64(c, c->d_packed2, c->d_packed_scan, C + 1));
   uint64_t tot = 0;
   SB_CUDA(cudaMemcpyAsync(&tot, c->d_packed_scan + C, 8, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaMemcpyAsync(&c->n_degenerate, d_ndeg, 8, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   const uint32_t Cm = (uint32_t)(tot >> 32);
   const uint32_t nnzm = (uint32_t)(tot & 0xffffffffu);
-  c->cm.n_rows = Cm; c->cm.nnz = nnzm;
+  c->n_cls = Cm; c->nnzm = nnzm;
 
-  SB_TRY(dev_alloc(&c->cm.off, (size_t)Cm + 1));
-  SB_TRY(dev_alloc(&c->cm.idx, (size_t)nnzm + 16));
-  SB_TRY(dev_alloc(&c->cm.w, (size_t)nnzm + 16));
+  // compact class-major CSR in final class order
+  SB_TRY(dev_alloc(&c->m_off, (size_t)Cm + 1));
+  SB_TRY(dev_alloc(&c->m_idx, (size_t)nnzm + 1));
+  SB_TRY(dev_alloc(&c->m_idx_state, (size_t)nnzm + 1));
+  SB_TRY(dev_alloc(&c->m_w, (size_t)nnzm + 1));
   SB_TRY(dev_alloc(&c->d_cnt, (size_t)Cm));
-  SB_TRY(dev_alloc(&c->d_scale, (size_t)Cm));
+  SB_TRY(dev_alloc(&c->d_scale, (size_t)Cm + 4));
   SB_TRY(dev_alloc(&c->d_ent_cls, (size_t)nnzm));
-  SB_CUDA(cudaMemsetAsync(c->cm.idx, 0, ((size_t)nnzm + 16) * 4, st));
-  SB_CUDA(cudaMemsetAsync(c->cm.w, 0, ((size_t)nnzm + 16) * 8, st));
-  SB_CUDA(cudaMemcpyAsync(c->cm.off + Cm, &nnzm, 4, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemsetAsync(c->d_scale, 0, ((size_t)Cm + 4) * 8, st));
+  SB_CUDA(cudaMemcpyAsync(c->m_off + Cm, &nnzm, 4, cudaMemcpyHostToDevice, st));
   if (C) {
-    k_compact<<<nblk(C, 128), 128, 0, st>>>(C, c->d_off, c->d_tids, c->d_cw, c->d_counts,
-                                             c->d_packed, c->d_packed_scan, c->cm.off, c->cm.idx,
-                                             c->cm.w, c->d_cnt, c->d_ent_cls, c->d_tcnt);
+    k_compact<<<nblk(C, 128), 128, 0, st>>>(C, c->d_order, c->d_off, c->d_tids, c->d_cw, c->d_counts,
+                                             c->d_packed2, c->d_packed_scan, c->m_off, c->m_idx,
+                                             c->m_w, c->d_cnt, c->d_ent_cls, c->d_tcnt);
     c->launches++;
   }
-  // transcript-major copy: stable radix sort of (tid, entry) pairs
-  SB_TRY(dev_alloc(&c->d_sort_keys, (size_t)nnzm));
-  SB_TRY(dev_alloc(&c->d_sort_vals, (size_t)nnzm));
-  SB_TRY(dev_alloc(&c->d_sort_keys2, (size_t)nnzm));
-  SB_TRY(dev_alloc(&c->d_sort_vals2, (size_t)nnzm));
+  // transcript-major CSR in rank order: stable radix sort of (tid, entry) pairs
   if (nnzm) {
-    SB_CUDA(cudaMemcpyAsync(c->d_sort_keys, c->cm.idx, (size_t)nnzm * 4, cudaMemcpyDeviceToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(c->d_sort_keys, c->m_idx, (size_t)nnzm * 4, cudaMemcpyDeviceToDevice, st));
     k_iota<<<nblk(nnzm, 256), 256, 0, st>>>(nnzm, c->d_sort_vals);
-    int end_bit = 1;
-    while (end_bit < 32 && (1ull << end_bit) < (uint64_t)M) ++end_bit;
-    size_t tb = c->tmp_bytes;
-    SB_CUDA(cub::DeviceRadixSort::SortPairs(c->d_tmp, tb, c->d_sort_keys, c->d_sort_keys2,
-                                            c->d_sort_vals, c->d_sort_vals2, (int)nnzm, 0, end_bit, st));
-    c->launches += 2 + (end_bit + 7) / 8 * 3;
+    c->launches++;
+    SB_TRY(sort_pairs(c, nnzm, bits_for(M)));
   }
   k_row_pack<<<nblk(M, 256), 256, 0, st>>>(M, c->d_tcnt, c->d_packed);
+  c->launches++;
   SB_CUDA(cudaMemsetAsync(c->d_packed + M, 0, 8, st));
-  {
-    size_t tb = c->tmp_bytes;
-    SB_CUDA(cub::DeviceScan::ExclusiveSum(c->d_tmp, tb, c->d_packed, c->d_packed_scan, (int)(M + 1), st));
-  }
-  c->launches += 3;
+  SB_TRY(scan_u64(c, c->d_packed, c->d_packed_scan, (uint64_t)M + 1));
   uint64_t tot2 = 0;
   SB_CUDA(cudaMemcpyAsync(&tot2, c->d_packed_scan + M, 8, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
@@ -878,25 +802,55 @@ extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* s
     set_error("internal: transcript-major entry count mismatch");
     return SB_ERR_STATE;
   }
-  c->tm.n_rows = R; c->tm.nnz = nnzm;
-  SB_TRY(dev_alloc(&c->tm.off, (size_t)R + 1));
-  SB_TRY(dev_alloc(&c->tm.idx, (size_t)nnzm + 16));
-  SB_TRY(dev_alloc(&c->tm.w, (size_t)nnzm + 16));
-  SB_TRY(dev_alloc(&c->d_row_tid, (size_t)R));
-  SB_CUDA(cudaMemsetAsync(c->tm.idx, 0, ((size_t)nnzm + 16) * 4, st));
-  SB_CUDA(cudaMemsetAsync(c->tm.w, 0, ((size_t)nnzm + 16) * 8, st));
-  SB_CUDA(cudaMemcpyAsync(c->tm.off + R, &nnzm, 4, cudaMemcpyHostToDevice, st));
-  k_row_fill<<<nblk(M, 256), 256, 0, st>>>(M, c->d_tcnt, c->d_packed_scan, c->tm.off, c->d_row_tid,
-                                            c->d_tid_row);
-  if (nnzm)
-    k_gather_csc<<<nblk(nnzm, 256), 256, 0, st>>>(nnzm, c->d_sort_vals2, c->d_ent_cls, c->cm.w,
-                                                   c->tm.idx, c->tm.w);
-  c->launches += 2;
-  uint32_t* d_nlong = (uint32_t*)(c->d_scalars + 8);
-  SB_TRY(build_tiles(c, c->cm, d_nlong));
-  SB_TRY(build_tiles(c, c->tm, d_nlong + 1));
+  c->n_rows = R;
+  SB_TRY(dev_alloc(&c->t_off, (size_t)R + 1));
+  SB_TRY(dev_alloc(&c->t_idx, (size_t)nnzm + 1));
+  SB_TRY(dev_alloc(&c->t_w, (size_t)nnzm + 1));
+  SB_TRY(dev_alloc(&c->d_rank_tid, (size_t)R + 1));
+  SB_TRY(dev_alloc(&c->d_rowperm, (size_t)R + 1));
+  SB_TRY(dev_alloc(&c->d_row_tid, (size_t)R + 1));
+  SB_TRY(dev_alloc(&c->r_alpha, (size_t)R + 1));
+  SB_TRY(dev_alloc(&c->r_theta, (size_t)R + 4));
+  SB_CUDA(cudaMemsetAsync(c->r_theta, 0, ((size_t)R + 4) * 8, st));
+  SB_TRY(dev_alloc(&c->r_prior, (size_t)R + 1));
+  SB_TRY(dev_alloc(&c->r_base, (size_t)R + 1));
+  SB_TRY(dev_alloc(&c->r_alpha0, (size_t)R + 1));
+  SB_CUDA(cudaMemcpyAsync(c->t_off + R, &nnzm, 4, cudaMemcpyHostToDevice, st));
+  // rank_packed reuses d_packed2 (class packing no longer needed)
+  k_rank_fill<<<nblk(M, 256), 256, 0, st>>>(M, c->d_tcnt, c->d_packed_scan, c->t_off, c->d_rank_tid,
+                                             c->d_packed2);
+  c->launches++;
+  if (nnzm) {
+    k_gather_csc<<<nblk(nnzm, 256), 256, 0, st>>>(nnzm, c->d_sort_vals2, c->d_ent_cls, c->m_w,
+                                                   c->t_idx, c->t_w);
+    c->launches++;
+  }
+  // rows: ranks bucketed by occurrence count inside groups of SELL_GROUP
+  if (R) {
+    k_bucket_key<<<nblk(R, 256), 256, 0, st>>>(R, nullptr, c->d_packed2, c->d_sort_keys, c->d_sort_vals);
+    c->launches++;
+    SB_TRY(sort_pairs(c, R, 32));
+    SB_CUDA(cudaMemcpyAsync(c->d_rowperm, c->d_sort_vals2, (size_t)R * 4, cudaMemcpyDeviceToDevice, st));
+    k_row_fill<<<nblk(R, 256), 256, 0, st>>>(R, c->d_rowperm, c->d_rank_tid, c->d_prior, c->d_base,
+                                              c->d_alpha0, c->d_row_tid, c->d_tid_row, c->r_prior,
+                                              c->r_base, c->r_alpha0);
+    c->launches++;
+  }
+  // class-major gather index: row ids (single GPU) or transcript ids (multi GPU)
+  if (nnzm) {
+    if (row_space) {
+      k_remap<<<nblk(nnzm, 256), 256, 0, st>>>(nnzm, c->m_idx, c->d_tid_row, c->m_idx_state);
+      c->launches++;
+    } else {
+      SB_CUDA(cudaMemcpyAsync(c->m_idx_state, c->m_idx, (size_t)nnzm * 4, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  // SELL-32 copies.  overhead = per-slice epilogue cost in "columns" for the work split
+  SB_TRY(build_sell(c, c->cm, Cm, nullptr, c->m_off, c->m_idx_state, c->m_w, row_space ? R : M, (uint32_t)c->ovh_p1, n_warps));
+  SB_TRY(build_sell(c, c->tm, R, c->d_rowperm, c->t_off, c->t_idx, c->t_w, Cm,
+                    (uint32_t)(c->params.use_vbem ? c->ovh_p2 : c->ovh_p1), n_warps));
 
-  // iteration-0 state
+  // iteration-0 reductions
   double* d_sum0 = c->d_scalars + 16;
   double* d_inact = c->d_scalars + 17;
   k_sum1<<<1, 1024, 0, st>>>(M, c->d_alpha0, c->d_prior, c->d_tid_row, 0, d_sum0);
@@ -904,18 +858,7 @@ extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* s
   c->launches += 2;
   SB_CUDA(cudaMemcpyAsync(&c->sum0, d_sum0, 8, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaMemcpyAsync(&c->inactive_sum, d_inact, 8, cudaMemcpyDeviceToHost, st));
-
-  // launch geometry
-  SB_CUDA(cudaFuncSetAttribute(k_em_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)SmemLayout::total));
-  SB_CUDA(cudaFuncSetAttribute(k_em_p1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout::total));
-  SB_CUDA(cudaFuncSetAttribute(k_em_p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout::total));
-  int occ = 0;
-  SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_em_persistent, THREADS, SmemLayout::total));
-  if (occ < 1) { set_error("persistent EM kernel does not fit on an SM"); return SB_ERR_CUDA; }
-  if (c->blocks_per_sm > 0) occ = std::min(occ, c->blocks_per_sm);
-  c->grid = (uint32_t)(occ * c->n_sm);
-  SB_TRY(dev_alloc(&c->d_sum_partial, (size_t)2 * c->grid));
+  SB_TRY(dev_alloc(&c->d_sum_partial, (size_t)2 * std::max<uint32_t>(c->grid, 4096)));
   SB_CUDA(cudaStreamSynchronize(st));
   SB_CUDA(cudaEventRecord(c->ev[1], st));
   SB_CUDA(cudaEventSynchronize(c->ev[1]));
@@ -935,15 +878,26 @@ extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* s
   return SB_OK;
 }
 
-static void fill_args(sb_em_ctx* c, EmArgs& A) {
+static Sell sell_view(const SellDev& m) {
+  Sell s;
+  s.slice_ptr = m.slice_ptr; s.len = m.len; s.idx = m.idx; s.w = m.w; s.warp_begin = m.warp_begin;
+  s.long_rows = m.long_rows; s.csr_idx = m.csr_idx; s.csr_w = m.csr_w;
+  s.n_rows = m.n_rows; s.n_slices = m.n_slices; s.n_long = m.n_long;
+  return s;
+}
+
+static void fill_args(sb_em_ctx* c, EmArgs& A, bool row_space) {
   memset(&A, 0, sizeof(A));
-  A.c_off = c->cm.off; A.c_idx = c->cm.idx; A.c_w = c->cm.w; A.c_tiles = c->cm.tiles;
-  A.c_long = c->cm.longs; A.c_cnt = c->d_cnt; A.scale = c->d_scale;
-  A.c_ntiles = c->cm.n_tiles; A.c_nlong = c->cm.n_long; A.c_nrows = c->cm.n_rows;
-  A.t_off = c->tm.off; A.t_idx = c->tm.idx; A.t_w = c->tm.w; A.t_tiles = c->tm.tiles;
-  A.t_long = c->tm.longs; A.row_tid = c->d_row_tid;
-  A.t_ntiles = c->tm.n_tiles; A.t_nlong = c->tm.n_long; A.t_nrows = c->tm.n_rows;
-  A.alpha = c->d_alpha; A.theta = c->d_theta; A.prior = c->d_prior; A.base = c->d_base;
+  A.cm = sell_view(c->cm);
+  A.tm = sell_view(c->tm);
+  A.c_cnt = c->d_cnt; A.scale = c->d_scale;
+  if (row_space) {
+    A.alpha = c->r_alpha; A.theta = c->r_theta; A.prior = c->r_prior; A.base = c->r_base;
+    A.row_tid = nullptr;
+  } else {
+    A.alpha = c->d_alpha; A.theta = c->d_theta; A.prior = c->d_prior; A.base = c->d_base;
+    A.row_tid = c->d_row_tid;
+  }
   A.sum_partial = c->d_sum_partial;
   A.maxrel = (unsigned long long*)(c->d_scalars + 24);
   A.inactive_sum = c->inactive_sum; A.sum0 = c->sum0;
@@ -1014,6 +968,7 @@ extern "C" int sb_em_comm_init(sb_em_ctx* c, int rank, int nranks, const void* u
   c->nccl_comm = comm;
   c->rank = rank;
   c->nranks = nranks;
+  c->prepared = false;  // gather windows depend on the index space
   return SB_OK;
 }
 extern "C" int sb_em_comm_destroy(sb_em_ctx* c) {
@@ -1028,8 +983,8 @@ extern "C" int sb_em_comm_destroy(sb_em_ctx* c) {
 }
 
 // One iteration = P1, P2-partial, all-reduce(alpha'), update.  Classes stay sharded.
-static int em_run_multi_gpu(sb_em_ctx* c, EmArgs& A, uint32_t* out, uint32_t* launches,
-                            uint32_t* loop_launches, float* loop_ms) {
+static int em_run_multi_gpu(sb_em_ctx* c, const KernelSet& ks, EmArgs& A, uint32_t* out,
+                            uint32_t* launches, uint32_t* loop_launches, float* loop_ms) {
   cudaStream_t st = c->stream;
   const uint32_t M = c->M;
   SB_TRY(dev_alloc(&c->d_part, (size_t)M));
@@ -1037,18 +992,18 @@ static int em_run_multi_gpu(sb_em_ctx* c, EmArgs& A, uint32_t* out, uint32_t* la
   // locally inactive transcripts contribute their (constant) folded singleton mass
   SB_CUDA(cudaMemcpyAsync(c->d_part, c->d_base, (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
   A.part_out = c->d_part;
-  const uint32_t ugrid = (uint32_t)std::min<uint32_t>(c->grid, (M + THREADS - 1) / THREADS);
-  // the update kernel writes its own partials: re-size for its grid
+  A.inactive_sum = 0.0;  // the update covers every transcript
+  const uint32_t ugrid = std::min<uint32_t>(4096u, (M + 255) / 256);
   uint32_t it = 0;
   bool converged = false;
   SB_CUDA(cudaEventRecord(c->ev[2], st));
   while (it < A.min_iter || (it < A.max_iter && !converged)) {
     k_reset_maxrel<<<1, 1, 0, st>>>(A.maxrel, it & 1u);
-    k_em_p1<<<c->grid, THREADS, SmemLayout::total, st>>>(A);
-    k_em_p2_partial<<<c->grid, THREADS, SmemLayout::total, st>>>(A);
+    ks.p1<<<c->grid, EM_THREADS, ks.smem, st>>>(A);
+    ks.p2_partial<<<c->grid, EM_THREADS, ks.smem, st>>>(A);
     SB_NCCL(g_nccl.AllReduce(c->d_part, c->d_part_red, (size_t)M, /*ncclFloat64*/ 8, /*ncclSum*/ 0,
                              c->nccl_comm, st));
-    k_em_update<<<ugrid, THREADS, 0, st>>>(A, c->d_part_red, M, it);
+    k_em_update<<<ugrid, 256, 0, st>>>(A, c->d_part_red, M, it);
     *launches += 5; *loop_launches += 4;
     ++it;
     if (it >= A.min_iter) {
@@ -1072,42 +1027,53 @@ extern "C" int sb_em_run(sb_em_ctx* c, sb_em_stats* stats) {
   if (!c->prepared) { set_error("sb_em_run before sb_em_prepare"); return SB_ERR_STATE; }
   SB_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
+  const KernelSet& ks = kernel_set(c->config);
   const uint32_t M = c->M;
+  const uint32_t R = c->n_rows;
+  const bool multi_gpu = c->nranks > 1;
   uint32_t launches = 0;
   SB_CUDA(cudaEventRecord(c->ev[0], st));
   // restart from the prepared state
-  k_theta0<<<nblk(M, 256), 256, 0, st>>>(M, c->params.use_vbem, c->d_alpha0, c->d_prior,
-                                          c->d_scalars + 16, c->d_alpha, c->d_theta);
-  ++launches;
+  double* d_sum0 = c->d_scalars + 16;
+  if (multi_gpu) {
+    k_theta0<<<nblk(M, 256), 256, 0, st>>>(M, c->params.use_vbem, c->d_alpha0, c->d_prior, d_sum0,
+                                            c->d_alpha, c->d_theta);
+    ++launches;
+  } else if (R) {
+    k_theta0<<<nblk(R, 256), 256, 0, st>>>(R, c->params.use_vbem, c->r_alpha0, c->r_prior, d_sum0,
+                                            c->r_alpha, c->r_theta);
+    ++launches;
+  }
   SB_CUDA(cudaMemsetAsync(c->d_scalars + 24, 0, 16 * 8, st));
   EmArgs A;
-  fill_args(c, A);
+  fill_args(c, A, !multi_gpu);
   uint32_t out[4] = {0, 0, 0, 0};
   float loop_ms = 0;
   uint32_t loop_launches = 0;
-  const bool multi_gpu = c->nranks > 1;
   if (c->params.max_iter == 0 && c->params.min_iter == 0) {
     // nothing to iterate
-  } else if (c->variant == 1 && !multi_gpu) {
+  } else if (multi_gpu) {
+    int r = em_run_multi_gpu(c, ks, A, out, &launches, &loop_launches, &loop_ms);
+    if (r != SB_OK) return r;
+  } else if (c->variant == 1) {
     void* args[] = {(void*)&A};
     SB_CUDA(cudaEventRecord(c->ev[2], st));
-    SB_CUDA(cudaLaunchCooperativeKernel((void*)k_em_persistent, dim3(c->grid), dim3(THREADS), args,
-                                        SmemLayout::total, st));
+    SB_CUDA(cudaLaunchCooperativeKernel(ks.persistent, dim3(c->grid), dim3(EM_THREADS), args, ks.smem, st));
     SB_CUDA(cudaEventRecord(c->ev[3], st));
     ++launches; ++loop_launches;
     SB_CUDA(cudaMemcpyAsync(out, A.out, 16, cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&loop_ms, c->ev[2], c->ev[3]);
-  } else if (!multi_gpu) {
-    // multi-kernel variant: host checks convergence every `check_every` iterations only
-    // where the reference's loop condition can actually change (it >= min_iter).
+  } else {
+    // one launch per phase; the host reads the convergence flag only where the
+    // reference's loop condition can change (it >= min_iter).
     uint32_t it = 0;
     bool converged = false;
     SB_CUDA(cudaEventRecord(c->ev[2], st));
     while (it < A.min_iter || (it < A.max_iter && !converged)) {
       k_reset_maxrel<<<1, 1, 0, st>>>(A.maxrel, it & 1u);
-      k_em_p1<<<c->grid, THREADS, SmemLayout::total, st>>>(A);
-      k_em_p2<<<c->grid, THREADS, SmemLayout::total, st>>>(A, it, nullptr);
+      ks.p1<<<c->grid, EM_THREADS, ks.smem, st>>>(A);
+      ks.p2<<<c->grid, EM_THREADS, ks.smem, st>>>(A, it);
       launches += 3; loop_launches += 2;
       ++it;
       if (it >= A.min_iter) {
@@ -1123,9 +1089,6 @@ extern "C" int sb_em_run(sb_em_ctx* c, sb_em_stats* stats) {
     SB_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&loop_ms, c->ev[2], c->ev[3]);
     out[0] = it; out[1] = converged; out[2] = (it - 1) & 1u;
-  } else {
-    int r = em_run_multi_gpu(c, A, out, &launches, &loop_launches, &loop_ms);
-    if (r != SB_OK) return r;
   }
   c->iters = out[0];
   c->converged = out[1];
@@ -1136,10 +1099,14 @@ extern "C" int sb_em_run(sb_em_ctx* c, sb_em_stats* stats) {
   } else {
     c->max_rel_diff = -DBL_MAX;
   }
-  // inactive transcripts
-  if (out[0] > 0 && !multi_gpu) {
-    double bias = (!c->params.use_vbem && out[0] == 1) ? 1.0 : 0.0;
-    k_finalize_inactive<<<nblk(M, 256), 256, 0, st>>>(M, c->d_tid_row, c->d_base, bias, c->d_alpha);
+  if (!multi_gpu) {
+    // row space -> transcript space (+ inactive transcripts)
+    if (out[0] > 0) {
+      double bias = (!c->params.use_vbem && out[0] == 1) ? 1.0 : 0.0;
+      k_finalize<<<nblk(M, 256), 256, 0, st>>>(M, c->d_tid_row, c->d_base, bias, c->r_alpha, c->d_alpha);
+    } else {
+      SB_CUDA(cudaMemcpyAsync(c->d_alpha, c->d_alpha0, (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
+    }
     ++launches;
   }
   SB_CUDA(cudaEventRecord(c->ev[1], st));
@@ -1153,9 +1120,9 @@ extern "C" int sb_em_run(sb_em_ctx* c, sb_em_stats* stats) {
     stats->converged = c->converged;
     stats->max_rel_diff = c->max_rel_diff;
     stats->n_degenerate = c->n_degenerate;
-    stats->n_multi_classes = c->cm.n_rows;
-    stats->nnz_multi = c->cm.nnz;
-    stats->n_active_txps = c->tm.n_rows;
+    stats->n_multi_classes = c->n_cls;
+    stats->nnz_multi = c->nnzm;
+    stats->n_active_txps = c->n_rows;
     stats->prepare_ms = c->prepare_ms;
     stats->run_ms = ms;
     stats->loop_kernel_ms = loop_ms;

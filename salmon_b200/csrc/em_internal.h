@@ -7,23 +7,19 @@
 
 namespace sb {
 
-// A segmented matrix in HBM: rows with (index, weight) entries, plus the tile
-// descriptors the streaming kernels walk.  Used twice: class-major
-// (row = class, index = transcript id) and transcript-major (row = active
-// transcript, index = compact class id).
-struct SegMat {
-  uint32_t n_rows = 0;
-  uint32_t nnz = 0;
-  uint32_t n_tiles = 0;
-  uint32_t n_long = 0;
-  uint32_t* off = nullptr;    // [n_rows+1]
-  uint32_t* idx = nullptr;    // [nnz+16]
-  double* w = nullptr;        // [nnz+16]
-  uint4* tiles = nullptr;     // [n_tiles] {row0,row1,ent0,ent1}
-  uint32_t* longs = nullptr;  // rows longer than LMAX
+// Device-side owner of one SELL-32 matrix (see em_kernels.cuh: struct Sell).
+struct SellDev {
+  uint32_t n_rows = 0, n_slices = 0, n_cols = 0, n_long = 0;
+  uint32_t* slice_ptr = nullptr;
+  uint32_t* width = nullptr;
+  uint16_t* len = nullptr;
+  uint32_t* idx = nullptr;
+  double* w = nullptr;
+  uint32_t* warp_begin = nullptr;
+  uint32_t* long_rows = nullptr;
+  const uint32_t* csr_idx = nullptr;  // not owned
+  const double* csr_w = nullptr;      // not owned
 };
-
-struct NcclApi;
 
 }  // namespace sb
 
@@ -37,7 +33,9 @@ struct sb_em_ctx {
   // options
   int variant = 1;        // 1 = persistent cooperative kernel, 0 = one launch per phase
   int blocks_per_sm = 0;  // 0 = as many as fit
-  int check_every = 1;
+  int config = 0;         // kernel configuration (tile/threads/stages), see kernel_set()
+  int occ = 0;
+  int ovh_p1 = 3, ovh_p2 = 12;  // per-slice epilogue cost (in columns) for the work split
 
   // problem
   uint64_t C = 0, nnz = 0;
@@ -66,10 +64,14 @@ struct sb_em_ctx {
   uint32_t* d_tcnt = nullptr;
   uint32_t* d_tid_row = nullptr;
   uint32_t* d_row_tid = nullptr;
+  // row-space (active transcripts) iteration state, single-GPU path
+  double *r_alpha = nullptr, *r_theta = nullptr, *r_prior = nullptr, *r_base = nullptr,
+         *r_alpha0 = nullptr;
 
   // per class / entry
   double* d_cw = nullptr;         // combinedWeights in input order
   uint64_t* d_packed = nullptr;
+  uint64_t* d_packed2 = nullptr;
   uint64_t* d_packed_scan = nullptr;
   uint8_t* d_valid = nullptr;
   double* d_cnt = nullptr;        // counts of compact classes (as f64)
@@ -80,7 +82,14 @@ struct sb_em_ctx {
   void* d_tmp = nullptr;
   size_t tmp_bytes = 0;
 
-  sb::SegMat cm, tm;
+  // compact CSR copies (final class order / rank order) + SELL-32 matrices
+  uint32_t n_cls = 0, nnzm = 0, n_rows = 0;
+  uint32_t *m_off = nullptr, *m_idx = nullptr, *m_idx_state = nullptr;
+  double* m_w = nullptr;
+  uint32_t *t_off = nullptr, *t_idx = nullptr;
+  double* t_w = nullptr;
+  uint32_t *d_rank_tid = nullptr, *d_rowperm = nullptr, *d_order = nullptr;
+  sb::SellDev cm, tm;
 
   double* d_scalars = nullptr;    // 64 doubles of misc device scalars
   double* d_sum_partial = nullptr;

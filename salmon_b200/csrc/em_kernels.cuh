@@ -1,0 +1,404 @@
+// em_kernels.cuh -- the EM / VBEM iteration kernels (sm_100a).
+//
+// One iteration = two segmented reductions over the class<->transcript map held
+// twice in HBM (class-major and transcript-major), no atomics on the data path,
+// fixed summation order:
+//   P1 (class-major):  denom_c = sum_i theta[t_i] * w_ci ;  scale_c = count_c / denom_c
+//   P2 (txp-major):    alpha'_t = base_t + theta_t * sum_c w_ct * scale_c, convergence
+//                      test, theta'_t (VBEM: exp(digamma(alpha'+prior) - logNorm))
+// Reference arithmetic: src/inference/CollapsedEMOptimizer.cpp:178-234 (EMUpdate_),
+// :241-328 (VBEMUpdate_), :945-957 (convergence + swap).
+//
+// Layout: sliced ELL, slice height 32 (SELL-32).  Rows are ordered for gather locality
+// (classes by first transcript id, transcripts by id) and then bucketed by length inside
+// groups of SELL_GROUP rows, so the 32 rows of a slice have (nearly) equal length.  A
+// warp owns a slice: lane = row, entry j of the 32 rows is one coalesced 128-byte (index)
+// + 256-byte (weight) load, each lane accumulates its row sequentially in label order.
+// Slices are dealt to warps in contiguous, work-balanced ranges computed at prepare time.
+// Rows longer than LMAX are reduced by a whole block from their CSR copy.
+#pragma once
+#include <cooperative_groups.h>
+#include <float.h>
+
+#include "common.cuh"
+
+namespace sb {
+namespace cg = cooperative_groups;
+
+constexpr int LMAX = 256;                    // rows longer than this take the block path
+constexpr int SELL_GROUP = 1024;             // rows per length-bucketing group
+constexpr int EM_THREADS = 256;
+constexpr double DIGAMMA_MIN = 1e-10;        // CollapsedEMOptimizer.cpp:43
+constexpr double MIN_EQ_W = DBL_MIN;         // :40
+constexpr double ALPHA_CHECK_CUTOFF = 1e-2;  // :884
+constexpr uint16_t LEN_LONG = 0xFFFFu;       // row handled by the block path
+
+// One segmented matrix in SELL-32 form (+ CSR copy of the long rows only).
+struct Sell {
+  const uint32_t* slice_ptr;   // [n_slices+1] first column of each slice
+  const uint16_t* len;         // [n_rows] entries per row (LEN_LONG: block path)
+  const uint32_t* idx;         // [n_cols*32] gather index, column-interleaved
+  const double* w;             // [n_cols*32]
+  const uint32_t* warp_begin;  // [n_warps+1] slice range per warp (work balanced)
+  // long rows: (row, first entry, end entry) triples into csr_idx / csr_w
+  const uint32_t* long_rows;   // [3*n_long]
+  const uint32_t* csr_idx;
+  const double* csr_w;
+  uint32_t n_rows, n_slices, n_long;
+};
+
+struct EmArgs {
+  Sell cm;                      // rows = kept multi-transcript classes; idx = state index
+  Sell tm;                      // rows = active transcripts;           idx = class id
+  const double* c_cnt;          // [classes] count as f64
+  double* scale;                // [classes] count / denom
+  // iteration state.  Single GPU: indexed by ROW of tm (cm.idx holds rows).  Multi GPU:
+  // indexed by transcript id (cm.idx holds ids) and row_tid maps tm rows to ids.
+  double* alpha; double* theta; const double* prior; const double* base;
+  const uint32_t* row_tid;
+  double* part_out;             // multi-GPU: this rank's alpha' share per transcript id
+  // reductions
+  double* sum_partial;          // [2][grid]
+  unsigned long long* maxrel;   // [2] bit pattern of a non-negative double
+  double inactive_sum; double sum0;
+  double tol;
+  uint32_t min_iter, max_iter;
+  int vbem;
+  uint32_t* out;                // [0]=iters [1]=converged [2]=maxrel slot
+};
+
+struct P2Acc {
+  double sum;     // sum of (alpha' + prior) over my rows
+  double maxrel;  // max rel diff over my rows
+};
+
+// Per-warp TMA ring: each warp streams ITS contiguous column range of the SELL arrays
+// through a private double-buffered shared-memory ring with 1-D bulk copies (lane 0 is
+// the producer, the warp is the consumer), so the index/weight stream is never a
+// dependent load and no block-level barrier exists on the data path.
+constexpr int RING = 2;   // chunks in flight per warp
+template <int CH>         // CH = columns (x32 entries) per chunk
+struct __align__(128) WarpRing {
+  double w[RING][CH * 32];
+  uint32_t idx[RING][CH * 32];
+};
+constexpr int EM_WARPS = EM_THREADS / 32;
+template <int CH>
+constexpr size_t em_smem() { return sizeof(WarpRing<CH>) * EM_WARPS + EM_WARPS * RING * 8 + 32 * 8; }
+
+template <int CH>
+struct WarpCtx {
+  WarpRing<CH>* ring;
+  uint64_t* bars;        // [RING]
+  uint32_t phase_bits;   // mbarrier parity per stage
+  double* scratch;       // block scratch (32 doubles)
+};
+
+template <int CH>
+__device__ __forceinline__ void warp_setup(WarpCtx<CH>& W, unsigned char* smem) {
+  const uint32_t wid = threadIdx.x >> 5;
+  W.ring = reinterpret_cast<WarpRing<CH>*>(smem) + wid;
+  W.bars = reinterpret_cast<uint64_t*>(smem + sizeof(WarpRing<CH>) * EM_WARPS) + wid * RING;
+  W.scratch = reinterpret_cast<double*>(smem + sizeof(WarpRing<CH>) * EM_WARPS + EM_WARPS * RING * 8);
+  W.phase_bits = 0;
+  if ((threadIdx.x & 31u) == 0) {
+#pragma unroll
+    for (int s = 0; s < RING; ++s) mbar_init(&W.bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+}
+
+// operands of a row's epilogue, fetched while the row's columns stream
+struct RowOps {
+  double x0, x1, x2, x3;
+  uint32_t len;
+};
+template <int PHASE>
+__device__ __forceinline__ RowOps load_ops(const EmArgs& A, const Sell& S, uint32_t row) {
+  RowOps o;
+  o.x0 = o.x1 = o.x2 = o.x3 = 0.0;
+  o.len = LEN_LONG;
+  if (row < S.n_rows) {
+    o.len = __ldg(&S.len[row]);
+    if (PHASE == 1) {
+      o.x0 = __ldg(&A.c_cnt[row]);
+    } else if (PHASE == 2) {
+      o.x0 = A.theta[row];
+      o.x1 = __ldg(&A.prior[row]);
+      o.x2 = __ldg(&A.base[row]);
+      o.x3 = A.alpha[row];
+    }
+  }
+  return o;
+}
+
+template <int PHASE>
+__device__ __forceinline__ void row_finish(const EmArgs& A, uint32_t row, const RowOps& o, double acc,
+                                           double logNorm, double bias, P2Acc& pa) {
+  if (o.len == LEN_LONG) return;  // beyond the last row, or a long row (block path)
+  if (PHASE == 1) {
+    A.scale[row] = (acc <= MIN_EQ_W) ? 0.0 : o.x0 / acc;
+  } else if (PHASE == 2) {
+    const double th = o.x0, pr = o.x1;
+    double na = o.x2 + bias;
+    if (th > 0.0) na += th * acc;
+    if (na > ALPHA_CHECK_CUTOFF) pa.maxrel = fmax(pa.maxrel, fabs(o.x3 - na) / na);
+    A.alpha[row] = na;
+    const double ap = na + pr;
+    pa.sum += ap;
+    A.theta[row] = A.vbem ? ((ap > DIGAMMA_MIN) ? exp(digamma_pos(ap) - logNorm) : 0.0) : na;
+  } else {
+    const uint32_t t = __ldg(&A.row_tid[row]);
+    const double th = A.theta[t];
+    double na = __ldg(&A.base[t]);
+    if (th > 0.0) na += th * acc;
+    A.part_out[t] = na;
+  }
+}
+
+// static stream range of one warp in one matrix (the matrices never change)
+struct WarpRange {
+  uint32_t s0, s1, cbeg, cend;
+};
+__device__ __forceinline__ WarpRange load_range(const Sell& S, uint32_t gwarp) {
+  WarpRange r;
+  r.s0 = __ldg(&S.warp_begin[gwarp]);
+  r.s1 = __ldg(&S.warp_begin[gwarp + 1]);
+  r.cbeg = __ldg(&S.slice_ptr[r.s0]);
+  r.cend = __ldg(&S.slice_ptr[r.s1]);
+  return r;
+}
+template <int CH>
+__device__ __forceinline__ void ring_issue(const Sell& S, WarpCtx<CH>& W, const WarpRange& R, uint32_t k) {
+  if ((threadIdx.x & 31u) == 0) {
+    const uint32_t c = R.cbeg + k * CH;
+    const uint32_t cols = min((uint32_t)CH, R.cend - c);
+    const int st = k % RING;
+    mbar_arrive_expect_tx(&W.bars[st], cols * 384u);
+    bulk_g2s(W.ring->w[st], S.w + (size_t)c * 32u, cols * 256u, &W.bars[st]);
+    bulk_g2s(W.ring->idx[st], S.idx + (size_t)c * 32u, cols * 128u, &W.bars[st]);
+  }
+}
+// fill the ring with the first chunks of a phase.  The matrices are read-only, so this
+// may run BEFORE the grid barrier that precedes the phase: the stream then lands while
+// the grid synchronises and is never on the critical path.
+template <int CH>
+__device__ __forceinline__ void ring_prefetch(const Sell& S, WarpCtx<CH>& W, const WarpRange& R) {
+  const uint32_t nchunks = (R.cend - R.cbeg + CH - 1) / CH;
+#pragma unroll
+  for (int k = 0; k < RING; ++k)
+    if ((uint32_t)k < nchunks) ring_issue(S, W, R, k);
+}
+
+template <int PHASE, int CH>
+__device__ __forceinline__ void run_phase(const EmArgs& A, WarpCtx<CH>& W, const WarpRange& R,
+                                          uint32_t bid, uint32_t nblk, double logNorm, double bias,
+                                          P2Acc& pa) {
+  const Sell& S = (PHASE == 1) ? A.cm : A.tm;
+  // theta / scale are rewritten by other blocks inside the persistent kernel: plain
+  // coherent loads only, never ld.global.nc.
+  const double* gsrc = (PHASE == 1) ? A.theta : A.scale;
+  const bool em_nan_guard = (PHASE == 1) && !A.vbem;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t s0 = R.s0, s1 = R.s1;
+  if (s1 > s0) {
+    const uint32_t cbeg = R.cbeg, cend = R.cend;
+    const uint32_t nchunks = (cend - cbeg + CH - 1) / CH;
+    auto issue = [&](uint32_t k) { ring_issue(S, W, R, k); };
+    // slice boundaries, 32 at a time: lane l holds the end column of slice sbase+l
+    uint32_t sbase = s0;
+    uint32_t sp = (s0 + lane < s1) ? __ldg(&S.slice_ptr[s0 + lane + 1]) : cend;
+    uint32_t s = s0;
+    uint32_t slice_end = __shfl_sync(0xffffffffu, sp, 0);
+    RowOps ops = load_ops<PHASE>(A, S, s * 32u + lane);
+    double acc = 0.0;
+    auto next_slice = [&]() {
+      row_finish<PHASE>(A, s * 32u + lane, ops, acc, logNorm, bias, pa);
+      ++s;
+      acc = 0.0;
+      if (s < s1) {
+        if (s - sbase == 32u) {
+          sbase = s;
+          sp = (s + lane < s1) ? __ldg(&S.slice_ptr[s + lane + 1]) : cend;
+        }
+        slice_end = __shfl_sync(0xffffffffu, sp, (int)(s - sbase));
+        ops = load_ops<PHASE>(A, S, s * 32u + lane);
+      }
+    };
+    for (uint32_t k = 0; k < nchunks; ++k) {
+      const int st = k % RING;
+      mbar_wait(&W.bars[st], (W.phase_bits >> st) & 1u);
+      W.phase_bits ^= (1u << st);
+      const uint32_t* sidx = W.ring->idx[st] + lane;
+      const double* sw = W.ring->w[st] + lane;
+      const uint32_t c0 = cbeg + k * CH;
+      const uint32_t cstop = min(cend, c0 + CH);
+      uint32_t col = c0;
+      while (col < cstop) {
+        while (col == slice_end && s < s1) next_slice();  // (possibly zero-width slices)
+        const uint32_t n = min(slice_end, cstop) - col;
+        const uint32_t l0 = col - c0;
+        uint32_t j = 0;
+        for (; j + 4 <= n; j += 4) {
+          const uint32_t o = (l0 + j) * 32u;
+          const double g0 = gsrc[sidx[o]], g1 = gsrc[sidx[o + 32]];
+          const double g2 = gsrc[sidx[o + 64]], g3 = gsrc[sidx[o + 96]];
+          double v0 = g0 * sw[o], v1 = g1 * sw[o + 32], v2 = g2 * sw[o + 64], v3 = g3 * sw[o + 96];
+          if (em_nan_guard) {
+            if (isnan(v0)) v0 = 0.0;
+            if (isnan(v1)) v1 = 0.0;
+            if (isnan(v2)) v2 = 0.0;
+            if (isnan(v3)) v3 = 0.0;
+          }
+          acc += v0; acc += v1; acc += v2; acc += v3;
+        }
+        for (; j < n; ++j) {
+          const uint32_t o = (l0 + j) * 32u;
+          double v = gsrc[sidx[o]] * sw[o];
+          if (em_nan_guard && isnan(v)) v = 0.0;
+          acc += v;
+        }
+        col += n;
+      }
+      __syncwarp();
+      if (k + RING < nchunks) issue(k + RING);
+    }
+    while (s < s1) next_slice();
+  }
+  // long rows: whole block per row, fixed-order tree reduction
+  for (uint32_t li = bid; li < S.n_long; li += nblk) {
+    const uint32_t r = __ldg(&S.long_rows[3 * li]);
+    const uint32_t b = __ldg(&S.long_rows[3 * li + 1]);
+    const uint32_t e = __ldg(&S.long_rows[3 * li + 2]);
+    double acc = 0.0;
+    for (uint32_t k = b + threadIdx.x; k < e; k += EM_THREADS) {
+      double v = gsrc[__ldg(&S.csr_idx[k])] * __ldg(&S.csr_w[k]);
+      if (em_nan_guard && isnan(v)) v = 0.0;
+      acc += v;
+    }
+    acc = block_reduce<false>(acc, W.scratch);
+    if (threadIdx.x == 0) {
+      RowOps o = load_ops<PHASE>(A, S, r);
+      o.len = 0;  // force the epilogue for this long row
+      row_finish<PHASE>(A, r, o, acc, logNorm, bias, pa);
+    }
+    __syncthreads();
+  }
+}
+
+// alphaSum of the iteration input, from the per-block partials of the previous P2
+__device__ __forceinline__ double sum_partials(const double* part, uint32_t n, double extra,
+                                               double* scratch) {
+  double acc = 0.0;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) acc += __ldcg(&part[i]);
+  acc = block_reduce<false>(acc, scratch);
+  return acc + extra;
+}
+
+__device__ __forceinline__ void p2_finish(const EmArgs& A, double* scratch, P2Acc& pa,
+                                          uint32_t par) {
+  double bs = block_reduce<false>(pa.sum, scratch);
+  double bm = block_reduce<true>(pa.maxrel, scratch);
+  if (threadIdx.x == 0) {
+    A.sum_partial[(size_t)par * gridDim.x + blockIdx.x] = bs;
+    if (bm > 0.0) atomicMax(&A.maxrel[par], (unsigned long long)__double_as_longlong(bm));
+  }
+}
+
+// ---- persistent cooperative kernel: the whole iteration loop, two grid barriers/iter
+template <int CH, int MINB>
+__global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent(const __grid_constant__ EmArgs A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  WarpCtx<CH> W;
+  warp_setup(W, smem);
+  double* scratch = W.scratch;
+  cg::grid_group grid = cg::this_grid();
+  const uint32_t bid = blockIdx.x, nblk = gridDim.x;
+  const uint32_t gwarp = bid * (EM_THREADS / 32) + (threadIdx.x >> 5);
+  const WarpRange R1 = load_range(A.cm, gwarp);
+  const WarpRange R2 = load_range(A.tm, gwarp);
+  uint32_t it = 0;
+  bool converged = false;
+  double logNorm = A.vbem ? digamma_pos(A.sum0) : 0.0;
+  ring_prefetch(A.cm, W, R1);
+  while (it < A.min_iter || (it < A.max_iter && !converged)) {
+    const uint32_t par = it & 1u;
+    if (bid == 0 && threadIdx.x == 0) A.maxrel[par] = 0ull;
+    P2Acc pa{0.0, 0.0};
+    run_phase<1, CH>(A, W, R1, bid, nblk, 0.0, 0.0, pa);
+    ring_prefetch(A.tm, W, R2);   // P2's stream lands during the grid barrier
+    grid.sync();
+    if (A.vbem && it > 0) {
+      // lagged logNorm: alphaSum of THIS iteration's input = partials written by the
+      // previous P2.  Any common factor in theta cancels in P1/P2.
+      logNorm = digamma_pos(sum_partials(A.sum_partial + (size_t)(par ^ 1u) * nblk, nblk,
+                                         A.inactive_sum, scratch));
+    }
+    const double bias = (!A.vbem && it == 0) ? 1.0 : 0.0;  // alphasPrime starts at 1.0 (:812,:821)
+    run_phase<2, CH>(A, W, R2, bid, nblk, logNorm, bias, pa);
+    ring_prefetch(A.cm, W, R1);   // next iteration's P1 stream (harmless if the loop ends)
+    p2_finish(A, scratch, pa, par);
+    grid.sync();
+    const double mr = __longlong_as_double((long long)__ldcg(&A.maxrel[par]));
+    converged = !(mr > A.tol);
+    ++it;
+  }
+  if (bid == 0 && threadIdx.x == 0) {
+    A.out[0] = it;
+    A.out[1] = converged ? 1u : 0u;
+    A.out[2] = (it - 1) & 1u;
+  }
+  // drain the speculative prefetch before the block (and its shared memory) retires
+  {
+    const uint32_t nchunks = (R1.cend - R1.cbeg + CH - 1) / CH;
+#pragma unroll
+    for (int k = 0; k < RING; ++k)
+      if ((uint32_t)k < nchunks) mbar_wait(&W.bars[k], (W.phase_bits >> k) & 1u);
+  }
+}
+
+// ---- one launch per phase (baseline variant; also the multi-GPU building blocks)
+template <int CH, int MINB>
+__global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p1(const __grid_constant__ EmArgs A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  WarpCtx<CH> W;
+  warp_setup(W, smem);
+  P2Acc pa{0.0, 0.0};
+  const WarpRange R = load_range(A.cm, blockIdx.x * (EM_THREADS / 32) + (threadIdx.x >> 5));
+  ring_prefetch(A.cm, W, R);
+  run_phase<1, CH>(A, W, R, blockIdx.x, gridDim.x, 0.0, 0.0, pa);
+}
+template <int CH, int MINB>
+__global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p2(const __grid_constant__ EmArgs A, uint32_t it) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  WarpCtx<CH> W;
+  warp_setup(W, smem);
+  double* scratch = W.scratch;
+  const uint32_t par = it & 1u;
+  double logNorm = 0.0;
+  if (A.vbem) {
+    if (it == 0) logNorm = digamma_pos(A.sum0);
+    else
+      logNorm = digamma_pos(sum_partials(A.sum_partial + (size_t)(par ^ 1u) * gridDim.x, gridDim.x,
+                                         A.inactive_sum, scratch));
+  }
+  const double bias = (!A.vbem && it == 0) ? 1.0 : 0.0;
+  P2Acc pa{0.0, 0.0};
+  const WarpRange R = load_range(A.tm, blockIdx.x * (EM_THREADS / 32) + (threadIdx.x >> 5));
+  ring_prefetch(A.tm, W, R);
+  run_phase<2, CH>(A, W, R, blockIdx.x, gridDim.x, logNorm, bias, pa);
+  p2_finish(A, scratch, pa, par);
+}
+template <int CH, int MINB>
+__global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p2_partial(const __grid_constant__ EmArgs A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  WarpCtx<CH> W;
+  warp_setup(W, smem);
+  P2Acc pa{0.0, 0.0};
+  const WarpRange R = load_range(A.tm, blockIdx.x * (EM_THREADS / 32) + (threadIdx.x >> 5));
+  ring_prefetch(A.tm, W, R);
+  run_phase<3, CH>(A, W, R, blockIdx.x, gridDim.x, 0.0, 0.0, pa);
+}
+
+}  // namespace sb
