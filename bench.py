@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- EM/VBEM iterations per second on BASELINE.json configs[1].
+
+Workload (config 2, the largest EM-only configuration; fits one GPU): synth_eq(seed=1):
+500 000 equivalence classes over 250 000 transcripts (nnz ~3.0 M, sum of counts ~20 M),
+VBEM (salmon's default), 1000 forced iterations per step (min_iter = max_iter = 1000).
+
+A "step" = one CollapsedEMOptimizer::optimize-equivalent run of 1000 iterations.
+  value : iterations / s with the class table resident in HBM (sb_em_run only),
+  e2e   : the same through sb_em_optimize with HOST buffers (pinned): H2D of the CSR
+          table + device-side preparation (combined weights, both layouts) + 1000
+          iterations + D2H of alpha, all inside the timed region.
+L2 is flushed (512 MB memset) before every timed step; inside a step the working set
+(~75 MB) is L2-resident by nature of the workload (the same table is swept 1000x).
+
+N > 1 (torchrun, one rank per GPU): weak scaling -- every rank holds its OWN 500k-class
+table (the eq-classes of its read shard) and alpha is all-reduced once per iteration.
+value = N x (iterations / s): 500k-class-shard iterations per second.
+
+--impl reference : the CPU path (oracle port, OpenMP over all host cores) on the same
+workload; each step is a bounded sample of iterations.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+os.environ.setdefault("OMP_PROC_BIND", "close")
+os.environ.setdefault("OMP_PLACES", "cores")
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+C2 = dict(C=500_000, M=250_000, total_count=20_000_000)
+ITERS_PER_STEP = 1000
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes_per_iter(eq, vbem=True):
+    """nnz*(4+8) + C*(8+8) + M*(8+8+8) [+ M*16 for VBEM's expTheta]."""
+    return eq.nnz * 12 + eq.n_classes * 16 + eq.n_txps * 24 + (eq.n_txps * 16 if vbem else 0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # samples under load = upper half of the observed clocks
+        hi = sorted(sm)[len(sm) // 2:]
+        return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+_CPU_BEST = {}
+
+
+def cpu_port_rate(eq, proj, eff, uniq, vbem, budget_s, threads):
+    """Times the CPU port (oracle) on a bounded number of iterations.
+
+    The port mirrors the reference's decomposition (parallel_for over classes + CAS f64
+    adds).  On many-core hosts that decomposition is contention-bound, so the thread
+    count is chosen by a short probe over {all, 64, 32, 16, 8} cores and the serial
+    restatement (the reference's -p); the best one is what gets timed and reported."""
+    import oracle_lib as O
+    from salmon_b200 import default_params
+
+    def run(n, t):
+        p = default_params(use_vbem=vbem, min_iter=n, max_iter=n)
+        t0 = time.perf_counter()
+        if t == 0:
+            O.em_optimize(eq, proj, eff, uniq, p)
+        else:
+            O.em_optimize(eq, proj, eff, uniq, p, mt=True, n_threads=t)
+        return time.perf_counter() - t0
+
+    def per_iter(t):
+        run(2, t)                      # warm-up (thread pool, page faults)
+        a, b = run(3, t), run(9, t)    # fixed serial setup cancels in the difference
+        return max((b - a) / 6.0, 1e-6), a
+
+    key = (eq.n_classes, eq.nnz, vbem, threads)
+    if key not in _CPU_BEST:
+        cands = sorted({t for t in (threads, 64, 32, 16, 8) if 0 < t <= threads}, reverse=True) + [0]
+        best = None
+        for t in cands:
+            pi, a = per_iter(t)
+            if best is None or pi < best[1]:
+                best = (t, pi, a)
+        _CPU_BEST[key] = best
+    t, pi, a = _CPU_BEST[key]
+    n = int(max(20, min(ITERS_PER_STEP, budget_s / pi)))
+    dtn = run(n, t)
+    setup = max(a - 3 * pi, 0.0)
+    return n / max(dtn - setup, 1e-9), n, (t if t else 1)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--em", action="store_true", help="plain EM instead of VBEM (not the headline)")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    vbem = 0 if args.em else 1
+    W = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    from salmon_b200.synth import synth_eq
+    ncores = os.cpu_count() or 1
+    workload = (f"configs[1] EM/VBEM-only: synth_eq(seed=1) C={C2['C']} classes, M={C2['M']} transcripts, "
+                f"{ITERS_PER_STEP} forced {'VBEM' if vbem else 'EM'} iterations per step")
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        eq, proj, eff, uniq = synth_eq(seed=1, **C2)
+        rates, sample_iters = [], 0
+        budget = max(2.0, min(args.cpu_budget, 120.0 / max(1, args.steps + args.warmup)))
+        for i in range(args.warmup + args.steps):
+            r, n, used = cpu_port_rate(eq, proj, eff, uniq, vbem, budget, ncores)
+            if i >= args.warmup:
+                rates.append(r); sample_iters = n
+        val = statistics.mean(rates)
+        line = {
+            "impl": "reference", "metric": "EM iters/s", "value": val, "unit": "iters/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * ITERS_PER_STEP / val, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "note": "reference cannot be built here (Boost/oneTBB/pufferfish "
+                       "absent); CPU arm = in-repo restatement parallelised like the reference (parallel_for "
+                       "over classes + CAS f64 adds), OpenMP for oneTBB"},
+            "cpu_baseline": {"value": val, "unit": "iters/s", "cores": used, "kind": "port", "host_cores": ncores,
+                             "sample": f"{sample_iters} iterations of the same workload per step; thread count "
+                                       f"chosen by probe (best of all/64/32/16/8/serial)"},
+            "e2e": {"value": val, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    from salmon_b200 import EMContext, default_params, _capi
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world)
+    ctx = EMContext(local)
+    # per-rank class table (weak scaling): the eq-classes of this rank's read shard
+    eq, proj, eff, uniq = synth_eq(seed=1 + rank, **C2)
+    if world > 1:
+        import torch
+        # end-of-mapping reductions: per-transcript masses are global
+        tp = torch.from_numpy(proj).cuda(); dist.all_reduce(tp); proj = tp.cpu().numpy()
+        tu = torch.from_numpy(uniq.astype(np.int64)).cuda(); dist.all_reduce(tu); uniq = tu.cpu().numpy().astype(np.uint64)
+        te = torch.from_numpy(eff).cuda(); dist.broadcast(te, 0); eff = te.cpu().numpy()
+        uid = [_capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+    for a in (eq.off, eq.tids, eq.weights, eq.counts, proj, eff, uniq):
+        _capi.pin(a)
+    p = default_params(use_vbem=vbem, min_iter=ITERS_PER_STEP, max_iter=ITERS_PER_STEP)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+            import torch
+            torch.cuda.synchronize()
+
+    # ---- device-resident: sb_em_run only
+    ctx.upload(eq, proj, eff, uniq)
+    ctx.prepare(p)
+    for _ in range(W):
+        ctx.flush_l2(); barrier(); ctx.run()
+    sampler = ClockSampler(local); sampler.start()
+    run_ms, loop_ms, launches, loop_launches = [], [], 0, 0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        barrier()
+        st = ctx.run()
+        run_ms.append(st.run_ms); loop_ms.append(st.loop_kernel_ms)
+        launches += st.gpu_launches; loop_launches += st.loop_kernel_launches
+    barrier()
+    wall_resident = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    alpha, alpha_sum, ok = ctx.download()
+    assert ok and st.iters == ITERS_PER_STEP
+    # every valid class hands out exactly its count (size-independent sanity inside the bench)
+    tot_counts = float(eq.counts.sum())
+    if world > 1:
+        import torch
+        tc = torch.tensor([tot_counts], dtype=torch.float64).cuda(); dist.all_reduce(tc); tot_counts = tc.item()
+    assert abs(alpha_sum - tot_counts) / tot_counts < 1e-9, (alpha_sum, tot_counts)
+
+    # ---- end to end: sb_em_optimize, host buffers in/out
+    e2e_ms = []
+    for i in range(2 + args.steps):
+        ctx.flush_l2()
+        barrier()
+        t0 = time.perf_counter()
+        a2, st2, ok2 = ctx.optimize(eq, p, proj, eff, uniq)
+        dt = time.perf_counter() - t0
+        if i >= 2:
+            e2e_ms.append(dt * 1e3)
+    h2d = eq.off.nbytes + eq.tids.nbytes + eq.weights.nbytes + eq.counts.nbytes + proj.nbytes + eff.nbytes + uniq.nbytes
+    d2h = alpha.nbytes
+
+    def reduce_max(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    step_ms = reduce_max(statistics.mean(run_ms))          # device time (CUDA events), max over ranks
+    e2e_step_ms = reduce_max(statistics.mean(e2e_ms))
+    loop_step_ms = reduce_max(statistics.mean(loop_ms))
+    value = world * ITERS_PER_STEP / (step_ms / 1e3)
+    e2e_value = world * ITERS_PER_STEP / (e2e_step_ms / 1e3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    b_iter = algorithmic_bytes_per_iter(eq, bool(vbem))
+    kern_iters_per_launch = ITERS_PER_STEP if (world == 1) else 1
+    avg_launch_ms = loop_step_ms if world == 1 else loop_step_ms / ITERS_PER_STEP
+    achieved = b_iter * kern_iters_per_launch / (avg_launch_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    cpu_val, cpu_n, cpu_used = cpu_port_rate(eq, proj, eff, uniq, vbem, args.cpu_budget, ncores) if world == 1 else (None, 0, 0)
+    line = {
+        "metric": "EM iters/s", "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
+        "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "iters_per_step": ITERS_PER_STEP,
+                   "per_gpu_classes": eq.n_classes, "per_gpu_nnz": eq.nnz, "transcripts": eq.n_txps,
+                   "l2": "flushed (memset > 2x L2) before every timed step; inside a step the table is re-swept "
+                         "1000x and stays L2-resident, as in production",
+                   "parallelism": "1 GPU" if world == 1 else
+                   f"classes sharded over {world} GPUs (own table per rank), alpha NCCL all-reduced per iteration; "
+                   f"value = {world} x iterations/s",
+                   "kernel": "persistent cooperative k_em_persistent (1 launch per step)" if world == 1 else
+                   "k_em_p1 + k_em_p2_partial + ncclAllReduce + k_em_update per iteration",
+                   "wall_s_resident_loop": wall_resident},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_step_ms, "api": "sb_em_optimize (C ABI, pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_iteration": b_iter,
+                     "kernel": "k_em_persistent" if world == 1 else "k_em_p1+k_em_p2_partial+k_em_update",
+                     "avg_launch_ms": avg_launch_ms, "iterations_per_launch": kern_iters_per_launch,
+                     "note": "data is L2-resident by design, so DRAM traffic is far below the algorithmic bytes"},
+    }
+    if cpu_val is not None:
+        line["cpu_baseline"] = {"value": cpu_val, "unit": "iters/s", "cores": cpu_used, "kind": "port",
+                                "host_cores": ncores,
+                                "sample": f"{cpu_n} iterations of the same workload; thread count chosen by probe "
+                                          f"(best of all/64/32/16/8/serial)"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

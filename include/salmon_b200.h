@@ -117,6 +117,11 @@ int sb_em_download(sb_em_ctx* ctx, double* alpha_out, sb_em_stats* stats);
 /* Debug/parity taps (tests): combinedWeights (:862-870) and validity flags. */
 int sb_em_get_combined(sb_em_ctx* ctx, double* combined_out, uint8_t* valid_out);
 
+/* Debug: per-warp phase timestamps (ns) of one iteration of the last persistent run:
+ * out[n_warps*8] = {P1 start, P1 end, barrier1 end, P2 start, P2 end, reduce end, barrier2 end, -}.
+ * Returns the number of warps (call with out=NULL to size the buffer). */
+int sb_em_debug_timeline(sb_em_ctx* ctx, uint64_t* out, uint32_t iteration);
+
 /* Tuning knobs (not part of the reference contract): kernel variant.
  * key: "variant" (0 = multi-kernel per iteration, 1 = persistent cooperative),
  *      "blocks_per_sm", "flush_l2_mb". */
@@ -132,6 +137,11 @@ int sb_em_comm_destroy(sb_em_ctx* ctx);
 
 /* Write a buffer larger than L2 (bench hygiene between timed steps). */
 int sb_flush_l2(sb_em_ctx* ctx);
+
+/* Page-lock / unlock a host buffer the caller will pass to sb_em_optimize / sb_em_upload
+ * repeatedly (cudaHostRegister), so the host->device copies run at full PCIe rate. */
+int sb_host_register(void* ptr, size_t bytes);
+int sb_host_unregister(void* ptr);
 
 #ifdef __cplusplus
 }

@@ -88,10 +88,13 @@ SYMBOLS = {
     "sb_em_download": (C.c_int, [_P, _P, C.POINTER(sb_em_stats)]),
     "sb_em_get_combined": (C.c_int, [_P, _P, _P]),
     "sb_em_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "sb_em_debug_timeline": (C.c_int, [_P, _P, C.c_uint32]),
     "sb_nccl_unique_id": (C.c_int, [_P]),
     "sb_em_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "sb_em_comm_destroy": (C.c_int, [_P]),
     "sb_flush_l2": (C.c_int, [_P]),
+    "sb_host_register": (C.c_int, [_P, C.c_size_t]),
+    "sb_host_unregister": (C.c_int, [_P]),
 }
 
 _lib = None
@@ -236,12 +239,30 @@ class EMContext:
         _check(self.lib.sb_em_get_combined(self.h, cw.ctypes.data, valid.ctypes.data), "sb_em_get_combined")
         return cw, valid
 
+    def arm_timeline(self, iteration: int) -> int:
+        return _check(self.lib.sb_em_debug_timeline(self.h, None, iteration), "sb_em_debug_timeline")
+
+    def read_timeline(self, n_warps: int):
+        out = np.zeros((n_warps, 8), dtype=np.uint64)
+        _check(self.lib.sb_em_debug_timeline(self.h, out.ctypes.data, 0), "sb_em_debug_timeline")
+        return out
+
     def flush_l2(self):
         _check(self.lib.sb_flush_l2(self.h), "sb_flush_l2")
 
     def comm_init(self, rank: int, nranks: int, uid: bytes):
         buf = C.create_string_buffer(uid, 128)
         _check(self.lib.sb_em_comm_init(self.h, rank, nranks, buf), "sb_em_comm_init")
+
+
+def pin(arr: np.ndarray):
+    """Page-lock a numpy array in place (returns the array)."""
+    _check(load().sb_host_register(arr.ctypes.data, arr.nbytes), "sb_host_register")
+    return arr
+
+
+def unpin(arr: np.ndarray):
+    _check(load().sb_host_unregister(arr.ctypes.data), "sb_host_unregister")
 
 
 def nccl_unique_id() -> bytes:

@@ -248,7 +248,8 @@ __global__ void k_remap(uint32_t n, const uint32_t* __restrict__ src,
 
 // ---- CSR -> SELL-32 -------------------------------------------------------------
 // one warp per slice: row lengths, slice width (= max non-long length)
-__global__ void k_sell_widths(uint32_t n_rows, uint32_t n_slices, const uint32_t* __restrict__ rowperm,
+__global__ void k_sell_widths(uint32_t n_rows, uint32_t n_slices, uint32_t lmax,
+                              const uint32_t* __restrict__ rowperm,
                               const uint32_t* __restrict__ csr_off, uint16_t* __restrict__ len16,
                               uint32_t* __restrict__ width, uint32_t* __restrict__ n_long) {
   const uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -259,7 +260,7 @@ __global__ void k_sell_widths(uint32_t n_rows, uint32_t n_slices, const uint32_t
   if (row < n_rows) {
     const uint32_t cr = rowperm ? rowperm[row] : row;
     len = csr_off[cr + 1] - csr_off[cr];
-    if (len > (uint32_t)LMAX) {
+    if (len > lmax) {
       len16[row] = LEN_LONG;
       atomicAdd(n_long, 1u);
       len = 0;
@@ -437,15 +438,29 @@ extern "C" void sb_em_default_params(sb_em_params* p) {
   p->max_iter = 10000;
 }
 
+// Grow-only device buffers: capacity is remembered per pointer slot so that repeated
+// optimize() calls on same-sized problems never touch cudaMalloc/cudaFree again.
+#include <unordered_map>
+static std::unordered_map<void**, size_t>& cap_table() {
+  static thread_local std::unordered_map<void**, size_t> t;
+  return t;
+}
 template <typename T>
 static int dev_alloc(T** p, size_t n) {
-  if (*p) { cudaFree(*p); *p = nullptr; }
   if (n == 0) n = 1;
-  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+  const size_t bytes = n * sizeof(T);
+  auto& caps = cap_table();
+  auto it = caps.find((void**)p);
+  if (*p && it != caps.end() && it->second >= bytes) return SB_OK;
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  const size_t want = bytes + bytes / 16 + 256;  // a little slack against small size changes
+  cudaError_t e = cudaMalloc((void**)p, want);
   if (e != cudaSuccess) {
-    set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+    caps.erase((void**)p);
     return SB_ERR_NOMEM;
   }
+  caps[(void**)p] = want;
   return SB_OK;
 }
 #define SB_TRY(x) do { int _r = (x); if (_r != SB_OK) return _r; } while (0)
@@ -482,6 +497,7 @@ static void free_sell(SellDev& m) {
   for (void** p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
+    cap_table().erase(p);
   }
 }
 static void free_all(sb_em_ctx* c) {
@@ -499,10 +515,12 @@ static void free_all(sb_em_ctx* c) {
                    (void**)&c->d_sort_keys2, (void**)&c->d_sort_vals2, (void**)&c->d_tmp,
                    (void**)&c->d_sum_partial, (void**)&c->d_flush, (void**)&c->d_part,
                    (void**)&c->d_part_red, (void**)&c->r_alpha, (void**)&c->r_theta,
-                   (void**)&c->r_prior, (void**)&c->r_base, (void**)&c->r_alpha0};
+                   (void**)&c->r_prior, (void**)&c->r_base, (void**)&c->r_alpha0,
+                   (void**)&c->d_dbg};
   for (void** p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
+    cap_table().erase(p);
   }
   free_sell(c->cm);
   free_sell(c->tm);
@@ -526,7 +544,12 @@ extern "C" int sb_em_set_option(sb_em_ctx* c, const char* key, int64_t value) {
     if (value < 0 || value >= N_KERNEL_SETS) { set_error("config out of range"); return SB_ERR_INVALID; }
     c->config = (int)value;
     c->prepared = false;
-  } else if (!strcmp(key, "overhead_p1")) { c->ovh_p1 = (int)value; c->prepared = false; }
+  } else if (!strcmp(key, "lmax")) {
+    if (value < 1 || value > 60000) { set_error("lmax out of range"); return SB_ERR_INVALID; }
+    c->lmax = (int)value; c->prepared = false;
+  } else if (!strcmp(key, "l2_keep_cm")) { c->keep_cm = (int)value; }
+  else if (!strcmp(key, "l2_keep_tm")) { c->keep_tm = (int)value; }
+  else if (!strcmp(key, "overhead_p1")) { c->ovh_p1 = (int)value; c->prepared = false; }
   else if (!strcmp(key, "overhead_p2")) { c->ovh_p2 = (int)value; c->prepared = false; }
   else { set_error("unknown option '%s'", key); return SB_ERR_INVALID; }
   return SB_OK;
@@ -622,7 +645,7 @@ static int build_sell(sb_em_ctx* c, SellDev& m, uint32_t n_rows, const uint32_t*
   SB_CUDA(cudaMemsetAsync(d_nlong, 0, 8, st));
   SB_CUDA(cudaMemsetAsync(m.width, 0, ((size_t)m.n_slices + 1) * 4, st));
   if (m.n_slices) {
-    k_sell_widths<<<nblk(m.n_slices, 8), 256, 0, st>>>(n_rows, m.n_slices, rowperm, csr_off, m.len,
+    k_sell_widths<<<nblk(m.n_slices, 8), 256, 0, st>>>(n_rows, m.n_slices, (uint32_t)c->lmax, rowperm, csr_off, m.len,
                                                        m.width, d_nlong);
     c->launches++;
   }
@@ -650,15 +673,22 @@ static int build_sell(sb_em_ctx* c, SellDev& m, uint32_t n_rows, const uint32_t*
   k_warp_ranges<<<nblk(n_warps + 1, 256), 256, 0, st>>>(m.n_slices, m.slice_ptr, overhead, n_warps,
                                                         m.warp_begin);
   c->launches++;
-  if (m.n_long > 1) {
-    // every long row is reduced independently with a fixed tree: list order does not
-    // affect results; sorted anyway so that block assignment is reproducible.
+  m.n_block = 0;
+  if (m.n_long > 0) {
+    // every long row is reduced independently with a fixed tree, so the list order does
+    // not affect results.  Longest first: the first n_block rows (> LWARP entries) take
+    // the block path, the rest are dealt round-robin to warps (longest-processing-time).
     std::vector<uint32_t> h((size_t)3 * m.n_long);
     SB_CUDA(cudaMemcpyAsync(h.data(), m.long_rows, h.size() * 4, cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
     std::vector<uint32_t> ord(m.n_long);
     for (uint32_t i = 0; i < m.n_long; ++i) ord[i] = i;
-    std::sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) { return h[3 * x] < h[3 * y]; });
+    std::sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) {
+      const uint32_t lx = h[3 * x + 2] - h[3 * x + 1], ly = h[3 * y + 2] - h[3 * y + 1];
+      return lx != ly ? lx > ly : h[3 * x] < h[3 * y];
+    });
+    for (uint32_t i = 0; i < m.n_long; ++i)
+      if (h[3 * ord[i] + 2] - h[3 * ord[i] + 1] > (uint32_t)LWARP) m.n_block = i + 1;
     std::vector<uint32_t> h2(h.size());
     for (uint32_t i = 0; i < m.n_long; ++i)
       for (int k = 0; k < 3; ++k) h2[3 * i + k] = h[3 * ord[i] + k];
@@ -883,6 +913,8 @@ static Sell sell_view(const SellDev& m) {
   s.slice_ptr = m.slice_ptr; s.len = m.len; s.idx = m.idx; s.w = m.w; s.warp_begin = m.warp_begin;
   s.long_rows = m.long_rows; s.csr_idx = m.csr_idx; s.csr_w = m.csr_w;
   s.n_rows = m.n_rows; s.n_slices = m.n_slices; s.n_long = m.n_long;
+  s.n_block = m.n_block;
+  s.keep_pct = 100;
   return s;
 }
 
@@ -890,6 +922,8 @@ static void fill_args(sb_em_ctx* c, EmArgs& A, bool row_space) {
   memset(&A, 0, sizeof(A));
   A.cm = sell_view(c->cm);
   A.tm = sell_view(c->tm);
+  A.cm.keep_pct = (uint32_t)c->keep_cm;
+  A.tm.keep_pct = (uint32_t)c->keep_tm;
   A.c_cnt = c->d_cnt; A.scale = c->d_scale;
   if (row_space) {
     A.alpha = c->r_alpha; A.theta = c->r_theta; A.prior = c->r_prior; A.base = c->r_base;
@@ -904,6 +938,8 @@ static void fill_args(sb_em_ctx* c, EmArgs& A, bool row_space) {
   A.tol = c->params.tol; A.min_iter = c->params.min_iter; A.max_iter = c->params.max_iter;
   A.vbem = c->params.use_vbem;
   A.out = (uint32_t*)(c->d_scalars + 32);
+  A.dbg = c->d_dbg;
+  A.dbg_it = c->dbg_it;
 }
 
 // ---------------------------------------------------------------------------
@@ -1182,4 +1218,33 @@ extern "C" int sb_flush_l2(sb_em_ctx* c) {
   SB_CUDA(cudaMemsetAsync(c->d_flush, (int)(c->flush_ctr++ & 0xff), bytes, c->stream));
   SB_CUDA(cudaStreamSynchronize(c->stream));
   return SB_OK;
+}
+
+extern "C" int sb_host_register(void* ptr, size_t bytes) {
+  if (!ptr || !bytes) { set_error("null argument"); return SB_ERR_INVALID; }
+  if (sb_device_count() <= 0) { set_error("no CUDA device available"); return SB_ERR_NO_DEVICE; }
+  SB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return SB_OK;
+}
+extern "C" int sb_host_unregister(void* ptr) {
+  if (!ptr) { set_error("null argument"); return SB_ERR_INVALID; }
+  SB_CUDA(cudaHostUnregister(ptr));
+  return SB_OK;
+}
+
+extern "C" int sb_em_debug_timeline(sb_em_ctx* c, uint64_t* out, uint32_t iteration) {
+  if (!c) { set_error("null argument"); return SB_ERR_INVALID; }
+  if (!c->prepared) { set_error("not prepared"); return SB_ERR_STATE; }
+  SB_CUDA(cudaSetDevice(c->device));
+  const uint32_t n_warps = c->grid * (EM_THREADS / 32);
+  if (!out) {
+    // arm: the next sb_em_run records iteration `iteration`
+    SB_TRY(dev_alloc(&c->d_dbg, (size_t)n_warps * 8));
+    SB_CUDA(cudaMemset(c->d_dbg, 0, (size_t)n_warps * 64));
+    c->dbg_it = iteration;
+    return (int)n_warps;
+  }
+  if (!c->d_dbg) { set_error("timeline not armed"); return SB_ERR_STATE; }
+  SB_CUDA(cudaMemcpy(out, c->d_dbg, (size_t)n_warps * 64, cudaMemcpyDeviceToHost));
+  return (int)n_warps;
 }

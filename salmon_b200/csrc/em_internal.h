@@ -9,7 +9,7 @@ namespace sb {
 
 // Device-side owner of one SELL-32 matrix (see em_kernels.cuh: struct Sell).
 struct SellDev {
-  uint32_t n_rows = 0, n_slices = 0, n_cols = 0, n_long = 0;
+  uint32_t n_rows = 0, n_slices = 0, n_cols = 0, n_long = 0, n_block = 0;
   uint32_t* slice_ptr = nullptr;
   uint32_t* width = nullptr;
   uint16_t* len = nullptr;
@@ -33,9 +33,11 @@ struct sb_em_ctx {
   // options
   int variant = 1;        // 1 = persistent cooperative kernel, 0 = one launch per phase
   int blocks_per_sm = 0;  // 0 = as many as fit
-  int config = 0;         // kernel configuration (tile/threads/stages), see kernel_set()
+  int config = 1;         // kernel configuration (tile/threads/stages), see kernel_set()
   int occ = 0;
-  int ovh_p1 = 3, ovh_p2 = 12;  // per-slice epilogue cost (in columns) for the work split
+  int ovh_p1 = 3, ovh_p2 = 12;
+  int lmax = 96;                    // longest row kept on the lane-per-row SELL path
+  int keep_cm = 100, keep_tm = 30;  // % of stream chunks pinned in L2 (evict_last)  // per-slice epilogue cost (in columns) for the work split
 
   // problem
   uint64_t C = 0, nnz = 0;
@@ -101,6 +103,10 @@ struct sb_em_ctx {
   void* nccl_comm = nullptr;
   double* d_part = nullptr;       // per-transcript partial alpha' (send)
   double* d_part_red = nullptr;   // all-reduced (recv)
+
+  // debug timeline
+  unsigned long long* d_dbg = nullptr;
+  uint32_t dbg_it = 0;
 
   // L2 flush
   void* d_flush = nullptr;

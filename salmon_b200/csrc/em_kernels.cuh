@@ -25,7 +25,8 @@
 namespace sb {
 namespace cg = cooperative_groups;
 
-constexpr int LMAX = 256;                    // rows longer than this take the block path
+constexpr int LMAX_DEFAULT = 96;             // rows longer than this leave the lane-per-row SELL path
+constexpr int LWARP = 2048;                  // ... and are reduced by one warp (<= LWARP) or one block
 constexpr int SELL_GROUP = 1024;             // rows per length-bucketing group
 constexpr int EM_THREADS = 256;
 constexpr double DIGAMMA_MIN = 1e-10;        // CollapsedEMOptimizer.cpp:43
@@ -45,6 +46,8 @@ struct Sell {
   const uint32_t* csr_idx;
   const double* csr_w;
   uint32_t n_rows, n_slices, n_long;
+  uint32_t n_block;            // the first n_block long rows (longest first) take the block path
+  uint32_t keep_pct;           // % of stream chunks loaded with L2 evict_last (rest evict_first)
 };
 
 struct EmArgs {
@@ -65,7 +68,15 @@ struct EmArgs {
   uint32_t min_iter, max_iter;
   int vbem;
   uint32_t* out;                // [0]=iters [1]=converged [2]=maxrel slot
+  unsigned long long* dbg;      // optional [n_warps*8] phase timestamps (ns) of iteration dbg_it
+  uint32_t dbg_it;
 };
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 struct P2Acc {
   double sum;     // sum of (alpha' + prior) over my rows
@@ -84,7 +95,7 @@ struct __align__(128) WarpRing {
 };
 constexpr int EM_WARPS = EM_THREADS / 32;
 template <int CH>
-constexpr size_t em_smem() { return sizeof(WarpRing<CH>) * EM_WARPS + EM_WARPS * RING * 8 + 32 * 8; }
+constexpr size_t em_smem() { return sizeof(WarpRing<CH>) * EM_WARPS + EM_WARPS * RING * 8 + 40 * 8; }
 
 template <int CH>
 struct WarpCtx {
@@ -92,6 +103,7 @@ struct WarpCtx {
   uint64_t* bars;        // [RING]
   uint32_t phase_bits;   // mbarrier parity per stage
   double* scratch;       // block scratch (32 doubles)
+  unsigned long long* dbg;  // optional: timestamp after the SELL part of a phase
 };
 
 template <int CH>
@@ -101,6 +113,7 @@ __device__ __forceinline__ void warp_setup(WarpCtx<CH>& W, unsigned char* smem) 
   W.bars = reinterpret_cast<uint64_t*>(smem + sizeof(WarpRing<CH>) * EM_WARPS) + wid * RING;
   W.scratch = reinterpret_cast<double*>(smem + sizeof(WarpRing<CH>) * EM_WARPS + EM_WARPS * RING * 8);
   W.phase_bits = 0;
+  W.dbg = nullptr;
   if ((threadIdx.x & 31u) == 0) {
 #pragma unroll
     for (int s = 0; s < RING; ++s) mbar_init(&W.bars[s], 1);
@@ -175,9 +188,13 @@ __device__ __forceinline__ void ring_issue(const Sell& S, WarpCtx<CH>& W, const 
     const uint32_t c = R.cbeg + k * CH;
     const uint32_t cols = min((uint32_t)CH, R.cend - c);
     const int st = k % RING;
+    // The two layouts together exceed what the L2 keeps under a cyclic sweep; pin a fixed
+    // pseudo-random subset of chunks (evict_last) and let the rest stream (evict_first).
+    const bool keep = (((c / CH) * 2654435761u) >> 16) % 100u < S.keep_pct;
+    const uint64_t pol = keep ? l2_policy_evict_last() : l2_policy_evict_first();
     mbar_arrive_expect_tx(&W.bars[st], cols * 384u);
-    bulk_g2s(W.ring->w[st], S.w + (size_t)c * 32u, cols * 256u, &W.bars[st]);
-    bulk_g2s(W.ring->idx[st], S.idx + (size_t)c * 32u, cols * 128u, &W.bars[st]);
+    bulk_g2s_hint(W.ring->w[st], S.w + (size_t)c * 32u, cols * 256u, &W.bars[st], pol);
+    bulk_g2s_hint(W.ring->idx[st], S.idx + (size_t)c * 32u, cols * 128u, &W.bars[st], pol);
   }
 }
 // fill the ring with the first chunks of a phase.  The matrices are read-only, so this
@@ -266,8 +283,9 @@ __device__ __forceinline__ void run_phase(const EmArgs& A, WarpCtx<CH>& W, const
     }
     while (s < s1) next_slice();
   }
-  // long rows: whole block per row, fixed-order tree reduction
-  for (uint32_t li = bid; li < S.n_long; li += nblk) {
+  if (W.dbg && lane == 0) *W.dbg = gtime_ns();
+  // very long rows: whole block per row, fixed-order tree reduction
+  for (uint32_t li = bid; li < S.n_block; li += nblk) {
     const uint32_t r = __ldg(&S.long_rows[3 * li]);
     const uint32_t b = __ldg(&S.long_rows[3 * li + 1]);
     const uint32_t e = __ldg(&S.long_rows[3 * li + 2]);
@@ -285,6 +303,52 @@ __device__ __forceinline__ void run_phase(const EmArgs& A, WarpCtx<CH>& W, const
     }
     __syncthreads();
   }
+  // long rows (LMAX < len <= LWARP): one warp per row, lanes stride the CSR copy, fixed
+  // shuffle tree.  Sorted longest-first and dealt round-robin over all warps of the grid.
+  {
+    const uint32_t gw = bid * EM_WARPS + (threadIdx.x >> 5);
+    const uint32_t nw = nblk * EM_WARPS;
+    // lane k keeps the sum of the k-th row this warp reduced; the epilogues (digamma, exp)
+    // then run lane-parallel, 32 rows at a time.
+    uint32_t cnt = 0, myrow = 0xffffffffu;
+    double myacc = 0.0;
+    auto flush = [&]() {
+      if (myrow != 0xffffffffu) {
+        RowOps o = load_ops<PHASE>(A, S, myrow);
+        o.len = 0;  // force the epilogue for a long row
+        row_finish<PHASE>(A, myrow, o, myacc, logNorm, bias, pa);
+      }
+      myrow = 0xffffffffu;
+      cnt = 0;
+    };
+    for (uint32_t li = S.n_block + gw; li < S.n_long; li += nw) {
+      const uint32_t r = __ldg(&S.long_rows[3 * li]);
+      const uint32_t b = __ldg(&S.long_rows[3 * li + 1]);
+      const uint32_t e = __ldg(&S.long_rows[3 * li + 2]);
+      double a0 = 0.0, a1 = 0.0;
+      uint32_t k = b + lane;
+      for (; k + 32 < e; k += 64) {
+        const uint32_t i0 = __ldg(&S.csr_idx[k]), i1 = __ldg(&S.csr_idx[k + 32]);
+        double v0 = gsrc[i0] * __ldg(&S.csr_w[k]);
+        double v1 = gsrc[i1] * __ldg(&S.csr_w[k + 32]);
+        if (em_nan_guard) {
+          if (isnan(v0)) v0 = 0.0;
+          if (isnan(v1)) v1 = 0.0;
+        }
+        a0 += v0;
+        a1 += v1;
+      }
+      if (k < e) {
+        double v = gsrc[__ldg(&S.csr_idx[k])] * __ldg(&S.csr_w[k]);
+        if (em_nan_guard && isnan(v)) v = 0.0;
+        a0 += v;
+      }
+      const double acc = warp_sum(a0 + a1);
+      if (lane == cnt) { myacc = acc; myrow = r; }
+      if (++cnt == 32) flush();
+    }
+    flush();
+  }
 }
 
 // alphaSum of the iteration input, from the per-block partials of the previous P2
@@ -296,6 +360,20 @@ __device__ __forceinline__ double sum_partials(const double* part, uint32_t n, d
   return acc + extra;
 }
 
+// lagged logNorm: alphaSum of THIS iteration's input = the per-block partials written by
+// the previous P2 (complete since the last grid barrier / kernel boundary).  Any common
+// factor in theta cancels in P1/P2.  Warp 0 only; result in scratch[33].
+__device__ __forceinline__ void lag_lognorm_warp0(const EmArgs& A, uint32_t par, uint32_t nblk,
+                                                  double* scratch) {
+  if (threadIdx.x < 32) {
+    const double* part = A.sum_partial + (size_t)(par ^ 1u) * nblk;
+    double acc = 0.0;
+    for (uint32_t i = threadIdx.x; i < nblk; i += 32) acc += __ldcg(&part[i]);
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) scratch[33] = digamma_pos(acc + A.inactive_sum);
+  }
+}
+
 __device__ __forceinline__ void p2_finish(const EmArgs& A, double* scratch, P2Acc& pa,
                                           uint32_t par) {
   double bs = block_reduce<false>(pa.sum, scratch);
@@ -305,6 +383,9 @@ __device__ __forceinline__ void p2_finish(const EmArgs& A, double* scratch, P2Ac
     if (bm > 0.0) atomicMax(&A.maxrel[par], (unsigned long long)__double_as_longlong(bm));
   }
 }
+
+#define SB_DBG(slot)                                                        \
+  if (A.dbg && it == A.dbg_it && (threadIdx.x & 31u) == 0) A.dbg[(size_t)gwarp * 8 + (slot)] = gtime_ns();
 
 // ---- persistent cooperative kernel: the whole iteration loop, two grid barriers/iter
 template <int CH, int MINB>
@@ -325,21 +406,26 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent(const __grid
   while (it < A.min_iter || (it < A.max_iter && !converged)) {
     const uint32_t par = it & 1u;
     if (bid == 0 && threadIdx.x == 0) A.maxrel[par] = 0ull;
+    if (A.vbem && it > 0) lag_lognorm_warp0(A, par, nblk, scratch);  // consumed after the next barrier
     P2Acc pa{0.0, 0.0};
+    SB_DBG(0)
     run_phase<1, CH>(A, W, R1, bid, nblk, 0.0, 0.0, pa);
+    SB_DBG(1)
     ring_prefetch(A.tm, W, R2);   // P2's stream lands during the grid barrier
     grid.sync();
-    if (A.vbem && it > 0) {
-      // lagged logNorm: alphaSum of THIS iteration's input = partials written by the
-      // previous P2.  Any common factor in theta cancels in P1/P2.
-      logNorm = digamma_pos(sum_partials(A.sum_partial + (size_t)(par ^ 1u) * nblk, nblk,
-                                         A.inactive_sum, scratch));
-    }
+    SB_DBG(2)
+    if (A.vbem && it > 0) logNorm = scratch[33];   // written before the grid barrier above
     const double bias = (!A.vbem && it == 0) ? 1.0 : 0.0;  // alphasPrime starts at 1.0 (:812,:821)
+    SB_DBG(3)
+    W.dbg = (A.dbg && it == A.dbg_it) ? &A.dbg[(size_t)gwarp * 8 + 7] : nullptr;
     run_phase<2, CH>(A, W, R2, bid, nblk, logNorm, bias, pa);
+    W.dbg = nullptr;
+    SB_DBG(4)
     ring_prefetch(A.cm, W, R1);   // next iteration's P1 stream (harmless if the loop ends)
     p2_finish(A, scratch, pa, par);
+    SB_DBG(5)
     grid.sync();
+    SB_DBG(6)
     const double mr = __longlong_as_double((long long)__ldcg(&A.maxrel[par]));
     converged = !(mr > A.tol);
     ++it;
@@ -378,10 +464,13 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p2(const __grid_constan
   const uint32_t par = it & 1u;
   double logNorm = 0.0;
   if (A.vbem) {
-    if (it == 0) logNorm = digamma_pos(A.sum0);
-    else
-      logNorm = digamma_pos(sum_partials(A.sum_partial + (size_t)(par ^ 1u) * gridDim.x, gridDim.x,
-                                         A.inactive_sum, scratch));
+    if (it == 0) {
+      logNorm = digamma_pos(A.sum0);
+    } else {
+      lag_lognorm_warp0(A, par, gridDim.x, scratch);
+      __syncthreads();
+      logNorm = scratch[33];
+    }
   }
   const double bias = (!A.vbem && it == 0) ? 1.0 : 0.0;
   P2Acc pa{0.0, 0.0};
