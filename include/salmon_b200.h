@@ -117,6 +117,34 @@ int sb_em_download(sb_em_ctx* ctx, double* alpha_out, sb_em_stats* stats);
 /* Debug/parity taps (tests): combinedWeights (:862-870) and validity flags. */
 int sb_em_get_combined(sb_em_ctx* ctx, double* combined_out, uint8_t* valid_out);
 
+/* ---- bootstraps and Gibbs samples ----------------------------------------
+ * Both run on the context sb_em_optimize (or upload+prepare+run) left behind: the class table,
+ * combinedWeights, validity flags and effective lengths stay resident in HBM.  Each sample
+ * is handed to the callback on the calling thread (the reference serialises its
+ * writeBootstrap callback with a mutex, src/output/GZipWriter.cpp:766-771); a non-zero
+ * return stops sampling.  Draws are a pure function of `seed` (Philox-4x32-10; stream
+ * layout in oracle/em_oracle.h), unlike the reference's random_device seeding. */
+typedef int (*sb_sample_cb)(const double* alpha, uint32_t n_txps, void* user);
+
+/* Replaces CollapsedEMOptimizer::gatherBootstraps (CollapsedEMOptimizer.hpp:30-34;
+ * src/inference/CollapsedEMOptimizer.cpp:554-690, doBootstrap :398-552).  p carries
+ * min_iter = 50 (:411), tol, max_iter and the VBEM switch; num_mapped_frags is
+ * readExp.numMappedFragments() (:572-573, used by the degenerate marking :608-621).
+ * Returns 1 where doBootstrap returns false (:521-525). */
+int sb_bootstrap(sb_em_ctx* ctx, const sb_em_params* p, double num_mapped_frags,
+                 uint32_t n_bootstraps, uint64_t seed, sb_sample_cb cb, void* user);
+/* Parity tap: per input class, the count drawn by the last replicate. */
+int sb_bootstrap_last_counts(sb_em_ctx* ctx, uint64_t* counts_out);
+
+/* Replaces CollapsedGibbsSampler::sample (CollapsedGibbsSampler.hpp:18-21;
+ * src/inference/CollapsedGibbsSampler.cpp:317-508, round :92-278).  alphas_init =
+ * Transcript::projectedCounts as writeAbundances leaves it (= sharedCount, GZipWriter.cpp:711-715);
+ * use_vbem / per_txp_prior / vb_prior select the prior (:357-371); thinning = sopt.thinningFactor
+ * (16); no_gamma_draw = sopt.noGammaDraw. */
+int sb_gibbs(sb_em_ctx* ctx, const double* alphas_init, int use_vbem, int per_txp_prior,
+             double vb_prior, uint32_t n_samples, uint32_t thinning, int no_gamma_draw,
+             double num_mapped_frags, uint64_t seed, sb_sample_cb cb, void* user);
+
 /* Debug: per-warp phase timestamps (ns) of one iteration of the last persistent run:
  * out[n_warps*8] = {P1 start, P1 end, barrier1 end, P2 start, P2 end, reduce end, barrier2 end, -}.
  * Returns the number of warps (call with out=NULL to size the buffer). */

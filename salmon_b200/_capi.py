@@ -89,6 +89,10 @@ SYMBOLS = {
     "sb_em_get_combined": (C.c_int, [_P, _P, _P]),
     "sb_em_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "sb_em_debug_timeline": (C.c_int, [_P, _P, C.c_uint32]),
+    "sb_bootstrap": (C.c_int, [_P, C.POINTER(sb_em_params), C.c_double, C.c_uint32, C.c_uint64, _P, _P]),
+    "sb_bootstrap_last_counts": (C.c_int, [_P, _P]),
+    "sb_gibbs": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_double, C.c_uint32, C.c_uint32, C.c_int, C.c_double,
+                           C.c_uint64, _P, _P]),
     "sb_nccl_unique_id": (C.c_int, [_P]),
     "sb_em_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "sb_em_comm_destroy": (C.c_int, [_P]),
@@ -206,6 +210,8 @@ class EMContext:
                                             eff_len.ctypes.data, unique.ctypes.data, alpha.ctypes.data,
                                             C.byref(st)), "sb_em_optimize")
         self.M = eq.n_txps
+        self._nnz = eq.nnz
+        self._C = eq.n_classes
         return alpha, st, rc == 0
 
     def upload(self, eq: EqClasses, projected, eff_len, unique):
@@ -238,6 +244,36 @@ class EMContext:
         valid = np.empty(self._C, dtype=np.uint8)
         _check(self.lib.sb_em_get_combined(self.h, cw.ctypes.data, valid.ctypes.data), "sb_em_get_combined")
         return cw, valid
+
+    def _collector(self):
+        samples = []
+        CB = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_uint32, C.c_void_p)
+
+        def cb(ptr, n, user):
+            samples.append(np.ctypeslib.as_array(ptr, shape=(n,)).copy())
+            return 0
+        return samples, CB(cb)
+
+    def bootstrap(self, params: sb_em_params, num_mapped_frags: float, n: int, seed: int):
+        """sb_bootstrap -> (array [n, M], ok)."""
+        samples, cb = self._collector()
+        rc = _check(self.lib.sb_bootstrap(self.h, C.byref(params), float(num_mapped_frags), n, seed,
+                                          C.cast(cb, C.c_void_p), None), "sb_bootstrap")
+        return np.array(samples), rc == 0
+
+    def bootstrap_last_counts(self):
+        out = np.zeros(self._C, dtype=np.uint64)
+        _check(self.lib.sb_bootstrap_last_counts(self.h, out.ctypes.data), "sb_bootstrap_last_counts")
+        return out
+
+    def gibbs(self, alphas_init, use_vbem, per_txp_prior, vb_prior, n_samples, thinning, no_gamma_draw,
+              num_mapped_frags, seed):
+        init = np.ascontiguousarray(alphas_init, dtype=np.float64)
+        samples, cb = self._collector()
+        _check(self.lib.sb_gibbs(self.h, init.ctypes.data, int(use_vbem), int(per_txp_prior), float(vb_prior),
+                                 n_samples, thinning, int(no_gamma_draw), float(num_mapped_frags), seed,
+                                 C.cast(cb, C.c_void_p), None), "sb_gibbs")
+        return np.array(samples)
 
     def arm_timeline(self, iteration: int) -> int:
         return _check(self.lib.sb_em_debug_timeline(self.h, None, iteration), "sb_em_debug_timeline")

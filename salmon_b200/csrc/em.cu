@@ -101,7 +101,7 @@ __global__ void k_class_combine(uint64_t C, uint32_t M, const uint64_t* __restri
                                 const double* __restrict__ effLens,
                                 const double* __restrict__ alpha0, sb_em_params p,
                                 double* __restrict__ cw, uint64_t* __restrict__ packed,
-                                uint32_t* __restrict__ sortkey,
+                                uint32_t* __restrict__ sortkey, uint32_t* __restrict__ cls_map,
                                 double* __restrict__ single, uint8_t* __restrict__ valid,
                                 unsigned long long* __restrict__ n_degenerate) {
   uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,16 +131,19 @@ __global__ void k_class_combine(uint64_t C, uint32_t M, const uint64_t* __restri
   uint64_t len = e - b;
   uint64_t pk = 0;
   uint32_t key = M;  // dropped classes sort last
+  uint32_t cmap = 0xffffffffu;  // class -> accumulator (samplers): 0x80000000|tid for singletons
   if (!ok) {
     atomicAdd(n_degenerate, 1ull);
   } else if (len == 1) {
     atomicAdd(&single[tids[b]], count);  // integer-valued: order independent
+    cmap = 0x80000000u | tids[b];
   } else if (len > 1) {
     pk = (1ull << 32) | len;             // (class count, entry count)
     key = tids[b];
   }
   packed[c] = pk;
   sortkey[c] = key;
+  cls_map[c] = cmap;
 }
 
 // second-level key: (locality group, length bucket); dropped rows last
@@ -170,7 +173,8 @@ __global__ void k_compact(uint64_t C, const uint32_t* __restrict__ order,
                           const uint64_t* __restrict__ packed_scan,
                           uint32_t* __restrict__ m_off, uint32_t* __restrict__ m_idx,
                           double* __restrict__ m_w, double* __restrict__ m_cnt,
-                          uint32_t* __restrict__ ent_cls, uint32_t* __restrict__ tcnt) {
+                          uint32_t* __restrict__ ent_cls, uint32_t* __restrict__ tcnt,
+                          uint32_t* __restrict__ cls_map) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C) return;
   if (packed_sorted[i] == 0) return;
@@ -180,6 +184,7 @@ __global__ void k_compact(uint64_t C, const uint32_t* __restrict__ order,
   uint32_t o = (uint32_t)(s & 0xffffffffu);
   m_off[cid] = o;
   m_cnt[cid] = (double)counts[c];
+  cls_map[c] = cid;
   for (uint64_t j = off[c]; j < off[c + 1]; ++j, ++o) {
     uint32_t t = tids[j];
     m_idx[o] = t;
@@ -380,7 +385,7 @@ k_em_update(const __grid_constant__ EmArgs A, const double* __restrict__ red, ui
     else logNorm = digamma_pos(sum_partials(A.sum_partial + (size_t)(par ^ 1u) * gridDim.x,
                                                  gridDim.x, 0.0, scratch));
   }
-  const double bias = (!A.vbem && it == 0) ? 1.0 : 0.0;
+  const double bias = (it == 0) ? A.first_bias : 0.0;
   double sum = 0.0, mx = 0.0;
   for (uint32_t t = blockIdx.x * 256 + threadIdx.x; t < M; t += gridDim.x * 256) {
     const double na = red[t] + bias;
@@ -516,7 +521,11 @@ static void free_all(sb_em_ctx* c) {
                    (void**)&c->d_sum_partial, (void**)&c->d_flush, (void**)&c->d_part,
                    (void**)&c->d_part_red, (void**)&c->r_alpha, (void**)&c->r_theta,
                    (void**)&c->r_prior, (void**)&c->r_base, (void**)&c->r_alpha0,
-                   (void**)&c->d_dbg};
+                   (void**)&c->d_dbg, (void**)&c->d_cdf, (void**)&c->d_cls_map, (void**)&c->d_samp,
+                   (void**)&c->d_valid_boot, (void**)&c->d_active, (void**)&c->d_gibbs_cnt,
+                   (void**)&c->d_gibbs_mu, (void**)&c->d_gibbs_prior, (void**)&c->d_gibbs_out,
+                   (void**)&c->ov_cnt, (void**)&c->ov_base_row, (void**)&c->ov_base_tid,
+                   (void**)&c->ov_alpha0_row, (void**)&c->ov_alpha0_tid};
   for (void** p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -739,6 +748,7 @@ extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* s
   SB_TRY(dev_alloc(&c->d_packed2, NP));
   SB_TRY(dev_alloc(&c->d_packed_scan, NP));
   SB_TRY(dev_alloc(&c->d_valid, C));
+  SB_TRY(dev_alloc(&c->d_cls_map, C));
   SB_TRY(dev_alloc(&c->d_scalars, 64));
   SB_TRY(dev_alloc(&c->d_tcnt, M));
   SB_TRY(dev_alloc(&c->d_tid_row, M));
@@ -772,8 +782,8 @@ extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* s
   if (C) {
     k_class_combine<<<nblk(C, 128), 128, 0, st>>>(C, M, c->d_off, c->d_tids, c->d_aux, c->d_counts,
                                                    c->d_efflens, c->d_alpha0, *p, c->d_cw,
-                                                   c->d_packed, c->d_sort_keys, c->d_base,
-                                                   c->d_valid, d_ndeg);
+                                                   c->d_packed, c->d_sort_keys, c->d_cls_map,
+                                                   c->d_base, c->d_valid, d_ndeg);
     // (1) locality order: classes by first transcript id
     k_iota<<<nblk(C, 256), 256, 0, st>>>((uint32_t)C, c->d_sort_vals);
     c->launches += 2;
@@ -810,7 +820,7 @@ extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* s
   if (C) {
     k_compact<<<nblk(C, 128), 128, 0, st>>>(C, c->d_order, c->d_off, c->d_tids, c->d_cw, c->d_counts,
                                              c->d_packed2, c->d_packed_scan, c->m_off, c->m_idx,
-                                             c->m_w, c->d_cnt, c->d_ent_cls, c->d_tcnt);
+                                             c->m_w, c->d_cnt, c->d_ent_cls, c->d_tcnt, c->d_cls_map);
     c->launches++;
   }
   // transcript-major CSR in rank order: stable radix sort of (tid, entry) pairs
@@ -924,9 +934,10 @@ static void fill_args(sb_em_ctx* c, EmArgs& A, bool row_space) {
   A.tm = sell_view(c->tm);
   A.cm.keep_pct = (uint32_t)c->keep_cm;
   A.tm.keep_pct = (uint32_t)c->keep_tm;
-  A.c_cnt = c->d_cnt; A.scale = c->d_scale;
+  A.c_cnt = c->ov_cnt ? c->ov_cnt : c->d_cnt; A.scale = c->d_scale;
   if (row_space) {
-    A.alpha = c->r_alpha; A.theta = c->r_theta; A.prior = c->r_prior; A.base = c->r_base;
+    A.alpha = c->r_alpha; A.theta = c->r_theta; A.prior = c->r_prior;
+    A.base = c->ov_base_row ? c->ov_base_row : c->r_base;
     A.row_tid = nullptr;
   } else {
     A.alpha = c->d_alpha; A.theta = c->d_theta; A.prior = c->d_prior; A.base = c->d_base;
@@ -934,7 +945,10 @@ static void fill_args(sb_em_ctx* c, EmArgs& A, bool row_space) {
   }
   A.sum_partial = c->d_sum_partial;
   A.maxrel = (unsigned long long*)(c->d_scalars + 24);
-  A.inactive_sum = c->inactive_sum; A.sum0 = c->sum0;
+  A.inactive_sum = c->ov_active ? c->ov_inactive_sum : c->inactive_sum;
+  A.sum0 = c->ov_active ? c->ov_sum0 : c->sum0;
+  A.min_eq_w = c->ov_active ? c->ov_min_eq_w : DBL_MIN;
+  A.first_bias = c->ov_active ? 0.0 : (c->params.use_vbem ? 0.0 : 1.0);
   A.tol = c->params.tol; A.min_iter = c->params.min_iter; A.max_iter = c->params.max_iter;
   A.vbem = c->params.use_vbem;
   A.out = (uint32_t*)(c->d_scalars + 32);
@@ -1076,7 +1090,9 @@ extern "C" int sb_em_run(sb_em_ctx* c, sb_em_stats* stats) {
                                             c->d_alpha, c->d_theta);
     ++launches;
   } else if (R) {
-    k_theta0<<<nblk(R, 256), 256, 0, st>>>(R, c->params.use_vbem, c->r_alpha0, c->r_prior, d_sum0,
+    k_theta0<<<nblk(R, 256), 256, 0, st>>>(R, c->params.use_vbem,
+                                            c->ov_alpha0_row ? c->ov_alpha0_row : c->r_alpha0,
+                                            c->r_prior, c->ov_active ? c->d_scalars + 18 : d_sum0,
                                             c->r_alpha, c->r_theta);
     ++launches;
   }
@@ -1138,10 +1154,12 @@ extern "C" int sb_em_run(sb_em_ctx* c, sb_em_stats* stats) {
   if (!multi_gpu) {
     // row space -> transcript space (+ inactive transcripts)
     if (out[0] > 0) {
-      double bias = (!c->params.use_vbem && out[0] == 1) ? 1.0 : 0.0;
-      k_finalize<<<nblk(M, 256), 256, 0, st>>>(M, c->d_tid_row, c->d_base, bias, c->r_alpha, c->d_alpha);
+      double bias = (!c->ov_active && !c->params.use_vbem && out[0] == 1) ? 1.0 : 0.0;
+      k_finalize<<<nblk(M, 256), 256, 0, st>>>(M, c->d_tid_row, c->ov_base_tid ? c->ov_base_tid : c->d_base,
+                                                bias, c->r_alpha, c->d_alpha);
     } else {
-      SB_CUDA(cudaMemcpyAsync(c->d_alpha, c->d_alpha0, (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
+      SB_CUDA(cudaMemcpyAsync(c->d_alpha, c->ov_alpha0_tid ? c->ov_alpha0_tid : c->d_alpha0, (size_t)M * 8,
+                              cudaMemcpyDeviceToDevice, st));
     }
     ++launches;
   }
@@ -1248,3 +1266,5 @@ extern "C" int sb_em_debug_timeline(sb_em_ctx* c, uint64_t* out, uint32_t iterat
   SB_CUDA(cudaMemcpy(out, c->d_dbg, (size_t)n_warps * 64, cudaMemcpyDeviceToHost));
   return (int)n_warps;
 }
+
+#include "sampling.cuh"

@@ -104,6 +104,22 @@ struct sb_em_ctx {
   double* d_part = nullptr;       // per-transcript partial alpha' (send)
   double* d_part_red = nullptr;   // all-reduced (recv)
 
+  // overrides used by the bootstrap driver (sampling.cuh): resampled counts, uniform init
+  bool ov_active = false;
+  double* ov_cnt = nullptr;
+  double* ov_base_row = nullptr;
+  double* ov_base_tid = nullptr;
+  double* ov_alpha0_row = nullptr;
+  double* ov_alpha0_tid = nullptr;
+  double ov_sum0 = 0.0, ov_inactive_sum = 0.0, ov_min_eq_w = 0.0;
+  // sampling scratch
+  uint64_t* d_cdf = nullptr;
+  uint32_t* d_cls_map = nullptr;
+  unsigned long long* d_samp = nullptr;
+  uint8_t* d_valid_boot = nullptr;
+  uint8_t* d_active = nullptr;
+  double *d_gibbs_cnt = nullptr, *d_gibbs_mu = nullptr, *d_gibbs_prior = nullptr, *d_gibbs_out = nullptr;
+
   // debug timeline
   unsigned long long* d_dbg = nullptr;
   uint32_t dbg_it = 0;

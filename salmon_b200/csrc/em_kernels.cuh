@@ -65,6 +65,8 @@ struct EmArgs {
   unsigned long long* maxrel;   // [2] bit pattern of a non-negative double
   double inactive_sum; double sum0;
   double tol;
+  double min_eq_w;              // denominator guard: DBL_MIN (optimize) / denorm_min (serial EM)
+  double first_bias;            // 1.0 for optimize's first plain-EM iteration (:812,:821), else 0
   uint32_t min_iter, max_iter;
   int vbem;
   uint32_t* out;                // [0]=iters [1]=converged [2]=maxrel slot
@@ -151,7 +153,7 @@ __device__ __forceinline__ void row_finish(const EmArgs& A, uint32_t row, const 
                                            double logNorm, double bias, P2Acc& pa) {
   if (o.len == LEN_LONG) return;  // beyond the last row, or a long row (block path)
   if (PHASE == 1) {
-    A.scale[row] = (acc <= MIN_EQ_W) ? 0.0 : o.x0 / acc;
+    A.scale[row] = (acc <= A.min_eq_w) ? 0.0 : o.x0 / acc;
   } else if (PHASE == 2) {
     const double th = o.x0, pr = o.x1;
     double na = o.x2 + bias;
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent(const __grid
     grid.sync();
     SB_DBG(2)
     if (A.vbem && it > 0) logNorm = scratch[33];   // written before the grid barrier above
-    const double bias = (!A.vbem && it == 0) ? 1.0 : 0.0;  // alphasPrime starts at 1.0 (:812,:821)
+    const double bias = (it == 0) ? A.first_bias : 0.0;  // alphasPrime starts at 1.0 (:812,:821)
     SB_DBG(3)
     W.dbg = (A.dbg && it == A.dbg_it) ? &A.dbg[(size_t)gwarp * 8 + 7] : nullptr;
     run_phase<2, CH>(A, W, R2, bid, nblk, logNorm, bias, pa);
@@ -472,7 +474,7 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p2(const __grid_constan
       logNorm = scratch[33];
     }
   }
-  const double bias = (!A.vbem && it == 0) ? 1.0 : 0.0;
+  const double bias = (it == 0) ? A.first_bias : 0.0;
   P2Acc pa{0.0, 0.0};
   const WarpRange R = load_range(A.tm, blockIdx.x * (EM_THREADS / 32) + (threadIdx.x >> 5));
   ring_prefetch(A.tm, W, R);

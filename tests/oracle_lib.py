@@ -122,3 +122,33 @@ def philox(c, k):
     load().orc_philox4x32(C.c_uint32(c[0]), C.c_uint32(c[1]), C.c_uint32(c[2]), C.c_uint32(c[3]),
                           C.c_uint32(k[0]), C.c_uint32(k[1]), out)
     return list(out)
+
+
+def bootstrap(eq, cw, valid, prior, active, p, n_boot, seed):
+    """orc_bootstrap -> (alphas [n_boot, M], sampled counts [n_boot, C], rc)."""
+    lib = load()
+    M, Cn = eq.n_txps, eq.n_classes
+    op = params_from(p)
+    alphas = np.zeros((n_boot, M))
+    samp = np.zeros((n_boot, Cn), dtype=np.uint64)
+    rc = lib.orc_bootstrap(C.c_uint64(Cn), C.c_uint32(M), _p(eq.off), _p(eq.tids), _p(np.ascontiguousarray(cw)),
+                           _p(eq.counts), _p(np.ascontiguousarray(valid, dtype=np.uint8)),
+                           _p(np.ascontiguousarray(prior, dtype=np.float64)),
+                           _p(np.ascontiguousarray(active, dtype=np.uint8)), C.byref(op), C.c_uint32(n_boot),
+                           C.c_uint64(seed), _p(alphas), _p(samp))
+    return alphas, samp, rc
+
+
+def gibbs(eq, valid, eff_len, alphas_init, use_vbem, per_txp_prior, vb_prior, n_samples, thinning, no_gamma_draw,
+          num_mapped_frags, seed):
+    lib = load()
+    M = eq.n_txps
+    out = np.zeros((n_samples, M))
+    rc = lib.orc_gibbs(C.c_uint64(eq.n_classes), C.c_uint32(M), _p(eq.off), _p(eq.tids), _p(eq.weights),
+                       _p(eq.counts), _p(np.ascontiguousarray(valid, dtype=np.uint8)),
+                       _p(np.ascontiguousarray(eff_len, dtype=np.float64)),
+                       _p(np.ascontiguousarray(alphas_init, dtype=np.float64)), C.c_int(use_vbem),
+                       C.c_int(per_txp_prior), C.c_double(vb_prior), C.c_uint32(n_samples), C.c_uint32(thinning),
+                       C.c_int(no_gamma_draw), C.c_double(num_mapped_frags), C.c_uint64(seed), _p(out))
+    assert rc == 0
+    return out
