@@ -145,6 +145,87 @@ int sb_gibbs(sb_em_ctx* ctx, const double* alphas_init, int use_vbem, int per_tx
              double vb_prior, uint32_t n_samples, uint32_t thinning, int no_gamma_draw,
              double num_mapped_frags, uint64_t seed, sb_sample_cb cb, void* user);
 
+/* ---- Stage A: index, per-read mapping, equivalence-class builder ------------------
+ * Seam B1: the body of processReads<IndexT> (src/quant/SalmonQuantify.cpp:1026-1874: per read
+ * MemCollector / findChains / joinReadsAndFilter / PuffAligner::calculateAlignments /
+ * updateRefMappings / filterAndCollectAlignments, then processMiniBatch :426-1023) and seam B2:
+ * EquivalenceClassBuilder<TGValue>::addGroup / finish / eqVec
+ * (include/salmon/internal/quant/EquivalenceClassBuilder.hpp:165-181,210-223,237-250).
+ * The mapping core (pufferfish) is not in the reference tree; the algorithm here is this
+ * project's own (DESIGN.md "MAPSPEC").  Reads are passed as one base per byte
+ * (0..3 = A,C,G,T; 4 = N), n_pairs x read_len, fixed length per batch. */
+typedef struct sb_index sb_index;
+/* Replaces SalmonIndex::build -> pufferfishIndex() for the purposes of this path
+ * (include/salmon/internal/index/SalmonIndex.hpp:106-118): canonical k-mer hash table ->
+ * postings (transcript, offset); own in-memory format.  seq_off[n_txps+1]: base offsets. */
+sb_index* sb_index_build(uint32_t n_txps, const uint64_t* seq_off, const uint8_t* codes, uint32_t k);
+void sb_index_free(sb_index* ix);
+/* out4 = {distinct k-mers, postings, table capacity, bytes} */
+int sb_index_info(const sb_index* ix, uint64_t* out4);
+/* Raw views of the index arrays (for serialisation): table = {u64 key, u32 first posting, u32 count}
+ * x capacity (open addressing, linear probing, key ~0 = free); postings = {u32 transcript, u32 offset}. */
+int sb_index_host_arrays(const sb_index* ix, const uint64_t** tx_off, const uint8_t** codes,
+                         const void** table, uint64_t* table_capacity, const void** postings,
+                         uint64_t* n_postings);
+
+/* SalmonOpts fields of the mapping / assignment path (defaults: SalmonDefaults.hpp:10-99;
+ * initMapperSettings, SalmonMappingUtils.hpp:153-223). */
+typedef struct sb_map_params {
+  uint32_t k;                 /* 31 */
+  uint32_t stride;            /* seed sampling stride (MAPSPEC) */
+  uint32_t max_occs_per_hit;  /* maxOccsPerHit 1000 */
+  uint32_t max_read_occ;      /* maxReadOcc 200 */
+  uint32_t max_frag_len;      /* fragLenDistMax 1000 */
+  uint32_t band;              /* bandwidth 15 */
+  uint32_t chain_gap;         /* MAPSPEC: diagonal gap inside a chain */
+  uint32_t range_bins;        /* rangeFactorizationBins 4 */
+  int32_t ma, mp, go, ge;     /* 2 -4 6 2 */
+  int32_t hard_filter;        /* hardFilter */
+  int32_t first_decoy;        /* firstDecoyIndex */
+  double consensus_frac;      /* 1 - consensusSlack */
+  double min_score_fraction;  /* 0.65 */
+  double score_exp;           /* 1.0 */
+  double min_aln_prob;        /* 1e-5 */
+  double decoy_threshold;     /* 1.0 */
+  double fld_mean, fld_sd;    /* 250, 25 */
+  uint64_t num_pre_burnin;    /* numPreBurninFrags 5000 */
+  uint64_t num_burnin;        /* numBurninFrags 5000000 */
+} sb_map_params;
+void sb_map_default_params(sb_map_params* p);
+
+typedef struct sb_map_batch_stats {
+  uint32_t n_pairs;
+  uint32_t gpu_launches;
+  uint64_t mapped, lookups, postings, seeds, candidates, kept, label_entries, n_batch_classes;
+  float device_ms;            /* H2D of the reads + all kernels of the batch (CUDA events) */
+} sb_map_batch_stats;
+
+typedef struct sb_map_result {   /* host CSR owned by the context, valid until destroy / next finish */
+  uint64_t n_classes;
+  const uint64_t* off;        /* [n_classes+1] */
+  const uint32_t* tids;       /* label, transcript part */
+  const double* weights;      /* normalised (finish()) */
+  const uint64_t* counts;
+  const uint32_t* bins;       /* range-factorisation part of the label (NULL if range_bins == 0) */
+  uint64_t n_mapped, lookups, postings, seeds, candidates, kept, label_entries;
+} sb_map_result;
+
+typedef struct sb_map_ctx sb_map_ctx;
+sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* p, int device, uint32_t max_pairs_per_batch,
+                          uint32_t max_read_len);
+void sb_map_destroy(sb_map_ctx* ctx);
+/* One mini-batch: H2D, seed/chain, DP scoring, filtering + auxiliary probabilities + labels,
+ * per-batch class aggregation.  Model state (fragment counter -> burn-in regime) is frozen for
+ * the duration of the batch. */
+int sb_map_batch(sb_map_ctx* ctx, const uint8_t* left, const uint8_t* right, uint32_t n_pairs,
+                 uint32_t read_len, sb_map_batch_stats* stats);
+/* finish(): merge batch tables, normalise weights, return the CSR (feeds sb_em_optimize). */
+int sb_map_finish(sb_map_ctx* ctx, sb_map_result* out);
+/* Parity tap: the per-read alignments / labels of the last batch (arrays n*cap; label n*2*cap). */
+int sb_map_last_alignments(sb_map_ctx* ctx, uint32_t n, uint32_t* n_aln, uint32_t* tid, int32_t* score,
+                           double* prob, int32_t* pos, int32_t* mate_pos, uint8_t* flags, int32_t* flen,
+                           uint32_t* label, double* weight);
+
 /* Debug: per-warp phase timestamps (ns) of one iteration of the last persistent run:
  * out[n_warps*8] = {P1 start, P1 end, barrier1 end, P2 start, P2 end, reduce end, barrier2 end, -}.
  * Returns the number of warps (call with out=NULL to size the buffer). */

@@ -71,6 +71,33 @@ class sb_em_stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class sb_map_params(C.Structure):
+    _fields_ = [
+        ("k", C.c_uint32), ("stride", C.c_uint32), ("max_occs_per_hit", C.c_uint32), ("max_read_occ", C.c_uint32),
+        ("max_frag_len", C.c_uint32), ("band", C.c_uint32), ("chain_gap", C.c_uint32), ("range_bins", C.c_uint32),
+        ("ma", C.c_int32), ("mp", C.c_int32), ("go", C.c_int32), ("ge", C.c_int32),
+        ("hard_filter", C.c_int32), ("first_decoy", C.c_int32),
+        ("consensus_frac", C.c_double), ("min_score_fraction", C.c_double), ("score_exp", C.c_double),
+        ("min_aln_prob", C.c_double), ("decoy_threshold", C.c_double), ("fld_mean", C.c_double), ("fld_sd", C.c_double),
+        ("num_pre_burnin", C.c_uint64), ("num_burnin", C.c_uint64),
+    ]
+
+
+class sb_map_batch_stats(C.Structure):
+    _fields_ = [("n_pairs", C.c_uint32), ("gpu_launches", C.c_uint32)] + \
+        [(k, C.c_uint64) for k in ("mapped", "lookups", "postings", "seeds", "candidates", "kept", "label_entries",
+                                   "n_batch_classes")] + [("device_ms", C.c_float)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class sb_map_result(C.Structure):
+    _fields_ = [("n_classes", C.c_uint64), ("off", C.POINTER(C.c_uint64)), ("tids", C.POINTER(C.c_uint32)),
+                ("weights", C.POINTER(C.c_double)), ("counts", C.POINTER(C.c_uint64)), ("bins", C.POINTER(C.c_uint32))] + \
+        [(k, C.c_uint64) for k in ("n_mapped", "lookups", "postings", "seeds", "candidates", "kept", "label_entries")]
+
+
 # every symbol include/salmon_b200.h declares: (name, restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -97,6 +124,16 @@ SYMBOLS = {
     "sb_em_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "sb_em_comm_destroy": (C.c_int, [_P]),
     "sb_flush_l2": (C.c_int, [_P]),
+    "sb_index_build": (_P, [C.c_uint32, _P, _P, C.c_uint32]),
+    "sb_index_free": (None, [_P]),
+    "sb_index_info": (C.c_int, [_P, _P]),
+    "sb_index_host_arrays": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "sb_map_default_params": (None, [C.POINTER(sb_map_params)]),
+    "sb_map_create": (_P, [_P, C.POINTER(sb_map_params), C.c_int, C.c_uint32, C.c_uint32]),
+    "sb_map_destroy": (None, [_P]),
+    "sb_map_batch": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, C.POINTER(sb_map_batch_stats)]),
+    "sb_map_finish": (C.c_int, [_P, C.POINTER(sb_map_result)]),
+    "sb_map_last_alignments": (C.c_int, [_P, C.c_uint32] + [_P] * 10),
     "sb_host_register": (C.c_int, [_P, C.c_size_t]),
     "sb_host_unregister": (C.c_int, [_P]),
 }
@@ -305,3 +342,117 @@ def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     _check(load().sb_nccl_unique_id(buf), "sb_nccl_unique_id")
     return buf.raw
+
+
+# ------------------------------------------------------------------------------ Stage A
+def map_default_params(**over) -> sb_map_params:
+    p = sb_map_params()
+    load().sb_map_default_params(C.byref(p))
+    for k, v in over.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+class Index:
+    """sb_index: host-built k-mer hash index over a transcriptome (list of uint8 code arrays)."""
+
+    def __init__(self, txps, k=31):
+        self.lib = load()
+        lens = np.array([t.shape[0] for t in txps], dtype=np.uint64)
+        self.off = np.concatenate(([0], np.cumsum(lens))).astype(np.uint64)
+        self.codes = np.ascontiguousarray(np.concatenate(txps).astype(np.uint8)) if len(txps) else np.zeros(0, np.uint8)
+        self.n_txps = len(txps)
+        self.k = k
+        self.h = self.lib.sb_index_build(self.n_txps, self.off.ctypes.data, self.codes.ctypes.data, k)
+        if not self.h:
+            raise SalmonB200Error("sb_index_build failed: " + self.lib.sb_last_error().decode())
+
+    def info(self):
+        out = np.zeros(4, dtype=np.uint64)
+        _check(self.lib.sb_index_info(self.h, out.ctypes.data), "sb_index_info")
+        return dict(n_kmers=int(out[0]), n_postings=int(out[1]), table_capacity=int(out[2]), bytes=int(out[3]))
+
+    def host_arrays(self):
+        ptrs = [C.c_void_p() for _ in range(4)]
+        cap, npost = C.c_uint64(), C.c_uint64()
+        _check(self.lib.sb_index_host_arrays(self.h, C.byref(ptrs[0]), C.byref(ptrs[1]), C.byref(ptrs[2]), C.byref(cap),
+                                             C.byref(ptrs[3]), C.byref(npost)), "sb_index_host_arrays")
+        return dict(tx_off=ptrs[0].value, codes=ptrs[1].value, table=ptrs[2].value, table_capacity=cap.value,
+                    postings=ptrs[3].value, n_postings=npost.value)
+
+    def close(self):
+        if self.h:
+            self.lib.sb_index_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def alloc_alignment_arrays(n, cap):
+    return dict(n_aln=np.zeros(n, dtype=np.uint32), tid=np.zeros((n, cap), dtype=np.uint32),
+                score=np.zeros((n, cap), dtype=np.int32), prob=np.zeros((n, cap)),
+                pos=np.zeros((n, cap), dtype=np.int32), mate_pos=np.zeros((n, cap), dtype=np.int32),
+                flags=np.zeros((n, cap), dtype=np.uint8), flen=np.zeros((n, cap), dtype=np.int32),
+                label=np.zeros((n, 2 * cap), dtype=np.uint32), weight=np.zeros((n, cap)))
+
+
+class MapContext:
+    """sb_map_ctx: per-GPU mapping + equivalence-class builder."""
+
+    def __init__(self, index: Index, params: sb_map_params, device=0, batch_cap=65536, max_read_len=150):
+        self.lib = load()
+        self.index = index
+        self.p = params
+        self.h = self.lib.sb_map_create(index.h, C.byref(params), device, batch_cap, max_read_len)
+        if not self.h:
+            raise SalmonB200Error("sb_map_create failed: " + self.lib.sb_last_error().decode())
+        self.last_n = 0
+
+    def map_batch(self, left, right) -> sb_map_batch_stats:
+        left = np.ascontiguousarray(left, dtype=np.uint8)
+        right = np.ascontiguousarray(right, dtype=np.uint8)
+        n, L = left.shape
+        st = sb_map_batch_stats()
+        _check(self.lib.sb_map_batch(self.h, left.ctypes.data, right.ctypes.data, n, L, C.byref(st)), "sb_map_batch")
+        self.last_n = n
+        return st
+
+    def last_alignments(self):
+        n, cap = self.last_n, self.p.max_read_occ
+        a = alloc_alignment_arrays(n, cap)
+        _check(self.lib.sb_map_last_alignments(self.h, n, *[a[k].ctypes.data for k in (
+            "n_aln", "tid", "score", "prob", "pos", "mate_pos", "flags", "flen", "label", "weight")]),
+            "sb_map_last_alignments")
+        return a
+
+    def finish(self):
+        r = sb_map_result()
+        _check(self.lib.sb_map_finish(self.h, C.byref(r)), "sb_map_finish")
+        nc = int(r.n_classes)
+        off = np.ctypeslib.as_array(r.off, shape=(nc + 1,)).copy() if nc else np.zeros(1, np.uint64)
+        nn = int(off[-1])
+        out = dict(off=off,
+                   tids=np.ctypeslib.as_array(r.tids, shape=(nn,)).copy() if nn else np.zeros(0, np.uint32),
+                   weights=np.ctypeslib.as_array(r.weights, shape=(nn,)).copy() if nn else np.zeros(0),
+                   counts=np.ctypeslib.as_array(r.counts, shape=(nc,)).copy() if nc else np.zeros(0, np.uint64),
+                   bins=(np.ctypeslib.as_array(r.bins, shape=(nn,)).copy() if (nn and r.bins) else None),
+                   counters={k: int(getattr(r, k)) for k in ("n_mapped", "lookups", "postings", "seeds", "candidates",
+                                                             "kept", "label_entries")})
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.sb_map_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

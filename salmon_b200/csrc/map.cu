@@ -1,0 +1,792 @@
+// map.cu -- Stage A on B200: index (host build, HBM resident), per-read mapping kernels, banded
+// affine DP scoring (one warp per mate alignment, lanes = band cells), alignment filtering +
+// auxiliary probabilities + labels, and the equivalence-class builder (hash -> radix sort ->
+// segmented reduce).  C ABI at the reference's seams B1 (processReads, src/quant/
+// SalmonQuantify.cpp:1026-1874) and B2 (EquivalenceClassBuilder, include/salmon/internal/quant/
+// EquivalenceClassBuilder.hpp:165-181,237-250).  See map_core.h for MAPSPEC.
+#include <cub/cub.cuh>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "map_core.h"
+
+using namespace sbmap;
+
+// ---------------------------------------------------------------------------------------------
+// index (host build)
+// ---------------------------------------------------------------------------------------------
+struct sb_index {
+  uint32_t n_txps = 0, k = 0;
+  std::vector<uint64_t> tx_off;
+  std::vector<uint8_t> codes;
+  std::vector<TableEntry> table;
+  std::vector<Posting> post;
+  uint64_t n_kmers = 0;
+  // device copies (one device)
+  int device = -1;
+  uint64_t* d_tx_off = nullptr;
+  uint8_t* d_codes = nullptr;
+  TableEntry* d_table = nullptr;
+  Posting* d_post = nullptr;
+};
+
+namespace {
+struct KP {
+  uint64_t km;
+  uint32_t tid, tpos;
+};
+IndexView host_view(const sb_index* ix) {
+  IndexView v;
+  v.n_txps = ix->n_txps; v.k = ix->k; v.mask = ix->table.size() - 1;
+  v.tx_off = ix->tx_off.data(); v.codes = ix->codes.data(); v.table = ix->table.data(); v.post = ix->post.data();
+  return v;
+}
+IndexView dev_view(const sb_index* ix) {
+  IndexView v;
+  v.n_txps = ix->n_txps; v.k = ix->k; v.mask = ix->table.size() - 1;
+  v.tx_off = ix->d_tx_off; v.codes = ix->d_codes; v.table = ix->d_table; v.post = ix->d_post;
+  return v;
+}
+}  // namespace
+
+extern "C" sb_index* sb_index_build(uint32_t n_txps, const uint64_t* seq_off, const uint8_t* codes, uint32_t k) {
+  if (!seq_off || (!codes && seq_off[n_txps]) || k < 3 || k > 31 || (k & 1) == 0) {
+    sb::set_error("sb_index_build: bad arguments (k must be odd, 3..31)");
+    return nullptr;
+  }
+  for (uint32_t t = 0; t < n_txps; ++t)
+    if (seq_off[t + 1] - seq_off[t] >= (1u << 21)) {
+      sb::set_error("sb_index_build: reference %u longer than 2^21 bases (seed key layout)", t);
+      return nullptr;
+    }
+  sb_index* ix = new sb_index();
+  ix->n_txps = n_txps; ix->k = k;
+  ix->tx_off.assign(seq_off, seq_off + n_txps + 1);
+  ix->codes.assign(codes, codes + seq_off[n_txps]);
+  std::vector<KP> kp;
+  uint64_t cap = 0;
+  for (uint32_t t = 0; t < n_txps; ++t) { uint64_t L = seq_off[t + 1] - seq_off[t]; if (L >= k) cap += L - k + 1; }
+  kp.reserve(cap);
+  const uint64_t kmask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1);
+  for (uint32_t t = 0; t < n_txps; ++t) {
+    const uint64_t b = seq_off[t], e = seq_off[t + 1];
+    uint64_t fw = 0, rc = 0;
+    uint32_t valid = 0;   // consecutive valid bases ending at p
+    for (uint64_t p = b; p < e; ++p) {
+      const uint8_t c = codes[p];
+      if (c > 3) { valid = 0; fw = rc = 0; continue; }
+      fw = ((fw << 2) | c) & kmask;
+      rc = (rc >> 2) | ((uint64_t)(3 - c) << (2 * (k - 1)));
+      if (++valid >= k) kp.push_back({fw < rc ? fw : rc, t, (uint32_t)(p + 1 - k - b)});
+    }
+  }
+  std::sort(kp.begin(), kp.end(), [](const KP& a, const KP& b) {
+    if (a.km != b.km) return a.km < b.km;
+    if (a.tid != b.tid) return a.tid < b.tid;
+    return a.tpos < b.tpos;
+  });
+  uint64_t nk = 0;
+  for (size_t i = 0; i < kp.size(); ++i) if (i == 0 || kp[i].km != kp[i - 1].km) ++nk;
+  ix->n_kmers = nk;
+  uint64_t capt = 1024;
+  while (capt < 2 * nk) capt <<= 1;
+  ix->table.assign(capt, TableEntry{EMPTY_KEY, 0, 0});
+  ix->post.resize(kp.size());
+  const uint64_t mask = capt - 1;
+  for (size_t i = 0; i < kp.size();) {
+    size_t j = i;
+    while (j < kp.size() && kp[j].km == kp[i].km) { ix->post[j] = Posting{kp[j].tid, kp[j].tpos}; ++j; }
+    uint64_t h = mix64(kp[i].km) & mask;
+    while (ix->table[h].key != EMPTY_KEY) h = (h + 1) & mask;
+    ix->table[h] = TableEntry{kp[i].km, (uint32_t)i, (uint32_t)(j - i)};
+    i = j;
+  }
+  return ix;
+}
+
+extern "C" void sb_index_free(sb_index* ix) {
+  if (!ix) return;
+  if (ix->device >= 0) {
+    cudaSetDevice(ix->device);
+    cudaFree(ix->d_tx_off); cudaFree(ix->d_codes); cudaFree(ix->d_table); cudaFree(ix->d_post);
+  }
+  delete ix;
+}
+
+extern "C" int sb_index_info(const sb_index* ix, uint64_t* out4) {
+  if (!ix || !out4) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  out4[0] = ix->n_kmers; out4[1] = ix->post.size(); out4[2] = ix->table.size();
+  out4[3] = ix->table.size() * sizeof(TableEntry) + ix->post.size() * sizeof(Posting) + ix->codes.size() +
+            ix->tx_off.size() * 8;
+  return SB_OK;
+}
+
+// raw views of the host-side arrays (serialisation; also lets tests run map_core.h on the CPU)
+extern "C" int sb_index_host_arrays(const sb_index* ix, const uint64_t** tx_off, const uint8_t** codes,
+                                    const void** table, uint64_t* table_capacity, const void** postings,
+                                    uint64_t* n_postings) {
+  if (!ix) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  if (tx_off) *tx_off = ix->tx_off.data();
+  if (codes) *codes = ix->codes.data();
+  if (table) *table = ix->table.data();
+  if (table_capacity) *table_capacity = ix->table.size();
+  if (postings) *postings = ix->post.data();
+  if (n_postings) *n_postings = ix->post.size();
+  return SB_OK;
+}
+
+static int index_to_device(sb_index* ix, int device) {
+  if (ix->device == device) return SB_OK;
+  if (ix->device >= 0) { sb::set_error("index already resident on device %d", ix->device); return SB_ERR_STATE; }
+  SB_CUDA(cudaSetDevice(device));
+  SB_CUDA(cudaMalloc(&ix->d_tx_off, ix->tx_off.size() * 8));
+  SB_CUDA(cudaMalloc(&ix->d_codes, std::max<size_t>(ix->codes.size(), 1) + 64));
+  SB_CUDA(cudaMalloc(&ix->d_table, ix->table.size() * sizeof(TableEntry)));
+  SB_CUDA(cudaMalloc(&ix->d_post, std::max<size_t>(ix->post.size(), 1) * sizeof(Posting)));
+  SB_CUDA(cudaMemcpy(ix->d_tx_off, ix->tx_off.data(), ix->tx_off.size() * 8, cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMemcpy(ix->d_codes, ix->codes.data(), ix->codes.size(), cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMemcpy(ix->d_table, ix->table.data(), ix->table.size() * sizeof(TableEntry), cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMemcpy(ix->d_post, ix->post.data(), ix->post.size() * sizeof(Posting), cudaMemcpyHostToDevice));
+  ix->device = device;
+  return SB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct BatchBufs {
+  // per read
+  uint32_t* n_l; uint32_t* n_r;      // candidates per mate
+  Cand* cand_l; Cand* cand_r;        // [B*MAXCAND]
+  int32_t* score_l; int32_t* score_r;// [B*MAXCAND]
+  uint64_t* keys;                    // [MAXSEEDS * T] interleaved seed scratch, T = threads of K1
+  // DP task list
+  uint32_t* n_tasks; uint32_t* tasks;  // task = read<<7 | mate<<6 | cand
+  // outputs (cap per read)
+  uint32_t* n_aln; uint32_t* tid; int32_t* score; double* prob; int32_t* pos; int32_t* mate_pos;
+  uint8_t* flags; int32_t* flen; uint32_t* label; double* weight;
+  // scratch for assign
+  int32_t* sc; int32_t* perm_idx; int32_t* perm_tid; int32_t* bs_tid; int32_t* bs_score; int32_t* bs_idx;
+  Joint* jh;
+  Counters* ctr;
+};
+
+__device__ __forceinline__ void add_counters(Counters* g, const Counters& c) {
+  if (c.lookups) atomicAdd(&g->lookups, c.lookups);
+  if (c.postings) atomicAdd(&g->postings, c.postings);
+  if (c.seeds) atomicAdd(&g->seeds, c.seeds);
+  if (c.candidates) atomicAdd(&g->candidates, c.candidates);
+  if (c.kept) atomicAdd(&g->kept, c.kept);
+  if (c.label_entries) atomicAdd(&g->label_entries, c.label_entries);
+  if (c.mapped) atomicAdd(&g->mapped, c.mapped);
+}
+
+// K1: one thread per read pair -- seeds, chains, candidates, DP task list
+__global__ void k_seed_chain(IndexView ix, Params p, const uint8_t* __restrict__ left,
+                             const uint8_t* __restrict__ right, uint32_t n, uint32_t L, BatchBufs b) {
+  const uint32_t T = gridDim.x * blockDim.x;
+  const uint32_t tid0 = blockIdx.x * blockDim.x + threadIdx.x;
+  Counters ctr;
+  memset(&ctr, 0, sizeof(ctr));
+  uint64_t* keys = b.keys + tid0;
+  for (uint32_t r = tid0; r < n; r += T) {
+    Cand* lc = b.cand_l + (size_t)r * MAXCAND;
+    Cand* rc = b.cand_r + (size_t)r * MAXCAND;
+    const uint32_t nl = mate_candidates(ix, p, left + (size_t)r * L, L, keys, T, lc, ctr);
+    const uint32_t nr = mate_candidates(ix, p, right + (size_t)r * L, L, keys, T, rc, ctr);
+    b.n_l[r] = nl;
+    b.n_r[r] = nr;
+    // which candidates take part in a joint hit (=> need a DP score)
+    unsigned long long used_l = 0, used_r = 0;
+    const uint32_t nj = for_each_joint(p, lc, nl, rc, nr, L, [&](const Joint& j, uint32_t) {
+      if (j.li >= 0) used_l |= 1ull << j.li;
+      if (j.ri >= 0) used_r |= 1ull << j.ri;
+    });
+    if (nj == 0 || nj > p.max_read_occ) { b.n_l[r] |= 0x80000000u; continue; }   // unmapped / too many places
+    const uint32_t cnt = (uint32_t)(__popcll(used_l) + __popcll(used_r));
+    uint32_t slot = atomicAdd(b.n_tasks, cnt);
+    for (uint32_t a = 0; a < nl; ++a) if (used_l >> a & 1) b.tasks[slot++] = (r << 7) | a;
+    for (uint32_t a = 0; a < nr; ++a) if (used_r >> a & 1) b.tasks[slot++] = (r << 7) | 64u | a;
+    ctr.candidates += cnt;
+  }
+  add_counters(b.ctr, ctr);
+}
+
+// K2: one warp per mate alignment.  Lane j <-> band cell j (W = 2*band+1 <= 32): for read row i
+// the cell is reference position diag_c + i + (j - band).  Same recurrences as dp_score_serial:
+//   M = H(i-1,j) + s ; E = max(H(i-1,j+1) - go - ge, E(i-1,j+1) - ge) ; F = max_{k<j} (H'(i,k) - go - (j-k) ge)
+// with H' = max(M, E): opening a gap from an F-derived H never beats extending that F (go >= 0),
+// so the in-row dependency of F is a max-plus prefix scan (5 shuffle steps).
+__global__ void k_dp_score(IndexView ix, Params p, const uint8_t* __restrict__ left,
+                           const uint8_t* __restrict__ right, uint32_t L, BatchBufs b) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t ntasks = *b.n_tasks;
+  const int32_t B = (int32_t)p.band, W = 2 * B + 1;
+  for (uint32_t t = warp; t < ntasks; t += nwarps) {
+    const uint32_t task = b.tasks[t];
+    const uint32_t r = task >> 7, mate = (task >> 6) & 1u, ci = task & 63u;
+    const Cand c = mate ? b.cand_r[(size_t)r * MAXCAND + ci] : b.cand_l[(size_t)r * MAXCAND + ci];
+    const uint8_t* read = (mate ? right : left) + (size_t)r * L;
+    const uint32_t ori = c.ori_cov >> 31;
+    const int64_t tlen = (int64_t)(ix.tx_off[c.tid + 1] - ix.tx_off[c.tid]);
+    const uint8_t* ref = ix.codes + ix.tx_off[c.tid];
+    const bool in_band = (int32_t)lane < W;
+    int32_t H = in_band ? 0 : NEG_SCORE, E = NEG_SCORE;
+    // the reference base of lane j for row i is ref[diag_c + i + j - B]: lane j's base for row i+1
+    // is lane j+1's base of row i, so each row needs ONE new base (for the last lane)
+    int64_t rpos = (int64_t)c.diag_c + ((int32_t)lane - B);
+    uint8_t rbase = (rpos >= 0 && rpos < tlen) ? ref[rpos] : (uint8_t)255;
+    for (uint32_t i = 0; i < L; ++i) {
+      const uint8_t cc = ori ? read[L - 1 - i] : read[i];
+      const uint8_t rb = ori ? (uint8_t)(cc > 3 ? 4 : 3 - cc) : cc;
+      const bool valid = in_band && rbase != 255;
+      const int32_t Hup = __shfl_down_sync(0xffffffffu, H, 1);
+      const int32_t Eup = __shfl_down_sync(0xffffffffu, E, 1);
+      int32_t m = NEG_SCORE, e = NEG_SCORE;
+      if (valid) {
+        m = H + ((rb < 4 && rb == rbase) ? p.ma : p.mp);
+        if ((int32_t)lane + 1 < W) e = max(Hup - p.go - p.ge, Eup - p.ge);
+        if (e < NEG_SCORE) e = NEG_SCORE;
+      }
+      const int32_t hp = valid ? max(m, e) : NEG_SCORE;
+      // F_j = max_{k<j} (hp_k + k*ge) - go - j*ge  (exclusive max-prefix over lanes)
+      int32_t x = (hp <= NEG_SCORE) ? NEG_SCORE : hp + (int32_t)lane * p.ge;
+      int32_t pref = __shfl_up_sync(0xffffffffu, x, 1);
+      if (lane == 0) pref = NEG_SCORE;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t y = __shfl_up_sync(0xffffffffu, pref, o);
+        if ((int)lane >= o) pref = max(pref, y);
+      }
+      int32_t f = (pref <= NEG_SCORE) ? NEG_SCORE : pref - p.go - (int32_t)lane * p.ge;
+      if (f < NEG_SCORE) f = NEG_SCORE;
+      int32_t h = NEG_SCORE;
+      if (valid) { h = max(hp, f); if (h < NEG_SCORE) h = NEG_SCORE; }
+      H = h;
+      E = valid ? e : NEG_SCORE;
+      // advance the reference window by one base
+      const uint8_t nb = __shfl_down_sync(0xffffffffu, rbase, 1);
+      ++rpos;
+      if ((int32_t)lane == W - 1) rbase = (rpos >= 0 && rpos < tlen) ? ref[rpos] : (uint8_t)255;
+      else rbase = nb;
+    }
+    int32_t best = in_band ? H : NEG_SCORE;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) (mate ? b.score_r : b.score_l)[(size_t)r * MAXCAND + ci] = best;
+  }
+}
+
+// K3: one thread per read pair -- salmon's alignment filtering, auxiliary probabilities, label
+__global__ void k_assign(IndexView ix, Params p, FldView fld, int useAux, int burnedIn, uint32_t n, uint32_t L,
+                         BatchBufs b) {
+  const uint32_t T = gridDim.x * blockDim.x;
+  const uint32_t tid0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t cap = p.max_read_occ;
+  Counters ctr;
+  memset(&ctr, 0, sizeof(ctr));
+  for (uint32_t r = tid0; r < n; r += T) {
+    ReadOut o;
+    o.n_aln = b.n_aln + r;
+    o.tid = b.tid + (size_t)r * cap; o.score = b.score + (size_t)r * cap; o.prob = b.prob + (size_t)r * cap;
+    o.pos = b.pos + (size_t)r * cap; o.mate_pos = b.mate_pos + (size_t)r * cap; o.flags = b.flags + (size_t)r * cap;
+    o.flen = b.flen + (size_t)r * cap; o.label = b.label + (size_t)r * 2 * cap; o.weight = b.weight + (size_t)r * cap;
+    const uint32_t nlr = b.n_l[r];
+    if (nlr & 0x80000000u) { *o.n_aln = 0; continue; }
+    const size_t so = (size_t)tid0 * cap;
+    assign_read(ix, p, fld, useAux != 0, burnedIn != 0, b.cand_l + (size_t)r * MAXCAND, nlr,
+                b.cand_r + (size_t)r * MAXCAND, b.n_r[r], b.score_l + (size_t)r * MAXCAND,
+                b.score_r + (size_t)r * MAXCAND, L, b.sc + so, b.perm_idx + so, b.perm_tid + so, b.bs_tid + so,
+                b.bs_score + so, b.bs_idx + so, b.jh + so, o, ctr);
+  }
+  add_counters(b.ctr, ctr);
+}
+
+// ---- equivalence-class builder: records (label, weights, count) -> classes ----------------
+// hash of a label (64-bit FNV-1a over the 32-bit words; the value is never persisted, like the
+// reference's XXH64 in TranscriptGroup::hash, src/model/TranscriptGroup.cpp:10-15)
+__global__ void k_label_hash(uint32_t n, const uint64_t* __restrict__ loff, const uint32_t* __restrict__ labels,
+                             uint64_t* __restrict__ hash, uint32_t* __restrict__ idx) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t h = 1469598103934665603ull;
+  for (uint64_t j = loff[i]; j < loff[i + 1]; ++j) { h ^= labels[j]; h *= 1099511628211ull; }
+  h ^= (loff[i + 1] - loff[i]);
+  h = mix64(h);
+  hash[i] = h;
+  idx[i] = i;
+}
+__global__ void k_label_heads(uint32_t n, const uint64_t* __restrict__ hash_sorted, const uint32_t* __restrict__ idx,
+                              const uint64_t* __restrict__ loff, const uint32_t* __restrict__ labels,
+                              uint32_t* __restrict__ head) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t h = 1;
+  if (i > 0 && hash_sorted[i] == hash_sorted[i - 1]) {
+    const uint32_t a = idx[i], b = idx[i - 1];
+    const uint64_t la = loff[a + 1] - loff[a], lb = loff[b + 1] - loff[b];
+    if (la == lb) {
+      h = 0;
+      for (uint64_t j = 0; j < la; ++j) if (labels[loff[a] + j] != labels[loff[b] + j]) { h = 1; break; }
+    }
+  }
+  head[i] = h;
+}
+// per class: label length / weight length (for the output offsets)
+__global__ void k_class_sizes(uint32_t n, const uint32_t* __restrict__ head, const uint32_t* __restrict__ head_scan,
+                              const uint32_t* __restrict__ idx, const uint64_t* __restrict__ loff,
+                              const uint64_t* __restrict__ woff, uint32_t* __restrict__ first, uint64_t* __restrict__ llen,
+                              uint64_t* __restrict__ wlen) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !head[i]) return;
+  const uint32_t c = head_scan[i];
+  const uint32_t r = idx[i];
+  first[c] = i;
+  llen[c] = loff[r + 1] - loff[r];
+  wlen[c] = woff[r + 1] - woff[r];
+}
+// per class (one thread): count and weights summed over its records IN RECORD ORDER
+// (EquivalenceClassBuilder.hpp:237-250: count++, weights[i] += w_i)
+__global__ void k_class_reduce(uint32_t n_classes, uint32_t n, const uint32_t* __restrict__ first,
+                               const uint32_t* __restrict__ idx, const uint64_t* __restrict__ loff,
+                               const uint64_t* __restrict__ woff, const uint32_t* __restrict__ labels,
+                               const double* __restrict__ weights, const uint64_t* __restrict__ counts,
+                               const uint64_t* __restrict__ out_loff, const uint64_t* __restrict__ out_woff,
+                               uint32_t* __restrict__ out_labels, double* __restrict__ out_weights,
+                               uint64_t* __restrict__ out_counts) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_classes) return;
+  const uint32_t b = first[c], e = (c + 1 < n_classes) ? first[c + 1] : n;
+  const uint32_t r0 = idx[b];
+  const uint64_t ll = loff[r0 + 1] - loff[r0], wl = woff[r0 + 1] - woff[r0];
+  for (uint64_t j = 0; j < ll; ++j) out_labels[out_loff[c] + j] = labels[loff[r0] + j];
+  for (uint64_t j = 0; j < wl; ++j) out_weights[out_woff[c] + j] = 0.0;
+  uint64_t cnt = 0;
+  for (uint32_t q = b; q < e; ++q) {
+    const uint32_t r = idx[q];
+    cnt += counts ? counts[r] : 1ull;
+    for (uint64_t j = 0; j < wl; ++j) out_weights[out_woff[c] + j] = __dadd_rn(out_weights[out_woff[c] + j], weights[woff[r] + j]);
+  }
+  out_counts[c] = cnt;
+}
+// finish(): TGValue::normalizeAux (EquivalenceClassBuilder.hpp:114-123)
+__global__ void k_normalize(uint64_t n_classes, const uint64_t* __restrict__ woff, double* __restrict__ w) {
+  uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_classes) return;
+  double s = 0.0;
+  for (uint64_t j = woff[c]; j < woff[c + 1]; ++j) s = __dadd_rn(s, w[j]);
+  const double norm = __ddiv_rn(1.0, s);
+  for (uint64_t j = woff[c]; j < woff[c + 1]; ++j) w[j] = __dmul_rn(w[j], norm);
+}
+// compact per-read slots (n_aln entries used of cap) into CSR records
+__global__ void k_read_lengths(uint32_t n, const uint32_t* __restrict__ n_aln, int binned, uint64_t* __restrict__ ll,
+                               uint64_t* __restrict__ wl) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ll[i] = (uint64_t)n_aln[i] * (binned ? 2 : 1);
+  wl[i] = n_aln[i];
+}
+__global__ void k_read_compact(uint32_t n, uint32_t cap, const uint32_t* __restrict__ n_aln, int binned,
+                               const uint32_t* __restrict__ label, const double* __restrict__ weight,
+                               const uint64_t* __restrict__ loff, const uint64_t* __restrict__ woff,
+                               uint32_t* __restrict__ labels, double* __restrict__ weights) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t na = n_aln[i];
+  for (uint32_t a = 0; a < na * (binned ? 2u : 1u); ++a) labels[loff[i] + a] = label[(size_t)i * 2 * cap + a];
+  for (uint32_t a = 0; a < na; ++a) weights[woff[i] + a] = weight[(size_t)i * cap + a];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------
+struct EqStore {   // device CSR of class records
+  uint64_t n = 0, n_lab = 0, n_w = 0;
+  uint64_t* loff = nullptr; uint64_t* woff = nullptr;
+  uint32_t* labels = nullptr; double* weights = nullptr; uint64_t* counts = nullptr;
+  void free_all() {
+    cudaFree(loff); cudaFree(woff); cudaFree(labels); cudaFree(weights); cudaFree(counts);
+    loff = woff = nullptr; labels = nullptr; weights = nullptr; counts = nullptr; n = n_lab = n_w = 0;
+  }
+};
+
+struct sb_map_ctx {
+  int device = 0;
+  int n_sm = 0;
+  cudaStream_t stream = nullptr;
+  sb_index* index = nullptr;
+  Params p{};
+  uint32_t batch_cap = 0, read_len_cap = 0;
+  uint32_t k1_threads = 0;
+  BatchBufs b{};
+  uint8_t *d_left = nullptr, *d_right = nullptr;
+  // FLD tables
+  double* d_fld = nullptr;
+  FldView fld{};
+  // eq-class store: one EqStore per processed batch, merged at finish
+  std::vector<EqStore> stores;
+  uint64_t frag_counter = 0;     // fragments assigned so far (batched semantics)
+  Counters totals{};
+  uint32_t launches = 0;
+  float last_ms = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // finished result (host)
+  std::vector<uint64_t> h_off, h_counts;
+  std::vector<uint32_t> h_tids, h_ntx, h_bins;
+  std::vector<double> h_w;
+};
+
+#define SB_TRY(x) do { int _r = (x); if (_r != SB_OK) return _r; } while (0)
+template <typename T>
+static int dmalloc(T** p, size_t n) {
+  cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) { sb::set_error("cudaMalloc(%zu) failed: %s", n * sizeof(T), cudaGetErrorString(e)); return SB_ERR_NOMEM; }
+  return SB_OK;
+}
+static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+extern "C" void sb_map_default_params(sb_map_params* q) {
+  memset(q, 0, sizeof(*q));
+  q->k = 31; q->stride = 4; q->max_occs_per_hit = 1000; q->max_read_occ = 200; q->max_frag_len = 1000;
+  q->band = 15; q->chain_gap = 8; q->range_bins = 4; q->ma = 2; q->mp = -4; q->go = 6; q->ge = 2;
+  q->hard_filter = 0; q->first_decoy = 0x7fffffff; q->consensus_frac = 0.65; q->min_score_fraction = 0.65;
+  q->score_exp = 1.0; q->min_aln_prob = 1e-5; q->decoy_threshold = 1.0; q->fld_mean = 250.0; q->fld_sd = 25.0;
+  q->num_pre_burnin = 5000; q->num_burnin = 5000000;
+}
+
+static void build_fld_host(const Params& p, std::vector<double>& t) {
+  // FragmentLengthDistribution ctor / pmf / cmf / cached tables (FragmentLengthDistribution.cpp:22-78,
+  // :122-132, :163-201) and LogCMFCache's pre-burn-in table (DistributionUtils.cpp:103-116); host libm.
+  const uint32_t n = p.max_frag_len + 1;
+  const double LOG_0 = HUGE_VAL, LOG_EPSILON = log(0.375e-10);
+  auto logAdd = [&](double x, double y) {
+    if (fabs(x) == LOG_0) return y;
+    if (fabs(y) == LOG_0) return x;
+    if (y > x) std::swap(x, y);
+    return x + log(1 + exp(y - x));
+  };
+  auto ncdf = [&](double x) { return 0.5 * erfc(-(x - p.fld_mean) / (p.fld_sd * sqrt(2.0))); };
+  t.assign((size_t)4 * n, 0.0);
+  double* pmf_live = t.data(); double* pmf_cached = t.data() + n; double* cmf_cached = t.data() + 2 * n;
+  double* cmf_quirk = t.data() + 3 * n;
+  std::vector<double> hist(n);
+  double tot = LOG_0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const double nm = ncdf(i + 0.5) - ncdf(i - 0.5);
+    double mass = LOG_EPSILON;
+    if (nm != 0) mass = 0.0 + log(nm);
+    hist[i] = mass;
+    tot = logAdd(tot, mass);
+  }
+  double tm = LOG_0;
+  for (uint32_t i = 0; i < n; ++i) { pmf_live[i] = hist[i] - tot; tm = logAdd(tm, pmf_live[i]); }
+  double cum = LOG_0, cq = LOG_0;
+  for (uint32_t i = 0; i < n; ++i) {
+    pmf_cached[i] = pmf_live[i] - tm;
+    cum = logAdd(cum, pmf_cached[i]);
+    cmf_cached[i] = cum;
+    cq = logAdd(cq, LOG_EPSILON);
+    cmf_quirk[i] = cq;
+  }
+}
+
+extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int device, uint32_t batch_cap,
+                                     uint32_t max_read_len) {
+  if (!ix || !q) { sb::set_error("null argument"); return nullptr; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    sb::set_error("no CUDA device available (libsalmon_b200 has no CPU fallback)");
+    return nullptr;
+  }
+  if (q->band > 15 || q->max_read_occ > 255 || max_read_len > 256 || q->k != ix->k || batch_cap == 0 ||
+      batch_cap > (1u << 24)) {
+    sb::set_error("sb_map_create: unsupported parameters (band<=15, max_read_occ<=255, read_len<=256, k must match the index)");
+    return nullptr;
+  }
+  if (index_to_device(ix, device) != SB_OK) return nullptr;
+  sb_map_ctx* c = new sb_map_ctx();
+  c->device = device; c->index = ix; c->batch_cap = batch_cap; c->read_len_cap = max_read_len;
+  Params& p = c->p;
+  p.k = q->k; p.stride = q->stride; p.max_occs_per_hit = q->max_occs_per_hit; p.max_read_occ = q->max_read_occ;
+  p.max_frag_len = q->max_frag_len; p.band = q->band; p.chain_gap = q->chain_gap; p.range_bins = q->range_bins;
+  p.ma = q->ma; p.mp = q->mp; p.go = q->go; p.ge = q->ge; p.hard_filter = q->hard_filter; p.first_decoy = q->first_decoy;
+  p.consensus_frac = q->consensus_frac; p.min_score_fraction = q->min_score_fraction; p.score_exp = q->score_exp;
+  p.min_aln_prob = q->min_aln_prob; p.decoy_threshold = q->decoy_threshold; p.fld_mean = q->fld_mean; p.fld_sd = q->fld_sd;
+  p.num_pre_burnin = q->num_pre_burnin; p.num_burnin = q->num_burnin;
+  cudaSetDevice(device);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  c->n_sm = prop.multiProcessorCount;
+  cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+  const uint32_t cap = p.max_read_occ;
+  const size_t B = batch_cap;
+  c->k1_threads = (uint32_t)std::min<size_t>((size_t)c->n_sm * 1024, (B + 127) / 128 * 128);
+  BatchBufs& b = c->b;
+  int rc = SB_OK;
+  auto A = [&](auto** ptr, size_t n) { if (rc == SB_OK) rc = dmalloc(ptr, n); };
+  A(&b.n_l, B); A(&b.n_r, B); A(&b.cand_l, B * MAXCAND); A(&b.cand_r, B * MAXCAND);
+  A(&b.score_l, B * MAXCAND); A(&b.score_r, B * MAXCAND);
+  A(&b.keys, (size_t)MAXSEEDS * c->k1_threads);
+  A(&b.n_tasks, 4); A(&b.tasks, B * 2 * MAXCAND);
+  A(&b.n_aln, B); A(&b.tid, B * cap); A(&b.score, B * cap); A(&b.prob, B * cap); A(&b.pos, B * cap);
+  A(&b.mate_pos, B * cap); A(&b.flags, B * cap); A(&b.flen, B * cap); A(&b.label, B * 2 * cap); A(&b.weight, B * cap);
+  const size_t S = (size_t)c->k1_threads * cap;
+  A(&b.sc, S); A(&b.perm_idx, S); A(&b.perm_tid, S); A(&b.bs_tid, S); A(&b.bs_score, S); A(&b.bs_idx, S); A(&b.jh, S);
+  A(&b.ctr, 1);
+  A(&c->d_left, B * max_read_len); A(&c->d_right, B * max_read_len);
+  std::vector<double> t;
+  build_fld_host(p, t);
+  A(&c->d_fld, t.size());
+  if (rc != SB_OK) { delete c; return nullptr; }
+  cudaMemcpy(c->d_fld, t.data(), t.size() * 8, cudaMemcpyHostToDevice);
+  const uint32_t n = p.max_frag_len + 1;
+  c->fld.max_val = p.max_frag_len; c->fld.pmf_live = c->d_fld; c->fld.pmf_cached = c->d_fld + n;
+  c->fld.cmf_cached = c->d_fld + 2 * n; c->fld.cmf_quirk = c->d_fld + 3 * n;
+  cudaMemset(b.ctr, 0, sizeof(Counters));
+  return c;
+}
+
+extern "C" void sb_map_destroy(sb_map_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  BatchBufs& b = c->b;
+  void* ptrs[] = {b.n_l, b.n_r, b.cand_l, b.cand_r, b.score_l, b.score_r, b.keys, b.n_tasks, b.tasks, b.n_aln, b.tid,
+                  b.score, b.prob, b.pos, b.mate_pos, b.flags, b.flen, b.label, b.weight, b.sc, b.perm_idx, b.perm_tid,
+                  b.bs_tid, b.bs_score, b.bs_idx, b.jh, b.ctr, c->d_left, c->d_right, c->d_fld};
+  for (void* p : ptrs) cudaFree(p);
+  for (auto& s : c->stores) s.free_all();
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+// records -> classes (used per batch with counts == nullptr, and at finish over all batch classes)
+static int aggregate(sb_map_ctx* c, uint32_t n, const uint64_t* loff, const uint64_t* woff, const uint32_t* labels,
+                     const double* weights, const uint64_t* counts, EqStore& out) {
+  cudaStream_t st = c->stream;
+  out = EqStore();
+  if (n == 0) return SB_OK;
+  uint64_t *hash = nullptr, *hash2 = nullptr;
+  uint32_t *idx = nullptr, *idx2 = nullptr, *head = nullptr, *head_scan = nullptr, *first = nullptr;
+  uint64_t *llen = nullptr, *wlen = nullptr;
+  void* tmp = nullptr;
+  SB_TRY(dmalloc(&hash, n)); SB_TRY(dmalloc(&hash2, n)); SB_TRY(dmalloc(&idx, n)); SB_TRY(dmalloc(&idx2, n));
+  SB_TRY(dmalloc(&head, (size_t)n + 1)); SB_TRY(dmalloc(&head_scan, (size_t)n + 1));
+  k_label_hash<<<nblk(n, 256), 256, 0, st>>>(n, loff, labels, hash, idx);
+  size_t tb = 0, tb2 = 0, tb3 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, hash, hash2, idx, idx2, (int)n, 0, 64, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb2, head, head_scan, (int)n + 1, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb3, llen, llen, (int)n + 1, st);
+  tb = std::max(tb, std::max(tb2, tb3));
+  SB_CUDA(cudaMalloc(&tmp, tb));
+  size_t t = tb;
+  SB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t, hash, hash2, idx, idx2, (int)n, 0, 64, st));   // stable
+  k_label_heads<<<nblk(n, 256), 256, 0, st>>>(n, hash2, idx2, loff, labels, head);
+  SB_CUDA(cudaMemsetAsync(head + n, 0, 4, st));
+  t = tb;
+  SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, t, head, head_scan, (int)n + 1, st));
+  uint32_t nc = 0;
+  SB_CUDA(cudaMemcpyAsync(&nc, head_scan + n, 4, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  SB_TRY(dmalloc(&first, (size_t)nc + 1)); SB_TRY(dmalloc(&llen, (size_t)nc + 1)); SB_TRY(dmalloc(&wlen, (size_t)nc + 1));
+  SB_CUDA(cudaMemsetAsync(llen + nc, 0, 8, st)); SB_CUDA(cudaMemsetAsync(wlen + nc, 0, 8, st));
+  k_class_sizes<<<nblk(n, 256), 256, 0, st>>>(n, head, head_scan, idx2, loff, woff, first, llen, wlen);
+  SB_TRY(dmalloc(&out.loff, (size_t)nc + 1)); SB_TRY(dmalloc(&out.woff, (size_t)nc + 1));
+  t = tb;
+  SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, t, llen, out.loff, (int)nc + 1, st));
+  t = tb;
+  SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, t, wlen, out.woff, (int)nc + 1, st));
+  uint64_t tl = 0, tw = 0;
+  SB_CUDA(cudaMemcpyAsync(&tl, out.loff + nc, 8, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(&tw, out.woff + nc, 8, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  SB_TRY(dmalloc(&out.labels, tl)); SB_TRY(dmalloc(&out.weights, tw)); SB_TRY(dmalloc(&out.counts, nc));
+  k_class_reduce<<<nblk(nc, 128), 128, 0, st>>>(nc, n, first, idx2, loff, woff, labels, weights, counts, out.loff,
+                                                out.woff, out.labels, out.weights, out.counts);
+  SB_CUDA(cudaStreamSynchronize(st));
+  out.n = nc; out.n_lab = tl; out.n_w = tw;
+  c->launches += 12;
+  cudaFree(hash); cudaFree(hash2); cudaFree(idx); cudaFree(idx2); cudaFree(head); cudaFree(head_scan);
+  cudaFree(first); cudaFree(llen); cudaFree(wlen); cudaFree(tmp);
+  return SB_OK;
+}
+
+extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* right, uint32_t n, uint32_t L,
+                            sb_map_batch_stats* stats) {
+  if (!c || (n && (!left || !right))) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  if (n > c->batch_cap || L > c->read_len_cap || L < c->p.k) { sb::set_error("batch larger than the context was created for"); return SB_ERR_INVALID; }
+  SB_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  BatchBufs& b = c->b;
+  const Params& p = c->p;
+  SB_CUDA(cudaEventRecord(c->ev0, st));
+  SB_CUDA(cudaMemcpyAsync(c->d_left, left, (size_t)n * L, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(c->d_right, right, (size_t)n * L, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemsetAsync(b.n_tasks, 0, 16, st));
+  SB_CUDA(cudaMemsetAsync(b.ctr, 0, sizeof(Counters), st));
+  const IndexView ix = dev_view(c->index);
+  const uint32_t T = c->k1_threads;
+  if (n) {
+    k_seed_chain<<<T / 128, 128, 0, st>>>(ix, p, c->d_left, c->d_right, n, L, b);
+    k_dp_score<<<c->n_sm * 8, 256, 0, st>>>(ix, p, c->d_left, c->d_right, L, b);
+    const int useAux = c->frag_counter >= p.num_pre_burnin, burnedIn = c->frag_counter >= p.num_burnin;
+    k_assign<<<T / 128, 128, 0, st>>>(ix, p, c->fld, useAux, burnedIn, n, L, b);
+    c->launches += 3;
+  }
+  // eq-class records of this batch
+  EqStore es;
+  if (n) {
+    uint64_t *ll = nullptr, *wl = nullptr, *loff = nullptr, *woff = nullptr;
+    SB_TRY(dmalloc(&ll, (size_t)n + 1)); SB_TRY(dmalloc(&wl, (size_t)n + 1));
+    SB_TRY(dmalloc(&loff, (size_t)n + 1)); SB_TRY(dmalloc(&woff, (size_t)n + 1));
+    const int binned = p.range_bins > 0;
+    k_read_lengths<<<nblk(n, 256), 256, 0, st>>>(n, b.n_aln, binned, ll, wl);
+    SB_CUDA(cudaMemsetAsync(ll + n, 0, 8, st)); SB_CUDA(cudaMemsetAsync(wl + n, 0, 8, st));
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, ll, loff, (int)n + 1, st);
+    void* tmp = nullptr;
+    SB_CUDA(cudaMalloc(&tmp, tb));
+    size_t t = tb;
+    SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, t, ll, loff, (int)n + 1, st));
+    t = tb;
+    SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, t, wl, woff, (int)n + 1, st));
+    uint64_t tl = 0, tw = 0;
+    SB_CUDA(cudaMemcpyAsync(&tl, loff + n, 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(&tw, woff + n, 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    uint32_t* labels = nullptr; double* weights = nullptr;
+    SB_TRY(dmalloc(&labels, tl)); SB_TRY(dmalloc(&weights, tw));
+    k_read_compact<<<nblk(n, 256), 256, 0, st>>>(n, p.max_read_occ, b.n_aln, binned, b.label, b.weight, loff, woff,
+                                                 labels, weights);
+    c->launches += 4;
+    // reads without alignments have empty labels: they all hash alike and would form one
+    // "empty" class; aggregate() keeps it and finish() drops it.
+    int rc = aggregate(c, n, loff, woff, labels, weights, nullptr, es);
+    cudaFree(ll); cudaFree(wl); cudaFree(loff); cudaFree(woff); cudaFree(labels); cudaFree(weights); cudaFree(tmp);
+    if (rc != SB_OK) return rc;
+    c->stores.push_back(es);
+  }
+  Counters h;
+  SB_CUDA(cudaMemcpyAsync(&h, b.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaEventRecord(c->ev1, st));
+  SB_CUDA(cudaEventSynchronize(c->ev1));
+  cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+  c->frag_counter += h.mapped;
+  c->totals.lookups += h.lookups; c->totals.postings += h.postings; c->totals.seeds += h.seeds;
+  c->totals.candidates += h.candidates; c->totals.kept += h.kept; c->totals.label_entries += h.label_entries;
+  c->totals.mapped += h.mapped;
+  if (stats) {
+    stats->n_pairs = n; stats->mapped = h.mapped; stats->lookups = h.lookups; stats->postings = h.postings;
+    stats->seeds = h.seeds; stats->candidates = h.candidates; stats->kept = h.kept; stats->label_entries = h.label_entries;
+    stats->device_ms = c->last_ms; stats->gpu_launches = c->launches;
+    stats->n_batch_classes = es.n;
+  }
+  return SB_OK;
+}
+
+// debug / parity tap: per-read alignments of the LAST batch (arrays sized n*cap, label n*2*cap)
+extern "C" int sb_map_last_alignments(sb_map_ctx* c, uint32_t n, uint32_t* n_aln, uint32_t* tid, int32_t* score,
+                                      double* prob, int32_t* pos, int32_t* mate_pos, uint8_t* flags, int32_t* flen,
+                                      uint32_t* label, double* weight) {
+  if (!c) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  SB_CUDA(cudaSetDevice(c->device));
+  const size_t cap = c->p.max_read_occ;
+  BatchBufs& b = c->b;
+  if (n_aln) SB_CUDA(cudaMemcpy(n_aln, b.n_aln, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (tid) SB_CUDA(cudaMemcpy(tid, b.tid, n * cap * 4, cudaMemcpyDeviceToHost));
+  if (score) SB_CUDA(cudaMemcpy(score, b.score, n * cap * 4, cudaMemcpyDeviceToHost));
+  if (prob) SB_CUDA(cudaMemcpy(prob, b.prob, n * cap * 8, cudaMemcpyDeviceToHost));
+  if (pos) SB_CUDA(cudaMemcpy(pos, b.pos, n * cap * 4, cudaMemcpyDeviceToHost));
+  if (mate_pos) SB_CUDA(cudaMemcpy(mate_pos, b.mate_pos, n * cap * 4, cudaMemcpyDeviceToHost));
+  if (flags) SB_CUDA(cudaMemcpy(flags, b.flags, n * cap, cudaMemcpyDeviceToHost));
+  if (flen) SB_CUDA(cudaMemcpy(flen, b.flen, n * cap * 4, cudaMemcpyDeviceToHost));
+  if (label) SB_CUDA(cudaMemcpy(label, b.label, n * 2 * cap * 4, cudaMemcpyDeviceToHost));
+  if (weight) SB_CUDA(cudaMemcpy(weight, b.weight, n * cap * 8, cudaMemcpyDeviceToHost));
+  return SB_OK;
+}
+
+// finish(): merge the per-batch class tables, normalise weights (EquivalenceClassBuilder.hpp:165-181,
+// TGValue::normalizeAux :114-123), hand back a host CSR (sb_eq_csr-compatible).
+extern "C" int sb_map_finish(sb_map_ctx* c, sb_map_result* out) {
+  if (!c || !out) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  SB_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  // concatenate the batch stores
+  uint64_t n = 0, nl = 0, nw = 0;
+  for (auto& s : c->stores) { n += s.n; nl += s.n_lab; nw += s.n_w; }
+  EqStore merged;
+  if (n) {
+    uint64_t *loff = nullptr, *woff = nullptr, *counts = nullptr;
+    uint32_t* labels = nullptr; double* weights = nullptr;
+    SB_TRY(dmalloc(&loff, n + 1)); SB_TRY(dmalloc(&woff, n + 1)); SB_TRY(dmalloc(&counts, n));
+    SB_TRY(dmalloc(&labels, nl)); SB_TRY(dmalloc(&weights, nw));
+    std::vector<uint64_t> hl(n + 1), hw(n + 1);
+    uint64_t i = 0, ol = 0, ow = 0;
+    for (auto& s : c->stores) {
+      std::vector<uint64_t> tl(s.n + 1), tw(s.n + 1);
+      SB_CUDA(cudaMemcpy(tl.data(), s.loff, (s.n + 1) * 8, cudaMemcpyDeviceToHost));
+      SB_CUDA(cudaMemcpy(tw.data(), s.woff, (s.n + 1) * 8, cudaMemcpyDeviceToHost));
+      for (uint64_t q = 0; q < s.n; ++q) { hl[i + q] = ol + tl[q]; hw[i + q] = ow + tw[q]; }
+      SB_CUDA(cudaMemcpy(labels + ol, s.labels, s.n_lab * 4, cudaMemcpyDeviceToDevice));
+      SB_CUDA(cudaMemcpy(weights + ow, s.weights, s.n_w * 8, cudaMemcpyDeviceToDevice));
+      SB_CUDA(cudaMemcpy(counts + i, s.counts, s.n * 8, cudaMemcpyDeviceToDevice));
+      i += s.n; ol += s.n_lab; ow += s.n_w;
+    }
+    hl[n] = ol; hw[n] = ow;
+    SB_CUDA(cudaMemcpy(loff, hl.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(woff, hw.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
+    int rc = aggregate(c, (uint32_t)n, loff, woff, labels, weights, counts, merged);
+    cudaFree(loff); cudaFree(woff); cudaFree(counts); cudaFree(labels); cudaFree(weights);
+    if (rc != SB_OK) return rc;
+  }
+  if (merged.n) {
+    k_normalize<<<nblk(merged.n, 128), 128, 0, st>>>(merged.n, merged.woff, merged.weights);
+    c->launches++;
+  }
+  // to host (data movement only): drop the empty-label class, split label into tids | bins
+  const int binned = c->p.range_bins > 0;
+  std::vector<uint64_t> loff(merged.n + 1), woff(merged.n + 1), counts(merged.n);
+  std::vector<uint32_t> labels(merged.n_lab);
+  std::vector<double> weights(merged.n_w);
+  if (merged.n) {
+    SB_CUDA(cudaMemcpyAsync(loff.data(), merged.loff, (merged.n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(woff.data(), merged.woff, (merged.n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(counts.data(), merged.counts, merged.n * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(labels.data(), merged.labels, merged.n_lab * 4, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(weights.data(), merged.weights, merged.n_w * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+  }
+  c->h_off.assign(1, 0); c->h_counts.clear(); c->h_tids.clear(); c->h_ntx.clear(); c->h_bins.clear(); c->h_w.clear();
+  for (uint64_t q = 0; q < merged.n; ++q) {
+    const uint64_t ntx = woff[q + 1] - woff[q];
+    if (ntx == 0) continue;
+    for (uint64_t a = 0; a < ntx; ++a) {
+      c->h_tids.push_back(labels[loff[q] + a]);
+      c->h_w.push_back(weights[woff[q] + a]);
+      if (binned) c->h_bins.push_back(labels[loff[q] + ntx + a]);
+    }
+    c->h_off.push_back(c->h_tids.size());
+    c->h_counts.push_back(counts[q]);
+    c->h_ntx.push_back((uint32_t)ntx);
+  }
+  merged.free_all();
+  out->n_classes = c->h_counts.size();
+  out->off = c->h_off.data(); out->tids = c->h_tids.data(); out->weights = c->h_w.data();
+  out->counts = c->h_counts.data(); out->bins = binned ? c->h_bins.data() : nullptr;
+  out->n_mapped = c->totals.mapped;
+  out->lookups = c->totals.lookups; out->postings = c->totals.postings; out->seeds = c->totals.seeds;
+  out->candidates = c->totals.candidates; out->kept = c->totals.kept; out->label_entries = c->totals.label_entries;
+  return SB_OK;
+}

@@ -1,0 +1,541 @@
+// map_core.h -- Stage A per-read logic of the product (sm_100a device code; also compiles for
+// the host so that tests can run the SAME code against the independent oracle without a GPU).
+//
+// MAPSPEC (DESIGN.md "Stage A"): seeds sampled every `stride` bases -> hash lookup of the
+// canonical k-mer -> postings (transcript, offset) -> seeds keyed (tid, ori, diag, qpos) ->
+// sorted -> chains by single linkage on the diagonal -> candidates filtered by coverage ->
+// inward pairing (IU) or orphans -> banded affine glocal DP score per mate -> salmon's own
+// updateRefMappings / filterAndCollectAlignments / auxiliary-probability / label arithmetic
+// (include/salmon/internal/quant/SalmonMappingUtils.hpp:225-405, src/quant/SalmonQuantify.cpp:599-857).
+// The mapping core replaces pufferfish's MemCollector / MemChainer / joinReadsAndFilter /
+// PuffAligner (call sites src/quant/SalmonQuantify.cpp:1266-1288,1339-1341,1523), whose source
+// is not in the reference tree.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/sb_detmath.h"
+
+#ifndef __CUDACC__
+#include <math.h>
+#endif
+
+namespace sbmap {
+
+constexpr int MAXSEEDS = 2048;
+constexpr int MAXCAND = 64;
+constexpr int32_t NEG_SCORE = -(1 << 28);
+constexpr int32_t INVALID_SCORE = (-2147483647 - 1);
+constexpr uint64_t EMPTY_KEY = ~0ull;
+
+struct Params {
+  uint32_t k, stride, max_occs_per_hit, max_read_occ, max_frag_len, band, chain_gap, range_bins;
+  int32_t ma, mp, go, ge, hard_filter, first_decoy;
+  double consensus_frac, min_score_fraction, score_exp, min_aln_prob, decoy_threshold;
+  double fld_mean, fld_sd;
+  uint64_t num_pre_burnin, num_burnin;
+};
+
+struct TableEntry {
+  uint64_t key;   // canonical k-mer, EMPTY_KEY if free
+  uint32_t off;   // first posting
+  uint32_t cnt;   // number of postings
+};
+struct Posting {
+  uint32_t tid, tpos;
+};
+
+struct IndexView {
+  uint32_t n_txps, k;
+  uint64_t mask;             // table capacity - 1 (power of two)
+  const uint64_t* tx_off;    // [n_txps+1] base offsets into codes
+  const uint8_t* codes;      // one base per byte: 0..3, 4 = N
+  const TableEntry* table;
+  const Posting* post;       // ascending (tid, tpos) per k-mer
+};
+
+// FLD tables (log space), built on the host from the prior (FragmentLengthDistribution.cpp:22-78)
+struct FldView {
+  uint32_t max_val;
+  const double* pmf_live;    // hist - totMass                      (:122-132)
+  const double* pmf_cached;  // renormalised copy used after burn-in (:163-175)
+  const double* cmf_cached;  // (:190-201)
+  const double* cmf_quirk;   // LogCMFCache before burn-in (DistributionUtils.cpp:103-116)
+};
+
+struct Cand {
+  uint32_t tid;
+  int32_t diag_c;
+  uint32_t ori_cov;  // bit 31 = orientation (1 = read maps reverse-complemented), low bits = coverage
+};
+
+struct Counters {
+  unsigned long long lookups, postings, seeds, candidates, kept, label_entries, mapped;
+};
+
+SB_HD uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+
+SB_HD bool index_lookup(const IndexView& ix, uint64_t canon, uint32_t& off, uint32_t& cnt) {
+  uint64_t h = mix64(canon) & ix.mask;
+  for (;;) {
+    const TableEntry e = ix.table[h];
+    if (e.key == canon) { off = e.off; cnt = e.cnt; return true; }
+    if (e.key == EMPTY_KEY) return false;
+    h = (h + 1) & ix.mask;
+  }
+}
+
+// seed key: tid(32) | ori(1) | diag + 2^21 (22) | qpos (9)
+SB_HD uint64_t seed_key(uint32_t tid, uint32_t ori, int32_t diag, int32_t qpos) {
+  return ((uint64_t)tid << 32) | ((uint64_t)ori << 31) | ((uint64_t)(uint32_t)(diag + (1 << 21)) << 9) |
+         (uint64_t)(uint32_t)qpos;
+}
+SB_HD uint32_t key_tid(uint64_t k) { return (uint32_t)(k >> 32); }
+SB_HD uint32_t key_ori(uint64_t k) { return (uint32_t)(k >> 31) & 1u; }
+SB_HD int32_t key_diag(uint64_t k) { return (int32_t)((k >> 9) & 0x3fffffu) - (1 << 21); }
+SB_HD int32_t key_qpos(uint64_t k) { return (int32_t)(k & 0x1ffu); }
+
+// in-place heapsort of n u64 keys stored with a stride (interleaved per-thread scratch)
+SB_HD void heapsort_u64(uint64_t* a, size_t stride, uint32_t n) {
+  if (n < 2) return;
+  for (uint32_t start = n / 2; start-- > 0;) {
+    uint32_t root = start;
+    const uint64_t v = a[(size_t)root * stride];
+    for (;;) {
+      uint32_t child = 2 * root + 1;
+      if (child >= n) break;
+      if (child + 1 < n && a[(size_t)child * stride] < a[(size_t)(child + 1) * stride]) ++child;
+      if (v >= a[(size_t)child * stride]) break;
+      a[(size_t)root * stride] = a[(size_t)child * stride];
+      root = child;
+    }
+    a[(size_t)root * stride] = v;
+  }
+  for (uint32_t end = n - 1; end > 0; --end) {
+    const uint64_t v = a[(size_t)end * stride];
+    a[(size_t)end * stride] = a[0];
+    uint32_t root = 0;
+    for (;;) {
+      uint32_t child = 2 * root + 1;
+      if (child >= end) break;
+      if (child + 1 < end && a[(size_t)child * stride] < a[(size_t)(child + 1) * stride]) ++child;
+      if (v >= a[(size_t)child * stride]) break;
+      a[(size_t)root * stride] = a[(size_t)child * stride];
+      root = child;
+    }
+    a[(size_t)root * stride] = v;
+  }
+}
+
+// Seeds + chains of one mate.  read: L byte codes.  keys: scratch for MAXSEEDS keys (strided).
+// Returns the number of candidates written to out[] in (tid, ori, diag_c) order.
+SB_HD uint32_t mate_candidates(const IndexView& ix, const Params& p, const uint8_t* read, uint32_t L,
+                               uint64_t* keys, size_t kstride, Cand* out, Counters& ctr) {
+  const uint32_t K = p.k;
+  if (L < K) return 0;
+  uint32_t ns = 0;
+  for (uint32_t i = 0;; i += p.stride) {
+    uint32_t pos_i = i;
+    bool last = false;
+    if (i > L - K) {
+      if ((L - K) % p.stride == 0) break;
+      pos_i = L - K;
+      last = true;
+    }
+    uint64_t fw = 0, rc = 0;
+    bool bad = false;
+    for (uint32_t j = 0; j < K; ++j) {
+      const uint8_t c = read[pos_i + j];
+      if (c > 3) { bad = true; break; }
+      fw = (fw << 2) | c;
+      rc |= (uint64_t)(3 - c) << (2 * j);
+    }
+    if (!bad) {
+      const uint64_t canon = fw < rc ? fw : rc;
+      ctr.lookups++;
+      uint32_t off, cnt;
+      if (index_lookup(ix, canon, off, cnt) && cnt <= p.max_occs_per_hit) {
+        // first base where the k-mer and its reverse complement differ (k odd => exists)
+        uint32_t d = 0;
+        while (((fw >> (2 * (K - 1 - d))) & 3) == ((rc >> (2 * (K - 1 - d))) & 3)) ++d;
+        const uint8_t fw_d = (uint8_t)((fw >> (2 * (K - 1 - d))) & 3);
+        for (uint32_t q = 0; q < cnt && ns < (uint32_t)MAXSEEDS; ++q) {
+          ctr.postings++;
+          const Posting po = ix.post[off + q];
+          const uint8_t ref_d = ix.codes[ix.tx_off[po.tid] + po.tpos + d];
+          uint32_t ori;
+          int32_t qpos;
+          if (ref_d == fw_d) { ori = 0; qpos = (int32_t)pos_i; }
+          else { ori = 1; qpos = (int32_t)(L - K - pos_i); }
+          keys[(size_t)ns * kstride] = seed_key(po.tid, ori, (int32_t)po.tpos - qpos, qpos);
+          ++ns;
+        }
+      }
+    }
+    if (last) break;
+  }
+  ctr.seeds += ns;
+  heapsort_u64(keys, kstride, ns);
+  // chains -> candidates; coverage = bases of the read covered by the chain's seeds
+  uint32_t nc = 0, best = 0;
+  uint32_t i = 0;
+  // pass 1: best coverage (candidates are re-derived in pass 2 to avoid storing all of them)
+  for (int pass = 0; pass < 2; ++pass) {
+    i = 0;
+    nc = 0;
+    uint32_t n_over = 0;
+    while (i < ns) {
+      const uint64_t k0 = keys[(size_t)i * kstride];
+      uint64_t cover[4] = {0, 0, 0, 0};
+      int32_t dmin = key_diag(k0), dmax = dmin, prev = dmin;
+      uint32_t j = i;
+      while (j < ns) {
+        const uint64_t kj = keys[(size_t)j * kstride];
+        if (key_tid(kj) != key_tid(k0) || key_ori(kj) != key_ori(k0)) break;
+        const int32_t dj = key_diag(kj);
+        if (j > i && dj - prev > (int32_t)p.chain_gap) break;
+        prev = dj;
+        dmax = dj;
+        const int32_t q0 = key_qpos(kj);
+        for (uint32_t b = 0; b < K; ++b) {
+          const int32_t q = q0 + (int32_t)b;
+          if (q >= 0 && q < 256) cover[q >> 6] |= 1ull << (q & 63);
+        }
+        ++j;
+      }
+      uint32_t cov = 0;
+      for (int w = 0; w < 4; ++w) {
+#if defined(__CUDA_ARCH__)
+        cov += (uint32_t)__popcll(cover[w]);
+#else
+        cov += (uint32_t)__builtin_popcountll(cover[w]);
+#endif
+      }
+      if (pass == 0) {
+        if (cov > best) best = cov;
+      } else if ((double)cov >= p.consensus_frac * (double)best) {
+        if (nc < (uint32_t)MAXCAND) {
+          out[nc].tid = key_tid(k0);
+          out[nc].diag_c = dmin + (dmax - dmin) / 2;
+          out[nc].ori_cov = (key_ori(k0) << 31) | cov;
+          ++nc;
+        } else {
+          ++n_over;
+        }
+      }
+      i = j;
+    }
+    if (pass == 1 && n_over) {
+      // more than MAXCAND survivors: keep the MAXCAND best by (coverage desc, tid, ori, diag_c).
+      // Rare; done by re-walking the chains and replacing the current worst entry.
+      // (worst = smallest coverage, ties: largest (tid, ori, diag_c))
+      i = 0;
+      uint32_t seen = 0;
+      while (i < ns) {
+        const uint64_t k0 = keys[(size_t)i * kstride];
+        uint64_t cover[4] = {0, 0, 0, 0};
+        int32_t dmin = key_diag(k0), dmax = dmin, prev = dmin;
+        uint32_t j = i;
+        while (j < ns) {
+          const uint64_t kj = keys[(size_t)j * kstride];
+          if (key_tid(kj) != key_tid(k0) || key_ori(kj) != key_ori(k0)) break;
+          const int32_t dj = key_diag(kj);
+          if (j > i && dj - prev > (int32_t)p.chain_gap) break;
+          prev = dj; dmax = dj;
+          const int32_t q0 = key_qpos(kj);
+          for (uint32_t b = 0; b < K; ++b) {
+            const int32_t q = q0 + (int32_t)b;
+            if (q >= 0 && q < 256) cover[q >> 6] |= 1ull << (q & 63);
+          }
+          ++j;
+        }
+        uint32_t cov = 0;
+        for (int w = 0; w < 4; ++w) {
+#if defined(__CUDA_ARCH__)
+          cov += (uint32_t)__popcll(cover[w]);
+#else
+          cov += (uint32_t)__builtin_popcountll(cover[w]);
+#endif
+        }
+        if ((double)cov >= p.consensus_frac * (double)best) {
+          if (seen >= (uint32_t)MAXCAND) {
+            // candidate beyond the first MAXCAND: replace the worst kept one if this is better
+            uint32_t wi = 0;
+            for (uint32_t c = 1; c < (uint32_t)MAXCAND; ++c) {
+              const uint32_t cw = out[wi].ori_cov & 0x7fffffffu, cc = out[c].ori_cov & 0x7fffffffu;
+              const bool worse = cc < cw || (cc == cw && (out[c].tid > out[wi].tid ||
+                                 (out[c].tid == out[wi].tid && ((out[c].ori_cov >> 31) > (out[wi].ori_cov >> 31) ||
+                                 ((out[c].ori_cov >> 31) == (out[wi].ori_cov >> 31) && out[c].diag_c > out[wi].diag_c)))));
+              if (worse) wi = c;
+            }
+            const uint32_t cw = out[wi].ori_cov & 0x7fffffffu;
+            const int32_t dc = dmin + (dmax - dmin) / 2;
+            const bool better = cov > cw || (cov == cw && (key_tid(k0) < out[wi].tid ||
+                                (key_tid(k0) == out[wi].tid && (key_ori(k0) < (out[wi].ori_cov >> 31) ||
+                                (key_ori(k0) == (out[wi].ori_cov >> 31) && dc < out[wi].diag_c)))));
+            if (better) {
+              out[wi].tid = key_tid(k0);
+              out[wi].diag_c = dc;
+              out[wi].ori_cov = (key_ori(k0) << 31) | cov;
+            }
+          }
+          ++seen;
+        }
+        i = j;
+      }
+      // restore (tid, ori, diag_c) order (insertion sort, MAXCAND entries)
+      for (uint32_t a = 1; a < (uint32_t)MAXCAND; ++a) {
+        const Cand v = out[a];
+        uint32_t b = a;
+        while (b > 0) {
+          const Cand& u = out[b - 1];
+          const bool gt = u.tid > v.tid || (u.tid == v.tid && ((u.ori_cov >> 31) > (v.ori_cov >> 31) ||
+                          ((u.ori_cov >> 31) == (v.ori_cov >> 31) && u.diag_c > v.diag_c)));
+          if (!gt) break;
+          out[b] = out[b - 1];
+          --b;
+        }
+        out[b] = v;
+      }
+    }
+  }
+  return nc;
+}
+
+// ---- joint hits (library type IU).  Enumerated in the oracle's order: left-major.
+struct Joint {
+  uint32_t tid;
+  int32_t li, ri;       // candidate indices, -1 if absent
+  int32_t frag_len;
+  uint32_t status;      // 0 paired, 1 left orphan, 2 right orphan
+};
+
+// visits joint hits in order; F(const Joint&) ; returns the number of joint hits
+template <class F>
+SB_HD uint32_t for_each_joint(const Params& p, const Cand* lc, uint32_t nl, const Cand* rc, uint32_t nr,
+                              uint32_t L, F&& f) {
+  uint32_t nj = 0;
+  for (uint32_t a = 0; a < nl; ++a)
+    for (uint32_t b = 0; b < nr; ++b) {
+      if (lc[a].tid != rc[b].tid || (lc[a].ori_cov >> 31) == (rc[b].ori_cov >> 31)) continue;
+      int32_t start, end;
+      bool ok;
+      if ((lc[a].ori_cov >> 31) == 0) { start = lc[a].diag_c; end = rc[b].diag_c + (int32_t)L; ok = rc[b].diag_c >= lc[a].diag_c; }
+      else { start = rc[b].diag_c; end = lc[a].diag_c + (int32_t)L; ok = lc[a].diag_c >= rc[b].diag_c; }
+      const int32_t fl = end - start;
+      if (!ok || fl <= 0 || fl > (int32_t)p.max_frag_len) continue;
+      Joint j;
+      j.tid = lc[a].tid; j.li = (int32_t)a; j.ri = (int32_t)b; j.frag_len = fl; j.status = 0;
+      f(j, nj);
+      ++nj;
+    }
+  if (nj == 0) {
+    for (uint32_t a = 0; a < nl; ++a) {
+      Joint j; j.tid = lc[a].tid; j.li = (int32_t)a; j.ri = -1; j.frag_len = 0; j.status = 1;
+      f(j, nj); ++nj;
+    }
+    for (uint32_t b = 0; b < nr; ++b) {
+      Joint j; j.tid = rc[b].tid; j.li = -1; j.ri = (int32_t)b; j.frag_len = 0; j.status = 2;
+      f(j, nj); ++nj;
+    }
+  }
+  return nj;
+}
+
+// ---- banded affine glocal DP, serial form (host tests; device fallback).  The warp form in
+// map.cu computes the same recurrences with lanes = band cells.
+SB_HD int32_t dp_score_serial(const IndexView& ix, const Params& p, const uint8_t* read, uint32_t L,
+                              uint32_t ori, uint32_t tid, int32_t diag_c) {
+  const int32_t B = (int32_t)p.band, W = 2 * B + 1;
+  const int64_t tlen = (int64_t)(ix.tx_off[tid + 1] - ix.tx_off[tid]);
+  const uint8_t* ref = ix.codes + ix.tx_off[tid];
+  int32_t H[64], E[64];
+  for (int32_t j = 0; j < W; ++j) { H[j] = 0; E[j] = NEG_SCORE; }
+  for (uint32_t i = 0; i < L; ++i) {
+    const uint8_t c = ori ? read[L - 1 - i] : read[i];
+    const uint8_t rb = ori ? (uint8_t)(c > 3 ? 4 : 3 - c) : c;
+    int32_t Fprev = NEG_SCORE, Hleft = NEG_SCORE;
+    int32_t Hn_next_diag;  // H[j+1] of the previous row must be read before H[j+1] is overwritten
+    for (int32_t j = 0; j < W; ++j) {
+      const int64_t r = (int64_t)diag_c + (int64_t)i + (j - B);
+      const int32_t Hup = (j + 1 < W) ? H[j + 1] : NEG_SCORE;   // previous row, lane j+1 (not yet overwritten)
+      const int32_t Eup = (j + 1 < W) ? E[j + 1] : NEG_SCORE;
+      int32_t h = NEG_SCORE, e = NEG_SCORE, f = NEG_SCORE;
+      if (r >= 0 && r < tlen) {
+        const int32_t s = (rb < 4 && rb == ref[r]) ? p.ma : p.mp;
+        const int32_t m = H[j] + s;
+        if (j + 1 < W) { const int32_t a = Hup - p.go - p.ge, b = Eup - p.ge; e = a > b ? a : b; }
+        if (j > 0) { const int32_t a = Hleft - p.go - p.ge, b = Fprev - p.ge; f = a > b ? a : b; }
+        h = m;
+        if (e > h) h = e;
+        if (f > h) h = f;
+        if (h < NEG_SCORE) h = NEG_SCORE;
+        if (e < NEG_SCORE) e = NEG_SCORE;
+        if (f < NEG_SCORE) f = NEG_SCORE;
+      }
+      (void)Hn_next_diag;
+      H[j] = h; E[j] = e;     // lane j of the previous row is no longer needed (lane j-1 used H[j] already)
+      Hleft = h; Fprev = f;
+    }
+  }
+  int32_t best = NEG_SCORE;
+  for (int32_t j = 0; j < W; ++j) if (H[j] > best) best = H[j];
+  return best;
+}
+
+// ---- salmon-owned arithmetic on the log scale (deterministic exp/log, sb_detmath.h)
+SB_HD double log0() { return sb_u2d(0x7ff0000000000000ull); }   // LOG_0 = HUGE_VAL (SalmonMath.hpp:40)
+SB_HD double dabs(double x) { return x < 0 ? -x : x; }
+SB_HD double log_add(double x, double y) {                       // SalmonMath.hpp:54-66
+  if (dabs(x) == log0()) return y;
+  if (dabs(y) == log0()) return x;
+  if (y > x) { const double t = x; x = y; y = t; }
+  return x + sb_det_log(1 + sb_det_exp(y - x));
+}
+SB_HD double tabv(const double* t, uint32_t max_val, uint64_t len) { return t[len > max_val ? max_val : len]; }
+
+// Per-read output of the assignment step.  cap = max_read_occ entries per read.
+struct ReadOut {
+  uint32_t* n_aln;       // [1]
+  uint32_t* tid;         // [cap]
+  int32_t* score;        // [cap]
+  double* prob;          // [cap]
+  int32_t* pos;          // [cap]
+  int32_t* mate_pos;     // [cap]
+  uint8_t* flags;        // [cap]  bit0 fwd, bit1 mate fwd, bits 2-3 mate status
+  int32_t* flen;         // [cap]
+  uint32_t* label;       // [2*cap] transcripts then range bins
+  double* weight;        // [cap]
+};
+
+// updateRefMappings + filterAndCollectAlignments + auxiliary probabilities + label, for one read.
+// score_l / score_r: DP score per left / right candidate.  perm_* scratch: >= nj entries each.
+SB_HD void assign_read(const IndexView& ix, const Params& p, const FldView& fld, bool useAux, bool burnedIn,
+                       const Cand* lc, uint32_t nl, const Cand* rcd, uint32_t nr, const int32_t* score_l,
+                       const int32_t* score_r, uint32_t L, int32_t* sc, int32_t* perm_idx, int32_t* perm_tid,
+                       int32_t* bs_tid, int32_t* bs_score, int32_t* bs_idx, Joint* jh, const ReadOut& o,
+                       Counters& ctr) {
+  const double LOG_EPSILON = -24.006680182952184;   // log(0.375e-10), SalmonMath.hpp:44-45 (libm and sb_det_log agree)
+  const uint32_t cap = p.max_read_occ;
+  *o.n_aln = 0;
+  uint32_t nj = 0;
+  const uint32_t total = for_each_joint(p, lc, nl, rcd, nr, L, [&](const Joint& j, uint32_t k) {
+    if (k < cap) jh[k] = j;
+  });
+  nj = total;
+  if (nj == 0 || nj > cap) return;
+  // ---- SalmonMappingUtils.hpp:225-281
+  int32_t bestScore = INVALID_SCORE, bestDecoyScore = INVALID_SCORE;
+  uint32_t nperm = 0, nbs = 0;
+  for (uint32_t h = 0; h < nj; ++h) {
+    int32_t tot = 0, maxPossible = 0;
+    bool bad = false;
+    if (jh[h].li >= 0) { const int32_t s = score_l[jh[h].li]; if (s <= NEG_SCORE) bad = true; tot += s; maxPossible += p.ma * (int32_t)L; }
+    if (jh[h].ri >= 0) { const int32_t s = score_r[jh[h].ri]; if (s <= NEG_SCORE) bad = true; tot += s; maxPossible += p.ma * (int32_t)L; }
+    const int32_t hitScore = (!bad && (double)tot >= p.min_score_fraction * (double)maxPossible) ? tot : INVALID_SCORE;
+    sc[h] = hitScore;
+    const bool isDecoy = (int32_t)jh[h].tid >= p.first_decoy;
+    const double decoyCutoff = (double)(int32_t)(p.decoy_threshold * (double)bestDecoyScore);
+    if (isDecoy) { if (hitScore > bestDecoyScore) bestDecoyScore = hitScore; continue; }
+    if ((double)hitScore < decoyCutoff || hitScore == INVALID_SCORE) continue;
+    uint32_t q = 0;
+    while (q < nbs && bs_tid[q] != (int32_t)jh[h].tid) ++q;
+    if (q == nbs) { bs_tid[nbs] = (int32_t)jh[h].tid; bs_score[nbs] = hitScore; bs_idx[nbs] = (int32_t)h; ++nbs; }
+    else if (hitScore >= bs_score[q]) { bs_score[q] = hitScore; sc[bs_idx[q]] = INVALID_SCORE; bs_idx[q] = (int32_t)h; }  // isCompat is always true for IU
+    else { sc[h] = INVALID_SCORE; }
+    if (hitScore > bestScore) bestScore = hitScore;
+    perm_idx[nperm] = (int32_t)h; perm_tid[nperm] = (int32_t)jh[h].tid; ++nperm;
+  }
+  // ---- :283-405
+  if (bestDecoyScore == INVALID_SCORE) bestDecoyScore = INVALID_SCORE + 1;
+  const int32_t decoyThreshold = (int32_t)(p.decoy_threshold * (double)bestDecoyScore);
+  const int32_t scoreThreshold = p.hard_filter ? bestScore : decoyThreshold;
+  uint32_t nk = 0;
+  for (uint32_t q = 0; q < nperm; ++q)
+    if (sc[perm_idx[q]] >= scoreThreshold) { perm_idx[nk] = perm_idx[q]; perm_tid[nk] = perm_tid[q]; ++nk; }
+  for (uint32_t a = 1; a < nk; ++a) {   // sort by transcript id (unique after the dedup above)
+    const int32_t vi = perm_idx[a], vt = perm_tid[a];
+    uint32_t b = a;
+    while (b > 0 && perm_tid[b - 1] > vt) { perm_idx[b] = perm_idx[b - 1]; perm_tid[b] = perm_tid[b - 1]; --b; }
+    perm_idx[b] = vi; perm_tid[b] = vt;
+  }
+  uint32_t na = 0;
+  for (uint32_t q = 0; q < nk; ++q) {
+    const Joint& j = jh[perm_idx[q]];
+    const double v = (double)bestScore - (double)sc[perm_idx[q]];
+    const double estAlnProb = p.hard_filter ? -1.0 : sb_det_exp(-p.score_exp * v);
+    if (!p.hard_filter && estAlnProb < p.min_aln_prob) continue;
+    const Cand& first = (j.status == 2) ? rcd[j.ri] : lc[j.li];
+    o.tid[na] = j.tid;
+    o.score[na] = sc[perm_idx[q]];
+    o.prob[na] = estAlnProb;
+    o.pos[na] = first.diag_c;
+    o.mate_pos[na] = (j.status == 0) ? rcd[j.ri].diag_c : 0;
+    uint8_t fl = (uint8_t)(((first.ori_cov >> 31) == 0) ? 1 : 0);
+    if (j.status == 0 && (rcd[j.ri].ori_cov >> 31) == 0) fl |= 2;
+    fl |= (uint8_t)(j.status << 2);
+    o.flags[na] = fl;
+    o.flen[na] = j.frag_len;
+    ++na;
+  }
+  *o.n_aln = na;
+  ctr.kept += na;
+  if (na == 0) return;
+  ctr.mapped++;
+  ctr.label_entries += na;
+  // ---- SalmonQuantify.cpp:599-857 (state frozen per batch); aux kept in o.weight until normalised
+  double auxDenom = log0();
+  for (uint32_t a = 0; a < na; ++a) {
+    const uint32_t tid = o.tid[a];
+    const int32_t refLen = (int32_t)(ix.tx_off[tid + 1] - ix.tx_off[tid]);
+    const double refLength = refLen > 0 ? (double)refLen : 1.0;
+    const uint32_t status = (o.flags[a] >> 2) & 3;
+    const int fwd = o.flags[a] & 1, mateFwd = (o.flags[a] >> 1) & 1;
+    const double coverage = o.prob[a];
+    const double logFragCov = (coverage > 0) ? sb_det_log(coverage) : 0.0;
+    int32_t flen = o.flen[a];
+    if (status == 0 && fwd != mateFwd) {
+      const int32_t pos = o.pos[a], mpos = o.mate_pos[a];
+      int32_t p1 = fwd ? pos : mpos; p1 = p1 < 0 ? 0 : p1; p1 = p1 > refLen ? refLen : p1;
+      int32_t p2 = fwd ? mpos + (int32_t)L : pos + (int32_t)L; p2 = p2 < 0 ? 0 : p2; p2 = p2 > refLen ? refLen : p2;
+      flen = (p1 > p2) ? p1 - p2 : p2 - p1;
+    }
+    double logFragProb = 0.0;
+    if (status != 0) {
+      const int32_t pos = o.pos[a];
+      int32_t maxFragLen;
+      if (fwd) { int32_t p1 = pos < 0 ? 0 : pos; p1 = p1 > refLen ? refLen : p1; maxFragLen = refLen - p1; }
+      else { int32_t p1 = pos + (int32_t)L; p1 = p1 < 0 ? 0 : p1; p1 = p1 > refLen ? refLen : p1; maxFragLen = p1; }
+      const double* cm = burnedIn ? fld.cmf_cached : fld.cmf_quirk;
+      const double refLengthCM = tabv(cm, fld.max_val, (uint64_t)refLen);
+      const double maxLenProb = tabv(cm, fld.max_val, (uint64_t)maxFragLen);
+      logFragProb = (refLengthCM != log0()) ? (maxLenProb - refLengthCM) : LOG_EPSILON;
+    }
+    if (flen > 0 && (burnedIn || useAux)) {
+      const uint64_t fl = (uint64_t)flen;
+      if (burnedIn) {
+        const double lenProb = tabv(fld.pmf_cached, fld.max_val, fl);
+        const double refLengthCM = tabv(fld.cmf_cached, fld.max_val, fl);
+        const bool computeMass = ((double)fl < refLength) && (refLengthCM != log0());
+        logFragProb = computeMass ? (lenProb - refLengthCM) : LOG_EPSILON;
+      } else {
+        logFragProb = tabv(fld.pmf_live, fld.max_val, fl);
+      }
+    }
+    const double aux = logFragProb + logFragCov + 0.0;
+    o.weight[a] = aux;
+    auxDenom = log_add(auxDenom, aux);
+  }
+  for (uint32_t a = 0; a < na; ++a) {
+    o.weight[a] = sb_det_exp(o.weight[a] - auxDenom);
+    o.label[a] = o.tid[a];
+  }
+  if (p.range_bins > 0) {
+    const int32_t rangeCount = (int32_t)sqrt((double)na) + (int32_t)p.range_bins;
+    for (uint32_t a = 0; a < na; ++a) o.label[na + a] = (uint32_t)(int32_t)(o.weight[a] * rangeCount);
+  }
+}
+
+}  // namespace sbmap

@@ -79,3 +79,83 @@ def shard_classes(eq: EqClasses, rank: int, nranks: int) -> EqClasses:
     starts = eq.off[:-1].astype(np.int64)[sel]
     idx = np.repeat(starts - off[:-1].astype(np.int64), s) + np.arange(int(off[-1]))
     return EqClasses(eq.n_txps, off, eq.tids[idx], eq.weights[idx], eq.counts[sel])
+
+
+# --------------------------------------------------------------------------------------
+# Stage A: synthetic transcriptome and paired-end reads
+# --------------------------------------------------------------------------------------
+_COMP = np.array([3, 2, 1, 0], dtype=np.uint8)   # A<->T, C<->G in 2-bit codes (A=0,C=1,G=2,T=3)
+
+
+def synth_txome(seed=44, n_genes=2000, max_isoforms=12, exon_mu=5.0, exon_sigma=0.8, min_len=300):
+    """Genes own a pool of exons; isoforms are ordered subsets of the pool, so isoforms of a
+    gene share >= k-mers (realistic multi-mapping).  Returns a list of uint8 arrays (2-bit codes)."""
+    rng = np.random.default_rng(seed)
+    txps = []
+    gene_of = []
+    for g in range(n_genes):
+        n_ex = int(rng.integers(3, 16))
+        exons = [rng.integers(0, 4, size=max(40, int(rng.lognormal(exon_mu, exon_sigma))), dtype=np.uint8)
+                 for _ in range(n_ex)]
+        n_iso = int(min(max_isoforms, 1 + rng.zipf(1.6)))
+        for _ in range(n_iso):
+            keep = rng.random(n_ex) < 0.7
+            keep[rng.integers(0, n_ex)] = True
+            seq = np.concatenate([e for e, k in zip(exons, keep) if k])
+            if seq.shape[0] < min_len:
+                seq = np.concatenate([seq, rng.integers(0, 4, size=min_len - seq.shape[0], dtype=np.uint8)])
+            txps.append(seq)
+            gene_of.append(g)
+    return txps, np.array(gene_of)
+
+
+def revcomp(codes):
+    return _COMP[codes[::-1]]
+
+
+def synth_reads(txps, seed=7, n=10000, read_len=100, frag_mean=250.0, frag_sd=25.0, sub_rate=0.005,
+                indel_rate=0.0001, random_frac=0.03, expressed_frac=0.4):
+    """IU (inward, unstranded) pairs.  Returns (left [n,L] uint8, right [n,L] uint8, truth dict)."""
+    rng = np.random.default_rng(seed)
+    N = len(txps)
+    lens = np.array([t.shape[0] for t in txps])
+    expr = np.zeros(N)
+    ex = rng.choice(N, size=max(1, int(N * expressed_frac)), replace=False)
+    expr[ex] = rng.lognormal(0.0, 2.0, size=ex.shape[0])
+    w = expr * np.maximum(lens - frag_mean, 1.0)
+    cdf = np.cumsum(w)
+    left = np.zeros((n, read_len), dtype=np.uint8)
+    right = np.zeros((n, read_len), dtype=np.uint8)
+    t_tid = np.full(n, -1, dtype=np.int64)
+    t_pos = np.zeros(n, dtype=np.int64)
+    t_flen = np.zeros(n, dtype=np.int64)
+
+    def mutate(r):
+        r = r.copy()
+        m = rng.random(r.shape[0]) < sub_rate
+        r[m] = (r[m] + rng.integers(1, 4, size=int(m.sum()))) % 4
+        if indel_rate > 0 and rng.random() < indel_rate * r.shape[0]:
+            p = int(rng.integers(5, r.shape[0] - 5))
+            if rng.random() < 0.5:   # deletion in the read: shift left, pad with random base
+                r = np.concatenate([r[:p], r[p + 1:], rng.integers(0, 4, size=1, dtype=np.uint8)])
+            else:                    # insertion
+                r = np.concatenate([r[:p], rng.integers(0, 4, size=1, dtype=np.uint8), r[p:-1]])
+        return r.astype(np.uint8)
+
+    for i in range(n):
+        if rng.random() < random_frac:
+            left[i] = rng.integers(0, 4, size=read_len); right[i] = rng.integers(0, 4, size=read_len)
+            continue
+        t = int(np.searchsorted(cdf, rng.random() * cdf[-1], side="right"))
+        t = min(t, N - 1)
+        L = lens[t]
+        fl = int(np.clip(round(rng.normal(frag_mean, frag_sd)), read_len, min(1000, L)))
+        pos = int(rng.integers(0, L - fl + 1))
+        frag = txps[t][pos:pos + fl]
+        a = frag[:read_len]
+        b = revcomp(frag[-read_len:])
+        if rng.random() < 0.5:       # unstranded: fragment from the reverse strand
+            a, b = b, a
+        left[i] = mutate(a); right[i] = mutate(b)
+        t_tid[i] = t; t_pos[i] = pos; t_flen[i] = fl
+    return left, right, dict(tid=t_tid, pos=t_pos, flen=t_flen)

@@ -152,3 +152,97 @@ def gibbs(eq, valid, eff_len, alphas_init, use_vbem, per_txp_prior, vb_prior, n_
                        C.c_int(no_gamma_draw), C.c_double(num_mapped_frags), C.c_uint64(seed), _p(out))
     assert rc == 0
     return out
+
+
+# ---------------------------------------------------------------------------- Stage A
+class orc_map_params(C.Structure):
+    _fields_ = [
+        ("k", C.c_uint32), ("stride", C.c_uint32), ("max_occs_per_hit", C.c_uint32), ("max_read_occ", C.c_uint32),
+        ("max_frag_len", C.c_uint32), ("band", C.c_uint32), ("chain_gap", C.c_uint32), ("range_bins", C.c_uint32),
+        ("ma", C.c_int32), ("mp", C.c_int32), ("go", C.c_int32), ("ge", C.c_int32),
+        ("hard_filter", C.c_int32), ("first_decoy", C.c_int32),
+        ("consensus_frac", C.c_double), ("min_score_fraction", C.c_double), ("score_exp", C.c_double),
+        ("min_aln_prob", C.c_double), ("decoy_threshold", C.c_double), ("fld_mean", C.c_double), ("fld_sd", C.c_double),
+        ("num_pre_burnin", C.c_uint64), ("num_burnin", C.c_uint64),
+    ]
+
+
+class orc_map_counters(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("lookups", "postings", "seeds", "candidates", "kept", "label_entries", "mapped")]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+MAP_DEFAULTS = dict(k=31, stride=4, max_occs_per_hit=1000, max_read_occ=200, max_frag_len=1000, band=15, chain_gap=8,
+                    range_bins=4, ma=2, mp=-4, go=6, ge=2, hard_filter=0, first_decoy=2**31 - 1, consensus_frac=0.65,
+                    min_score_fraction=0.65, score_exp=1.0, min_aln_prob=1e-5, decoy_threshold=1.0, fld_mean=250.0,
+                    fld_sd=25.0, num_pre_burnin=5000, num_burnin=5000000)
+
+
+def map_params(**over):
+    p = orc_map_params()
+    d = dict(MAP_DEFAULTS); d.update(over)
+    for k, v in d.items():
+        setattr(p, k, v)
+    return p
+
+
+def pack_txome(txps):
+    lens = np.array([t.shape[0] for t in txps], dtype=np.uint64)
+    off = np.concatenate(([0], np.cumsum(lens))).astype(np.uint64)
+    codes = np.ascontiguousarray(np.concatenate(txps).astype(np.uint8))
+    return off, codes
+
+
+class MapIndex:
+    def __init__(self, txps, k=31):
+        lib = load()
+        lib.orc_index_build.restype = C.c_void_p
+        lib.orc_index_n_kmers.restype = C.c_uint64
+        lib.orc_index_n_kmers.argtypes = [C.c_void_p]
+        self.off, self.codes = pack_txome(txps)
+        self.n = len(txps)
+        self.h = C.c_void_p(lib.orc_index_build(C.c_uint32(self.n), _p(self.off), _p(self.codes), C.c_uint32(k)))
+        self.n_kmers = lib.orc_index_n_kmers(self.h)
+
+    def __del__(self):
+        try:
+            load().orc_index_free.argtypes = [C.c_void_p]
+            load().orc_index_free(self.h)
+        except Exception:
+            pass
+
+
+def map_reads(index, p, left, right, frag_counter=0):
+    lib = load()
+    n, L = left.shape
+    cap = p.max_read_occ
+    left = np.ascontiguousarray(left, dtype=np.uint8); right = np.ascontiguousarray(right, dtype=np.uint8)
+    out = dict(n_aln=np.zeros(n, dtype=np.uint32), tid=np.zeros((n, cap), dtype=np.uint32),
+               score=np.zeros((n, cap), dtype=np.int32), prob=np.zeros((n, cap)), pos=np.zeros((n, cap), dtype=np.int32),
+               mate_pos=np.zeros((n, cap), dtype=np.int32), flags=np.zeros((n, cap), dtype=np.uint8),
+               flen=np.zeros((n, cap), dtype=np.int32), label=np.zeros((n, 2 * cap), dtype=np.uint32),
+               weight=np.zeros((n, cap)))
+    ctr = orc_map_counters()
+    rc = lib.orc_map_reads(index.h, C.byref(p), _p(left), _p(right), C.c_uint32(n), C.c_uint32(L),
+                           C.c_uint64(frag_counter), _p(out["n_aln"]), _p(out["tid"]), _p(out["score"]),
+                           _p(out["prob"]), _p(out["pos"]), _p(out["mate_pos"]), _p(out["flags"]), _p(out["flen"]),
+                           _p(out["label"]), _p(out["weight"]), C.byref(ctr))
+    assert rc == 0
+    out["counters"] = ctr.asdict()
+    return out
+
+
+def eq_aggregate(m, cap, binned=True):
+    lib = load()
+    lib.orc_eq_aggregate.restype = C.c_uint64
+    n = m["n_aln"].shape[0]
+    tot = int(m["n_aln"].sum())
+    off = np.zeros(n + 1, dtype=np.uint64); ntx = np.zeros(n, dtype=np.uint32)
+    lab = np.zeros(max(tot, 1), dtype=np.uint32); w = np.zeros(max(tot, 1)); cnt = np.zeros(n, dtype=np.uint64)
+    nc = lib.orc_eq_aggregate(C.c_uint32(n), C.c_uint32(cap), C.c_int(1 if binned else 0), _p(m["n_aln"]),
+                              _p(m["label"]), _p(m["weight"]), _p(off), _p(ntx), _p(lab), _p(w), _p(cnt))
+    nc = int(nc)
+    nn = int(off[nc])
+    return dict(off=off[:nc + 1].copy(), ntx=ntx[:nc].copy(), tids=lab[:nn].copy(), weights=w[:nn].copy(), counts=cnt[:nc].copy())

@@ -1,0 +1,152 @@
+"""GPU parity of Stage A (mapping -> scoring -> filtering -> labels -> equivalence classes) against
+the oracle: per-read alignments, scores, probabilities, labels, weights bit-exact; class labels and
+counts bit-exact; class weights bit-exact within one batch (same summation order) and 1e-12 across
+batches (batch-wise association)."""
+import numpy as np
+import pytest
+
+from salmon_b200 import EMContext, default_params
+from salmon_b200._capi import EqClasses, Index, MapContext, map_default_params
+from salmon_b200.synth import synth_reads, synth_txome
+from test_map_host import compare
+
+pytestmark = pytest.mark.gpu
+
+
+def canon(res):
+    """classes as a list sorted by full label (tids ++ bins)."""
+    off = res["off"].astype(np.int64)
+    out = []
+    for c in range(len(res["counts"])):
+        t = tuple(res["tids"][off[c]:off[c + 1]].tolist())
+        b = tuple(res["bins"][off[c]:off[c + 1]].tolist()) if res.get("bins") is not None else ()
+        out.append((t + b, t, res["weights"][off[c]:off[c + 1]].copy(), int(res["counts"][c])))
+    out.sort(key=lambda x: (x[0]))
+    return out
+
+
+def oracle_classes(oracle, m, cap, binned=True):
+    e = oracle.eq_aggregate(m, cap, binned)
+    # recover bins from the first fragment of each class is not needed: orc_eq_aggregate sorts by full label
+    return e
+
+
+def check_classes(got, ref_e, exact_weights=True):
+    g = canon(got)
+    assert len(g) == len(ref_e["counts"])
+    off = ref_e["off"].astype(np.int64)
+    for c, (lab, t, w, cnt) in enumerate(g):
+        assert list(t) == ref_e["tids"][off[c]:off[c + 1]].tolist()
+        assert cnt == int(ref_e["counts"][c])
+        rw = ref_e["weights"][off[c]:off[c + 1]]
+        if exact_weights:
+            assert np.array_equal(w.view(np.uint64), rw.view(np.uint64))
+        else:
+            np.testing.assert_allclose(w, rw, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("frag_counter_reads", [0, 1])
+def test_single_batch_bit_exact(oracle, frag_counter_reads):
+    txps, _ = synth_txome(seed=3, n_genes=200)
+    left, right, truth = synth_reads(txps, seed=5, n=6000, indel_rate=0.002)
+    p = map_default_params(num_pre_burnin=0 if frag_counter_reads else 5000)
+    idx = Index(txps)
+    ctx = MapContext(idx, p, batch_cap=8192, max_read_len=100)
+    st = ctx.map_batch(left, right)
+    got = ctx.last_alignments()
+    oix = oracle.MapIndex(txps)
+    op = oracle.map_params(num_pre_burnin=0 if frag_counter_reads else 5000)
+    ref = oracle.map_reads(oix, op, left, right, 0)
+    compare(got, ref, p.max_read_occ)
+    for k in ("lookups", "postings", "seeds", "kept", "label_entries", "mapped"):
+        assert getattr(st, k) == ref["counters"][k], k
+    res = ctx.finish()
+    check_classes(res, oracle.eq_aggregate(ref, p.max_read_occ, True), exact_weights=True)
+    assert res["counters"]["n_mapped"] == ref["counters"]["mapped"]
+    assert st.gpu_launches > 0
+    ctx.close()
+
+
+def test_multi_batch_and_regimes(oracle):
+    """three batches; the fragment counter crosses numPreBurninFrags between them (batched semantics)."""
+    txps, _ = synth_txome(seed=4, n_genes=120)
+    left, right, _ = synth_reads(txps, seed=6, n=9000)
+    p = map_default_params(num_pre_burnin=2500, num_burnin=5500)
+    idx = Index(txps)
+    ctx = MapContext(idx, p, batch_cap=3000, max_read_len=100)
+    oix = oracle.MapIndex(txps)
+    op = oracle.map_params(num_pre_burnin=2500, num_burnin=5500)
+    fc = 0
+    parts = []
+    for b in range(3):
+        sl = slice(3000 * b, 3000 * (b + 1))
+        st = ctx.map_batch(left[sl], right[sl])
+        ref = oracle.map_reads(oix, op, left[sl], right[sl], fc)
+        compare(ctx.last_alignments(), ref, p.max_read_occ)
+        fc += ref["counters"]["mapped"]
+        parts.append(ref)
+    res = ctx.finish()
+    cap = p.max_read_occ
+    merged = {k: np.concatenate([q[k] for q in parts]) for k in ("n_aln", "label", "weight")}
+    check_classes(res, oracle.eq_aggregate(merged, cap, True), exact_weights=False)
+    ctx.close()
+
+
+def test_edge_cases_gpu(oracle):
+    rng = np.random.default_rng(9)
+    unit = rng.integers(0, 4, size=400, dtype=np.uint8)
+    txps = [unit.copy() for _ in range(90)]
+    txps += [np.concatenate([unit[:200], rng.integers(0, 4, size=150, dtype=np.uint8)]) for _ in range(130)]
+    txps += [rng.integers(0, 4, size=20, dtype=np.uint8)]
+    withn = rng.integers(0, 4, size=500, dtype=np.uint8); withn[100:103] = 4
+    txps += [withn]
+    left, right, _ = synth_reads(txps, seed=2, n=500, read_len=75, frag_mean=180, frag_sd=15, random_frac=0.1)
+    left[5, 10] = 4; right[7, 60] = 4
+    for over in (dict(), dict(max_read_occ=50, max_occs_per_hit=64, stride=3, range_bins=0),
+                 dict(first_decoy=200, decoy_threshold=0.9), dict(hard_filter=1)):
+        p = map_default_params(**over)
+        idx = Index(txps)
+        ctx = MapContext(idx, p, batch_cap=512, max_read_len=75)
+        ctx.map_batch(left, right)
+        ref = oracle.map_reads(oracle.MapIndex(txps), oracle.map_params(**over), left, right, 0)
+        compare(ctx.last_alignments(), ref, p.max_read_occ)
+        res = ctx.finish()
+        check_classes(res, oracle.eq_aggregate(ref, p.max_read_occ, p.range_bins > 0), exact_weights=True)
+        ctx.close()
+    # an empty batch and a batch of unmappable reads
+    p = map_default_params()
+    idx = Index(txps)
+    ctx = MapContext(idx, p, batch_cap=64, max_read_len=75)
+    junk = rng.integers(0, 4, size=(32, 75), dtype=np.uint8)
+    st = ctx.map_batch(junk, junk)
+    assert st.mapped == 0
+    res = ctx.finish()
+    assert len(res["counts"]) == 0
+    ctx.close()
+
+
+def test_map_then_em_end_to_end(oracle):
+    """config-1-style plumbing: reads -> eq classes (GPU) -> VBEM (GPU) vs the oracle chain."""
+    txps, _ = synth_txome(seed=11, n_genes=150)
+    left, right, _ = synth_reads(txps, seed=12, n=8000)
+    p = map_default_params()
+    idx = Index(txps)
+    ctx = MapContext(idx, p, batch_cap=8192, max_read_len=100)
+    ctx.map_batch(left, right)
+    res = ctx.finish()
+    ctx.close()
+    M = len(txps)
+    eq = EqClasses(M, res["off"], res["tids"], res["weights"], res["counts"])
+    lens = np.array([t.shape[0] for t in txps], dtype=np.float64)
+    eff = np.maximum(1.0, lens - 250.0 + 1.0)
+    sizes = (eq.off[1:] - eq.off[:-1]).astype(np.int64)
+    proj = np.bincount(eq.tids, weights=np.repeat(eq.counts.astype(float), sizes) * eq.weights, minlength=M)
+    uniq = np.bincount(eq.tids[np.repeat(sizes == 1, sizes)], weights=eq.counts[sizes == 1].astype(float),
+                       minlength=M).astype(np.uint64)
+    em = EMContext(0)
+    alpha, st, ok = em.optimize(eq, default_params(), proj, eff, uniq)
+    ref, rst = oracle.em_optimize(eq, proj, eff, uniq, default_params())
+    assert ok and st.iters == rst.iters
+    np.testing.assert_allclose(alpha, ref, rtol=1e-9, atol=1e-9)
+    assert abs(alpha.sum() - float(eq.counts.sum())) < 1e-6 * float(eq.counts.sum())
+    em.close()

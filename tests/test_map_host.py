@@ -1,0 +1,91 @@
+"""CPU tests of Stage A: the product's per-read logic (map_core.h compiled for the host) against the
+independent oracle -- bit-exact alignments, scores, probabilities, labels and weights."""
+import numpy as np
+import pytest
+
+from salmon_b200._capi import Index, map_default_params
+from salmon_b200.synth import synth_reads, synth_txome
+
+
+def compare(a, b, cap):
+    assert np.array_equal(a["n_aln"], b["n_aln"])
+    n = a["n_aln"].shape[0]
+    m = np.arange(cap)[None, :] < a["n_aln"][:, None]
+    for k in ("tid", "score", "pos", "mate_pos", "flags", "flen"):
+        assert np.array_equal(a[k][m], b[k][m]), k
+    assert np.array_equal(a["prob"][m].view(np.uint64), b["prob"][m].view(np.uint64))
+    assert np.array_equal(a["weight"][m].view(np.uint64), b["weight"][m].view(np.uint64))
+    m2 = np.arange(2 * cap)[None, :] < 2 * a["n_aln"][:, None]
+    assert np.array_equal(a["label"][m2], b["label"][m2])
+
+
+def run_both(oracle, txps, left, right, frag_counter=0, **over):
+    import hostmap_lib
+    idx = Index(txps, k=over.get("k", 31))
+    p = map_default_params(**over)
+    got = hostmap_lib.map_reads(idx, p, left, right, frag_counter)
+    oix = oracle.MapIndex(txps, k=over.get("k", 31))
+    ref = oracle.map_reads(oix, oracle.map_params(**over), left, right, frag_counter)
+    assert idx.info()["n_kmers"] == oix.n_kmers
+    compare(got, ref, p.max_read_occ)
+    for k in ("lookups", "postings", "seeds", "kept", "label_entries", "mapped"):
+        assert got["counters"][k] == ref["counters"][k], k
+    return got, ref
+
+
+@pytest.mark.parametrize("frag_counter", [0, 6000, 6_000_000])
+def test_host_logic_matches_oracle(oracle, frag_counter):
+    txps, _ = synth_txome(seed=3, n_genes=150)
+    left, right, truth = synth_reads(txps, seed=5, n=1500, indel_rate=0.002)
+    got, ref = run_both(oracle, txps, left, right, frag_counter)
+    na = got["n_aln"]
+    ok = sum(1 for i in range(len(na)) if truth["tid"][i] >= 0 and truth["tid"][i] in got["tid"][i, :na[i]])
+    assert ok >= 0.97 * (truth["tid"] >= 0).sum()
+    assert ((truth["tid"] < 0) & (na > 0)).sum() == 0
+
+
+def test_repeats_ns_short_transcripts_and_caps(oracle):
+    rng = np.random.default_rng(9)
+    unit = rng.integers(0, 4, size=400, dtype=np.uint8)
+    txps = [unit.copy() for _ in range(90)]                 # 90 identical transcripts: > MAXCAND candidates
+    txps += [np.concatenate([unit[:200], rng.integers(0, 4, size=150, dtype=np.uint8)]) for _ in range(130)]  # > maxReadOcc
+    txps += [rng.integers(0, 4, size=20, dtype=np.uint8)]    # shorter than k
+    withn = rng.integers(0, 4, size=500, dtype=np.uint8); withn[100:103] = 4
+    txps += [withn]
+    left, right, _ = synth_reads(txps, seed=2, n=400, read_len=75, frag_mean=180, frag_sd=15, random_frac=0.1)
+    left[5, 10] = 4; right[7, 60] = 4                        # N in reads
+    run_both(oracle, txps, left, right)
+    run_both(oracle, txps, left, right, max_read_occ=50, max_occs_per_hit=64, stride=3, range_bins=0)
+
+
+def test_decoys_and_hard_filter(oracle):
+    txps, _ = synth_txome(seed=8, n_genes=60)
+    n_real = len(txps) - 20
+    left, right, _ = synth_reads(txps, seed=1, n=600)
+    run_both(oracle, txps, left, right, first_decoy=n_real)
+    run_both(oracle, txps, left, right, hard_filter=1)
+    run_both(oracle, txps, left, right, first_decoy=n_real, decoy_threshold=0.9, min_score_fraction=0.8)
+
+
+def test_detmath_close_to_libm():
+    import ctypes as C, math, os, subprocess, tempfile
+    src = r'''
+    #include "sb_detmath.h"
+    double e(double x) { return sb_det_exp(x); }
+    double l(double x) { return sb_det_log(x); }
+    '''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        so = os.path.join(d, "t.so")
+        subprocess.check_call(["/usr/bin/gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I" + os.path.join(root, "include"),
+                               "-o", so, os.path.join(d, "t.c")])
+        lib = C.CDLL(so)
+        lib.e.restype = lib.l.restype = C.c_double
+        lib.e.argtypes = lib.l.argtypes = [C.c_double]
+        rng = np.random.default_rng(0)
+        for x in rng.uniform(-700, 700, size=20000):
+            assert abs(lib.e(x) - math.exp(x)) <= 2.3e-16 * math.exp(x)
+        for x in np.exp(rng.uniform(-700, 700, size=20000)):
+            assert abs(lib.l(x) - math.log(x)) <= 2.3e-16 * max(abs(math.log(x)), 1e-300) + 1e-320
+        assert lib.e(0.0) == 1.0 and lib.l(1.0) == 0.0 and lib.e(-lib.l(2.0)) == 0.5
