@@ -34,19 +34,19 @@
 #define SB_DIV(a, b) ((a) / (b))
 #endif
 
-SB_HD uint64_t sb_d2u(double x) { uint64_t u; memcpy(&u, &x, 8); return u; }
-SB_HD double sb_u2d(uint64_t u) { double x; memcpy(&x, &u, 8); return x; }
+SB_HD uint64_t sbm_d2u(double x) { uint64_t u; memcpy(&u, &x, 8); return u; }
+SB_HD double sbm_u2d(uint64_t u) { double x; memcpy(&x, &u, 8); return x; }
 
 /* exp(x) for finite x; returns +inf above 709.78, 0 below -745.13 (subnormal results are
  * produced by a two-step scale, as fdlibm does). */
-SB_HD double sb_det_exp(double x) {
+SB_HD double sbm_det_exp(double x) {
   const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10,
                invln2 = 1.44269504088896338700e+00;
   const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03,
                P3 = 6.61375632143793436117e-05, P4 = -1.65339022054652515390e-06,
                P5 = 4.13813679705723846039e-08;
   if (x != x) return x;
-  if (x > 7.09782712893383973096e+02) return sb_u2d(0x7ff0000000000000ull);
+  if (x > 7.09782712893383973096e+02) return sbm_u2d(0x7ff0000000000000ull);
   if (x < -7.45133219101941108420e+02) return 0.0;
   double hi = x, lo = 0.0;
   int k = 0;
@@ -75,25 +75,25 @@ SB_HD double sb_det_exp(double x) {
   if (k == 0) return SB_SUB(1.0, SB_SUB(SB_DIV(SB_MUL(x, c), SB_SUB(c, 2.0)), x));
   y = SB_SUB(1.0, SB_SUB(SB_SUB(lo, SB_DIV(SB_MUL(x, c), SB_SUB(2.0, c))), hi));
   if (k >= -1021) {
-    return sb_u2d(sb_d2u(y) + ((uint64_t)(int64_t)k << 52));
+    return sbm_u2d(sbm_d2u(y) + ((uint64_t)(int64_t)k << 52));
   }
   /* subnormal result: scale in two steps */
-  y = sb_u2d(sb_d2u(y) + ((uint64_t)(int64_t)(k + 1000) << 52));
+  y = sbm_u2d(sbm_d2u(y) + ((uint64_t)(int64_t)(k + 1000) << 52));
   return SB_MUL(y, 9.33263618503218878990e-302 /* 2^-1000 */);
 }
 
 /* log(x) for x > 0 (finite); callers guard x <= 0. */
-SB_HD double sb_det_log(double x) {
+SB_HD double sbm_det_log(double x) {
   const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
   const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
                Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
                Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
                Lg7 = 1.479819860511658591e-01;
   int k = 0;
-  uint64_t u = sb_d2u(x);
+  uint64_t u = sbm_d2u(x);
   if ((u >> 52) == 0) {          /* subnormal: scale up by 2^54 */
     x = SB_MUL(x, 18014398509481984.0);
-    u = sb_d2u(x);
+    u = sbm_d2u(x);
     k -= 54;
   }
   uint32_t hx = (uint32_t)(u >> 32);
@@ -102,7 +102,7 @@ SB_HD double sb_det_log(double x) {
   const uint32_t i = (hx + 0x95f64u) & 0x100000u;
   u = ((uint64_t)(hx | (i ^ 0x3ff00000u)) << 32) | (u & 0xffffffffull);   /* normalise x or x/2 */
   k += (int)(i >> 20);
-  x = sb_u2d(u);
+  x = sbm_u2d(u);
   const double f = SB_SUB(x, 1.0);
   const double dk = (double)k;
   const double s = SB_DIV(f, SB_ADD(2.0, f));

@@ -30,7 +30,7 @@ static double logAddDet(double x, double y) {
   if (fabs(x) == LOG_0) return y;
   if (fabs(y) == LOG_0) return x;
   if (y > x) { double t = x; x = y; y = t; }
-  return x + sb_det_log(1 + sb_det_exp(y - x));
+  return x + sbm_det_log(1 + sbm_det_exp(y - x));
 }
 
 /* ---------------------------------------------------------------- FLD tables
@@ -417,7 +417,7 @@ int orc_map_reads(const orc_index* ix, const orc_map_params* p, const uint8_t* l
     for (uint32_t q = 0; q < nkept; ++q) {
       const joint_t* j = &jh[perm[q].idx];
       double v = (double)bestScore - (double)scores[perm[q].idx];
-      double estAlnProb = p->hard_filter ? -1.0 : sb_det_exp(-p->score_exp * v);
+      double estAlnProb = p->hard_filter ? -1.0 : sbm_det_exp(-p->score_exp * v);
       if (!p->hard_filter && estAlnProb < p->min_aln_prob) continue;
       const cand_t* first = (j->status == 2) ? &rcand[j->ri] : &lc[j->li];
       aln_tid[base + na] = j->tid;
@@ -447,7 +447,7 @@ int orc_map_reads(const orc_index* ix, const orc_map_params* p, const uint8_t* l
       const uint32_t status = (aln_flags[base + a] >> 2) & 3;
       const int fwd = aln_flags[base + a] & 1, mateFwd = (aln_flags[base + a] >> 1) & 1;
       const double coverage = aln_prob[base + a];
-      const double logFragCov = (coverage > 0) ? sb_det_log(coverage) : LOG_1;          /* :602-603 */
+      const double logFragCov = (coverage > 0) ? sbm_det_log(coverage) : LOG_1;          /* :602-603 */
       int32_t flen = aln_flen[base + a];
       if (status == 0 && fwd != mateFwd) {                                       /* :629-632 fragLengthPedantic */
         int32_t pos = aln_pos[base + a], mpos = aln_mate_pos[base + a];
@@ -481,7 +481,7 @@ int orc_map_reads(const orc_index* ix, const orc_map_params* p, const uint8_t* l
       auxDenom = logAddDet(auxDenom, aux[a]);
     }
     for (uint32_t a = 0; a < na; ++a) {                                            /* :818-820 */
-      weight[base + a] = sb_det_exp(aux[a] - auxDenom);
+      weight[base + a] = sbm_det_exp(aux[a] - auxDenom);
       label[(size_t)r * 2 * cap + a] = aln_tid[base + a];
     }
     if (p->range_bins > 0) {                                                        /* :845-853 */

@@ -386,13 +386,13 @@ SB_HD int32_t dp_score_serial(const IndexView& ix, const Params& p, const uint8_
 }
 
 // ---- salmon-owned arithmetic on the log scale (deterministic exp/log, sb_detmath.h)
-SB_HD double log0() { return sb_u2d(0x7ff0000000000000ull); }   // LOG_0 = HUGE_VAL (SalmonMath.hpp:40)
+SB_HD double log0() { return sbm_u2d(0x7ff0000000000000ull); }   // LOG_0 = HUGE_VAL (SalmonMath.hpp:40)
 SB_HD double dabs(double x) { return x < 0 ? -x : x; }
 SB_HD double log_add(double x, double y) {                       // SalmonMath.hpp:54-66
   if (dabs(x) == log0()) return y;
   if (dabs(y) == log0()) return x;
   if (y > x) { const double t = x; x = y; y = t; }
-  return x + sb_det_log(1 + sb_det_exp(y - x));
+  return x + sbm_det_log(1 + sbm_det_exp(y - x));
 }
 SB_HD double tabv(const double* t, uint32_t max_val, uint64_t len) { return t[len > max_val ? max_val : len]; }
 
@@ -417,7 +417,7 @@ SB_HD void assign_read(const IndexView& ix, const Params& p, const FldView& fld,
                        const int32_t* score_r, uint32_t L, int32_t* sc, int32_t* perm_idx, int32_t* perm_tid,
                        int32_t* bs_tid, int32_t* bs_score, int32_t* bs_idx, Joint* jh, const ReadOut& o,
                        Counters& ctr) {
-  const double LOG_EPSILON = -24.006680182952184;   // log(0.375e-10), SalmonMath.hpp:44-45 (libm and sb_det_log agree)
+  const double LOG_EPSILON = -24.006680182952184;   // log(0.375e-10), SalmonMath.hpp:44-45 (libm and sbm_det_log agree)
   const uint32_t cap = p.max_read_occ;
   *o.n_aln = 0;
   uint32_t nj = 0;
@@ -465,7 +465,7 @@ SB_HD void assign_read(const IndexView& ix, const Params& p, const FldView& fld,
   for (uint32_t q = 0; q < nk; ++q) {
     const Joint& j = jh[perm_idx[q]];
     const double v = (double)bestScore - (double)sc[perm_idx[q]];
-    const double estAlnProb = p.hard_filter ? -1.0 : sb_det_exp(-p.score_exp * v);
+    const double estAlnProb = p.hard_filter ? -1.0 : sbm_det_exp(-p.score_exp * v);
     if (!p.hard_filter && estAlnProb < p.min_aln_prob) continue;
     const Cand& first = (j.status == 2) ? rcd[j.ri] : lc[j.li];
     o.tid[na] = j.tid;
@@ -494,7 +494,7 @@ SB_HD void assign_read(const IndexView& ix, const Params& p, const FldView& fld,
     const uint32_t status = (o.flags[a] >> 2) & 3;
     const int fwd = o.flags[a] & 1, mateFwd = (o.flags[a] >> 1) & 1;
     const double coverage = o.prob[a];
-    const double logFragCov = (coverage > 0) ? sb_det_log(coverage) : 0.0;
+    const double logFragCov = (coverage > 0) ? sbm_det_log(coverage) : 0.0;
     int32_t flen = o.flen[a];
     if (status == 0 && fwd != mateFwd) {
       const int32_t pos = o.pos[a], mpos = o.mate_pos[a];
@@ -529,7 +529,7 @@ SB_HD void assign_read(const IndexView& ix, const Params& p, const FldView& fld,
     auxDenom = log_add(auxDenom, aux);
   }
   for (uint32_t a = 0; a < na; ++a) {
-    o.weight[a] = sb_det_exp(o.weight[a] - auxDenom);
+    o.weight[a] = sbm_det_exp(o.weight[a] - auxDenom);
     o.label[a] = o.tid[a];
   }
   if (p.range_bins > 0) {

@@ -71,8 +71,8 @@ def test_detmath_close_to_libm():
     import ctypes as C, math, os, subprocess, tempfile
     src = r'''
     #include "sb_detmath.h"
-    double e(double x) { return sb_det_exp(x); }
-    double l(double x) { return sb_det_log(x); }
+    double e(double x) { return sbm_det_exp(x); }
+    double l(double x) { return sbm_det_log(x); }
     '''
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     with tempfile.TemporaryDirectory() as d:
