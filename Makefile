@@ -1,7 +1,7 @@
 # Top-level build: libsalmon_b200.so (CUDA, sm_100a only) + the oracle (test infra).
 NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xcompiler -Wall $(PTXAS_V)
+NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -fopenmp $(PTXAS_V)
 CSRC      := salmon_b200/csrc
 LIB       := salmon_b200/libsalmon_b200.so
 SRCS      := $(wildcard $(CSRC)/*.cu)
@@ -10,7 +10,7 @@ HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 all: $(LIB) oracle
 
 $(LIB): $(SRCS) $(HDRS)
-	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(SRCS) -ldl
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(SRCS) -ldl -lgomp
 
 oracle:
 	$(MAKE) -C oracle

@@ -198,6 +198,8 @@ typedef struct sb_map_batch_stats {
   uint32_t gpu_launches;
   uint64_t mapped, lookups, postings, seeds, candidates, kept, label_entries, n_batch_classes;
   float device_ms;            /* H2D of the reads + all kernels of the batch (CUDA events) */
+  uint32_t reserved;
+  uint64_t full_dp;           /* mate alignments that needed the banded DP (the rest: ungapped shortcut) */
 } sb_map_batch_stats;
 
 typedef struct sb_map_result {   /* host CSR owned by the context, valid until destroy / next finish */
@@ -225,6 +227,10 @@ int sb_map_finish(sb_map_ctx* ctx, sb_map_result* out);
 int sb_map_last_alignments(sb_map_ctx* ctx, uint32_t n, uint32_t* n_aln, uint32_t* tid, int32_t* score,
                            double* prob, int32_t* pos, int32_t* mate_pos, uint8_t* flags, int32_t* flen,
                            uint32_t* label, double* weight);
+
+/* Tuning knobs of the mapping context: "variant" (1 = warp-cooperative kernels, 0 = serial-form kernels),
+ * "fast_dp" (ungapped shortcut of the DP kernel on/off).  Results are identical for every setting. */
+int sb_map_set_option(sb_map_ctx* ctx, const char* key, int64_t value);
 
 /* Debug: per-warp phase timestamps (ns) of one iteration of the last persistent run:
  * out[n_warps*8] = {P1 start, P1 end, barrier1 end, P2 start, P2 end, reduce end, barrier2 end, -}.

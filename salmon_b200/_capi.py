@@ -86,7 +86,7 @@ class sb_map_params(C.Structure):
 class sb_map_batch_stats(C.Structure):
     _fields_ = [("n_pairs", C.c_uint32), ("gpu_launches", C.c_uint32)] + \
         [(k, C.c_uint64) for k in ("mapped", "lookups", "postings", "seeds", "candidates", "kept", "label_entries",
-                                   "n_batch_classes")] + [("device_ms", C.c_float)]
+                                   "n_batch_classes")] + [("device_ms", C.c_float), ("reserved", C.c_uint32), ("full_dp", C.c_uint64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -133,6 +133,7 @@ SYMBOLS = {
     "sb_map_destroy": (None, [_P]),
     "sb_map_batch": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, C.POINTER(sb_map_batch_stats)]),
     "sb_map_finish": (C.c_int, [_P, C.POINTER(sb_map_result)]),
+    "sb_map_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "sb_map_last_alignments": (C.c_int, [_P, C.c_uint32] + [_P] * 10),
     "sb_host_register": (C.c_int, [_P, C.c_size_t]),
     "sb_host_unregister": (C.c_int, [_P]),
@@ -422,6 +423,9 @@ class MapContext:
         _check(self.lib.sb_map_batch(self.h, left.ctypes.data, right.ctypes.data, n, L, C.byref(st)), "sb_map_batch")
         self.last_n = n
         return st
+
+    def set_option(self, key: str, value: int):
+        _check(self.lib.sb_map_set_option(self.h, key.encode(), int(value)), "sb_map_set_option")
 
     def last_alignments(self):
         n, cap = self.last_n, self.p.max_read_occ

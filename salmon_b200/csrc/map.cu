@@ -9,10 +9,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <parallel/algorithm>
 #include <vector>
 
 #include "common.cuh"
 #include "map_core.h"
+#include "map_kernels.cuh"
 
 using namespace sbmap;
 
@@ -25,6 +27,8 @@ struct sb_index {
   std::vector<uint8_t> codes;
   std::vector<TableEntry> table;
   std::vector<Posting> post;
+  std::vector<uint64_t> packed;     // 2-bit packed codes with PACK_GUARD_BASES of guard on both sides
+  std::vector<uint8_t> tx_has_n;
   uint64_t n_kmers = 0;
   // device copies (one device)
   int device = -1;
@@ -32,23 +36,20 @@ struct sb_index {
   uint8_t* d_codes = nullptr;
   TableEntry* d_table = nullptr;
   Posting* d_post = nullptr;
+  uint64_t* d_packed = nullptr;
+  uint8_t* d_tx_has_n = nullptr;
 };
 
 namespace {
 struct KP {
   uint64_t km;
-  uint32_t tid, tpos;
+  uint32_t tid, tpos_rc;
 };
-IndexView host_view(const sb_index* ix) {
-  IndexView v;
-  v.n_txps = ix->n_txps; v.k = ix->k; v.mask = ix->table.size() - 1;
-  v.tx_off = ix->tx_off.data(); v.codes = ix->codes.data(); v.table = ix->table.data(); v.post = ix->post.data();
-  return v;
-}
 IndexView dev_view(const sb_index* ix) {
   IndexView v;
   v.n_txps = ix->n_txps; v.k = ix->k; v.mask = ix->table.size() - 1;
   v.tx_off = ix->d_tx_off; v.codes = ix->d_codes; v.table = ix->d_table; v.post = ix->d_post;
+  v.packed = ix->d_packed; v.tx_has_n = ix->d_tx_has_n;
   return v;
 }
 }  // namespace
@@ -81,14 +82,28 @@ extern "C" sb_index* sb_index_build(uint32_t n_txps, const uint64_t* seq_off, co
       if (c > 3) { valid = 0; fw = rc = 0; continue; }
       fw = ((fw << 2) | c) & kmask;
       rc = (rc >> 2) | ((uint64_t)(3 - c) << (2 * (k - 1)));
-      if (++valid >= k) kp.push_back({fw < rc ? fw : rc, t, (uint32_t)(p + 1 - k - b)});
+      if (++valid >= k) kp.push_back({fw < rc ? fw : rc, t, (uint32_t)(p + 1 - k - b) | (fw < rc ? 0u : 0x80000000u)});
     }
   }
-  std::sort(kp.begin(), kp.end(), [](const KP& a, const KP& b) {
+  // (k-mer, transcript, offset) order; the orientation flag (bit 31) is a function of the other three
+  __gnu_parallel::sort(kp.begin(), kp.end(), [](const KP& a, const KP& b) {
     if (a.km != b.km) return a.km < b.km;
     if (a.tid != b.tid) return a.tid < b.tid;
-    return a.tpos < b.tpos;
+    return (a.tpos_rc & 0x7fffffffu) < (b.tpos_rc & 0x7fffffffu);
   });
+  // 2-bit packed reference (DP windows, exact-match tests); transcripts with N keep using the byte codes
+  {
+    const uint64_t total = seq_off[n_txps];
+    ix->packed.assign((total + 2 * (uint64_t)PACK_GUARD_BASES + 31) / 32 + 2, 0);
+    ix->tx_has_n.assign(std::max<uint32_t>(n_txps, 1), 0);
+    for (uint32_t t = 0; t < n_txps; ++t)
+      for (uint64_t g = seq_off[t]; g < seq_off[t + 1]; ++g) {
+        const uint8_t c = codes[g];
+        if (c > 3) { ix->tx_has_n[t] = 1; continue; }
+        const uint64_t q = g + PACK_GUARD_BASES;
+        ix->packed[q >> 5] |= (uint64_t)c << (2 * (q & 31));
+      }
+  }
   uint64_t nk = 0;
   for (size_t i = 0; i < kp.size(); ++i) if (i == 0 || kp[i].km != kp[i - 1].km) ++nk;
   ix->n_kmers = nk;
@@ -99,7 +114,7 @@ extern "C" sb_index* sb_index_build(uint32_t n_txps, const uint64_t* seq_off, co
   const uint64_t mask = capt - 1;
   for (size_t i = 0; i < kp.size();) {
     size_t j = i;
-    while (j < kp.size() && kp[j].km == kp[i].km) { ix->post[j] = Posting{kp[j].tid, kp[j].tpos}; ++j; }
+    while (j < kp.size() && kp[j].km == kp[i].km) { ix->post[j] = Posting{kp[j].tid, kp[j].tpos_rc}; ++j; }
     uint64_t h = mix64(kp[i].km) & mask;
     while (ix->table[h].key != EMPTY_KEY) h = (h + 1) & mask;
     ix->table[h] = TableEntry{kp[i].km, (uint32_t)i, (uint32_t)(j - i)};
@@ -113,6 +128,7 @@ extern "C" void sb_index_free(sb_index* ix) {
   if (ix->device >= 0) {
     cudaSetDevice(ix->device);
     cudaFree(ix->d_tx_off); cudaFree(ix->d_codes); cudaFree(ix->d_table); cudaFree(ix->d_post);
+    cudaFree(ix->d_packed); cudaFree(ix->d_tx_has_n);
   }
   delete ix;
 }
@@ -121,7 +137,7 @@ extern "C" int sb_index_info(const sb_index* ix, uint64_t* out4) {
   if (!ix || !out4) { sb::set_error("null argument"); return SB_ERR_INVALID; }
   out4[0] = ix->n_kmers; out4[1] = ix->post.size(); out4[2] = ix->table.size();
   out4[3] = ix->table.size() * sizeof(TableEntry) + ix->post.size() * sizeof(Posting) + ix->codes.size() +
-            ix->tx_off.size() * 8;
+            ix->tx_off.size() * 8 + ix->packed.size() * 8 + ix->tx_has_n.size();
   return SB_OK;
 }
 
@@ -151,6 +167,10 @@ static int index_to_device(sb_index* ix, int device) {
   SB_CUDA(cudaMemcpy(ix->d_codes, ix->codes.data(), ix->codes.size(), cudaMemcpyHostToDevice));
   SB_CUDA(cudaMemcpy(ix->d_table, ix->table.data(), ix->table.size() * sizeof(TableEntry), cudaMemcpyHostToDevice));
   SB_CUDA(cudaMemcpy(ix->d_post, ix->post.data(), ix->post.size() * sizeof(Posting), cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMalloc(&ix->d_packed, ix->packed.size() * 8));
+  SB_CUDA(cudaMalloc(&ix->d_tx_has_n, ix->tx_has_n.size()));
+  SB_CUDA(cudaMemcpy(ix->d_packed, ix->packed.data(), ix->packed.size() * 8, cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMemcpy(ix->d_tx_has_n, ix->tx_has_n.data(), ix->tx_has_n.size(), cudaMemcpyHostToDevice));
   ix->device = device;
   return SB_OK;
 }
@@ -311,71 +331,93 @@ __global__ void k_assign(IndexView ix, Params p, FldView fld, int useAux, int bu
 }
 
 // ---- equivalence-class builder: records (label, weights, count) -> classes ----------------
+// A record i is (labels[lstart[i] .. +llen[i]), weights[wstart[i] .. +wlen[i]), counts[i] or 1).
 // hash of a label (64-bit FNV-1a over the 32-bit words; the value is never persisted, like the
 // reference's XXH64 in TranscriptGroup::hash, src/model/TranscriptGroup.cpp:10-15)
-__global__ void k_label_hash(uint32_t n, const uint64_t* __restrict__ loff, const uint32_t* __restrict__ labels,
-                             uint64_t* __restrict__ hash, uint32_t* __restrict__ idx) {
+struct Records {
+  uint32_t n;
+  const uint64_t* lstart; const uint32_t* llen;
+  const uint64_t* wstart; const uint32_t* wlen;
+  const uint32_t* labels; const double* weights; const uint64_t* counts;
+};
+
+// per-read slots of a batch as records: read i owns labels[i*2cap ..), weights[i*cap ..)
+__global__ void k_read_records(uint32_t n, uint32_t cap, int binned, const uint32_t* __restrict__ n_aln,
+                               uint64_t* __restrict__ lstart, uint32_t* __restrict__ llen,
+                               uint64_t* __restrict__ wstart, uint32_t* __restrict__ wlen) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const uint32_t na = n_aln[i];
+  lstart[i] = (uint64_t)i * 2 * cap; llen[i] = na * (binned ? 2u : 1u);
+  wstart[i] = (uint64_t)i * cap; wlen[i] = na;
+}
+__global__ void k_label_hash(Records R, uint64_t* __restrict__ hash, uint32_t* __restrict__ idx) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R.n) return;
   uint64_t h = 1469598103934665603ull;
-  for (uint64_t j = loff[i]; j < loff[i + 1]; ++j) { h ^= labels[j]; h *= 1099511628211ull; }
-  h ^= (loff[i + 1] - loff[i]);
+  const uint32_t* lab = R.labels + R.lstart[i];
+  const uint32_t len = R.llen[i];
+  for (uint32_t j = 0; j < len; ++j) { h ^= lab[j]; h *= 1099511628211ull; }
+  h ^= len;
   h = mix64(h);
   hash[i] = h;
   idx[i] = i;
 }
-__global__ void k_label_heads(uint32_t n, const uint64_t* __restrict__ hash_sorted, const uint32_t* __restrict__ idx,
-                              const uint64_t* __restrict__ loff, const uint32_t* __restrict__ labels,
+__global__ void k_label_heads(Records R, const uint64_t* __restrict__ hash_sorted, const uint32_t* __restrict__ idx,
                               uint32_t* __restrict__ head) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i > R.n) return;
+  if (i == R.n) { head[i] = 0; return; }
   uint32_t h = 1;
   if (i > 0 && hash_sorted[i] == hash_sorted[i - 1]) {
     const uint32_t a = idx[i], b = idx[i - 1];
-    const uint64_t la = loff[a + 1] - loff[a], lb = loff[b + 1] - loff[b];
+    const uint32_t la = R.llen[a], lb = R.llen[b];
     if (la == lb) {
       h = 0;
-      for (uint64_t j = 0; j < la; ++j) if (labels[loff[a] + j] != labels[loff[b] + j]) { h = 1; break; }
+      const uint32_t* pa = R.labels + R.lstart[a];
+      const uint32_t* pb = R.labels + R.lstart[b];
+      for (uint32_t j = 0; j < la; ++j) if (pa[j] != pb[j]) { h = 1; break; }
     }
   }
   head[i] = h;
 }
-// per class: label length / weight length (for the output offsets)
-__global__ void k_class_sizes(uint32_t n, const uint32_t* __restrict__ head, const uint32_t* __restrict__ head_scan,
-                              const uint32_t* __restrict__ idx, const uint64_t* __restrict__ loff,
-                              const uint64_t* __restrict__ woff, uint32_t* __restrict__ first, uint64_t* __restrict__ llen,
-                              uint64_t* __restrict__ wlen) {
+// per class: position of its first record in the sorted order, label / weight lengths
+__global__ void k_class_sizes(Records R, const uint32_t* __restrict__ head, const uint32_t* __restrict__ head_scan,
+                              const uint32_t* __restrict__ idx, uint32_t* __restrict__ first,
+                              uint64_t* __restrict__ cls_llen, uint64_t* __restrict__ cls_wlen) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !head[i]) return;
+  if (i >= R.n || !head[i]) return;
   const uint32_t c = head_scan[i];
   const uint32_t r = idx[i];
   first[c] = i;
-  llen[c] = loff[r + 1] - loff[r];
-  wlen[c] = woff[r + 1] - woff[r];
+  cls_llen[c] = R.llen[r];
+  cls_wlen[c] = R.wlen[r];
 }
-// per class (one thread): count and weights summed over its records IN RECORD ORDER
-// (EquivalenceClassBuilder.hpp:237-250: count++, weights[i] += w_i)
-__global__ void k_class_reduce(uint32_t n_classes, uint32_t n, const uint32_t* __restrict__ first,
-                               const uint32_t* __restrict__ idx, const uint64_t* __restrict__ loff,
-                               const uint64_t* __restrict__ woff, const uint32_t* __restrict__ labels,
-                               const double* __restrict__ weights, const uint64_t* __restrict__ counts,
-                               const uint64_t* __restrict__ out_loff, const uint64_t* __restrict__ out_woff,
-                               uint32_t* __restrict__ out_labels, double* __restrict__ out_weights,
-                               uint64_t* __restrict__ out_counts) {
-  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+// per class (one warp): count and weights summed over its records IN RECORD ORDER
+// (EquivalenceClassBuilder.hpp:237-250: count++, weights[i] += w_i); lanes = label / weight entries
+__global__ void k_class_reduce(Records R, uint32_t n_classes, const uint32_t* __restrict__ first,
+                               const uint32_t* __restrict__ idx, const uint64_t* __restrict__ out_loff,
+                               const uint64_t* __restrict__ out_woff, uint32_t* __restrict__ out_labels,
+                               double* __restrict__ out_weights, uint64_t* __restrict__ out_counts) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= n_classes) return;
-  const uint32_t b = first[c], e = (c + 1 < n_classes) ? first[c + 1] : n;
+  const uint32_t b = first[c], e = (c + 1 < n_classes) ? first[c + 1] : R.n;
   const uint32_t r0 = idx[b];
-  const uint64_t ll = loff[r0 + 1] - loff[r0], wl = woff[r0 + 1] - woff[r0];
-  for (uint64_t j = 0; j < ll; ++j) out_labels[out_loff[c] + j] = labels[loff[r0] + j];
-  for (uint64_t j = 0; j < wl; ++j) out_weights[out_woff[c] + j] = 0.0;
-  uint64_t cnt = 0;
-  for (uint32_t q = b; q < e; ++q) {
-    const uint32_t r = idx[q];
-    cnt += counts ? counts[r] : 1ull;
-    for (uint64_t j = 0; j < wl; ++j) out_weights[out_woff[c] + j] = __dadd_rn(out_weights[out_woff[c] + j], weights[woff[r] + j]);
+  const uint32_t ll = R.llen[r0], wl = R.wlen[r0];
+  const uint32_t* lab = R.labels + R.lstart[r0];
+  for (uint32_t j = lane; j < ll; j += 32) out_labels[out_loff[c] + j] = lab[j];
+  for (uint32_t j = lane; j < wl; j += 32) {
+    double s = 0.0;
+    for (uint32_t q = b; q < e; ++q) s = __dadd_rn(s, R.weights[R.wstart[idx[q]] + j]);
+    out_weights[out_woff[c] + j] = s;
   }
-  out_counts[c] = cnt;
+  if (lane == 0) {
+    uint64_t cnt = 0;
+    if (R.counts) for (uint32_t q = b; q < e; ++q) cnt += R.counts[idx[q]];
+    else cnt = e - b;
+    out_counts[c] = cnt;
+  }
 }
 // finish(): TGValue::normalizeAux (EquivalenceClassBuilder.hpp:114-123)
 __global__ void k_normalize(uint64_t n_classes, const uint64_t* __restrict__ woff, double* __restrict__ w) {
@@ -386,23 +428,14 @@ __global__ void k_normalize(uint64_t n_classes, const uint64_t* __restrict__ wof
   const double norm = __ddiv_rn(1.0, s);
   for (uint64_t j = woff[c]; j < woff[c + 1]; ++j) w[j] = __dmul_rn(w[j], norm);
 }
-// compact per-read slots (n_aln entries used of cap) into CSR records
-__global__ void k_read_lengths(uint32_t n, const uint32_t* __restrict__ n_aln, int binned, uint64_t* __restrict__ ll,
-                               uint64_t* __restrict__ wl) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// CSR store -> record descriptors (finish: the class tables of all batches become records)
+__global__ void k_store_records(uint64_t n, const uint64_t* __restrict__ loff, const uint64_t* __restrict__ woff,
+                                uint64_t lbase, uint64_t wbase, uint64_t* __restrict__ lstart, uint32_t* __restrict__ llen,
+                                uint64_t* __restrict__ wstart, uint32_t* __restrict__ wlen) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  ll[i] = (uint64_t)n_aln[i] * (binned ? 2 : 1);
-  wl[i] = n_aln[i];
-}
-__global__ void k_read_compact(uint32_t n, uint32_t cap, const uint32_t* __restrict__ n_aln, int binned,
-                               const uint32_t* __restrict__ label, const double* __restrict__ weight,
-                               const uint64_t* __restrict__ loff, const uint64_t* __restrict__ woff,
-                               uint32_t* __restrict__ labels, double* __restrict__ weights) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t na = n_aln[i];
-  for (uint32_t a = 0; a < na * (binned ? 2u : 1u); ++a) labels[loff[i] + a] = label[(size_t)i * 2 * cap + a];
-  for (uint32_t a = 0; a < na; ++a) weights[woff[i] + a] = weight[(size_t)i * cap + a];
+  lstart[i] = lbase + loff[i]; llen[i] = (uint32_t)(loff[i + 1] - loff[i]);
+  wstart[i] = wbase + woff[i]; wlen[i] = (uint32_t)(woff[i + 1] - woff[i]);
 }
 
 }  // namespace
@@ -420,23 +453,45 @@ struct EqStore {   // device CSR of class records
   }
 };
 
+struct AggScratch {   // sized for `cap` records
+  uint64_t cap = 0;
+  uint64_t *lstart = nullptr, *wstart = nullptr, *hash = nullptr, *hash2 = nullptr, *cls_llen = nullptr, *cls_wlen = nullptr;
+  uint32_t *llen = nullptr, *wlen = nullptr, *idx = nullptr, *idx2 = nullptr, *head = nullptr, *head_scan = nullptr, *first = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  void free_all() {
+    void* ps[] = {lstart, wstart, hash, hash2, cls_llen, cls_wlen, llen, wlen, idx, idx2, head, head_scan, first, tmp};
+    for (void* q : ps) cudaFree(q);
+    *this = AggScratch();
+  }
+};
+
 struct sb_map_ctx {
   int device = 0;
   int n_sm = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
   sb_index* index = nullptr;
   Params p{};
-  uint32_t batch_cap = 0, read_len_cap = 0;
-  uint32_t k1_threads = 0;
-  BatchBufs b{};
-  uint8_t *d_left = nullptr, *d_right = nullptr;
+  uint32_t batch_cap = 0, read_len_cap = 0, chunk = 0;
+  int variant = 1;                   // 1 = warp kernels (map_kernels.cuh), 0 = serial-form kernels
+  int fast_ok = 1;
+  uint32_t k1_threads = 0, seed_blocks = 0, dp_blocks = 0;
+  BatchBufs b{};                     // cand/score/task buffers: one chunk; outputs: whole batch
+  uint8_t* d_in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [slot][mate]
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  PackedReads pr{};
+  uint64_t* d_overflow = nullptr;
+  uint32_t* d_next_task = nullptr;
+  unsigned long long* d_full_dp = nullptr;
   // FLD tables
   double* d_fld = nullptr;
   FldView fld{};
+  AggScratch agg;
   // eq-class store: one EqStore per processed batch, merged at finish
   std::vector<EqStore> stores;
   uint64_t frag_counter = 0;     // fragments assigned so far (batched semantics)
   Counters totals{};
+  uint64_t full_dp_total = 0;
   uint32_t launches = 0;
   float last_ms = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -500,6 +555,24 @@ static void build_fld_host(const Params& p, std::vector<double>& t) {
   }
 }
 
+static int agg_reserve(AggScratch& a, uint64_t n) {
+  if (n <= a.cap) return SB_OK;
+  a.free_all();
+  const uint64_t cap = std::max<uint64_t>(n, 1024);
+  SB_TRY(dmalloc(&a.lstart, cap)); SB_TRY(dmalloc(&a.wstart, cap)); SB_TRY(dmalloc(&a.hash, cap)); SB_TRY(dmalloc(&a.hash2, cap));
+  SB_TRY(dmalloc(&a.cls_llen, cap + 1)); SB_TRY(dmalloc(&a.cls_wlen, cap + 1));
+  SB_TRY(dmalloc(&a.llen, cap)); SB_TRY(dmalloc(&a.wlen, cap)); SB_TRY(dmalloc(&a.idx, cap)); SB_TRY(dmalloc(&a.idx2, cap));
+  SB_TRY(dmalloc(&a.head, cap + 1)); SB_TRY(dmalloc(&a.head_scan, cap + 1)); SB_TRY(dmalloc(&a.first, cap + 1));
+  size_t tb = 0, tb2 = 0, tb3 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, a.hash, a.hash2, a.idx, a.idx2, (int)cap, 0, 64, (cudaStream_t)0);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb2, a.head, a.head_scan, (int)cap + 1, (cudaStream_t)0);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb3, a.cls_llen, a.cls_llen, (int)cap + 1, (cudaStream_t)0);
+  a.tmp_bytes = std::max(tb, std::max(tb2, tb3));
+  SB_CUDA(cudaMalloc(&a.tmp, a.tmp_bytes));
+  a.cap = cap;
+  return SB_OK;
+}
+
 extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int device, uint32_t batch_cap,
                                      uint32_t max_read_len) {
   if (!ix || !q) { sb::set_error("null argument"); return nullptr; }
@@ -510,8 +583,10 @@ extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int d
     return nullptr;
   }
   if (q->band > 15 || q->max_read_occ > 255 || max_read_len > 256 || q->k != ix->k || batch_cap == 0 ||
-      batch_cap > (1u << 24)) {
-    sb::set_error("sb_map_create: unsupported parameters (band<=15, max_read_occ<=255, read_len<=256, k must match the index)");
+      batch_cap > (1u << 24) || q->stride == 0 || max_read_len < q->k ||
+      (max_read_len - q->k) / q->stride + 2 > MAX_LOOKUPS) {
+    sb::set_error("sb_map_create: unsupported parameters (band<=15, max_read_occ<=255, read_len<=256, k must match "
+                  "the index, at most %u seed positions per mate)", MAX_LOOKUPS);
     return nullptr;
   }
   if (index_to_device(ix, device) != SB_OK) return nullptr;
@@ -524,102 +599,126 @@ extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int d
   p.consensus_frac = q->consensus_frac; p.min_score_fraction = q->min_score_fraction; p.score_exp = q->score_exp;
   p.min_aln_prob = q->min_aln_prob; p.decoy_threshold = q->decoy_threshold; p.fld_mean = q->fld_mean; p.fld_sd = q->fld_sd;
   p.num_pre_burnin = q->num_pre_burnin; p.num_burnin = q->num_burnin;
+  // the ungapped shortcut of k_dp_score_w needs: no cell scores above ma, gaps cost something
+  c->fast_ok = (p.ma >= 0 && p.mp <= p.ma && p.go >= 0 && p.ge >= 0) ? 1 : 0;
   cudaSetDevice(device);
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   c->n_sm = prop.multiProcessorCount;
   cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
   cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+  for (int s = 0; s < 2; ++s) {
+    cudaEventCreateWithFlags(&c->ev_in[s], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_free[s], cudaEventDisableTiming);
+  }
   const uint32_t cap = p.max_read_occ;
   const size_t B = batch_cap;
-  c->k1_threads = (uint32_t)std::min<size_t>((size_t)c->n_sm * 1024, (B + 127) / 128 * 128);
+  c->chunk = (uint32_t)std::min<size_t>(B, 65536);
+  const size_t CH = c->chunk;
+  c->k1_threads = (uint32_t)std::min<size_t>((size_t)c->n_sm * 1024, (CH + 127) / 128 * 128);
+  c->seed_blocks = (uint32_t)c->n_sm * 4;
+  c->dp_blocks = (uint32_t)c->n_sm * 4;
   BatchBufs& b = c->b;
   int rc = SB_OK;
   auto A = [&](auto** ptr, size_t n) { if (rc == SB_OK) rc = dmalloc(ptr, n); };
-  A(&b.n_l, B); A(&b.n_r, B); A(&b.cand_l, B * MAXCAND); A(&b.cand_r, B * MAXCAND);
-  A(&b.score_l, B * MAXCAND); A(&b.score_r, B * MAXCAND);
+  // per chunk
+  A(&b.n_l, CH); A(&b.n_r, CH); A(&b.cand_l, CH * MAXCAND); A(&b.cand_r, CH * MAXCAND);
+  A(&b.score_l, CH * MAXCAND); A(&b.score_r, CH * MAXCAND);
   A(&b.keys, (size_t)MAXSEEDS * c->k1_threads);
-  A(&b.n_tasks, 4); A(&b.tasks, B * 2 * MAXCAND);
-  A(&b.n_aln, B); A(&b.tid, B * cap); A(&b.score, B * cap); A(&b.prob, B * cap); A(&b.pos, B * cap);
-  A(&b.mate_pos, B * cap); A(&b.flags, B * cap); A(&b.flen, B * cap); A(&b.label, B * 2 * cap); A(&b.weight, B * cap);
+  A(&b.n_tasks, 4); A(&b.tasks, CH * 2 * MAXCAND);
   const size_t S = (size_t)c->k1_threads * cap;
   A(&b.sc, S); A(&b.perm_idx, S); A(&b.perm_tid, S); A(&b.bs_tid, S); A(&b.bs_score, S); A(&b.bs_idx, S); A(&b.jh, S);
   A(&b.ctr, 1);
-  A(&c->d_left, B * max_read_len); A(&c->d_right, B * max_read_len);
+  A(&c->d_overflow, (size_t)c->seed_blocks * SEED_WARPS * MAXSEEDS);
+  A(&c->d_next_task, 4); A(&c->d_full_dp, 1);
+  for (int s = 0; s < 2; ++s) for (int m = 0; m < 2; ++m) A(&c->d_in[s][m], CH * max_read_len);
+  c->pr.wpr = (max_read_len + 31) / 32 + 1; c->pr.mpr = (max_read_len + 63) / 64 + 1;
+  A(&c->pr.bits, 2 * CH * c->pr.wpr); A(&c->pr.nmask, 2 * CH * c->pr.mpr);
+  // per batch (outputs)
+  A(&b.n_aln, B); A(&b.tid, B * cap); A(&b.score, B * cap); A(&b.prob, B * cap); A(&b.pos, B * cap);
+  A(&b.mate_pos, B * cap); A(&b.flags, B * cap); A(&b.flen, B * cap); A(&b.label, B * 2 * cap); A(&b.weight, B * cap);
   std::vector<double> t;
   build_fld_host(p, t);
   A(&c->d_fld, t.size());
-  if (rc != SB_OK) { delete c; return nullptr; }
+  if (rc == SB_OK) rc = agg_reserve(c->agg, B);
+  if (rc != SB_OK) { sb_map_destroy(c); return nullptr; }
   cudaMemcpy(c->d_fld, t.data(), t.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemset(c->pr.nmask, 0, 2 * CH * c->pr.mpr * 8);
   const uint32_t n = p.max_frag_len + 1;
   c->fld.max_val = p.max_frag_len; c->fld.pmf_live = c->d_fld; c->fld.pmf_cached = c->d_fld + n;
   c->fld.cmf_cached = c->d_fld + 2 * n; c->fld.cmf_quirk = c->d_fld + 3 * n;
   cudaMemset(b.ctr, 0, sizeof(Counters));
+  cudaMemset(c->d_full_dp, 0, 8);
   return c;
 }
 
 extern "C" void sb_map_destroy(sb_map_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
   BatchBufs& b = c->b;
   void* ptrs[] = {b.n_l, b.n_r, b.cand_l, b.cand_r, b.score_l, b.score_r, b.keys, b.n_tasks, b.tasks, b.n_aln, b.tid,
                   b.score, b.prob, b.pos, b.mate_pos, b.flags, b.flen, b.label, b.weight, b.sc, b.perm_idx, b.perm_tid,
-                  b.bs_tid, b.bs_score, b.bs_idx, b.jh, b.ctr, c->d_left, c->d_right, c->d_fld};
+                  b.bs_tid, b.bs_score, b.bs_idx, b.jh, b.ctr, c->d_in[0][0], c->d_in[0][1], c->d_in[1][0], c->d_in[1][1],
+                  c->d_fld, c->pr.bits, c->pr.nmask, c->d_overflow, c->d_next_task, c->d_full_dp};
   for (void* p : ptrs) cudaFree(p);
+  c->agg.free_all();
   for (auto& s : c->stores) s.free_all();
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
-  cudaStreamDestroy(c->stream);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  for (int s = 0; s < 2; ++s) { if (c->ev_in[s]) cudaEventDestroy(c->ev_in[s]); if (c->ev_free[s]) cudaEventDestroy(c->ev_free[s]); }
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
 }
 
-// records -> classes (used per batch with counts == nullptr, and at finish over all batch classes)
-static int aggregate(sb_map_ctx* c, uint32_t n, const uint64_t* loff, const uint64_t* woff, const uint32_t* labels,
-                     const double* weights, const uint64_t* counts, EqStore& out) {
+extern "C" int sb_map_set_option(sb_map_ctx* c, const char* key, int64_t value) {
+  if (!c || !key) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  if (!strcmp(key, "variant")) { c->variant = (int)value; return SB_OK; }
+  if (!strcmp(key, "fast_dp")) { c->fast_ok = value ? 1 : 0; return SB_OK; }
+  if (!strcmp(key, "chunk")) {   // reads per pipeline chunk (<= the size the context was created with)
+    const uint32_t mx = (uint32_t)std::min<size_t>(c->batch_cap, 65536);
+    if (value < 1 || value > (int64_t)mx) { sb::set_error("chunk must be in 1..%u", mx); return SB_ERR_INVALID; }
+    c->chunk = (uint32_t)value;
+    return SB_OK;
+  }
+  sb::set_error("sb_map_set_option: unknown key %s", key);
+  return SB_ERR_INVALID;
+}
+
+// records -> classes (per batch over the read slots, and at finish over all batch classes)
+static int aggregate(sb_map_ctx* c, Records R, EqStore& out) {
   cudaStream_t st = c->stream;
+  AggScratch& a = c->agg;
   out = EqStore();
+  const uint32_t n = R.n;
   if (n == 0) return SB_OK;
-  uint64_t *hash = nullptr, *hash2 = nullptr;
-  uint32_t *idx = nullptr, *idx2 = nullptr, *head = nullptr, *head_scan = nullptr, *first = nullptr;
-  uint64_t *llen = nullptr, *wlen = nullptr;
-  void* tmp = nullptr;
-  SB_TRY(dmalloc(&hash, n)); SB_TRY(dmalloc(&hash2, n)); SB_TRY(dmalloc(&idx, n)); SB_TRY(dmalloc(&idx2, n));
-  SB_TRY(dmalloc(&head, (size_t)n + 1)); SB_TRY(dmalloc(&head_scan, (size_t)n + 1));
-  k_label_hash<<<nblk(n, 256), 256, 0, st>>>(n, loff, labels, hash, idx);
-  size_t tb = 0, tb2 = 0, tb3 = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tb, hash, hash2, idx, idx2, (int)n, 0, 64, st);
-  cub::DeviceScan::ExclusiveSum(nullptr, tb2, head, head_scan, (int)n + 1, st);
-  cub::DeviceScan::ExclusiveSum(nullptr, tb3, llen, llen, (int)n + 1, st);
-  tb = std::max(tb, std::max(tb2, tb3));
-  SB_CUDA(cudaMalloc(&tmp, tb));
-  size_t t = tb;
-  SB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t, hash, hash2, idx, idx2, (int)n, 0, 64, st));   // stable
-  k_label_heads<<<nblk(n, 256), 256, 0, st>>>(n, hash2, idx2, loff, labels, head);
-  SB_CUDA(cudaMemsetAsync(head + n, 0, 4, st));
-  t = tb;
-  SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, t, head, head_scan, (int)n + 1, st));
+  k_label_hash<<<nblk(n, 256), 256, 0, st>>>(R, a.hash, a.idx);
+  size_t t = a.tmp_bytes;
+  SB_CUDA(cub::DeviceRadixSort::SortPairs(a.tmp, t, a.hash, a.hash2, a.idx, a.idx2, (int)n, 0, 64, st));   // stable
+  k_label_heads<<<nblk((uint64_t)n + 1, 256), 256, 0, st>>>(R, a.hash2, a.idx2, a.head);
+  t = a.tmp_bytes;
+  SB_CUDA(cub::DeviceScan::ExclusiveSum(a.tmp, t, a.head, a.head_scan, (int)n + 1, st));
   uint32_t nc = 0;
-  SB_CUDA(cudaMemcpyAsync(&nc, head_scan + n, 4, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(&nc, a.head_scan + n, 4, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
-  SB_TRY(dmalloc(&first, (size_t)nc + 1)); SB_TRY(dmalloc(&llen, (size_t)nc + 1)); SB_TRY(dmalloc(&wlen, (size_t)nc + 1));
-  SB_CUDA(cudaMemsetAsync(llen + nc, 0, 8, st)); SB_CUDA(cudaMemsetAsync(wlen + nc, 0, 8, st));
-  k_class_sizes<<<nblk(n, 256), 256, 0, st>>>(n, head, head_scan, idx2, loff, woff, first, llen, wlen);
+  SB_CUDA(cudaMemsetAsync(a.cls_llen + nc, 0, 8, st)); SB_CUDA(cudaMemsetAsync(a.cls_wlen + nc, 0, 8, st));
+  k_class_sizes<<<nblk(n, 256), 256, 0, st>>>(R, a.head, a.head_scan, a.idx2, a.first, a.cls_llen, a.cls_wlen);
   SB_TRY(dmalloc(&out.loff, (size_t)nc + 1)); SB_TRY(dmalloc(&out.woff, (size_t)nc + 1));
-  t = tb;
-  SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, t, llen, out.loff, (int)nc + 1, st));
-  t = tb;
-  SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, t, wlen, out.woff, (int)nc + 1, st));
+  t = a.tmp_bytes;
+  SB_CUDA(cub::DeviceScan::ExclusiveSum(a.tmp, t, a.cls_llen, out.loff, (int)nc + 1, st));
+  t = a.tmp_bytes;
+  SB_CUDA(cub::DeviceScan::ExclusiveSum(a.tmp, t, a.cls_wlen, out.woff, (int)nc + 1, st));
   uint64_t tl = 0, tw = 0;
   SB_CUDA(cudaMemcpyAsync(&tl, out.loff + nc, 8, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaMemcpyAsync(&tw, out.woff + nc, 8, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   SB_TRY(dmalloc(&out.labels, tl)); SB_TRY(dmalloc(&out.weights, tw)); SB_TRY(dmalloc(&out.counts, nc));
-  k_class_reduce<<<nblk(nc, 128), 128, 0, st>>>(nc, n, first, idx2, loff, woff, labels, weights, counts, out.loff,
-                                                out.woff, out.labels, out.weights, out.counts);
-  SB_CUDA(cudaStreamSynchronize(st));
+  k_class_reduce<<<nblk((uint64_t)nc * 32, 256), 256, 0, st>>>(R, nc, a.first, a.idx2, out.loff, out.woff, out.labels,
+                                                              out.weights, out.counts);
   out.n = nc; out.n_lab = tl; out.n_w = tw;
-  c->launches += 12;
-  cudaFree(hash); cudaFree(hash2); cudaFree(idx); cudaFree(idx2); cudaFree(head); cudaFree(head_scan);
-  cudaFree(first); cudaFree(llen); cudaFree(wlen); cudaFree(tmp);
+  c->launches += 10;
   return SB_OK;
 }
 
@@ -628,62 +727,80 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
   if (!c || (n && (!left || !right))) { sb::set_error("null argument"); return SB_ERR_INVALID; }
   if (n > c->batch_cap || L > c->read_len_cap || L < c->p.k) { sb::set_error("batch larger than the context was created for"); return SB_ERR_INVALID; }
   SB_CUDA(cudaSetDevice(c->device));
-  cudaStream_t st = c->stream;
-  BatchBufs& b = c->b;
+  cudaStream_t st = c->stream, cs = c->copy_stream;
+  BatchBufs b = c->b;
   const Params& p = c->p;
-  SB_CUDA(cudaEventRecord(c->ev0, st));
-  SB_CUDA(cudaMemcpyAsync(c->d_left, left, (size_t)n * L, cudaMemcpyHostToDevice, st));
-  SB_CUDA(cudaMemcpyAsync(c->d_right, right, (size_t)n * L, cudaMemcpyHostToDevice, st));
-  SB_CUDA(cudaMemsetAsync(b.n_tasks, 0, 16, st));
-  SB_CUDA(cudaMemsetAsync(b.ctr, 0, sizeof(Counters), st));
+  const uint32_t cap = p.max_read_occ;
   const IndexView ix = dev_view(c->index);
-  const uint32_t T = c->k1_threads;
-  if (n) {
-    k_seed_chain<<<T / 128, 128, 0, st>>>(ix, p, c->d_left, c->d_right, n, L, b);
-    k_dp_score<<<c->n_sm * 8, 256, 0, st>>>(ix, p, c->d_left, c->d_right, L, b);
-    const int useAux = c->frag_counter >= p.num_pre_burnin, burnedIn = c->frag_counter >= p.num_burnin;
-    k_assign<<<T / 128, 128, 0, st>>>(ix, p, c->fld, useAux, burnedIn, n, L, b);
-    c->launches += 3;
+  const int useAux = c->frag_counter >= p.num_pre_burnin, burnedIn = c->frag_counter >= p.num_burnin;
+  SB_CUDA(cudaEventRecord(c->ev0, st));
+  SB_CUDA(cudaMemsetAsync(c->b.ctr, 0, sizeof(Counters), st));
+  SB_CUDA(cudaMemsetAsync(c->d_full_dp, 0, 8, st));
+  // chunks: the host->device copy of chunk i+1 (copy stream) overlaps the kernels of chunk i
+  const uint32_t CH = c->chunk;
+  const uint32_t nch = (n + CH - 1) / CH;
+  SB_CUDA(cudaStreamWaitEvent(cs, c->ev0, 0));
+  for (uint32_t ch = 0; ch < nch; ++ch) {
+    const uint32_t c0 = ch * CH, cn = std::min(CH, n - c0);
+    const int s = (int)(ch & 1);
+    if (ch >= 2) SB_CUDA(cudaStreamWaitEvent(cs, c->ev_free[s], 0));
+    SB_CUDA(cudaMemcpyAsync(c->d_in[s][0], left + (size_t)c0 * L, (size_t)cn * L, cudaMemcpyHostToDevice, cs));
+    SB_CUDA(cudaMemcpyAsync(c->d_in[s][1], right + (size_t)c0 * L, (size_t)cn * L, cudaMemcpyHostToDevice, cs));
+    SB_CUDA(cudaEventRecord(c->ev_in[s], cs));
+    SB_CUDA(cudaStreamWaitEvent(st, c->ev_in[s], 0));
+    SB_CUDA(cudaMemsetAsync(c->b.n_tasks, 0, 16, st));
+    SB_CUDA(cudaMemsetAsync(c->d_next_task, 0, 16, st));
+    const uint8_t* dl = c->d_in[s][0];
+    const uint8_t* dr = c->d_in[s][1];
+    // outputs of this chunk inside the batch-wide arrays
+    BatchBufs bc = c->b;
+    bc.n_aln += c0; bc.tid += (size_t)c0 * cap; bc.score += (size_t)c0 * cap; bc.prob += (size_t)c0 * cap;
+    bc.pos += (size_t)c0 * cap; bc.mate_pos += (size_t)c0 * cap; bc.flags += (size_t)c0 * cap; bc.flen += (size_t)c0 * cap;
+    bc.label += (size_t)c0 * 2 * cap; bc.weight += (size_t)c0 * cap;
+    const uint32_t T = c->k1_threads;
+    if (c->variant == 0) {
+      k_seed_chain<<<T / 128, 128, 0, st>>>(ix, p, dl, dr, cn, L, bc);
+      k_dp_score<<<c->n_sm * 8, 256, 0, st>>>(ix, p, dl, dr, L, bc);
+      c->launches += 2;
+    } else {
+      k_pack_reads<<<nblk((uint64_t)2 * cn * c->pr.wpr, 256), 256, 0, st>>>(dl, dr, cn, L, c->pr);
+      SeedOut so{bc.n_l, bc.n_r, bc.cand_l, bc.cand_r, bc.n_tasks, bc.tasks, c->d_overflow, bc.ctr};
+      DpIo io{bc.n_tasks, bc.tasks, bc.cand_l, bc.cand_r, bc.score_l, bc.score_r, c->d_next_task, c->d_full_dp};
+      if (c->read_len_cap <= 128) {
+        k_seed_chain_w<2><<<c->seed_blocks, SEED_WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
+        k_dp_score_w<4><<<c->dp_blocks, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, c->fast_ok, io);
+      } else {
+        k_seed_chain_w<4><<<c->seed_blocks, SEED_WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
+        k_dp_score_w<8><<<c->dp_blocks, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, c->fast_ok, io);
+      }
+      c->launches += 3;
+    }
+    k_assign<<<T / 128, 128, 0, st>>>(ix, p, c->fld, useAux, burnedIn, cn, L, bc);
+    c->launches += 1;
+    SB_CUDA(cudaEventRecord(c->ev_free[s], st));
   }
-  // eq-class records of this batch
+  // eq-class records of this batch: the per-read slots themselves (no compaction)
   EqStore es;
   if (n) {
-    uint64_t *ll = nullptr, *wl = nullptr, *loff = nullptr, *woff = nullptr;
-    SB_TRY(dmalloc(&ll, (size_t)n + 1)); SB_TRY(dmalloc(&wl, (size_t)n + 1));
-    SB_TRY(dmalloc(&loff, (size_t)n + 1)); SB_TRY(dmalloc(&woff, (size_t)n + 1));
+    AggScratch& a = c->agg;
     const int binned = p.range_bins > 0;
-    k_read_lengths<<<nblk(n, 256), 256, 0, st>>>(n, b.n_aln, binned, ll, wl);
-    SB_CUDA(cudaMemsetAsync(ll + n, 0, 8, st)); SB_CUDA(cudaMemsetAsync(wl + n, 0, 8, st));
-    size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, ll, loff, (int)n + 1, st);
-    void* tmp = nullptr;
-    SB_CUDA(cudaMalloc(&tmp, tb));
-    size_t t = tb;
-    SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, t, ll, loff, (int)n + 1, st));
-    t = tb;
-    SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, t, wl, woff, (int)n + 1, st));
-    uint64_t tl = 0, tw = 0;
-    SB_CUDA(cudaMemcpyAsync(&tl, loff + n, 8, cudaMemcpyDeviceToHost, st));
-    SB_CUDA(cudaMemcpyAsync(&tw, woff + n, 8, cudaMemcpyDeviceToHost, st));
-    SB_CUDA(cudaStreamSynchronize(st));
-    uint32_t* labels = nullptr; double* weights = nullptr;
-    SB_TRY(dmalloc(&labels, tl)); SB_TRY(dmalloc(&weights, tw));
-    k_read_compact<<<nblk(n, 256), 256, 0, st>>>(n, p.max_read_occ, b.n_aln, binned, b.label, b.weight, loff, woff,
-                                                 labels, weights);
-    c->launches += 4;
-    // reads without alignments have empty labels: they all hash alike and would form one
-    // "empty" class; aggregate() keeps it and finish() drops it.
-    int rc = aggregate(c, n, loff, woff, labels, weights, nullptr, es);
-    cudaFree(ll); cudaFree(wl); cudaFree(loff); cudaFree(woff); cudaFree(labels); cudaFree(weights); cudaFree(tmp);
-    if (rc != SB_OK) return rc;
+    k_read_records<<<nblk(n, 256), 256, 0, st>>>(n, cap, binned, b.n_aln, a.lstart, a.llen, a.wstart, a.wlen);
+    c->launches += 1;
+    // reads without alignments have empty labels: they all hash alike and form one "empty"
+    // class; aggregate() keeps it and finish() drops it.
+    Records R{n, a.lstart, a.llen, a.wstart, a.wlen, b.label, b.weight, nullptr};
+    SB_TRY(aggregate(c, R, es));
     c->stores.push_back(es);
   }
   Counters h;
+  unsigned long long full_dp = 0;
   SB_CUDA(cudaMemcpyAsync(&h, b.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(&full_dp, c->d_full_dp, 8, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaEventRecord(c->ev1, st));
   SB_CUDA(cudaEventSynchronize(c->ev1));
   cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
   c->frag_counter += h.mapped;
+  c->full_dp_total += full_dp;
   c->totals.lookups += h.lookups; c->totals.postings += h.postings; c->totals.seeds += h.seeds;
   c->totals.candidates += h.candidates; c->totals.kept += h.kept; c->totals.label_entries += h.label_entries;
   c->totals.mapped += h.mapped;
@@ -692,6 +809,7 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
     stats->seeds = h.seeds; stats->candidates = h.candidates; stats->kept = h.kept; stats->label_entries = h.label_entries;
     stats->device_ms = c->last_ms; stats->gpu_launches = c->launches;
     stats->n_batch_classes = es.n;
+    stats->full_dp = full_dp;
   }
   return SB_OK;
 }
@@ -723,32 +841,30 @@ extern "C" int sb_map_finish(sb_map_ctx* c, sb_map_result* out) {
   if (!c || !out) { sb::set_error("null argument"); return SB_ERR_INVALID; }
   SB_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
-  // concatenate the batch stores
+  // the class tables of all batches, concatenated, become the records of one more aggregation
   uint64_t n = 0, nl = 0, nw = 0;
   for (auto& s : c->stores) { n += s.n; nl += s.n_lab; nw += s.n_w; }
+  if (n >= (1ull << 31)) { sb::set_error("sb_map_finish: too many batch classes"); return SB_ERR_INVALID; }
   EqStore merged;
   if (n) {
-    uint64_t *loff = nullptr, *woff = nullptr, *counts = nullptr;
-    uint32_t* labels = nullptr; double* weights = nullptr;
-    SB_TRY(dmalloc(&loff, n + 1)); SB_TRY(dmalloc(&woff, n + 1)); SB_TRY(dmalloc(&counts, n));
-    SB_TRY(dmalloc(&labels, nl)); SB_TRY(dmalloc(&weights, nw));
-    std::vector<uint64_t> hl(n + 1), hw(n + 1);
+    uint64_t* counts = nullptr; uint32_t* labels = nullptr; double* weights = nullptr;
+    SB_TRY(dmalloc(&counts, n)); SB_TRY(dmalloc(&labels, nl)); SB_TRY(dmalloc(&weights, nw));
+    SB_TRY(agg_reserve(c->agg, n));
+    AggScratch& a = c->agg;
     uint64_t i = 0, ol = 0, ow = 0;
     for (auto& s : c->stores) {
-      std::vector<uint64_t> tl(s.n + 1), tw(s.n + 1);
-      SB_CUDA(cudaMemcpy(tl.data(), s.loff, (s.n + 1) * 8, cudaMemcpyDeviceToHost));
-      SB_CUDA(cudaMemcpy(tw.data(), s.woff, (s.n + 1) * 8, cudaMemcpyDeviceToHost));
-      for (uint64_t q = 0; q < s.n; ++q) { hl[i + q] = ol + tl[q]; hw[i + q] = ow + tw[q]; }
-      SB_CUDA(cudaMemcpy(labels + ol, s.labels, s.n_lab * 4, cudaMemcpyDeviceToDevice));
-      SB_CUDA(cudaMemcpy(weights + ow, s.weights, s.n_w * 8, cudaMemcpyDeviceToDevice));
-      SB_CUDA(cudaMemcpy(counts + i, s.counts, s.n * 8, cudaMemcpyDeviceToDevice));
+      if (!s.n) continue;
+      SB_CUDA(cudaMemcpyAsync(labels + ol, s.labels, s.n_lab * 4, cudaMemcpyDeviceToDevice, st));
+      SB_CUDA(cudaMemcpyAsync(weights + ow, s.weights, s.n_w * 8, cudaMemcpyDeviceToDevice, st));
+      SB_CUDA(cudaMemcpyAsync(counts + i, s.counts, s.n * 8, cudaMemcpyDeviceToDevice, st));
+      k_store_records<<<nblk(s.n, 256), 256, 0, st>>>(s.n, s.loff, s.woff, ol, ow, a.lstart + i, a.llen + i, a.wstart + i,
+                                                      a.wlen + i);
       i += s.n; ol += s.n_lab; ow += s.n_w;
     }
-    hl[n] = ol; hw[n] = ow;
-    SB_CUDA(cudaMemcpy(loff, hl.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
-    SB_CUDA(cudaMemcpy(woff, hw.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
-    int rc = aggregate(c, (uint32_t)n, loff, woff, labels, weights, counts, merged);
-    cudaFree(loff); cudaFree(woff); cudaFree(counts); cudaFree(labels); cudaFree(weights);
+    Records R{(uint32_t)n, a.lstart, a.llen, a.wstart, a.wlen, labels, weights, counts};
+    int rc = aggregate(c, R, merged);
+    cudaStreamSynchronize(st);
+    cudaFree(counts); cudaFree(labels); cudaFree(weights);
     if (rc != SB_OK) return rc;
   }
   if (merged.n) {
@@ -769,6 +885,7 @@ extern "C" int sb_map_finish(sb_map_ctx* c, sb_map_result* out) {
     SB_CUDA(cudaStreamSynchronize(st));
   }
   c->h_off.assign(1, 0); c->h_counts.clear(); c->h_tids.clear(); c->h_ntx.clear(); c->h_bins.clear(); c->h_w.clear();
+  c->h_tids.reserve(merged.n_w); c->h_w.reserve(merged.n_w); c->h_counts.reserve(merged.n); c->h_off.reserve(merged.n + 1);
   for (uint64_t q = 0; q < merged.n; ++q) {
     const uint64_t ntx = woff[q + 1] - woff[q];
     if (ntx == 0) continue;

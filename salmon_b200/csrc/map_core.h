@@ -41,8 +41,11 @@ struct TableEntry {
   uint32_t cnt;   // number of postings
 };
 struct Posting {
-  uint32_t tid, tpos;
+  uint32_t tid;
+  uint32_t tpos_rc;   // bits 0..30: offset in the transcript; bit 31: the reference k-mer there is the
+                      // reverse complement of the canonical k-mer (orientation without touching the sequence)
 };
+constexpr uint32_t PACK_GUARD_BASES = 512;   // guard bases in front of / behind the 2-bit packed reference
 
 struct IndexView {
   uint32_t n_txps, k;
@@ -51,6 +54,8 @@ struct IndexView {
   const uint8_t* codes;      // one base per byte: 0..3, 4 = N
   const TableEntry* table;
   const Posting* post;       // ascending (tid, tpos) per k-mer
+  const uint64_t* packed;    // 2-bit codes, base g at bits 2*((g+GUARD)&31) of word (g+GUARD)>>5 (N stored as 0)
+  const uint8_t* tx_has_n;   // [n_txps] transcript contains a non-ACGT base (packed form unusable)
 };
 
 // FLD tables (log space), built on the host from the prior (FragmentLengthDistribution.cpp:22-78)
@@ -157,19 +162,14 @@ SB_HD uint32_t mate_candidates(const IndexView& ix, const Params& p, const uint8
       ctr.lookups++;
       uint32_t off, cnt;
       if (index_lookup(ix, canon, off, cnt) && cnt <= p.max_occs_per_hit) {
-        // first base where the k-mer and its reverse complement differ (k odd => exists)
-        uint32_t d = 0;
-        while (((fw >> (2 * (K - 1 - d))) & 3) == ((rc >> (2 * (K - 1 - d))) & 3)) ++d;
-        const uint8_t fw_d = (uint8_t)((fw >> (2 * (K - 1 - d))) & 3);
+        const uint32_t read_rc = (fw < rc) ? 0u : 1u;   // the read k-mer is the reverse complement of the canonical one
         for (uint32_t q = 0; q < cnt && ns < (uint32_t)MAXSEEDS; ++q) {
           ctr.postings++;
           const Posting po = ix.post[off + q];
-          const uint8_t ref_d = ix.codes[ix.tx_off[po.tid] + po.tpos + d];
-          uint32_t ori;
-          int32_t qpos;
-          if (ref_d == fw_d) { ori = 0; qpos = (int32_t)pos_i; }
-          else { ori = 1; qpos = (int32_t)(L - K - pos_i); }
-          keys[(size_t)ns * kstride] = seed_key(po.tid, ori, (int32_t)po.tpos - qpos, qpos);
+          const uint32_t tpos = po.tpos_rc & 0x7fffffffu;
+          const uint32_t ori = read_rc ^ (po.tpos_rc >> 31);
+          const int32_t qpos = ori ? (int32_t)(L - K - pos_i) : (int32_t)pos_i;
+          keys[(size_t)ns * kstride] = seed_key(po.tid, ori, (int32_t)tpos - qpos, qpos);
           ++ns;
         }
       }

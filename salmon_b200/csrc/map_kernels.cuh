@@ -1,0 +1,623 @@
+// map_kernels.cuh -- Stage A hot kernels for sm_100a (warp-cooperative forms of MAPSPEC, map_core.h).
+//
+//   k_pack_reads   byte codes -> 2-bit packed reads + N masks (once per batch; both later kernels read 48 B
+//                  per mate instead of L bytes)
+//   k_seed_chain_w one WARP per read pair.  Lanes = seed positions: the hash probes and the posting reads of
+//                  a mate are all in flight together (memory-level parallelism instead of a serial per-thread
+//                  walk); seeds are expanded into a per-warp shared-memory key array by a warp prefix sum,
+//                  bitonic-sorted there, chained by a segmented warp scan (coverage bit masks OR-ed along each
+//                  chain), filtered, paired, and the DP task list is written with one atomic per read.
+//   k_dp_score_w   one warp per mate alignment.  Read and reference window live in registers (2-bit packed,
+//                  no memory access in the DP loop).  Lanes = band diagonals first evaluate the 2*band+1
+//                  ungapped alignments by XOR/popcount; when the best of them is within (go+ge) of a perfect
+//                  score no gapped path can beat it, so the banded affine DP -- same recurrences as
+//                  dp_score_serial -- only runs for the remaining alignments.
+//
+// All three produce exactly what the serial forms in map_core.h produce (tests/test_map_gpu.py compares the
+// CUDA path with the independent oracle bit for bit).
+#pragma once
+#include "map_core.h"
+
+namespace sbmap {
+
+constexpr int SEED_WARPS = 8;        // warps per block of k_seed_chain_w
+constexpr int SK = 512;              // seed keys per warp held in shared memory (more: global scratch)
+constexpr uint32_t MAX_LOOKUPS = 64; // seed positions per mate handled by the warp kernel (2 rounds of 32)
+
+struct PackedReads {
+  uint64_t* bits;    // [(2*n) * wpr]  base j of a mate at bits 2*(j&31) of word j>>5 (N stored as 0)
+  uint64_t* nmask;   // [(2*n) * mpr]  bit j set: base j is N
+  uint32_t wpr, mpr; // words per mate: ceil(Lcap/32)+1 (one zero guard word), ceil(Lcap/64)+1
+};
+
+// reverse the order of the 32 two-bit groups of a word
+__device__ __forceinline__ uint64_t brev2(uint64_t x) {
+  const uint64_t y = __brevll(x);
+  return ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
+}
+// 64-bit window starting `sh` bits into lo (sh in 0..63), continuing into hi
+__device__ __forceinline__ uint64_t funnel64(uint64_t lo, uint64_t hi, uint32_t sh) {
+  return sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_pack_reads: one thread per (mate, 32-base word)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack_reads(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right, uint32_t n,
+                             uint32_t L, PackedReads pr) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t total = (uint64_t)2 * n * pr.wpr;
+  if (t >= total) return;
+  const uint32_t w = (uint32_t)(t % pr.wpr);
+  const uint64_t m = t / pr.wpr;               // mate index: 2*r + mate
+  const uint8_t* src = ((m & 1) ? right : left) + (m >> 1) * L;
+  uint64_t bits = 0;
+  uint32_t nm = 0;
+  const uint32_t b0 = w * 32;
+  for (uint32_t j = 0; j < 32; ++j) {
+    const uint32_t q = b0 + j;
+    if (q >= L) break;
+    const uint8_t c = src[q];
+    if (c > 3) nm |= 1u << j;
+    else bits |= (uint64_t)c << (2 * j);
+  }
+  pr.bits[m * pr.wpr + w] = bits;
+  // the N mask of word w is half of mask word w>>1: two threads of the same mate share a word
+  if (w < 2 * pr.mpr) {
+    uint32_t* nm32 = reinterpret_cast<uint32_t*>(pr.nmask + m * pr.mpr);
+    nm32[w] = nm;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_seed_chain_w
+// ---------------------------------------------------------------------------------------------
+struct SeedOut {
+  uint32_t* n_l; uint32_t* n_r;
+  Cand* cand_l; Cand* cand_r;
+  uint32_t* n_tasks; uint32_t* tasks;
+  uint64_t* overflow_keys;   // [n_warps * MAXSEEDS]
+  Counters* ctr;
+};
+
+// candidate packed like a seed key with the coverage in the qpos field
+__device__ __forceinline__ uint64_t cand_word(uint64_t key, int32_t diag_c, uint32_t cov) {
+  return (key & 0xffffffff80000000ull) | ((uint64_t)(uint32_t)(diag_c + (1 << 21)) << 9) | (uint64_t)cov;
+}
+__device__ __forceinline__ uint32_t cw_cov(uint64_t w) { return (uint32_t)(w & 0x1ffu); }
+
+// (cov desc, tid, ori, diag_c) order of the oracle's cmp_cand_cov: does a beat b?
+__device__ __forceinline__ bool cand_beats(uint64_t a, uint64_t b) {
+  const uint32_t ca = cw_cov(a), cb = cw_cov(b);
+  if (ca != cb) return ca > cb;
+  return (a >> 9) < (b >> 9);
+}
+
+template <int CW>   // coverage words: 2 for read_len <= 128, 4 for <= 256
+__device__ __forceinline__ uint32_t warp_mate_candidates(const IndexView& ix, const Params& p,
+                                                         const uint64_t* __restrict__ rbits,   // shared: wpr words
+                                                         const uint64_t* __restrict__ rnm,     // shared: mpr words
+                                                         uint32_t L, uint64_t* skeys, uint64_t* gkeys,
+                                                         uint64_t* cands /* shared, MAXCAND */, Counters& ctr,
+                                                         uint32_t lane) {
+  const uint32_t K = p.k;
+  const uint64_t kmask = (1ull << (2 * K)) - 1;
+  const uint32_t span = L - K;
+  uint32_t npos = span / p.stride + 1;
+  if (span % p.stride) ++npos;
+  // ---- lookups: lane + 32*round = seed position index
+  uint32_t off[2], cnt[2], meta[2];   // meta: pos_i | read_rc << 16
+  uint32_t n_valid = 0;
+#pragma unroll
+  for (int rd = 0; rd < 2; ++rd) {
+    const uint32_t li = lane + 32u * rd;
+    off[rd] = 0; cnt[rd] = 0; meta[rd] = 0;
+    if (li < npos) {
+      uint32_t pos_i = li * p.stride;
+      if (pos_i > span) pos_i = span;
+      const uint32_t wi = pos_i >> 5, sh = 2 * (pos_i & 31);
+      const uint64_t fwle = funnel64(rbits[wi], rbits[wi + 1], sh) & kmask;
+      const uint32_t mi = pos_i >> 6, msh = pos_i & 63;
+      const uint64_t nwin = funnel64(rnm[mi], rnm[mi + 1], msh) & ((1ull << K) - 1);
+      if (nwin == 0) {
+        const uint64_t fw = brev2(fwle) >> (64 - 2 * K);
+        const uint64_t rc = (~fwle) & kmask;
+        const uint64_t canon = fw < rc ? fw : rc;
+        ++n_valid;
+        uint32_t o, c;
+        if (index_lookup(ix, canon, o, c) && c <= p.max_occs_per_hit) {
+          off[rd] = o; cnt[rd] = c;
+          meta[rd] = pos_i | ((fw < rc ? 0u : 1u) << 16);
+        }
+      }
+    }
+  }
+  // ---- slots: exclusive prefix over the lookups in position order
+  uint32_t excl[2], tot[2];
+#pragma unroll
+  for (int rd = 0; rd < 2; ++rd) {
+    uint32_t x = cnt[rd];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((int)lane >= o) x += y;
+    }
+    tot[rd] = __shfl_sync(0xffffffffu, x, 31);
+    excl[rd] = x - cnt[rd];
+  }
+  const uint32_t total = tot[0] + tot[1];
+  const uint32_t T = total < (uint32_t)MAXSEEDS ? total : (uint32_t)MAXSEEDS;
+  if (lane == 0) { ctr.postings += T; ctr.seeds += T; }
+  ctr.lookups += n_valid;     // per lane; summed when the counters are flushed
+  if (T == 0) return 0;
+  uint64_t* keys = (T <= (uint32_t)SK) ? skeys : gkeys;
+  uint32_t n2 = 32;
+  while (n2 < T) n2 <<= 1;
+  // ---- expand postings into seed keys
+  uint32_t carry = 0;
+#pragma unroll
+  for (int rd = 0; rd < 2; ++rd) {
+    for (uint32_t it = 0; it < tot[rd]; it += 32) {
+      const uint32_t item = it + lane;
+      uint32_t lo = 0;
+#pragma unroll
+      for (int st = 16; st > 0; st >>= 1) {
+        const uint32_t e = __shfl_sync(0xffffffffu, excl[rd], lo + st);
+        if (e <= item) lo += st;
+      }
+      const uint32_t o_off = __shfl_sync(0xffffffffu, off[rd], lo);
+      const uint32_t o_excl = __shfl_sync(0xffffffffu, excl[rd], lo);
+      const uint32_t o_meta = __shfl_sync(0xffffffffu, meta[rd], lo);
+      const uint32_t slot = carry + item;
+      if (item < tot[rd] && slot < (uint32_t)MAXSEEDS) {
+        const Posting po = ix.post[o_off + (item - o_excl)];
+        const uint32_t pos_i = o_meta & 0xffffu;
+        const uint32_t ori = (o_meta >> 16) ^ (po.tpos_rc >> 31);
+        const int32_t qpos = ori ? (int32_t)(span - pos_i) : (int32_t)pos_i;
+        keys[slot] = seed_key(po.tid, ori, (int32_t)(po.tpos_rc & 0x7fffffffu) - qpos, qpos);
+      }
+    }
+    carry += tot[rd];
+  }
+  for (uint32_t i = T + lane; i < n2; i += 32) keys[i] = EMPTY_KEY;
+  __syncwarp();
+  // ---- bitonic sort of n2 keys
+  for (uint32_t k = 2; k <= n2; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = lane; t < (n2 >> 1); t += 32) {
+        const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const uint32_t l = i | j;
+        const uint64_t a = keys[i], b = keys[l];
+        const bool asc = (i & k) == 0;
+        if ((a > b) == asc) { keys[i] = b; keys[l] = a; }
+      }
+      __syncwarp();
+    }
+  // ---- chains: segmented scan over the sorted keys; the tail of every chain is replaced by its
+  //      candidate word, every other slot by EMPTY
+  uint32_t best = 0;
+  uint64_t carry_key = EMPTY_KEY;
+  uint64_t carry_m[CW];
+  int32_t carry_dmin = 0;
+#pragma unroll
+  for (int w = 0; w < CW; ++w) carry_m[w] = 0;
+  const int32_t gap = (int32_t)p.chain_gap;
+  for (uint32_t base = 0; base < T; base += 32) {
+    const uint32_t i = base + lane;
+    const bool active = i < T;
+    const uint64_t k = active ? keys[i] : EMPTY_KEY;
+    uint64_t kprev = __shfl_up_sync(0xffffffffu, k, 1);
+    if (lane == 0) kprev = carry_key;
+    uint64_t knext = __shfl_down_sync(0xffffffffu, k, 1);
+    if (lane == 31) knext = (i + 1 < T) ? keys[i + 1] : EMPTY_KEY;
+    const int32_t dg = key_diag(k);
+    const bool head = active && (i == 0 || (kprev >> 31) != (k >> 31) || dg - key_diag(kprev) > gap);
+    const bool tail = active && (i + 1 >= T || (knext >> 31) != (k >> 31) || key_diag(knext) - dg > gap);
+    uint64_t m[CW];
+    {
+      const int32_t q = key_qpos(k);
+#pragma unroll
+      for (int w = 0; w < CW; ++w) {
+        int32_t lo = q - 64 * w, hi = lo + (int32_t)K;
+        lo = lo < 0 ? 0 : lo;
+        hi = hi > 64 ? 64 : hi;
+        m[w] = (active && lo < hi) ? (((1ull << (hi - lo)) - 1) << lo) : 0ull;
+      }
+    }
+    int32_t dmin = dg;
+    uint32_t f = head ? 1u : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t pf = __shfl_up_sync(0xffffffffu, f, o);
+      const int32_t pd = __shfl_up_sync(0xffffffffu, dmin, o);
+      uint64_t pm[CW];
+#pragma unroll
+      for (int w = 0; w < CW; ++w) pm[w] = __shfl_up_sync(0xffffffffu, m[w], o);
+      if ((int)lane >= o && !f) {
+#pragma unroll
+        for (int w = 0; w < CW; ++w) m[w] |= pm[w];
+        dmin = pd;
+        f = pf;
+      }
+    }
+    if (!f) {   // the chain started in an earlier chunk
+#pragma unroll
+      for (int w = 0; w < CW; ++w) m[w] |= carry_m[w];
+      dmin = carry_dmin;
+    }
+    carry_key = __shfl_sync(0xffffffffu, k, 31);
+    carry_dmin = __shfl_sync(0xffffffffu, dmin, 31);
+#pragma unroll
+    for (int w = 0; w < CW; ++w) carry_m[w] = __shfl_sync(0xffffffffu, m[w], 31);
+    uint32_t cov = 0;
+#pragma unroll
+    for (int w = 0; w < CW; ++w) cov += (uint32_t)__popcll(m[w]);
+    if (tail && cov > best) best = cov;
+    __syncwarp();
+    if (active) keys[i] = tail ? cand_word(k, dmin + (dg - dmin) / 2, cov) : EMPTY_KEY;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, best, o);
+    best = y > best ? y : best;
+  }
+  __syncwarp();
+  // ---- survivors (coverage >= consensus_frac * best), in (tid, ori, diag) order
+  const double thr = p.consensus_frac * (double)best;
+  uint32_t nc = 0;
+  for (uint32_t base = 0; base < T; base += 32) {
+    const uint32_t i = base + lane;
+    const uint64_t w = (i < T) ? keys[i] : EMPTY_KEY;
+    const bool keep = (w != EMPTY_KEY) && ((double)cw_cov(w) >= thr);
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    const uint32_t rank = nc + (uint32_t)__popc(bal & ((1u << lane) - 1));
+    if (keep && rank < (uint32_t)MAXCAND) cands[rank] = w;
+    nc += (uint32_t)__popc(bal);
+  }
+  if (nc > (uint32_t)MAXCAND) {
+    // rare: keep the MAXCAND best by (coverage desc, tid, ori, diag); rank by counting who beats whom
+    uint32_t out = 0;
+    for (uint32_t base = 0; base < T; base += 32) {
+      const uint32_t i = base + lane;
+      const uint64_t w = (i < T) ? keys[i] : EMPTY_KEY;
+      const bool surv = (w != EMPTY_KEY) && ((double)cw_cov(w) >= thr);
+      uint32_t beaten_by = 0;
+      for (uint32_t q = 0; q < T; ++q) {
+        const uint64_t x = keys[q];
+        if (x != EMPTY_KEY && (double)cw_cov(x) >= thr && surv && cand_beats(x, w)) ++beaten_by;
+      }
+      const bool keep = surv && beaten_by < (uint32_t)MAXCAND;
+      const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+      const uint32_t rank = out + (uint32_t)__popc(bal & ((1u << lane) - 1));
+      if (keep) cands[rank] = w;
+      out += (uint32_t)__popc(bal);
+    }
+    nc = (uint32_t)MAXCAND;
+  }
+  __syncwarp();
+  return nc;
+}
+
+__device__ __forceinline__ uint32_t cwd_tid(uint64_t w) { return (uint32_t)(w >> 32); }
+__device__ __forceinline__ uint32_t cwd_ori(uint64_t w) { return (uint32_t)(w >> 31) & 1u; }
+__device__ __forceinline__ int32_t cwd_diag(uint64_t w) { return (int32_t)((w >> 9) & 0x3fffffu) - (1 << 21); }
+
+template <int CW>
+__global__ void __launch_bounds__(SEED_WARPS * 32, 4)
+k_seed_chain_w(IndexView ix, Params p, PackedReads pr, uint32_t n, uint32_t L, SeedOut o) {
+  __shared__ uint64_t s_keys[SEED_WARPS][SK];
+  __shared__ uint64_t s_cand[SEED_WARPS][2][MAXCAND];
+  __shared__ uint64_t s_read[SEED_WARPS][16];   // wpr (<= 9) + mpr (<= 5) words of the current mate
+  const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  const uint32_t warp = blockIdx.x * SEED_WARPS + wib, nwarps = gridDim.x * SEED_WARPS;
+  uint64_t* gkeys = o.overflow_keys + (size_t)warp * MAXSEEDS;
+  Counters ctr;
+  ctr.lookups = ctr.postings = ctr.seeds = ctr.candidates = ctr.kept = ctr.label_entries = ctr.mapped = 0;
+  for (uint32_t r = warp; r < n; r += nwarps) {
+    uint32_t ncand[2];
+#pragma unroll
+    for (int mate = 0; mate < 2; ++mate) {
+      const uint64_t mi = (uint64_t)2 * r + mate;
+      __syncwarp();
+      if (lane < pr.wpr) s_read[wib][lane] = pr.bits[mi * pr.wpr + lane];
+      else if (lane < pr.wpr + pr.mpr) s_read[wib][lane] = pr.nmask[mi * pr.mpr + (lane - pr.wpr)];
+      __syncwarp();
+      ncand[mate] = warp_mate_candidates<CW>(ix, p, s_read[wib], s_read[wib] + pr.wpr, L, s_keys[wib], gkeys,
+                                             s_cand[wib][mate], ctr, lane);
+    }
+    const uint32_t nl = ncand[0], nr = ncand[1];
+    const uint64_t* cl = s_cand[wib][0];
+    const uint64_t* cr = s_cand[wib][1];
+    // ---- joint hits (IU): which candidates take part in one
+    uint32_t my_cnt = 0;
+    unsigned long long my_used_r = 0ull;
+    bool used_a[2] = {false, false};
+#pragma unroll
+    for (int rd = 0; rd < 2; ++rd) {
+      const uint32_t a = lane + 32u * rd;
+      if (a < nl) {
+        const uint64_t wa = cl[a];
+        const int32_t da = cwd_diag(wa);
+        for (uint32_t b = 0; b < nr; ++b) {
+          const uint64_t wb = cr[b];
+          if (cwd_tid(wa) != cwd_tid(wb) || cwd_ori(wa) == cwd_ori(wb)) continue;
+          const int32_t db = cwd_diag(wb);
+          int32_t start, end;
+          bool ok;
+          if (cwd_ori(wa) == 0) { start = da; end = db + (int32_t)L; ok = db >= da; }
+          else { start = db; end = da + (int32_t)L; ok = da >= db; }
+          const int32_t fl = end - start;
+          if (!ok || fl <= 0 || fl > (int32_t)p.max_frag_len) continue;
+          ++my_cnt;
+          my_used_r |= 1ull << b;
+          used_a[rd] = true;
+        }
+      }
+    }
+    unsigned long long used_l = (unsigned long long)__ballot_sync(0xffffffffu, used_a[0]) |
+                                ((unsigned long long)__ballot_sync(0xffffffffu, used_a[1]) << 32);
+    unsigned long long used_r = my_used_r;
+    uint32_t nj = my_cnt;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      nj += __shfl_xor_sync(0xffffffffu, nj, s);
+      used_r |= __shfl_xor_sync(0xffffffffu, used_r, s);
+    }
+    if (nj == 0) {   // orphans
+      nj = nl + nr;
+      used_l = nl >= 64 ? ~0ull : ((1ull << nl) - 1);
+      used_r = nr >= 64 ? ~0ull : ((1ull << nr) - 1);
+    }
+    // ---- write the candidates and the DP tasks
+    for (uint32_t a = lane; a < nl; a += 32) {
+      Cand c; c.tid = cwd_tid(cl[a]); c.diag_c = cwd_diag(cl[a]); c.ori_cov = (cwd_ori(cl[a]) << 31) | cw_cov(cl[a]);
+      o.cand_l[(size_t)r * MAXCAND + a] = c;
+    }
+    for (uint32_t a = lane; a < nr; a += 32) {
+      Cand c; c.tid = cwd_tid(cr[a]); c.diag_c = cwd_diag(cr[a]); c.ori_cov = (cwd_ori(cr[a]) << 31) | cw_cov(cr[a]);
+      o.cand_r[(size_t)r * MAXCAND + a] = c;
+    }
+    const bool unmapped = (nj == 0 || nj > p.max_read_occ);
+    if (lane == 0) { o.n_l[r] = unmapped ? (nl | 0x80000000u) : nl; o.n_r[r] = nr; }
+    if (!unmapped) {
+      const uint32_t cl_n = (uint32_t)__popcll(used_l), cnt = cl_n + (uint32_t)__popcll(used_r);
+      uint32_t slot = 0;
+      if (lane == 0) { slot = atomicAdd(o.n_tasks, cnt); ctr.candidates += cnt; }
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+#pragma unroll
+      for (int rd = 0; rd < 2; ++rd) {
+        const uint32_t a = lane + 32u * rd;
+        if ((used_l >> a) & 1ull) o.tasks[slot + (uint32_t)__popcll(used_l & ((1ull << a) - 1))] = (r << 7) | a;
+        if ((used_r >> a) & 1ull) o.tasks[slot + cl_n + (uint32_t)__popcll(used_r & ((1ull << a) - 1))] = (r << 7) | 64u | a;
+      }
+    }
+  }
+  // flush counters: lookups are per lane, the rest live in lane 0
+  unsigned long long lk = ctr.lookups;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) lk += __shfl_xor_sync(0xffffffffu, lk, s);
+  if (lane == 0) {
+    if (lk) atomicAdd(&o.ctr->lookups, lk);
+    if (ctr.postings) atomicAdd(&o.ctr->postings, ctr.postings);
+    if (ctr.seeds) atomicAdd(&o.ctr->seeds, ctr.seeds);
+    if (ctr.candidates) atomicAdd(&o.ctr->candidates, ctr.candidates);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_dp_score_w
+// ---------------------------------------------------------------------------------------------
+struct DpIo {
+  const uint32_t* n_tasks; const uint32_t* tasks;
+  const Cand* cand_l; const Cand* cand_r;
+  int32_t* score_l; int32_t* score_r;
+  uint32_t* next_task;            // dynamic task counter
+  unsigned long long* n_full_dp;  // statistics: alignments that needed the full DP
+};
+
+// byte-code form (transcripts with N, reads with N): lanes = band cells, one reference byte per row
+__device__ __forceinline__ int32_t dp_warp_bytes(const IndexView& ix, const Params& p, const uint8_t* read, uint32_t L,
+                                                 const Cand& c, uint32_t lane) {
+  const int32_t B = (int32_t)p.band, W = 2 * B + 1;
+  const uint32_t ori = c.ori_cov >> 31;
+  const int64_t tlen = (int64_t)(ix.tx_off[c.tid + 1] - ix.tx_off[c.tid]);
+  const uint8_t* ref = ix.codes + ix.tx_off[c.tid];
+  const bool in_band = (int32_t)lane < W;
+  int32_t H = in_band ? 0 : NEG_SCORE, E = NEG_SCORE;
+  int64_t rpos = (int64_t)c.diag_c + ((int32_t)lane - B);
+  uint8_t rbase = (rpos >= 0 && rpos < tlen) ? ref[rpos] : (uint8_t)255;
+  for (uint32_t i = 0; i < L; ++i) {
+    const uint8_t cc = ori ? read[L - 1 - i] : read[i];
+    const uint8_t rb = ori ? (uint8_t)(cc > 3 ? 4 : 3 - cc) : cc;
+    const bool valid = in_band && rbase != 255;
+    const int32_t Hup = __shfl_down_sync(0xffffffffu, H, 1);
+    const int32_t Eup = __shfl_down_sync(0xffffffffu, E, 1);
+    int32_t m = NEG_SCORE, e = NEG_SCORE;
+    if (valid) {
+      m = H + ((rb < 4 && rb == rbase) ? p.ma : p.mp);
+      if ((int32_t)lane + 1 < W) e = max(Hup - p.go - p.ge, Eup - p.ge);
+      if (e < NEG_SCORE) e = NEG_SCORE;
+    }
+    const int32_t hp = valid ? max(m, e) : NEG_SCORE;
+    int32_t x = (hp <= NEG_SCORE) ? NEG_SCORE : hp + (int32_t)lane * p.ge;
+    int32_t pref = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane == 0) pref = NEG_SCORE;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t y = __shfl_up_sync(0xffffffffu, pref, o);
+      if ((int)lane >= o) pref = max(pref, y);
+    }
+    int32_t f = (pref <= NEG_SCORE) ? NEG_SCORE : pref - p.go - (int32_t)lane * p.ge;
+    if (f < NEG_SCORE) f = NEG_SCORE;
+    int32_t h = NEG_SCORE;
+    if (valid) { h = max(hp, f); if (h < NEG_SCORE) h = NEG_SCORE; }
+    H = h;
+    E = valid ? e : NEG_SCORE;
+    const uint8_t nb = __shfl_down_sync(0xffffffffu, rbase, 1);
+    ++rpos;
+    if ((int32_t)lane == W - 1) rbase = (rpos >= 0 && rpos < tlen) ? ref[rpos] : (uint8_t)255;
+    else rbase = nb;
+  }
+  int32_t best = in_band ? H : NEG_SCORE;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+  return best;
+}
+
+template <int NWR>   // read words: 4 (read_len <= 128) or 8 (<= 256)
+__global__ void __launch_bounds__(256, 4)
+k_dp_score_w(IndexView ix, Params p, PackedReads pr, const uint8_t* __restrict__ left,
+             const uint8_t* __restrict__ right, uint32_t L, int fast_ok, DpIo io) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t ntasks = *io.n_tasks;
+  const int32_t B = (int32_t)p.band, W = 2 * B + 1;
+  unsigned long long n_full = 0;
+  for (;;) {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(io.next_task, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= ntasks) break;
+    const uint32_t task = io.tasks[t];
+    const uint32_t r = task >> 7, mate = (task >> 6) & 1u, ci = task & 63u;
+    const Cand c = mate ? io.cand_r[(size_t)r * MAXCAND + ci] : io.cand_l[(size_t)r * MAXCAND + ci];
+    int32_t* out = (mate ? io.score_r : io.score_l) + (size_t)r * MAXCAND + ci;
+    const uint64_t mi = (uint64_t)2 * r + mate;
+    // ---- N anywhere: byte path
+    bool slow = ix.tx_has_n[c.tid] != 0;
+    for (uint32_t w = 0; w < pr.mpr; ++w) slow |= pr.nmask[mi * pr.mpr + w] != 0;
+    if (slow) {
+      const int32_t s = dp_warp_bytes(ix, p, (mate ? right : left) + (size_t)r * L, L, c, lane);
+      if (lane == 0) *out = s;
+      ++n_full;
+      continue;
+    }
+    const uint32_t ori = c.ori_cov >> 31;
+    const int64_t tbase = (int64_t)ix.tx_off[c.tid];
+    const int64_t tlen = (int64_t)ix.tx_off[c.tid + 1] - tbase;
+    // ---- the read as it aligns to the forward reference strand (reverse-complemented when ori = 1)
+    uint64_t rw[NWR];
+#pragma unroll
+    for (int m = 0; m < NWR; ++m) rw[m] = ((uint32_t)m < pr.wpr) ? pr.bits[mi * pr.wpr + m] : 0ull;
+    if (ori) {
+      uint64_t t2[NWR + 1];
+#pragma unroll
+      for (int m = 0; m < NWR; ++m) t2[m] = brev2(~rw[NWR - 1 - m]);
+      t2[NWR] = 0;
+      const uint32_t drop = (uint32_t)NWR * 32u - L;          // bases to drop at the low end
+      const uint32_t dw = drop >> 5, dsh = 2 * (drop & 31);
+#pragma unroll
+      for (int m = 0; m < NWR; ++m) {
+        uint64_t lo = 0, hi = 0;
+#pragma unroll
+        for (int q = 0; q <= NWR; ++q) {
+          if ((uint32_t)q == (uint32_t)m + dw) lo = t2[q];
+          if ((uint32_t)q == (uint32_t)m + dw + 1) hi = t2[q];
+        }
+        rw[m] = funnel64(lo, hi, dsh);
+      }
+    }
+    // mask the bases beyond L
+#pragma unroll
+    for (int m = 0; m < NWR; ++m) {
+      const int32_t nb = (int32_t)L - 32 * m;
+      if (nb <= 0) rw[m] = 0;
+      else if (nb < 32) rw[m] &= (1ull << (2 * nb)) - 1;
+    }
+    // ---- reference window: bases diag_c - B ... diag_c + L + B - 1  (window index 0 ... L + 2B - 1)
+    const int64_t g0 = tbase + (int64_t)c.diag_c - B + (int64_t)PACK_GUARD_BASES;
+    const uint64_t* P = ix.packed + (g0 >> 5);
+    const uint32_t gsh = 2 * (uint32_t)(g0 & 31);
+    uint64_t ww[NWR + 2];
+    {
+      uint64_t prev = __ldg(P);
+#pragma unroll
+      for (int m = 0; m < NWR + 1; ++m) {
+        const uint64_t nxt = __ldg(P + m + 1);
+        ww[m] = funnel64(prev, nxt, gsh);
+        prev = nxt;
+      }
+      ww[NWR + 1] = 0;
+    }
+    // ---- ungapped alignments on the 2B+1 diagonals (lane = diagonal)
+    int32_t best_u = NEG_SCORE;
+    if (fast_ok) {
+      const int64_t s0 = (int64_t)c.diag_c + ((int32_t)lane - B);
+      if ((int32_t)lane < W && s0 >= 0 && s0 + (int64_t)L <= tlen) {
+        uint32_t mm = 0;
+#pragma unroll
+        for (int m = 0; m < NWR; ++m) {
+          const uint64_t x = funnel64(ww[m], ww[m + 1], 2 * lane) ^ rw[m];
+          uint64_t d = (x | (x >> 1)) & 0x5555555555555555ull;
+          const int32_t nb = (int32_t)L - 32 * m;
+          if (nb <= 0) d = 0;
+          else if (nb < 32) d &= (1ull << (2 * nb)) - 1;
+          mm += (uint32_t)__popcll(d);
+        }
+        best_u = p.ma * (int32_t)(L - mm) + p.mp * (int32_t)mm;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) best_u = max(best_u, __shfl_xor_sync(0xffffffffu, best_u, o));
+      if (best_u >= p.ma * (int32_t)L - p.go - p.ge) {
+        if (lane == 0) *out = best_u;
+        continue;
+      }
+    }
+    ++n_full;
+    // ---- banded affine DP, operands in registers
+    const bool in_band = (int32_t)lane < W;
+    int32_t H = in_band ? 0 : NEG_SCORE, E = NEG_SCORE;
+    int64_t rpos = (int64_t)c.diag_c + ((int32_t)lane - B);
+    uint32_t rbase = (rpos >= 0 && rpos < tlen) ? (uint32_t)((ww[0] >> (2 * lane)) & 3ull) : 255u;
+    // stream of the bases entering at the last band lane: window index W, W+1, ...
+    uint64_t rs[NWR + 1];
+#pragma unroll
+    for (int m = 0; m < NWR + 1; ++m) rs[m] = funnel64(ww[m], ww[m + 1], 2 * (uint32_t)W);
+#pragma unroll
+    for (int m = 0; m < NWR; ++m) {
+      uint64_t cur = rw[m], curs = rs[m];
+      const uint32_t i0 = 32u * m;
+      if (i0 >= L) break;
+      const uint32_t iend = (L - i0 < 32u) ? (L - i0) : 32u;
+      for (uint32_t ii = 0; ii < iend; ++ii) {
+        const uint32_t rb = (uint32_t)(cur & 3ull);
+        cur >>= 2;
+        const bool valid = in_band && rbase != 255u;
+        const int32_t Hup = __shfl_down_sync(0xffffffffu, H, 1);
+        const int32_t Eup = __shfl_down_sync(0xffffffffu, E, 1);
+        int32_t mval = NEG_SCORE, e = NEG_SCORE;
+        if (valid) {
+          mval = H + ((rb == rbase) ? p.ma : p.mp);
+          if ((int32_t)lane + 1 < W) e = max(Hup - p.go - p.ge, Eup - p.ge);
+          if (e < NEG_SCORE) e = NEG_SCORE;
+        }
+        const int32_t hp = valid ? max(mval, e) : NEG_SCORE;
+        int32_t x = (hp <= NEG_SCORE) ? NEG_SCORE : hp + (int32_t)lane * p.ge;
+        int32_t pref = __shfl_up_sync(0xffffffffu, x, 1);
+        if (lane == 0) pref = NEG_SCORE;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int32_t y = __shfl_up_sync(0xffffffffu, pref, o);
+          if ((int)lane >= o) pref = max(pref, y);
+        }
+        int32_t f = (pref <= NEG_SCORE) ? NEG_SCORE : pref - p.go - (int32_t)lane * p.ge;
+        if (f < NEG_SCORE) f = NEG_SCORE;
+        int32_t h = NEG_SCORE;
+        if (valid) { h = max(hp, f); if (h < NEG_SCORE) h = NEG_SCORE; }
+        H = h;
+        E = valid ? e : NEG_SCORE;
+        const uint32_t nb = __shfl_down_sync(0xffffffffu, rbase, 1);
+        ++rpos;
+        if ((int32_t)lane == W - 1) rbase = (rpos >= 0 && rpos < tlen) ? (uint32_t)(curs & 3ull) : 255u;
+        else rbase = nb;
+        curs >>= 2;
+      }
+    }
+    int32_t best = in_band ? H : NEG_SCORE;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) *out = best;
+  }
+  if (lane == 0 && n_full) atomicAdd(io.n_full_dp, n_full);
+}
+
+}  // namespace sbmap

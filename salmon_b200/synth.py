@@ -159,3 +159,55 @@ def synth_reads(txps, seed=7, n=10000, read_len=100, frag_mean=250.0, frag_sd=25
         left[i] = mutate(a); right[i] = mutate(b)
         t_tid[i] = t; t_pos[i] = pos; t_flen[i] = fl
     return left, right, dict(tid=t_tid, pos=t_pos, flen=t_flen)
+
+
+def flatten_txome(txps):
+    lens = np.array([t.shape[0] for t in txps], dtype=np.uint64)
+    off = np.concatenate(([0], np.cumsum(lens))).astype(np.uint64)
+    codes = np.ascontiguousarray(np.concatenate(txps).astype(np.uint8)) if len(txps) else np.zeros(0, np.uint8)
+    return off, codes
+
+
+def synth_reads_fast(txps, seed=7, n=1_000_000, read_len=100, frag_mean=250.0, frag_sd=25.0, sub_rate=0.005,
+                     indel_rate=0.0001, random_frac=0.03, expressed_frac=0.4, flat=None):
+    """Vectorised synth_reads (same model, different random stream): IU pairs, substitutions everywhere,
+    one indel in a fraction indel_rate*read_len of the mates.  Returns (left, right, truth)."""
+    rng = np.random.default_rng(seed)
+    off, codes = flat if flat is not None else flatten_txome(txps)
+    N = off.shape[0] - 1
+    lens = (off[1:] - off[:-1]).astype(np.int64)
+    expr = np.zeros(N)
+    ex = rng.choice(N, size=max(1, int(N * expressed_frac)), replace=False)
+    expr[ex] = rng.lognormal(0.0, 2.0, size=ex.shape[0])
+    w = expr * np.maximum(lens - frag_mean, 1.0)
+    cdf = np.cumsum(w)
+    t = np.minimum(np.searchsorted(cdf, rng.random(n) * cdf[-1], side="right"), N - 1)
+    L = lens[t]
+    fl = np.clip(np.rint(rng.normal(frag_mean, frag_sd, size=n)).astype(np.int64), read_len, np.minimum(1000, L))
+    pos = (rng.random(n) * (L - fl + 1)).astype(np.int64)
+    g0 = off[:-1].astype(np.int64)[t] + pos
+    ar = np.arange(read_len, dtype=np.int64)
+    a = codes[g0[:, None] + ar[None, :]]                                   # fragment start, forward
+    b = _COMP[codes[(g0 + fl - 1)[:, None] - ar[None, :]]]                 # fragment end, reverse-complemented
+    swap = rng.random(n) < 0.5
+    left = np.where(swap[:, None], b, a)
+    right = np.where(swap[:, None], a, b)
+    for r in (left, right):
+        m = rng.random(r.shape) < sub_rate
+        r[m] = (r[m] + rng.integers(1, 4, size=int(m.sum()), dtype=np.uint8)) % 4
+        if indel_rate > 0:
+            rows = np.nonzero(rng.random(n) < indel_rate * read_len)[0]
+            for i in rows:
+                p = int(rng.integers(5, read_len - 5))
+                x = r[i]
+                if rng.random() < 0.5:
+                    r[i] = np.concatenate([x[:p], x[p + 1:], rng.integers(0, 4, size=1, dtype=np.uint8)])
+                else:
+                    r[i] = np.concatenate([x[:p], rng.integers(0, 4, size=1, dtype=np.uint8), x[p:-1]])
+    rnd = rng.random(n) < random_frac
+    nr = int(rnd.sum())
+    left[rnd] = rng.integers(0, 4, size=(nr, read_len), dtype=np.uint8)
+    right[rnd] = rng.integers(0, 4, size=(nr, read_len), dtype=np.uint8)
+    t = np.where(rnd, -1, t)
+    return np.ascontiguousarray(left, dtype=np.uint8), np.ascontiguousarray(right, dtype=np.uint8), \
+        dict(tid=t, pos=pos, flen=fl)

@@ -20,6 +20,7 @@ extern "C" int hmc_map_reads(uint32_t n_txps, uint32_t k, const uint64_t* tx_off
   IndexView ix;
   ix.n_txps = n_txps; ix.k = k; ix.mask = table_capacity - 1; ix.tx_off = tx_off; ix.codes = codes;
   ix.table = (const TableEntry*)table; ix.post = (const Posting*)postings;
+  ix.packed = nullptr; ix.tx_has_n = nullptr;   // the serial forms read the byte codes
   const uint32_t nf = p->max_frag_len + 1;
   FldView fld;
   fld.max_val = p->max_frag_len; fld.pmf_live = fld4; fld.pmf_cached = fld4 + nf; fld.cmf_cached = fld4 + 2 * nf;

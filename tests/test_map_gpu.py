@@ -150,3 +150,53 @@ def test_map_then_em_end_to_end(oracle):
     np.testing.assert_allclose(alpha, ref, rtol=1e-9, atol=1e-9)
     assert abs(alpha.sum() - float(eq.counts.sum())) < 1e-6 * float(eq.counts.sum())
     em.close()
+
+
+def test_long_reads_chunks_and_variants(oracle):
+    """2x150 bp (the 4-word coverage / 8-word read paths), a batch cut into several pipeline chunks, and
+    every kernel variant: all bit-identical to the oracle."""
+    txps, _ = synth_txome(seed=21, n_genes=120)
+    left, right, _ = synth_reads(txps, seed=22, n=3000, read_len=150, frag_mean=320, frag_sd=30, indel_rate=0.003)
+    left[11, 5] = 4
+    p = map_default_params()
+    idx = Index(txps)
+    oix = oracle.MapIndex(txps)
+    ref = oracle.map_reads(oix, oracle.map_params(), left, right, 0)
+    ref_e = oracle.eq_aggregate(ref, p.max_read_occ, True)
+    for opts in (dict(), dict(chunk=700), dict(variant=0), dict(fast_dp=0)):
+        ctx = MapContext(idx, p, batch_cap=4096, max_read_len=150)
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        st = ctx.map_batch(left, right)
+        compare(ctx.last_alignments(), ref, p.max_read_occ)
+        for k in ("lookups", "postings", "seeds", "kept", "label_entries", "mapped"):
+            assert getattr(st, k) == ref["counters"][k], (opts, k)
+        if opts.get("variant", 1) == 1 and opts.get("fast_dp", 1) == 1:
+            assert st.full_dp < st.candidates          # the ungapped shortcut resolved some alignments
+        check_classes(ctx.finish(), ref_e, exact_weights=True)
+        ctx.close()
+
+
+def test_variants_agree_at_scale():
+    """no oracle (too slow at this size): warp kernels == serial-form kernels on 150k pairs, two batches."""
+    from salmon_b200.synth import synth_reads_fast
+    txps, _ = synth_txome(seed=31, n_genes=1500)
+    left, right, _ = synth_reads_fast(txps, seed=32, n=150_000, indel_rate=0.001)
+    p = map_default_params()
+    idx = Index(txps)
+    outs = []
+    for variant in (1, 0):
+        ctx = MapContext(idx, p, batch_cap=100_000, max_read_len=100)
+        ctx.set_option("variant", variant)
+        stats = [ctx.map_batch(left[:100_000], right[:100_000])]
+        a = ctx.last_alignments()
+        stats.append(ctx.map_batch(left[100_000:], right[100_000:]))
+        res = ctx.finish()
+        outs.append((a, canon(res), [(s.mapped, s.lookups, s.postings, s.seeds, s.candidates, s.kept) for s in stats]))
+        ctx.close()
+    compare(outs[0][0], outs[1][0], p.max_read_occ)
+    assert outs[0][2] == outs[1][2]
+    assert len(outs[0][1]) == len(outs[1][1])
+    for x, y in zip(outs[0][1], outs[1][1]):
+        assert x[0] == y[0] and x[3] == y[3]
+        assert np.array_equal(x[2].view(np.uint64), y[2].view(np.uint64))
