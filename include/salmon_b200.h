@@ -190,6 +190,9 @@ typedef struct sb_map_params {
   double fld_mean, fld_sd;    /* 250, 25 */
   uint64_t num_pre_burnin;    /* numPreBurninFrags 5000 */
   uint64_t num_burnin;        /* numBurninFrags 5000000 */
+  uint64_t seed;              /* stream of the stochastic FLD update (the reference seeds from random_device) */
+  uint32_t mini_batch;        /* reads per forgetting-mass timestep (miniBatchSize 5000) */
+  uint32_t reserved2;
 } sb_map_params;
 void sb_map_default_params(sb_map_params* p);
 
@@ -210,19 +213,32 @@ typedef struct sb_map_result {   /* host CSR owned by the context, valid until d
   const uint64_t* counts;
   const uint32_t* bins;       /* range-factorisation part of the label (NULL if range_bins == 0) */
   uint64_t n_mapped, lookups, postings, seeds, candidates, kept, label_entries;
+  /* what CollapsedEMOptimizer::optimize reads per transcript (inputs of sb_em_optimize): */
+  uint32_t n_txps;
+  uint32_t reserved;
+  const double* projected_counts;  /* normalizeAlphas (src/util/SalmonUtils.cpp:461-529): Transcript::projectedCounts */
+  const double* eff_len;           /* exp(cachedLogEffectiveLength) (CollapsedEMOptimizer.cpp:782-784) */
+  const uint64_t* unique_counts;   /* Transcript::uniqueCount() */
+  const uint64_t* total_counts;    /* Transcript::totalCount() */
 } sb_map_result;
 
 typedef struct sb_map_ctx sb_map_ctx;
 sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* p, int device, uint32_t max_pairs_per_batch,
                           uint32_t max_read_len);
 void sb_map_destroy(sb_map_ctx* ctx);
-/* One mini-batch: H2D, seed/chain, DP scoring, filtering + auxiliary probabilities + labels,
- * per-batch class aggregation.  Model state (fragment counter -> burn-in regime) is frozen for
- * the duration of the batch. */
+/* One batch: H2D, seed/chain, DP scoring, filtering + auxiliary probabilities + labels, online mass / FLD
+ * updates (processMiniBatch), per-batch class aggregation.  BATCHED SEMANTICS: the model state (transcript
+ * masses, fragment-length distribution, burn-in regime) is frozen for the duration of the batch and the batch's
+ * contributions are folded in afterwards (order-independent, bit-reproducible); forgetting-mass timesteps still
+ * advance every `mini_batch` reads.  Smaller batches track the reference's per-5000-read dynamics more closely. */
 int sb_map_batch(sb_map_ctx* ctx, const uint8_t* left, const uint8_t* right, uint32_t n_pairs,
                  uint32_t read_len, sb_map_batch_stats* stats);
 /* finish(): merge batch tables, normalise weights, return the CSR (feeds sb_em_optimize). */
 int sb_map_finish(sb_map_ctx* ctx, sb_map_result* out);
+/* Parity tap: the online state after the last batch.  mass_out[n_txps] (log scale, +inf = none),
+ * hist_out[max_frag_len+1] (log FLD histogram), log_eff_out[n_txps],
+ * scalars6 = {assigned fragments, fragments seen, timestep, burned in, FLD min, bits of the log total FLD mass}. */
+int sb_map_online_state(sb_map_ctx* ctx, double* mass_out, double* hist_out, double* log_eff_out, uint64_t* scalars6);
 /* Parity tap: the per-read alignments / labels of the last batch (arrays n*cap; label n*2*cap). */
 int sb_map_last_alignments(sb_map_ctx* ctx, uint32_t n, uint32_t* n_aln, uint32_t* tid, int32_t* score,
                            double* prob, int32_t* pos, int32_t* mate_pos, uint8_t* flags, int32_t* flen,

@@ -3,6 +3,7 @@
  * Straightforward, allocation-happy, sort-based statement of Stage A ("MAPSPEC" in DESIGN.md).
  */
 #include "map_oracle.h"
+#include "em_oracle.h"
 #include "../include/sb_detmath.h"
 
 #include <limits.h>
@@ -332,17 +333,20 @@ static int cmp_perm(const void* a, const void* b) {
   return x->tid < y->tid ? -1 : (x->tid > y->tid);
 }
 
-int orc_map_reads(const orc_index* ix, const orc_map_params* p, const uint8_t* left,
-                  const uint8_t* right, uint32_t n, uint32_t L, uint64_t frag_counter,
+struct orc_online;
+static void online_fragment(struct orc_online* on, uint32_t r, uint32_t L, uint32_t na, const uint32_t* tid,
+                            const int32_t* pos, const int32_t* mate_pos, const uint8_t* flags, const int32_t* flen,
+                            const double* aux);
+
+static int map_reads_core(const orc_index* ix, const orc_map_params* p, const fld_t* fldp, int useAux, int burnedIn,
+                          struct orc_online* on, const uint8_t* left,
+                  const uint8_t* right, uint32_t n, uint32_t L,
                   uint32_t* n_aln, uint32_t* aln_tid, int32_t* aln_score, double* aln_prob,
                   int32_t* aln_pos, int32_t* aln_mate_pos, uint8_t* aln_flags, int32_t* aln_flen,
                   uint32_t* label, double* weight, orc_map_counters* ctr) {
   const double LOG_EPSILON = log(EPSILON_);
   const uint32_t cap = p->max_read_occ;
-  const int useAux = frag_counter >= p->num_pre_burnin;       /* SalmonQuantify.cpp:496-497 */
-  const int burnedIn = frag_counter >= p->num_burnin;
-  fld_t fld;
-  fld_init(&fld, p->fld_mean, p->fld_sd, p->max_frag_len);
+  const fld_t fld = *fldp;   /* tables of the state the batch starts from (frozen for the batch) */
   orc_map_counters local;
   memset(&local, 0, sizeof(local));
   cand_t* lc = (cand_t*)malloc(MAXCAND * sizeof(cand_t));
@@ -489,11 +493,27 @@ int orc_map_reads(const orc_index* ix, const orc_map_params* p, const uint8_t* l
       for (uint32_t a = 0; a < na; ++a)
         label[(size_t)r * 2 * cap + na + a] = (uint32_t)(int32_t)(weight[base + a] * rangeCount);
     }
+    if (on) online_fragment(on, r, L, na, aln_tid + base, aln_pos + base, aln_mate_pos + base, aln_flags + base,
+                            aln_flen + base, aux);
   }
   if (ctr) *ctr = local;
   free(lc); free(rcand); free(jh); free(scores); free(perm); free(bs_tid); free(bs_score); free(bs_idx);
-  fld_free(&fld);
   return 0;
+}
+
+/* stateless form: the FLD is the prior, the regime is chosen by frag_counter (SalmonQuantify.cpp:496-497) */
+int orc_map_reads(const orc_index* ix, const orc_map_params* p, const uint8_t* left,
+                  const uint8_t* right, uint32_t n, uint32_t L, uint64_t frag_counter,
+                  uint32_t* n_aln, uint32_t* aln_tid, int32_t* aln_score, double* aln_prob,
+                  int32_t* aln_pos, int32_t* aln_mate_pos, uint8_t* aln_flags, int32_t* aln_flen,
+                  uint32_t* label, double* weight, orc_map_counters* ctr) {
+  fld_t fld;
+  fld_init(&fld, p->fld_mean, p->fld_sd, p->max_frag_len);
+  int rc = map_reads_core(ix, p, &fld, frag_counter >= p->num_pre_burnin, frag_counter >= p->num_burnin, NULL, left,
+                          right, n, L, n_aln, aln_tid, aln_score, aln_prob, aln_pos, aln_mate_pos, aln_flags, aln_flen,
+                          label, weight, ctr);
+  fld_free(&fld);
+  return rc;
 }
 
 /* ---------------------------------------------------------------- eq-class aggregation */
@@ -540,4 +560,291 @@ uint64_t orc_eq_aggregate(uint32_t n, uint32_t cap, int binned, const uint32_t* 
   out_off[nc] = woff;
   free(refs);
   return nc;
+}
+
+/* ================================================================ online phase (rows a7, a9)
+ * processMiniBatch's state updates (src/quant/SalmonQuantify.cpp:515, 599-623, 749-757, 783-790, 859-1018),
+ * ForgettingMassCalculator (include/salmon/internal/quant/ForgettingMassCalculator.hpp:24-92),
+ * FragmentLengthDistribution::addVal / pmf / dumpPMF / cacheCMF (src/model/FragmentLengthDistribution.cpp:84-186),
+ * ReadExperiment::updateTranscriptLengthsAtomic (include/salmon/internal/quant/ReadExperiment.inl:61-94),
+ * correctionFactorsFromMass / computeSmoothedEffectiveLengths (src/util/DistributionUtils.cpp:9-56),
+ * normalizeAlphas (src/util/SalmonUtils.cpp:461-529), TranscriptCluster::projectToPolytope
+ * (include/salmon/internal/quant/TranscriptCluster.hpp:46-101), ClusterForest (ClusterForest.hpp:29-139).
+ *
+ * BATCHED SEMANTICS: the reference mutates masses and the FLD fragment by fragment from many threads
+ * (order-dependent, not reproducible).  Here the state is frozen for the duration of one batch; a batch's
+ * contributions are accumulated as integers (multiples of 2^-40 of the batch's largest forgetting mass), hence
+ * order-independent and bit-reproducible, and folded into the state at the end of the batch.  Forgetting-mass
+ * timesteps advance every `mini_batch` reads as in the reference (miniBatchSize 5000).  The stochastic FLD update
+ * (r < exp(logProb), :974-983) draws r from Philox(fragment index, alignment index, 3; seed). */
+#define MASS_SCALE 1099511627776.0 /* 2^40 */
+
+struct orc_online {
+  const orc_index* ix;
+  orc_map_params p;
+  uint32_t M, nfld, mini_batch;
+  uint64_t seed;
+  double *mass, *prior, *log_eff;
+  fld_t fld;
+  uint64_t min_val;
+  uint64_t assigned, frags_seen, timestep;
+  int burned_in;
+  double* fm; uint64_t n_fm;
+  /* per batch */
+  uint64_t *mass_acc, *fld_acc;
+  uint64_t batch_min, batch_t0, batch_assigned;
+  double batch_ref;
+};
+
+static double fm_at(orc_online* on, uint64_t t) {   /* ForgettingMassCalculator.hpp:24-40 (forgettingFactor 0.65) */
+  const double ff = 0.65;
+  while (on->n_fm <= t) {
+    uint64_t j = on->n_fm;
+    on->fm = (double*)realloc(on->fm, (j + 1) * sizeof(double));
+    if (j == 0) on->fm[0] = 0.0;
+    else on->fm[j] = on->fm[j - 1] + ff * log((double)j) - log(pow((double)(j + 1), ff) - 1);
+    on->n_fm = j + 1;
+  }
+  return on->fm[t];
+}
+
+orc_online* orc_online_create(const orc_index* ix, const orc_map_params* p, uint64_t seed, uint32_t mini_batch) {
+  orc_online* on = (orc_online*)calloc(1, sizeof(orc_online));
+  on->ix = ix; on->p = *p; on->M = ix->n_txps; on->nfld = p->max_frag_len + 1; on->mini_batch = mini_batch ? mini_batch : 5000;
+  on->seed = seed;
+  on->mass = (double*)malloc((on->M ? on->M : 1) * sizeof(double));
+  on->prior = (double*)malloc((on->M ? on->M : 1) * sizeof(double));
+  on->log_eff = (double*)malloc((on->M ? on->M : 1) * sizeof(double));
+  for (uint32_t t = 0; t < on->M; ++t) {
+    const double len = (double)(ix->off[t + 1] - ix->off[t]);
+    on->mass[t] = LOG_0;
+    on->prior[t] = sbm_det_log(0.005 * len);           /* Transcript(id, name, len, alpha = 0.005): priorMass_ = log(alpha*len) */
+    on->log_eff[t] = sbm_det_log(len);
+  }
+  fld_init(&on->fld, p->fld_mean, p->fld_sd, p->max_frag_len);
+  on->min_val = p->max_frag_len;
+  on->mass_acc = (uint64_t*)calloc(on->M ? on->M : 1, sizeof(uint64_t));
+  on->fld_acc = (uint64_t*)calloc(on->nfld, sizeof(uint64_t));
+  return on;
+}
+void orc_online_free(orc_online* on) {
+  if (!on) return;
+  free(on->mass); free(on->prior); free(on->log_eff); free(on->fm); free(on->mass_acc); free(on->fld_acc);
+  fld_free(&on->fld); free(on);
+}
+
+static int64_t quant40(double x) { return llrint(x * MASS_SCALE); }
+
+static void online_fragment(orc_online* on, uint32_t r, uint32_t L, uint32_t na, const uint32_t* tid,
+                            const int32_t* pos, const int32_t* mate_pos, const uint8_t* flags, const int32_t* flen_raw,
+                            const double* aux) {
+  const double LOG_EPSILON = log(EPSILON_);
+  const orc_index* ix = on->ix;
+  const uint64_t t = on->batch_t0 + r / on->mini_batch;
+  const double fmv = fm_at(on, t), ref = on->batch_ref;
+  double lp[256];
+  int32_t fped[256];
+  double S = LOG_0;
+  for (uint32_t a = 0; a < na; ++a) {
+    const uint32_t ti = tid[a];
+    const int32_t refLen = (int32_t)(ix->off[ti + 1] - ix->off[ti]);
+    const double refLength = refLen > 0 ? (double)refLen : 1.0;
+    const uint32_t status = (flags[a] >> 2) & 3;
+    const int fwd = flags[a] & 1, mateFwd = (flags[a] >> 1) & 1;
+    int32_t flen = flen_raw[a];
+    fped[a] = 0;
+    if (status == 0 && fwd != mateFwd) {
+      int32_t p1 = fwd ? pos[a] : mate_pos[a]; p1 = p1 < 0 ? 0 : p1; p1 = p1 > refLen ? refLen : p1;
+      int32_t p2 = fwd ? mate_pos[a] + (int32_t)L : pos[a] + (int32_t)L; p2 = p2 < 0 ? 0 : p2; p2 = p2 > refLen ? refLen : p2;
+      flen = (p1 > p2) ? p1 - p2 : p2 - p1;
+      fped[a] = flen;
+    }
+    const double logRefLength = on->burned_in ? on->log_eff[ti] : sbm_det_log((double)refLen);      /* :617-623 */
+    double startPosProb = -logRefLength;                                                           /* :749-757 */
+    if (status == 0) startPosProb = ((double)flen <= refLength) ? -sbm_det_log(refLength - (double)flen + 1) : LOG_EPSILON;
+    const double transcriptLogCount = logAddDet(on->prior[ti], on->mass[ti]);                       /* mass(initialRound) */
+    lp[a] = transcriptLogCount + aux[a] + startPosProb;                                            /* :785 */
+    S = logAddDet(S, lp[a]);                                                                        /* :792 */
+  }
+  const uint64_t g = on->frags_seen + r;
+  for (uint32_t a = 0; a < na; ++a) {
+    const double nlp = lp[a] - S;                                                                   /* :865 */
+    on->mass_acc[tid[a]] += (uint64_t)quant40(sbm_det_exp(fmv - ref + nlp));                        /* :871-872 */
+    if (!on->burned_in) {                                                                           /* :974-983 */
+      uint32_t rnd[4];
+      orc_philox4x32((uint32_t)g, (uint32_t)(g >> 32), a, 3u, (uint32_t)on->seed, (uint32_t)(on->seed >> 32), rnd);
+      const double u = (double)rnd[0] * (1.0 / 4294967296.0);
+      if (u < sbm_det_exp(nlp) && fped[a] > 0) {
+        /* FragmentLengthDistribution::addVal(len, logForgettingMass), :84-106; kernel = binomial(4, 0.5) */
+        static const double kern_lin[5] = {1.0 / 16, 4.0 / 16, 6.0 / 16, 4.0 / 16, 1.0 / 16};
+        uint64_t len = (uint64_t)fped[a];
+        if (len > on->p.max_frag_len) len = on->p.max_frag_len;
+        if (len < on->batch_min) on->batch_min = len;
+        int64_t off = (int64_t)len - 2;
+        for (int i = 0; i < 5; ++i, ++off)
+          if (off > 0 && off < (int64_t)on->nfld)
+            on->fld_acc[off] += (uint64_t)quant40(sbm_det_exp(fmv - ref + sbm_det_log(kern_lin[i])));
+      }
+    }
+  }
+  on->batch_assigned++;
+}
+
+/* cached effective lengths from the current FLD */
+static void online_eff_lengths(orc_online* on) {
+  const uint32_t n = on->nfld;
+  const uint64_t maxV = n - 1;
+  const uint64_t minV = (on->min_val == n - 1) ? 1 : on->min_val;
+  double* logPMF = (double*)malloc(n * sizeof(double));
+  double sum = LOG_0;
+  for (uint64_t i = minV; i <= maxV; ++i) { logPMF[i - minV] = on->fld.hist[i] - on->fld.tot; sum = logAddDet(sum, logPMF[i - minV]); }
+  double* pmf = (double*)calloc(maxV + 1, sizeof(double));
+  for (uint64_t i = minV; i < maxV; ++i) pmf[i] = 100.0 * sbm_det_exp(logPMF[i - minV] - sum);
+  const uint64_t maxLen = maxV + 1;
+  double* cf = (double*)calloc(maxLen, sizeof(double));
+  double vals = 0.0, mult = pmf[0];
+  for (uint64_t i = 1; i < maxLen; ++i) {
+    vals = pmf[i] * (double)i + vals;
+    mult = pmf[i] + mult;
+    if (mult > 0) cf[i] = vals / mult;
+  }
+  for (uint32_t t = 0; t < on->M; ++t) {
+    const double origLen = (double)(on->ix->off[t + 1] - on->ix->off[t]);
+    const double c = (origLen >= (double)maxLen) ? cf[maxLen - 1] : cf[(uint64_t)origLen];
+    double effLen = origLen - c;
+    if (effLen < 1.0) effLen = origLen;
+    on->log_eff[t] = sbm_det_log(effLen);
+  }
+  free(logPMF); free(pmf); free(cf);
+}
+
+int orc_online_batch(orc_online* on, const uint8_t* left, const uint8_t* right, uint32_t n, uint32_t L,
+                     uint32_t* n_aln, uint32_t* aln_tid, int32_t* aln_score, double* aln_prob, int32_t* aln_pos,
+                     int32_t* aln_mate_pos, uint8_t* aln_flags, int32_t* aln_flen, uint32_t* label, double* weight,
+                     orc_map_counters* ctr) {
+  const uint32_t nfld = on->nfld;
+  const uint64_t nsteps = (n + on->mini_batch - 1) / on->mini_batch;
+  on->batch_t0 = on->timestep;
+  on->batch_ref = fm_at(on, on->timestep + (nsteps ? nsteps - 1 : 0));
+  on->batch_min = on->p.max_frag_len;
+  on->batch_assigned = 0;
+  const int useAux = on->assigned >= on->p.num_pre_burnin;
+  int rc = map_reads_core(on->ix, &on->p, &on->fld, useAux, on->burned_in, on, left, right, n, L, n_aln, aln_tid,
+                          aln_score, aln_prob, aln_pos, aln_mate_pos, aln_flags, aln_flen, label, weight, ctr);
+  /* fold the batch into the state */
+  for (uint32_t t = 0; t < on->M; ++t)
+    if (on->mass_acc[t]) {
+      on->mass[t] = logAddDet(on->mass[t], on->batch_ref + sbm_det_log((double)on->mass_acc[t] * (1.0 / MASS_SCALE)));
+      on->mass_acc[t] = 0;
+    }
+  uint64_t tot_acc = 0;
+  for (uint32_t j = 0; j < nfld; ++j)
+    if (on->fld_acc[j]) {
+      on->fld.hist[j] = logAddDet(on->fld.hist[j], on->batch_ref + sbm_det_log((double)on->fld_acc[j] * (1.0 / MASS_SCALE)));
+      tot_acc += on->fld_acc[j];
+      on->fld_acc[j] = 0;
+    }
+  if (tot_acc) {
+    on->fld.tot = logAddDet(on->fld.tot, on->batch_ref + sbm_det_log((double)tot_acc * (1.0 / MASS_SCALE)));
+    if (on->batch_min < on->min_val) on->min_val = on->batch_min;
+    for (uint32_t j = 0; j < nfld; ++j) on->fld.pmf_live[j] = on->fld.hist[j] - on->fld.tot;
+  }
+  on->assigned += on->batch_assigned;
+  on->frags_seen += n;
+  on->timestep += nsteps;
+  if (!on->burned_in && on->assigned >= on->p.num_burnin) {            /* SalmonQuantify.cpp:1013-1018 */
+    online_eff_lengths(on);
+    double tm = LOG_0, cum = LOG_0;                                    /* cacheCMF: getLockedPMF + cmf(pmf) */
+    for (uint32_t j = 0; j < nfld; ++j) tm = logAddDet(tm, on->fld.hist[j] - on->fld.tot);
+    for (uint32_t j = 0; j < nfld; ++j) {
+      on->fld.pmf_cached[j] = (on->fld.hist[j] - on->fld.tot) - tm;
+      cum = logAddDet(cum, on->fld.pmf_cached[j]);
+      on->fld.cmf_cached[j] = cum;
+    }
+    on->burned_in = 1;
+  }
+  return rc;
+}
+
+/* scalars[6] = {assigned, frags_seen, timestep, burned_in, min_val, log totMass (as bits of a double)} */
+void orc_online_state(const orc_online* on, double* mass_out, double* hist_out, double* log_eff_out, uint64_t* scalars) {
+  if (mass_out) memcpy(mass_out, on->mass, on->M * sizeof(double));
+  if (hist_out) memcpy(hist_out, on->fld.hist, on->nfld * sizeof(double));
+  if (log_eff_out) memcpy(log_eff_out, on->log_eff, on->M * sizeof(double));
+  if (scalars) {
+    scalars[0] = on->assigned; scalars[1] = on->frags_seen; scalars[2] = on->timestep; scalars[3] = (uint64_t)on->burned_in;
+    scalars[4] = on->min_val; scalars[5] = sbm_d2u(on->fld.tot);
+  }
+}
+
+/* normalizeAlphas over the finished classes (transcript parts of the labels): per-transcript unique / total counts,
+ * clusters = connected components of the class <-> transcript graph (ClusterForest::mergeClusters per fragment
+ * gives the same partition), cluster hit counts, projection.  Members are visited in ascending transcript id. */
+static uint32_t uf_find(uint32_t* parent, uint32_t x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; }
+
+int orc_online_finish(orc_online* on, uint64_t n_classes, const uint64_t* off, const uint32_t* tids,
+                      const uint64_t* counts, double* projected, double* eff_len, uint64_t* unique, uint64_t* total) {
+  const uint32_t M = on->M;
+  if (!on->burned_in && on->assigned < on->p.num_burnin) online_eff_lengths(on);   /* SalmonQuantify.cpp:2734-2738 */
+  uint32_t* parent = (uint32_t*)malloc((M ? M : 1) * sizeof(uint32_t));
+  double* hits = (double*)calloc(M ? M : 1, sizeof(double));
+  for (uint32_t t = 0; t < M; ++t) { parent[t] = t; unique[t] = 0; total[t] = 0; projected[t] = 0.0; }
+  for (uint64_t c = 0; c < n_classes; ++c) {
+    const uint64_t b = off[c], e = off[c + 1];
+    if (e == b) continue;
+    hits[tids[b]] += (double)counts[c];                      /* updateCluster(first transcript, 1.0, ...) per fragment */
+    if (e - b == 1) unique[tids[b]] += counts[c];            /* transcriptUnique, :987-990 */
+    for (uint64_t j = b; j < e; ++j) {
+      total[tids[j]] += counts[c];                           /* addTotalCount, :795-797 */
+      uint32_t ra = uf_find(parent, tids[b]), rb = uf_find(parent, tids[j]);
+      if (ra != rb) { if (ra < rb) parent[rb] = ra; else parent[ra] = rb; }
+    }
+  }
+  /* members by cluster, ascending id: counting sort on the root */
+  uint32_t* root = (uint32_t*)malloc((M ? M : 1) * sizeof(uint32_t));
+  uint32_t* start = (uint32_t*)calloc((size_t)M + 1, sizeof(uint32_t));
+  uint32_t* memb = (uint32_t*)malloc((M ? M : 1) * sizeof(uint32_t));
+  for (uint32_t t = 0; t < M; ++t) { root[t] = uf_find(parent, t); start[root[t] + 1]++; }
+  for (uint32_t t = 0; t < M; ++t) start[t + 1] += start[t];
+  uint32_t* fill = (uint32_t*)malloc((M ? M : 1) * sizeof(uint32_t));
+  memcpy(fill, start, (M ? M : 1) * sizeof(uint32_t));
+  for (uint32_t t = 0; t < M; ++t) memb[fill[root[t]]++] = t;
+  uint8_t* bound = (uint8_t*)malloc(M ? M : 1);
+  for (uint32_t r = 0; r < M; ++r) {
+    const uint32_t b = start[r], e = start[r + 1];
+    if (e == b) continue;
+    double clusterHits = 0.0, logClusterMass = LOG_0;
+    for (uint32_t q = b; q < e; ++q) { clusterHits += hits[memb[q]]; logClusterMass = logAddDet(logClusterMass, on->mass[memb[q]]); }
+    const double logClusterCount = sbm_det_log(clusterHits);
+    int requiresProjection = 0;
+    for (uint32_t q = b; q < e; ++q) {
+      const uint32_t t = memb[q];
+      if (on->mass[t] == LOG_0) projected[t] = 0.0;
+      else {
+        projected[t] = sbm_det_exp((on->mass[t] - logClusterMass) + logClusterCount);
+        requiresProjection |= projected[t] > (double)total[t] || projected[t] < (double)unique[t];
+      }
+    }
+    if (e - b > 1 && requiresProjection) {                   /* TranscriptCluster::projectToPolytope */
+      const uint32_t cs = e - b;
+      memset(bound, 0, cs);
+      for (uint32_t round = 0;; ) {
+        double unboundCounts = 0.0, boundCounts = 0.0;
+        for (uint32_t i = 0; i < cs; ++i) {
+          const uint32_t t = memb[b + i];
+          if (projected[t] > (double)total[t]) { projected[t] = (double)total[t]; bound[i] = 1; }
+          else if (projected[t] < (double)unique[t]) { projected[t] = (double)unique[t]; bound[i] = 1; }
+          if (bound[i]) boundCounts += projected[t]; else unboundCounts += projected[t];
+        }
+        if (fabs(unboundCounts + boundCounts - clusterHits) <= EPSILON_) break;
+        if (unboundCounts == 0) { memset(bound, 0, cs); unboundCounts = boundCounts; boundCounts = 0; }
+        const double normalizer = (clusterHits - boundCounts) / unboundCounts;
+        for (uint32_t i = 0; i < cs; ++i) if (!bound[i]) projected[memb[b + i]] *= normalizer;
+        if (++round > 5000) break;
+      }
+    }
+  }
+  for (uint32_t t = 0; t < M; ++t) eff_len[t] = sbm_det_exp(on->log_eff[t]);   /* CollapsedEMOptimizer.cpp:782-784 */
+  free(parent); free(hits); free(root); free(start); free(memb); free(fill); free(bound);
+  return 0;
 }

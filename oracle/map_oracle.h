@@ -90,6 +90,22 @@ uint64_t orc_eq_aggregate(uint32_t n, uint32_t cap, int binned, const uint32_t* 
 /* FLD tables (log pmf, log cmf over 0..max_val) as the prior N(mean, sd) gives them. */
 void orc_fld_tables(double mean, double sd, uint32_t max_val, double* log_pmf, double* log_cmf);
 
+/* ---- online phase with batched semantics (see map_oracle.c): masses, FLD, burn-in, normalizeAlphas ---- */
+typedef struct orc_online orc_online;
+orc_online* orc_online_create(const orc_index* idx, const orc_map_params* p, uint64_t seed, uint32_t mini_batch);
+void orc_online_free(orc_online*);
+/* like orc_map_reads, from the state's FLD / regime; then folds the batch into the state */
+int orc_online_batch(orc_online* on, const uint8_t* left, const uint8_t* right, uint32_t n, uint32_t read_len,
+                     uint32_t* n_aln, uint32_t* aln_tid, int32_t* aln_score, double* aln_prob, int32_t* aln_pos,
+                     int32_t* aln_mate_pos, uint8_t* aln_flags, int32_t* aln_flen, uint32_t* label, double* weight,
+                     orc_map_counters* ctr);
+/* mass_out[M] (log, +inf = none), hist_out[max_frag_len+1] (log), log_eff_out[M],
+ * scalars[6] = {assigned, frags_seen, timestep, burned_in, min_val, bits of log totMass} */
+void orc_online_state(const orc_online* on, double* mass_out, double* hist_out, double* log_eff_out, uint64_t* scalars);
+/* normalizeAlphas over the finished classes (transcript part of the labels) */
+int orc_online_finish(orc_online* on, uint64_t n_classes, const uint64_t* off, const uint32_t* tids,
+                      const uint64_t* counts, double* projected, double* eff_len, uint64_t* unique, uint64_t* total);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,7 @@ class sb_map_params(C.Structure):
         ("consensus_frac", C.c_double), ("min_score_fraction", C.c_double), ("score_exp", C.c_double),
         ("min_aln_prob", C.c_double), ("decoy_threshold", C.c_double), ("fld_mean", C.c_double), ("fld_sd", C.c_double),
         ("num_pre_burnin", C.c_uint64), ("num_burnin", C.c_uint64),
+        ("seed", C.c_uint64), ("mini_batch", C.c_uint32), ("reserved2", C.c_uint32),
     ]
 
 
@@ -95,7 +96,10 @@ class sb_map_batch_stats(C.Structure):
 class sb_map_result(C.Structure):
     _fields_ = [("n_classes", C.c_uint64), ("off", C.POINTER(C.c_uint64)), ("tids", C.POINTER(C.c_uint32)),
                 ("weights", C.POINTER(C.c_double)), ("counts", C.POINTER(C.c_uint64)), ("bins", C.POINTER(C.c_uint32))] + \
-        [(k, C.c_uint64) for k in ("n_mapped", "lookups", "postings", "seeds", "candidates", "kept", "label_entries")]
+        [(k, C.c_uint64) for k in ("n_mapped", "lookups", "postings", "seeds", "candidates", "kept", "label_entries")] + \
+        [("n_txps", C.c_uint32), ("reserved", C.c_uint32), ("projected_counts", C.POINTER(C.c_double)),
+         ("eff_len", C.POINTER(C.c_double)), ("unique_counts", C.POINTER(C.c_uint64)),
+         ("total_counts", C.POINTER(C.c_uint64))]
 
 
 # every symbol include/salmon_b200.h declares: (name, restype, argtypes)
@@ -134,6 +138,7 @@ SYMBOLS = {
     "sb_map_batch": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, C.POINTER(sb_map_batch_stats)]),
     "sb_map_finish": (C.c_int, [_P, C.POINTER(sb_map_result)]),
     "sb_map_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "sb_map_online_state": (C.c_int, [_P, _P, _P, _P, _P]),
     "sb_map_last_alignments": (C.c_int, [_P, C.c_uint32] + [_P] * 10),
     "sb_host_register": (C.c_int, [_P, C.c_size_t]),
     "sb_host_unregister": (C.c_int, [_P]),
@@ -448,7 +453,19 @@ class MapContext:
                    bins=(np.ctypeslib.as_array(r.bins, shape=(nn,)).copy() if (nn and r.bins) else None),
                    counters={k: int(getattr(r, k)) for k in ("n_mapped", "lookups", "postings", "seeds", "candidates",
                                                              "kept", "label_entries")})
+        M = int(r.n_txps)
+        for k, dt in (("projected_counts", np.float64), ("eff_len", np.float64), ("unique_counts", np.uint64),
+                      ("total_counts", np.uint64)):
+            out[k] = np.ctypeslib.as_array(getattr(r, k), shape=(M,)).copy() if M else np.zeros(0, dt)
         return out
+
+    def online_state(self):
+        M, nf = self.index.n_txps, self.p.max_frag_len + 1
+        mass = np.zeros(M); hist = np.zeros(nf); le = np.zeros(M); sc = np.zeros(6, dtype=np.uint64)
+        _check(self.lib.sb_map_online_state(self.h, mass.ctypes.data, hist.ctypes.data, le.ctypes.data, sc.ctypes.data),
+               "sb_map_online_state")
+        return dict(mass=mass, hist=hist, log_eff=le, assigned=int(sc[0]), frags_seen=int(sc[1]), timestep=int(sc[2]),
+                    burned_in=int(sc[3]), min_val=int(sc[4]), tot=sc[5:6].view(np.float64)[0])
 
     def close(self):
         if self.h:

@@ -194,6 +194,7 @@ struct BatchBufs {
   // scratch for assign
   int32_t* sc; int32_t* perm_idx; int32_t* perm_tid; int32_t* bs_tid; int32_t* bs_score; int32_t* bs_idx;
   Joint* jh;
+  double* lp;                        // per-thread scratch: alignment log-probabilities
   Counters* ctr;
 };
 
@@ -307,7 +308,7 @@ __global__ void k_dp_score(IndexView ix, Params p, const uint8_t* __restrict__ l
 
 // K3: one thread per read pair -- salmon's alignment filtering, auxiliary probabilities, label
 __global__ void k_assign(IndexView ix, Params p, FldView fld, int useAux, int burnedIn, uint32_t n, uint32_t L,
-                         BatchBufs b) {
+                         BatchBufs b, OnlineView on, uint32_t chunk_first_read) {
   const uint32_t T = gridDim.x * blockDim.x;
   const uint32_t tid0 = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t cap = p.max_read_occ;
@@ -325,9 +326,223 @@ __global__ void k_assign(IndexView ix, Params p, FldView fld, int useAux, int bu
     assign_read(ix, p, fld, useAux != 0, burnedIn != 0, b.cand_l + (size_t)r * MAXCAND, nlr,
                 b.cand_r + (size_t)r * MAXCAND, b.n_r[r], b.score_l + (size_t)r * MAXCAND,
                 b.score_r + (size_t)r * MAXCAND, L, b.sc + so, b.perm_idx + so, b.perm_tid + so, b.bs_tid + so,
-                b.bs_score + so, b.bs_idx + so, b.jh + so, o, ctr);
+                b.bs_score + so, b.bs_idx + so, b.jh + so, o, ctr, &on, chunk_first_read + r, b.lp + so);
   }
   add_counters(b.ctr, ctr);
+}
+
+// ---- online state: initialisation, end-of-batch fold, burn-in, effective lengths ---------------------------
+struct OnlineState {
+  double *mass = nullptr, *prior = nullptr, *log_eff = nullptr;   // [M]
+  double *hist = nullptr;             // [nf] log histogram of the FLD
+  double *tot = nullptr;              // [1] log total mass
+  double *cf = nullptr;               // [nf] correction factors (effective lengths)
+  unsigned long long *mass_acc = nullptr, *fld_acc = nullptr;
+  unsigned int *mins = nullptr;       // [0] this batch's smallest FLD length, [1] FragmentLengthDistribution::min_
+  double *fm_rel = nullptr; unsigned long long *tap_q = nullptr;   // per-batch tables
+  uint32_t table_cap = 0;
+};
+
+__global__ void k_online_init(uint32_t M, const uint64_t* __restrict__ tx_off, double* mass, double* prior, double* log_eff) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M) return;
+  const double len = (double)(tx_off[t + 1] - tx_off[t]);
+  mass[t] = log0();
+  prior[t] = sbm_det_log(0.005 * len);      // Transcript(id, name, len, alpha = 0.005), Transcript.hpp:51
+  log_eff[t] = sbm_det_log(len);
+}
+__global__ void k_online_fold_mass(uint32_t M, double ref, double* __restrict__ mass, unsigned long long* __restrict__ acc) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M) return;
+  const unsigned long long a = acc[t];
+  if (!a) return;
+  mass[t] = log_add(mass[t], ref + sbm_det_log((double)a * (1.0 / MASS_SCALE)));
+  acc[t] = 0;
+}
+// one block: FLD histogram, total mass, min, live pmf table
+__global__ void k_online_fold_fld(uint32_t nf, double ref, OnlineState S, double* __restrict__ pmf_live) {
+  __shared__ unsigned long long s_tot[32];
+  unsigned long long mine = 0;
+  for (uint32_t j = threadIdx.x; j < nf; j += blockDim.x) {
+    const unsigned long long a = S.fld_acc[j];
+    if (a) {
+      S.hist[j] = log_add(S.hist[j], ref + sbm_det_log((double)a * (1.0 / MASS_SCALE)));
+      mine += a;
+      S.fld_acc[j] = 0;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0) s_tot[threadIdx.x >> 5] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tot_acc = 0;
+    for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) tot_acc += s_tot[w];
+    if (tot_acc) {
+      *S.tot = log_add(*S.tot, ref + sbm_det_log((double)tot_acc * (1.0 / MASS_SCALE)));
+      if (S.mins[0] < S.mins[1]) S.mins[1] = S.mins[0];
+    }
+  }
+  __syncthreads();
+  const double tot = *S.tot;
+  for (uint32_t j = threadIdx.x; j < nf; j += blockDim.x) pmf_live[j] = S.hist[j] - tot;
+}
+// ReadExperiment::updateTranscriptLengthsAtomic (ReadExperiment.inl:61-94) + correctionFactorsFromMass
+// (DistributionUtils.cpp:9-31): one thread, nf sequential steps.  With cache != 0 also FragmentLengthDistribution::
+// cacheCMF (getLockedPMF + cmf(pmf), FragmentLengthDistribution.cpp:159-201) into pmf_cached / cmf_cached.
+__global__ void k_online_correction(uint32_t nf, OnlineState S, int cache, double* __restrict__ scratch /* nf */,
+                                    double* __restrict__ pmf_cached, double* __restrict__ cmf_cached) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const uint32_t maxV = nf - 1;
+  const uint32_t minV = (S.mins[1] == nf - 1) ? 1u : S.mins[1];
+  const double tot = *S.tot;
+  double sum = log0();
+  for (uint32_t i = minV; i <= maxV; ++i) sum = log_add(sum, S.hist[i] - tot);
+  for (uint32_t i = 0; i < nf; ++i) scratch[i] = 0.0;
+  for (uint32_t i = minV; i < maxV; ++i) scratch[i] = 100.0 * sbm_det_exp((S.hist[i] - tot) - sum);
+  double vals = 0.0, mult = scratch[0];
+  S.cf[0] = 0.0;
+  for (uint32_t i = 1; i < nf; ++i) {
+    const double v = scratch[i];
+    vals = v * (double)i + vals;
+    mult = v + mult;
+    S.cf[i] = (mult > 0) ? vals / mult : 0.0;
+  }
+  if (cache) {
+    double tm = log0(), cum = log0();
+    for (uint32_t j = 0; j < nf; ++j) tm = log_add(tm, S.hist[j] - tot);
+    for (uint32_t j = 0; j < nf; ++j) {
+      pmf_cached[j] = (S.hist[j] - tot) - tm;
+      cum = log_add(cum, pmf_cached[j]);
+      cmf_cached[j] = cum;
+    }
+  }
+}
+// computeSmoothedEffectiveLengths (DistributionUtils.cpp:33-56)
+__global__ void k_online_eff_len(uint32_t M, uint32_t nf, const uint64_t* __restrict__ tx_off, const double* __restrict__ cf,
+                                 double* __restrict__ log_eff) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M) return;
+  const double origLen = (double)(tx_off[t + 1] - tx_off[t]);
+  const double c = (origLen >= (double)nf) ? cf[nf - 1] : cf[(uint32_t)origLen];
+  double effLen = origLen - c;
+  if (effLen < 1.0) effLen = origLen;
+  log_eff[t] = sbm_det_log(effLen);
+}
+
+// ---- normalizeAlphas (src/util/SalmonUtils.cpp:461-529) over the finished classes -------------------------
+__device__ __forceinline__ uint32_t uf_find(const uint32_t* parent, uint32_t x) {
+  for (;;) { const uint32_t q = ((const volatile uint32_t*)parent)[x]; if (q == x) return x; x = q; }
+}
+// per class: unique / total counts, cluster hits (at the first transcript), unions (ClusterForest::mergeClusters)
+__global__ void k_cls_accumulate(uint64_t n_classes, const uint64_t* __restrict__ loff, const uint64_t* __restrict__ woff,
+                                 const uint32_t* __restrict__ labels, const uint64_t* __restrict__ counts,
+                                 unsigned long long* uniq, unsigned long long* total, unsigned long long* hits,
+                                 uint32_t* parent) {
+  uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_classes) return;
+  const uint32_t ntx = (uint32_t)(woff[c + 1] - woff[c]);
+  if (ntx == 0) return;
+  const uint32_t* t = labels + loff[c];
+  const unsigned long long cnt = counts[c];
+  atomicAdd(hits + t[0], cnt);
+  if (ntx == 1) atomicAdd(uniq + t[0], cnt);
+  for (uint32_t j = 0; j < ntx; ++j) {
+    atomicAdd(total + t[j], cnt);
+    uint32_t a = t[0], b = t[j];
+    for (;;) {   // hook the larger root under the smaller: the root of a cluster is its smallest member
+      a = uf_find(parent, a); b = uf_find(parent, b);
+      if (a == b) break;
+      if (a < b) { const uint32_t x = a; a = b; b = x; }
+      if (atomicCAS(parent + a, a, b) == a) break;
+    }
+  }
+}
+__global__ void k_iota(uint32_t n, uint32_t* a) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }
+__global__ void k_roots(uint32_t M, const uint32_t* __restrict__ parent, uint32_t* __restrict__ root, uint32_t* __restrict__ ids) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M) return;
+  root[t] = uf_find(parent, t); ids[t] = t;
+}
+__global__ void k_cluster_heads(uint32_t M, const uint32_t* __restrict__ root_sorted, uint32_t* __restrict__ head) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > M) return;
+  head[i] = (i < M && (i == 0 || root_sorted[i] != root_sorted[i - 1])) ? 1u : 0u;
+}
+__global__ void k_cluster_starts(uint32_t M, const uint32_t* __restrict__ head, const uint32_t* __restrict__ head_scan,
+                                 uint32_t* __restrict__ start) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M && head[i]) start[head_scan[i]] = i;
+}
+// one warp per cluster (members ascending by transcript id): projected counts + TranscriptCluster::projectToPolytope
+__global__ void k_cluster_project(uint32_t n_clusters, uint32_t M, const uint32_t* __restrict__ start,
+                                  const uint32_t* __restrict__ memb, const double* __restrict__ mass,
+                                  const unsigned long long* __restrict__ hits, const unsigned long long* __restrict__ uniq,
+                                  const unsigned long long* __restrict__ total, double* __restrict__ projected,
+                                  uint8_t* __restrict__ bound) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= n_clusters) return;
+  const uint32_t b = start[c], e = (c + 1 < n_clusters) ? start[c + 1] : M;
+  const uint32_t cs = e - b;
+  unsigned long long h = 0;
+  double mx = -log0();
+  for (uint32_t q = b + lane; q < e; q += 32) {
+    const uint32_t t = memb[q];
+    h += hits[t];
+    const double m = mass[t];
+    if (m != log0() && m > mx) mx = m;
+  }
+  for (int o = 16; o > 0; o >>= 1) { h += __shfl_xor_sync(0xffffffffu, h, o); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  if (mx == -log0()) {   // no mass anywhere in the cluster: projectedCounts = 0 (SalmonUtils.cpp:497-498)
+    for (uint32_t q = b + lane; q < e; q += 32) projected[memb[q]] = 0.0;
+    return;
+  }
+  double se = 0.0;
+  for (uint32_t q = b + lane; q < e; q += 32) { const double m = mass[memb[q]]; if (m != log0()) se += sbm_det_exp(m - mx); }
+  se = sb::warp_sum(se);
+  const double logClusterMass = mx + sbm_det_log(se);
+  const double clusterHits = (double)h;
+  const double logClusterCount = sbm_det_log(clusterHits);
+  int req = 0;
+  for (uint32_t q = b + lane; q < e; q += 32) {
+    const uint32_t t = memb[q];
+    const double m = mass[t];
+    double pc = 0.0;
+    if (m != log0()) {
+      pc = sbm_det_exp((m - logClusterMass) + logClusterCount);
+      req |= (pc > (double)total[t]) || (pc < (double)uniq[t]);
+    }
+    projected[t] = pc;
+    bound[q] = 0;
+  }
+  req = __any_sync(0xffffffffu, req);
+  if (cs <= 1 || !req) return;
+  __syncwarp();
+  for (uint32_t round = 0;;) {
+    double ub = 0.0, bd = 0.0;
+    for (uint32_t q = b + lane; q < e; q += 32) {
+      const uint32_t t = memb[q];
+      double pc = projected[t];
+      if (pc > (double)total[t]) { pc = (double)total[t]; bound[q] = 1; projected[t] = pc; }
+      else if (pc < (double)uniq[t]) { pc = (double)uniq[t]; bound[q] = 1; projected[t] = pc; }
+      if (bound[q]) bd += pc; else ub += pc;
+    }
+    ub = sb::warp_sum(ub); bd = sb::warp_sum(bd);
+    if (fabs(ub + bd - clusterHits) <= 0.375e-10) break;     // approxEqual, SalmonMath.hpp:51-53
+    if (ub == 0) {
+      for (uint32_t q = b + lane; q < e; q += 32) bound[q] = 0;
+      ub = bd; bd = 0;
+    }
+    const double normalizer = (clusterHits - bd) / ub;
+    __syncwarp();
+    for (uint32_t q = b + lane; q < e; q += 32) if (!bound[q]) projected[memb[q]] *= normalizer;
+    __syncwarp();
+    if (++round > 5000) break;
+  }
+}
+__global__ void k_exp_vec(uint32_t n, const double* __restrict__ in, double* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = sbm_det_exp(in[i]);
 }
 
 // ---- equivalence-class builder: records (label, weights, count) -> classes ----------------
@@ -487,6 +702,17 @@ struct sb_map_ctx {
   double* d_fld = nullptr;
   FldView fld{};
   AggScratch agg;
+  // online state (masses, FLD, effective lengths)
+  OnlineState on;
+  uint32_t M = 0, nf = 0;
+  uint64_t frags_seen = 0, timestep = 0;
+  int burned_in = 0;
+  std::vector<double> fm;                 // log forgetting masses by timestep
+  std::vector<double> h_fm_rel; std::vector<unsigned long long> h_tap_q;
+  double* d_scratch_nf = nullptr;
+  unsigned int h_bm = 0;
+  std::vector<double> h_proj, h_eff;
+  std::vector<uint64_t> h_uniq, h_total;
   // eq-class store: one EqStore per processed batch, merged at finish
   std::vector<EqStore> stores;
   uint64_t frag_counter = 0;     // fragments assigned so far (batched semantics)
@@ -517,6 +743,7 @@ extern "C" void sb_map_default_params(sb_map_params* q) {
   q->hard_filter = 0; q->first_decoy = 0x7fffffff; q->consensus_frac = 0.65; q->min_score_fraction = 0.65;
   q->score_exp = 1.0; q->min_aln_prob = 1e-5; q->decoy_threshold = 1.0; q->fld_mean = 250.0; q->fld_sd = 25.0;
   q->num_pre_burnin = 5000; q->num_burnin = 5000000;
+  q->seed = 42; q->mini_batch = 5000;
 }
 
 static void build_fld_host(const Params& p, std::vector<double>& t) {
@@ -531,10 +758,10 @@ static void build_fld_host(const Params& p, std::vector<double>& t) {
     return x + log(1 + exp(y - x));
   };
   auto ncdf = [&](double x) { return 0.5 * erfc(-(x - p.fld_mean) / (p.fld_sd * sqrt(2.0))); };
-  t.assign((size_t)4 * n, 0.0);
+  t.assign((size_t)5 * n + 1, 0.0);
   double* pmf_live = t.data(); double* pmf_cached = t.data() + n; double* cmf_cached = t.data() + 2 * n;
   double* cmf_quirk = t.data() + 3 * n;
-  std::vector<double> hist(n);
+  double* hist = t.data() + 4 * n;     // [4n, 5n): log histogram; [5n]: log total mass
   double tot = LOG_0;
   for (uint32_t i = 0; i < n; ++i) {
     const double nm = ncdf(i + 0.5) - ncdf(i - 0.5);
@@ -553,6 +780,18 @@ static void build_fld_host(const Params& p, std::vector<double>& t) {
     cq = logAdd(cq, LOG_EPSILON);
     cmf_quirk[i] = cq;
   }
+  t[(size_t)5 * n] = tot;
+}
+
+// ForgettingMassCalculator (ForgettingMassCalculator.hpp:24-40), forgettingFactor 0.65
+static double forgetting_mass(std::vector<double>& fm, uint64_t t) {
+  const double ff = 0.65;
+  while (fm.size() <= t) {
+    const uint64_t j = fm.size();
+    if (j == 0) fm.push_back(0.0);
+    else fm.push_back(fm[j - 1] + ff * log((double)j) - log(pow((double)(j + 1), ff) - 1));
+  }
+  return fm[t];
 }
 
 static int agg_reserve(AggScratch& a, uint64_t n) {
@@ -599,6 +838,7 @@ extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int d
   p.consensus_frac = q->consensus_frac; p.min_score_fraction = q->min_score_fraction; p.score_exp = q->score_exp;
   p.min_aln_prob = q->min_aln_prob; p.decoy_threshold = q->decoy_threshold; p.fld_mean = q->fld_mean; p.fld_sd = q->fld_sd;
   p.num_pre_burnin = q->num_pre_burnin; p.num_burnin = q->num_burnin;
+  p.seed = q->seed; p.mini_batch = q->mini_batch ? q->mini_batch : 5000; p.reserved = 0;
   // the ungapped shortcut of k_dp_score_w needs: no cell scores above ma, gaps cost something
   c->fast_ok = (p.ma >= 0 && p.mp <= p.ma && p.go >= 0 && p.ge >= 0) ? 1 : 0;
   cudaSetDevice(device);
@@ -629,7 +869,18 @@ extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int d
   A(&b.n_tasks, 4); A(&b.tasks, CH * 2 * MAXCAND);
   const size_t S = (size_t)c->k1_threads * cap;
   A(&b.sc, S); A(&b.perm_idx, S); A(&b.perm_tid, S); A(&b.bs_tid, S); A(&b.bs_score, S); A(&b.bs_idx, S); A(&b.jh, S);
+  A(&b.lp, S);
   A(&b.ctr, 1);
+  // online state
+  c->M = ix->n_txps; c->nf = p.max_frag_len + 1;
+  {
+    OnlineState& o = c->on;
+    const size_t M = std::max<uint32_t>(c->M, 1), nf = c->nf;
+    o.table_cap = (uint32_t)((B + p.mini_batch - 1) / p.mini_batch + 1);
+    A(&o.mass, M); A(&o.prior, M); A(&o.log_eff, M); A(&o.hist, nf); A(&o.tot, 1); A(&o.cf, nf);
+    A(&o.mass_acc, M); A(&o.fld_acc, nf); A(&o.mins, 2); A(&o.fm_rel, o.table_cap); A(&o.tap_q, (size_t)o.table_cap * 5);
+    A(&c->d_scratch_nf, nf);
+  }
   A(&c->d_overflow, (size_t)c->seed_blocks * SEED_WARPS * MAXSEEDS);
   A(&c->d_next_task, 4); A(&c->d_full_dp, 1);
   for (int s = 0; s < 2; ++s) for (int m = 0; m < 2; ++m) A(&c->d_in[s][m], CH * max_read_len);
@@ -640,10 +891,20 @@ extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int d
   A(&b.mate_pos, B * cap); A(&b.flags, B * cap); A(&b.flen, B * cap); A(&b.label, B * 2 * cap); A(&b.weight, B * cap);
   std::vector<double> t;
   build_fld_host(p, t);
-  A(&c->d_fld, t.size());
+  A(&c->d_fld, (size_t)4 * (p.max_frag_len + 1));
   if (rc == SB_OK) rc = agg_reserve(c->agg, B);
   if (rc != SB_OK) { sb_map_destroy(c); return nullptr; }
-  cudaMemcpy(c->d_fld, t.data(), t.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(c->d_fld, t.data(), (size_t)4 * c->nf * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(c->on.hist, t.data() + (size_t)4 * c->nf, (size_t)c->nf * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(c->on.tot, t.data() + (size_t)5 * c->nf, 8, cudaMemcpyHostToDevice);
+  cudaMemset(c->on.mass_acc, 0, std::max<uint32_t>(c->M, 1) * 8);
+  cudaMemset(c->on.fld_acc, 0, (size_t)c->nf * 8);
+  {
+    const unsigned int mins[2] = {p.max_frag_len, p.max_frag_len};   // FragmentLengthDistribution::min_ starts at max_val
+    cudaMemcpy(c->on.mins, mins, 8, cudaMemcpyHostToDevice);
+  }
+  if (c->M) k_online_init<<<nblk(c->M, 256), 256>>>(c->M, ix->d_tx_off, c->on.mass, c->on.prior, c->on.log_eff);
+  cudaDeviceSynchronize();
   cudaMemset(c->pr.nmask, 0, 2 * CH * c->pr.mpr * 8);
   const uint32_t n = p.max_frag_len + 1;
   c->fld.max_val = p.max_frag_len; c->fld.pmf_live = c->d_fld; c->fld.pmf_cached = c->d_fld + n;
@@ -661,7 +922,9 @@ extern "C" void sb_map_destroy(sb_map_ctx* c) {
   void* ptrs[] = {b.n_l, b.n_r, b.cand_l, b.cand_r, b.score_l, b.score_r, b.keys, b.n_tasks, b.tasks, b.n_aln, b.tid,
                   b.score, b.prob, b.pos, b.mate_pos, b.flags, b.flen, b.label, b.weight, b.sc, b.perm_idx, b.perm_tid,
                   b.bs_tid, b.bs_score, b.bs_idx, b.jh, b.ctr, c->d_in[0][0], c->d_in[0][1], c->d_in[1][0], c->d_in[1][1],
-                  c->d_fld, c->pr.bits, c->pr.nmask, c->d_overflow, c->d_next_task, c->d_full_dp};
+                  c->d_fld, c->pr.bits, c->pr.nmask, c->d_overflow, c->d_next_task, c->d_full_dp, b.lp,
+                  c->on.mass, c->on.prior, c->on.log_eff, c->on.hist, c->on.tot, c->on.cf, c->on.mass_acc, c->on.fld_acc,
+                  c->on.mins, c->on.fm_rel, c->on.tap_q, c->d_scratch_nf};
   for (void* p : ptrs) cudaFree(p);
   c->agg.free_all();
   for (auto& s : c->stores) s.free_all();
@@ -732,7 +995,28 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
   const Params& p = c->p;
   const uint32_t cap = p.max_read_occ;
   const IndexView ix = dev_view(c->index);
-  const int useAux = c->frag_counter >= p.num_pre_burnin, burnedIn = c->frag_counter >= p.num_burnin;
+  const int useAux = c->frag_counter >= p.num_pre_burnin, burnedIn = c->burned_in;
+  // forgetting masses of the batch's mini-batches, relative to the largest (the last); FLD kernel taps
+  const uint64_t nsteps = ((uint64_t)n + p.mini_batch - 1) / p.mini_batch;
+  const double fm_ref = forgetting_mass(c->fm, c->timestep + (nsteps ? nsteps - 1 : 0));
+  {
+    static const double kern_lin[5] = {1.0 / 16, 4.0 / 16, 6.0 / 16, 4.0 / 16, 1.0 / 16};   // binomial(4, 1/2)
+    c->h_fm_rel.assign(std::max<uint64_t>(nsteps, 1), 0.0);
+    c->h_tap_q.assign(std::max<uint64_t>(nsteps, 1) * 5, 0ull);
+    for (uint64_t s2 = 0; s2 < nsteps; ++s2) {
+      c->h_fm_rel[s2] = forgetting_mass(c->fm, c->timestep + s2) - fm_ref;
+      for (int i = 0; i < 5; ++i)
+        c->h_tap_q[s2 * 5 + i] = (unsigned long long)llrint(sbm_det_exp(c->h_fm_rel[s2] + sbm_det_log(kern_lin[i])) * MASS_SCALE);
+    }
+    SB_CUDA(cudaMemcpyAsync(c->on.fm_rel, c->h_fm_rel.data(), c->h_fm_rel.size() * 8, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(c->on.tap_q, c->h_tap_q.data(), c->h_tap_q.size() * 8, cudaMemcpyHostToDevice, st));
+    c->h_bm = p.max_frag_len;
+    SB_CUDA(cudaMemcpyAsync(c->on.mins, &c->h_bm, 4, cudaMemcpyHostToDevice, st));
+  }
+  OnlineView onv;
+  onv.mass = c->on.mass; onv.prior = c->on.prior; onv.log_eff = c->on.log_eff; onv.mass_acc = c->on.mass_acc;
+  onv.fld_acc = c->on.fld_acc; onv.batch_min = c->on.mins; onv.fm_rel = c->on.fm_rel; onv.tap_q = c->on.tap_q;
+  onv.mini_batch = p.mini_batch; onv.max_frag_len = p.max_frag_len; onv.frag_base = c->frags_seen; onv.seed = p.seed;
   SB_CUDA(cudaEventRecord(c->ev0, st));
   SB_CUDA(cudaMemsetAsync(c->b.ctr, 0, sizeof(Counters), st));
   SB_CUDA(cudaMemsetAsync(c->d_full_dp, 0, 8, st));
@@ -775,9 +1059,15 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
       }
       c->launches += 3;
     }
-    k_assign<<<T / 128, 128, 0, st>>>(ix, p, c->fld, useAux, burnedIn, cn, L, bc);
+    k_assign<<<T / 128, 128, 0, st>>>(ix, p, c->fld, useAux, burnedIn, cn, L, bc, onv, c0);
     c->launches += 1;
     SB_CUDA(cudaEventRecord(c->ev_free[s], st));
+  }
+  // fold the batch into the online state (masses, FLD)
+  if (n) {
+    if (c->M) k_online_fold_mass<<<nblk(c->M, 256), 256, 0, st>>>(c->M, fm_ref, c->on.mass, c->on.mass_acc);
+    k_online_fold_fld<<<1, 1024, 0, st>>>(c->nf, fm_ref, c->on, c->d_fld);
+    c->launches += 2;
   }
   // eq-class records of this batch: the per-read slots themselves (no compaction)
   EqStore es;
@@ -800,7 +1090,16 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
   SB_CUDA(cudaEventSynchronize(c->ev1));
   cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
   c->frag_counter += h.mapped;
+  c->frags_seen += n;
+  c->timestep += nsteps;
   c->full_dp_total += full_dp;
+  if (!c->burned_in && c->frag_counter >= p.num_burnin) {   // SalmonQuantify.cpp:1013-1018
+    k_online_correction<<<1, 32, 0, st>>>(c->nf, c->on, 1, c->d_scratch_nf, c->d_fld + c->nf, c->d_fld + 2 * (size_t)c->nf);
+    if (c->M) k_online_eff_len<<<nblk(c->M, 256), 256, 0, st>>>(c->M, c->nf, c->index->d_tx_off, c->on.cf, c->on.log_eff);
+    SB_CUDA(cudaStreamSynchronize(st));
+    c->burned_in = 1;
+    c->launches += 2;
+  }
   c->totals.lookups += h.lookups; c->totals.postings += h.postings; c->totals.seeds += h.seeds;
   c->totals.candidates += h.candidates; c->totals.kept += h.kept; c->totals.label_entries += h.label_entries;
   c->totals.mapped += h.mapped;
@@ -871,6 +1170,61 @@ extern "C" int sb_map_finish(sb_map_ctx* c, sb_map_result* out) {
     k_normalize<<<nblk(merged.n, 128), 128, 0, st>>>(merged.n, merged.woff, merged.weights);
     c->launches++;
   }
+  // ---- normalizeAlphas (SalmonUtils.cpp:461-529): initial alphas for the optimiser, plus what optimize() reads
+  //      per transcript (effective length, unique count)
+  {
+    const uint32_t M = c->M;
+    if (!c->burned_in) {   // burn-in never reached: effective lengths from the observed FLD (SalmonQuantify.cpp:2734-2738)
+      k_online_correction<<<1, 32, 0, st>>>(c->nf, c->on, 0, c->d_scratch_nf, nullptr, nullptr);
+      if (M) k_online_eff_len<<<nblk(M, 256), 256, 0, st>>>(M, c->nf, c->index->d_tx_off, c->on.cf, c->on.log_eff);
+      c->launches += 2;
+    }
+    c->h_proj.assign(M, 0.0); c->h_eff.assign(M, 0.0); c->h_uniq.assign(M, 0); c->h_total.assign(M, 0);
+    if (M) {
+      unsigned long long *uniq = nullptr, *total = nullptr, *hits = nullptr;
+      uint32_t *parent = nullptr, *root = nullptr, *root2 = nullptr, *ids = nullptr, *memb = nullptr, *head = nullptr,
+               *head_scan = nullptr, *start = nullptr;
+      double *proj = nullptr, *eff = nullptr;
+      uint8_t* bound = nullptr;
+      void* tmp = nullptr;
+      SB_TRY(dmalloc(&uniq, M)); SB_TRY(dmalloc(&total, M)); SB_TRY(dmalloc(&hits, M)); SB_TRY(dmalloc(&parent, M));
+      SB_TRY(dmalloc(&root, M)); SB_TRY(dmalloc(&root2, M)); SB_TRY(dmalloc(&ids, M)); SB_TRY(dmalloc(&memb, M));
+      SB_TRY(dmalloc(&head, (size_t)M + 1)); SB_TRY(dmalloc(&head_scan, (size_t)M + 1)); SB_TRY(dmalloc(&start, (size_t)M + 1));
+      SB_TRY(dmalloc(&proj, M)); SB_TRY(dmalloc(&eff, M)); SB_TRY(dmalloc(&bound, M));
+      SB_CUDA(cudaMemsetAsync(uniq, 0, (size_t)M * 8, st)); SB_CUDA(cudaMemsetAsync(total, 0, (size_t)M * 8, st));
+      SB_CUDA(cudaMemsetAsync(hits, 0, (size_t)M * 8, st));
+      k_iota<<<nblk(M, 256), 256, 0, st>>>(M, parent);
+      if (merged.n)
+        k_cls_accumulate<<<nblk(merged.n, 256), 256, 0, st>>>(merged.n, merged.loff, merged.woff, merged.labels,
+                                                              merged.counts, uniq, total, hits, parent);
+      k_roots<<<nblk(M, 256), 256, 0, st>>>(M, parent, root, ids);
+      size_t tb = 0, tb2 = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, root, root2, ids, memb, (int)M, 0, 32, st);
+      cub::DeviceScan::ExclusiveSum(nullptr, tb2, head, head_scan, (int)M + 1, st);
+      tb = std::max(tb, tb2);
+      SB_CUDA(cudaMalloc(&tmp, tb));
+      size_t t2 = tb;
+      SB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t2, root, root2, ids, memb, (int)M, 0, 32, st));   // stable: members ascending
+      k_cluster_heads<<<nblk((uint64_t)M + 1, 256), 256, 0, st>>>(M, root2, head);
+      t2 = tb;
+      SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, t2, head, head_scan, (int)M + 1, st));
+      uint32_t ncl = 0;
+      SB_CUDA(cudaMemcpyAsync(&ncl, head_scan + M, 4, cudaMemcpyDeviceToHost, st));
+      SB_CUDA(cudaStreamSynchronize(st));
+      k_cluster_starts<<<nblk(M, 256), 256, 0, st>>>(M, head, head_scan, start);
+      k_cluster_project<<<nblk((uint64_t)ncl * 32, 256), 256, 0, st>>>(ncl, M, start, memb, c->on.mass, hits, uniq, total,
+                                                                       proj, bound);
+      k_exp_vec<<<nblk(M, 256), 256, 0, st>>>(M, c->on.log_eff, eff);     // CollapsedEMOptimizer.cpp:782-784
+      c->launches += 10;
+      SB_CUDA(cudaMemcpyAsync(c->h_proj.data(), proj, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+      SB_CUDA(cudaMemcpyAsync(c->h_eff.data(), eff, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+      SB_CUDA(cudaMemcpyAsync(c->h_uniq.data(), uniq, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+      SB_CUDA(cudaMemcpyAsync(c->h_total.data(), total, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+      SB_CUDA(cudaStreamSynchronize(st));
+      void* fr[] = {uniq, total, hits, parent, root, root2, ids, memb, head, head_scan, start, proj, eff, bound, tmp};
+      for (void* q : fr) cudaFree(q);
+    }
+  }
   // to host (data movement only): drop the empty-label class, split label into tids | bins
   const int binned = c->p.range_bins > 0;
   std::vector<uint64_t> loff(merged.n + 1), woff(merged.n + 1), counts(merged.n);
@@ -905,5 +1259,27 @@ extern "C" int sb_map_finish(sb_map_ctx* c, sb_map_result* out) {
   out->n_mapped = c->totals.mapped;
   out->lookups = c->totals.lookups; out->postings = c->totals.postings; out->seeds = c->totals.seeds;
   out->candidates = c->totals.candidates; out->kept = c->totals.kept; out->label_entries = c->totals.label_entries;
+  out->n_txps = c->M;
+  out->projected_counts = c->h_proj.data(); out->eff_len = c->h_eff.data();
+  out->unique_counts = c->h_uniq.data(); out->total_counts = c->h_total.data();
+  return SB_OK;
+}
+
+// parity tap: the online state after the last batch
+extern "C" int sb_map_online_state(sb_map_ctx* c, double* mass_out, double* hist_out, double* log_eff_out,
+                                   uint64_t* scalars6) {
+  if (!c) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  SB_CUDA(cudaSetDevice(c->device));
+  if (mass_out && c->M) SB_CUDA(cudaMemcpy(mass_out, c->on.mass, (size_t)c->M * 8, cudaMemcpyDeviceToHost));
+  if (hist_out) SB_CUDA(cudaMemcpy(hist_out, c->on.hist, (size_t)c->nf * 8, cudaMemcpyDeviceToHost));
+  if (log_eff_out && c->M) SB_CUDA(cudaMemcpy(log_eff_out, c->on.log_eff, (size_t)c->M * 8, cudaMemcpyDeviceToHost));
+  if (scalars6) {
+    unsigned int mins[2];
+    double tot;
+    SB_CUDA(cudaMemcpy(mins, c->on.mins, 8, cudaMemcpyDeviceToHost));
+    SB_CUDA(cudaMemcpy(&tot, c->on.tot, 8, cudaMemcpyDeviceToHost));
+    scalars6[0] = c->frag_counter; scalars6[1] = c->frags_seen; scalars6[2] = c->timestep; scalars6[3] = (uint64_t)c->burned_in;
+    scalars6[4] = mins[1]; scalars6[5] = sbm_d2u(tot);
+  }
   return SB_OK;
 }

@@ -33,6 +33,8 @@ struct Params {
   double consensus_frac, min_score_fraction, score_exp, min_aln_prob, decoy_threshold;
   double fld_mean, fld_sd;
   uint64_t num_pre_burnin, num_burnin;
+  uint64_t seed;
+  uint32_t mini_batch, reserved;
 };
 
 struct TableEntry {
@@ -396,6 +398,63 @@ SB_HD double log_add(double x, double y) {                       // SalmonMath.h
 }
 SB_HD double tabv(const double* t, uint32_t max_val, uint64_t len) { return t[len > max_val ? max_val : len]; }
 
+// ---- online phase (processMiniBatch's state updates, src/quant/SalmonQuantify.cpp:599-623, 749-757, 783-792,
+// 859-983) with BATCHED SEMANTICS: the state (masses, FLD) is frozen while a batch is processed; the batch's
+// contributions are accumulated as integers -- multiples of 2^-40 of the batch's largest forgetting mass -- so
+// the sums do not depend on the order in which threads add them, and folded into the state afterwards.
+struct OnlineView {
+  const double* mass;        // [M] log mass (+inf = none), Transcript::mass_
+  const double* prior;       // [M] log(0.005 * length), Transcript::priorMass_
+  const double* log_eff;     // [M] cached log effective length (used once burned in)
+  unsigned long long* mass_acc;   // [M]
+  unsigned long long* fld_acc;    // [max_frag_len + 1]
+  unsigned int* batch_min;        // smallest fragment length added to the FLD in this batch
+  const double* fm_rel;      // [timesteps of the batch] log forgetting mass minus the batch's largest
+  const unsigned long long* tap_q;   // [timesteps * 5] FLD kernel taps (binomial(4, 1/2)) x forgetting mass, quantised
+  uint32_t mini_batch, max_frag_len;
+  uint64_t frag_base;        // global index of the batch's first fragment (RNG stream)
+  uint64_t seed;
+};
+constexpr double MASS_SCALE = 1099511627776.0;   // 2^40
+
+// Philox-4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11): r < exp(logProb) of the stochastic FLD update (:974-983)
+SB_HD uint32_t philox_first(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+  for (int i = 0; i < 10; ++i) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+SB_HD void acc_add(unsigned long long* p, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+}
+SB_HD void acc_min(unsigned int* p, unsigned int v) {
+#if defined(__CUDA_ARCH__)
+  atomicMin(p, v);
+#else
+  if (v < *p) *p = v;
+#endif
+}
+SB_HD long long quant40(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2ll_rn(SB_MUL(x, MASS_SCALE));
+#else
+  return llrint(x * MASS_SCALE);
+#endif
+}
+// QuasiAlignment::fragLengthPedantic for an inward pair: span of the outer ends clamped to the transcript
+SB_HD int32_t pedantic_flen(int fwd, int32_t pos, int32_t mpos, int32_t L, int32_t refLen) {
+  int32_t p1 = fwd ? pos : mpos; p1 = p1 < 0 ? 0 : p1; p1 = p1 > refLen ? refLen : p1;
+  int32_t p2 = fwd ? mpos + L : pos + L; p2 = p2 < 0 ? 0 : p2; p2 = p2 > refLen ? refLen : p2;
+  return (p1 > p2) ? p1 - p2 : p2 - p1;
+}
+
 // Per-read output of the assignment step.  cap = max_read_occ entries per read.
 struct ReadOut {
   uint32_t* n_aln;       // [1]
@@ -416,7 +475,8 @@ SB_HD void assign_read(const IndexView& ix, const Params& p, const FldView& fld,
                        const Cand* lc, uint32_t nl, const Cand* rcd, uint32_t nr, const int32_t* score_l,
                        const int32_t* score_r, uint32_t L, int32_t* sc, int32_t* perm_idx, int32_t* perm_tid,
                        int32_t* bs_tid, int32_t* bs_score, int32_t* bs_idx, Joint* jh, const ReadOut& o,
-                       Counters& ctr) {
+                       Counters& ctr, const OnlineView* on = nullptr, uint32_t read_in_batch = 0,
+                       double* lpbuf = nullptr /* >= cap doubles */) {
   const double LOG_EPSILON = -24.006680182952184;   // log(0.375e-10), SalmonMath.hpp:44-45 (libm and sbm_det_log agree)
   const uint32_t cap = p.max_read_occ;
   *o.n_aln = 0;
@@ -486,7 +546,7 @@ SB_HD void assign_read(const IndexView& ix, const Params& p, const FldView& fld,
   ctr.mapped++;
   ctr.label_entries += na;
   // ---- SalmonQuantify.cpp:599-857 (state frozen per batch); aux kept in o.weight until normalised
-  double auxDenom = log0();
+  double auxDenom = log0(), sumLp = log0();
   for (uint32_t a = 0; a < na; ++a) {
     const uint32_t tid = o.tid[a];
     const int32_t refLen = (int32_t)(ix.tx_off[tid + 1] - ix.tx_off[tid]);
@@ -527,6 +587,13 @@ SB_HD void assign_read(const IndexView& ix, const Params& p, const FldView& fld,
     const double aux = logFragProb + logFragCov + 0.0;
     o.weight[a] = aux;
     auxDenom = log_add(auxDenom, aux);
+    if (on) {   // aln.logProb = transcriptLogCount + auxProb + startPosProb  (:607-623, 749-757, 785)
+      const double logRefLength = burnedIn ? on->log_eff[tid] : sbm_det_log((double)refLen);
+      double startPosProb = -logRefLength;
+      if (status == 0) startPosProb = ((double)flen <= refLength) ? -sbm_det_log(refLength - (double)flen + 1) : LOG_EPSILON;
+      lpbuf[a] = log_add(on->prior[tid], on->mass[tid]) + aux + startPosProb;
+      sumLp = log_add(sumLp, lpbuf[a]);
+    }
   }
   for (uint32_t a = 0; a < na; ++a) {
     o.weight[a] = sbm_det_exp(o.weight[a] - auxDenom);
@@ -535,6 +602,33 @@ SB_HD void assign_read(const IndexView& ix, const Params& p, const FldView& fld,
   if (p.range_bins > 0) {
     const int32_t rangeCount = (int32_t)sqrt((double)na) + (int32_t)p.range_bins;
     for (uint32_t a = 0; a < na; ++a) o.label[na + a] = (uint32_t)(int32_t)(o.weight[a] * rangeCount);
+  }
+  if (on) {   // :859-983: normalise, add mass (x forgetting mass), stochastic FLD update
+    const uint32_t step = read_in_batch / on->mini_batch;
+    const double fm = on->fm_rel[step];
+    const uint64_t g = on->frag_base + read_in_batch;
+    for (uint32_t a = 0; a < na; ++a) {
+      const double nlp = lpbuf[a] - sumLp;
+      acc_add(on->mass_acc + o.tid[a], (unsigned long long)quant40(sbm_det_exp(fm + nlp)));
+      if (!burnedIn) {
+        const uint32_t status = (o.flags[a] >> 2) & 3;
+        const int fwd = o.flags[a] & 1, mateFwd = (o.flags[a] >> 1) & 1;
+        if (status != 0 || fwd == mateFwd) continue;          // fragLengthPedantic is 0 for anything but an inward pair
+        const uint32_t x = philox_first((uint32_t)g, (uint32_t)(g >> 32), a, 3u, (uint32_t)on->seed, (uint32_t)(on->seed >> 32));
+        const double u = (double)x * (1.0 / 4294967296.0);
+        if (!(u < sbm_det_exp(nlp))) continue;
+        const uint32_t tid = o.tid[a];
+        const int32_t refLen = (int32_t)(ix.tx_off[tid + 1] - ix.tx_off[tid]);
+        const int32_t fped = pedantic_flen(fwd, o.pos[a], o.mate_pos[a], (int32_t)L, refLen);
+        if (fped <= 0) continue;
+        uint32_t len = (uint32_t)fped;                         // FragmentLengthDistribution::addVal (:84-106)
+        if (len > on->max_frag_len) len = on->max_frag_len;
+        acc_min(on->batch_min, len);
+        int64_t off = (int64_t)len - 2;
+        for (int i = 0; i < 5; ++i, ++off)
+          if (off > 0 && off <= (int64_t)on->max_frag_len) acc_add(on->fld_acc + off, on->tap_q[step * 5 + i]);
+      }
+    }
   }
 }
 

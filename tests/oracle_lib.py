@@ -246,3 +246,55 @@ def eq_aggregate(m, cap, binned=True):
     nc = int(nc)
     nn = int(off[nc])
     return dict(off=off[:nc + 1].copy(), ntx=ntx[:nc].copy(), tids=lab[:nn].copy(), weights=w[:nn].copy(), counts=cnt[:nc].copy())
+
+
+class Online:
+    """orc_online: the stateful oracle of the online phase (batched semantics, oracle/map_oracle.c)."""
+
+    def __init__(self, index, p, seed=42, mini_batch=5000):
+        lib = load()
+        lib.orc_online_create.restype = C.c_void_p
+        self.index, self.p = index, p
+        self.h = C.c_void_p(lib.orc_online_create(index.h, C.byref(p), C.c_uint64(seed), C.c_uint32(mini_batch)))
+
+    def batch(self, left, right):
+        lib = load()
+        n, L = left.shape
+        cap = self.p.max_read_occ
+        left = np.ascontiguousarray(left, dtype=np.uint8); right = np.ascontiguousarray(right, dtype=np.uint8)
+        out = dict(n_aln=np.zeros(n, dtype=np.uint32), tid=np.zeros((n, cap), dtype=np.uint32),
+                   score=np.zeros((n, cap), dtype=np.int32), prob=np.zeros((n, cap)), pos=np.zeros((n, cap), dtype=np.int32),
+                   mate_pos=np.zeros((n, cap), dtype=np.int32), flags=np.zeros((n, cap), dtype=np.uint8),
+                   flen=np.zeros((n, cap), dtype=np.int32), label=np.zeros((n, 2 * cap), dtype=np.uint32),
+                   weight=np.zeros((n, cap)))
+        ctr = orc_map_counters()
+        rc = lib.orc_online_batch(self.h, _p(left), _p(right), C.c_uint32(n), C.c_uint32(L), _p(out["n_aln"]),
+                                  _p(out["tid"]), _p(out["score"]), _p(out["prob"]), _p(out["pos"]), _p(out["mate_pos"]),
+                                  _p(out["flags"]), _p(out["flen"]), _p(out["label"]), _p(out["weight"]), C.byref(ctr))
+        assert rc == 0
+        out["counters"] = ctr.asdict()
+        return out
+
+    def state(self):
+        M, nf = self.index.n, self.p.max_frag_len + 1
+        mass = np.zeros(M); hist = np.zeros(nf); le = np.zeros(M); sc = np.zeros(6, dtype=np.uint64)
+        load().orc_online_state(self.h, _p(mass), _p(hist), _p(le), _p(sc))
+        return dict(mass=mass, hist=hist, log_eff=le, assigned=int(sc[0]), frags_seen=int(sc[1]), timestep=int(sc[2]),
+                    burned_in=int(sc[3]), min_val=int(sc[4]), tot=sc[5:6].view(np.float64)[0])
+
+    def finish(self, off, tids, counts):
+        M = self.index.n
+        off = np.ascontiguousarray(off, dtype=np.uint64); tids = np.ascontiguousarray(tids, dtype=np.uint32)
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        proj = np.zeros(M); eff = np.zeros(M); uniq = np.zeros(M, dtype=np.uint64); tot = np.zeros(M, dtype=np.uint64)
+        rc = load().orc_online_finish(self.h, C.c_uint64(len(counts)), _p(off), _p(tids), _p(counts), _p(proj), _p(eff),
+                                      _p(uniq), _p(tot))
+        assert rc == 0
+        return dict(projected_counts=proj, eff_len=eff, unique_counts=uniq, total_counts=tot)
+
+    def __del__(self):
+        try:
+            load().orc_online_free.argtypes = [C.c_void_p]
+            load().orc_online_free(self.h)
+        except Exception:
+            pass

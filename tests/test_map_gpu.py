@@ -67,28 +67,74 @@ def test_single_batch_bit_exact(oracle, frag_counter_reads):
     ctx.close()
 
 
-def test_multi_batch_and_regimes(oracle):
-    """three batches; the fragment counter crosses numPreBurninFrags between them (batched semantics)."""
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def check_state(got, ref):
+    for k in ("assigned", "frags_seen", "timestep", "burned_in", "min_val"):
+        assert got[k] == ref[k], (k, got[k], ref[k])
+    assert np.array_equal(bits(got["mass"]), bits(ref["mass"]))          # integer accumulation: order-free, bit-exact
+    assert np.array_equal(bits(got["hist"]), bits(ref["hist"]))
+    assert bits(np.array([got["tot"]]))[0] == bits(np.array([ref["tot"]]))[0]
+    assert np.array_equal(bits(got["log_eff"]), bits(ref["log_eff"]))
+
+
+def test_multi_batch_online_state_and_regimes(oracle):
+    """three batches: masses and the fragment-length distribution evolve (batched semantics), the fragment counter
+    crosses numPreBurninFrags and numBurninFrags between batches, effective lengths and the cached FLD tables are
+    built at burn-in; then normalizeAlphas.  State bit-exact after every batch."""
     txps, _ = synth_txome(seed=4, n_genes=120)
     left, right, _ = synth_reads(txps, seed=6, n=9000)
-    p = map_default_params(num_pre_burnin=2500, num_burnin=5500)
+    over = dict(num_pre_burnin=2500, num_burnin=5500)
+    p = map_default_params(mini_batch=1000, seed=7, **over)
     idx = Index(txps)
     ctx = MapContext(idx, p, batch_cap=3000, max_read_len=100)
     oix = oracle.MapIndex(txps)
-    op = oracle.map_params(num_pre_burnin=2500, num_burnin=5500)
-    fc = 0
+    on = oracle.Online(oix, oracle.map_params(**over), seed=7, mini_batch=1000)
+    check_state(ctx.online_state(), on.state())
     parts = []
     for b in range(3):
         sl = slice(3000 * b, 3000 * (b + 1))
-        st = ctx.map_batch(left[sl], right[sl])
-        ref = oracle.map_reads(oix, op, left[sl], right[sl], fc)
+        ctx.map_batch(left[sl], right[sl])
+        ref = on.batch(left[sl], right[sl])
         compare(ctx.last_alignments(), ref, p.max_read_occ)
-        fc += ref["counters"]["mapped"]
+        check_state(ctx.online_state(), on.state())
         parts.append(ref)
+    st = on.state()
+    assert st["burned_in"] == 1 and st["timestep"] == 9 and st["min_val"] < 1000
     res = ctx.finish()
     cap = p.max_read_occ
     merged = {k: np.concatenate([q[k] for q in parts]) for k in ("n_aln", "label", "weight")}
-    check_classes(res, oracle.eq_aggregate(merged, cap, True), exact_weights=False)
+    ref_e = oracle.eq_aggregate(merged, cap, True)
+    check_classes(res, ref_e, exact_weights=False)
+    fin = on.finish(res["off"], res["tids"], res["counts"])
+    assert np.array_equal(res["unique_counts"], fin["unique_counts"])
+    assert np.array_equal(res["total_counts"], fin["total_counts"])
+    assert np.array_equal(bits(res["eff_len"]), bits(fin["eff_len"]))
+    np.testing.assert_allclose(res["projected_counts"], fin["projected_counts"], rtol=1e-9, atol=1e-9)
+    assert abs(res["projected_counts"].sum() - st["assigned"]) < 1e-6 * st["assigned"]
+    ctx.close()
+
+
+def test_never_burned_in_effective_lengths(oracle):
+    """fewer fragments than numBurninFrags: effective lengths come from the observed FLD at finish."""
+    txps, _ = synth_txome(seed=14, n_genes=60)
+    left, right, _ = synth_reads(txps, seed=16, n=4000)
+    p = map_default_params(num_pre_burnin=1000)
+    idx = Index(txps)
+    ctx = MapContext(idx, p, batch_cap=2048, max_read_len=100)
+    on = oracle.Online(oracle.MapIndex(txps), oracle.map_params(num_pre_burnin=1000), seed=42, mini_batch=5000)
+    for sl in (slice(0, 2048), slice(2048, 4000)):
+        ctx.map_batch(left[sl], right[sl])
+        compare(ctx.last_alignments(), on.batch(left[sl], right[sl]), p.max_read_occ)
+    check_state(ctx.online_state(), on.state())
+    res = ctx.finish()
+    fin = on.finish(res["off"], res["tids"], res["counts"])
+    assert np.array_equal(bits(res["eff_len"]), bits(fin["eff_len"]))
+    lens = np.array([t.shape[0] for t in txps], dtype=np.float64)
+    assert np.all(res["eff_len"] <= lens) and np.all(res["eff_len"] >= 1.0)
+    np.testing.assert_allclose(res["projected_counts"], fin["projected_counts"], rtol=1e-9, atol=1e-9)
     ctx.close()
 
 

@@ -140,3 +140,42 @@ def test_degenerate_classes_are_dropped(oracle):
                                np.zeros(3, dtype=np.uint64), p)
     assert st.n_degenerate == 1
     assert a[2] == 5.0 and a[0] == 0.0 and a[1] == 0.0
+
+
+
+def test_online_oracle_properties():
+    """Stage A online phase of the oracle: every assigned fragment adds exactly its forgetting mass (spread over its
+    alignments), clusters keep their hit counts through normalizeAlphas, effective lengths stay in (1, length]."""
+    import oracle_lib as O
+    from salmon_b200.synth import synth_reads, synth_txome
+    txps, _ = synth_txome(seed=5, n_genes=40)
+    left, right, _ = synth_reads(txps, seed=8, n=2400)
+    p = O.map_params(num_pre_burnin=500, num_burnin=1500)
+    oix = O.MapIndex(txps)
+    on = O.Online(oix, p, seed=3, mini_batch=400)
+    fm = [0.0]
+    for j in range(1, 12):
+        fm.append(fm[-1] + 0.65 * np.log(j) - np.log((j + 1) ** 0.65 - 1))
+    expect, parts = 0.0, []
+    for b in range(3):
+        sl = slice(800 * b, 800 * (b + 1))
+        m = on.batch(left[sl], right[sl])
+        parts.append(m)
+        mapped = m["n_aln"] > 0
+        step = 2 * b + np.arange(800) // 400
+        expect += np.exp(np.array(fm)[step][mapped]).sum()
+    st = on.state()
+    assert st["timestep"] == 6 and st["frags_seen"] == 2400 and st["burned_in"] == 1
+    tot_mass = np.exp(st["mass"][np.isfinite(st["mass"])]).sum()
+    assert abs(tot_mass - expect) < 1e-6 * expect
+    assert abs(np.exp(st["hist"] - st["tot"]).sum() - 1.0) < 1e-9      # the FLD stays a distribution
+    cap = p.max_read_occ
+    merged = {k: np.concatenate([q[k] for q in parts]) for k in ("n_aln", "label", "weight")}
+    e = O.eq_aggregate(merged, cap, True)
+    fin = on.finish(e["off"], e["tids"], e["counts"])
+    assert abs(fin["projected_counts"].sum() - st["assigned"]) < 1e-6 * st["assigned"]
+    assert np.all(fin["projected_counts"] <= fin["total_counts"] + 1e-6)
+    assert np.all(fin["projected_counts"] >= fin["unique_counts"] - 1e-6)
+    lens = np.array([t.shape[0] for t in txps], dtype=np.float64)
+    assert np.all(fin["eff_len"] >= 1.0) and np.all(fin["eff_len"] <= lens)
+    assert fin["eff_len"].mean() < lens.mean() - 100          # roughly length - mean fragment length
