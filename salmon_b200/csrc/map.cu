@@ -696,7 +696,8 @@ struct sb_map_ctx {
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   PackedReads pr{};
   uint64_t* d_overflow = nullptr;
-  uint32_t* d_next_task = nullptr;
+  uint32_t* d_next_task = nullptr;     // [0] task counter, [4..6] list sizes
+  uint32_t *d_list_int = nullptr, *d_list_edge = nullptr, *d_list_n = nullptr;
   unsigned long long* d_full_dp = nullptr;
   // FLD tables
   double* d_fld = nullptr;
@@ -882,7 +883,8 @@ extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int d
     A(&c->d_scratch_nf, nf);
   }
   A(&c->d_overflow, (size_t)c->seed_blocks * SEED_WARPS * MAXSEEDS);
-  A(&c->d_next_task, 4); A(&c->d_full_dp, 1);
+  A(&c->d_next_task, 8); A(&c->d_full_dp, 1);
+  A(&c->d_list_int, CH * 2 * MAXCAND); A(&c->d_list_edge, CH * 2 * MAXCAND); A(&c->d_list_n, CH * 2 * MAXCAND);
   for (int s = 0; s < 2; ++s) for (int m = 0; m < 2; ++m) A(&c->d_in[s][m], CH * max_read_len);
   c->pr.wpr = (max_read_len + 31) / 32 + 1; c->pr.mpr = (max_read_len + 63) / 64 + 1;
   A(&c->pr.bits, 2 * CH * c->pr.wpr); A(&c->pr.nmask, 2 * CH * c->pr.mpr);
@@ -924,7 +926,7 @@ extern "C" void sb_map_destroy(sb_map_ctx* c) {
                   b.bs_tid, b.bs_score, b.bs_idx, b.jh, b.ctr, c->d_in[0][0], c->d_in[0][1], c->d_in[1][0], c->d_in[1][1],
                   c->d_fld, c->pr.bits, c->pr.nmask, c->d_overflow, c->d_next_task, c->d_full_dp, b.lp,
                   c->on.mass, c->on.prior, c->on.log_eff, c->on.hist, c->on.tot, c->on.cf, c->on.mass_acc, c->on.fld_acc,
-                  c->on.mins, c->on.fm_rel, c->on.tap_q, c->d_scratch_nf};
+                  c->on.mins, c->on.fm_rel, c->on.tap_q, c->d_scratch_nf, c->d_list_int, c->d_list_edge, c->d_list_n};
   for (void* p : ptrs) cudaFree(p);
   c->agg.free_all();
   for (auto& s : c->stores) s.free_all();
@@ -1033,7 +1035,7 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
     SB_CUDA(cudaEventRecord(c->ev_in[s], cs));
     SB_CUDA(cudaStreamWaitEvent(st, c->ev_in[s], 0));
     SB_CUDA(cudaMemsetAsync(c->b.n_tasks, 0, 16, st));
-    SB_CUDA(cudaMemsetAsync(c->d_next_task, 0, 16, st));
+    SB_CUDA(cudaMemsetAsync(c->d_next_task, 0, 32, st));
     const uint8_t* dl = c->d_in[s][0];
     const uint8_t* dr = c->d_in[s][1];
     // outputs of this chunk inside the batch-wide arrays
@@ -1049,15 +1051,20 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
     } else {
       k_pack_reads<<<nblk((uint64_t)2 * cn * c->pr.wpr, 256), 256, 0, st>>>(dl, dr, cn, L, c->pr);
       SeedOut so{bc.n_l, bc.n_r, bc.cand_l, bc.cand_r, bc.n_tasks, bc.tasks, c->d_overflow, bc.ctr};
-      DpIo io{bc.n_tasks, bc.tasks, bc.cand_l, bc.cand_r, bc.score_l, bc.score_r, c->d_next_task, c->d_full_dp};
+      DpIo io{bc.n_tasks, bc.tasks, bc.cand_l, bc.cand_r, bc.score_l, bc.score_r, c->d_next_task, c->d_next_task + 4,
+              c->d_list_int, c->d_list_edge, c->d_list_n, c->d_full_dp};
       if (c->read_len_cap <= 128) {
         k_seed_chain_w<2><<<c->seed_blocks, SEED_WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
-        k_dp_score_w<4><<<c->dp_blocks, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, c->fast_ok, io);
+        k_dp_classify<4><<<c->dp_blocks, 256, 0, st>>>(ix, p, c->pr, L, c->fast_ok, io);
+        k_dp_pair<4><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, L, io);
+        k_dp_general<4><<<c->n_sm, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, io);
       } else {
         k_seed_chain_w<4><<<c->seed_blocks, SEED_WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
-        k_dp_score_w<8><<<c->dp_blocks, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, c->fast_ok, io);
+        k_dp_classify<8><<<c->dp_blocks, 256, 0, st>>>(ix, p, c->pr, L, c->fast_ok, io);
+        k_dp_pair<8><<<c->n_sm * 2, 256, 0, st>>>(ix, p, c->pr, L, io);
+        k_dp_general<8><<<c->n_sm, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, io);
       }
-      c->launches += 3;
+      c->launches += 5;
     }
     k_assign<<<T / 128, 128, 0, st>>>(ix, p, c->fld, useAux, burnedIn, cn, L, bc, onv, c0);
     c->launches += 1;

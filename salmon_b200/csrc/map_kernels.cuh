@@ -7,11 +7,12 @@
 //                  walk); seeds are expanded into a per-warp shared-memory key array by a warp prefix sum,
 //                  bitonic-sorted there, chained by a segmented warp scan (coverage bit masks OR-ed along each
 //                  chain), filtered, paired, and the DP task list is written with one atomic per read.
-//   k_dp_score_w   one warp per mate alignment.  Read and reference window live in registers (2-bit packed,
-//                  no memory access in the DP loop).  Lanes = band diagonals first evaluate the 2*band+1
-//                  ungapped alignments by XOR/popcount; when the best of them is within (go+ge) of a perfect
-//                  score no gapped path can beat it, so the banded affine DP -- same recurrences as
-//                  dp_score_serial -- only runs for the remaining alignments.
+//   k_dp_classify  one warp per mate alignment.  Lanes = band diagonals evaluate the 2*band+1 ungapped alignments
+//                  by XOR/popcount on 2-bit words; when the best of them is within (go+ge) of a perfect score no
+//                  gapped path can beat it.  The rest is queued for
+//   k_dp_pair      the banded affine DP (same recurrences as dp_score_serial), two alignments per warp, two band
+//                  cells per lane, read and reference window in registers (no memory access in the row loop), or
+//   k_dp_general   (band leaves the transcript, or an N is involved: rare).
 //
 // All three produce exactly what the serial forms in map_core.h produce (tests/test_map_gpu.py compares the
 // CUDA path with the independent oracle bit for bit).
@@ -405,14 +406,16 @@ k_seed_chain_w(IndexView ix, Params p, PackedReads pr, uint32_t n, uint32_t L, S
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_dp_score_w
+// DP scoring: k_dp_classify -> { k_dp_pair , k_dp_general }
 // ---------------------------------------------------------------------------------------------
 struct DpIo {
   const uint32_t* n_tasks; const uint32_t* tasks;
   const Cand* cand_l; const Cand* cand_r;
   int32_t* score_l; int32_t* score_r;
-  uint32_t* next_task;            // dynamic task counter
-  unsigned long long* n_full_dp;  // statistics: alignments that needed the full DP
+  uint32_t* next_task;            // dynamic task counter of k_dp_classify
+  uint32_t* list_n;               // [0] interior alignments, [1] edge alignments, [2] alignments with N
+  uint32_t* list_int; uint32_t* list_edge; uint32_t* list_n_tasks;   // task words
+  unsigned long long* n_full_dp;  // statistics: alignments that needed the banded DP
 };
 
 // byte-code form (transcripts with N, reads with N): lanes = band cells, one reference byte per row
@@ -464,14 +467,64 @@ __device__ __forceinline__ int32_t dp_warp_bytes(const IndexView& ix, const Para
   return best;
 }
 
+// the read as it aligns to the forward reference strand (reverse-complemented when ori = 1), bases beyond L zeroed
+template <int NWR>
+__device__ __forceinline__ void load_oriented_read(const PackedReads& pr, uint64_t mi, uint32_t L, uint32_t ori,
+                                                   uint64_t (&rw)[NWR]) {
+#pragma unroll
+  for (int m = 0; m < NWR; ++m) rw[m] = ((uint32_t)m < pr.wpr) ? pr.bits[mi * pr.wpr + m] : 0ull;
+  if (ori) {
+    uint64_t t2[NWR + 1];
+#pragma unroll
+    for (int m = 0; m < NWR; ++m) t2[m] = brev2(~rw[NWR - 1 - m]);
+    t2[NWR] = 0;
+    const uint32_t drop = (uint32_t)NWR * 32u - L;          // bases to drop at the low end
+    const uint32_t dw = drop >> 5, dsh = 2 * (drop & 31);
+#pragma unroll
+    for (int m = 0; m < NWR; ++m) {
+      uint64_t lo = 0, hi = 0;
+#pragma unroll
+      for (int q = 0; q <= NWR; ++q) {
+        if ((uint32_t)q == (uint32_t)m + dw) lo = t2[q];
+        if ((uint32_t)q == (uint32_t)m + dw + 1) hi = t2[q];
+      }
+      rw[m] = funnel64(lo, hi, dsh);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < NWR; ++m) {
+    const int32_t nb = (int32_t)L - 32 * m;
+    if (nb <= 0) rw[m] = 0;
+    else if (nb < 32) rw[m] &= (1ull << (2 * nb)) - 1;
+  }
+}
+// reference window: bases diag_c - B ... (window index 0 ... 32*(NWR+1) - 1), ww[NWR+1] = 0
+template <int NWR>
+__device__ __forceinline__ void load_window(const IndexView& ix, int64_t tbase, int32_t diag_c, int32_t B,
+                                            uint64_t (&ww)[NWR + 2]) {
+  const int64_t g0 = tbase + (int64_t)diag_c - B + (int64_t)PACK_GUARD_BASES;
+  const uint64_t* P = ix.packed + (g0 >> 5);
+  const uint32_t gsh = 2 * (uint32_t)(g0 & 31);
+  uint64_t prev = __ldg(P);
+#pragma unroll
+  for (int m = 0; m < NWR + 1; ++m) {
+    const uint64_t nxt = __ldg(P + m + 1);
+    ww[m] = funnel64(prev, nxt, gsh);
+    prev = nxt;
+  }
+  ww[NWR + 1] = 0;
+}
+
+// k_dp_classify: one warp per mate alignment.  Lanes = band diagonals evaluate the 2*band+1 ungapped alignments
+// (XOR + popcount on the 2-bit words); when the best is within (go+ge) of a perfect score no gapped path can beat
+// it.  Otherwise the alignment goes to the interior list (whole band inside the transcript -> k_dp_pair) or the
+// edge list; anything touching an N goes to the byte-code list.
 template <int NWR>   // read words: 4 (read_len <= 128) or 8 (<= 256)
 __global__ void __launch_bounds__(256, 4)
-k_dp_score_w(IndexView ix, Params p, PackedReads pr, const uint8_t* __restrict__ left,
-             const uint8_t* __restrict__ right, uint32_t L, int fast_ok, DpIo io) {
+k_dp_classify(IndexView ix, Params p, PackedReads pr, uint32_t L, int fast_ok, DpIo io) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t ntasks = *io.n_tasks;
   const int32_t B = (int32_t)p.band, W = 2 * B + 1;
-  unsigned long long n_full = 0;
   for (;;) {
     uint32_t t = 0;
     if (lane == 0) t = atomicAdd(io.next_task, 1u);
@@ -480,67 +533,22 @@ k_dp_score_w(IndexView ix, Params p, PackedReads pr, const uint8_t* __restrict__
     const uint32_t task = io.tasks[t];
     const uint32_t r = task >> 7, mate = (task >> 6) & 1u, ci = task & 63u;
     const Cand c = mate ? io.cand_r[(size_t)r * MAXCAND + ci] : io.cand_l[(size_t)r * MAXCAND + ci];
-    int32_t* out = (mate ? io.score_r : io.score_l) + (size_t)r * MAXCAND + ci;
     const uint64_t mi = (uint64_t)2 * r + mate;
-    // ---- N anywhere: byte path
     bool slow = ix.tx_has_n[c.tid] != 0;
     for (uint32_t w = 0; w < pr.mpr; ++w) slow |= pr.nmask[mi * pr.mpr + w] != 0;
     if (slow) {
-      const int32_t s = dp_warp_bytes(ix, p, (mate ? right : left) + (size_t)r * L, L, c, lane);
-      if (lane == 0) *out = s;
-      ++n_full;
+      if (lane == 0) io.list_n_tasks[atomicAdd(io.list_n + 2, 1u)] = task;
       continue;
     }
     const uint32_t ori = c.ori_cov >> 31;
     const int64_t tbase = (int64_t)ix.tx_off[c.tid];
     const int64_t tlen = (int64_t)ix.tx_off[c.tid + 1] - tbase;
-    // ---- the read as it aligns to the forward reference strand (reverse-complemented when ori = 1)
-    uint64_t rw[NWR];
-#pragma unroll
-    for (int m = 0; m < NWR; ++m) rw[m] = ((uint32_t)m < pr.wpr) ? pr.bits[mi * pr.wpr + m] : 0ull;
-    if (ori) {
-      uint64_t t2[NWR + 1];
-#pragma unroll
-      for (int m = 0; m < NWR; ++m) t2[m] = brev2(~rw[NWR - 1 - m]);
-      t2[NWR] = 0;
-      const uint32_t drop = (uint32_t)NWR * 32u - L;          // bases to drop at the low end
-      const uint32_t dw = drop >> 5, dsh = 2 * (drop & 31);
-#pragma unroll
-      for (int m = 0; m < NWR; ++m) {
-        uint64_t lo = 0, hi = 0;
-#pragma unroll
-        for (int q = 0; q <= NWR; ++q) {
-          if ((uint32_t)q == (uint32_t)m + dw) lo = t2[q];
-          if ((uint32_t)q == (uint32_t)m + dw + 1) hi = t2[q];
-        }
-        rw[m] = funnel64(lo, hi, dsh);
-      }
-    }
-    // mask the bases beyond L
-#pragma unroll
-    for (int m = 0; m < NWR; ++m) {
-      const int32_t nb = (int32_t)L - 32 * m;
-      if (nb <= 0) rw[m] = 0;
-      else if (nb < 32) rw[m] &= (1ull << (2 * nb)) - 1;
-    }
-    // ---- reference window: bases diag_c - B ... diag_c + L + B - 1  (window index 0 ... L + 2B - 1)
-    const int64_t g0 = tbase + (int64_t)c.diag_c - B + (int64_t)PACK_GUARD_BASES;
-    const uint64_t* P = ix.packed + (g0 >> 5);
-    const uint32_t gsh = 2 * (uint32_t)(g0 & 31);
-    uint64_t ww[NWR + 2];
-    {
-      uint64_t prev = __ldg(P);
-#pragma unroll
-      for (int m = 0; m < NWR + 1; ++m) {
-        const uint64_t nxt = __ldg(P + m + 1);
-        ww[m] = funnel64(prev, nxt, gsh);
-        prev = nxt;
-      }
-      ww[NWR + 1] = 0;
-    }
-    // ---- ungapped alignments on the 2B+1 diagonals (lane = diagonal)
-    int32_t best_u = NEG_SCORE;
     if (fast_ok) {
+      uint64_t rw[NWR];
+      load_oriented_read<NWR>(pr, mi, L, ori, rw);
+      uint64_t ww[NWR + 2];
+      load_window<NWR>(ix, tbase, c.diag_c, B, ww);
+      int32_t best_u = NEG_SCORE;
       const int64_t s0 = (int64_t)c.diag_c + ((int32_t)lane - B);
       if ((int32_t)lane < W && s0 >= 0 && s0 + (int64_t)L <= tlen) {
         uint32_t mm = 0;
@@ -558,12 +566,124 @@ k_dp_score_w(IndexView ix, Params p, PackedReads pr, const uint8_t* __restrict__
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) best_u = max(best_u, __shfl_xor_sync(0xffffffffu, best_u, o));
       if (best_u >= p.ma * (int32_t)L - p.go - p.ge) {
-        if (lane == 0) *out = best_u;
+        if (lane == 0) (mate ? io.score_r : io.score_l)[(size_t)r * MAXCAND + ci] = best_u;
         continue;
       }
     }
-    ++n_full;
-    // ---- banded affine DP, operands in registers
+    if (lane == 0) {
+      const bool interior = ((int64_t)c.diag_c - B >= 0) && ((int64_t)c.diag_c + (int64_t)L + B <= tlen);
+      if (interior) io.list_int[atomicAdd(io.list_n + 0, 1u)] = task;
+      else io.list_edge[atomicAdd(io.list_n + 1, 1u)] = task;
+    }
+  }
+}
+
+// k_dp_pair: banded affine DP for interior alignments, TWO alignments per warp: a half-warp owns one alignment,
+// lane hl owns band cells 2*hl and 2*hl+1 (cell 31 does not exist and is kept dead).  Same recurrences as
+// dp_score_serial; read and reference window live in registers (2-bit), no memory access in the row loop.  Dead
+// cells carry values around NEG_SCORE without re-clamping: they stay below -2^27, which every consumer treats
+// like NEG_SCORE (the hit is invalid), and never reach a live cell's maximum.
+template <int NWR>
+__global__ void __launch_bounds__(256, 3)
+k_dp_pair(IndexView ix, Params p, PackedReads pr, uint32_t L, DpIo io) {
+  const uint32_t lane = threadIdx.x & 31u, hl = lane & 15u, half = lane >> 4;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n = io.list_n[0];
+  const int32_t B = (int32_t)p.band;
+  const int32_t goe = p.go + p.ge, ge = p.ge;
+  const int32_t kge0 = (int32_t)(2 * hl) * ge, kge1 = kge0 + ge;
+  const bool last = hl == 15u;          // cell 30 | cell 31 (dead)
+  for (uint32_t t2 = warp * 2; t2 < n; t2 += nwarps * 2) {
+    const uint32_t t = (t2 + half < n) ? t2 + half : t2;       // odd tail: both halves do the same alignment
+    const uint32_t task = io.list_int[t];
+    const uint32_t r = task >> 7, mate = (task >> 6) & 1u, ci = task & 63u;
+    const Cand c = mate ? io.cand_r[(size_t)r * MAXCAND + ci] : io.cand_l[(size_t)r * MAXCAND + ci];
+    const uint64_t mi = (uint64_t)2 * r + mate;
+    uint64_t rw[NWR];
+    load_oriented_read<NWR>(pr, mi, L, c.ori_cov >> 31, rw);
+    uint64_t ww[NWR + 2];
+    load_window<NWR>(ix, (int64_t)ix.tx_off[c.tid], c.diag_c, B, ww);
+    int32_t H0 = 0, H1 = last ? NEG_SCORE : 0, E0 = NEG_SCORE, E1 = NEG_SCORE;
+    // blocks of 16 rows: the lane's reference bases for rows r0 .. r0+15 are window indices r0 + 2hl (+1) ...
+#pragma unroll
+    for (int blk = 0; blk < 2 * NWR; ++blk) {
+      const uint32_t r0 = 16u * blk;
+      if (r0 >= L) break;
+      const uint32_t rows = (L - r0 < 16u) ? (L - r0) : 16u;
+      const int q = blk >> 1;
+      const uint32_t off = 32u * (blk & 1) + 4u * hl;          // bit offset of window index r0 + 2hl inside ww[q]
+      const uint64_t lo = (off >= 64u) ? ww[q + 1] : ww[q];
+      const uint64_t hi = (off >= 64u) ? ww[q + 2] : ww[q + 1];
+      const uint64_t st = funnel64(lo, hi, off & 63u);
+      uint32_t rb0 = (uint32_t)(st & 3ull);
+      uint32_t stream = (uint32_t)(st >> 2);                   // bases r0 + 2hl + 1 ... (16 of them)
+      uint32_t cur = (uint32_t)(rw[q] >> (32 * (blk & 1)));    // read bases r0 ... r0 + 15
+      for (uint32_t ii = 0; ii < rows; ++ii) {
+        const uint32_t rb = cur & 3u; cur >>= 2;
+        const uint32_t rb1 = stream & 3u; stream >>= 2;
+        const int32_t s0 = (rb == rb0) ? p.ma : p.mp;
+        const int32_t s1 = (rb == rb1) ? p.ma : p.mp;
+        const int32_t Hn = __shfl_down_sync(0xffffffffu, H0, 1, 16);   // cell 2hl+2 of the previous row
+        const int32_t En = __shfl_down_sync(0xffffffffu, E0, 1, 16);
+        const int32_t e0 = max(H1 - goe, E1 - ge);
+        int32_t e1 = max(Hn - goe, En - ge);
+        int32_t hp0 = max(H0 + s0, e0);
+        int32_t hp1 = max(H1 + s1, e1);
+        if (last) { e1 = NEG_SCORE; hp1 = NEG_SCORE; }
+        const int32_t x0 = hp0 + kge0, x1 = hp1 + kge1;
+        int32_t inc = max(x0, x1);
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+          const int32_t y = __shfl_up_sync(0xffffffffu, inc, o, 16);
+          if ((int)hl >= o) inc = max(inc, y);
+        }
+        int32_t exc = __shfl_up_sync(0xffffffffu, inc, 1, 16);
+        if (hl == 0) exc = NEG_SCORE;
+        const int32_t f0 = exc - p.go - kge0;
+        const int32_t f1 = max(exc, x0) - p.go - kge1;
+        H0 = max(hp0, f0);
+        H1 = last ? NEG_SCORE : max(hp1, f1);
+        E0 = e0; E1 = e1;
+        rb0 = rb1;
+      }
+    }
+    int32_t best = max(H0, H1);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o, 16));
+    if (best < -(1 << 27)) best = NEG_SCORE;
+    if (hl == 0 && t2 + half < n) (mate ? io.score_r : io.score_l)[(size_t)r * MAXCAND + ci] = best;
+  }
+}
+
+// k_dp_general: the rare rest -- alignments whose band leaves the transcript (register form with per-cell validity)
+// and alignments touching an N (byte form).  One warp per alignment, lanes = band cells.
+template <int NWR>
+__global__ void __launch_bounds__(256, 3)
+k_dp_general(IndexView ix, Params p, PackedReads pr, const uint8_t* __restrict__ left,
+             const uint8_t* __restrict__ right, uint32_t L, DpIo io) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_edge = io.list_n[1], n_n = io.list_n[2];
+  const int32_t B = (int32_t)p.band, W = 2 * B + 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(io.n_full_dp, (unsigned long long)io.list_n[0] + n_edge + n_n);
+  for (uint32_t t = warp; t < n_edge + n_n; t += nwarps) {
+    const bool bytes = t >= n_edge;
+    const uint32_t task = bytes ? io.list_n_tasks[t - n_edge] : io.list_edge[t];
+    const uint32_t r = task >> 7, mate = (task >> 6) & 1u, ci = task & 63u;
+    const Cand c = mate ? io.cand_r[(size_t)r * MAXCAND + ci] : io.cand_l[(size_t)r * MAXCAND + ci];
+    int32_t* out = (mate ? io.score_r : io.score_l) + (size_t)r * MAXCAND + ci;
+    if (bytes) {
+      const int32_t s = dp_warp_bytes(ix, p, (mate ? right : left) + (size_t)r * L, L, c, lane);
+      if (lane == 0) *out = s;
+      continue;
+    }
+    const uint64_t mi = (uint64_t)2 * r + mate;
+    const int64_t tbase = (int64_t)ix.tx_off[c.tid];
+    const int64_t tlen = (int64_t)ix.tx_off[c.tid + 1] - tbase;
+    uint64_t rw[NWR];
+    load_oriented_read<NWR>(pr, mi, L, c.ori_cov >> 31, rw);
+    uint64_t ww[NWR + 2];
+    load_window<NWR>(ix, tbase, c.diag_c, B, ww);
     const bool in_band = (int32_t)lane < W;
     int32_t H = in_band ? 0 : NEG_SCORE, E = NEG_SCORE;
     int64_t rpos = (int64_t)c.diag_c + ((int32_t)lane - B);
@@ -617,7 +737,6 @@ k_dp_score_w(IndexView ix, Params p, PackedReads pr, const uint8_t* __restrict__
     for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
     if (lane == 0) *out = best;
   }
-  if (lane == 0 && n_full) atomicAdd(io.n_full_dp, n_full);
 }
 
 }  // namespace sbmap
