@@ -322,11 +322,22 @@ __global__ void k_assign(IndexView ix, Params p, FldView fld, int useAux, int bu
     o.flen = b.flen + (size_t)r * cap; o.label = b.label + (size_t)r * 2 * cap; o.weight = b.weight + (size_t)r * cap;
     const uint32_t nlr = b.n_l[r];
     if (nlr & 0x80000000u) { *o.n_aln = 0; continue; }
-    const size_t so = (size_t)tid0 * cap;
-    assign_read(ix, p, fld, useAux != 0, burnedIn != 0, b.cand_l + (size_t)r * MAXCAND, nlr,
-                b.cand_r + (size_t)r * MAXCAND, b.n_r[r], b.score_l + (size_t)r * MAXCAND,
-                b.score_r + (size_t)r * MAXCAND, L, b.sc + so, b.perm_idx + so, b.perm_tid + so, b.bs_tid + so,
-                b.bs_score + so, b.bs_idx + so, b.jh + so, o, ctr, &on, chunk_first_read + r, b.lp + so);
+    const uint32_t nl = nlr, nr = b.n_r[r];
+    if (nl * nr <= 32u && nl + nr <= 32u) {
+      // common case: few joint hits -> per-thread scratch in local memory (interleaved across threads, L1-cached)
+      int32_t sc[32], pi[32], pt[32], b1[32], b2[32], b3[32];
+      Joint jh[32];
+      double lp[32];
+      assign_read(ix, p, fld, useAux != 0, burnedIn != 0, b.cand_l + (size_t)r * MAXCAND, nl,
+                  b.cand_r + (size_t)r * MAXCAND, nr, b.score_l + (size_t)r * MAXCAND,
+                  b.score_r + (size_t)r * MAXCAND, L, sc, pi, pt, b1, b2, b3, jh, o, ctr, &on, chunk_first_read + r, lp);
+    } else {
+      const size_t so = (size_t)tid0 * cap;
+      assign_read(ix, p, fld, useAux != 0, burnedIn != 0, b.cand_l + (size_t)r * MAXCAND, nl,
+                  b.cand_r + (size_t)r * MAXCAND, nr, b.score_l + (size_t)r * MAXCAND,
+                  b.score_r + (size_t)r * MAXCAND, L, b.sc + so, b.perm_idx + so, b.perm_tid + so, b.bs_tid + so,
+                  b.bs_score + so, b.bs_idx + so, b.jh + so, o, ctr, &on, chunk_first_read + r, b.lp + so);
+    }
   }
   add_counters(b.ctr, ctr);
 }
@@ -1054,13 +1065,13 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
       DpIo io{bc.n_tasks, bc.tasks, bc.cand_l, bc.cand_r, bc.score_l, bc.score_r, c->d_next_task, c->d_next_task + 4,
               c->d_list_int, c->d_list_edge, c->d_list_n, c->d_full_dp};
       if (c->read_len_cap <= 128) {
-        k_seed_chain_w<2><<<c->seed_blocks, SEED_WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
-        k_dp_classify<4><<<c->dp_blocks, 256, 0, st>>>(ix, p, c->pr, L, c->fast_ok, io);
+        k_seed_chain_w<2><<<c->seed_blocks, SeedCfg<2>::WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
+        k_dp_classify<4><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, L, c->fast_ok, io);
         k_dp_pair<4><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, L, io);
         k_dp_general<4><<<c->n_sm, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, io);
       } else {
-        k_seed_chain_w<4><<<c->seed_blocks, SEED_WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
-        k_dp_classify<8><<<c->dp_blocks, 256, 0, st>>>(ix, p, c->pr, L, c->fast_ok, io);
+        k_seed_chain_w<4><<<c->seed_blocks, SeedCfg<4>::WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
+        k_dp_classify<8><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, L, c->fast_ok, io);
         k_dp_pair<8><<<c->n_sm * 2, 256, 0, st>>>(ix, p, c->pr, L, io);
         k_dp_general<8><<<c->n_sm, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, io);
       }

@@ -94,11 +94,21 @@ __device__ __forceinline__ bool cand_beats(uint64_t a, uint64_t b) {
   return (a >> 9) < (b >> 9);
 }
 
+constexpr uint32_t HS = 128;         // slots of the per-warp diagonal table (hash mode)
+template <int CW> struct SeedRegion { static constexpr uint32_t WORDS = HS + HS * CW + HS; };   // keys | masks | dense
+static_assert(SeedRegion<2>::WORDS == (uint32_t)SK, "sort mode reuses the table region");
+
+// Candidates of one mate.  Seeds with the same (transcript, orientation, diagonal) only differ in the read bases
+// they cover, and a read's seeds fall on a handful of diagonals (one per isoform), so the seeds are first merged
+// per diagonal in a small shared-memory hash table (coverage masks OR-ed with shared atomics); only the distinct
+// diagonals are sorted (in registers when there are <= 32) and chained.  If the table overflows (repeats), the
+// general path sorts all seeds instead.  Both paths give what mate_candidates() (map_core.h) gives.
+//   region: SeedRegion<CW>::WORDS words of shared memory;  gkeys: MAXSEEDS words of global scratch (T > SK)
 template <int CW>   // coverage words: 2 for read_len <= 128, 4 for <= 256
 __device__ __forceinline__ uint32_t warp_mate_candidates(const IndexView& ix, const Params& p,
                                                          const uint64_t* __restrict__ rbits,   // shared: wpr words
                                                          const uint64_t* __restrict__ rnm,     // shared: mpr words
-                                                         uint32_t L, uint64_t* skeys, uint64_t* gkeys,
+                                                         uint32_t L, uint64_t* region, uint64_t* gkeys,
                                                          uint64_t* cands /* shared, MAXCAND */, Counters& ctr,
                                                          uint32_t lane) {
   const uint32_t K = p.k;
@@ -151,49 +161,157 @@ __device__ __forceinline__ uint32_t warp_mate_candidates(const IndexView& ix, co
   if (lane == 0) { ctr.postings += T; ctr.seeds += T; }
   ctr.lookups += n_valid;     // per lane; summed when the counters are flushed
   if (T == 0) return 0;
-  uint64_t* keys = (T <= (uint32_t)SK) ? skeys : gkeys;
-  uint32_t n2 = 32;
-  while (n2 < T) n2 <<= 1;
-  // ---- expand postings into seed keys
-  uint32_t carry = 0;
-#pragma unroll
-  for (int rd = 0; rd < 2; ++rd) {
-    for (uint32_t it = 0; it < tot[rd]; it += 32) {
-      const uint32_t item = it + lane;
-      uint32_t lo = 0;
-#pragma unroll
-      for (int st = 16; st > 0; st >>= 1) {
-        const uint32_t e = __shfl_sync(0xffffffffu, excl[rd], lo + st);
-        if (e <= item) lo += st;
-      }
-      const uint32_t o_off = __shfl_sync(0xffffffffu, off[rd], lo);
-      const uint32_t o_excl = __shfl_sync(0xffffffffu, excl[rd], lo);
-      const uint32_t o_meta = __shfl_sync(0xffffffffu, meta[rd], lo);
-      const uint32_t slot = carry + item;
-      if (item < tot[rd] && slot < (uint32_t)MAXSEEDS) {
-        const Posting po = ix.post[o_off + (item - o_excl)];
-        const uint32_t pos_i = o_meta & 0xffffu;
-        const uint32_t ori = (o_meta >> 16) ^ (po.tpos_rc >> 31);
-        const int32_t qpos = ori ? (int32_t)(span - pos_i) : (int32_t)pos_i;
-        keys[slot] = seed_key(po.tid, ori, (int32_t)(po.tpos_rc & 0x7fffffffu) - qpos, qpos);
-      }
-    }
-    carry += tot[rd];
-  }
-  for (uint32_t i = T + lane; i < n2; i += 32) keys[i] = EMPTY_KEY;
+
+  uint64_t* tkeys = region;                 // [HS]
+  uint64_t* tmask = region + HS;            // [HS * CW]
+  uint64_t* dense = region + HS + HS * CW;  // [HS]
+  uint64_t* keys = nullptr;                 // the sorted array the chain pass walks
+  uint32_t N = 0;                           // its length
+  bool hash_mode = true;
+  // ---- hash mode: merge the seeds per diagonal
+  for (uint32_t i = lane; i < HS; i += 32) tkeys[i] = EMPTY_KEY;
+  for (uint32_t i = lane; i < HS * CW; i += 32) tmask[i] = 0ull;
   __syncwarp();
-  // ---- bitonic sort of n2 keys
-  for (uint32_t k = 2; k <= n2; k <<= 1)
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t t = lane; t < (n2 >> 1); t += 32) {
-        const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const uint32_t l = i | j;
-        const uint64_t a = keys[i], b = keys[l];
-        const bool asc = (i & k) == 0;
-        if ((a > b) == asc) { keys[i] = b; keys[l] = a; }
+  {
+    bool failed = false;
+    uint32_t carry = 0;
+#pragma unroll
+    for (int rd = 0; rd < 2; ++rd) {
+      for (uint32_t it = 0; it < tot[rd]; it += 32) {
+        const uint32_t item = it + lane;
+        uint32_t lo = 0;
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1) {
+          const uint32_t e = __shfl_sync(0xffffffffu, excl[rd], lo + st);
+          if (e <= item) lo += st;
+        }
+        const uint32_t o_off = __shfl_sync(0xffffffffu, off[rd], lo);
+        const uint32_t o_excl = __shfl_sync(0xffffffffu, excl[rd], lo);
+        const uint32_t o_meta = __shfl_sync(0xffffffffu, meta[rd], lo);
+        const uint32_t slot = carry + item;
+        if (item < tot[rd] && slot < (uint32_t)MAXSEEDS) {
+          const Posting po = ix.post[o_off + (item - o_excl)];
+          const uint32_t pos_i = o_meta & 0xffffu;
+          const uint32_t ori = (o_meta >> 16) ^ (po.tpos_rc >> 31);
+          const int32_t qpos = ori ? (int32_t)(span - pos_i) : (int32_t)pos_i;
+          const uint64_t kd = seed_key(po.tid, ori, (int32_t)(po.tpos_rc & 0x7fffffffu) - qpos, 0);
+          uint32_t h = (uint32_t)(((kd >> 9) * 0x9E3779B97F4A7C15ull) >> 57);
+          bool done = false;
+          for (uint32_t pr = 0; pr < 32 && !done; ++pr) {
+            const unsigned long long old = atomicCAS((unsigned long long*)&tkeys[h], (unsigned long long)EMPTY_KEY,
+                                                     (unsigned long long)kd);
+            if (old == (unsigned long long)EMPTY_KEY || old == (unsigned long long)kd) {
+#pragma unroll
+              for (int w = 0; w < CW; ++w) {
+                int32_t lo2 = qpos - 64 * w, hi2 = lo2 + (int32_t)K;
+                lo2 = lo2 < 0 ? 0 : lo2;
+                hi2 = hi2 > 64 ? 64 : hi2;
+                if (lo2 < hi2) atomicOr((unsigned long long*)&tmask[h * CW + w], (unsigned long long)(((1ull << (hi2 - lo2)) - 1) << lo2));
+              }
+              done = true;
+            } else {
+              h = (h + 1) & (HS - 1);
+            }
+          }
+          failed |= !done;
+        }
       }
-      __syncwarp();
+      carry += tot[rd];
     }
+    __syncwarp();
+    if (__any_sync(0xffffffffu, failed)) hash_mode = false;
+  }
+  if (hash_mode) {
+    // ---- compact the table: dense[] = diagonal key | slot index (low bits, where qpos would be)
+    uint32_t nd = 0;
+#pragma unroll
+    for (uint32_t s0 = 0; s0 < HS; s0 += 32) {
+      const uint32_t sidx = s0 + lane;
+      const uint64_t k = tkeys[sidx];
+      const bool v = k != EMPTY_KEY;
+      const uint32_t bal = __ballot_sync(0xffffffffu, v);
+      if (v) dense[nd + (uint32_t)__popc(bal & ((1u << lane) - 1))] = k | (uint64_t)sidx;
+      nd += (uint32_t)__popc(bal);
+    }
+    __syncwarp();
+    N = nd;
+    keys = dense;
+    if (nd <= 32) {
+      // one key per lane: bitonic network on shuffles
+      uint64_t k = lane < nd ? dense[lane] : EMPTY_KEY;
+#pragma unroll
+      for (uint32_t kk = 2; kk <= 32; kk <<= 1)
+#pragma unroll
+        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+          const uint64_t o = __shfl_xor_sync(0xffffffffu, k, j);
+          const bool keep_min = ((lane & j) == 0) == ((lane & kk) == 0);
+          k = keep_min ? (k < o ? k : o) : (k > o ? k : o);
+        }
+      __syncwarp();
+      dense[lane] = k;
+      __syncwarp();
+    } else {
+      uint32_t n2 = 64;
+      while (n2 < nd) n2 <<= 1;
+      for (uint32_t i = nd + lane; i < n2; i += 32) dense[i] = EMPTY_KEY;
+      __syncwarp();
+      for (uint32_t k = 2; k <= n2; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          for (uint32_t t = lane; t < (n2 >> 1); t += 32) {
+            const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+            const uint32_t l = i | j;
+            const uint64_t a = dense[i], b = dense[l];
+            const bool asc = (i & k) == 0;
+            if ((a > b) == asc) { dense[i] = b; dense[l] = a; }
+          }
+          __syncwarp();
+        }
+    }
+  } else {
+    // ---- general path: all seeds as keys (shared memory up to SK, else global scratch), bitonic sort
+    keys = (T <= (uint32_t)SK) ? region : gkeys;
+    N = T;
+    uint32_t n2 = 32;
+    while (n2 < T) n2 <<= 1;
+    uint32_t carry = 0;
+#pragma unroll
+    for (int rd = 0; rd < 2; ++rd) {
+      for (uint32_t it = 0; it < tot[rd]; it += 32) {
+        const uint32_t item = it + lane;
+        uint32_t lo = 0;
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1) {
+          const uint32_t e = __shfl_sync(0xffffffffu, excl[rd], lo + st);
+          if (e <= item) lo += st;
+        }
+        const uint32_t o_off = __shfl_sync(0xffffffffu, off[rd], lo);
+        const uint32_t o_excl = __shfl_sync(0xffffffffu, excl[rd], lo);
+        const uint32_t o_meta = __shfl_sync(0xffffffffu, meta[rd], lo);
+        const uint32_t slot = carry + item;
+        if (item < tot[rd] && slot < (uint32_t)MAXSEEDS) {
+          const Posting po = ix.post[o_off + (item - o_excl)];
+          const uint32_t pos_i = o_meta & 0xffffu;
+          const uint32_t ori = (o_meta >> 16) ^ (po.tpos_rc >> 31);
+          const int32_t qpos = ori ? (int32_t)(span - pos_i) : (int32_t)pos_i;
+          keys[slot] = seed_key(po.tid, ori, (int32_t)(po.tpos_rc & 0x7fffffffu) - qpos, qpos);
+        }
+      }
+      carry += tot[rd];
+    }
+    for (uint32_t i = T + lane; i < n2; i += 32) keys[i] = EMPTY_KEY;
+    __syncwarp();
+    for (uint32_t k = 2; k <= n2; k <<= 1)
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t t = lane; t < (n2 >> 1); t += 32) {
+          const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          const uint32_t l = i | j;
+          const uint64_t a = keys[i], b = keys[l];
+          const bool asc = (i & k) == 0;
+          if ((a > b) == asc) { keys[i] = b; keys[l] = a; }
+        }
+        __syncwarp();
+      }
+  }
   // ---- chains: segmented scan over the sorted keys; the tail of every chain is replaced by its
   //      candidate word, every other slot by EMPTY
   uint32_t best = 0;
@@ -203,19 +321,23 @@ __device__ __forceinline__ uint32_t warp_mate_candidates(const IndexView& ix, co
 #pragma unroll
   for (int w = 0; w < CW; ++w) carry_m[w] = 0;
   const int32_t gap = (int32_t)p.chain_gap;
-  for (uint32_t base = 0; base < T; base += 32) {
+  for (uint32_t base = 0; base < N; base += 32) {
     const uint32_t i = base + lane;
-    const bool active = i < T;
+    const bool active = i < N;
     const uint64_t k = active ? keys[i] : EMPTY_KEY;
     uint64_t kprev = __shfl_up_sync(0xffffffffu, k, 1);
     if (lane == 0) kprev = carry_key;
     uint64_t knext = __shfl_down_sync(0xffffffffu, k, 1);
-    if (lane == 31) knext = (i + 1 < T) ? keys[i + 1] : EMPTY_KEY;
+    if (lane == 31) knext = (i + 1 < N) ? keys[i + 1] : EMPTY_KEY;
     const int32_t dg = key_diag(k);
     const bool head = active && (i == 0 || (kprev >> 31) != (k >> 31) || dg - key_diag(kprev) > gap);
-    const bool tail = active && (i + 1 >= T || (knext >> 31) != (k >> 31) || key_diag(knext) - dg > gap);
+    const bool tail = active && (i + 1 >= N || (knext >> 31) != (k >> 31) || key_diag(knext) - dg > gap);
     uint64_t m[CW];
-    {
+    if (hash_mode) {
+      const uint32_t sidx = (uint32_t)(k & (HS - 1));
+#pragma unroll
+      for (int w = 0; w < CW; ++w) m[w] = active ? tmask[sidx * CW + w] : 0ull;
+    } else {
       const int32_t q = key_qpos(k);
 #pragma unroll
       for (int w = 0; w < CW; ++w) {
@@ -266,9 +388,9 @@ __device__ __forceinline__ uint32_t warp_mate_candidates(const IndexView& ix, co
   // ---- survivors (coverage >= consensus_frac * best), in (tid, ori, diag) order
   const double thr = p.consensus_frac * (double)best;
   uint32_t nc = 0;
-  for (uint32_t base = 0; base < T; base += 32) {
+  for (uint32_t base = 0; base < N; base += 32) {
     const uint32_t i = base + lane;
-    const uint64_t w = (i < T) ? keys[i] : EMPTY_KEY;
+    const uint64_t w = (i < N) ? keys[i] : EMPTY_KEY;
     const bool keep = (w != EMPTY_KEY) && ((double)cw_cov(w) >= thr);
     const uint32_t bal = __ballot_sync(0xffffffffu, keep);
     const uint32_t rank = nc + (uint32_t)__popc(bal & ((1u << lane) - 1));
@@ -278,12 +400,12 @@ __device__ __forceinline__ uint32_t warp_mate_candidates(const IndexView& ix, co
   if (nc > (uint32_t)MAXCAND) {
     // rare: keep the MAXCAND best by (coverage desc, tid, ori, diag); rank by counting who beats whom
     uint32_t out = 0;
-    for (uint32_t base = 0; base < T; base += 32) {
+    for (uint32_t base = 0; base < N; base += 32) {
       const uint32_t i = base + lane;
-      const uint64_t w = (i < T) ? keys[i] : EMPTY_KEY;
+      const uint64_t w = (i < N) ? keys[i] : EMPTY_KEY;
       const bool surv = (w != EMPTY_KEY) && ((double)cw_cov(w) >= thr);
       uint32_t beaten_by = 0;
-      for (uint32_t q = 0; q < T; ++q) {
+      for (uint32_t q = 0; q < N; ++q) {
         const uint64_t x = keys[q];
         if (x != EMPTY_KEY && (double)cw_cov(x) >= thr && surv && cand_beats(x, w)) ++beaten_by;
       }
@@ -303,14 +425,17 @@ __device__ __forceinline__ uint32_t cwd_tid(uint64_t w) { return (uint32_t)(w >>
 __device__ __forceinline__ uint32_t cwd_ori(uint64_t w) { return (uint32_t)(w >> 31) & 1u; }
 __device__ __forceinline__ int32_t cwd_diag(uint64_t w) { return (int32_t)((w >> 9) & 0x3fffffu) - (1 << 21); }
 
+template <int CW> struct SeedCfg { static constexpr int WARPS = (CW == 2) ? 8 : 6; };   // <= 48 KB static shared memory
+
 template <int CW>
-__global__ void __launch_bounds__(SEED_WARPS * 32, 4)
+__global__ void __launch_bounds__(SeedCfg<CW>::WARPS * 32, 4)
 k_seed_chain_w(IndexView ix, Params p, PackedReads pr, uint32_t n, uint32_t L, SeedOut o) {
-  __shared__ uint64_t s_keys[SEED_WARPS][SK];
-  __shared__ uint64_t s_cand[SEED_WARPS][2][MAXCAND];
-  __shared__ uint64_t s_read[SEED_WARPS][16];   // wpr (<= 9) + mpr (<= 5) words of the current mate
+  constexpr int WPB = SeedCfg<CW>::WARPS;
+  __shared__ uint64_t s_keys[WPB][SeedRegion<CW>::WORDS];
+  __shared__ uint64_t s_cand[WPB][2][MAXCAND];
+  __shared__ uint64_t s_read[WPB][16];   // wpr (<= 9) + mpr (<= 5) words of the current mate
   const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-  const uint32_t warp = blockIdx.x * SEED_WARPS + wib, nwarps = gridDim.x * SEED_WARPS;
+  const uint32_t warp = blockIdx.x * WPB + wib, nwarps = gridDim.x * WPB;
   uint64_t* gkeys = o.overflow_keys + (size_t)warp * MAXSEEDS;
   Counters ctr;
   ctr.lookups = ctr.postings = ctr.seeds = ctr.candidates = ctr.kept = ctr.label_entries = ctr.mapped = 0;
@@ -515,65 +640,84 @@ __device__ __forceinline__ void load_window(const IndexView& ix, int64_t tbase, 
   ww[NWR + 1] = 0;
 }
 
-// k_dp_classify: one warp per mate alignment.  Lanes = band diagonals evaluate the 2*band+1 ungapped alignments
-// (XOR + popcount on the 2-bit words); when the best is within (go+ge) of a perfect score no gapped path can beat
-// it.  Otherwise the alignment goes to the interior list (whole band inside the transcript -> k_dp_pair) or the
-// edge list; anything touching an N goes to the byte-code list.
+// k_dp_classify: one THREAD per mate alignment (32 independent alignments in flight per warp hide the chain of
+// dependent loads: task -> candidate -> read words -> reference window).  Each thread evaluates the ungapped
+// alignment on the candidate diagonal first (XOR + popcount on the 2-bit words; a perfect match ends here), then
+// the other 2*band diagonals; when the best ungapped score is within (go+ge) of a perfect score no gapped path can
+// beat it.  Otherwise the alignment goes to the interior list (whole band inside the transcript -> k_dp_pair) or the
+// edge list; anything touching an N goes to the byte-code list.  List slots are reserved once per warp.
 template <int NWR>   // read words: 4 (read_len <= 128) or 8 (<= 256)
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 k_dp_classify(IndexView ix, Params p, PackedReads pr, uint32_t L, int fast_ok, DpIo io) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t ntasks = *io.n_tasks;
+  const uint32_t nthreads = gridDim.x * blockDim.x;
   const int32_t B = (int32_t)p.band, W = 2 * B + 1;
-  for (;;) {
-    uint32_t t = 0;
-    if (lane == 0) t = atomicAdd(io.next_task, 1u);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= ntasks) break;
-    const uint32_t task = io.tasks[t];
-    const uint32_t r = task >> 7, mate = (task >> 6) & 1u, ci = task & 63u;
-    const Cand c = mate ? io.cand_r[(size_t)r * MAXCAND + ci] : io.cand_l[(size_t)r * MAXCAND + ci];
-    const uint64_t mi = (uint64_t)2 * r + mate;
-    bool slow = ix.tx_has_n[c.tid] != 0;
-    for (uint32_t w = 0; w < pr.mpr; ++w) slow |= pr.nmask[mi * pr.mpr + w] != 0;
-    if (slow) {
-      if (lane == 0) io.list_n_tasks[atomicAdd(io.list_n + 2, 1u)] = task;
-      continue;
-    }
-    const uint32_t ori = c.ori_cov >> 31;
-    const int64_t tbase = (int64_t)ix.tx_off[c.tid];
-    const int64_t tlen = (int64_t)ix.tx_off[c.tid + 1] - tbase;
-    if (fast_ok) {
-      uint64_t rw[NWR];
-      load_oriented_read<NWR>(pr, mi, L, ori, rw);
-      uint64_t ww[NWR + 2];
-      load_window<NWR>(ix, tbase, c.diag_c, B, ww);
-      int32_t best_u = NEG_SCORE;
-      const int64_t s0 = (int64_t)c.diag_c + ((int32_t)lane - B);
-      if ((int32_t)lane < W && s0 >= 0 && s0 + (int64_t)L <= tlen) {
-        uint32_t mm = 0;
+  const int32_t perfect = p.ma * (int32_t)L, bound = perfect - p.go - p.ge;
+  const uint32_t rounds = (ntasks + nthreads - 1) / nthreads;
+  for (uint32_t rd = 0; rd < rounds; ++rd) {
+    const uint32_t t = rd * nthreads + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool have = t < ntasks;
+    uint32_t task = 0;
+    int dest = -1;               // -1 resolved / none, 0 interior, 1 edge, 2 N
+    if (have) {
+      task = io.tasks[t];
+      const uint32_t r = task >> 7, mate = (task >> 6) & 1u, ci = task & 63u;
+      const Cand c = mate ? io.cand_r[(size_t)r * MAXCAND + ci] : io.cand_l[(size_t)r * MAXCAND + ci];
+      const uint64_t mi = (uint64_t)2 * r + mate;
+      bool slow = ix.tx_has_n[c.tid] != 0;
+      for (uint32_t w = 0; w < pr.mpr; ++w) slow |= pr.nmask[mi * pr.mpr + w] != 0;
+      if (slow) dest = 2;
+      else {
+        const int64_t tbase = (int64_t)ix.tx_off[c.tid];
+        const int64_t tlen = (int64_t)ix.tx_off[c.tid + 1] - tbase;
+        int32_t best_u = NEG_SCORE;
+        if (fast_ok) {
+          uint64_t rw[NWR];
+          load_oriented_read<NWR>(pr, mi, L, c.ori_cov >> 31, rw);
+          uint64_t ww[NWR + 2];
+          load_window<NWR>(ix, tbase, c.diag_c, B, ww);
+          // diagonal order: the candidate's own (j = B) first, then the rest
+          for (int32_t jj = 0; jj < W; ++jj) {
+            const int32_t j = (jj == 0) ? B : (jj <= B ? jj - 1 : jj);
+            const int64_t s0 = (int64_t)c.diag_c + (j - B);
+            if (s0 < 0 || s0 + (int64_t)L > tlen) continue;
+            uint32_t mm = 0;
 #pragma unroll
-        for (int m = 0; m < NWR; ++m) {
-          const uint64_t x = funnel64(ww[m], ww[m + 1], 2 * lane) ^ rw[m];
-          uint64_t d = (x | (x >> 1)) & 0x5555555555555555ull;
-          const int32_t nb = (int32_t)L - 32 * m;
-          if (nb <= 0) d = 0;
-          else if (nb < 32) d &= (1ull << (2 * nb)) - 1;
-          mm += (uint32_t)__popcll(d);
+            for (int m = 0; m < NWR; ++m) {
+              const uint64_t x = funnel64(ww[m], ww[m + 1], 2u * (uint32_t)j) ^ rw[m];
+              uint64_t d = (x | (x >> 1)) & 0x5555555555555555ull;
+              const int32_t nb = (int32_t)L - 32 * m;
+              if (nb <= 0) d = 0;
+              else if (nb < 32) d &= (1ull << (2 * nb)) - 1;
+              mm += (uint32_t)__popcll(d);
+            }
+            const int32_t u = p.ma * (int32_t)(L - mm) + p.mp * (int32_t)mm;
+            if (u > best_u) best_u = u;
+            if (best_u == perfect) break;
+          }
         }
-        best_u = p.ma * (int32_t)(L - mm) + p.mp * (int32_t)mm;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) best_u = max(best_u, __shfl_xor_sync(0xffffffffu, best_u, o));
-      if (best_u >= p.ma * (int32_t)L - p.go - p.ge) {
-        if (lane == 0) (mate ? io.score_r : io.score_l)[(size_t)r * MAXCAND + ci] = best_u;
-        continue;
+        if (fast_ok && best_u >= bound) {
+          (mate ? io.score_r : io.score_l)[(size_t)r * MAXCAND + ci] = best_u;
+        } else {
+          const bool interior = ((int64_t)c.diag_c - B >= 0) && ((int64_t)c.diag_c + (int64_t)L + B <= tlen);
+          dest = interior ? 0 : 1;
+        }
       }
     }
-    if (lane == 0) {
-      const bool interior = ((int64_t)c.diag_c - B >= 0) && ((int64_t)c.diag_c + (int64_t)L + B <= tlen);
-      if (interior) io.list_int[atomicAdd(io.list_n + 0, 1u)] = task;
-      else io.list_edge[atomicAdd(io.list_n + 1, 1u)] = task;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const uint32_t bal = __ballot_sync(0xffffffffu, dest == d);
+      if (bal) {
+        uint32_t base = 0;
+        const uint32_t leader = (uint32_t)__ffs(bal) - 1;
+        if (lane == leader) base = atomicAdd(io.list_n + d, (uint32_t)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (dest == d) {
+          uint32_t* list = d == 0 ? io.list_int : (d == 1 ? io.list_edge : io.list_n_tasks);
+          list[base + (uint32_t)__popc(bal & ((1u << lane) - 1))] = task;
+        }
+      }
     }
   }
 }
