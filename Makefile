@@ -10,7 +10,7 @@ HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 all: $(LIB) oracle
 
 $(LIB): $(SRCS) $(HDRS)
-	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(SRCS) -ldl -lgomp
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(SRCS) -ldl -lgomp -lz
 
 oracle:
 	$(MAKE) -C oracle

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""bench.py -- EM/VBEM iterations per second on BASELINE.json configs[1].
+"""bench.py -- EM/VBEM iterations per second on BASELINE.json configs[1] (headline), plus Stage A
+(selective-alignment Mreads/s at human-transcriptome scale, configs[2] shape) in the "stage_a" object.
 
 Workload (config 2, the largest EM-only configuration; fits one GPU): synth_eq(seed=1):
 500 000 equivalence classes over 250 000 transcripts (nnz ~3.0 M, sum of counts ~20 M),
@@ -148,6 +149,144 @@ def cpu_port_rate(eq, proj, eff, uniq, vbem, budget_s, threads):
     return n / max(dtn - setup, 1e-9), n, (t if t else 1)
 
 
+# --------------------------------------------------------------------------------------------
+# Stage A: selective alignment + online assignment + eq-class builder (BASELINE.json configs[2] shape)
+# --------------------------------------------------------------------------------------------
+SA = dict(n_genes=60_000, reads_per_step=2_097_152, batch=262_144, read_len=100)
+
+
+def stage_a_algorithmic_bytes(n_frags, read_len, c, band=15):
+    """B_frag = 2*len/4 + L*96 + E/4 + P*8 + A*(len+2*band)/4 + 32*K (+ 4*sum|label|)."""
+    return (n_frags * 2 * read_len / 4 + c["lookups"] * 96 + c["postings"] * 8 + c["candidates"] * (read_len + 2 * band) / 4
+            + 32 * c["kept"] + 4 * c["label_entries"])
+
+
+def stage_a_workload(rank, small=False):
+    from salmon_b200.synth import synth_txome, synth_reads_fast, flatten_txome
+    g = SA["n_genes"] // (20 if small else 1)
+    txps, _ = synth_txome(seed=44, n_genes=g)
+    flat = flatten_txome(txps)
+    left, right, _ = synth_reads_fast(txps, seed=7 + rank, n=SA["reads_per_step"] // (16 if small else 1),
+                                      read_len=SA["read_len"], flat=flat)
+    return txps, flat, left, right
+
+
+def stage_a_cpu(idx, p, left, right, budget_s, ncores):
+    """CPU port (the product's serial forms compiled for the host, OpenMP over reads) on a bounded sample."""
+    import hostmap_lib
+    probe = min(20_000, left.shape[0])
+    dt, _, _ = hostmap_lib.map_throughput(idx, p, left[:probe], right[:probe], 0, ncores)
+    n = int(min(left.shape[0], max(probe, probe * budget_s / max(dt, 1e-3))))
+    dt, na, c = hostmap_lib.map_throughput(idx, p, left[:n], right[:n], 0, ncores)
+    return n / dt / 1e6, n, c
+
+
+def bench_stage_a(args, rank, world, local, dist, W, peak, peak_src, ncores):
+    import torch
+    from salmon_b200 import _capi
+    from salmon_b200._capi import Index, MapContext, map_default_params
+    t0 = time.perf_counter()
+    txps, flat, left, right = stage_a_workload(rank, small=args.sa_small)
+    n, L = left.shape
+    idx = Index(txps)
+    info = idx.info()
+    t_setup = time.perf_counter() - t0
+    p = map_default_params()
+    batch = min(SA["batch"], n)
+    ctx = MapContext(idx, p, device=local, batch_cap=batch, max_read_len=L)
+    _capi.pin(left); _capi.pin(right)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(dev_ptrs=None):
+        """one pass over this rank's n read pairs: all batches + finish()."""
+        ctx.reset()
+        dev_ms, seed_ms, seed_n, launches, ctr = 0.0, 0.0, 0, 0, None
+        t0 = time.perf_counter()
+        for s in range(0, n, batch):
+            m = min(batch, n - s)
+            if dev_ptrs is None:
+                st = ctx.map_batch(left[s:s + m], right[s:s + m])
+            else:
+                st = ctx.map_batch_ptr(dev_ptrs[0] + s * L, dev_ptrs[1] + s * L, m, L)
+            dev_ms += st.device_ms; seed_ms += st.seed_kernel_ms; seed_n += st.seed_kernel_launches
+            launches = st.gpu_launches
+        res = ctx.finish()
+        wall = time.perf_counter() - t0
+        return wall, dev_ms, seed_ms, seed_n, launches, res
+
+    # ---- e2e: host (pinned) buffers through the C ABI, H2D inside, finish() (D2H of the class table) inside
+    for _ in range(W):
+        barrier(); step()
+    e2e_s, launches0 = [], 0
+    for _ in range(args.steps):
+        barrier()
+        wall, dev_ms, seed_ms, seed_n, launches, res = step()
+        e2e_s.append(wall)
+    # ---- inputs resident in HBM
+    torch.cuda.set_device(local)
+    dl = torch.from_numpy(left).cuda(); dr = torch.from_numpy(right).cuda()
+    ctx.set_option("input_on_device", 1)
+    barrier(); step((dl.data_ptr(), dr.data_ptr()))
+    res_s, seed_ms_l, seed_n_l = [], [], 0
+    for _ in range(args.steps):
+        barrier()
+        wall, dev_ms, seed_ms, seed_n, launches, res = step((dl.data_ptr(), dr.data_ptr()))
+        res_s.append(wall); seed_ms_l.append(seed_ms); seed_n_l = seed_n
+    barrier()
+    c = res["counters"]
+
+    def reduce_max(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    res_t = reduce_max(statistics.mean(res_s)); e2e_t = reduce_max(statistics.mean(e2e_s))
+    if rank != 0:
+        ctx.close()
+        return None
+    d2h = sum(res[k].nbytes for k in ("off", "tids", "weights", "counts", "projected_counts", "eff_len", "unique_counts",
+                                     "total_counts")) + (res["bins"].nbytes if res["bins"] is not None else 0)
+    seed_launch_ms = statistics.mean(seed_ms_l) / max(seed_n_l, 1)
+    frags_per_launch = n / max(seed_n_l, 1)
+    seed_bytes = (n * 2 * L / 4 + c["lookups"] * 96 + c["postings"] * 8) / max(seed_n_l, 1)
+    seed_achieved = seed_bytes / (seed_launch_ms / 1e3) / 1e9
+    out = {
+        "metric": "Mreads/s selective-align", "value": world * n / res_t / 1e6, "unit": "Mreads/s",
+        "ms_per_step": res_t * 1e3, "higher_is_better": True, "scaling": "weak", "dtype": "u8/i32 (mapping), f64 (weights)",
+        "config": {"workload": f"configs[2] shape: synth_txome(seed=44, n_genes={SA['n_genes'] // (20 if args.sa_small else 1)}) = "
+                               f"{len(txps)} transcripts / {flat[1].shape[0] / 1e6:.0f} Mb / {info['n_kmers'] / 1e6:.0f} M distinct 31-mers; "
+                               f"{n} synthetic 2x{L} bp IU pairs per GPU per step (0.5% substitutions, 3% unmappable), "
+                               f"batches of {batch}; a step = all batches + finish()",
+                   "index_bytes": info["bytes"], "setup_s": t_setup,
+                   "l2": "index (7.9 GB) and per-step reads (419 MB) exceed L2",
+                   "counters_per_step": c, "classes": int(len(res["counts"]))},
+        "e2e": {"value": world * n / e2e_t / 1e6, "unit": "Mreads/s", "h2d_bytes_per_step": int(2 * n * L),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_t * 1e3,
+                "api": "sb_map_batch x batches + sb_map_finish (C ABI, pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k_seed_chain_w", "achieved": seed_achieved, "peak": peak, "unit": "GB/s",
+                     "frac": seed_achieved / peak, "peak_source": peak_src, "avg_launch_ms": seed_launch_ms,
+                     "fragments_per_launch": frags_per_launch,
+                     "algorithmic_bytes_per_launch": seed_bytes,
+                     "traffic": None,
+                     "whole_stage_algorithmic_gbs": stage_a_algorithmic_bytes(n, L, c) / res_t / 1e9,
+                     "note": "the kernel is latency/issue-bound (dependent hash-probe -> posting loads, warp-level sort "
+                             "and scans), not bandwidth-bound: see DESIGN.md"},
+    }
+    if world == 1:
+        v, ns, cc = stage_a_cpu(idx, p, left, right, args.cpu_budget, ncores)
+        out["cpu_baseline"] = {"value": v, "unit": "Mreads/s", "cores": ncores, "kind": "port",
+                               "sample": f"{ns} read pairs of the same workload, same index, OpenMP over reads"}
+    ctx.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -156,6 +295,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--em", action="store_true", help="plain EM instead of VBEM (not the headline)")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-stage-a", action="store_true", help="skip the Stage A (mapping) measurement")
+    ap.add_argument("--sa-small", action="store_true", help="Stage A on a 20x smaller transcriptome (dev)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,6 +335,14 @@ def main():
             "e2e": {"value": val, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
+        if not args.no_stage_a:
+            from salmon_b200._capi import Index, map_default_params
+            txps, flat, left, right = stage_a_workload(0, small=args.sa_small)
+            idx = Index(txps)
+            v, ns, cc = stage_a_cpu(idx, map_default_params(), left, right, max(4.0, min(args.cpu_budget, 20.0)), ncores)
+            line["stage_a"] = {"metric": "Mreads/s selective-align", "value": v, "unit": "Mreads/s", "impl": "reference",
+                               "cpu_baseline": {"value": v, "unit": "Mreads/s", "cores": ncores, "kind": "port",
+                                                "sample": f"{ns} read pairs, {len(txps)} transcripts, OpenMP over reads"}}
         print(json.dumps(line))
         return 0
 
@@ -280,12 +429,16 @@ def main():
     value = world * ITERS_PER_STEP / (step_ms / 1e3)
     e2e_value = world * ITERS_PER_STEP / (e2e_step_ms / 1e3)
 
+    peak, peak_src = measured_peak()
+    ctx.close()
+    stage_a = None
+    if not args.no_stage_a:
+        stage_a = bench_stage_a(args, rank, world, local, dist, W, peak, peak_src, ncores)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
-    peak, peak_src = measured_peak()
     b_iter = algorithmic_bytes_per_iter(eq, bool(vbem))
     kern_iters_per_launch = ITERS_PER_STEP if (world == 1) else 1
     avg_launch_ms = loop_step_ms if world == 1 else loop_step_ms / ITERS_PER_STEP
@@ -325,6 +478,8 @@ def main():
                                 "host_cores": ncores,
                                 "sample": f"{cpu_n} iterations of the same workload; thread count chosen by probe "
                                           f"(best of all/64/32/16/8/serial)"}
+    if stage_a is not None:
+        line["stage_a"] = stage_a
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -145,6 +145,18 @@ int sb_gibbs(sb_em_ctx* ctx, const double* alphas_init, int use_vbem, int per_tx
              double vb_prior, uint32_t n_samples, uint32_t thinning, int no_gamma_draw,
              double num_mapped_frags, uint64_t seed, sb_sample_cb cb, void* user);
 
+/* ---- output seam (host code): the reference's file formats ---------------------------------
+ * TPM as GZipWriter::writeAbundances computes it (src/output/GZipWriter.cpp:719-736). */
+int sb_tpm(uint32_t n_txps, const double* alpha, const double* eff_len, double num_mapped_frags, double* tpm_out);
+/* quant.sf (GZipWriter.cpp:684-739): Name, Length (CompleteLength), EffectiveLength %.{sig}f, TPM %f, NumReads %.{sig}f */
+int sb_write_quant_sf(const char* path, uint32_t n_txps, const char* const* names, const uint32_t* complete_len,
+                      const double* eff_len, const double* alpha, double num_mapped_frags, int sig_digits);
+/* aux_info/eq_classes.txt[.gz] (GZipWriter.cpp:64-168; gzip when the path ends in .gz).  weights != NULL is the
+ * --dumpEqWeights layout the --eqclasses reader expects (src/util/SalmonUtils.cpp:1026-1122); weights == NULL
+ * collapses range-factorised classes by transcript set like the reference (:86-113). */
+int sb_write_eq_classes(const char* path, uint32_t n_txps, const char* const* names, uint64_t n_classes,
+                        const uint64_t* off, const uint32_t* tids, const double* weights, const uint64_t* counts);
+
 /* ---- Stage A: index, per-read mapping, equivalence-class builder ------------------
  * Seam B1: the body of processReads<IndexT> (src/quant/SalmonQuantify.cpp:1026-1874: per read
  * MemCollector / findChains / joinReadsAndFilter / PuffAligner::calculateAlignments /
@@ -203,6 +215,8 @@ typedef struct sb_map_batch_stats {
   float device_ms;            /* H2D of the reads + all kernels of the batch (CUDA events) */
   uint32_t reserved;
   uint64_t full_dp;           /* mate alignments that needed the banded DP (the rest: ungapped shortcut) */
+  float seed_kernel_ms;       /* device time of the seed/chain kernel launches of this batch (CUDA events) */
+  uint32_t seed_kernel_launches;
 } sb_map_batch_stats;
 
 typedef struct sb_map_result {   /* host CSR owned by the context, valid until destroy / next finish */
@@ -233,6 +247,32 @@ void sb_map_destroy(sb_map_ctx* ctx);
  * advance every `mini_batch` reads.  Smaller batches track the reference's per-5000-read dynamics more closely. */
 int sb_map_batch(sb_map_ctx* ctx, const uint8_t* left, const uint8_t* right, uint32_t n_pairs,
                  uint32_t read_len, sb_map_batch_stats* stats);
+/* ---- multi-GPU Stage A: reads sharded over ranks, one context per GPU / process, class tables stay
+ * per rank.  After sb_map_finish every rank exports its statistics (sb_map_partial_get); the host layer reduces them
+ * over the ranks once -- masses and the FLD by log-sum-exp (the FLD prior counted once), counts by sum, fld_min by min,
+ * cluster roots all-gathered -- and calls sb_map_project_global, which redoes normalizeAlphas with the global state:
+ * every rank then holds identical projected counts / effective lengths / unique counts for sb_em_optimize
+ * (classes sharded, alpha all-reduced per iteration). */
+typedef struct sb_map_partial {
+  uint32_t n_txps, n_fld;          /* n_fld = max_frag_len + 1 */
+  const double* mass;              /* [n_txps] log mass (+inf = none) */
+  const double* fld_hist;          /* [n_fld] log histogram */
+  double fld_tot;                  /* log total mass */
+  const double* fld_prior_hist;    /* [n_fld] the prior every rank started from */
+  double fld_prior_tot;
+  uint32_t fld_min, reserved;
+  const uint64_t* unique_counts;   /* [n_txps] */
+  const uint64_t* total_counts;    /* [n_txps] */
+  const uint64_t* cluster_hits;    /* [n_txps] fragments whose first transcript this is */
+  const uint32_t* cluster_root;    /* [n_txps] smallest transcript id of the transcript's cluster */
+  uint64_t assigned;               /* fragments assigned by this rank */
+} sb_map_partial;
+int sb_map_partial_get(sb_map_ctx* ctx, sb_map_partial* out);
+int sb_map_project_global(sb_map_ctx* ctx, const sb_map_partial* global_stats, uint32_t n_ranks,
+                          const uint32_t* roots_all /* n_ranks x n_txps */, sb_map_result* out);
+
+/* Forget everything mapped so far (class tables, online state, counters) without re-allocating. */
+int sb_map_reset(sb_map_ctx* ctx);
 /* finish(): merge batch tables, normalise weights, return the CSR (feeds sb_em_optimize). */
 int sb_map_finish(sb_map_ctx* ctx, sb_map_result* out);
 /* Parity tap: the online state after the last batch.  mass_out[n_txps] (log scale, +inf = none),
@@ -245,7 +285,9 @@ int sb_map_last_alignments(sb_map_ctx* ctx, uint32_t n, uint32_t* n_aln, uint32_
                            uint32_t* label, double* weight);
 
 /* Tuning knobs of the mapping context: "variant" (1 = warp-cooperative kernels, 0 = serial-form kernels),
- * "fast_dp" (ungapped shortcut of the DP kernel on/off).  Results are identical for every setting. */
+ * "fast_dp" (ungapped shortcut of the DP kernel on/off), "chunk" (reads per pipeline chunk), "input_on_device"
+ * (sb_map_batch's read pointers are device pointers: inputs already resident in HBM).  Results are identical for
+ * every setting. */
 int sb_map_set_option(sb_map_ctx* ctx, const char* key, int64_t value);
 
 /* Debug: per-warp phase timestamps (ns) of one iteration of the last persistent run:

@@ -87,7 +87,8 @@ class sb_map_params(C.Structure):
 class sb_map_batch_stats(C.Structure):
     _fields_ = [("n_pairs", C.c_uint32), ("gpu_launches", C.c_uint32)] + \
         [(k, C.c_uint64) for k in ("mapped", "lookups", "postings", "seeds", "candidates", "kept", "label_entries",
-                                   "n_batch_classes")] + [("device_ms", C.c_float), ("reserved", C.c_uint32), ("full_dp", C.c_uint64)]
+                                   "n_batch_classes")] + [("device_ms", C.c_float), ("reserved", C.c_uint32), ("full_dp", C.c_uint64),
+                                                              ("seed_kernel_ms", C.c_float), ("seed_kernel_launches", C.c_uint32)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -104,6 +105,14 @@ class sb_map_result(C.Structure):
 
 # every symbol include/salmon_b200.h declares: (name, restype, argtypes)
 _P = C.c_void_p
+class sb_map_partial(C.Structure):
+    _fields_ = [("n_txps", C.c_uint32), ("n_fld", C.c_uint32), ("mass", C.POINTER(C.c_double)),
+                ("fld_hist", C.POINTER(C.c_double)), ("fld_tot", C.c_double), ("fld_prior_hist", C.POINTER(C.c_double)),
+                ("fld_prior_tot", C.c_double), ("fld_min", C.c_uint32), ("reserved", C.c_uint32),
+                ("unique_counts", C.POINTER(C.c_uint64)), ("total_counts", C.POINTER(C.c_uint64)),
+                ("cluster_hits", C.POINTER(C.c_uint64)), ("cluster_root", C.POINTER(C.c_uint32)), ("assigned", C.c_uint64)]
+
+
 SYMBOLS = {
     "sb_version": (C.c_int, []),
     "sb_last_error": (C.c_char_p, []),
@@ -139,6 +148,12 @@ SYMBOLS = {
     "sb_map_finish": (C.c_int, [_P, C.POINTER(sb_map_result)]),
     "sb_map_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "sb_map_online_state": (C.c_int, [_P, _P, _P, _P, _P]),
+    "sb_map_reset": (C.c_int, [_P]),
+    "sb_tpm": (C.c_int, [C.c_uint32, _P, _P, C.c_double, _P]),
+    "sb_write_quant_sf": (C.c_int, [C.c_char_p, C.c_uint32, _P, _P, _P, _P, C.c_double, C.c_int]),
+    "sb_write_eq_classes": (C.c_int, [C.c_char_p, C.c_uint32, _P, C.c_uint64, _P, _P, _P, _P]),
+    "sb_map_partial_get": (C.c_int, [_P, C.POINTER(sb_map_partial)]),
+    "sb_map_project_global": (C.c_int, [_P, C.POINTER(sb_map_partial), C.c_uint32, _P, C.POINTER(sb_map_result)]),
     "sb_map_last_alignments": (C.c_int, [_P, C.c_uint32] + [_P] * 10),
     "sb_host_register": (C.c_int, [_P, C.c_size_t]),
     "sb_host_unregister": (C.c_int, [_P]),
@@ -429,6 +444,51 @@ class MapContext:
         self.last_n = n
         return st
 
+    def map_batch_ptr(self, left_ptr: int, right_ptr: int, n: int, L: int) -> sb_map_batch_stats:
+        """raw pointers (device pointers with set_option("input_on_device", 1))"""
+        st = sb_map_batch_stats()
+        _check(self.lib.sb_map_batch(self.h, C.c_void_p(left_ptr), C.c_void_p(right_ptr), n, L, C.byref(st)), "sb_map_batch")
+        self.last_n = n
+        return st
+
+    def reset(self):
+        _check(self.lib.sb_map_reset(self.h), "sb_map_reset")
+
+    def partial(self) -> dict:
+        """this rank's statistics after finish() (multi-GPU: reduce them with salmon_b200.dist.reduce_partials)"""
+        q = sb_map_partial()
+        _check(self.lib.sb_map_partial_get(self.h, C.byref(q)), "sb_map_partial_get")
+        M, nf = int(q.n_txps), int(q.n_fld)
+        arr = lambda ptr, n, dt: (np.ctypeslib.as_array(ptr, shape=(n,)).copy() if n else np.zeros(0, dt))
+        return dict(mass=arr(q.mass, M, np.float64), fld_hist=arr(q.fld_hist, nf, np.float64), fld_tot=float(q.fld_tot),
+                    fld_prior_hist=arr(q.fld_prior_hist, nf, np.float64), fld_prior_tot=float(q.fld_prior_tot),
+                    fld_min=int(q.fld_min), unique_counts=arr(q.unique_counts, M, np.uint64),
+                    total_counts=arr(q.total_counts, M, np.uint64), cluster_hits=arr(q.cluster_hits, M, np.uint64),
+                    cluster_root=arr(q.cluster_root, M, np.uint32), assigned=int(q.assigned))
+
+    def project_global(self, g: dict, roots_all: np.ndarray) -> dict:
+        """normalizeAlphas with the statistics reduced over all ranks; returns the per-transcript EM inputs"""
+        keep = {k: np.ascontiguousarray(g[k], dtype=dt) for k, dt in (
+            ("mass", np.float64), ("fld_hist", np.float64), ("fld_prior_hist", np.float64), ("unique_counts", np.uint64),
+            ("total_counts", np.uint64), ("cluster_hits", np.uint64))}
+        roots_all = np.ascontiguousarray(roots_all, dtype=np.uint32)
+        q = sb_map_partial()
+        q.n_txps = keep["mass"].shape[0]; q.n_fld = keep["fld_hist"].shape[0]
+        q.mass = keep["mass"].ctypes.data_as(C.POINTER(C.c_double))
+        q.fld_hist = keep["fld_hist"].ctypes.data_as(C.POINTER(C.c_double)); q.fld_tot = float(g["fld_tot"])
+        q.fld_prior_hist = keep["fld_prior_hist"].ctypes.data_as(C.POINTER(C.c_double)); q.fld_prior_tot = float(g["fld_prior_tot"])
+        q.fld_min = int(g["fld_min"])
+        q.unique_counts = keep["unique_counts"].ctypes.data_as(C.POINTER(C.c_uint64))
+        q.total_counts = keep["total_counts"].ctypes.data_as(C.POINTER(C.c_uint64))
+        q.cluster_hits = keep["cluster_hits"].ctypes.data_as(C.POINTER(C.c_uint64))
+        q.cluster_root = None; q.assigned = int(g["assigned"])
+        r = sb_map_result()
+        _check(self.lib.sb_map_project_global(self.h, C.byref(q), roots_all.shape[0], roots_all.ctypes.data, C.byref(r)),
+               "sb_map_project_global")
+        M = int(r.n_txps)
+        return {k: (np.ctypeslib.as_array(getattr(r, k), shape=(M,)).copy() if M else np.zeros(0))
+                for k in ("projected_counts", "eff_len", "unique_counts", "total_counts")}
+
     def set_option(self, key: str, value: int):
         _check(self.lib.sb_map_set_option(self.h, key.encode(), int(value)), "sb_map_set_option")
 
@@ -477,3 +537,36 @@ class MapContext:
             self.close()
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------------------ output seam
+def _names(names):
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    return arr
+
+
+def tpm(alpha, eff_len, num_mapped_frags=None):
+    alpha = np.ascontiguousarray(alpha, dtype=np.float64); eff_len = np.ascontiguousarray(eff_len, dtype=np.float64)
+    out = np.zeros_like(alpha)
+    nm = float(alpha.sum()) if num_mapped_frags is None else float(num_mapped_frags)
+    _check(load().sb_tpm(alpha.shape[0], alpha.ctypes.data, eff_len.ctypes.data, nm, out.ctypes.data), "sb_tpm")
+    return out
+
+
+def write_quant_sf(path, names, complete_len, eff_len, alpha, num_mapped_frags=None, sig_digits=3):
+    alpha = np.ascontiguousarray(alpha, dtype=np.float64); eff_len = np.ascontiguousarray(eff_len, dtype=np.float64)
+    cl = np.ascontiguousarray(complete_len, dtype=np.uint32)
+    nm = float(alpha.sum()) if num_mapped_frags is None else float(num_mapped_frags)
+    arr = _names(names)
+    _check(load().sb_write_quant_sf(str(path).encode(), len(names), C.cast(arr, C.c_void_p), cl.ctypes.data,
+                                    eff_len.ctypes.data, alpha.ctypes.data, nm, sig_digits), "sb_write_quant_sf")
+
+
+def write_eq_classes(path, names, off, tids, counts, weights=None):
+    off = np.ascontiguousarray(off, dtype=np.uint64); tids = np.ascontiguousarray(tids, dtype=np.uint32)
+    counts = np.ascontiguousarray(counts, dtype=np.uint64)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    arr = _names(names)
+    _check(load().sb_write_eq_classes(str(path).encode(), len(names), C.cast(arr, C.c_void_p), counts.shape[0],
+                                      off.ctypes.data, tids.ctypes.data, None if w is None else w.ctypes.data,
+                                      counts.ctypes.data), "sb_write_eq_classes")

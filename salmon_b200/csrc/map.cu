@@ -692,6 +692,16 @@ struct AggScratch {   // sized for `cap` records
   }
 };
 
+struct FinBufs {   // normalizeAlphas scratch, [M] each
+  unsigned long long *uniq = nullptr, *total = nullptr, *hits = nullptr;
+  uint32_t *parent = nullptr, *root = nullptr, *root2 = nullptr, *ids = nullptr, *memb = nullptr, *head = nullptr,
+           *head_scan = nullptr, *start = nullptr;
+  double *proj = nullptr, *eff = nullptr;
+  uint8_t* bound = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+};
+
 struct sb_map_ctx {
   int device = 0;
   int n_sm = 0;
@@ -700,6 +710,7 @@ struct sb_map_ctx {
   Params p{};
   uint32_t batch_cap = 0, read_len_cap = 0, chunk = 0;
   int variant = 1;                   // 1 = warp kernels (map_kernels.cuh), 0 = serial-form kernels
+  int input_dev = 0;                 // sb_map_batch's read pointers are device pointers (bench: inputs resident in HBM)
   int fast_ok = 1;
   uint32_t k1_threads = 0, seed_blocks = 0, dp_blocks = 0;
   BatchBufs b{};                     // cand/score/task buffers: one chunk; outputs: whole batch
@@ -714,6 +725,11 @@ struct sb_map_ctx {
   double* d_fld = nullptr;
   FldView fld{};
   AggScratch agg;
+  FinBufs fin;
+  // multi-GPU: this rank's partial statistics on the host (sb_map_partial_get)
+  std::vector<double> hp_mass, hp_hist;
+  std::vector<uint64_t> hp_uniq, hp_total, hp_hits;
+  std::vector<uint32_t> hp_root;
   // online state (masses, FLD, effective lengths)
   OnlineState on;
   uint32_t M = 0, nf = 0;
@@ -723,6 +739,8 @@ struct sb_map_ctx {
   std::vector<double> h_fm_rel; std::vector<unsigned long long> h_tap_q;
   double* d_scratch_nf = nullptr;
   unsigned int h_bm = 0;
+  std::vector<double> init_tables;     // FLD tables of the prior (sb_map_reset)
+  std::vector<cudaEvent_t> ev_seed;    // pairs of events around the seed kernel of each chunk
   std::vector<double> h_proj, h_eff;
   std::vector<uint64_t> h_uniq, h_total;
   // eq-class store: one EqStore per processed batch, merged at finish
@@ -892,6 +910,14 @@ extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int d
     A(&o.mass, M); A(&o.prior, M); A(&o.log_eff, M); A(&o.hist, nf); A(&o.tot, 1); A(&o.cf, nf);
     A(&o.mass_acc, M); A(&o.fld_acc, nf); A(&o.mins, 2); A(&o.fm_rel, o.table_cap); A(&o.tap_q, (size_t)o.table_cap * 5);
     A(&c->d_scratch_nf, nf);
+    FinBufs& f = c->fin;
+    A(&f.uniq, M); A(&f.total, M); A(&f.hits, M); A(&f.parent, M); A(&f.root, M); A(&f.root2, M); A(&f.ids, M); A(&f.memb, M);
+    A(&f.head, M + 1); A(&f.head_scan, M + 1); A(&f.start, M + 1); A(&f.proj, M); A(&f.eff, M); A(&f.bound, M);
+    size_t tb = 0, tb2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, f.root, f.root2, f.ids, f.memb, (int)M, 0, 32, (cudaStream_t)0);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb2, f.head, f.head_scan, (int)M + 1, (cudaStream_t)0);
+    f.tmp_bytes = std::max(tb, tb2);
+    if (rc == SB_OK && cudaMalloc(&f.tmp, f.tmp_bytes) != cudaSuccess) rc = SB_ERR_NOMEM;
   }
   A(&c->d_overflow, (size_t)c->seed_blocks * SEED_WARPS * MAXSEEDS);
   A(&c->d_next_task, 8); A(&c->d_full_dp, 1);
@@ -902,7 +928,7 @@ extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int d
   // per batch (outputs)
   A(&b.n_aln, B); A(&b.tid, B * cap); A(&b.score, B * cap); A(&b.prob, B * cap); A(&b.pos, B * cap);
   A(&b.mate_pos, B * cap); A(&b.flags, B * cap); A(&b.flen, B * cap); A(&b.label, B * 2 * cap); A(&b.weight, B * cap);
-  std::vector<double> t;
+  std::vector<double>& t = c->init_tables;
   build_fld_host(p, t);
   A(&c->d_fld, (size_t)4 * (p.max_frag_len + 1));
   if (rc == SB_OK) rc = agg_reserve(c->agg, B);
@@ -937,10 +963,13 @@ extern "C" void sb_map_destroy(sb_map_ctx* c) {
                   b.bs_tid, b.bs_score, b.bs_idx, b.jh, b.ctr, c->d_in[0][0], c->d_in[0][1], c->d_in[1][0], c->d_in[1][1],
                   c->d_fld, c->pr.bits, c->pr.nmask, c->d_overflow, c->d_next_task, c->d_full_dp, b.lp,
                   c->on.mass, c->on.prior, c->on.log_eff, c->on.hist, c->on.tot, c->on.cf, c->on.mass_acc, c->on.fld_acc,
-                  c->on.mins, c->on.fm_rel, c->on.tap_q, c->d_scratch_nf, c->d_list_int, c->d_list_edge, c->d_list_n};
+                  c->on.mins, c->on.fm_rel, c->on.tap_q, c->d_scratch_nf, c->d_list_int, c->d_list_edge, c->d_list_n,
+                  c->fin.uniq, c->fin.total, c->fin.hits, c->fin.parent, c->fin.root, c->fin.root2, c->fin.ids, c->fin.memb,
+                  c->fin.head, c->fin.head_scan, c->fin.start, c->fin.proj, c->fin.eff, c->fin.bound, c->fin.tmp};
   for (void* p : ptrs) cudaFree(p);
   c->agg.free_all();
   for (auto& s : c->stores) s.free_all();
+  for (cudaEvent_t e : c->ev_seed) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   for (int s = 0; s < 2; ++s) { if (c->ev_in[s]) cudaEventDestroy(c->ev_in[s]); if (c->ev_free[s]) cudaEventDestroy(c->ev_free[s]); }
@@ -953,6 +982,7 @@ extern "C" int sb_map_set_option(sb_map_ctx* c, const char* key, int64_t value) 
   if (!c || !key) { sb::set_error("null argument"); return SB_ERR_INVALID; }
   if (!strcmp(key, "variant")) { c->variant = (int)value; return SB_OK; }
   if (!strcmp(key, "fast_dp")) { c->fast_ok = value ? 1 : 0; return SB_OK; }
+  if (!strcmp(key, "input_on_device")) { c->input_dev = value ? 1 : 0; return SB_OK; }
   if (!strcmp(key, "chunk")) {   // reads per pipeline chunk (<= the size the context was created with)
     const uint32_t mx = (uint32_t)std::min<size_t>(c->batch_cap, 65536);
     if (value < 1 || value > (int64_t)mx) { sb::set_error("chunk must be in 1..%u", mx); return SB_ERR_INVALID; }
@@ -1040,15 +1070,19 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
   for (uint32_t ch = 0; ch < nch; ++ch) {
     const uint32_t c0 = ch * CH, cn = std::min(CH, n - c0);
     const int s = (int)(ch & 1);
-    if (ch >= 2) SB_CUDA(cudaStreamWaitEvent(cs, c->ev_free[s], 0));
-    SB_CUDA(cudaMemcpyAsync(c->d_in[s][0], left + (size_t)c0 * L, (size_t)cn * L, cudaMemcpyHostToDevice, cs));
-    SB_CUDA(cudaMemcpyAsync(c->d_in[s][1], right + (size_t)c0 * L, (size_t)cn * L, cudaMemcpyHostToDevice, cs));
-    SB_CUDA(cudaEventRecord(c->ev_in[s], cs));
-    SB_CUDA(cudaStreamWaitEvent(st, c->ev_in[s], 0));
-    SB_CUDA(cudaMemsetAsync(c->b.n_tasks, 0, 16, st));
-    SB_CUDA(cudaMemsetAsync(c->d_next_task, 0, 32, st));
     const uint8_t* dl = c->d_in[s][0];
     const uint8_t* dr = c->d_in[s][1];
+    if (c->input_dev) {
+      dl = left + (size_t)c0 * L; dr = right + (size_t)c0 * L;
+    } else {
+      if (ch >= 2) SB_CUDA(cudaStreamWaitEvent(cs, c->ev_free[s], 0));
+      SB_CUDA(cudaMemcpyAsync(c->d_in[s][0], left + (size_t)c0 * L, (size_t)cn * L, cudaMemcpyHostToDevice, cs));
+      SB_CUDA(cudaMemcpyAsync(c->d_in[s][1], right + (size_t)c0 * L, (size_t)cn * L, cudaMemcpyHostToDevice, cs));
+      SB_CUDA(cudaEventRecord(c->ev_in[s], cs));
+      SB_CUDA(cudaStreamWaitEvent(st, c->ev_in[s], 0));
+    }
+    SB_CUDA(cudaMemsetAsync(c->b.n_tasks, 0, 16, st));
+    SB_CUDA(cudaMemsetAsync(c->d_next_task, 0, 32, st));
     // outputs of this chunk inside the batch-wide arrays
     BatchBufs bc = c->b;
     bc.n_aln += c0; bc.tid += (size_t)c0 * cap; bc.score += (size_t)c0 * cap; bc.prob += (size_t)c0 * cap;
@@ -1064,13 +1098,17 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
       SeedOut so{bc.n_l, bc.n_r, bc.cand_l, bc.cand_r, bc.n_tasks, bc.tasks, c->d_overflow, bc.ctr};
       DpIo io{bc.n_tasks, bc.tasks, bc.cand_l, bc.cand_r, bc.score_l, bc.score_r, c->d_next_task, c->d_next_task + 4,
               c->d_list_int, c->d_list_edge, c->d_list_n, c->d_full_dp};
+      while (c->ev_seed.size() < 2 * (size_t)(ch + 1)) { cudaEvent_t e; cudaEventCreate(&e); c->ev_seed.push_back(e); }
+      SB_CUDA(cudaEventRecord(c->ev_seed[2 * ch], st));
       if (c->read_len_cap <= 128) {
         k_seed_chain_w<2><<<c->seed_blocks, SeedCfg<2>::WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
+        SB_CUDA(cudaEventRecord(c->ev_seed[2 * ch + 1], st));
         k_dp_classify<4><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, L, c->fast_ok, io);
         k_dp_pair<4><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, L, io);
         k_dp_general<4><<<c->n_sm, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, io);
       } else {
         k_seed_chain_w<4><<<c->seed_blocks, SeedCfg<4>::WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
+        SB_CUDA(cudaEventRecord(c->ev_seed[2 * ch + 1], st));
         k_dp_classify<8><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, L, c->fast_ok, io);
         k_dp_pair<8><<<c->n_sm * 2, 256, 0, st>>>(ix, p, c->pr, L, io);
         k_dp_general<8><<<c->n_sm, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, io);
@@ -1127,6 +1165,14 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
     stats->device_ms = c->last_ms; stats->gpu_launches = c->launches;
     stats->n_batch_classes = es.n;
     stats->full_dp = full_dp;
+    stats->seed_kernel_ms = 0; stats->seed_kernel_launches = 0;
+    if (c->variant != 0)
+      for (uint32_t ch = 0; ch < nch; ++ch) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->ev_seed[2 * ch], c->ev_seed[2 * ch + 1]) == cudaSuccess) {
+          stats->seed_kernel_ms += ms; stats->seed_kernel_launches++;
+        }
+      }
   }
   return SB_OK;
 }
@@ -1149,6 +1195,50 @@ extern "C" int sb_map_last_alignments(sb_map_ctx* c, uint32_t n, uint32_t* n_aln
   if (flen) SB_CUDA(cudaMemcpy(flen, b.flen, n * cap * 4, cudaMemcpyDeviceToHost));
   if (label) SB_CUDA(cudaMemcpy(label, b.label, n * 2 * cap * 4, cudaMemcpyDeviceToHost));
   if (weight) SB_CUDA(cudaMemcpy(weight, b.weight, n * cap * 8, cudaMemcpyDeviceToHost));
+  return SB_OK;
+}
+
+// per-transcript counts and the transcript clusters of this context's classes (device arrays in c->fin)
+static int finish_stats(sb_map_ctx* c, const EqStore& merged) {
+  cudaStream_t st = c->stream;
+  const uint32_t M = c->M;
+  if (!M) return SB_OK;
+  FinBufs& f = c->fin;
+  SB_CUDA(cudaMemsetAsync(f.uniq, 0, (size_t)M * 8, st)); SB_CUDA(cudaMemsetAsync(f.total, 0, (size_t)M * 8, st));
+  SB_CUDA(cudaMemsetAsync(f.hits, 0, (size_t)M * 8, st));
+  k_iota<<<nblk(M, 256), 256, 0, st>>>(M, f.parent);
+  if (merged.n)
+    k_cls_accumulate<<<nblk(merged.n, 256), 256, 0, st>>>(merged.n, merged.loff, merged.woff, merged.labels, merged.counts,
+                                                          f.uniq, f.total, f.hits, f.parent);
+  k_roots<<<nblk(M, 256), 256, 0, st>>>(M, f.parent, f.root, f.ids);
+  c->launches += 3;
+  return SB_OK;
+}
+// clusters from f.root, projection with c->on.mass and f.{hits,uniq,total}; results to the host vectors
+static int finish_project(sb_map_ctx* c) {
+  cudaStream_t st = c->stream;
+  const uint32_t M = c->M;
+  c->h_proj.assign(M, 0.0); c->h_eff.assign(M, 0.0); c->h_uniq.assign(M, 0); c->h_total.assign(M, 0);
+  if (!M) return SB_OK;
+  FinBufs& f = c->fin;
+  size_t t2 = f.tmp_bytes;
+  SB_CUDA(cub::DeviceRadixSort::SortPairs(f.tmp, t2, f.root, f.root2, f.ids, f.memb, (int)M, 0, 32, st));   // stable: members ascending
+  k_cluster_heads<<<nblk((uint64_t)M + 1, 256), 256, 0, st>>>(M, f.root2, f.head);
+  t2 = f.tmp_bytes;
+  SB_CUDA(cub::DeviceScan::ExclusiveSum(f.tmp, t2, f.head, f.head_scan, (int)M + 1, st));
+  uint32_t ncl = 0;
+  SB_CUDA(cudaMemcpyAsync(&ncl, f.head_scan + M, 4, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  k_cluster_starts<<<nblk(M, 256), 256, 0, st>>>(M, f.head, f.head_scan, f.start);
+  k_cluster_project<<<nblk((uint64_t)ncl * 32, 256), 256, 0, st>>>(ncl, M, f.start, f.memb, c->on.mass, f.hits, f.uniq,
+                                                                   f.total, f.proj, f.bound);
+  k_exp_vec<<<nblk(M, 256), 256, 0, st>>>(M, c->on.log_eff, f.eff);     // CollapsedEMOptimizer.cpp:782-784
+  c->launches += 7;
+  SB_CUDA(cudaMemcpyAsync(c->h_proj.data(), f.proj, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(c->h_eff.data(), f.eff, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(c->h_uniq.data(), f.uniq, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(c->h_total.data(), f.total, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
   return SB_OK;
 }
 
@@ -1190,59 +1280,13 @@ extern "C" int sb_map_finish(sb_map_ctx* c, sb_map_result* out) {
   }
   // ---- normalizeAlphas (SalmonUtils.cpp:461-529): initial alphas for the optimiser, plus what optimize() reads
   //      per transcript (effective length, unique count)
-  {
-    const uint32_t M = c->M;
-    if (!c->burned_in) {   // burn-in never reached: effective lengths from the observed FLD (SalmonQuantify.cpp:2734-2738)
-      k_online_correction<<<1, 32, 0, st>>>(c->nf, c->on, 0, c->d_scratch_nf, nullptr, nullptr);
-      if (M) k_online_eff_len<<<nblk(M, 256), 256, 0, st>>>(M, c->nf, c->index->d_tx_off, c->on.cf, c->on.log_eff);
-      c->launches += 2;
-    }
-    c->h_proj.assign(M, 0.0); c->h_eff.assign(M, 0.0); c->h_uniq.assign(M, 0); c->h_total.assign(M, 0);
-    if (M) {
-      unsigned long long *uniq = nullptr, *total = nullptr, *hits = nullptr;
-      uint32_t *parent = nullptr, *root = nullptr, *root2 = nullptr, *ids = nullptr, *memb = nullptr, *head = nullptr,
-               *head_scan = nullptr, *start = nullptr;
-      double *proj = nullptr, *eff = nullptr;
-      uint8_t* bound = nullptr;
-      void* tmp = nullptr;
-      SB_TRY(dmalloc(&uniq, M)); SB_TRY(dmalloc(&total, M)); SB_TRY(dmalloc(&hits, M)); SB_TRY(dmalloc(&parent, M));
-      SB_TRY(dmalloc(&root, M)); SB_TRY(dmalloc(&root2, M)); SB_TRY(dmalloc(&ids, M)); SB_TRY(dmalloc(&memb, M));
-      SB_TRY(dmalloc(&head, (size_t)M + 1)); SB_TRY(dmalloc(&head_scan, (size_t)M + 1)); SB_TRY(dmalloc(&start, (size_t)M + 1));
-      SB_TRY(dmalloc(&proj, M)); SB_TRY(dmalloc(&eff, M)); SB_TRY(dmalloc(&bound, M));
-      SB_CUDA(cudaMemsetAsync(uniq, 0, (size_t)M * 8, st)); SB_CUDA(cudaMemsetAsync(total, 0, (size_t)M * 8, st));
-      SB_CUDA(cudaMemsetAsync(hits, 0, (size_t)M * 8, st));
-      k_iota<<<nblk(M, 256), 256, 0, st>>>(M, parent);
-      if (merged.n)
-        k_cls_accumulate<<<nblk(merged.n, 256), 256, 0, st>>>(merged.n, merged.loff, merged.woff, merged.labels,
-                                                              merged.counts, uniq, total, hits, parent);
-      k_roots<<<nblk(M, 256), 256, 0, st>>>(M, parent, root, ids);
-      size_t tb = 0, tb2 = 0;
-      cub::DeviceRadixSort::SortPairs(nullptr, tb, root, root2, ids, memb, (int)M, 0, 32, st);
-      cub::DeviceScan::ExclusiveSum(nullptr, tb2, head, head_scan, (int)M + 1, st);
-      tb = std::max(tb, tb2);
-      SB_CUDA(cudaMalloc(&tmp, tb));
-      size_t t2 = tb;
-      SB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t2, root, root2, ids, memb, (int)M, 0, 32, st));   // stable: members ascending
-      k_cluster_heads<<<nblk((uint64_t)M + 1, 256), 256, 0, st>>>(M, root2, head);
-      t2 = tb;
-      SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, t2, head, head_scan, (int)M + 1, st));
-      uint32_t ncl = 0;
-      SB_CUDA(cudaMemcpyAsync(&ncl, head_scan + M, 4, cudaMemcpyDeviceToHost, st));
-      SB_CUDA(cudaStreamSynchronize(st));
-      k_cluster_starts<<<nblk(M, 256), 256, 0, st>>>(M, head, head_scan, start);
-      k_cluster_project<<<nblk((uint64_t)ncl * 32, 256), 256, 0, st>>>(ncl, M, start, memb, c->on.mass, hits, uniq, total,
-                                                                       proj, bound);
-      k_exp_vec<<<nblk(M, 256), 256, 0, st>>>(M, c->on.log_eff, eff);     // CollapsedEMOptimizer.cpp:782-784
-      c->launches += 10;
-      SB_CUDA(cudaMemcpyAsync(c->h_proj.data(), proj, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
-      SB_CUDA(cudaMemcpyAsync(c->h_eff.data(), eff, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
-      SB_CUDA(cudaMemcpyAsync(c->h_uniq.data(), uniq, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
-      SB_CUDA(cudaMemcpyAsync(c->h_total.data(), total, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
-      SB_CUDA(cudaStreamSynchronize(st));
-      void* fr[] = {uniq, total, hits, parent, root, root2, ids, memb, head, head_scan, start, proj, eff, bound, tmp};
-      for (void* q : fr) cudaFree(q);
-    }
+  if (!c->burned_in) {   // burn-in never reached: effective lengths from the observed FLD (SalmonQuantify.cpp:2734-2738)
+    k_online_correction<<<1, 32, 0, st>>>(c->nf, c->on, 0, c->d_scratch_nf, nullptr, nullptr);
+    if (c->M) k_online_eff_len<<<nblk(c->M, 256), 256, 0, st>>>(c->M, c->nf, c->index->d_tx_off, c->on.cf, c->on.log_eff);
+    c->launches += 2;
   }
+  SB_TRY(finish_stats(c, merged));
+  SB_TRY(finish_project(c));
   // to host (data movement only): drop the empty-label class, split label into tids | bins
   const int binned = c->p.range_bins > 0;
   std::vector<uint64_t> loff(merged.n + 1), woff(merged.n + 1), counts(merged.n);
@@ -1280,6 +1324,107 @@ extern "C" int sb_map_finish(sb_map_ctx* c, sb_map_result* out) {
   out->n_txps = c->M;
   out->projected_counts = c->h_proj.data(); out->eff_len = c->h_eff.data();
   out->unique_counts = c->h_uniq.data(); out->total_counts = c->h_total.data();
+  return SB_OK;
+}
+
+// ---- multi-GPU: reads are sharded over ranks, every rank keeps its own class table; what
+// normalizeAlphas needs globally -- transcript masses, the FLD, unique / total / cluster-hit counts and the
+// transcript clusters -- is reduced over the ranks ONCE at the end of mapping by the host layer (M-sized vectors).
+__global__ void k_union_roots(uint32_t M, const uint32_t* __restrict__ root, uint32_t* parent) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M) return;
+  uint32_t a = t, b = root[t];
+  for (;;) {
+    a = uf_find(parent, a); b = uf_find(parent, b);
+    if (a == b) break;
+    if (a < b) { const uint32_t x = a; a = b; b = x; }
+    if (atomicCAS(parent + a, a, b) == a) break;
+  }
+}
+
+// this rank's statistics after sb_map_finish (host arrays owned by the context)
+extern "C" int sb_map_partial_get(sb_map_ctx* c, sb_map_partial* out) {
+  if (!c || !out) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  SB_CUDA(cudaSetDevice(c->device));
+  const uint32_t M = c->M, nf = c->nf;
+  c->hp_mass.assign(M, 0.0); c->hp_hist.assign((size_t)nf + 1, 0.0); c->hp_uniq.assign(M, 0); c->hp_total.assign(M, 0);
+  c->hp_hits.assign(M, 0); c->hp_root.assign(M, 0);
+  unsigned int mins[2] = {0, 0};
+  if (M) {
+    SB_CUDA(cudaMemcpy(c->hp_mass.data(), c->on.mass, (size_t)M * 8, cudaMemcpyDeviceToHost));
+    SB_CUDA(cudaMemcpy(c->hp_uniq.data(), c->fin.uniq, (size_t)M * 8, cudaMemcpyDeviceToHost));
+    SB_CUDA(cudaMemcpy(c->hp_total.data(), c->fin.total, (size_t)M * 8, cudaMemcpyDeviceToHost));
+    SB_CUDA(cudaMemcpy(c->hp_hits.data(), c->fin.hits, (size_t)M * 8, cudaMemcpyDeviceToHost));
+    SB_CUDA(cudaMemcpy(c->hp_root.data(), c->fin.root, (size_t)M * 4, cudaMemcpyDeviceToHost));
+  }
+  SB_CUDA(cudaMemcpy(c->hp_hist.data(), c->on.hist, (size_t)nf * 8, cudaMemcpyDeviceToHost));
+  SB_CUDA(cudaMemcpy(c->hp_hist.data() + nf, c->on.tot, 8, cudaMemcpyDeviceToHost));
+  SB_CUDA(cudaMemcpy(mins, c->on.mins, 8, cudaMemcpyDeviceToHost));
+  out->n_txps = M; out->n_fld = nf; out->mass = c->hp_mass.data(); out->fld_hist = c->hp_hist.data();
+  out->fld_tot = c->hp_hist[nf]; out->fld_prior_hist = c->init_tables.data() + (size_t)4 * nf;
+  out->fld_prior_tot = c->init_tables[(size_t)5 * nf]; out->fld_min = mins[1];
+  out->unique_counts = c->hp_uniq.data(); out->total_counts = c->hp_total.data(); out->cluster_hits = c->hp_hits.data();
+  out->cluster_root = c->hp_root.data(); out->assigned = c->frag_counter;
+  return SB_OK;
+}
+
+// normalizeAlphas with the statistics reduced over all ranks: g holds the GLOBAL masses / FLD / counts, roots_all the
+// n_ranks cluster-root arrays (n_ranks x n_txps).  Effective lengths are recomputed from the global FLD.
+extern "C" int sb_map_project_global(sb_map_ctx* c, const sb_map_partial* g, uint32_t n_ranks, const uint32_t* roots_all,
+                                     sb_map_result* out) {
+  if (!c || !g || !out || (n_ranks && !roots_all)) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  if (g->n_txps != c->M || g->n_fld != c->nf) { sb::set_error("sb_map_project_global: size mismatch"); return SB_ERR_INVALID; }
+  SB_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const uint32_t M = c->M, nf = c->nf;
+  if (M) {
+    SB_CUDA(cudaMemcpyAsync(c->on.mass, g->mass, (size_t)M * 8, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(c->fin.uniq, g->unique_counts, (size_t)M * 8, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(c->fin.total, g->total_counts, (size_t)M * 8, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(c->fin.hits, g->cluster_hits, (size_t)M * 8, cudaMemcpyHostToDevice, st));
+  }
+  SB_CUDA(cudaMemcpyAsync(c->on.hist, g->fld_hist, (size_t)nf * 8, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(c->on.tot, &g->fld_tot, 8, cudaMemcpyHostToDevice, st));
+  const unsigned int mins[2] = {g->fld_min, g->fld_min};
+  SB_CUDA(cudaMemcpyAsync(c->on.mins, mins, 8, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  if (M) {
+    k_iota<<<nblk(M, 256), 256, 0, st>>>(M, c->fin.parent);
+    for (uint32_t r = 0; r < n_ranks; ++r) {
+      SB_CUDA(cudaMemcpyAsync(c->fin.root, roots_all + (size_t)r * M, (size_t)M * 4, cudaMemcpyHostToDevice, st));
+      k_union_roots<<<nblk(M, 256), 256, 0, st>>>(M, c->fin.root, c->fin.parent);
+    }
+    k_roots<<<nblk(M, 256), 256, 0, st>>>(M, c->fin.parent, c->fin.root, c->fin.ids);
+  }
+  k_online_correction<<<1, 32, 0, st>>>(nf, c->on, 0, c->d_scratch_nf, nullptr, nullptr);
+  if (M) k_online_eff_len<<<nblk(M, 256), 256, 0, st>>>(M, nf, c->index->d_tx_off, c->on.cf, c->on.log_eff);
+  c->launches += 4 + n_ranks;
+  SB_TRY(finish_project(c));
+  out->n_txps = M;
+  out->projected_counts = c->h_proj.data(); out->eff_len = c->h_eff.data();
+  out->unique_counts = c->h_uniq.data(); out->total_counts = c->h_total.data();
+  return SB_OK;
+}
+
+// forget everything mapped so far (class tables, online state, counters): a fresh context without re-allocating
+extern "C" int sb_map_reset(sb_map_ctx* c) {
+  if (!c) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  SB_CUDA(cudaSetDevice(c->device));
+  SB_CUDA(cudaDeviceSynchronize());
+  for (auto& s : c->stores) s.free_all();
+  c->stores.clear();
+  c->frag_counter = 0; c->frags_seen = 0; c->timestep = 0; c->burned_in = 0; c->full_dp_total = 0;
+  memset(&c->totals, 0, sizeof(c->totals));
+  const std::vector<double>& t = c->init_tables;
+  SB_CUDA(cudaMemcpy(c->d_fld, t.data(), (size_t)4 * c->nf * 8, cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMemcpy(c->on.hist, t.data() + (size_t)4 * c->nf, (size_t)c->nf * 8, cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMemcpy(c->on.tot, t.data() + (size_t)5 * c->nf, 8, cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMemset(c->on.mass_acc, 0, std::max<uint32_t>(c->M, 1) * 8));
+  SB_CUDA(cudaMemset(c->on.fld_acc, 0, (size_t)c->nf * 8));
+  const unsigned int mins[2] = {c->p.max_frag_len, c->p.max_frag_len};
+  SB_CUDA(cudaMemcpy(c->on.mins, mins, 8, cudaMemcpyHostToDevice));
+  if (c->M) k_online_init<<<nblk(c->M, 256), 256>>>(c->M, c->index->d_tx_off, c->on.mass, c->on.prior, c->on.log_eff);
+  SB_CUDA(cudaDeviceSynchronize());
   return SB_OK;
 }
 

@@ -1,12 +1,14 @@
-"""torchrun -> per-rank class shards, alpha all-reduced per iteration; rank 0 compares the
-result with the oracle run on the union of the shards (same iterations)."""
+"""torchrun --nproc-per-node N: (1) EM: per-rank class shards, alpha all-reduced per iteration; rank 0 compares with
+the oracle on the union of the shards.  (2) Stage A + quant: reads sharded over the ranks, end-of-mapping reductions
+(salmon_b200.dist), sharded VBEM; rank 0 compares with a single-GPU run over all reads."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch, torch.distributed as dist
 from salmon_b200 import EMContext, default_params, _capi
-from salmon_b200._capi import EqClasses
-from salmon_b200.synth import synth_eq, shard_classes
+from salmon_b200._capi import EqClasses, Index
+from salmon_b200.synth import synth_eq, shard_classes, synth_txome, synth_reads_fast
+from salmon_b200.quant import quant_reads
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local); dist.init_process_group("nccl", rank=rank, world_size=world)
 eq, proj, eff, uniq = synth_eq(seed=5, C=80000, M=30000, total_count=3_000_000)
@@ -26,7 +28,6 @@ for vbem in (1, 0):
             good = np.allclose(alpha, ref, rtol=1e-9, atol=1e-9) and st.iters == rst.iters
             ok_all &= bool(good)
             print(f"world {world} vbem {vbem} k {k}: iters {st.iters} max rel err {err:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
-# run to convergence
 p = default_params()
 alpha, st, ok = ctx.optimize(sh, p, proj, eff, uniq)
 if rank == 0:
@@ -34,5 +35,27 @@ if rank == 0:
     ref, rst = O.em_optimize(eq, proj, eff, uniq, p)
     good = st.iters == rst.iters and np.allclose(alpha, ref, rtol=1e-9, atol=1e-9)
     ok_all &= bool(good)
-    print(f"converged run: iters {st.iters} vs {rst.iters} -> {'OK' if good else 'FAIL'}; ALL {'OK' if ok_all else 'FAIL'}", flush=True)
+    print(f"converged run: iters {st.iters} vs {rst.iters} -> {'OK' if good else 'FAIL'}", flush=True)
+ctx.close()
+# ---- Stage A + quant, reads sharded
+txps, _ = synth_txome(seed=51, n_genes=800)
+left, right, truth = synth_reads_fast(txps, seed=52, n=120_000)
+idx = Index(txps)
+sl = slice(rank, None, world)
+out = quant_reads(idx, left[sl], right[sl], device=local, batch=32768, dist=dist)
+if rank == 0:
+    one = quant_reads(idx, left, right, device=local, batch=32768)
+    M = len(txps)
+    g1 = out["n_mapped"] == one["n_mapped"]
+    g2 = np.array_equal(out["unique_counts"], one["unique_counts"])
+    g3 = abs(out["alpha"].sum() - one["alpha"].sum()) < 1e-6 * one["alpha"].sum()
+    r = np.corrcoef(out["alpha"], one["alpha"])[0, 1]
+    rel = np.abs(out["tpm"] - one["tpm"]) / np.maximum(one["tpm"], 1.0)
+    true_counts = np.bincount(truth["tid"][truth["tid"] >= 0], minlength=M).astype(float)
+    rt = np.corrcoef(out["alpha"], true_counts)[0, 1]
+    good = g1 and g2 and g3 and r > 0.9999 and rt > 0.97
+    ok_all &= bool(good)
+    print(f"stage A sharded over {world}: mapped equal {g1}, unique counts equal {g2}, sum alpha equal {g3}, "
+          f"corr(alpha sharded, alpha single) {r:.6f}, median rel TPM diff {np.median(rel):.2e}, corr vs truth {rt:.4f} "
+          f"-> {'OK' if good else 'FAIL'}; ALL {'OK' if ok_all else 'FAIL'}", flush=True)
 dist.destroy_process_group()

@@ -246,3 +246,25 @@ def test_variants_agree_at_scale():
     for x, y in zip(outs[0][1], outs[1][1]):
         assert x[0] == y[0] and x[3] == y[3]
         assert np.array_equal(x[2].view(np.uint64), y[2].view(np.uint64))
+
+
+def test_quant_pipeline_end_to_end(tmp_path):
+    """config-0 style plumbing + accuracy: reads with known origin -> map -> classes -> normalizeAlphas -> VBEM -> TPM;
+    estimated read counts track the simulated truth, files are written in the reference's layouts."""
+    from salmon_b200.quant import quant_reads
+    txps, _ = synth_txome(seed=41, n_genes=150)
+    left, right, truth = synth_reads(txps, seed=42, n=30000)
+    idx = Index(txps)
+    out = quant_reads(idx, left, right, batch=8192, out_dir=str(tmp_path), dump_eq_weights=True)
+    M = len(txps)
+    true_counts = np.bincount(truth["tid"][truth["tid"] >= 0], minlength=M).astype(float)
+    assert abs(out["alpha"].sum() - out["n_mapped"]) < 1e-6 * out["n_mapped"]
+    assert out["n_mapped"] >= 0.97 * (truth["tid"] >= 0).sum()
+    r = np.corrcoef(out["alpha"], true_counts)[0, 1]
+    assert r > 0.97, r
+    assert abs(out["tpm"].sum() - 1e6) < 1e-3
+    lines = (tmp_path / "quant.sf").read_text().splitlines()
+    assert lines[0].split("\t") == ["Name", "Length", "EffectiveLength", "TPM", "NumReads"] and len(lines) == M + 1
+    import gzip
+    eqt = gzip.open(tmp_path / "aux_info" / "eq_classes.txt.gz", "rt").read().splitlines()
+    assert int(eqt[0]) == M and int(eqt[1]) == len(out["classes"]["counts"])
