@@ -328,9 +328,15 @@ __global__ void k_assign(IndexView ix, Params p, FldView fld, int useAux, int bu
       int32_t sc[32], pi[32], pt[32], b1[32], b2[32], b3[32];
       Joint jh[32];
       double lp[32];
-      assign_read(ix, p, fld, useAux != 0, burnedIn != 0, b.cand_l + (size_t)r * MAXCAND, nl,
-                  b.cand_r + (size_t)r * MAXCAND, nr, b.score_l + (size_t)r * MAXCAND,
-                  b.score_r + (size_t)r * MAXCAND, L, sc, pi, pt, b1, b2, b3, jh, o, ctr, &on, chunk_first_read + r, lp);
+      // candidates and their scores first, with independent loads (the logic below re-reads them many times)
+      Cand lcl[32], rcl[32];
+      int32_t sl[32], sr[32];
+      const Cand* gl = b.cand_l + (size_t)r * MAXCAND;
+      const Cand* gr = b.cand_r + (size_t)r * MAXCAND;
+      for (uint32_t a = 0; a < nl; ++a) { lcl[a] = gl[a]; sl[a] = b.score_l[(size_t)r * MAXCAND + a]; }
+      for (uint32_t a = 0; a < nr; ++a) { rcl[a] = gr[a]; sr[a] = b.score_r[(size_t)r * MAXCAND + a]; }
+      assign_read(ix, p, fld, useAux != 0, burnedIn != 0, lcl, nl, rcl, nr, sl, sr, L, sc, pi, pt, b1, b2, b3, jh, o, ctr,
+                  &on, chunk_first_read + r, lp);
     } else {
       const size_t so = (size_t)tid0 * cap;
       assign_read(ix, p, fld, useAux != 0, burnedIn != 0, b.cand_l + (size_t)r * MAXCAND, nl,
@@ -1098,16 +1104,19 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
       SeedOut so{bc.n_l, bc.n_r, bc.cand_l, bc.cand_r, bc.n_tasks, bc.tasks, c->d_overflow, bc.ctr};
       DpIo io{bc.n_tasks, bc.tasks, bc.cand_l, bc.cand_r, bc.score_l, bc.score_r, c->d_next_task, c->d_next_task + 4,
               c->d_list_int, c->d_list_edge, c->d_list_n, c->d_full_dp};
+      const uint32_t npos = (L - p.k) / p.stride + 1 + (((L - p.k) % p.stride) ? 1u : 0u);   // seed positions per mate
       while (c->ev_seed.size() < 2 * (size_t)(ch + 1)) { cudaEvent_t e; cudaEventCreate(&e); c->ev_seed.push_back(e); }
       SB_CUDA(cudaEventRecord(c->ev_seed[2 * ch], st));
       if (c->read_len_cap <= 128) {
-        k_seed_chain_w<2><<<c->seed_blocks, SeedCfg<2>::WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
+        if (npos <= 32) k_seed_chain_w<2, 1><<<c->seed_blocks, SeedCfg<2>::WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
+        else k_seed_chain_w<2, 2><<<c->seed_blocks, SeedCfg<2>::WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
         SB_CUDA(cudaEventRecord(c->ev_seed[2 * ch + 1], st));
         k_dp_classify<4><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, L, c->fast_ok, io);
         k_dp_pair<4><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, L, io);
         k_dp_general<4><<<c->n_sm, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, io);
       } else {
-        k_seed_chain_w<4><<<c->seed_blocks, SeedCfg<4>::WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
+        if (npos <= 32) k_seed_chain_w<4, 1><<<c->seed_blocks, SeedCfg<4>::WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
+        else k_seed_chain_w<4, 2><<<c->seed_blocks, SeedCfg<4>::WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
         SB_CUDA(cudaEventRecord(c->ev_seed[2 * ch + 1], st));
         k_dp_classify<8><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, L, c->fast_ok, io);
         k_dp_pair<8><<<c->n_sm * 2, 256, 0, st>>>(ix, p, c->pr, L, io);

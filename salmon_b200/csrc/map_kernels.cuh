@@ -94,6 +94,76 @@ __device__ __forceinline__ bool cand_beats(uint64_t a, uint64_t b) {
   return (a >> 9) < (b >> 9);
 }
 
+// general path of warp_mate_candidates: every seed becomes a key, bitonic sort of all of them
+template <int RD>
+__device__ __noinline__ void seeds_sort_all(const IndexView& ix, uint32_t span, const uint32_t (&off)[RD],
+                                            const uint32_t (&cnt)[RD], const uint32_t (&meta)[RD],
+                                            const uint32_t (&excl)[RD], const uint32_t (&tot)[RD], uint32_t T,
+                                            uint64_t* keys, uint32_t lane) {
+    uint32_t n2 = 32;
+    while (n2 < T) n2 <<= 1;
+    uint32_t carry = 0;
+#pragma unroll
+    for (int rd = 0; rd < RD; ++rd) {
+      for (uint32_t it = 0; it < tot[rd]; it += 32) {
+        const uint32_t item = it + lane;
+        uint32_t lo = 0;
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1) {
+          const uint32_t e = __shfl_sync(0xffffffffu, excl[rd], lo + st);
+          if (e <= item) lo += st;
+        }
+        const uint32_t o_off = __shfl_sync(0xffffffffu, off[rd], lo);
+        const uint32_t o_excl = __shfl_sync(0xffffffffu, excl[rd], lo);
+        const uint32_t o_meta = __shfl_sync(0xffffffffu, meta[rd], lo);
+        const uint32_t slot = carry + item;
+        if (item < tot[rd] && slot < (uint32_t)MAXSEEDS) {
+          const Posting po = ix.post[o_off + (item - o_excl)];
+          const uint32_t pos_i = o_meta & 0xffffu;
+          const uint32_t ori = (o_meta >> 16) ^ (po.tpos_rc >> 31);
+          const int32_t qpos = ori ? (int32_t)(span - pos_i) : (int32_t)pos_i;
+          keys[slot] = seed_key(po.tid, ori, (int32_t)(po.tpos_rc & 0x7fffffffu) - qpos, qpos);
+        }
+      }
+      carry += tot[rd];
+    }
+    for (uint32_t i = T + lane; i < n2; i += 32) keys[i] = EMPTY_KEY;
+    __syncwarp();
+    for (uint32_t k = 2; k <= n2; k <<= 1)
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t t = lane; t < (n2 >> 1); t += 32) {
+          const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          const uint32_t l = i | j;
+          const uint64_t a = keys[i], b = keys[l];
+          const bool asc = (i & k) == 0;
+          if ((a > b) == asc) { keys[i] = b; keys[l] = a; }
+        }
+        __syncwarp();
+      }
+}
+
+// more than MAXCAND survivors (rare): keep the MAXCAND best by (coverage desc, tid, ori, diag)
+__device__ __noinline__ void cands_top(const uint64_t* keys, uint32_t N, double thr, uint64_t* cands, uint32_t lane) {
+    // rare: keep the MAXCAND best by (coverage desc, tid, ori, diag); rank by counting who beats whom
+    uint32_t out = 0;
+    for (uint32_t base = 0; base < N; base += 32) {
+      const uint32_t i = base + lane;
+      const uint64_t w = (i < N) ? keys[i] : EMPTY_KEY;
+      const bool surv = (w != EMPTY_KEY) && ((double)cw_cov(w) >= thr);
+      uint32_t beaten_by = 0;
+      for (uint32_t q = 0; q < N; ++q) {
+        const uint64_t x = keys[q];
+        if (x != EMPTY_KEY && (double)cw_cov(x) >= thr && surv && cand_beats(x, w)) ++beaten_by;
+      }
+      const bool keep = surv && beaten_by < (uint32_t)MAXCAND;
+      const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+      const uint32_t rank = out + (uint32_t)__popc(bal & ((1u << lane) - 1));
+      if (keep) cands[rank] = w;
+      out += (uint32_t)__popc(bal);
+    }
+
+}
+
 constexpr uint32_t HS = 128;         // slots of the per-warp diagonal table (hash mode)
 template <int CW> struct SeedRegion { static constexpr uint32_t WORDS = HS + HS * CW + HS; };   // keys | masks | dense
 static_assert(SeedRegion<2>::WORDS == (uint32_t)SK, "sort mode reuses the table region");
@@ -104,7 +174,7 @@ static_assert(SeedRegion<2>::WORDS == (uint32_t)SK, "sort mode reuses the table 
 // diagonals are sorted (in registers when there are <= 32) and chained.  If the table overflows (repeats), the
 // general path sorts all seeds instead.  Both paths give what mate_candidates() (map_core.h) gives.
 //   region: SeedRegion<CW>::WORDS words of shared memory;  gkeys: MAXSEEDS words of global scratch (T > SK)
-template <int CW>   // coverage words: 2 for read_len <= 128, 4 for <= 256
+template <int CW, int RD>   // coverage words: 2 for read_len <= 128, 4 for <= 256; lookup rounds of 32 positions
 __device__ __forceinline__ uint32_t warp_mate_candidates(const IndexView& ix, const Params& p,
                                                          const uint64_t* __restrict__ rbits,   // shared: wpr words
                                                          const uint64_t* __restrict__ rnm,     // shared: mpr words
@@ -117,10 +187,10 @@ __device__ __forceinline__ uint32_t warp_mate_candidates(const IndexView& ix, co
   uint32_t npos = span / p.stride + 1;
   if (span % p.stride) ++npos;
   // ---- lookups: lane + 32*round = seed position index
-  uint32_t off[2], cnt[2], meta[2];   // meta: pos_i | read_rc << 16
+  uint32_t off[RD], cnt[RD], meta[RD];   // meta: pos_i | read_rc << 16
   uint32_t n_valid = 0;
 #pragma unroll
-  for (int rd = 0; rd < 2; ++rd) {
+  for (int rd = 0; rd < RD; ++rd) {
     const uint32_t li = lane + 32u * rd;
     off[rd] = 0; cnt[rd] = 0; meta[rd] = 0;
     if (li < npos) {
@@ -144,9 +214,9 @@ __device__ __forceinline__ uint32_t warp_mate_candidates(const IndexView& ix, co
     }
   }
   // ---- slots: exclusive prefix over the lookups in position order
-  uint32_t excl[2], tot[2];
+  uint32_t excl[RD], tot[RD];
 #pragma unroll
-  for (int rd = 0; rd < 2; ++rd) {
+  for (int rd = 0; rd < RD; ++rd) {
     uint32_t x = cnt[rd];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -156,7 +226,9 @@ __device__ __forceinline__ uint32_t warp_mate_candidates(const IndexView& ix, co
     tot[rd] = __shfl_sync(0xffffffffu, x, 31);
     excl[rd] = x - cnt[rd];
   }
-  const uint32_t total = tot[0] + tot[1];
+  uint32_t total = 0;
+#pragma unroll
+  for (int rd = 0; rd < RD; ++rd) total += tot[rd];
   const uint32_t T = total < (uint32_t)MAXSEEDS ? total : (uint32_t)MAXSEEDS;
   if (lane == 0) { ctr.postings += T; ctr.seeds += T; }
   ctr.lookups += n_valid;     // per lane; summed when the counters are flushed
@@ -176,7 +248,7 @@ __device__ __forceinline__ uint32_t warp_mate_candidates(const IndexView& ix, co
     bool failed = false;
     uint32_t carry = 0;
 #pragma unroll
-    for (int rd = 0; rd < 2; ++rd) {
+    for (int rd = 0; rd < RD; ++rd) {
       for (uint32_t it = 0; it < tot[rd]; it += 32) {
         const uint32_t item = it + lane;
         uint32_t lo = 0;
@@ -268,49 +340,11 @@ __device__ __forceinline__ uint32_t warp_mate_candidates(const IndexView& ix, co
         }
     }
   } else {
-    // ---- general path: all seeds as keys (shared memory up to SK, else global scratch), bitonic sort
+    // ---- general path (rare): all seeds as keys, bitonic sort -- kept out of line so that the common path stays
+    //      small in the instruction cache
     keys = (T <= (uint32_t)SK) ? region : gkeys;
     N = T;
-    uint32_t n2 = 32;
-    while (n2 < T) n2 <<= 1;
-    uint32_t carry = 0;
-#pragma unroll
-    for (int rd = 0; rd < 2; ++rd) {
-      for (uint32_t it = 0; it < tot[rd]; it += 32) {
-        const uint32_t item = it + lane;
-        uint32_t lo = 0;
-#pragma unroll
-        for (int st = 16; st > 0; st >>= 1) {
-          const uint32_t e = __shfl_sync(0xffffffffu, excl[rd], lo + st);
-          if (e <= item) lo += st;
-        }
-        const uint32_t o_off = __shfl_sync(0xffffffffu, off[rd], lo);
-        const uint32_t o_excl = __shfl_sync(0xffffffffu, excl[rd], lo);
-        const uint32_t o_meta = __shfl_sync(0xffffffffu, meta[rd], lo);
-        const uint32_t slot = carry + item;
-        if (item < tot[rd] && slot < (uint32_t)MAXSEEDS) {
-          const Posting po = ix.post[o_off + (item - o_excl)];
-          const uint32_t pos_i = o_meta & 0xffffu;
-          const uint32_t ori = (o_meta >> 16) ^ (po.tpos_rc >> 31);
-          const int32_t qpos = ori ? (int32_t)(span - pos_i) : (int32_t)pos_i;
-          keys[slot] = seed_key(po.tid, ori, (int32_t)(po.tpos_rc & 0x7fffffffu) - qpos, qpos);
-        }
-      }
-      carry += tot[rd];
-    }
-    for (uint32_t i = T + lane; i < n2; i += 32) keys[i] = EMPTY_KEY;
-    __syncwarp();
-    for (uint32_t k = 2; k <= n2; k <<= 1)
-      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-        for (uint32_t t = lane; t < (n2 >> 1); t += 32) {
-          const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-          const uint32_t l = i | j;
-          const uint64_t a = keys[i], b = keys[l];
-          const bool asc = (i & k) == 0;
-          if ((a > b) == asc) { keys[i] = b; keys[l] = a; }
-        }
-        __syncwarp();
-      }
+    seeds_sort_all<RD>(ix, span, off, cnt, meta, excl, tot, T, keys, lane);
   }
   // ---- chains: segmented scan over the sorted keys; the tail of every chain is replaced by its
   //      candidate word, every other slot by EMPTY
@@ -397,26 +431,7 @@ __device__ __forceinline__ uint32_t warp_mate_candidates(const IndexView& ix, co
     if (keep && rank < (uint32_t)MAXCAND) cands[rank] = w;
     nc += (uint32_t)__popc(bal);
   }
-  if (nc > (uint32_t)MAXCAND) {
-    // rare: keep the MAXCAND best by (coverage desc, tid, ori, diag); rank by counting who beats whom
-    uint32_t out = 0;
-    for (uint32_t base = 0; base < N; base += 32) {
-      const uint32_t i = base + lane;
-      const uint64_t w = (i < N) ? keys[i] : EMPTY_KEY;
-      const bool surv = (w != EMPTY_KEY) && ((double)cw_cov(w) >= thr);
-      uint32_t beaten_by = 0;
-      for (uint32_t q = 0; q < N; ++q) {
-        const uint64_t x = keys[q];
-        if (x != EMPTY_KEY && (double)cw_cov(x) >= thr && surv && cand_beats(x, w)) ++beaten_by;
-      }
-      const bool keep = surv && beaten_by < (uint32_t)MAXCAND;
-      const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-      const uint32_t rank = out + (uint32_t)__popc(bal & ((1u << lane) - 1));
-      if (keep) cands[rank] = w;
-      out += (uint32_t)__popc(bal);
-    }
-    nc = (uint32_t)MAXCAND;
-  }
+  if (nc > (uint32_t)MAXCAND) { cands_top(keys, N, thr, cands, lane); nc = (uint32_t)MAXCAND; }
   __syncwarp();
   return nc;
 }
@@ -427,7 +442,7 @@ __device__ __forceinline__ int32_t cwd_diag(uint64_t w) { return (int32_t)((w >>
 
 template <int CW> struct SeedCfg { static constexpr int WARPS = (CW == 2) ? 8 : 6; };   // <= 48 KB static shared memory
 
-template <int CW>
+template <int CW, int RD>
 __global__ void __launch_bounds__(SeedCfg<CW>::WARPS * 32, 4)
 k_seed_chain_w(IndexView ix, Params p, PackedReads pr, uint32_t n, uint32_t L, SeedOut o) {
   constexpr int WPB = SeedCfg<CW>::WARPS;
@@ -441,14 +456,14 @@ k_seed_chain_w(IndexView ix, Params p, PackedReads pr, uint32_t n, uint32_t L, S
   ctr.lookups = ctr.postings = ctr.seeds = ctr.candidates = ctr.kept = ctr.label_entries = ctr.mapped = 0;
   for (uint32_t r = warp; r < n; r += nwarps) {
     uint32_t ncand[2];
-#pragma unroll
+#pragma unroll 1
     for (int mate = 0; mate < 2; ++mate) {
       const uint64_t mi = (uint64_t)2 * r + mate;
       __syncwarp();
       if (lane < pr.wpr) s_read[wib][lane] = pr.bits[mi * pr.wpr + lane];
       else if (lane < pr.wpr + pr.mpr) s_read[wib][lane] = pr.nmask[mi * pr.mpr + (lane - pr.wpr)];
       __syncwarp();
-      ncand[mate] = warp_mate_candidates<CW>(ix, p, s_read[wib], s_read[wib] + pr.wpr, L, s_keys[wib], gkeys,
+      ncand[mate] = warp_mate_candidates<CW, RD>(ix, p, s_read[wib], s_read[wib] + pr.wpr, L, s_keys[wib], gkeys,
                                              s_cand[wib][mate], ctr, lane);
     }
     const uint32_t nl = ncand[0], nr = ncand[1];
