@@ -307,14 +307,27 @@ __global__ void k_dp_score(IndexView ix, Params p, const uint8_t* __restrict__ l
 }
 
 // K3: one thread per read pair -- salmon's alignment filtering, auxiliary probabilities, label
+// work estimate of a read for k_assign (joint hits to walk): reads are handed to threads in this order so that the
+// threads of a warp run loops of similar length
+__global__ void k_assign_work(uint32_t n, const uint32_t* __restrict__ n_l, const uint32_t* __restrict__ n_r,
+                              uint32_t* __restrict__ work, uint32_t* __restrict__ ids) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint32_t nl = n_l[r], nr = n_r[r];
+  uint32_t w = 0;
+  if (!(nl & 0x80000000u)) { w = 1 + nl * nr + nl + nr; if (w > 255u) w = 255u; }
+  work[r] = w; ids[r] = r;
+}
+
 __global__ void k_assign(IndexView ix, Params p, FldView fld, int useAux, int burnedIn, uint32_t n, uint32_t L,
-                         BatchBufs b, OnlineView on, uint32_t chunk_first_read) {
+                         BatchBufs b, OnlineView on, uint32_t chunk_first_read, const uint32_t* __restrict__ order) {
   const uint32_t T = gridDim.x * blockDim.x;
   const uint32_t tid0 = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t cap = p.max_read_occ;
   Counters ctr;
   memset(&ctr, 0, sizeof(ctr));
-  for (uint32_t r = tid0; r < n; r += T) {
+  for (uint32_t q = tid0; q < n; q += T) {
+    const uint32_t r = order ? order[q] : q;
     ReadOut o;
     o.n_aln = b.n_aln + r;
     o.tid = b.tid + (size_t)r * cap; o.score = b.score + (size_t)r * cap; o.prob = b.prob + (size_t)r * cap;
@@ -726,6 +739,7 @@ struct sb_map_ctx {
   uint64_t* d_overflow = nullptr;
   uint32_t* d_next_task = nullptr;     // [0] task counter, [4..6] list sizes
   uint32_t *d_list_int = nullptr, *d_list_edge = nullptr, *d_list_n = nullptr;
+  uint32_t *d_work = nullptr, *d_work2 = nullptr, *d_ids = nullptr, *d_order = nullptr;   // k_assign read order
   unsigned long long* d_full_dp = nullptr;
   // FLD tables
   double* d_fld = nullptr;
@@ -928,6 +942,7 @@ extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int d
   A(&c->d_overflow, (size_t)c->seed_blocks * SEED_WARPS * MAXSEEDS);
   A(&c->d_next_task, 8); A(&c->d_full_dp, 1);
   A(&c->d_list_int, CH * 2 * MAXCAND); A(&c->d_list_edge, CH * 2 * MAXCAND); A(&c->d_list_n, CH * 2 * MAXCAND);
+  A(&c->d_work, CH); A(&c->d_work2, CH); A(&c->d_ids, CH); A(&c->d_order, CH);
   for (int s = 0; s < 2; ++s) for (int m = 0; m < 2; ++m) A(&c->d_in[s][m], CH * max_read_len);
   c->pr.wpr = (max_read_len + 31) / 32 + 1; c->pr.mpr = (max_read_len + 63) / 64 + 1;
   A(&c->pr.bits, 2 * CH * c->pr.wpr); A(&c->pr.nmask, 2 * CH * c->pr.mpr);
@@ -970,7 +985,7 @@ extern "C" void sb_map_destroy(sb_map_ctx* c) {
                   c->d_fld, c->pr.bits, c->pr.nmask, c->d_overflow, c->d_next_task, c->d_full_dp, b.lp,
                   c->on.mass, c->on.prior, c->on.log_eff, c->on.hist, c->on.tot, c->on.cf, c->on.mass_acc, c->on.fld_acc,
                   c->on.mins, c->on.fm_rel, c->on.tap_q, c->d_scratch_nf, c->d_list_int, c->d_list_edge, c->d_list_n,
-                  c->fin.uniq, c->fin.total, c->fin.hits, c->fin.parent, c->fin.root, c->fin.root2, c->fin.ids, c->fin.memb,
+                  c->d_work, c->d_work2, c->d_ids, c->d_order, c->fin.uniq, c->fin.total, c->fin.hits, c->fin.parent, c->fin.root, c->fin.root2, c->fin.ids, c->fin.memb,
                   c->fin.head, c->fin.head_scan, c->fin.start, c->fin.proj, c->fin.eff, c->fin.bound, c->fin.tmp};
   for (void* p : ptrs) cudaFree(p);
   c->agg.free_all();
@@ -1113,19 +1128,24 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
         SB_CUDA(cudaEventRecord(c->ev_seed[2 * ch + 1], st));
         k_dp_classify<4><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, L, c->fast_ok, io);
         k_dp_pair<4><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, L, io);
-        k_dp_general<4><<<c->n_sm, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, io);
+        k_dp_general<4><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, io);
       } else {
         if (npos <= 32) k_seed_chain_w<4, 1><<<c->seed_blocks, SeedCfg<4>::WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
         else k_seed_chain_w<4, 2><<<c->seed_blocks, SeedCfg<4>::WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
         SB_CUDA(cudaEventRecord(c->ev_seed[2 * ch + 1], st));
         k_dp_classify<8><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, L, c->fast_ok, io);
         k_dp_pair<8><<<c->n_sm * 2, 256, 0, st>>>(ix, p, c->pr, L, io);
-        k_dp_general<8><<<c->n_sm, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, io);
+        k_dp_general<8><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, io);
       }
       c->launches += 5;
     }
-    k_assign<<<T / 128, 128, 0, st>>>(ix, p, c->fld, useAux, burnedIn, cn, L, bc, onv, c0);
-    c->launches += 1;
+    {
+      k_assign_work<<<nblk(cn, 256), 256, 0, st>>>(cn, bc.n_l, bc.n_r, c->d_work, c->d_ids);
+      size_t tb = c->agg.tmp_bytes;
+      SB_CUDA(cub::DeviceRadixSort::SortPairs(c->agg.tmp, tb, c->d_work, c->d_work2, c->d_ids, c->d_order, (int)cn, 0, 8, st));
+    }
+    k_assign<<<T / 128, 128, 0, st>>>(ix, p, c->fld, useAux, burnedIn, cn, L, bc, onv, c0, c->d_order);
+    c->launches += 3;
     SB_CUDA(cudaEventRecord(c->ev_free[s], st));
   }
   // fold the batch into the online state (masses, FLD)
