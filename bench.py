@@ -259,6 +259,7 @@ def bench_stage_a(args, rank, world, local, dist, W, peak, peak_src, ncores):
     out = {
         "metric": "Mreads/s selective-align", "value": world * n / res_t / 1e6, "unit": "Mreads/s",
         "ms_per_step": res_t * 1e3, "higher_is_better": True, "scaling": "weak", "dtype": "u8/i32 (mapping), f64 (weights)",
+        "steps_ms_rank0": {"resident": [round(x * 1e3, 2) for x in res_s], "e2e": [round(x * 1e3, 2) for x in e2e_s]},
         "config": {"workload": f"configs[2] shape: synth_txome(seed=44, n_genes={SA['n_genes'] // (20 if args.sa_small else 1)}) = "
                                f"{len(txps)} transcripts / {flat[1].shape[0] / 1e6:.0f} Mb / {info['n_kmers'] / 1e6:.0f} M distinct 31-mers; "
                                f"{n} synthetic 2x{L} bp IU pairs per GPU per step (0.5% substitutions, 3% unmappable), "
@@ -295,6 +296,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--em", action="store_true", help="plain EM instead of VBEM (not the headline)")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--nccl", action="store_true", help="N>1: per-iteration ncclAllReduce instead of the fused kernel")
     ap.add_argument("--no-stage-a", action="store_true", help="skip the Stage A (mapping) measurement")
     ap.add_argument("--sa-small", action="store_true", help="Stage A on a 20x smaller transcriptome (dev)")
     args = ap.parse_args()
@@ -363,9 +365,12 @@ def main():
         tp = torch.from_numpy(proj).cuda(); dist.all_reduce(tp); proj = tp.cpu().numpy()
         tu = torch.from_numpy(uniq.astype(np.int64)).cuda(); dist.all_reduce(tu); uniq = tu.cpu().numpy().astype(np.uint64)
         te = torch.from_numpy(eff).cuda(); dist.broadcast(te, 0); eff = te.cpu().numpy()
-        uid = [_capi.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(rank, world, uid[0])
+        if args.nccl:
+            uid = [_capi.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            ctx.comm_init(rank, world, uid[0])
+        else:
+            ctx.peer_setup(dist, C2["M"])
     for a in (eq.off, eq.tids, eq.weights, eq.counts, proj, eff, uniq):
         _capi.pin(a)
     p = default_params(use_vbem=vbem, min_iter=ITERS_PER_STEP, max_iter=ITERS_PER_STEP)
@@ -440,8 +445,9 @@ def main():
         return 0
 
     b_iter = algorithmic_bytes_per_iter(eq, bool(vbem))
-    kern_iters_per_launch = ITERS_PER_STEP if (world == 1) else 1
-    avg_launch_ms = loop_step_ms if world == 1 else loop_step_ms / ITERS_PER_STEP
+    fused = world == 1 or not args.nccl
+    kern_iters_per_launch = ITERS_PER_STEP if fused else 1
+    avg_launch_ms = loop_step_ms if fused else loop_step_ms / ITERS_PER_STEP
     achieved = b_iter * kern_iters_per_launch / (avg_launch_ms / 1e3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic_r1.json")
@@ -457,10 +463,12 @@ def main():
                    "l2": "flushed (memset > 2x L2) before every timed step; inside a step the table is re-swept "
                          "1000x and stays L2-resident, as in production",
                    "parallelism": "1 GPU" if world == 1 else
-                   f"classes sharded over {world} GPUs (own table per rank), alpha NCCL all-reduced per iteration; "
+                   f"classes sharded over {world} GPUs (own table per rank), alpha all-reduced per iteration "
+                   f"({'ncclAllReduce' if args.nccl else 'inside the persistent kernel over NVLink peer memory'}); "
                    f"value = {world} x iterations/s",
                    "kernel": "persistent cooperative k_em_persistent (1 launch per step)" if world == 1 else
-                   "k_em_p1 + k_em_p2_partial + ncclAllReduce + k_em_update per iteration",
+                   ("k_em_p1 + k_em_p2_partial + ncclAllReduce + k_em_update per iteration" if args.nccl else
+                    "k_em_persistent_mgpu: 1 cooperative launch per step per rank, fused reduce-scatter/all-gather over peer memory"),
                    "wall_s_resident_loop": wall_resident},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -469,7 +477,8 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_iteration": b_iter,
-                     "kernel": "k_em_persistent" if world == 1 else "k_em_p1+k_em_p2_partial+k_em_update",
+                     "kernel": "k_em_persistent" if world == 1 else
+                     ("k_em_p1+k_em_p2_partial+k_em_update" if args.nccl else "k_em_persistent_mgpu"),
                      "avg_launch_ms": avg_launch_ms, "iterations_per_launch": kern_iters_per_launch,
                      "note": "data is L2-resident by design, so DRAM traffic is far below the algorithmic bytes"},
     }

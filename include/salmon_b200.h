@@ -307,6 +307,13 @@ int sb_em_set_option(sb_em_ctx* ctx, const char* key, int64_t value);
 int sb_nccl_unique_id(void* out128);
 int sb_em_comm_init(sb_em_ctx* ctx, int rank, int nranks, const void* unique_id128);
 int sb_em_comm_destroy(sb_em_ctx* ctx);
+/* Fused all-reduce (GPUs of one box, NVLink P2P): every rank allocates an exchange block (sb_em_peer_handle returns
+ * its 64-byte CUDA IPC handle), the host layer all-gathers the handles, sb_em_peer_open maps the peers' blocks.  From
+ * then on sb_em_optimize / sb_em_run iterate inside ONE persistent kernel per rank that all-reduces alpha' over peer
+ * memory (reduce-scatter + all-gather with in-kernel GPU-to-GPU barriers) instead of calling NCCL per iteration.
+ * Without peers the NCCL path (sb_em_comm_init) is used. */
+int sb_em_peer_handle(sb_em_ctx* ctx, uint32_t max_txps, void* out64);
+int sb_em_peer_open(sb_em_ctx* ctx, int rank, int nranks, const void* handles /* nranks x 64 bytes */);
 
 /* Write a buffer larger than L2 (bench hygiene between timed steps). */
 int sb_flush_l2(sb_em_ctx* ctx);

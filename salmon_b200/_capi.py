@@ -136,6 +136,8 @@ SYMBOLS = {
     "sb_nccl_unique_id": (C.c_int, [_P]),
     "sb_em_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "sb_em_comm_destroy": (C.c_int, [_P]),
+    "sb_em_peer_handle": (C.c_int, [_P, C.c_uint32, _P]),
+    "sb_em_peer_open": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "sb_flush_l2": (C.c_int, [_P]),
     "sb_index_build": (_P, [C.c_uint32, _P, _P, C.c_uint32]),
     "sb_index_free": (None, [_P]),
@@ -343,6 +345,16 @@ class EMContext:
 
     def flush_l2(self):
         _check(self.lib.sb_flush_l2(self.h), "sb_flush_l2")
+
+    def peer_setup(self, dist, max_txps: int):
+        """fused multi-GPU all-reduce: exchange CUDA IPC handles of the per-rank blocks (torch.distributed) and map
+        the peers (NVLink P2P).  Call before upload/prepare/optimize."""
+        buf = C.create_string_buffer(64)
+        _check(self.lib.sb_em_peer_handle(self.h, int(max_txps), buf), "sb_em_peer_handle")
+        hs = [None] * dist.get_world_size()
+        dist.all_gather_object(hs, buf.raw)
+        allh = C.create_string_buffer(b"".join(hs), 64 * len(hs))
+        _check(self.lib.sb_em_peer_open(self.h, dist.get_rank(), dist.get_world_size(), allh), "sb_em_peer_open")
 
     def comm_init(self, rank: int, nranks: int, uid: bytes):
         buf = C.create_string_buffer(uid, 128)

@@ -38,6 +38,7 @@ struct KernelSet {
   const char* name;
   size_t smem;
   const void* persistent;
+  const void* persistent_mgpu;
   void (*p1)(EmArgs);
   void (*p2)(EmArgs, uint32_t);
   void (*p2_partial)(EmArgs);
@@ -48,6 +49,7 @@ static KernelSet make_set(const char* name) {
   k.name = name;
   k.smem = em_smem<CH>();
   k.persistent = (const void*)k_em_persistent<CH, MINB>;
+  k.persistent_mgpu = (const void*)k_em_persistent_mgpu<CH, MINB>;
   k.p1 = k_em_p1<CH, MINB>;
   k.p2 = k_em_p2<CH, MINB>;
   k.p2_partial = k_em_p2_partial<CH, MINB>;
@@ -538,6 +540,9 @@ static void free_all(sb_em_ctx* c) {
 extern "C" void sb_em_destroy(sb_em_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (void* p : c->x_opened) cudaIpcCloseMemHandle(p);
+  cudaFree(c->x_block); cudaFree(c->d_peers); cudaFree(c->d_xfail);
   sb_em_comm_destroy(c);
   free_all(c);
   for (int i = 0; i < 4; ++i) cudaEventDestroy(c->ev[i]);
@@ -1032,11 +1037,84 @@ extern "C" int sb_em_comm_destroy(sb_em_ctx* c) {
   return SB_OK;
 }
 
+// ---- exchange blocks for the fused multi-GPU kernel (CUDA IPC over NVLink P2P) ----------------------
+extern "C" int sb_em_peer_handle(sb_em_ctx* c, uint32_t max_txps, void* out64) {
+  if (!c || !out64 || !max_txps) { set_error("null argument"); return SB_ERR_INVALID; }
+  SB_CUDA(cudaSetDevice(c->device));
+  if (c->x_block && c->x_cap < max_txps) { set_error("exchange block already allocated for %u transcripts", c->x_cap); return SB_ERR_STATE; }
+  if (!c->x_block) {
+    const size_t bytes = ((size_t)2 * max_txps + 64) * 8;
+    SB_CUDA(cudaMalloc(&c->x_block, bytes));
+    SB_CUDA(cudaMemset(c->x_block, 0, bytes));
+    SB_CUDA(cudaMalloc(&c->d_xfail, 4));
+    c->x_cap = max_txps;
+  }
+  cudaIpcMemHandle_t h;
+  SB_CUDA(cudaIpcGetMemHandle(&h, c->x_block));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(out64, &h, 64);
+  return SB_OK;
+}
+
+// handles: nranks x 64 bytes (every rank's sb_em_peer_handle, all-gathered by the host layer).  The block layout
+// depends on the number of transcripts of the run: [part M | red M | flags], so M is fixed by the first run after
+// this call (max_txps of sb_em_peer_handle must be >= M).
+extern "C" int sb_em_peer_open(sb_em_ctx* c, int rank, int nranks, const void* handles) {
+  if (!c || !handles || nranks < 2 || nranks > 64 || rank < 0 || rank >= nranks) { set_error("bad arguments"); return SB_ERR_INVALID; }
+  if (!c->x_block) { set_error("sb_em_peer_open before sb_em_peer_handle"); return SB_ERR_STATE; }
+  SB_CUDA(cudaSetDevice(c->device));
+  std::vector<double*> ptrs(nranks, nullptr);
+  for (int q = 0; q < nranks; ++q) {
+    if (q == rank) { ptrs[q] = c->x_block; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)q * 64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e)); cudaGetLastError(); return SB_ERR_CUDA; }
+    ptrs[q] = (double*)p;
+    c->x_opened.push_back(p);
+  }
+  if (!c->d_peers) SB_CUDA(cudaMalloc(&c->d_peers, 64 * sizeof(double*)));
+  SB_CUDA(cudaMemcpy(c->d_peers, ptrs.data(), (size_t)nranks * sizeof(double*), cudaMemcpyHostToDevice));
+  c->rank = rank; c->nranks = nranks;
+  c->peers_ready = true;
+  return SB_OK;
+}
+
+// Fused path: one cooperative launch per run on every rank; alpha' is all-reduced inside the kernel over the
+// peers' exchange blocks (see k_em_persistent_mgpu).
+static int em_run_multi_gpu_fused(sb_em_ctx* c, const KernelSet& ks, EmArgs& A, uint32_t* out,
+                                  uint32_t* launches, uint32_t* loop_launches, float* loop_ms) {
+  cudaStream_t st = c->stream;
+  const uint32_t M = c->M;
+  // locally inactive transcripts contribute their (constant) folded singleton mass
+  SB_CUDA(cudaMemcpyAsync(c->x_block + 64, c->d_base, (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
+  SB_CUDA(cudaMemsetAsync(c->d_xfail, 0, 4, st));
+  A.part_out = c->x_block + 64;
+  A.inactive_sum = 0.0;
+  A.peers = c->d_peers; A.rank = (uint32_t)c->rank; A.nranks = (uint32_t)c->nranks; A.M = M;
+  A.epoch0 = c->x_epoch; A.xfail = c->d_xfail;
+  void* args[] = {(void*)&A};
+  SB_CUDA(cudaEventRecord(c->ev[2], st));
+  SB_CUDA(cudaLaunchCooperativeKernel(ks.persistent_mgpu, dim3(c->grid), dim3(EM_THREADS), args, ks.smem, st));
+  SB_CUDA(cudaEventRecord(c->ev[3], st));
+  *launches += 1; *loop_launches += 1;
+  uint32_t fail = 0;
+  SB_CUDA(cudaMemcpyAsync(out, A.out, 16, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(&fail, c->d_xfail, 4, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(loop_ms, c->ev[2], c->ev[3]);
+  c->x_epoch += 2ull * out[0];
+  if (fail) { set_error("multi-GPU EM: a peer GPU did not reach the in-kernel barrier (rank %d of %d)", c->rank, c->nranks); return SB_ERR_NCCL; }
+  return SB_OK;
+}
+
 // One iteration = P1, P2-partial, all-reduce(alpha'), update.  Classes stay sharded.
 static int em_run_multi_gpu(sb_em_ctx* c, const KernelSet& ks, EmArgs& A, uint32_t* out,
                             uint32_t* launches, uint32_t* loop_launches, float* loop_ms) {
   cudaStream_t st = c->stream;
   const uint32_t M = c->M;
+  if (!c->nccl_comm) { set_error("multi-GPU EM: neither peers (sb_em_peer_open) nor NCCL (sb_em_comm_init) are set up"); return SB_ERR_STATE; }
   SB_TRY(dev_alloc(&c->d_part, (size_t)M));
   SB_TRY(dev_alloc(&c->d_part_red, (size_t)M));
   // locally inactive transcripts contribute their (constant) folded singleton mass
@@ -1105,7 +1183,9 @@ extern "C" int sb_em_run(sb_em_ctx* c, sb_em_stats* stats) {
   if (c->params.max_iter == 0 && c->params.min_iter == 0) {
     // nothing to iterate
   } else if (multi_gpu) {
-    int r = em_run_multi_gpu(c, ks, A, out, &launches, &loop_launches, &loop_ms);
+    const bool fused = c->peers_ready && c->M <= c->x_cap && c->variant == 1;
+    int r = fused ? em_run_multi_gpu_fused(c, ks, A, out, &launches, &loop_launches, &loop_ms)
+                  : em_run_multi_gpu(c, ks, A, out, &launches, &loop_launches, &loop_ms);
     if (r != SB_OK) return r;
   } else if (c->variant == 1) {
     void* args[] = {(void*)&A};

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/salmon_b200.h"
 
 namespace sb {
@@ -103,6 +105,14 @@ struct sb_em_ctx {
   void* nccl_comm = nullptr;
   double* d_part = nullptr;       // per-transcript partial alpha' (send)
   double* d_part_red = nullptr;   // all-reduced (recv)
+  // fused path: exchange block [part M | red M | flags 64] shared with the peers through CUDA IPC
+  double* x_block = nullptr;
+  uint32_t x_cap = 0;
+  double** d_peers = nullptr;
+  std::vector<void*> x_opened;
+  bool peers_ready = false;
+  unsigned long long x_epoch = 0;
+  uint32_t* d_xfail = nullptr;
 
   // overrides used by the bootstrap driver (sampling.cuh): resampled counts, uniform init
   bool ov_active = false;

@@ -72,6 +72,12 @@ struct EmArgs {
   uint32_t* out;                // [0]=iters [1]=converged [2]=maxrel slot
   unsigned long long* dbg;      // optional [n_warps*8] phase timestamps (ns) of iteration dbg_it
   uint32_t dbg_it;
+  // multi-GPU, fused all-reduce over peer memory (k_em_persistent_mgpu): every rank owns one exchange block
+  //   [ flags: 64 u64 | part: M doubles | red: M doubles ]   mapped into every peer (CUDA IPC, NVLink P2P)
+  double* const* peers;         // [nranks] base pointers of the exchange blocks (peers[rank] = own)
+  uint32_t rank, nranks, M;
+  unsigned long long epoch0;    // barrier epochs consumed by earlier launches
+  uint32_t* xfail;              // set when a peer did not show up in time
 };
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -438,6 +444,117 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent(const __grid
     A.out[2] = (it - 1) & 1u;
   }
   // drain the speculative prefetch before the block (and its shared memory) retires
+  {
+    const uint32_t nchunks = (R1.cend - R1.cbeg + CH - 1) / CH;
+#pragma unroll
+    for (int k = 0; k < RING; ++k)
+      if ((uint32_t)k < nchunks) mbar_wait(&W.bars[k], (W.phase_bits >> k) & 1u);
+  }
+}
+
+// ---- multi-GPU persistent kernel: classes stay sharded per rank; alpha' is all-reduced INSIDE the kernel over
+// peer memory (NVLink P2P), once per iteration, as a reduce-scatter + all-gather:
+//   P1, P2-partial (this rank's share of alpha' per transcript id, into its exchange block)
+//   barrier over all GPUs -> rank r sums slice r of every rank's partial in fixed rank order (remote loads) and
+//   stores the sums into every rank's `red` (remote stores) -> barrier over all GPUs -> every rank runs the same
+//   update on identical data (identical alpha, theta, convergence decision).
+// GPU-to-GPU barrier: system-scope fence, grid barrier, block 0 pushes the epoch into each peer's flag slot
+// (st.release.sys) and polls its own slots (ld.acquire.sys), grid barrier.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void xgpu_barrier(cg::grid_group& grid, const EmArgs& A, unsigned long long epoch) {
+  __threadfence_system();
+  grid.sync();
+  if (blockIdx.x == 0 && threadIdx.x < A.nranks) {
+    const uint32_t q = threadIdx.x;
+    st_release_sys(reinterpret_cast<unsigned long long*>(A.peers[q]) + A.rank, epoch);
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(A.peers[A.rank]) + q;
+    const unsigned long long t0 = gtime_ns();
+    while (ld_acquire_sys(mine) < epoch) {
+      if (gtime_ns() - t0 > 20000000000ull) { *A.xfail = 1u; break; }   // a peer is missing: give up, report
+    }
+  }
+  grid.sync();
+}
+
+template <int CH, int MINB>
+__global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent_mgpu(const __grid_constant__ EmArgs A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  WarpCtx<CH> W;
+  warp_setup(W, smem);
+  double* scratch = W.scratch;
+  cg::grid_group grid = cg::this_grid();
+  const uint32_t bid = blockIdx.x, nblk = gridDim.x;
+  const uint32_t gwarp = bid * (EM_THREADS / 32) + (threadIdx.x >> 5);
+  const uint32_t gtid = bid * EM_THREADS + threadIdx.x, gthreads = nblk * EM_THREADS;
+  const WarpRange R1 = load_range(A.cm, gwarp);
+  const WarpRange R2 = load_range(A.tm, gwarp);
+  const uint32_t M = A.M, G = A.nranks;
+  const uint32_t S = (M + G - 1) / G, lo = A.rank * S, hi = (lo + S < M) ? lo + S : M;
+  double* my_red = A.peers[A.rank] + 64 + M;
+  unsigned long long epoch = A.epoch0;
+  uint32_t it = 0;
+  bool converged = false;
+  ring_prefetch(A.cm, W, R1);
+  while (it < A.min_iter || (it < A.max_iter && !converged)) {
+    const uint32_t par = it & 1u;
+    if (bid == 0 && threadIdx.x == 0) A.maxrel[par] = 0ull;
+    P2Acc pa{0.0, 0.0};
+    run_phase<1, CH>(A, W, R1, bid, nblk, 0.0, 0.0, pa);
+    ring_prefetch(A.tm, W, R2);
+    grid.sync();
+    run_phase<3, CH>(A, W, R2, bid, nblk, 0.0, 0.0, pa);      // A.part_out = own exchange block
+    ring_prefetch(A.cm, W, R1);
+    xgpu_barrier(grid, A, ++epoch);                            // every rank's partial is complete and visible
+    for (uint32_t t = lo + gtid; t < hi; t += gthreads) {
+      double v = 0.0;
+      for (uint32_t q = 0; q < G; ++q) v += ld_relaxed_sys_f64(A.peers[q] + 64 + t);
+      for (uint32_t q = 0; q < G; ++q) st_relaxed_sys_f64(A.peers[q] + 64 + M + t, v);
+    }
+    xgpu_barrier(grid, A, ++epoch);                            // every slice has been delivered everywhere
+    // ---- update (k_em_update): identical on every rank
+    double logNorm = 0.0;
+    if (A.vbem) {
+      if (it == 0) logNorm = digamma_pos(A.sum0);
+      else logNorm = digamma_pos(sum_partials(A.sum_partial + (size_t)(par ^ 1u) * nblk, nblk, 0.0, scratch));
+    }
+    const double bias = (it == 0) ? A.first_bias : 0.0;
+    double sum = 0.0, mx = 0.0;
+    for (uint32_t t = gtid; t < M; t += gthreads) {
+      const double na = __ldcg(&my_red[t]) + bias;
+      const double old = A.alpha[t];
+      if (na > ALPHA_CHECK_CUTOFF) mx = fmax(mx, fabs(old - na) / na);
+      A.alpha[t] = na;
+      const double ap = na + A.prior[t];
+      sum += ap;
+      A.theta[t] = A.vbem ? ((ap > DIGAMMA_MIN) ? exp(digamma_pos(ap) - logNorm) : 0.0) : na;
+    }
+    pa.sum = sum; pa.maxrel = mx;
+    p2_finish(A, scratch, pa, par);
+    grid.sync();
+    const double mr = __longlong_as_double((long long)__ldcg(&A.maxrel[par]));
+    converged = !(mr > A.tol);
+    ++it;
+  }
+  if (bid == 0 && threadIdx.x == 0) {
+    A.out[0] = it;
+    A.out[1] = converged ? 1u : 0u;
+    A.out[2] = (it - 1) & 1u;
+  }
   {
     const uint32_t nchunks = (R1.cend - R1.cbeg + CH - 1) / CH;
 #pragma unroll

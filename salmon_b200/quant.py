@@ -44,9 +44,7 @@ def quant_reads(index, left, right, map_params=None, em_params=None, device=0, b
     eq = EqClasses(M, res["off"], res["tids"], res["weights"], res["counts"])
     em = EMContext(device)
     if world > 1:
-        uid = [_capi.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        em.comm_init(rank, world, uid[0])
+        em.peer_setup(dist, M)          # alpha all-reduced inside the persistent kernel over NVLink peer memory
     alpha, st, ok = em.optimize(eq, ep, inputs["projected_counts"], inputs["eff_len"], inputs["unique_counts"])
     em.close()
     if not ok:
