@@ -732,7 +732,9 @@ extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* s
   SB_CUDA(cudaFuncSetAttribute((const void*)ks.p1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
   SB_CUDA(cudaFuncSetAttribute((const void*)ks.p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
   SB_CUDA(cudaFuncSetAttribute((const void*)ks.p2_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
-  SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ks.persistent, EM_THREADS, ks.smem));
+  SB_CUDA(cudaFuncSetAttribute(ks.persistent_mgpu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
+  SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->nranks > 1 ? ks.persistent_mgpu : ks.persistent,
+                                                        EM_THREADS, ks.smem));
   if (occ < 1) { set_error("persistent EM kernel does not fit on an SM"); return SB_ERR_CUDA; }
   if (c->blocks_per_sm > 0) occ = std::min(occ, c->blocks_per_sm);
   c->grid = (uint32_t)(occ * c->n_sm);

@@ -688,14 +688,17 @@ __global__ void k_store_records(uint64_t n, const uint64_t* __restrict__ loff, c
 // ---------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------
-struct EqStore {   // device CSR of class records
-  uint64_t n = 0, n_lab = 0, n_w = 0;
-  uint64_t* loff = nullptr; uint64_t* woff = nullptr;
+// Class tables live in a growing device arena (no cudaMalloc / cudaFree per batch: with peer access enabled -- any
+// multi-GPU run -- every allocation is mapped into all peers and becomes expensive).  A store = one table.
+struct Arena {
   uint32_t* labels = nullptr; double* weights = nullptr; uint64_t* counts = nullptr;
-  void free_all() {
-    cudaFree(loff); cudaFree(woff); cudaFree(labels); cudaFree(weights); cudaFree(counts);
-    loff = woff = nullptr; labels = nullptr; weights = nullptr; counts = nullptr; n = n_lab = n_w = 0;
-  }
+  uint64_t *loff = nullptr, *woff = nullptr;        // per store n+1 entries, relative to the store's label / weight base
+  uint64_t cap_l = 0, cap_w = 0, cap_c = 0, cap_o = 0, cap_o_w = 0;   // capacities (entries)
+  uint64_t n_l = 0, n_w = 0, n_c = 0, n_o = 0;           // cursors
+};
+struct EqStore {   // a CSR table inside the arena
+  uint64_t n = 0, n_lab = 0, n_w = 0;
+  uint64_t base_l = 0, base_w = 0, base_c = 0, base_o = 0;
 };
 
 struct AggScratch {   // sized for `cap` records
@@ -764,6 +767,7 @@ struct sb_map_ctx {
   std::vector<double> h_proj, h_eff;
   std::vector<uint64_t> h_uniq, h_total;
   // eq-class store: one EqStore per processed batch, merged at finish
+  Arena arena;
   std::vector<EqStore> stores;
   uint64_t frag_counter = 0;     // fragments assigned so far (batched semantics)
   Counters totals{};
@@ -989,7 +993,7 @@ extern "C" void sb_map_destroy(sb_map_ctx* c) {
                   c->fin.head, c->fin.head_scan, c->fin.start, c->fin.proj, c->fin.eff, c->fin.bound, c->fin.tmp};
   for (void* p : ptrs) cudaFree(p);
   c->agg.free_all();
-  for (auto& s : c->stores) s.free_all();
+  cudaFree(c->arena.labels); cudaFree(c->arena.weights); cudaFree(c->arena.counts); cudaFree(c->arena.loff); cudaFree(c->arena.woff);
   for (cudaEvent_t e : c->ev_seed) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1014,10 +1018,25 @@ extern "C" int sb_map_set_option(sb_map_ctx* c, const char* key, int64_t value) 
   return SB_ERR_INVALID;
 }
 
-// records -> classes (per batch over the read slots, and at finish over all batch classes)
+template <typename T>
+static int arena_grow(T** p, uint64_t* cap, uint64_t used, uint64_t need, cudaStream_t st) {
+  if (need <= *cap) return SB_OK;
+  uint64_t ncap = std::max<uint64_t>(need, *cap * 2);
+  T* q = nullptr;
+  SB_TRY(dmalloc(&q, ncap));
+  if (used) SB_CUDA(cudaMemcpyAsync(q, *p, used * sizeof(T), cudaMemcpyDeviceToDevice, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(*p);
+  *p = q; *cap = ncap;
+  return SB_OK;
+}
+
+// records -> classes (per batch over the read slots, and at finish over all batch classes); the table is appended to
+// the arena
 static int aggregate(sb_map_ctx* c, Records R, EqStore& out) {
   cudaStream_t st = c->stream;
   AggScratch& a = c->agg;
+  Arena& ar = c->arena;
   out = EqStore();
   const uint32_t n = R.n;
   if (n == 0) return SB_OK;
@@ -1032,19 +1051,35 @@ static int aggregate(sb_map_ctx* c, Records R, EqStore& out) {
   SB_CUDA(cudaStreamSynchronize(st));
   SB_CUDA(cudaMemsetAsync(a.cls_llen + nc, 0, 8, st)); SB_CUDA(cudaMemsetAsync(a.cls_wlen + nc, 0, 8, st));
   k_class_sizes<<<nblk(n, 256), 256, 0, st>>>(R, a.head, a.head_scan, a.idx2, a.first, a.cls_llen, a.cls_wlen);
-  SB_TRY(dmalloc(&out.loff, (size_t)nc + 1)); SB_TRY(dmalloc(&out.woff, (size_t)nc + 1));
-  t = a.tmp_bytes;
-  SB_CUDA(cub::DeviceScan::ExclusiveSum(a.tmp, t, a.cls_llen, out.loff, (int)nc + 1, st));
-  t = a.tmp_bytes;
-  SB_CUDA(cub::DeviceScan::ExclusiveSum(a.tmp, t, a.cls_wlen, out.woff, (int)nc + 1, st));
-  uint64_t tl = 0, tw = 0;
-  SB_CUDA(cudaMemcpyAsync(&tl, out.loff + nc, 8, cudaMemcpyDeviceToHost, st));
-  SB_CUDA(cudaMemcpyAsync(&tw, out.woff + nc, 8, cudaMemcpyDeviceToHost, st));
-  SB_CUDA(cudaStreamSynchronize(st));
-  SB_TRY(dmalloc(&out.labels, tl)); SB_TRY(dmalloc(&out.weights, tw)); SB_TRY(dmalloc(&out.counts, nc));
-  k_class_reduce<<<nblk((uint64_t)nc * 32, 256), 256, 0, st>>>(R, nc, a.first, a.idx2, out.loff, out.woff, out.labels,
-                                                              out.weights, out.counts);
-  out.n = nc; out.n_lab = tl; out.n_w = tw;
+  out.base_o = ar.n_o; out.base_c = ar.n_c;
+  {
+    // R may point into the arena (finish): growing moves it, so remember the offsets of its arrays
+    const bool in_arena = R.labels >= ar.labels && R.labels < ar.labels + ar.cap_l;
+    const uint64_t ro_l = in_arena ? (uint64_t)(R.labels - ar.labels) : 0, ro_w = in_arena ? (uint64_t)(R.weights - ar.weights) : 0,
+                   ro_c = (in_arena && R.counts) ? (uint64_t)(R.counts - ar.counts) : 0;
+    SB_TRY(arena_grow(&ar.loff, &ar.cap_o, ar.n_o, ar.n_o + nc + 1, st));
+    uint64_t capw = ar.cap_o_w;
+    SB_TRY(arena_grow(&ar.woff, &capw, ar.n_o, ar.n_o + nc + 1, st));
+    ar.cap_o_w = capw;
+    SB_TRY(arena_grow(&ar.counts, &ar.cap_c, ar.n_c, ar.n_c + nc, st));
+    t = a.tmp_bytes;
+    SB_CUDA(cub::DeviceScan::ExclusiveSum(a.tmp, t, a.cls_llen, ar.loff + out.base_o, (int)nc + 1, st));
+    t = a.tmp_bytes;
+    SB_CUDA(cub::DeviceScan::ExclusiveSum(a.tmp, t, a.cls_wlen, ar.woff + out.base_o, (int)nc + 1, st));
+    uint64_t tl = 0, tw = 0;
+    SB_CUDA(cudaMemcpyAsync(&tl, ar.loff + out.base_o + nc, 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(&tw, ar.woff + out.base_o + nc, 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    out.base_l = ar.n_l; out.base_w = ar.n_w;
+    SB_TRY(arena_grow(&ar.labels, &ar.cap_l, ar.n_l, ar.n_l + tl, st));
+    SB_TRY(arena_grow(&ar.weights, &ar.cap_w, ar.n_w, ar.n_w + tw, st));
+    if (in_arena) { R.labels = ar.labels + ro_l; R.weights = ar.weights + ro_w; if (R.counts) R.counts = ar.counts + ro_c; }
+    k_class_reduce<<<nblk((uint64_t)nc * 32, 256), 256, 0, st>>>(R, nc, a.first, a.idx2, ar.loff + out.base_o,
+                                                                ar.woff + out.base_o, ar.labels + out.base_l,
+                                                                ar.weights + out.base_w, ar.counts + out.base_c);
+    out.n = nc; out.n_lab = tl; out.n_w = tw;
+    ar.n_o += (uint64_t)nc + 1; ar.n_c += nc; ar.n_l += tl; ar.n_w += tw;
+  }
   c->launches += 10;
   return SB_OK;
 }
@@ -1228,7 +1263,8 @@ extern "C" int sb_map_last_alignments(sb_map_ctx* c, uint32_t n, uint32_t* n_aln
 }
 
 // per-transcript counts and the transcript clusters of this context's classes (device arrays in c->fin)
-static int finish_stats(sb_map_ctx* c, const EqStore& merged) {
+static int finish_stats(sb_map_ctx* c, uint64_t n_cls, const uint64_t* loff, const uint64_t* woff, const uint32_t* labels,
+                        const uint64_t* counts) {
   cudaStream_t st = c->stream;
   const uint32_t M = c->M;
   if (!M) return SB_OK;
@@ -1236,9 +1272,8 @@ static int finish_stats(sb_map_ctx* c, const EqStore& merged) {
   SB_CUDA(cudaMemsetAsync(f.uniq, 0, (size_t)M * 8, st)); SB_CUDA(cudaMemsetAsync(f.total, 0, (size_t)M * 8, st));
   SB_CUDA(cudaMemsetAsync(f.hits, 0, (size_t)M * 8, st));
   k_iota<<<nblk(M, 256), 256, 0, st>>>(M, f.parent);
-  if (merged.n)
-    k_cls_accumulate<<<nblk(merged.n, 256), 256, 0, st>>>(merged.n, merged.loff, merged.woff, merged.labels, merged.counts,
-                                                          f.uniq, f.total, f.hits, f.parent);
+  if (n_cls)
+    k_cls_accumulate<<<nblk(n_cls, 256), 256, 0, st>>>(n_cls, loff, woff, labels, counts, f.uniq, f.total, f.hits, f.parent);
   k_roots<<<nblk(M, 256), 256, 0, st>>>(M, f.parent, f.root, f.ids);
   c->launches += 3;
   return SB_OK;
@@ -1282,29 +1317,27 @@ extern "C" int sb_map_finish(sb_map_ctx* c, sb_map_result* out) {
   for (auto& s : c->stores) { n += s.n; nl += s.n_lab; nw += s.n_w; }
   if (n >= (1ull << 31)) { sb::set_error("sb_map_finish: too many batch classes"); return SB_ERR_INVALID; }
   EqStore merged;
+  Arena& ar = c->arena;
+  const uint64_t mark_l = ar.n_l, mark_w = ar.n_w, mark_c = ar.n_c, mark_o = ar.n_o;   // the merged table is temporary
   if (n) {
-    uint64_t* counts = nullptr; uint32_t* labels = nullptr; double* weights = nullptr;
-    SB_TRY(dmalloc(&counts, n)); SB_TRY(dmalloc(&labels, nl)); SB_TRY(dmalloc(&weights, nw));
     SB_TRY(agg_reserve(c->agg, n));
     AggScratch& a = c->agg;
-    uint64_t i = 0, ol = 0, ow = 0;
-    for (auto& s : c->stores) {
+    uint64_t i = 0;
+    for (auto& s : c->stores) {   // the batch tables are the records: label / weight starts are arena positions
       if (!s.n) continue;
-      SB_CUDA(cudaMemcpyAsync(labels + ol, s.labels, s.n_lab * 4, cudaMemcpyDeviceToDevice, st));
-      SB_CUDA(cudaMemcpyAsync(weights + ow, s.weights, s.n_w * 8, cudaMemcpyDeviceToDevice, st));
-      SB_CUDA(cudaMemcpyAsync(counts + i, s.counts, s.n * 8, cudaMemcpyDeviceToDevice, st));
-      k_store_records<<<nblk(s.n, 256), 256, 0, st>>>(s.n, s.loff, s.woff, ol, ow, a.lstart + i, a.llen + i, a.wstart + i,
-                                                      a.wlen + i);
-      i += s.n; ol += s.n_lab; ow += s.n_w;
+      k_store_records<<<nblk(s.n, 256), 256, 0, st>>>(s.n, ar.loff + s.base_o, ar.woff + s.base_o, s.base_l, s.base_w,
+                                                      a.lstart + i, a.llen + i, a.wstart + i, a.wlen + i);
+      i += s.n;
     }
-    Records R{(uint32_t)n, a.lstart, a.llen, a.wstart, a.wlen, labels, weights, counts};
-    int rc = aggregate(c, R, merged);
-    cudaStreamSynchronize(st);
-    cudaFree(counts); cudaFree(labels); cudaFree(weights);
-    if (rc != SB_OK) return rc;
+    // counts of the batch tables are contiguous in the arena in store order (every store appends)
+    Records R{(uint32_t)n, a.lstart, a.llen, a.wstart, a.wlen, ar.labels, ar.weights, ar.counts + c->stores.front().base_c};
+    SB_TRY(aggregate(c, R, merged));
   }
+  const uint64_t* m_loff = ar.loff + merged.base_o; const uint64_t* m_woff = ar.woff + merged.base_o;
+  const uint32_t* m_labels = ar.labels + merged.base_l; double* m_weights = ar.weights + merged.base_w;
+  const uint64_t* m_counts = ar.counts + merged.base_c;
   if (merged.n) {
-    k_normalize<<<nblk(merged.n, 128), 128, 0, st>>>(merged.n, merged.woff, merged.weights);
+    k_normalize<<<nblk(merged.n, 128), 128, 0, st>>>(merged.n, m_woff, m_weights);
     c->launches++;
   }
   // ---- normalizeAlphas (SalmonUtils.cpp:461-529): initial alphas for the optimiser, plus what optimize() reads
@@ -1314,7 +1347,7 @@ extern "C" int sb_map_finish(sb_map_ctx* c, sb_map_result* out) {
     if (c->M) k_online_eff_len<<<nblk(c->M, 256), 256, 0, st>>>(c->M, c->nf, c->index->d_tx_off, c->on.cf, c->on.log_eff);
     c->launches += 2;
   }
-  SB_TRY(finish_stats(c, merged));
+  SB_TRY(finish_stats(c, merged.n, m_loff, m_woff, m_labels, m_counts));
   SB_TRY(finish_project(c));
   // to host (data movement only): drop the empty-label class, split label into tids | bins
   const int binned = c->p.range_bins > 0;
@@ -1322,11 +1355,11 @@ extern "C" int sb_map_finish(sb_map_ctx* c, sb_map_result* out) {
   std::vector<uint32_t> labels(merged.n_lab);
   std::vector<double> weights(merged.n_w);
   if (merged.n) {
-    SB_CUDA(cudaMemcpyAsync(loff.data(), merged.loff, (merged.n + 1) * 8, cudaMemcpyDeviceToHost, st));
-    SB_CUDA(cudaMemcpyAsync(woff.data(), merged.woff, (merged.n + 1) * 8, cudaMemcpyDeviceToHost, st));
-    SB_CUDA(cudaMemcpyAsync(counts.data(), merged.counts, merged.n * 8, cudaMemcpyDeviceToHost, st));
-    SB_CUDA(cudaMemcpyAsync(labels.data(), merged.labels, merged.n_lab * 4, cudaMemcpyDeviceToHost, st));
-    SB_CUDA(cudaMemcpyAsync(weights.data(), merged.weights, merged.n_w * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(loff.data(), m_loff, (merged.n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(woff.data(), m_woff, (merged.n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(counts.data(), m_counts, merged.n * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(labels.data(), m_labels, merged.n_lab * 4, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(weights.data(), m_weights, merged.n_w * 8, cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
   }
   c->h_off.assign(1, 0); c->h_counts.clear(); c->h_tids.clear(); c->h_ntx.clear(); c->h_bins.clear(); c->h_w.clear();
@@ -1343,7 +1376,7 @@ extern "C" int sb_map_finish(sb_map_ctx* c, sb_map_result* out) {
     c->h_counts.push_back(counts[q]);
     c->h_ntx.push_back((uint32_t)ntx);
   }
-  merged.free_all();
+  ar.n_l = mark_l; ar.n_w = mark_w; ar.n_c = mark_c; ar.n_o = mark_o;     // drop the merged table, keep the batch tables
   out->n_classes = c->h_counts.size();
   out->off = c->h_off.data(); out->tids = c->h_tids.data(); out->weights = c->h_w.data();
   out->counts = c->h_counts.data(); out->bins = binned ? c->h_bins.data() : nullptr;
@@ -1440,8 +1473,8 @@ extern "C" int sb_map_reset(sb_map_ctx* c) {
   if (!c) { sb::set_error("null argument"); return SB_ERR_INVALID; }
   SB_CUDA(cudaSetDevice(c->device));
   SB_CUDA(cudaDeviceSynchronize());
-  for (auto& s : c->stores) s.free_all();
   c->stores.clear();
+  c->arena.n_l = c->arena.n_w = c->arena.n_c = c->arena.n_o = 0;
   c->frag_counter = 0; c->frags_seen = 0; c->timestep = 0; c->burned_in = 0; c->full_dp_total = 0;
   memset(&c->totals, 0, sizeof(c->totals));
   const std::vector<double>& t = c->init_tables;
