@@ -286,8 +286,9 @@ int sb_map_last_alignments(sb_map_ctx* ctx, uint32_t n, uint32_t* n_aln, uint32_
 
 /* Tuning knobs of the mapping context: "variant" (1 = warp-cooperative kernels, 0 = serial-form kernels),
  * "fast_dp" (ungapped shortcut of the DP kernel on/off), "chunk" (reads per pipeline chunk), "input_on_device"
- * (sb_map_batch's read pointers are device pointers: inputs already resident in HBM).  Results are identical for
- * every setting. */
+ * (sb_map_batch's read pointers are device pointers: inputs already resident in HBM), "ascii_reads" (the read bytes
+ * are sequence characters A/C/G/T/N as the reference's parser delivers them, klibpp::KSeq::seq, instead of base
+ * codes).  Results are identical for every setting. */
 int sb_map_set_option(sb_map_ctx* ctx, const char* key, int64_t value);
 
 /* Debug: per-warp phase timestamps (ns) of one iteration of the last persistent run:

@@ -733,6 +733,7 @@ struct sb_map_ctx {
   uint32_t batch_cap = 0, read_len_cap = 0, chunk = 0;
   int variant = 1;                   // 1 = warp kernels (map_kernels.cuh), 0 = serial-form kernels
   int input_dev = 0;                 // sb_map_batch's read pointers are device pointers (bench: inputs resident in HBM)
+  int ascii = 0;                     // reads are sequence characters (ACGTN...) instead of base codes
   int fast_ok = 1;
   uint32_t k1_threads = 0, seed_blocks = 0, dp_blocks = 0;
   BatchBufs b{};                     // cand/score/task buffers: one chunk; outputs: whole batch
@@ -1008,6 +1009,10 @@ extern "C" int sb_map_set_option(sb_map_ctx* c, const char* key, int64_t value) 
   if (!strcmp(key, "variant")) { c->variant = (int)value; return SB_OK; }
   if (!strcmp(key, "fast_dp")) { c->fast_ok = value ? 1 : 0; return SB_OK; }
   if (!strcmp(key, "input_on_device")) { c->input_dev = value ? 1 : 0; return SB_OK; }
+  if (!strcmp(key, "ascii_reads")) {
+    if (value && c->variant == 0) { sb::set_error("ascii_reads needs the warp kernels (variant 1)"); return SB_ERR_INVALID; }
+    c->ascii = value ? 1 : 0; return SB_OK;
+  }
   if (!strcmp(key, "chunk")) {   // reads per pipeline chunk (<= the size the context was created with)
     const uint32_t mx = (uint32_t)std::min<size_t>(c->batch_cap, 65536);
     if (value < 1 || value > (int64_t)mx) { sb::set_error("chunk must be in 1..%u", mx); return SB_ERR_INVALID; }
@@ -1150,7 +1155,7 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
       k_dp_score<<<c->n_sm * 8, 256, 0, st>>>(ix, p, dl, dr, L, bc);
       c->launches += 2;
     } else {
-      k_pack_reads<<<nblk((uint64_t)2 * cn * c->pr.wpr, 256), 256, 0, st>>>(dl, dr, cn, L, c->pr);
+      k_pack_reads<<<nblk((uint64_t)2 * cn * c->pr.wpr, 256), 256, 0, st>>>(dl, dr, cn, L, c->pr, c->ascii);
       SeedOut so{bc.n_l, bc.n_r, bc.cand_l, bc.cand_r, bc.n_tasks, bc.tasks, c->d_overflow, bc.ctr};
       DpIo io{bc.n_tasks, bc.tasks, bc.cand_l, bc.cand_r, bc.score_l, bc.score_r, c->d_next_task, c->d_next_task + 4,
               c->d_list_int, c->d_list_edge, c->d_list_n, c->d_full_dp};

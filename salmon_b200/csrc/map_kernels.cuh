@@ -44,8 +44,10 @@ __device__ __forceinline__ uint64_t funnel64(uint64_t lo, uint64_t hi, uint32_t 
 // ---------------------------------------------------------------------------------------------
 // k_pack_reads: one thread per (mate, 32-base word)
 // ---------------------------------------------------------------------------------------------
+// ascii != 0: the input bytes are sequence characters (A C G T, any case; everything else is N) as the reference's
+// parser hands them over (klibpp::KSeq::seq), instead of base codes 0..4
 __global__ void k_pack_reads(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right, uint32_t n,
-                             uint32_t L, PackedReads pr) {
+                             uint32_t L, PackedReads pr, int ascii) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t total = (uint64_t)2 * n * pr.wpr;
   if (t >= total) return;
@@ -58,7 +60,11 @@ __global__ void k_pack_reads(const uint8_t* __restrict__ left, const uint8_t* __
   for (uint32_t j = 0; j < 32; ++j) {
     const uint32_t q = b0 + j;
     if (q >= L) break;
-    const uint8_t c = src[q];
+    uint8_t c = src[q];
+    if (ascii) {
+      const uint8_t u = c & 0xDFu;      // upper case
+      c = (u == 'A') ? 0 : (u == 'C') ? 1 : (u == 'G') ? 2 : (u == 'T') ? 3 : 4;
+    }
     if (c > 3) nm |= 1u << j;
     else bits |= (uint64_t)c << (2 * j);
   }

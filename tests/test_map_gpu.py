@@ -209,11 +209,12 @@ def test_long_reads_chunks_and_variants(oracle):
     oix = oracle.MapIndex(txps)
     ref = oracle.map_reads(oix, oracle.map_params(), left, right, 0)
     ref_e = oracle.eq_aggregate(ref, p.max_read_occ, True)
-    for opts in (dict(), dict(chunk=700), dict(variant=0), dict(fast_dp=0)):
+    asc = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    for opts in (dict(), dict(chunk=700), dict(variant=0), dict(fast_dp=0), dict(ascii_reads=1)):
         ctx = MapContext(idx, p, batch_cap=4096, max_read_len=150)
         for k, v in opts.items():
             ctx.set_option(k, v)
-        st = ctx.map_batch(left, right)
+        st = ctx.map_batch(asc[left], asc[right]) if opts.get("ascii_reads") else ctx.map_batch(left, right)
         compare(ctx.last_alignments(), ref, p.max_read_occ)
         for k in ("lookups", "postings", "seeds", "kept", "label_entries", "mapped"):
             assert getattr(st, k) == ref["counters"][k], (opts, k)
