@@ -157,6 +157,63 @@ int sb_write_quant_sf(const char* path, uint32_t n_txps, const char* const* name
 int sb_write_eq_classes(const char* path, uint32_t n_txps, const char* const* names, uint64_t n_classes,
                         const uint64_t* off, const uint32_t* tids, const double* weights, const uint64_t* counts);
 
+/* ---- input seam (host code): what sits immediately before B1 / B3 in the reference ---------------
+ * sb_reads_*: FASTQ / FASTA read files (plain or gzip) -> batches of base codes.  Replaces FQFeeder's
+ * fastx_parser<ReadPair> / <ReadSeq> as salmon drives it (src/quant/SalmonQuantify.cpp:2357-2373 construction,
+ * :2419-2430 start, :1118-1141 the ReadGroup loop).  One splitter thread per mate stream cuts record-aligned
+ * blocks, sb_reads_next translates a batch with n_threads OpenMP threads straight into the caller's buffers
+ * (0..3 = A,C,G,T, 4 = anything else; one byte per base, `stride` bytes per read, the tail padded with 4).
+ * files2 == NULL: single-end.  4-line FASTQ and 2-line FASTA records; mates are paired by record index. */
+typedef struct sb_reads sb_reads;
+sb_reads* sb_reads_open(const char* const* files1, const char* const* files2, uint32_t n_files, uint32_t n_threads);
+/* Returns the number of reads (pairs) delivered, 0 at the end of the input, < 0 on error (malformed record, mate
+ * files of different length, a read longer than `stride`). */
+int64_t sb_reads_next(sb_reads* r, uint32_t max_pairs, uint32_t stride, uint8_t* left, uint8_t* right,
+                      uint32_t* len_left, uint32_t* len_right);
+void sb_reads_close(sb_reads* r);
+
+/* The --eqclasses input (src/util/SalmonUtils.cpp:1024-1122 readEquivCounts): N, C, N names, C lines
+ * `k t_1..t_k [w_1..w_k] count`, then optional `name effective_length` lines (missing -> 100.0, :1109-1116). */
+typedef struct sb_eq_file {
+  uint32_t n_txps, has_weights;
+  uint64_t n_classes;
+  const char* const* names;   /* [n_txps] */
+  const uint64_t* off;        /* [n_classes+1] */
+  const uint32_t* tids;
+  const double* weights;      /* NULL when the file has none (--dumpEq without --dumpEqWeights) */
+  const uint64_t* counts;
+  const double* eff_len;      /* [n_txps] */
+  uint32_t n_missing_eff_len, reserved;
+} sb_eq_file;
+int sb_eq_file_read(const char* path, sb_eq_file** out);
+void sb_eq_file_free(sb_eq_file* f);
+
+/* aux_info/bootstrap/bootstraps.gz (src/output/GZipWriter.cpp:765-789 writeBootstrap): every sample is n raw doubles
+ * appended to one gzip stream (level 6); write() may be called from several threads (the sb_bootstrap / sb_gibbs
+ * callback).  close() returns the number of samples written. */
+typedef struct sb_bootstrap_writer sb_bootstrap_writer;
+sb_bootstrap_writer* sb_bootstrap_writer_open(const char* path);
+int sb_bootstrap_writer_write(sb_bootstrap_writer* w, const double* sample, uint32_t n);
+int64_t sb_bootstrap_writer_close(sb_bootstrap_writer* w);
+
+/* Transcript FASTA (plain / gzip, multi-line) -> the arrays sb_index_build takes, with the `salmon index` options of
+ * src/index/BuildSalmonIndex.cpp:72-124: --gencode (name ends at the first '|'), --decoys (names listed in a file;
+ * decoys must come last, first_decoy feeds sb_map_params.first_decoy), --no-clip (poly-A clipping off: by default a
+ * run of more than 10 trailing A is removed), --keepDuplicates (by default sequence-identical transcripts are
+ * dropped, the first one is kept).  Non-ACGT bases become code 4 (no k-mers; the reference's pufferfish replaces
+ * them with random bases -- documented deviation).  complete_len = length before clipping (quant.sf "Length"). */
+typedef struct sb_txome {
+  uint32_t n_txps, first_decoy;      /* first_decoy == n_txps: no decoys */
+  const char* const* names;
+  const uint64_t* seq_off;           /* [n_txps+1] */
+  const uint8_t* codes;
+  const uint32_t* complete_len;
+  uint32_t n_duplicates_removed, n_clipped, n_short, reserved;
+} sb_txome;
+int sb_txome_read_fasta(const char* path, uint32_t k, int gencode, const char* decoys_path, int no_clip,
+                        int keep_duplicates, sb_txome** out);
+void sb_txome_free(sb_txome* t);
+
 /* ---- Stage A: index, per-read mapping, equivalence-class builder ------------------
  * Seam B1: the body of processReads<IndexT> (src/quant/SalmonQuantify.cpp:1026-1874: per read
  * MemCollector / findChains / joinReadsAndFilter / PuffAligner::calculateAlignments /

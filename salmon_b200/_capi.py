@@ -113,7 +113,35 @@ class sb_map_partial(C.Structure):
                 ("cluster_hits", C.POINTER(C.c_uint64)), ("cluster_root", C.POINTER(C.c_uint32)), ("assigned", C.c_uint64)]
 
 
+class sb_eq_file(C.Structure):
+    _fields_ = [
+        ("n_txps", C.c_uint32), ("has_weights", C.c_uint32), ("n_classes", C.c_uint64),
+        ("names", C.POINTER(C.c_char_p)), ("off", C.c_void_p), ("tids", C.c_void_p), ("weights", C.c_void_p),
+        ("counts", C.c_void_p), ("eff_len", C.c_void_p), ("n_missing_eff_len", C.c_uint32), ("reserved", C.c_uint32),
+    ]
+
+
+class sb_txome(C.Structure):
+    _fields_ = [
+        ("n_txps", C.c_uint32), ("first_decoy", C.c_uint32), ("names", C.POINTER(C.c_char_p)),
+        ("seq_off", C.c_void_p), ("codes", C.c_void_p), ("complete_len", C.c_void_p),
+        ("n_duplicates_removed", C.c_uint32), ("n_clipped", C.c_uint32), ("n_short", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
 SYMBOLS = {
+    "sb_reads_open": (_P, [_P, _P, C.c_uint32, C.c_uint32]),
+    "sb_reads_next": (C.c_int64, [_P, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
+    "sb_reads_close": (None, [_P]),
+    "sb_eq_file_read": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(sb_eq_file))]),
+    "sb_eq_file_free": (None, [C.POINTER(sb_eq_file)]),
+    "sb_bootstrap_writer_open": (_P, [C.c_char_p]),
+    "sb_bootstrap_writer_write": (C.c_int, [_P, _P, C.c_uint32]),
+    "sb_bootstrap_writer_close": (C.c_int64, [_P]),
+    "sb_txome_read_fasta": (C.c_int, [C.c_char_p, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.c_int,
+                                      C.POINTER(C.POINTER(sb_txome))]),
+    "sb_txome_free": (None, [C.POINTER(sb_txome)]),
     "sb_version": (C.c_int, []),
     "sb_last_error": (C.c_char_p, []),
     "sb_device_count": (C.c_int, []),
@@ -582,3 +610,123 @@ def write_eq_classes(path, names, off, tids, counts, weights=None):
     _check(load().sb_write_eq_classes(str(path).encode(), len(names), C.cast(arr, C.c_void_p), counts.shape[0],
                                       off.ctypes.data, tids.ctypes.data, None if w is None else w.ctypes.data,
                                       counts.ctypes.data), "sb_write_eq_classes")
+
+
+# ---- input seam (host code; no device needed) ------------------------------------------------------------------------
+def _view(ptr, n, dtype):
+    """Copy n items of dtype from a C pointer into a fresh numpy array."""
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n).copy()
+
+
+class ReadFiles:
+    """FASTQ/FASTA reader (sb_reads_*): mirrors how salmon consumes fastx_parser<ReadPair> / <ReadSeq>
+    (src/quant/SalmonQuantify.cpp:1118-1141): batches of reads, here as base codes."""
+
+    def __init__(self, files1, files2=None, n_threads=4):
+        lib = load()
+        files1 = [files1] if isinstance(files1, (str, bytes, os.PathLike)) else list(files1)
+        if files2 is not None:
+            files2 = [files2] if isinstance(files2, (str, bytes, os.PathLike)) else list(files2)
+            if len(files2) != len(files1):
+                raise ValueError("the two mate file lists differ in length")
+        self.paired = files2 is not None
+        a1 = (C.c_char_p * len(files1))(*[os.fsencode(f) for f in files1])
+        a2 = (C.c_char_p * len(files1))(*[os.fsencode(f) for f in files2]) if self.paired else None
+        self.lib = lib
+        self.h = lib.sb_reads_open(a1, a2, len(files1), n_threads)
+        if not self.h:
+            raise SalmonB200Error(lib.sb_last_error().decode())
+
+    def next_batch(self, max_pairs, stride, out=None):
+        """-> (n, left[n,stride], right[n,stride] | None, len_left[n], len_right[n] | None); n == 0 at the end."""
+        if out is None:
+            out = (np.empty((max_pairs, stride), np.uint8), np.empty((max_pairs, stride), np.uint8) if self.paired else None,
+                   np.empty(max_pairs, np.uint32), np.empty(max_pairs, np.uint32) if self.paired else None)
+        left, right, ll, lr = out
+        n = self.lib.sb_reads_next(self.h, max_pairs, stride, left.ctypes.data,
+                                   right.ctypes.data if self.paired else None, ll.ctypes.data,
+                                   lr.ctypes.data if self.paired else None)
+        _check(n, "sb_reads_next")
+        return n, left[:n], (right[:n] if self.paired else None), ll[:n], (lr[:n] if self.paired else None)
+
+    def close(self):
+        if self.h:
+            self.lib.sb_reads_close(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def read_eq_classes(path):
+    """--eqclasses reader (src/util/SalmonUtils.cpp:1024-1122) -> dict(names, eq=EqClasses, eff_len, has_weights, n_missing_eff_len)."""
+    lib = load()
+    pf = C.POINTER(sb_eq_file)()
+    _check(lib.sb_eq_file_read(os.fsencode(path), C.byref(pf)), "sb_eq_file_read")
+    f = pf.contents
+    try:
+        M, Cn = f.n_txps, f.n_classes
+        off = _view(f.off, Cn + 1, np.uint64)
+        nnz = int(off[-1]) if Cn else 0
+        tids = _view(f.tids, nnz, np.uint32)
+        w = _view(f.weights, nnz, np.float64) if f.has_weights else None
+        counts = _view(f.counts, Cn, np.uint64)
+        names = [f.names[i].decode() for i in range(M)]
+        eff = _view(f.eff_len, M, np.float64)
+        return {"names": names, "n_txps": M, "off": off, "tids": tids, "weights": w, "counts": counts,
+                "eff_len": eff, "has_weights": bool(f.has_weights), "n_missing_eff_len": int(f.n_missing_eff_len)}
+    finally:
+        lib.sb_eq_file_free(pf)
+
+
+class BootstrapWriter:
+    """aux_info/bootstrap/bootstraps.gz (src/output/GZipWriter.cpp:765-789)."""
+
+    def __init__(self, path):
+        self.lib = load()
+        self.h = self.lib.sb_bootstrap_writer_open(os.fsencode(path))
+        if not self.h:
+            raise SalmonB200Error(self.lib.sb_last_error().decode())
+
+    def write(self, sample):
+        sample = np.ascontiguousarray(sample, dtype=np.float64)
+        _check(self.lib.sb_bootstrap_writer_write(self.h, sample.ctypes.data, sample.shape[0]), "sb_bootstrap_writer_write")
+
+    def close(self):
+        n = 0
+        if self.h:
+            n = self.lib.sb_bootstrap_writer_close(self.h)
+            self.h = None
+        return n
+
+
+def read_txome_fasta(path, k=31, gencode=False, decoys=None, no_clip=False, keep_duplicates=False):
+    """`salmon index -t` input handling -> dict(names, seqs (list of code arrays), complete_len, first_decoy, ...)."""
+    lib = load()
+    pt = C.POINTER(sb_txome)()
+    _check(lib.sb_txome_read_fasta(os.fsencode(path), k, int(gencode), os.fsencode(decoys) if decoys else None,
+                                   int(no_clip), int(keep_duplicates), C.byref(pt)), "sb_txome_read_fasta")
+    t = pt.contents
+    try:
+        M = t.n_txps
+        off = _view(t.seq_off, M + 1, np.uint64)
+        codes = _view(t.codes, int(off[-1]) if M else 0, np.uint8)
+        return {"names": [t.names[i].decode() for i in range(M)], "seq_off": off, "codes": codes,
+                "seqs": [codes[int(off[i]):int(off[i + 1])] for i in range(M)],
+                "complete_len": _view(t.complete_len, M, np.uint32), "first_decoy": int(t.first_decoy),
+                "n_duplicates_removed": int(t.n_duplicates_removed), "n_clipped": int(t.n_clipped),
+                "n_short": int(t.n_short)}
+    finally:
+        lib.sb_txome_free(pt)

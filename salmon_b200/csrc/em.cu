@@ -43,23 +43,27 @@ struct KernelSet {
   void (*p2)(EmArgs, uint32_t);
   void (*p2_partial)(EmArgs);
 };
-template <int CH, int MINB>
+template <int CH, int MINB, int MODE>
 static KernelSet make_set(const char* name) {
   KernelSet k;
   k.name = name;
   k.smem = em_smem<CH>();
-  k.persistent = (const void*)k_em_persistent<CH, MINB>;
-  k.persistent_mgpu = (const void*)k_em_persistent_mgpu<CH, MINB>;
-  k.p1 = k_em_p1<CH, MINB>;
-  k.p2 = k_em_p2<CH, MINB>;
-  k.p2_partial = k_em_p2_partial<CH, MINB>;
+  k.persistent = (const void*)k_em_persistent<CH, MINB, MODE>;
+  k.persistent_mgpu = (const void*)k_em_persistent_mgpu<CH, MINB, MODE>;
+  k.p1 = k_em_p1<CH, MINB, MODE>;
+  k.p2 = k_em_p2<CH, MINB, MODE>;
+  k.p2_partial = k_em_p2_partial<CH, MINB, MODE>;
   return k;
 }
-constexpr int N_KERNEL_SETS = 6;
+// MODE 0: lane-per-row loop with inline epilogues (round-1 kernel); MODE 1 / 2: batched streaming (8 / 16 gathers
+// per lane in flight, epilogues after the stream), see run_phase_b.
+constexpr int N_KERNEL_SETS = 11;
 static const KernelSet& kernel_set(int cfg) {
   static const KernelSet sets[N_KERNEL_SETS] = {
-      make_set<8, 3>("ch8b3"),  make_set<16, 2>("ch16b2"), make_set<8, 4>("ch8b4"),
-      make_set<4, 4>("ch4b4"),  make_set<4, 3>("ch4b3"),   make_set<8, 2>("ch8b2"),
+      make_set<8, 3, 0>("ch8b3"),     make_set<16, 2, 0>("ch16b2"),   make_set<8, 4, 0>("ch8b4"),
+      make_set<4, 4, 0>("ch4b4"),     make_set<4, 3, 0>("ch4b3"),     make_set<8, 2, 0>("ch8b2"),
+      make_set<16, 2, 1>("ch16b2m1"), make_set<16, 2, 2>("ch16b2m2"), make_set<8, 2, 1>("ch8b2m1"),
+      make_set<8, 3, 1>("ch8b3m1"),   make_set<8, 4, 1>("ch8b4m1"),
   };
   if (cfg < 0 || cfg >= N_KERNEL_SETS) cfg = 0;
   return sets[cfg];
@@ -315,12 +319,13 @@ __global__ void k_sell_fill(uint32_t n_rows, uint32_t n_slices, const uint32_t* 
 }
 // contiguous, work-balanced slice ranges per warp: work(slice) = width + overhead
 __global__ void k_warp_ranges(uint32_t n_slices, const uint32_t* __restrict__ slice_ptr,
-                              uint32_t overhead, uint32_t n_warps, uint32_t* __restrict__ warp_begin) {
+                              uint32_t overhead, uint32_t n_warps, const uint64_t* __restrict__ targets,
+                              uint32_t* __restrict__ warp_begin) {
   const uint32_t wid = blockIdx.x * blockDim.x + threadIdx.x;
   if (wid > n_warps) return;
   if (wid == n_warps || n_slices == 0) { warp_begin[wid] = n_slices; return; }
   const uint64_t total = (uint64_t)slice_ptr[n_slices] + (uint64_t)overhead * n_slices;
-  const uint64_t target = total * wid / n_warps;
+  const uint64_t target = targets ? targets[wid] : total * wid / n_warps;
   uint32_t lo = 0, hi = n_slices;  // first slice whose cumulative work (before it) >= target
   while (lo < hi) {
     uint32_t mid = (lo + hi) >> 1;
@@ -495,12 +500,16 @@ extern "C" sb_em_ctx* sb_em_create(int device) {
   c->n_sm = prop.multiProcessorCount;
   c->l2_bytes = (size_t)prop.l2CacheSize;
   for (int i = 0; i < 4; ++i) cudaEventCreate(&c->ev[i]);
+  // development overrides of the tuning defaults (sweeps over the test-suite)
+  if (const char* e = getenv("SB_EM_CONFIG")) { const int v = atoi(e); if (v >= 0 && v < N_KERNEL_SETS) c->config = v; }
+  if (const char* e = getenv("SB_EM_LWARP")) { const int v = atoi(e); if (v >= 1) c->lwarp = v; }
+  if (const char* e = getenv("SB_EM_BALANCE")) c->balance_long = atoi(e);
   return c;
 }
 
 static void free_sell(SellDev& m) {
   void** ptrs[] = {(void**)&m.slice_ptr, (void**)&m.width, (void**)&m.len, (void**)&m.idx,
-                   (void**)&m.w, (void**)&m.warp_begin, (void**)&m.long_rows};
+                   (void**)&m.w, (void**)&m.warp_begin, (void**)&m.long_rows, (void**)&m.targets};
   for (void** p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -516,7 +525,7 @@ static void free_all(sb_em_ctx* c) {
                    (void**)&c->d_valid, (void**)&c->d_scalars, (void**)&c->d_tcnt,
                    (void**)&c->d_tid_row, (void**)&c->m_off, (void**)&c->m_idx,
                    (void**)&c->m_idx_state, (void**)&c->m_w, (void**)&c->t_off, (void**)&c->t_idx,
-                   (void**)&c->t_w, (void**)&c->d_cnt, (void**)&c->d_scale, (void**)&c->d_ent_cls,
+                   (void**)&c->t_w, (void**)&c->d_cnt, (void**)&c->d_scale, (void**)&c->d_raw1, (void**)&c->d_raw2, (void**)&c->d_ent_cls,
                    (void**)&c->d_row_tid, (void**)&c->d_rank_tid, (void**)&c->d_rowperm,
                    (void**)&c->d_order, (void**)&c->d_sort_keys, (void**)&c->d_sort_vals,
                    (void**)&c->d_sort_keys2, (void**)&c->d_sort_vals2, (void**)&c->d_tmp,
@@ -561,6 +570,10 @@ extern "C" int sb_em_set_option(sb_em_ctx* c, const char* key, int64_t value) {
   } else if (!strcmp(key, "lmax")) {
     if (value < 1 || value > 60000) { set_error("lmax out of range"); return SB_ERR_INVALID; }
     c->lmax = (int)value; c->prepared = false;
+  } else if (!strcmp(key, "lwarp")) {
+    if (value < 1 || value > 1000000) { set_error("lwarp out of range"); return SB_ERR_INVALID; }
+    c->lwarp = (int)value; c->prepared = false;
+  } else if (!strcmp(key, "balance_long")) { c->balance_long = (int)value; c->prepared = false;
   } else if (!strcmp(key, "l2_keep_cm")) { c->keep_cm = (int)value; }
   else if (!strcmp(key, "l2_keep_tm")) { c->keep_tm = (int)value; }
   else if (!strcmp(key, "overhead_p1")) { c->ovh_p1 = (int)value; c->prepared = false; }
@@ -684,10 +697,8 @@ static int build_sell(sb_em_ctx* c, SellDev& m, uint32_t n_rows, const uint32_t*
                                                      m.w, m.long_rows, d_nlong + 1);
     c->launches++;
   }
-  k_warp_ranges<<<nblk(n_warps + 1, 256), 256, 0, st>>>(m.n_slices, m.slice_ptr, overhead, n_warps,
-                                                        m.warp_begin);
-  c->launches++;
   m.n_block = 0;
+  std::vector<uint64_t> h_targets;
   if (m.n_long > 0) {
     // every long row is reduced independently with a fixed tree, so the list order does
     // not affect results.  Longest first: the first n_block rows (> LWARP entries) take
@@ -702,13 +713,50 @@ static int build_sell(sb_em_ctx* c, SellDev& m, uint32_t n_rows, const uint32_t*
       return lx != ly ? lx > ly : h[3 * x] < h[3 * y];
     });
     for (uint32_t i = 0; i < m.n_long; ++i)
-      if (h[3 * ord[i] + 2] - h[3 * ord[i] + 1] > (uint32_t)LWARP) m.n_block = i + 1;
+      if (h[3 * ord[i] + 2] - h[3 * ord[i] + 1] > (uint32_t)c->lwarp) m.n_block = i + 1;
     std::vector<uint32_t> h2(h.size());
     for (uint32_t i = 0; i < m.n_long; ++i)
       for (int k = 0; k < 3; ++k) h2[3 * i + k] = h[3 * ord[i] + k];
     SB_CUDA(cudaMemcpyAsync(m.long_rows, h2.data(), h2.size() * 4, cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaStreamSynchronize(st));
+    if (c->balance_long > 0 && n_warps > 0) {
+      // The long rows are dealt to warps / blocks by position in the list; charge their cost (in slice columns,
+      // balance_long = percent of one column per 32 entries) to the owner's share of the slice stream.
+      const uint32_t wpb = EM_THREADS / 32, grid = n_warps / wpb;
+      std::vector<double> extra(n_warps, 0.0);
+      for (uint32_t i = 0; i < m.n_long; ++i) {
+        const double L = (double)(h2[3 * i + 2] - h2[3 * i + 1]);
+        if (i < m.n_block) {
+          const uint32_t b = i % grid;
+          for (uint32_t w = 0; w < wpb; ++w) extra[b * wpb + w] += L / EM_THREADS * c->balance_long / 100.0 + 8.0;
+        } else {
+          extra[(i - m.n_block) % n_warps] += L / 32.0 * c->balance_long / 100.0 + 4.0;
+        }
+      }
+      const double total = (double)ncols + (double)overhead * m.n_slices;
+      double sum_extra = 0.0;
+      for (double e : extra) sum_extra += e;
+      const double T = (total + sum_extra) / n_warps;
+      double sum_share = 0.0;
+      for (uint32_t w = 0; w < n_warps; ++w) sum_share += std::max(0.0, T - extra[w]);
+      h_targets.resize(n_warps);
+      double cum = 0.0;
+      for (uint32_t w = 0; w < n_warps; ++w) {
+        h_targets[w] = (uint64_t)(sum_share > 0.0 ? total * (cum / sum_share) : total * w / n_warps);
+        cum += std::max(0.0, T - extra[w]);
+      }
+    }
   }
+  uint64_t* d_targets = nullptr;
+  if (!h_targets.empty()) {
+    SB_TRY(dev_alloc(&m.targets, (size_t)n_warps));
+    SB_CUDA(cudaMemcpyAsync(m.targets, h_targets.data(), h_targets.size() * 8, cudaMemcpyHostToDevice, st));
+    d_targets = m.targets;
+  }
+  k_warp_ranges<<<nblk(n_warps + 1, 256), 256, 0, st>>>(m.n_slices, m.slice_ptr, overhead, n_warps, d_targets,
+                                                        m.warp_begin);
+  c->launches++;
+  SB_CUDA(cudaStreamSynchronize(st));   // h_targets must outlive the copy
   return SB_OK;
 }
 
@@ -823,6 +871,8 @@ extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* s
   SB_TRY(dev_alloc(&c->d_scale, (size_t)Cm + 4));
   SB_TRY(dev_alloc(&c->d_ent_cls, (size_t)nnzm));
   SB_CUDA(cudaMemsetAsync(c->d_scale, 0, ((size_t)Cm + 4) * 8, st));
+  SB_TRY(dev_alloc(&c->d_raw1, (size_t)Cm + 32));
+  SB_TRY(dev_alloc(&c->d_raw2, (size_t)M + 32));
   SB_CUDA(cudaMemcpyAsync(c->m_off + Cm, &nnzm, 4, cudaMemcpyHostToDevice, st));
   if (C) {
     k_compact<<<nblk(C, 128), 128, 0, st>>>(C, c->d_order, c->d_off, c->d_tids, c->d_cw, c->d_counts,
@@ -942,6 +992,7 @@ static void fill_args(sb_em_ctx* c, EmArgs& A, bool row_space) {
   A.cm.keep_pct = (uint32_t)c->keep_cm;
   A.tm.keep_pct = (uint32_t)c->keep_tm;
   A.c_cnt = c->ov_cnt ? c->ov_cnt : c->d_cnt; A.scale = c->d_scale;
+  A.raw1 = c->d_raw1; A.raw2 = c->d_raw2;
   if (row_space) {
     A.alpha = c->r_alpha; A.theta = c->r_theta; A.prior = c->r_prior;
     A.base = c->ov_base_row ? c->ov_base_row : c->r_base;

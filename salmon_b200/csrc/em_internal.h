@@ -19,6 +19,7 @@ struct SellDev {
   double* w = nullptr;
   uint32_t* warp_begin = nullptr;
   uint32_t* long_rows = nullptr;
+  uint64_t* targets = nullptr;   // optional per-warp cumulative work targets (balance_long)
   const uint32_t* csr_idx = nullptr;  // not owned
   const double* csr_w = nullptr;      // not owned
 };
@@ -39,6 +40,8 @@ struct sb_em_ctx {
   int occ = 0;
   int ovh_p1 = 3, ovh_p2 = 12;
   int lmax = 96;                    // longest row kept on the lane-per-row SELL path
+  int lwarp = 2048;                 // longest row reduced by one warp (longer: one block)
+  int balance_long = 0;             // charge the long rows of a warp / block to its share of the slice stream
   int keep_cm = 100, keep_tm = 30;  // % of stream chunks pinned in L2 (evict_last)  // per-slice epilogue cost (in columns) for the work split
 
   // problem
@@ -80,6 +83,7 @@ struct sb_em_ctx {
   uint8_t* d_valid = nullptr;
   double* d_cnt = nullptr;        // counts of compact classes (as f64)
   double* d_scale = nullptr;      // count/denom per compact class
+  double *d_raw1 = nullptr, *d_raw2 = nullptr;   // per-row sums of the batched streaming path
   uint32_t* d_ent_cls = nullptr;
   uint32_t *d_sort_keys = nullptr, *d_sort_vals = nullptr, *d_sort_keys2 = nullptr,
            *d_sort_vals2 = nullptr;

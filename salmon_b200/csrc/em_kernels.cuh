@@ -55,6 +55,7 @@ struct EmArgs {
   Sell tm;                      // rows = active transcripts;           idx = class id
   const double* c_cnt;          // [classes] count as f64
   double* scale;                // [classes] count / denom
+  double* raw1; double* raw2;   // batched streaming (run_phase_b): per-row sums of the SELL path, [rows of cm] / [rows of tm]
   // iteration state.  Single GPU: indexed by ROW of tm (cm.idx holds rows).  Multi GPU:
   // indexed by transcript id (cm.idx holds ids) and row_tid maps tm rows to ids.
   double* alpha; double* theta; const double* prior; const double* base;
@@ -359,6 +360,202 @@ __device__ __forceinline__ void run_phase(const EmArgs& A, WarpCtx<CH>& W, const
   }
 }
 
+
+// The SELL stream of one warp's slice range: raw[row] = sum_j gsrc[idx_j] * w_j in column order (see run_phase_b).
+template <int CH, int NB, bool GUARD>
+__device__ __forceinline__ void stream_sell(const Sell& S, WarpCtx<CH>& W, const WarpRange& R,
+                                            const double* gsrc, double* raw) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t s0 = R.s0, s1 = R.s1;
+  const uint32_t cbeg = R.cbeg, cend = R.cend;
+  const uint32_t nchunks = (cend - cbeg + CH - 1) / CH;
+  const uint32_t n_rows = S.n_rows;
+  uint32_t sbase = s0;
+  uint32_t sp = (s0 + lane < s1) ? __ldg(&S.slice_ptr[s0 + lane + 1]) : cend;
+  uint32_t s = s0;
+  uint32_t slice_end = __shfl_sync(0xffffffffu, sp, 0);
+  uint32_t col = cbeg;
+  double acc = 0.0;
+  auto boundary = [&]() {   // slice s is complete
+    const uint32_t row = s * 32u + lane;
+    if (row < n_rows) raw[row] = acc;
+    acc = 0.0;
+    ++s;
+    if (s < s1) {
+      if (s - sbase == 32u) {
+        sbase = s;
+        sp = (s + lane < s1) ? __ldg(&S.slice_ptr[s + lane + 1]) : cend;
+      }
+      slice_end = __shfl_sync(0xffffffffu, sp, (int)(s - sbase));
+    }
+  };
+  for (uint32_t k = 0; k < nchunks; ++k) {
+    const int st = k % RING;
+    mbar_wait(&W.bars[st], (W.phase_bits >> st) & 1u);
+    W.phase_bits ^= (1u << st);
+    const uint32_t* sidx = W.ring->idx[st] + lane;
+    const double* sw = W.ring->w[st] + lane;
+    const uint32_t cstop = min(cend, cbeg + (k + 1) * CH);
+    auto step = [&](double gj, double wj) {
+      while (col == slice_end && s < s1) boundary();   // warp-uniform (possibly zero-width slices)
+      double v = gj * wj;
+      if (GUARD && isnan(v)) v = 0.0;
+      acc += v;
+      ++col;
+    };
+#pragma unroll 1
+    for (uint32_t l0 = 0; col < cstop; l0 += NB * 32u) {
+      const uint32_t nb = cstop - col;   // columns left in this chunk (>= 1)
+      double g[NB];
+      if (nb >= (uint32_t)NB) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) g[j] = gsrc[sidx[l0 + j * 32]];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) step(g[j], sw[l0 + j * 32]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) g[j] = ((uint32_t)j < nb) ? gsrc[sidx[l0 + j * 32]] : 0.0;
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          if ((uint32_t)j < nb) step(g[j], sw[l0 + j * 32]);
+      }
+    }
+    __syncwarp();
+    if (k + RING < nchunks) ring_issue(S, W, R, k + RING);
+  }
+  while (s < s1) boundary();
+}
+
+// ---- batched streaming (MODE 1) ----------------------------------------------------------------------------------
+// The lane-per-row loop above is bound by the latency of the gathers: a warp waits one L2 round trip per group of
+// columns it has in flight, and with short slices (a class has ~6 members) that is 2-3 round trips per slice
+// (ncu r1: 42 % of the warp-time at the grid barriers, long-scoreboard on the first use of every gather group, and
+// per-warp phase times that match  #groups x L2 latency).  Here the gathers of NB consecutive COLUMNS of the chunk
+// are issued together, whatever slices they belong to (the indices are already in shared memory); the slice
+// boundaries are handled while the values are consumed.  The per-row epilogue (count/denominator; digamma/exp) is
+// taken out of the stream: a boundary only stores the row's sum, and after the stream the warp finishes its rows
+// lane-parallel with all operand loads independent.  Summation order per row is unchanged -> same bits as MODE 0.
+template <int PHASE, int CH, int NB>
+__device__ __forceinline__ void run_phase_b(const EmArgs& A, WarpCtx<CH>& W, const WarpRange& R,
+                                            uint32_t bid, uint32_t nblk, double logNorm, double bias,
+                                            P2Acc& pa) {
+  static_assert(CH % NB == 0, "batch must divide the chunk");
+  const Sell& S = (PHASE == 1) ? A.cm : A.tm;
+  const double* gsrc = (PHASE == 1) ? A.theta : A.scale;   // rewritten by other blocks: coherent loads only
+  double* raw = (PHASE == 1) ? A.raw1 : A.raw2;
+  const bool em_nan_guard = (PHASE == 1) && !A.vbem;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t s0 = R.s0, s1 = R.s1;
+  // long rows first: they are the longest single items of a phase (critical path), the stream's first chunks are
+  // already in flight (ring_prefetch) and land meanwhile.
+  // very long rows: whole block per row, fixed-order tree reduction
+  for (uint32_t li = bid; li < S.n_block; li += nblk) {
+    const uint32_t r = __ldg(&S.long_rows[3 * li]);
+    const uint32_t b = __ldg(&S.long_rows[3 * li + 1]);
+    const uint32_t e = __ldg(&S.long_rows[3 * li + 2]);
+    double a0 = 0.0, a1 = 0.0;
+    uint32_t k = b + threadIdx.x;
+    for (; k + EM_THREADS < e; k += 2 * EM_THREADS) {
+      const uint32_t i0 = __ldg(&S.csr_idx[k]), i1 = __ldg(&S.csr_idx[k + EM_THREADS]);
+      double v0 = gsrc[i0] * __ldg(&S.csr_w[k]);
+      double v1 = gsrc[i1] * __ldg(&S.csr_w[k + EM_THREADS]);
+      if (em_nan_guard) {
+        if (isnan(v0)) v0 = 0.0;
+        if (isnan(v1)) v1 = 0.0;
+      }
+      a0 += v0;
+      a1 += v1;
+    }
+    if (k < e) {
+      double v = gsrc[__ldg(&S.csr_idx[k])] * __ldg(&S.csr_w[k]);
+      if (em_nan_guard && isnan(v)) v = 0.0;
+      a0 += v;
+    }
+    const double acc = block_reduce<false>(a0 + a1, W.scratch);
+    if (threadIdx.x == 0) {
+      RowOps o = load_ops<PHASE>(A, S, r);
+      o.len = 0;  // force the epilogue for this long row
+      row_finish<PHASE>(A, r, o, acc, logNorm, bias, pa);
+    }
+    __syncthreads();
+  }
+  // long rows (LMAX < len <= lwarp): one warp per row, 4 independent gathers per lane in flight
+  {
+    const uint32_t gw = bid * EM_WARPS + (threadIdx.x >> 5);
+    const uint32_t nw = nblk * EM_WARPS;
+    uint32_t cnt = 0, myrow = 0xffffffffu;
+    double myacc = 0.0;
+    auto flush = [&]() {
+      if (myrow != 0xffffffffu) {
+        RowOps o = load_ops<PHASE>(A, S, myrow);
+        o.len = 0;
+        row_finish<PHASE>(A, myrow, o, myacc, logNorm, bias, pa);
+      }
+      myrow = 0xffffffffu;
+      cnt = 0;
+    };
+    for (uint32_t li = S.n_block + gw; li < S.n_long; li += nw) {
+      const uint32_t r = __ldg(&S.long_rows[3 * li]);
+      const uint32_t b = __ldg(&S.long_rows[3 * li + 1]);
+      const uint32_t e = __ldg(&S.long_rows[3 * li + 2]);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      uint32_t k = b + lane;
+      for (; k + 96 < e; k += 128) {
+        const uint32_t i0 = __ldg(&S.csr_idx[k]), i1 = __ldg(&S.csr_idx[k + 32]);
+        const uint32_t i2 = __ldg(&S.csr_idx[k + 64]), i3 = __ldg(&S.csr_idx[k + 96]);
+        const double g0 = gsrc[i0], g1 = gsrc[i1], g2 = gsrc[i2], g3 = gsrc[i3];
+        double v0 = g0 * __ldg(&S.csr_w[k]), v1 = g1 * __ldg(&S.csr_w[k + 32]);
+        double v2 = g2 * __ldg(&S.csr_w[k + 64]), v3 = g3 * __ldg(&S.csr_w[k + 96]);
+        if (em_nan_guard) {
+          if (isnan(v0)) v0 = 0.0;
+          if (isnan(v1)) v1 = 0.0;
+          if (isnan(v2)) v2 = 0.0;
+          if (isnan(v3)) v3 = 0.0;
+        }
+        a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+      }
+      for (; k < e; k += 32) {
+        double v = gsrc[__ldg(&S.csr_idx[k])] * __ldg(&S.csr_w[k]);
+        if (em_nan_guard && isnan(v)) v = 0.0;
+        a0 += v;
+      }
+      const double acc = warp_sum((a0 + a1) + (a2 + a3));
+      if (lane == cnt) { myacc = acc; myrow = r; }
+      if (++cnt == 32) flush();
+    }
+    flush();
+  }
+  if (s1 > s0) {
+    if (em_nan_guard) stream_sell<CH, NB, true>(S, W, R, gsrc, raw);
+    else stream_sell<CH, NB, false>(S, W, R, gsrc, raw);
+    if (W.dbg && lane == 0) *W.dbg = gtime_ns();
+    // epilogues of my rows, two slices at a time (operand loads of both in flight together)
+    for (uint32_t q = s0; q < s1; q += 2) {
+      const uint32_t r0 = q * 32u + lane, r1 = r0 + 32u;
+      const bool has1 = (q + 1 < s1);
+      RowOps o0 = load_ops<PHASE>(A, S, r0);
+      RowOps o1;
+      o1.x0 = o1.x1 = o1.x2 = o1.x3 = 0.0;
+      o1.len = LEN_LONG;
+      if (has1) o1 = load_ops<PHASE>(A, S, r1);
+      const double v0 = (r0 < S.n_rows) ? raw[r0] : 0.0;
+      const double v1 = (has1 && r1 < S.n_rows) ? raw[r1] : 0.0;
+      row_finish<PHASE>(A, r0, o0, v0, logNorm, bias, pa);
+      row_finish<PHASE>(A, r1, o1, v1, logNorm, bias, pa);
+    }
+  } else if (W.dbg && lane == 0) {
+    *W.dbg = gtime_ns();
+  }
+}
+
+template <int PHASE, int CH, int MODE>
+__device__ __forceinline__ void run_phase_m(const EmArgs& A, WarpCtx<CH>& W, const WarpRange& R,
+                                            uint32_t bid, uint32_t nblk, double logNorm, double bias,
+                                            P2Acc& pa) {
+  if constexpr (MODE == 0) run_phase<PHASE, CH>(A, W, R, bid, nblk, logNorm, bias, pa);
+  else run_phase_b<PHASE, CH, (MODE == 2 && CH % 16 == 0) ? 16 : 8>(A, W, R, bid, nblk, logNorm, bias, pa);
+}
+
 // alphaSum of the iteration input, from the per-block partials of the previous P2
 __device__ __forceinline__ double sum_partials(const double* part, uint32_t n, double extra,
                                                double* scratch) {
@@ -396,7 +593,7 @@ __device__ __forceinline__ void p2_finish(const EmArgs& A, double* scratch, P2Ac
   if (A.dbg && it == A.dbg_it && (threadIdx.x & 31u) == 0) A.dbg[(size_t)gwarp * 8 + (slot)] = gtime_ns();
 
 // ---- persistent cooperative kernel: the whole iteration loop, two grid barriers/iter
-template <int CH, int MINB>
+template <int CH, int MINB, int MODE>
 __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent(const __grid_constant__ EmArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   WarpCtx<CH> W;
@@ -417,7 +614,7 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent(const __grid
     if (A.vbem && it > 0) lag_lognorm_warp0(A, par, nblk, scratch);  // consumed after the next barrier
     P2Acc pa{0.0, 0.0};
     SB_DBG(0)
-    run_phase<1, CH>(A, W, R1, bid, nblk, 0.0, 0.0, pa);
+    run_phase_m<1, CH, MODE>(A, W, R1, bid, nblk, 0.0, 0.0, pa);
     SB_DBG(1)
     ring_prefetch(A.tm, W, R2);   // P2's stream lands during the grid barrier
     grid.sync();
@@ -426,7 +623,7 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent(const __grid
     const double bias = (it == 0) ? A.first_bias : 0.0;  // alphasPrime starts at 1.0 (:812,:821)
     SB_DBG(3)
     W.dbg = (A.dbg && it == A.dbg_it) ? &A.dbg[(size_t)gwarp * 8 + 7] : nullptr;
-    run_phase<2, CH>(A, W, R2, bid, nblk, logNorm, bias, pa);
+    run_phase_m<2, CH, MODE>(A, W, R2, bid, nblk, logNorm, bias, pa);
     W.dbg = nullptr;
     SB_DBG(4)
     ring_prefetch(A.cm, W, R1);   // next iteration's P1 stream (harmless if the loop ends)
@@ -491,7 +688,7 @@ __device__ __forceinline__ void xgpu_barrier(cg::grid_group& grid, const EmArgs&
   grid.sync();
 }
 
-template <int CH, int MINB>
+template <int CH, int MINB, int MODE>
 __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent_mgpu(const __grid_constant__ EmArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   WarpCtx<CH> W;
@@ -514,10 +711,10 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent_mgpu(const _
     const uint32_t par = it & 1u;
     if (bid == 0 && threadIdx.x == 0) A.maxrel[par] = 0ull;
     P2Acc pa{0.0, 0.0};
-    run_phase<1, CH>(A, W, R1, bid, nblk, 0.0, 0.0, pa);
+    run_phase_m<1, CH, MODE>(A, W, R1, bid, nblk, 0.0, 0.0, pa);
     ring_prefetch(A.tm, W, R2);
     grid.sync();
-    run_phase<3, CH>(A, W, R2, bid, nblk, 0.0, 0.0, pa);      // A.part_out = own exchange block
+    run_phase_m<3, CH, MODE>(A, W, R2, bid, nblk, 0.0, 0.0, pa);      // A.part_out = own exchange block
     ring_prefetch(A.cm, W, R1);
     xgpu_barrier(grid, A, ++epoch);                            // every rank's partial is complete and visible
     for (uint32_t t = lo + gtid; t < hi; t += gthreads) {
@@ -564,7 +761,7 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent_mgpu(const _
 }
 
 // ---- one launch per phase (baseline variant; also the multi-GPU building blocks)
-template <int CH, int MINB>
+template <int CH, int MINB, int MODE>
 __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p1(const __grid_constant__ EmArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   WarpCtx<CH> W;
@@ -572,9 +769,9 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p1(const __grid_constan
   P2Acc pa{0.0, 0.0};
   const WarpRange R = load_range(A.cm, blockIdx.x * (EM_THREADS / 32) + (threadIdx.x >> 5));
   ring_prefetch(A.cm, W, R);
-  run_phase<1, CH>(A, W, R, blockIdx.x, gridDim.x, 0.0, 0.0, pa);
+  run_phase_m<1, CH, MODE>(A, W, R, blockIdx.x, gridDim.x, 0.0, 0.0, pa);
 }
-template <int CH, int MINB>
+template <int CH, int MINB, int MODE>
 __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p2(const __grid_constant__ EmArgs A, uint32_t it) {
   extern __shared__ __align__(128) unsigned char smem[];
   WarpCtx<CH> W;
@@ -595,10 +792,10 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p2(const __grid_constan
   P2Acc pa{0.0, 0.0};
   const WarpRange R = load_range(A.tm, blockIdx.x * (EM_THREADS / 32) + (threadIdx.x >> 5));
   ring_prefetch(A.tm, W, R);
-  run_phase<2, CH>(A, W, R, blockIdx.x, gridDim.x, logNorm, bias, pa);
+  run_phase_m<2, CH, MODE>(A, W, R, blockIdx.x, gridDim.x, logNorm, bias, pa);
   p2_finish(A, scratch, pa, par);
 }
-template <int CH, int MINB>
+template <int CH, int MINB, int MODE>
 __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p2_partial(const __grid_constant__ EmArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   WarpCtx<CH> W;
@@ -606,7 +803,7 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p2_partial(const __grid
   P2Acc pa{0.0, 0.0};
   const WarpRange R = load_range(A.tm, blockIdx.x * (EM_THREADS / 32) + (threadIdx.x >> 5));
   ring_prefetch(A.tm, W, R);
-  run_phase<3, CH>(A, W, R, blockIdx.x, gridDim.x, 0.0, 0.0, pa);
+  run_phase_m<3, CH, MODE>(A, W, R, blockIdx.x, gridDim.x, 0.0, 0.0, pa);
 }
 
 }  // namespace sb

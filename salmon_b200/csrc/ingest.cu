@@ -1,0 +1,562 @@
+// ingest.cu -- the input seam of the hot path (host code, no device work): what sits immediately before seam B1 and
+// B3 in the reference:
+//   * sb_reads_*   : FASTQ / FASTA (plain or gzip) -> batches of base codes.  Replaces FQFeeder's
+//                    fastx_parser<ReadPair> / <ReadSeq> as salmon drives it (src/quant/SalmonQuantify.cpp:2357-2373
+//                    parser construction, :2419-2430 start(), :1118-1141 the per-thread ReadGroup loop).
+//   * sb_eq_file_* : the --eqclasses reader (src/util/SalmonUtils.cpp:1024-1122 readEquivCounts).
+//   * sb_bootstrap_writer_* : aux_info/bootstrap/bootstraps.gz (src/output/GZipWriter.cpp:765-789 writeBootstrap).
+//   * sb_txome_*   : transcript FASTA -> names / base codes / decoy boundary, the input of sb_index_build
+//                    (src/index/BuildSalmonIndex.cpp:72-124 options; the FASTA "fixing" itself is pufferfish code that is
+//                    not in the reference tree, the rules here follow the option help strings).
+//
+// Design: one splitter thread per mate stream inflates / reads 8 MiB chunks and cuts them at record boundaries (three
+// memchr per record), queueing blocks with a (offset, length) list of the sequence lines; sb_reads_next() hands the
+// records of a batch to an OpenMP team that translates bytes to codes straight into the caller's (pinned) buffers.
+#include <stdio.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+// base byte -> code (0..3 = A,C,G,T; everything else 4 = N).  U is read as T.
+struct CodeLut {
+  uint8_t t[256];
+  CodeLut() {
+    memset(t, 4, sizeof t);
+    t['A'] = t['a'] = 0; t['C'] = t['c'] = 1; t['G'] = t['g'] = 2; t['T'] = t['t'] = 3; t['U'] = t['u'] = 3;
+  }
+};
+const CodeLut LUT;
+
+struct RecBlock {
+  std::vector<char> buf;       // raw text of whole records
+  std::vector<uint32_t> seq;   // 2 per record: offset, length of the sequence line
+  uint32_t n = 0;
+};
+
+struct Stream {
+  std::vector<std::string> files;
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv_put, cv_get;
+  std::deque<std::unique_ptr<RecBlock>> q;
+  bool done = false, stop = false;
+  std::string err;
+  // consumer side
+  std::unique_ptr<RecBlock> cur;
+  uint32_t cur_pos = 0;
+};
+
+constexpr size_t CHUNK = 8u << 20;
+constexpr size_t MAX_QUEUED = 8;
+
+bool push_block(Stream* s, std::unique_ptr<RecBlock> b) {
+  std::unique_lock<std::mutex> lk(s->mu);
+  s->cv_put.wait(lk, [&] { return s->q.size() < MAX_QUEUED || s->stop; });
+  if (s->stop) return false;
+  s->q.push_back(std::move(b));
+  s->cv_get.notify_one();
+  return true;
+}
+
+void finish_stream(Stream* s, const std::string& err) {
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (!err.empty()) s->err = err;
+  s->done = true;
+  s->cv_get.notify_all();
+}
+
+inline size_t line_len(const char* b, const char* e) {   // length without a trailing '\r'
+  size_t n = (size_t)(e - b);
+  if (n && b[n - 1] == '\r') --n;
+  return n;
+}
+
+// Cut `len` bytes at buf into whole records.  Returns the number of bytes consumed; records are appended to blk->seq
+// with offsets relative to buf.  eof: no more data follows (the last line may lack its newline).
+size_t scan_records(const char* buf, size_t len, bool eof, RecBlock* blk, std::string& err) {
+  size_t p = 0, cut = 0;
+  while (p < len) {
+    const char c = buf[p];
+    if (c == '\n' || c == '\r') { ++p; cut = p; continue; }
+    if (c != '@' && c != '>') { err = "malformed read file: record does not start with '@' or '>'"; return cut; }
+    const char* nl1 = (const char*)memchr(buf + p, '\n', len - p);
+    if (!nl1) break;
+    const size_t s0 = (size_t)(nl1 - buf) + 1;
+    const char* nl2 = (const char*)memchr(buf + s0, '\n', len - s0);
+    if (c == '>') {
+      size_t send, next;
+      if (nl2) { send = (size_t)(nl2 - buf); next = send + 1; }
+      else if (eof) { send = len; next = len; }
+      else break;
+      if (next >= len && !eof) break;          // cannot see whether the sequence continues on another line
+      if (next < len && buf[next] != '>' && buf[next] != '\n' && buf[next] != '\r') {
+        err = "multi-line FASTA reads are not supported";
+        return cut;
+      }
+      blk->seq.push_back((uint32_t)s0);
+      blk->seq.push_back((uint32_t)line_len(buf + s0, buf + send));
+      p = next; cut = p;
+      continue;
+    }
+    if (!nl2) break;
+    const size_t slen = line_len(buf + s0, nl2);
+    const size_t p3 = (size_t)(nl2 - buf) + 1;
+    if (p3 >= len) break;
+    if (buf[p3] != '+') { err = "malformed FASTQ: third line of a record does not start with '+' (multi-line FASTQ is not supported)"; return cut; }
+    const char* nl3 = (const char*)memchr(buf + p3, '\n', len - p3);
+    if (!nl3) break;
+    const size_t q0 = (size_t)(nl3 - buf) + 1;
+    const char* nl4 = (q0 < len) ? (const char*)memchr(buf + q0, '\n', len - q0) : nullptr;
+    size_t qend, next;
+    if (nl4) { qend = (size_t)(nl4 - buf); next = qend + 1; }
+    else if (eof && q0 <= len) { qend = len; next = len; }
+    else break;
+    if (line_len(buf + q0, buf + qend) != slen) { err = "malformed FASTQ: quality and sequence lengths differ"; return cut; }
+    blk->seq.push_back((uint32_t)s0);
+    blk->seq.push_back((uint32_t)slen);
+    p = next; cut = p;
+  }
+  return cut;
+}
+
+void split_stream(Stream* s) {
+  std::string err;
+  for (const std::string& path : s->files) {
+    gzFile g = gzopen(path.c_str(), "rb");
+    if (!g) { err = "cannot open " + path; break; }
+    gzbuffer(g, 1u << 20);
+    std::vector<char> carry;
+    bool eof = false;
+    while (!eof && err.empty()) {
+      std::unique_ptr<RecBlock> blk(new RecBlock());
+      blk->buf.resize(carry.size() + CHUNK);
+      if (!carry.empty()) memcpy(blk->buf.data(), carry.data(), carry.size());
+      const int got = gzread(g, blk->buf.data() + carry.size(), (unsigned)CHUNK);
+      if (got < 0) { int e; err = std::string("read error in ") + path + ": " + gzerror(g, &e); break; }
+      const size_t len = carry.size() + (size_t)got;
+      eof = (size_t)got < CHUNK;
+      const size_t cut = scan_records(blk->buf.data(), len, eof, blk.get(), err);
+      if (!err.empty()) { err += " (" + path + ")"; break; }
+      carry.assign(blk->buf.data() + cut, blk->buf.data() + len);
+      blk->buf.resize(cut);
+      blk->n = (uint32_t)(blk->seq.size() / 2);
+      if (eof) {
+        for (char ch : carry)
+          if (ch != '\n' && ch != '\r' && ch != ' ' && ch != '\t') { err = "truncated record at the end of " + path; break; }
+      }
+      if (blk->n && err.empty() && !push_block(s, std::move(blk))) { gzclose(g); finish_stream(s, ""); return; }
+    }
+    gzclose(g);
+    if (!err.empty()) break;
+  }
+  finish_stream(s, err);
+}
+
+struct Task {
+  const RecBlock* blk;
+  uint32_t from, cnt;
+  uint64_t dst;
+  int mate;
+};
+
+}  // namespace
+
+struct sb_reads {
+  Stream st[2];
+  int n_streams = 0;
+  uint32_t n_threads = 1;
+  uint64_t n_delivered = 0;
+  uint32_t max_len_seen = 0;
+  bool failed = false;
+};
+
+extern "C" sb_reads* sb_reads_open(const char* const* files1, const char* const* files2, uint32_t n_files,
+                                   uint32_t n_threads) {
+  if (!files1 || !n_files) { sb::set_error("sb_reads_open: no input files"); return nullptr; }
+  sb_reads* r = new sb_reads();
+  r->n_streams = files2 ? 2 : 1;
+  r->n_threads = n_threads ? n_threads : 1;
+  for (uint32_t i = 0; i < n_files; ++i) {
+    if (!files1[i] || (files2 && !files2[i])) { delete r; sb::set_error("sb_reads_open: null file name"); return nullptr; }
+    r->st[0].files.push_back(files1[i]);
+    if (files2) r->st[1].files.push_back(files2[i]);
+  }
+  for (int m = 0; m < r->n_streams; ++m) r->st[m].th = std::thread(split_stream, &r->st[m]);
+  return r;
+}
+
+extern "C" void sb_reads_close(sb_reads* r) {
+  if (!r) return;
+  for (int m = 0; m < r->n_streams; ++m) {
+    { std::lock_guard<std::mutex> lk(r->st[m].mu); r->st[m].stop = true; }
+    r->st[m].cv_put.notify_all();
+    if (r->st[m].th.joinable()) r->st[m].th.join();
+  }
+  delete r;
+}
+
+extern "C" int64_t sb_reads_next(sb_reads* r, uint32_t max_pairs, uint32_t stride, uint8_t* left, uint8_t* right,
+                                 uint32_t* len_left, uint32_t* len_right) {
+  if (!r || !left || !len_left || !stride || (r->n_streams == 2 && (!right || !len_right))) {
+    sb::set_error("sb_reads_next: null argument"); return SB_ERR_INVALID;
+  }
+  if (r->failed) { sb::set_error("sb_reads_next: the reader is in a failed state"); return SB_ERR_INVALID; }
+  std::vector<Task> tasks;
+  std::vector<std::unique_ptr<RecBlock>> retired;
+  uint64_t filled[2] = {0, 0};
+  for (int m = 0; m < r->n_streams; ++m) {
+    Stream& s = r->st[m];
+    while (filled[m] < max_pairs) {
+      if (!s.cur) {
+        std::unique_lock<std::mutex> lk(s.mu);
+        s.cv_get.wait(lk, [&] { return !s.q.empty() || s.done; });
+        if (!s.err.empty()) { r->failed = true; sb::set_error("%s", s.err.c_str()); return SB_ERR_INVALID; }
+        if (s.q.empty()) break;   // end of the stream
+        s.cur = std::move(s.q.front());
+        s.q.pop_front();
+        s.cur_pos = 0;
+        s.cv_put.notify_one();
+      }
+      const uint32_t take = (uint32_t)std::min<uint64_t>(s.cur->n - s.cur_pos, max_pairs - filled[m]);
+      for (uint32_t o = 0; o < take; o += 2048)
+        tasks.push_back(Task{s.cur.get(), s.cur_pos + o, std::min(2048u, take - o), filled[m] + o, m});
+      s.cur_pos += take;
+      filled[m] += take;
+      if (s.cur_pos == s.cur->n) retired.push_back(std::move(s.cur));
+    }
+  }
+  if (r->n_streams == 2 && filled[0] != filled[1]) {
+    r->failed = true;
+    sb::set_error("the mate files hold different numbers of records (after %llu pairs)",
+                  (unsigned long long)(r->n_delivered + std::min(filled[0], filled[1])));
+    return SB_ERR_INVALID;
+  }
+  uint32_t maxlen = 0;
+  const int nt = (int)std::max<size_t>(1, std::min<size_t>(r->n_threads, tasks.size()));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt) reduction(max : maxlen)
+  for (long ti = 0; ti < (long)tasks.size(); ++ti) {
+    const Task& t = tasks[ti];
+    uint8_t* out = t.mate ? right : left;
+    uint32_t* lens = t.mate ? len_right : len_left;
+    for (uint32_t i = 0; i < t.cnt; ++i) {
+      const uint32_t off = t.blk->seq[2 * (size_t)(t.from + i)], len = t.blk->seq[2 * (size_t)(t.from + i) + 1];
+      maxlen = std::max(maxlen, len);
+      lens[t.dst + i] = len;
+      const uint32_t n = std::min(len, stride);
+      const uint8_t* src = (const uint8_t*)t.blk->buf.data() + off;
+      uint8_t* d = out + (t.dst + i) * (size_t)stride;
+      for (uint32_t j = 0; j < n; ++j) d[j] = LUT.t[src[j]];
+      if (n < stride) memset(d + n, 4, stride - n);
+    }
+  }
+  r->max_len_seen = std::max(r->max_len_seen, maxlen);
+  if (maxlen > stride) {
+    r->failed = true;
+    sb::set_error("a read of %u bases exceeds the buffer stride of %u", maxlen, stride);
+    return SB_ERR_INVALID;
+  }
+  r->n_delivered += filled[0];
+  return (int64_t)filled[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// --eqclasses reader
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+bool slurp(const char* path, std::string& out, std::string& err) {
+  gzFile g = gzopen(path, "rb");
+  if (!g) { err = std::string("cannot open ") + path; return false; }
+  gzbuffer(g, 1u << 20);
+  std::vector<char> buf(4u << 20);
+  for (;;) {
+    const int got = gzread(g, buf.data(), (unsigned)buf.size());
+    if (got < 0) { int e; err = std::string("read error in ") + path + ": " + gzerror(g, &e); gzclose(g); return false; }
+    out.append(buf.data(), (size_t)got);
+    if ((size_t)got < buf.size()) break;
+  }
+  gzclose(g);
+  return true;
+}
+struct Tok {   // whitespace tokenizer that also knows where lines end
+  const char* p; const char* e;
+  void skip_ws() { while (p < e && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p; }
+  bool next(const char*& b, size_t& n) {
+    skip_ws();
+    if (p >= e) return false;
+    b = p;
+    while (p < e && !(*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p;
+    n = (size_t)(p - b);
+    return true;
+  }
+};
+struct EqFileStore {
+  sb_eq_file pub;
+  std::vector<std::string> names;
+  std::vector<const char*> name_ptrs;
+  std::vector<uint64_t> off, counts;
+  std::vector<uint32_t> tids;
+  std::vector<double> weights, eff;
+};
+}  // namespace
+
+extern "C" int sb_eq_file_read(const char* path, sb_eq_file** out) {
+  if (!path || !out) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  std::string text, err;
+  if (!slurp(path, text, err)) { sb::set_error("%s", err.c_str()); return SB_ERR_INVALID; }
+  std::unique_ptr<EqFileStore> S(new EqFileStore());
+  Tok tk{text.data(), text.data() + text.size()};
+  const char* b; size_t n;
+  auto bad = [&](const char* what) { sb::set_error("%s: %s", path, what); return SB_ERR_INVALID; };
+  auto get_u64 = [&](uint64_t& v) {
+    if (!tk.next(b, n)) return false;
+    char* endp = nullptr;
+    v = strtoull(b, &endp, 10);
+    return endp == b + n;
+  };
+  uint64_t numTxps = 0, numEq = 0;
+  if (!get_u64(numTxps) || !get_u64(numEq)) return bad("missing transcript / class counts");
+  if (numTxps > 0xffffffffull) return bad("too many transcripts");
+  S->names.reserve(numTxps);
+  std::unordered_map<std::string, uint32_t> nameToIndex;
+  nameToIndex.reserve(numTxps * 2);
+  for (uint64_t i = 0; i < numTxps; ++i) {
+    if (!tk.next(b, n)) return bad("truncated transcript name list");
+    S->names.emplace_back(b, n);
+    nameToIndex[S->names.back()] = (uint32_t)i;
+  }
+  S->off.reserve(numEq + 1);
+  S->off.push_back(0);
+  S->counts.reserve(numEq);
+  int has_w = -1;
+  for (uint64_t c = 0; c < numEq; ++c) {
+    uint64_t k = 0;
+    if (!get_u64(k) || k == 0) return bad("bad class size");
+    for (uint64_t i = 0; i < k; ++i) {
+      uint64_t t;
+      if (!get_u64(t) || t >= numTxps) return bad("bad transcript id in a class");
+      S->tids.push_back((uint32_t)t);
+    }
+    // the rest of the line: either `count` or `w_1 .. w_k count` (--dumpEqWeights, what readEquivCounts expects)
+    const char* line_end = (const char*)memchr(tk.p, '\n', (size_t)(tk.e - tk.p));
+    if (!line_end) line_end = tk.e;
+    size_t ntok = 0;
+    { Tok t2{tk.p, line_end}; const char* bb; size_t nn; while (t2.next(bb, nn)) ++ntok; }
+    const int w_here = (ntok == k + 1) ? 1 : (ntok == 1 ? 0 : -1);
+    if (w_here < 0) return bad("class line has neither `count` nor `weights count` after the ids");
+    if (has_w < 0) has_w = w_here;
+    if (has_w != w_here) return bad("classes with and without weights are mixed");
+    if (w_here)
+      for (uint64_t i = 0; i < k; ++i) {
+        if (!tk.next(b, n)) return bad("truncated class");
+        char* endp = nullptr;
+        const double w = strtod(b, &endp);
+        if (endp != b + n) return bad("bad weight");
+        S->weights.push_back(w);
+      }
+    uint64_t cnt;
+    if (!get_u64(cnt)) return bad("bad class count");
+    S->counts.push_back(cnt);
+    S->off.push_back(S->tids.size());
+  }
+  // optional trailer: `name effective_length` lines; missing ones are set to 100.0 (SalmonUtils.cpp:1109-1116)
+  S->eff.assign(numTxps, 100.0);
+  std::vector<uint8_t> seen(numTxps, 0);
+  uint32_t n_seen = 0;
+  while (tk.next(b, n)) {
+    std::string nm(b, n);
+    if (!tk.next(b, n)) return bad("effective-length trailer: name without a value");
+    char* endp = nullptr;
+    const double v = strtod(b, &endp);
+    if (endp != b + n) return bad("effective-length trailer: bad value");
+    auto it = nameToIndex.find(nm);
+    if (it == nameToIndex.end()) return bad("effective-length trailer names an unknown transcript");
+    if (!seen[it->second]) { seen[it->second] = 1; ++n_seen; }
+    S->eff[it->second] = v;
+  }
+  S->name_ptrs.resize(numTxps);
+  for (uint64_t i = 0; i < numTxps; ++i) S->name_ptrs[i] = S->names[i].c_str();
+  sb_eq_file& P = S->pub;
+  memset(&P, 0, sizeof P);
+  P.n_txps = (uint32_t)numTxps;
+  P.has_weights = has_w > 0 ? 1u : 0u;
+  P.n_classes = numEq;
+  P.names = S->name_ptrs.data();
+  P.off = S->off.data();
+  P.tids = S->tids.data();
+  P.weights = P.has_weights ? S->weights.data() : nullptr;
+  P.counts = S->counts.data();
+  P.eff_len = S->eff.data();
+  P.n_missing_eff_len = (uint32_t)(numTxps - n_seen);
+  *out = &S.release()->pub;
+  return SB_OK;
+}
+
+extern "C" void sb_eq_file_free(sb_eq_file* f) {
+  if (f) delete reinterpret_cast<EqFileStore*>(f);   // pub is the first member
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// bootstraps.gz
+// ---------------------------------------------------------------------------------------------------------------------
+struct sb_bootstrap_writer {
+  gzFile g = nullptr;
+  std::mutex mu;
+  uint64_t n_written = 0;
+};
+
+extern "C" sb_bootstrap_writer* sb_bootstrap_writer_open(const char* path) {
+  if (!path) { sb::set_error("null argument"); return nullptr; }
+  gzFile g = gzopen(path, "wb6");   // zstr::ofstream(..., level 6), GZipWriter.cpp:774-776
+  if (!g) { sb::set_error("cannot open %s", path); return nullptr; }
+  sb_bootstrap_writer* w = new sb_bootstrap_writer();
+  w->g = g;
+  return w;
+}
+
+// One sample = n raw native-endian doubles appended to the stream (GZipWriter.cpp:779-783); callable from several
+// threads like the reference's writeBootstrap (serialised by a mutex, :766-771).
+extern "C" int sb_bootstrap_writer_write(sb_bootstrap_writer* w, const double* sample, uint32_t n) {
+  if (!w || !sample) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  std::lock_guard<std::mutex> lk(w->mu);
+  const size_t bytes = (size_t)n * sizeof(double);
+  size_t done = 0;
+  while (done < bytes) {
+    const unsigned part = (unsigned)std::min<size_t>(bytes - done, 1u << 30);
+    if (gzwrite(w->g, (const char*)sample + done, part) != (int)part) { sb::set_error("write error (bootstraps)"); return SB_ERR_INVALID; }
+    done += part;
+  }
+  ++w->n_written;
+  return SB_OK;
+}
+
+extern "C" int64_t sb_bootstrap_writer_close(sb_bootstrap_writer* w) {
+  if (!w) return 0;
+  const int64_t n = (int64_t)w->n_written;
+  gzclose(w->g);
+  delete w;
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// transcript FASTA -> sb_txome
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct TxomeStore {
+  sb_txome pub;
+  std::vector<std::string> names;
+  std::vector<const char*> name_ptrs;
+  std::vector<uint64_t> seq_off;
+  std::vector<uint8_t> codes;
+  std::vector<uint32_t> complete_len;
+};
+inline uint64_t fnv1a(const uint8_t* p, size_t n) {
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+}  // namespace
+
+extern "C" int sb_txome_read_fasta(const char* path, uint32_t k, int gencode, const char* decoys_path, int no_clip,
+                                   int keep_duplicates, sb_txome** out) {
+  if (!path || !out) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  std::string text, err;
+  if (!slurp(path, text, err)) { sb::set_error("%s", err.c_str()); return SB_ERR_INVALID; }
+  std::unordered_set<std::string> decoys;
+  if (decoys_path && *decoys_path) {
+    std::string dtext;
+    if (!slurp(decoys_path, dtext, err)) { sb::set_error("%s", err.c_str()); return SB_ERR_INVALID; }
+    Tok tk{dtext.data(), dtext.data() + dtext.size()};
+    const char* b; size_t n;
+    while (tk.next(b, n)) decoys.emplace(b, n);
+  }
+  std::unique_ptr<TxomeStore> S(new TxomeStore());
+  S->seq_off.push_back(0);
+  std::unordered_map<uint64_t, std::vector<uint32_t>> by_hash;
+  uint32_t n_dup = 0, n_clipped = 0, n_short = 0, first_decoy = 0xffffffffu;
+  const char* p = text.data();
+  const char* e = p + text.size();
+  std::vector<uint8_t> seq;
+  while (p < e) {
+    while (p < e && (*p == '\n' || *p == '\r')) ++p;
+    if (p >= e) break;
+    if (*p != '>') { sb::set_error("%s: expected '>' at the start of a record", path); return SB_ERR_INVALID; }
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+    if (!nl) nl = e;
+    const char* hb = p + 1;
+    const char* he = hb;
+    // the name ends at the first white space (or, with --gencode, at the first '|'; BuildSalmonIndex.cpp:82-88)
+    while (he < nl && *he != ' ' && *he != '\t' && *he != '\r' && !(gencode && *he == '|')) ++he;
+    std::string name(hb, he);
+    p = (nl < e) ? nl + 1 : e;
+    seq.clear();
+    while (p < e && *p != '>') {
+      const char* l2 = (const char*)memchr(p, '\n', (size_t)(e - p));
+      if (!l2) l2 = e;
+      for (const char* q = p; q < l2; ++q)
+        if (*q != '\r' && *q != ' ') seq.push_back(LUT.t[(uint8_t)*q]);
+      p = (l2 < e) ? l2 + 1 : e;
+    }
+    const uint32_t complete = (uint32_t)seq.size();
+    const bool is_decoy = decoys.count(name) != 0;
+    if (is_decoy) {
+      if (first_decoy == 0xffffffffu) first_decoy = (uint32_t)S->names.size();
+    } else if (first_decoy != 0xffffffffu) {
+      sb::set_error("%s: the non-decoy sequence %s follows a decoy; decoys must come last", path, name.c_str());
+      return SB_ERR_INVALID;
+    }
+    // poly-A clipping (--no-clip turns it off): a run of more than 10 trailing A's is removed
+    if (!no_clip && !is_decoy) {
+      size_t a = seq.size();
+      while (a > 0 && seq[a - 1] == 0) --a;
+      if (seq.size() - a > 10) { seq.resize(a); ++n_clipped; }
+    }
+    if (seq.size() < k) ++n_short;
+    if (!keep_duplicates && !is_decoy) {
+      const uint64_t h = fnv1a(seq.data(), seq.size());
+      auto& cand = by_hash[h];
+      bool dup = false;
+      for (uint32_t t : cand) {
+        const uint64_t b0 = S->seq_off[t], n0 = S->seq_off[t + 1] - b0;
+        if (n0 == seq.size() && (n0 == 0 || memcmp(S->codes.data() + b0, seq.data(), n0) == 0)) { dup = true; break; }
+      }
+      if (dup) { ++n_dup; continue; }
+      cand.push_back((uint32_t)S->names.size());
+    }
+    S->names.push_back(std::move(name));
+    S->complete_len.push_back(complete);
+    S->codes.insert(S->codes.end(), seq.begin(), seq.end());
+    S->seq_off.push_back(S->codes.size());
+  }
+  S->name_ptrs.resize(S->names.size());
+  for (size_t i = 0; i < S->names.size(); ++i) S->name_ptrs[i] = S->names[i].c_str();
+  sb_txome& P = S->pub;
+  memset(&P, 0, sizeof P);
+  P.n_txps = (uint32_t)S->names.size();
+  P.first_decoy = (first_decoy == 0xffffffffu) ? P.n_txps : first_decoy;
+  P.names = S->name_ptrs.data();
+  P.seq_off = S->seq_off.data();
+  P.codes = S->codes.data();
+  P.complete_len = S->complete_len.data();
+  P.n_duplicates_removed = n_dup;
+  P.n_clipped = n_clipped;
+  P.n_short = n_short;
+  *out = &S.release()->pub;
+  return SB_OK;
+}
+
+extern "C" void sb_txome_free(sb_txome* t) {
+  if (t) delete reinterpret_cast<TxomeStore*>(t);
+}

@@ -1,0 +1,245 @@
+"""Input seam (host code, no GPU): FASTQ/FASTA reader, --eqclasses reader, bootstraps.gz writer, transcript FASTA
+loader.  The checker is an independent pure-Python parse of the same files; formats follow the reference
+(FQFeeder records as consumed in src/quant/SalmonQuantify.cpp:1118-1141; src/util/SalmonUtils.cpp:1024-1122;
+src/output/GZipWriter.cpp:64-168,765-789; src/index/BuildSalmonIndex.cpp:72-124)."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from salmon_b200 import _capi
+
+CODE = {c: i for i, c in enumerate("ACGT")}
+CODE.update({c.lower(): i for c, i in list(CODE.items())})
+
+
+def encode(seq):
+    return np.array([CODE.get(c, 4) for c in seq], dtype=np.uint8)
+
+
+def rand_seq(rng, n, alphabet="ACGT"):
+    return "".join(rng.choice(list(alphabet), size=n))
+
+
+def write_text(path, text, gz):
+    if gz:
+        with gzip.open(path, "wt") as f:
+            f.write(text)
+    else:
+        with open(path, "w") as f:
+            f.write(text)
+
+
+def make_reads(rng, n, lo=30, hi=120):
+    out = []
+    for i in range(n):
+        L = int(rng.integers(lo, hi + 1))
+        s = rand_seq(rng, L, "ACGTNacgt" if i % 7 == 0 else "ACGT")
+        out.append(s)
+    return out
+
+
+def fastq_text(reads, tag, crlf=False, final_newline=True):
+    nl = "\r\n" if crlf else "\n"
+    recs = [f"@r{i}/{tag} extra{nl}{s}{nl}+{nl}{'I' * len(s)}" for i, s in enumerate(reads)]
+    t = nl.join(recs)
+    return t + (nl if final_newline else "")
+
+
+@pytest.mark.parametrize("gz", [False, True])
+@pytest.mark.parametrize("crlf", [False, True])
+def test_fastq_pairs_match_python_parse(tmp_path, gz, crlf):
+    rng = np.random.default_rng(5)
+    n = 5000
+    r1, r2 = make_reads(rng, n), make_reads(rng, n)
+    f1 = tmp_path / ("a_1.fq.gz" if gz else "a_1.fq")
+    f2 = tmp_path / ("a_2.fq.gz" if gz else "a_2.fq")
+    write_text(f1, fastq_text(r1, 1, crlf), gz)
+    write_text(f2, fastq_text(r2, 2, crlf, final_newline=False), gz)
+    got_l, got_r = [], []
+    with _capi.ReadFiles(str(f1), str(f2), n_threads=3) as rf:
+        while True:
+            k, left, right, ll, lr = rf.next_batch(777, 128)
+            if k == 0:
+                break
+            for i in range(k):
+                got_l.append(left[i, :ll[i]].copy())
+                got_r.append(right[i, :lr[i]].copy())
+                assert np.all(left[i, ll[i]:] == 4) and np.all(right[i, lr[i]:] == 4)   # padding
+    assert len(got_l) == n and len(got_r) == n
+    for i in range(n):
+        assert np.array_equal(got_l[i], encode(r1[i])), i
+        assert np.array_equal(got_r[i], encode(r2[i])), i
+
+
+def test_multiple_files_single_end_and_fasta(tmp_path):
+    rng = np.random.default_rng(6)
+    a, b = make_reads(rng, 300), make_reads(rng, 411)
+    fa = tmp_path / "a.fq"
+    fb = tmp_path / "b.fa.gz"
+    write_text(fa, fastq_text(a, 1), False)
+    write_text(fb, "".join(f">s{i} d\n{s}\n" for i, s in enumerate(b)), True)
+    rf = _capi.ReadFiles([str(fa), str(fb)], None, n_threads=2)
+    seqs = []
+    while True:
+        k, left, right, ll, lr = rf.next_batch(128, 120)
+        if k == 0:
+            break
+        assert right is None and lr is None
+        seqs += [left[i, :ll[i]].copy() for i in range(k)]
+    rf.close()
+    want = a + b
+    assert len(seqs) == len(want)
+    assert all(np.array_equal(x, encode(y)) for x, y in zip(seqs, want))
+
+
+def test_large_block_boundaries(tmp_path):
+    # > 8 MiB per file so that records straddle the splitter's chunk boundaries
+    rng = np.random.default_rng(7)
+    n = 60000
+    base = rng.integers(0, 4, size=(n, 100), dtype=np.uint8)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs = [lut[row].tobytes().decode() for row in base]
+    f1, f2 = tmp_path / "l_1.fq", tmp_path / "l_2.fq"
+    write_text(f1, fastq_text(seqs, 1), False)
+    write_text(f2, fastq_text(seqs[::-1], 2), False)
+    assert os.path.getsize(f1) > (8 << 20)
+    tot = 0
+    with _capi.ReadFiles(str(f1), str(f2), n_threads=4) as rf:
+        while True:
+            k, left, right, ll, lr = rf.next_batch(16384, 100)
+            if k == 0:
+                break
+            assert np.all(ll == 100) and np.all(lr == 100)
+            assert np.array_equal(left, base[tot:tot + k])
+            assert np.array_equal(right, base[::-1][tot:tot + k])
+            tot += k
+    assert tot == n
+
+
+def test_reader_errors(tmp_path):
+    rng = np.random.default_rng(8)
+    a = make_reads(rng, 50)
+    f1, f2 = tmp_path / "e_1.fq", tmp_path / "e_2.fq"
+    write_text(f1, fastq_text(a, 1), False)
+    write_text(f2, fastq_text(a[:40], 2), False)
+    rf = _capi.ReadFiles(str(f1), str(f2))
+    with pytest.raises(_capi.SalmonB200Error, match="different numbers of records"):
+        while rf.next_batch(64, 128)[0]:
+            pass
+    rf.close()
+    # a read longer than the stride
+    rf = _capi.ReadFiles(str(f1), None)
+    with pytest.raises(_capi.SalmonB200Error, match="exceeds the buffer stride"):
+        rf.next_batch(64, 20)
+    rf.close()
+    # quality / sequence length mismatch
+    bad = tmp_path / "bad.fq"
+    bad.write_text("@x\nACGT\n+\nIII\n")
+    rf = _capi.ReadFiles(str(bad), None)
+    with pytest.raises(_capi.SalmonB200Error, match="quality and sequence lengths differ"):
+        rf.next_batch(4, 16)
+    rf.close()
+    # truncated record
+    bad.write_text("@x\nACGT\n+\nIIII\n@y\nAC")
+    rf = _capi.ReadFiles(str(bad), None)
+    with pytest.raises(_capi.SalmonB200Error, match="truncated"):
+        while rf.next_batch(4, 16)[0]:
+            pass
+    rf.close()
+    # missing file
+    rf = _capi.ReadFiles(str(tmp_path / "nope.fq"), None)
+    with pytest.raises(_capi.SalmonB200Error, match="cannot open"):
+        rf.next_batch(4, 16)
+    rf.close()
+
+
+def test_eq_classes_round_trip(tmp_path):
+    rng = np.random.default_rng(9)
+    M, Cn = 40, 200
+    names = [f"tx{i}|g" for i in range(M)]
+    sizes = rng.integers(1, 6, size=Cn)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    tids = np.concatenate([np.sort(rng.choice(M, size=k, replace=False)) for k in sizes]).astype(np.uint32)
+    w = rng.random(int(off[-1]))
+    counts = rng.integers(1, 1000, size=Cn).astype(np.uint64)
+    for gz in (False, True):
+        path = str(tmp_path / ("eq.txt.gz" if gz else "eq.txt"))
+        _capi.write_eq_classes(path, names, off, tids, counts, w)
+        got = _capi.read_eq_classes(path)
+        assert got["names"] == names and got["has_weights"] and got["n_missing_eff_len"] == M
+        assert np.array_equal(got["off"], off) and np.array_equal(got["tids"], tids)
+        assert np.array_equal(got["counts"], counts)
+        np.testing.assert_allclose(got["weights"], w, rtol=1e-5)   # the reference prints 6 significant digits
+        assert np.all(got["eff_len"] == 100.0)                       # SalmonUtils.cpp:1109-1116
+    # the trailer with effective lengths, as the reader expects it (readEquivCounts :1095-1107)
+    path = str(tmp_path / "eq_trailer.txt")
+    _capi.write_eq_classes(path, names, off, tids, counts, w)
+    eff = rng.random(M) * 1000 + 1
+    with open(path, "a") as f:
+        for i in rng.permutation(M)[:30]:
+            f.write(f"{names[i]}\t{eff[i]:.17g}\n")
+            eff[i] = -eff[i]
+    got = _capi.read_eq_classes(path)
+    assert got["n_missing_eff_len"] == 10
+    given = eff < 0
+    assert np.array_equal(got["eff_len"][given], -eff[given]) and np.all(got["eff_len"][~given] == 100.0)
+    # without weights (--dumpEq only): classes collapse by transcript set
+    path = str(tmp_path / "eq_now.txt")
+    _capi.write_eq_classes(path, names, off, tids, counts, None)
+    got = _capi.read_eq_classes(path)
+    assert not got["has_weights"] and got["weights"] is None
+    assert int(got["counts"].sum()) == int(counts.sum())
+    # malformed
+    bad = tmp_path / "bad.txt"
+    bad.write_text("2\n1\na\nb\n2\t0\t5\t7\n")
+    with pytest.raises(_capi.SalmonB200Error):
+        _capi.read_eq_classes(str(bad))
+
+
+def test_bootstrap_writer_format(tmp_path):
+    rng = np.random.default_rng(10)
+    path = str(tmp_path / "bootstraps.gz")
+    w = _capi.BootstrapWriter(path)
+    samples = [rng.random(123) * 50 for _ in range(7)]
+    for smp in samples:
+        w.write(smp)
+    assert w.close() == 7
+    raw = gzip.open(path, "rb").read()
+    got = np.frombuffer(raw, dtype=np.float64).reshape(7, 123)   # tximport / fishpond read it exactly like this
+    assert np.array_equal(got, np.stack(samples))
+
+
+def test_txome_fasta_options(tmp_path):
+    rng = np.random.default_rng(11)
+    s0 = rand_seq(rng, 300)
+    s1 = rand_seq(rng, 200) + "A" * 25           # poly-A tail: clipped
+    s2 = s0                                        # duplicate of tx0
+    s3 = rand_seq(rng, 20)                         # shorter than k
+    s4 = rand_seq(rng, 150) + "NNNN" + rand_seq(rng, 50) + "A" * 8   # short A run stays
+    d0 = rand_seq(rng, 500) + "A" * 30             # decoy: never clipped
+    def wrap(s):
+        return "\n".join(s[i:i + 60] for i in range(0, len(s), 60))
+    fa = tmp_path / "t.fa.gz"
+    write_text(fa, "".join(f">{n} desc\n{wrap(s)}\n" for n, s in [
+        ("ENST0|ENSG0|x", s0), ("ENST1|ENSG1|x", s1), ("ENST2|ENSG0|x", s2), ("ENST3|g", s3), ("ENST4|g", s4),
+        ("chr1", d0)]), True)
+    dec = tmp_path / "decoys.txt"
+    dec.write_text("chr1\n")
+    t = _capi.read_txome_fasta(str(fa), k=31, gencode=True, decoys=str(dec))
+    assert t["names"] == ["ENST0", "ENST1", "ENST3", "ENST4", "chr1"]
+    assert t["first_decoy"] == 4 and t["n_duplicates_removed"] == 1 and t["n_clipped"] == 1 and t["n_short"] == 1
+    assert list(t["complete_len"]) == [300, 225, 20, len(s4), 530]
+    assert np.array_equal(t["seqs"][0], encode(s0))
+    assert np.array_equal(t["seqs"][1], encode(s1[:200].rstrip("A")))
+    assert np.array_equal(t["seqs"][3], encode(s4)) and int((t["seqs"][3] == 4).sum()) == 4
+    assert np.array_equal(t["seqs"][4], encode(d0))
+    # --keepDuplicates --no-clip, names up to the first white space
+    t2 = _capi.read_txome_fasta(str(fa), k=31, keep_duplicates=True, no_clip=True)
+    assert t2["names"][0] == "ENST0|ENSG0|x" and len(t2["names"]) == 6 and t2["first_decoy"] == 6
+    assert np.array_equal(t2["seqs"][1], encode(s1))
+    # a decoy in the middle is an error
+    dec.write_text("ENST1|ENSG1|x\n")
+    with pytest.raises(_capi.SalmonB200Error, match="decoys must come last"):
+        _capi.read_txome_fasta(str(fa), k=31, decoys=str(dec))
