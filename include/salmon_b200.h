@@ -229,6 +229,15 @@ typedef struct sb_index sb_index;
  * postings (transcript, offset); own in-memory format.  seq_off[n_txps+1]: base offsets. */
 sb_index* sb_index_build(uint32_t n_txps, const uint64_t* seq_off, const uint8_t* codes, uint32_t k);
 void sb_index_free(sb_index* ix);
+/* Reference metadata carried by the index (what `salmon quant` prints in quant.sf): names, lengths before poly-A
+ * clipping, index of the first decoy (== n_txps: none).  Optional; get returns NULL arrays when never set. */
+int sb_index_set_meta(sb_index* ix, const char* const* names, const uint32_t* complete_len, uint32_t first_decoy);
+int sb_index_get_meta(const sb_index* ix, uint32_t* n_txps, uint32_t* k, uint32_t* first_decoy,
+                      const char* const** names, const uint32_t** complete_len);
+/* On-disk form (own binary format, one file; `salmon index -i dir` analog).  NOT the pufferfish / SSHash layout
+ * (that source is absent from the reference tree). */
+int sb_index_save(const sb_index* ix, const char* path);
+sb_index* sb_index_load(const char* path);
 /* out4 = {distinct k-mers, postings, table capacity, bytes} */
 int sb_index_info(const sb_index* ix, uint64_t* out4);
 /* Raw views of the index arrays (for serialisation): table = {u64 key, u32 first posting, u32 count}

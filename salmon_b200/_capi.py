@@ -169,6 +169,10 @@ SYMBOLS = {
     "sb_flush_l2": (C.c_int, [_P]),
     "sb_index_build": (_P, [C.c_uint32, _P, _P, C.c_uint32]),
     "sb_index_free": (None, [_P]),
+    "sb_index_set_meta": (C.c_int, [_P, _P, _P, C.c_uint32]),
+    "sb_index_get_meta": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "sb_index_save": (C.c_int, [_P, C.c_char_p]),
+    "sb_index_load": (_P, [C.c_char_p]),
     "sb_index_info": (C.c_int, [_P, _P]),
     "sb_index_host_arrays": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "sb_map_default_params": (None, [C.POINTER(sb_map_params)]),
@@ -419,8 +423,57 @@ def map_default_params(**over) -> sb_map_params:
 class Index:
     """sb_index: host-built k-mer hash index over a transcriptome (list of uint8 code arrays)."""
 
-    def __init__(self, txps, k=31):
+    def __init__(self, txps, k=31, names=None, complete_len=None, first_decoy=None, _handle=None):
         self.lib = load()
+        if _handle is not None:
+            self.h = _handle
+            m = self.meta()
+            self.n_txps, self.k = m["n_txps"], m["k"]
+            return
+        self._build(txps, k)
+        if names is not None or complete_len is not None or first_decoy is not None:
+            self.set_meta(names, complete_len, first_decoy)
+
+    @classmethod
+    def load(cls, path):
+        """sb_index_load: the on-disk form written by save()."""
+        lib = load()
+        h = lib.sb_index_load(os.fsencode(path))
+        if not h:
+            raise SalmonB200Error("sb_index_load failed: " + lib.sb_last_error().decode())
+        return cls(None, _handle=h)
+
+    @classmethod
+    def from_fasta(cls, path, k=31, **opts):
+        """`salmon index -t path` (read_txome_fasta options: gencode, decoys, no_clip, keep_duplicates)."""
+        t = read_txome_fasta(path, k=k, **opts)
+        return cls(t["seqs"], k=k, names=t["names"], complete_len=t["complete_len"], first_decoy=t["first_decoy"])
+
+    def save(self, path):
+        _check(self.lib.sb_index_save(self.h, os.fsencode(path)), "sb_index_save")
+
+    def set_meta(self, names=None, complete_len=None, first_decoy=None):
+        na = (C.c_char_p * self.n_txps)(*[n.encode() for n in names]) if names is not None else None
+        cl = np.ascontiguousarray(complete_len, dtype=np.uint32) if complete_len is not None else None
+        _check(self.lib.sb_index_set_meta(self.h, na, cl.ctypes.data if cl is not None else None,
+                                          self.n_txps if first_decoy is None else int(first_decoy)), "sb_index_set_meta")
+
+    def meta(self):
+        n, k, fd = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        names = C.POINTER(C.c_char_p)()
+        cl = C.c_void_p()
+        _check(self.lib.sb_index_get_meta(self.h, C.byref(n), C.byref(k), C.byref(fd), C.byref(names), C.byref(cl)),
+               "sb_index_get_meta")
+        return {"n_txps": n.value, "k": k.value, "first_decoy": fd.value,
+                "names": [names[i].decode() for i in range(n.value)] if names else None,
+                "complete_len": _view(cl.value, n.value, np.uint32) if cl.value else None}
+
+    def tx_lengths(self):
+        ha = self.host_arrays()
+        off = _view(ha["tx_off"], self.n_txps + 1, np.uint64)
+        return (off[1:] - off[:-1]).astype(np.uint32)
+
+    def _build(self, txps, k):
         lens = np.array([t.shape[0] for t in txps], dtype=np.uint64)
         self.off = np.concatenate(([0], np.cumsum(lens))).astype(np.uint64)
         self.codes = np.ascontiguousarray(np.concatenate(txps).astype(np.uint8)) if len(txps) else np.zeros(0, np.uint8)

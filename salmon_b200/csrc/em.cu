@@ -154,13 +154,13 @@ __global__ void k_class_combine(uint64_t C, uint32_t M, const uint64_t* __restri
 
 // second-level key: (locality group, length bucket); dropped rows last
 __global__ void k_bucket_key(uint64_t n, const uint32_t* __restrict__ order,
-                             const uint64_t* __restrict__ packed, uint32_t* __restrict__ key,
-                             uint32_t* __restrict__ val) {
+                             const uint64_t* __restrict__ packed, uint32_t group,
+                             uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
   uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const uint64_t pk = packed[order ? order[p] : p];
   const uint32_t len = (uint32_t)(pk & 0xffffffffu);
-  key[p] = pk ? ((uint32_t)(p / SELL_GROUP) << 9) | min(len, 511u) : 0xffffffffu;
+  key[p] = pk ? ((uint32_t)(p / group) << 9) | min(len, 511u) : 0xffffffffu;
   val[p] = order ? order[p] : (uint32_t)p;
 }
 
@@ -504,6 +504,8 @@ extern "C" sb_em_ctx* sb_em_create(int device) {
   if (const char* e = getenv("SB_EM_CONFIG")) { const int v = atoi(e); if (v >= 0 && v < N_KERNEL_SETS) c->config = v; }
   if (const char* e = getenv("SB_EM_LWARP")) { const int v = atoi(e); if (v >= 1) c->lwarp = v; }
   if (const char* e = getenv("SB_EM_BALANCE")) c->balance_long = atoi(e);
+  if (const char* e = getenv("SB_EM_GROUP_CM")) { const int v = atoi(e); if (v >= 32 && !(v & (v - 1))) c->sell_group_cm = v; }
+  if (const char* e = getenv("SB_EM_GROUP_TM")) { const int v = atoi(e); if (v >= 32 && !(v & (v - 1))) c->sell_group_tm = v; }
   return c;
 }
 
@@ -570,6 +572,9 @@ extern "C" int sb_em_set_option(sb_em_ctx* c, const char* key, int64_t value) {
   } else if (!strcmp(key, "lmax")) {
     if (value < 1 || value > 60000) { set_error("lmax out of range"); return SB_ERR_INVALID; }
     c->lmax = (int)value; c->prepared = false;
+  } else if (!strcmp(key, "sell_group_cm") || !strcmp(key, "sell_group_tm")) {
+    if (value < 32 || value > (1 << 20) || (value & (value - 1))) { set_error("sell_group must be a power of two >= 32"); return SB_ERR_INVALID; }
+    (key[11] == 'c' ? c->sell_group_cm : c->sell_group_tm) = (int)value; c->prepared = false;
   } else if (!strcmp(key, "lwarp")) {
     if (value < 1 || value > 1000000) { set_error("lwarp out of range"); return SB_ERR_INVALID; }
     c->lwarp = (int)value; c->prepared = false;
@@ -845,7 +850,7 @@ extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* s
     SB_TRY(sort_pairs(c, (uint32_t)C, bits_for(M)));
     SB_CUDA(cudaMemcpyAsync(c->d_order, c->d_sort_vals2, C * 4, cudaMemcpyDeviceToDevice, st));
     // (2) inside groups of SELL_GROUP classes, bucket by label length
-    k_bucket_key<<<nblk(C, 256), 256, 0, st>>>(C, c->d_order, c->d_packed, c->d_sort_keys, c->d_sort_vals);
+    k_bucket_key<<<nblk(C, 256), 256, 0, st>>>(C, c->d_order, c->d_packed, (uint32_t)c->sell_group_cm, c->d_sort_keys, c->d_sort_vals);
     c->launches++;
     SB_TRY(sort_pairs(c, (uint32_t)C, 32));
     SB_CUDA(cudaMemcpyAsync(c->d_order, c->d_sort_vals2, C * 4, cudaMemcpyDeviceToDevice, st));
@@ -924,7 +929,7 @@ extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* s
   }
   // rows: ranks bucketed by occurrence count inside groups of SELL_GROUP
   if (R) {
-    k_bucket_key<<<nblk(R, 256), 256, 0, st>>>(R, nullptr, c->d_packed2, c->d_sort_keys, c->d_sort_vals);
+    k_bucket_key<<<nblk(R, 256), 256, 0, st>>>(R, nullptr, c->d_packed2, (uint32_t)c->sell_group_tm, c->d_sort_keys, c->d_sort_vals);
     c->launches++;
     SB_TRY(sort_pairs(c, R, 32));
     SB_CUDA(cudaMemcpyAsync(c->d_rowperm, c->d_sort_vals2, (size_t)R * 4, cudaMemcpyDeviceToDevice, st));

@@ -40,6 +40,7 @@ struct sb_em_ctx {
   int occ = 0;
   int ovh_p1 = 3, ovh_p2 = 12;
   int lmax = 96;                    // longest row kept on the lane-per-row SELL path
+  int sell_group_cm = 1024, sell_group_tm = 1024;   // rows per length-bucketing group (locality window of the gathers)
   int lwarp = 2048;                 // longest row reduced by one warp (longer: one block)
   int balance_long = 0;             // charge the long rows of a warp / block to its share of the slice stream
   int keep_cm = 100, keep_tm = 30;  // % of stream chunks pinned in L2 (evict_last)  // per-slice epilogue cost (in columns) for the work split

@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <parallel/algorithm>
 #include <vector>
+#include <new>
+#include <string>
 
 #include "common.cuh"
 #include "map_core.h"
@@ -30,6 +32,11 @@ struct sb_index {
   std::vector<uint64_t> packed;     // 2-bit packed codes with PACK_GUARD_BASES of guard on both sides
   std::vector<uint8_t> tx_has_n;
   uint64_t n_kmers = 0;
+  // what `salmon quant` needs besides the sequence: names, lengths before clipping, first decoy (optional)
+  std::vector<std::string> names;
+  std::vector<const char*> name_ptrs;
+  std::vector<uint32_t> complete_len;
+  uint32_t first_decoy = 0xffffffffu;   // clamped to n_txps by set_meta / build
   // device copies (one device)
   int device = -1;
   uint64_t* d_tx_off = nullptr;
@@ -65,7 +72,7 @@ extern "C" sb_index* sb_index_build(uint32_t n_txps, const uint64_t* seq_off, co
       return nullptr;
     }
   sb_index* ix = new sb_index();
-  ix->n_txps = n_txps; ix->k = k;
+  ix->n_txps = n_txps; ix->k = k; ix->first_decoy = n_txps;
   ix->tx_off.assign(seq_off, seq_off + n_txps + 1);
   ix->codes.assign(codes, codes + seq_off[n_txps]);
   std::vector<KP> kp;
@@ -153,6 +160,107 @@ extern "C" int sb_index_host_arrays(const sb_index* ix, const uint64_t** tx_off,
   if (postings) *postings = ix->post.data();
   if (n_postings) *n_postings = ix->post.size();
   return SB_OK;
+}
+
+// ---- on-disk form of the index (own format; `salmon index` writes a directory, so do we: <dir>/sb_index.bin).
+// Header + the host arrays verbatim + the reference names / complete lengths / decoy boundary that `salmon quant`
+// needs for quant.sf.  Not the pufferfish / SSHash format (that source is not in the reference tree).
+namespace {
+constexpr uint64_t INDEX_MAGIC = 0x3130584449324253ull;   // "SB2IDX01"
+struct IndexHeader {
+  uint64_t magic;
+  uint32_t version, k, n_txps, first_decoy;
+  uint64_t n_codes, n_table, n_post, n_packed, n_kmers, names_bytes;
+};
+template <typename T>
+bool wr(FILE* f, const T* p, size_t n) { return n == 0 || fwrite(p, sizeof(T), n, f) == n; }
+template <typename T>
+bool rd(FILE* f, T* p, size_t n) { return n == 0 || fread(p, sizeof(T), n, f) == n; }
+}  // namespace
+
+extern "C" int sb_index_set_meta(sb_index* ix, const char* const* names, const uint32_t* complete_len, uint32_t first_decoy) {
+  if (!ix) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  ix->names.clear(); ix->complete_len.clear();
+  if (names) for (uint32_t t = 0; t < ix->n_txps; ++t) ix->names.emplace_back(names[t] ? names[t] : "");
+  if (complete_len) ix->complete_len.assign(complete_len, complete_len + ix->n_txps);
+  ix->first_decoy = first_decoy > ix->n_txps ? ix->n_txps : first_decoy;
+  ix->name_ptrs.clear();
+  for (auto& n : ix->names) ix->name_ptrs.push_back(n.c_str());
+  return SB_OK;
+}
+
+extern "C" int sb_index_get_meta(const sb_index* ix, uint32_t* n_txps, uint32_t* k, uint32_t* first_decoy,
+                                 const char* const** names, const uint32_t** complete_len) {
+  if (!ix) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  if (n_txps) *n_txps = ix->n_txps;
+  if (k) *k = ix->k;
+  if (first_decoy) *first_decoy = ix->first_decoy;
+  if (names) *names = ix->name_ptrs.empty() ? nullptr : ix->name_ptrs.data();
+  if (complete_len) *complete_len = ix->complete_len.empty() ? nullptr : ix->complete_len.data();
+  return SB_OK;
+}
+
+extern "C" int sb_index_save(const sb_index* ix, const char* path) {
+  if (!ix || !path) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  FILE* f = fopen(path, "wb");
+  if (!f) { sb::set_error("cannot open %s for writing", path); return SB_ERR_INVALID; }
+  std::string names;
+  for (auto& n : ix->names) { names += n; names += '\n'; }
+  IndexHeader h{};
+  h.magic = INDEX_MAGIC; h.version = 1; h.k = ix->k; h.n_txps = ix->n_txps; h.first_decoy = ix->first_decoy;
+  h.n_codes = ix->codes.size(); h.n_table = ix->table.size(); h.n_post = ix->post.size(); h.n_packed = ix->packed.size();
+  h.n_kmers = ix->n_kmers; h.names_bytes = names.size();
+  const uint32_t has_len = ix->complete_len.empty() ? 0u : 1u;
+  bool ok = wr(f, &h, 1) && wr(f, &has_len, 1) && wr(f, ix->tx_off.data(), ix->tx_off.size()) &&
+            wr(f, ix->codes.data(), ix->codes.size()) && wr(f, ix->table.data(), ix->table.size()) &&
+            wr(f, ix->post.data(), ix->post.size()) && wr(f, ix->packed.data(), ix->packed.size()) &&
+            wr(f, ix->tx_has_n.data(), ix->tx_has_n.size()) && wr(f, names.data(), names.size()) &&
+            (!has_len || wr(f, ix->complete_len.data(), ix->complete_len.size()));
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) { sb::set_error("write error on %s", path); return SB_ERR_INVALID; }
+  return SB_OK;
+}
+
+extern "C" sb_index* sb_index_load(const char* path) {
+  if (!path) { sb::set_error("null argument"); return nullptr; }
+  FILE* f = fopen(path, "rb");
+  if (!f) { sb::set_error("cannot open %s", path); return nullptr; }
+  IndexHeader h{};
+  uint32_t has_len = 0;
+  if (!rd(f, &h, 1) || h.magic != INDEX_MAGIC || h.version != 1 || !rd(f, &has_len, 1)) {
+    fclose(f); sb::set_error("%s is not an sb index (bad header)", path); return nullptr;
+  }
+  if (h.n_table == 0 || (h.n_table & (h.n_table - 1)) || h.k < 3 || h.k > 31 || h.first_decoy > h.n_txps) {
+    fclose(f); sb::set_error("%s: corrupt header", path); return nullptr;
+  }
+  sb_index* ix = new sb_index();
+  ix->n_txps = h.n_txps; ix->k = h.k; ix->n_kmers = h.n_kmers; ix->first_decoy = h.first_decoy;
+  bool ok = true;
+  try {
+    ix->tx_off.resize((size_t)h.n_txps + 1); ix->codes.resize(h.n_codes); ix->table.resize(h.n_table);
+    ix->post.resize(h.n_post); ix->packed.resize(h.n_packed); ix->tx_has_n.resize(std::max<uint32_t>(h.n_txps, 1));
+    std::string names(h.names_bytes, '\0');
+    ok = rd(f, ix->tx_off.data(), ix->tx_off.size()) && rd(f, ix->codes.data(), ix->codes.size()) &&
+         rd(f, ix->table.data(), ix->table.size()) && rd(f, ix->post.data(), ix->post.size()) &&
+         rd(f, ix->packed.data(), ix->packed.size()) && rd(f, ix->tx_has_n.data(), ix->tx_has_n.size()) &&
+         rd(f, &names[0], names.size());
+    if (ok && has_len) { ix->complete_len.resize(h.n_txps); ok = rd(f, ix->complete_len.data(), ix->complete_len.size()); }
+    if (ok) {
+      size_t b = 0;
+      while (b < names.size()) {
+        size_t e = names.find('\n', b);
+        if (e == std::string::npos) e = names.size();
+        ix->names.emplace_back(names, b, e - b);
+        b = e + 1;
+      }
+      if (!ix->names.empty() && ix->names.size() != h.n_txps) ok = false;
+      for (auto& n : ix->names) ix->name_ptrs.push_back(n.c_str());
+      ok = ok && ix->tx_off[h.n_txps] == h.n_codes;
+    }
+  } catch (const std::bad_alloc&) { ok = false; }
+  fclose(f);
+  if (!ok) { delete ix; sb::set_error("%s: truncated or corrupt index", path); return nullptr; }
+  return ix;
 }
 
 static int index_to_device(sb_index* ix, int device) {
@@ -730,7 +838,7 @@ struct sb_map_ctx {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   sb_index* index = nullptr;
   Params p{};
-  uint32_t batch_cap = 0, read_len_cap = 0, chunk = 0;
+  uint32_t batch_cap = 0, read_len_cap = 0, chunk = 0, chunk_cap = 0;
   int variant = 1;                   // 1 = warp kernels (map_kernels.cuh), 0 = serial-form kernels
   int input_dev = 0;                 // sb_map_batch's read pointers are device pointers (bench: inputs resident in HBM)
   int ascii = 0;                     // reads are sequence characters (ACGTN...) instead of base codes
@@ -909,7 +1017,10 @@ extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int d
   }
   const uint32_t cap = p.max_read_occ;
   const size_t B = batch_cap;
-  c->chunk = (uint32_t)std::min<size_t>(B, 65536);
+  // reads per pipeline chunk: the per-chunk buffers are sized for chunk_cap; SB_MAP_CHUNK raises it for sweeps
+  size_t chunk_cap = 65536;
+  if (const char* e = getenv("SB_MAP_CHUNK")) { const long v = atol(e); if (v >= 1024 && v <= (1 << 24)) chunk_cap = (size_t)v; }
+  c->chunk = c->chunk_cap = (uint32_t)std::min<size_t>(B, chunk_cap);
   const size_t CH = c->chunk;
   c->k1_threads = (uint32_t)std::min<size_t>((size_t)c->n_sm * 1024, (CH + 127) / 128 * 128);
   c->seed_blocks = (uint32_t)c->n_sm * 4;
@@ -1014,7 +1125,7 @@ extern "C" int sb_map_set_option(sb_map_ctx* c, const char* key, int64_t value) 
     c->ascii = value ? 1 : 0; return SB_OK;
   }
   if (!strcmp(key, "chunk")) {   // reads per pipeline chunk (<= the size the context was created with)
-    const uint32_t mx = (uint32_t)std::min<size_t>(c->batch_cap, 65536);
+    const uint32_t mx = c->chunk_cap;
     if (value < 1 || value > (int64_t)mx) { sb::set_error("chunk must be in 1..%u", mx); return SB_ERR_INVALID; }
     c->chunk = (uint32_t)value;
     return SB_OK;

@@ -53,7 +53,10 @@ def quant_reads(index, left, right, map_params=None, em_params=None, device=0, b
     if out_dir is not None and rank == 0:
         os.makedirs(os.path.join(out_dir, "aux_info"), exist_ok=True)
         nm = names or [f"t{i}" for i in range(M)]
-        lens = (index.off[1:] - index.off[:-1]).astype(np.uint32)
+        meta = index.meta()
+        if names is None and meta["names"]:
+            nm = meta["names"]
+        lens = meta["complete_len"] if meta["complete_len"] is not None else index.tx_lengths()
         _capi.write_quant_sf(os.path.join(out_dir, "quant.sf"), nm, lens, inputs["eff_len"], alpha,
                              float(n_mapped) if n_mapped else None)
         if dump_eq or dump_eq_weights:
@@ -61,3 +64,183 @@ def quant_reads(index, left, right, map_params=None, em_params=None, device=0, b
                                    res["counts"], res["weights"] if dump_eq_weights else None)
     return dict(alpha=alpha, tpm=tpm, eff_len=inputs["eff_len"], classes=res, n_mapped=int(n_mapped), em_stats=st,
                 projected_counts=inputs["projected_counts"], unique_counts=inputs["unique_counts"])
+
+
+class _LengthBuckets:
+    """sb_map_batch takes one read length per call; reads are therefore grouped by length on the host.  A pair whose
+    mates differ in length is mapped at the shorter length (the longer mate loses its 3' end) -- documented deviation,
+    the kernels take per-mate lengths in a later round.  Uniform-length input (the common case) passes straight
+    through without a copy."""
+
+    def __init__(self, ctx, batch, k):
+        self.ctx, self.batch, self.k = ctx, batch, k
+        self.pending = {}        # L -> [list of left blocks, list of right blocks, count]
+        self.too_short = 0
+        self.n_in = 0
+
+    def _flush(self, L, force=False):
+        ent = self.pending.get(L)
+        if not ent:
+            return
+        while ent[2] >= self.batch or (force and ent[2] > 0):
+            left = np.concatenate(ent[0]) if len(ent[0]) > 1 else ent[0][0]
+            right = np.concatenate(ent[1]) if len(ent[1]) > 1 else ent[1][0]
+            take = min(self.batch, left.shape[0])
+            self.ctx.map_batch(left[:take], right[:take])
+            ent[0], ent[1], ent[2] = ([left[take:]] if take < left.shape[0] else []), \
+                                     ([right[take:]] if take < right.shape[0] else []), left.shape[0] - take
+            if ent[2] == 0:
+                break
+
+    def add(self, left, right, ll, lr):
+        n = left.shape[0]
+        self.n_in += n
+        L = np.minimum(ll, lr)
+        if n and L.min() == L.max() and int(L[0]) == left.shape[1] and int(L[0]) >= self.k and not self.pending:
+            self.ctx.map_batch(left, right)      # uniform, full-width: no regrouping
+            return
+        for Lv in np.unique(L):
+            sel = np.nonzero(L == Lv)[0]
+            Lv = int(Lv)
+            if Lv < self.k:
+                self.too_short += sel.shape[0]   # cannot hold a k-mer: unmappable (counted as observed, not assigned)
+                continue
+            ent = self.pending.setdefault(Lv, [[], [], 0])
+            ent[0].append(np.ascontiguousarray(left[sel, :Lv]))
+            ent[1].append(np.ascontiguousarray(right[sel, :Lv]))
+            ent[2] += sel.shape[0]
+            self._flush(Lv)
+
+    def finish(self):
+        for L in sorted(self.pending):
+            self._flush(L, force=True)
+
+
+def _quantify(index, ctx, ep, device, dist, names, out_dir, dump_eq, dump_eq_weights, num_bootstraps=0, seed=0,
+              n_observed=None):
+    """Everything after mapping: finish() -> (multi-GPU reduction) -> EM -> outputs.  Shared by quant_reads-style
+    callers that drive the MapContext themselves."""
+    world = dist.get_world_size() if (dist is not None and dist.is_initialized()) else 1
+    rank = dist.get_rank() if world > 1 else 0
+    res = ctx.finish()
+    inputs = res
+    n_mapped = res["counters"]["n_mapped"]
+    if world > 1:
+        from .dist import reduce_partials
+        g, roots = reduce_partials(ctx.partial(), dist, f"cuda:{device}")
+        inputs = ctx.project_global(g, roots)
+        n_mapped = g["assigned"]
+    ctx.close()
+    M = index.n_txps
+    eq = EqClasses(M, res["off"], res["tids"], res["weights"], res["counts"])
+    em = EMContext(device)
+    if world > 1:
+        em.peer_setup(dist, M)
+    alpha, st, ok = em.optimize(eq, ep, inputs["projected_counts"], inputs["eff_len"], inputs["unique_counts"])
+    if not ok:
+        em.close()
+        raise _capi.SalmonB200Error("The optimization algorithm failed (total alpha weight too small)")
+    boots = None
+    if num_bootstraps > 0 and world == 1:
+        boots, _ = em.bootstrap(ep, float(n_mapped), num_bootstraps, seed)
+    em.close()
+    tpm = _capi.tpm(alpha, inputs["eff_len"], float(n_mapped) if n_mapped else None)
+    if out_dir is not None and rank == 0:
+        os.makedirs(os.path.join(out_dir, "aux_info"), exist_ok=True)
+        meta = index.meta()
+        nm = names or meta["names"] or [f"t{i}" for i in range(M)]
+        lens = meta["complete_len"] if meta["complete_len"] is not None else index.tx_lengths()
+        _capi.write_quant_sf(os.path.join(out_dir, "quant.sf"), nm, lens, inputs["eff_len"], alpha,
+                             float(n_mapped) if n_mapped else None)
+        if dump_eq or dump_eq_weights:
+            _capi.write_eq_classes(os.path.join(out_dir, "aux_info", "eq_classes.txt.gz"), nm, res["off"], res["tids"],
+                                   res["counts"], res["weights"] if dump_eq_weights else None)
+        if boots is not None:
+            os.makedirs(os.path.join(out_dir, "aux_info", "bootstrap"), exist_ok=True)
+            w = _capi.BootstrapWriter(os.path.join(out_dir, "aux_info", "bootstrap", "bootstraps.gz"))
+            for b in boots:
+                w.write(b)
+            w.close()
+    return dict(alpha=alpha, tpm=tpm, eff_len=inputs["eff_len"], classes=res, n_mapped=int(n_mapped), em_stats=st,
+                projected_counts=inputs["projected_counts"], unique_counts=inputs["unique_counts"], bootstraps=boots,
+                n_observed=n_observed)
+
+
+def quant_files(index, mates1, mates2, out_dir=None, map_params=None, em_params=None, device=0, batch=262_144,
+                max_read_len=256, threads=8, dist=None, dump_eq=False, dump_eq_weights=False, num_bootstraps=0, seed=0):
+    """`salmon quant -i index -l IU -1 mates1 -2 mates2 -o out_dir` for the hot path: FASTQ/FASTA(.gz) files ->
+    sb_reads_* -> sb_map_batch -> ... -> quant.sf.  index: an _capi.Index or the path of a saved one.  With
+    torch.distributed initialised every rank takes the batches b with b % world == rank (round-robin sharding of
+    the read stream)."""
+    if isinstance(index, (str, bytes, os.PathLike)):
+        index = _capi.Index.load(index)
+    mp = map_params or map_default_params()
+    meta = index.meta()
+    if meta["first_decoy"] < index.n_txps:
+        mp.first_decoy = meta["first_decoy"]
+    ep = em_params or default_params()
+    world = dist.get_world_size() if (dist is not None and dist.is_initialized()) else 1
+    rank = dist.get_rank() if world > 1 else 0
+    ctx = MapContext(index, mp, device=device, batch_cap=batch, max_read_len=max_read_len)
+    buckets = _LengthBuckets(ctx, batch, mp.k)
+    bufs = (np.empty((batch, max_read_len), np.uint8), np.empty((batch, max_read_len), np.uint8),
+            np.empty(batch, np.uint32), np.empty(batch, np.uint32))
+    for b in bufs[:2]:
+        _capi.pin(b)
+    n_observed = 0
+    try:
+        with _capi.ReadFiles(mates1, mates2, n_threads=threads) as rf:
+            bi = 0
+            while True:
+                n, left, right, ll, lr = rf.next_batch(batch, max_read_len, out=bufs)
+                if n == 0:
+                    break
+                n_observed += n
+                if bi % world == rank:
+                    L0 = int(ll[0])
+                    if np.all(ll == L0) and np.all(lr == L0) and L0 < max_read_len:
+                        left, right = np.ascontiguousarray(left[:, :L0]), np.ascontiguousarray(right[:, :L0])
+                        ll = lr = np.full(n, L0, np.uint32)
+                        buckets.add(left, right, ll, lr)
+                    else:
+                        buckets.add(left, right, ll, lr)
+                bi += 1
+        buckets.finish()
+    finally:
+        for b in bufs[:2]:
+            _capi.unpin(b)
+    return _quantify(index, ctx, ep, device, dist, None, out_dir, dump_eq, dump_eq_weights, num_bootstraps, seed,
+                     n_observed=n_observed)
+
+
+def quant_eqclasses(eq_path, out_dir=None, em_params=None, device=0, num_bootstraps=0, seed=0):
+    """`salmon quant --eqclasses eq_classes.txt[.gz]` (EM only; src/quant/SalmonQuantify.cpp eq-class mode ->
+    CollapsedEMOptimizer::optimize with eq_class_mode): BASELINE.json configs[1]."""
+    f = _capi.read_eq_classes(eq_path)
+    if not f["has_weights"]:
+        raise _capi.SalmonB200Error("--eqclasses input needs the weights (write it with --dumpEqWeights)")
+    M = f["n_txps"]
+    eq = EqClasses(M, f["off"], f["tids"], f["weights"], f["counts"])
+    # processEqClasses (src/alignment/SalmonQuantifyAlignments.cpp:1406-1440): fresh transcripts (no projected counts,
+    # no unique counts), initUniform + eqClassMode, effective lengths taken from the file as they are
+    projected = np.zeros(M)
+    uniq = np.zeros(M, dtype=np.uint64)
+    ep = em_params or default_params()
+    ep.eq_class_mode = 1
+    ep.init_uniform = 1
+    em = EMContext(device)
+    alpha, st, ok = em.optimize(eq, ep, projected, f["eff_len"], uniq)
+    if not ok:
+        em.close()
+        raise _capi.SalmonB200Error("The optimization algorithm failed (total alpha weight too small)")
+    n_frags = float(f["counts"].sum())
+    boots = None
+    if num_bootstraps > 0:
+        boots, _ = em.bootstrap(ep, n_frags, num_bootstraps, seed)
+    em.close()
+    tpm = _capi.tpm(alpha, f["eff_len"], n_frags)
+    if out_dir is not None:
+        os.makedirs(out_dir, exist_ok=True)
+        lens = np.maximum(f["eff_len"], 1).astype(np.uint32)   # the eq file carries no transcript lengths
+        _capi.write_quant_sf(os.path.join(out_dir, "quant.sf"), f["names"], lens, f["eff_len"], alpha, n_frags)
+    return dict(alpha=alpha, tpm=tpm, eff_len=f["eff_len"], em_stats=st, names=f["names"], bootstraps=boots)

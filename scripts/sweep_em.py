@@ -1,5 +1,5 @@
 """EM kernel sweep on BASELINE config 2 (dev helper): every setting is checked against the first one.
-usage: sweep_em.py iters "cfg:lmax:lwarp:balance:ovh1:ovh2:keep_cm:keep_tm,..." [vbem]"""
+usage: sweep_em.py iters "cfg:lmax:lwarp:balance:ovh1:ovh2:keep_cm:keep_tm:group_cm:group_tm,..." [vbem]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -14,7 +14,7 @@ ctx = EMContext(0)
 p = default_params(min_iter=iters, max_iter=iters, use_vbem=vbem)
 ctx.upload(eq, proj, eff, uniq)
 ref = None
-names = ["config", "lmax", "lwarp", "balance_long", "overhead_p1", "overhead_p2", "l2_keep_cm", "l2_keep_tm"]
+names = ["config", "lmax", "lwarp", "balance_long", "overhead_p1", "overhead_p2", "l2_keep_cm", "l2_keep_tm", "sell_group_cm", "sell_group_tm"]
 for stg in settings:
     for k, v in zip(names, stg):
         ctx.set_option(k, v)

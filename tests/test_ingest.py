@@ -243,3 +243,40 @@ def test_txome_fasta_options(tmp_path):
     dec.write_text("ENST1|ENSG1|x\n")
     with pytest.raises(_capi.SalmonB200Error, match="decoys must come last"):
         _capi.read_txome_fasta(str(fa), k=31, decoys=str(dec))
+
+
+def test_index_save_load_round_trip(tmp_path):
+    # host-side only: build (sb_index_build never touches the device), save, load, compare every array
+    import ctypes as C
+    rng = np.random.default_rng(12)
+    fa = tmp_path / "t.fa"
+    seqs = [rand_seq(rng, int(rng.integers(40, 400))) for _ in range(30)]
+    seqs[3] = seqs[3][:50] + "NN" + seqs[3][52:]
+    fa.write_text("".join(f">t{i}|g{i // 3} x\n{s}\n" for i, s in enumerate(seqs)))
+    ix = _capi.Index.from_fasta(str(fa), k=21, gencode=True)
+    path = str(tmp_path / "sb_index.bin")
+    ix.save(path)
+    iy = _capi.Index.load(path)
+    assert iy.n_txps == ix.n_txps == 30 and iy.k == 21
+    ma, mb = ix.meta(), iy.meta()
+    assert ma["names"] == mb["names"] == [f"t{i}" for i in range(30)]
+    assert np.array_equal(ma["complete_len"], mb["complete_len"]) and mb["first_decoy"] == 30
+    assert ix.info() == iy.info()
+    ha, hb = ix.host_arrays(), iy.host_arrays()
+    assert ha["table_capacity"] == hb["table_capacity"] and ha["n_postings"] == hb["n_postings"]
+
+    def raw(ptr, nbytes):
+        return bytes((C.c_char * nbytes).from_address(ptr))
+    total = int(ix.tx_lengths().sum())
+    assert raw(ha["tx_off"], 8 * 31) == raw(hb["tx_off"], 8 * 31)
+    assert raw(ha["codes"], total) == raw(hb["codes"], total)
+    assert raw(ha["table"], 16 * ha["table_capacity"]) == raw(hb["table"], 16 * hb["table_capacity"])
+    assert raw(ha["postings"], 8 * ha["n_postings"]) == raw(hb["postings"], 8 * hb["n_postings"])
+    # a truncated file is rejected
+    data = open(path, "rb").read()
+    open(path, "wb").write(data[: len(data) // 2])
+    with pytest.raises(_capi.SalmonB200Error, match="truncated or corrupt"):
+        _capi.Index.load(path)
+    open(path, "wb").write(b"not an index at all, just text padding to be long enough for a header " * 2)
+    with pytest.raises(_capi.SalmonB200Error, match="bad header"):
+        _capi.Index.load(path)

@@ -269,3 +269,29 @@ def test_quant_pipeline_end_to_end(tmp_path):
     import gzip
     eqt = gzip.open(tmp_path / "aux_info" / "eq_classes.txt.gz", "rt").read().splitlines()
     assert int(eqt[0]) == M and int(eqt[1]) == len(out["classes"]["counts"])
+
+
+@pytest.mark.parametrize("L,cap_len", [(60, 128), (100, 128), (31, 100), (140, 256)])
+def test_read_length_below_context_capacity(oracle, L, cap_len):
+    """One context serves batches of different read lengths (quant_files groups reads by length): a batch of L-base
+    reads in a context created for cap_len bases is bit-exact against the oracle, like a context created for L."""
+    txps, _ = synth_txome(seed=3, n_genes=100)
+    left, right, _ = synth_reads(txps, seed=15, n=2000, read_len=L, frag_mean=max(200, 2 * L), frag_sd=20)
+    p = map_default_params()
+    idx = Index(txps)
+    ctx = MapContext(idx, p, batch_cap=2048, max_read_len=cap_len)
+    st = ctx.map_batch(left, right)
+    got = ctx.last_alignments()
+    ref = oracle.map_reads(oracle.MapIndex(txps), oracle.map_params(), left, right, 0)
+    compare(got, ref, p.max_read_occ)
+    for k in ("lookups", "postings", "seeds", "kept", "label_entries", "mapped"):
+        assert getattr(st, k) == ref["counters"][k], k
+    # and a second batch of another length through the same context
+    left2, right2, _ = synth_reads(txps, seed=16, n=1000, read_len=max(31, L - 9), frag_mean=max(200, 2 * L), frag_sd=20)
+    ctx.map_batch(left2, right2)
+    got2 = ctx.last_alignments()
+    ref2 = oracle.map_reads(oracle.MapIndex(txps), oracle.map_params(), left2, right2, 0)
+    assert np.array_equal(got2["n_aln"], ref2["n_aln"])
+    m = np.arange(p.max_read_occ)[None, :] < got2["n_aln"][:, None]
+    assert np.array_equal(got2["tid"][m], ref2["tid"][m]) and np.array_equal(got2["score"][m], ref2["score"][m])
+    ctx.close()

@@ -1,0 +1,96 @@
+"""File-level pipelines on the GPU: FASTQ files -> quant.sf (quant_files) and --eqclasses -> quant.sf (quant_eqclasses).
+The mapping / EM kernels are checked against the oracle elsewhere; here the file seams must not change results."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from salmon_b200 import _capi
+from salmon_b200._capi import Index
+from salmon_b200.synth import synth_eq, synth_reads, synth_txome
+
+pytestmark = pytest.mark.gpu
+LETTERS = np.frombuffer(b"ACGTN", dtype=np.uint8)
+
+
+def write_fastq(path, codes, lens=None, gz=True):
+    op = gzip.open if gz else open
+    with op(path, "wb") as f:
+        for i, row in enumerate(codes):
+            L = len(row) if lens is None else int(lens[i])
+            s = LETTERS[row[:L]].tobytes()
+            f.write(b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * L))
+
+
+def test_quant_files_equals_quant_reads(tmp_path):
+    from salmon_b200.quant import quant_files, quant_reads
+    txps, _ = synth_txome(seed=41, n_genes=120)
+    left, right, truth = synth_reads(txps, seed=43, n=20000)
+    names = [f"ENST{i:05d}" for i in range(len(txps))]
+    idx = Index(txps, names=names)
+    f1, f2 = str(tmp_path / "r_1.fq.gz"), str(tmp_path / "r_2.fq.gz")
+    write_fastq(f1, left); write_fastq(f2, right)
+    ipath = str(tmp_path / "sb_index.bin")
+    idx.save(ipath)
+    a = quant_reads(idx, left, right, batch=8192)
+    b = quant_files(ipath, f1, f2, out_dir=str(tmp_path / "out"), batch=8192, max_read_len=left.shape[1],
+                    dump_eq_weights=True, num_bootstraps=3, seed=7)
+    assert b["n_observed"] == 20000 and a["n_mapped"] == b["n_mapped"]
+    assert np.array_equal(a["classes"]["counts"], b["classes"]["counts"])
+    assert np.array_equal(a["classes"]["tids"], b["classes"]["tids"])
+    assert np.array_equal(a["alpha"], b["alpha"])          # same batches, same order: bit-identical
+    lines = (tmp_path / "out" / "quant.sf").read_text().splitlines()
+    assert lines[1].split("\t")[0] == "ENST00000" and len(lines) == len(txps) + 1
+    raw = gzip.open(tmp_path / "out" / "aux_info" / "bootstrap" / "bootstraps.gz", "rb").read()
+    boots = np.frombuffer(raw, dtype=np.float64).reshape(3, len(txps))
+    assert np.array_equal(boots, b["bootstraps"])
+    assert np.all(np.abs(boots.sum(axis=1) - b["n_mapped"]) < 1e-3 * b["n_mapped"])
+    # the eq file written by the run feeds the --eqclasses mode
+    from salmon_b200.quant import quant_eqclasses
+    c = quant_eqclasses(str(tmp_path / "out" / "aux_info" / "eq_classes.txt.gz"))
+    assert abs(c["alpha"].sum() - b["n_mapped"]) < 1e-6 * b["n_mapped"]
+
+
+def test_quant_files_variable_read_lengths(tmp_path):
+    from salmon_b200.quant import quant_files
+    txps, _ = synth_txome(seed=41, n_genes=120)
+    left, right, truth = synth_reads(txps, seed=44, n=12000)
+    n, L = left.shape
+    rng = np.random.default_rng(3)
+    ll = np.full(n, L); lr = np.full(n, L)
+    trim = rng.random(n) < 0.4                      # adapter-trimmed reads: 3' ends removed
+    ll[trim] = rng.integers(20, L + 1, size=int(trim.sum()))
+    lr[trim] = np.where(rng.random(int(trim.sum())) < 0.5, ll[trim], rng.integers(20, L + 1, size=int(trim.sum())))
+    f1, f2 = str(tmp_path / "v_1.fq"), str(tmp_path / "v_2.fq")
+    write_fastq(f1, left, ll, gz=False); write_fastq(f2, right, lr, gz=False)
+    idx = Index(txps)
+    out = quant_files(idx, f1, f2, batch=4096, max_read_len=128)
+    M = len(txps)
+    mappable = truth["tid"] >= 0
+    true_counts = np.bincount(truth["tid"][mappable], minlength=M).astype(float)
+    assert out["n_observed"] == n
+    assert out["n_mapped"] >= 0.9 * mappable.sum()      # reads trimmed below k (31) cannot map
+    assert abs(out["alpha"].sum() - out["n_mapped"]) < 1e-6 * out["n_mapped"]
+    assert np.corrcoef(out["alpha"], true_counts)[0, 1] > 0.95
+
+
+def test_quant_eqclasses_matches_oracle(tmp_path):
+    from salmon_b200.quant import quant_eqclasses
+    eq, proj, eff, uniq = synth_eq(seed=5, C=20000, M=6000, total_count=400000)
+    names = [f"t{i}" for i in range(eq.n_txps)]
+    path = str(tmp_path / "eq_classes.txt.gz")
+    _capi.write_eq_classes(path, names, eq.off, eq.tids, eq.counts, eq.weights)
+    with gzip.open(path, "at") as f:
+        for i in range(eq.n_txps):
+            f.write(f"{names[i]}\t{eff[i]:.17g}\n")
+    got = quant_eqclasses(path, out_dir=str(tmp_path / "o"))
+    f = _capi.read_eq_classes(path)
+    eq2 = _capi.EqClasses(f["n_txps"], f["off"], f["tids"], f["weights"], f["counts"])
+    p = _capi.default_params(eq_class_mode=1, init_uniform=1)
+    ref, rst = O.em_optimize(eq2, np.zeros(eq.n_txps), f["eff_len"], np.zeros(eq.n_txps, np.uint64), p)
+    assert got["em_stats"].iters == rst.iters
+    np.testing.assert_allclose(got["alpha"], ref, rtol=1e-9, atol=1e-9)
+    assert np.array_equal(f["eff_len"], eff)
+    assert len((tmp_path / "o" / "quant.sf").read_text().splitlines()) == eq.n_txps + 1
