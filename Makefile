@@ -7,15 +7,21 @@ LIB       := salmon_b200/libsalmon_b200.so
 SRCS      := $(wildcard $(CSRC)/*.cu)
 HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 
-all: $(LIB) oracle
+CLI       := salmon_b200/sb_salmon
+
+all: $(LIB) $(CLI) oracle
 
 $(LIB): $(SRCS) $(HDRS)
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(SRCS) -ldl -lgomp -lz
+
+# command-line front end (host C++ over the C ABI; finds the library next to itself)
+$(CLI): $(CSRC)/cli_main.cpp $(LIB) include/salmon_b200.h
+	g++ -O2 -std=c++17 -Wall -o $@ $(CSRC)/cli_main.cpp -Lsalmon_b200 -lsalmon_b200 -Wl,-rpath,'$$ORIGIN'
 
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -f $(LIB); $(MAKE) -C oracle clean
+	rm -f $(LIB) $(CLI); $(MAKE) -C oracle clean
 
 .PHONY: all oracle clean

@@ -350,6 +350,38 @@ int sb_map_last_alignments(sb_map_ctx* ctx, uint32_t n, uint32_t* n_aln, uint32_
                            double* prob, int32_t* pos, int32_t* mate_pos, uint8_t* flags, int32_t* flen,
                            uint32_t* label, double* weight);
 
+/* ---- the host driver of the path (C++; salmon_b200/csrc/pipeline.cu): `salmon quant -i idx -l IU -1 .. -2 .. -o out`
+ * for the hot path.  Mirrors processReadLibrary / quantifyLibrary (src/quant/SalmonQuantify.cpp:2339-2730) and
+ * stageFinalizeMappingOutputs (src/quant/pipeline/MappingPipelineStages.cpp:37-206): a reader thread parses and groups
+ * reads by length into pinned buffers while the calling thread runs sb_map_batch on the previous ones; then
+ * sb_map_finish, sb_em_optimize, optional bootstraps / Gibbs samples, and the output files under out_dir
+ * (quant.sf, aux_info/eq_classes.txt.gz, aux_info/bootstrap/{bootstraps.gz,names.tsv.gz}).  One GPU per call. */
+typedef struct sb_quant_opts {
+  int32_t device;
+  uint32_t batch;            /* read pairs per sb_map_batch (262144) */
+  uint32_t max_read_len;     /* longest read accepted, 32..256 */
+  uint32_t threads;          /* read-file translation threads */
+  int32_t dump_eq;           /* --dumpEq */
+  int32_t dump_eq_weights;   /* --dumpEqWeights */
+  uint32_t num_bootstraps;   /* --numBootstraps */
+  uint32_t num_gibbs;        /* --numGibbsSamples */
+  uint32_t thinning;         /* --thinningFactor (16) */
+  int32_t no_gamma_draw;     /* --noGammaDraw */
+  uint32_t shard_index, shard_count;   /* this process maps the reader batches b with b % shard_count == shard_index */
+  uint64_t seed;
+} sb_quant_opts;
+typedef struct sb_quant_summary {
+  uint64_t n_observed, n_mapped, n_too_short, n_trimmed_mates, n_classes, n_batches;
+  uint32_t n_read_lengths, em_iters, em_converged, reserved;
+  double map_seconds, em_seconds, total_seconds;   /* wall clock */
+  float map_device_ms, reserved2;                  /* sum of sb_map_batch_stats.device_ms */
+} sb_quant_summary;
+void sb_quant_default_opts(sb_quant_opts* o);
+/* mp / ep / o may be NULL (defaults); out_dir may be NULL (no files); alpha_out[n_txps] may be NULL. */
+int sb_quant_files(sb_index* ix, const char* const* mates1, const char* const* mates2, uint32_t n_files,
+                   const sb_map_params* mp, const sb_em_params* ep, const sb_quant_opts* o, const char* out_dir,
+                   double* alpha_out, sb_quant_summary* summary);
+
 /* Tuning knobs of the mapping context: "variant" (1 = warp-cooperative kernels, 0 = serial-form kernels),
  * "fast_dp" (ungapped shortcut of the DP kernel on/off), "chunk" (reads per pipeline chunk), "input_on_device"
  * (sb_map_batch's read pointers are device pointers: inputs already resident in HBM), "ascii_reads" (the read bytes

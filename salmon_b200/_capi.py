@@ -130,7 +130,25 @@ class sb_txome(C.Structure):
     ]
 
 
+class sb_quant_opts(C.Structure):
+    _fields_ = [("device", C.c_int32), ("batch", C.c_uint32), ("max_read_len", C.c_uint32), ("threads", C.c_uint32),
+                ("dump_eq", C.c_int32), ("dump_eq_weights", C.c_int32), ("num_bootstraps", C.c_uint32),
+                ("num_gibbs", C.c_uint32), ("thinning", C.c_uint32), ("no_gamma_draw", C.c_int32),
+                ("shard_index", C.c_uint32), ("shard_count", C.c_uint32), ("seed", C.c_uint64)]
+
+
+class sb_quant_summary(C.Structure):
+    _fields_ = [("n_observed", C.c_uint64), ("n_mapped", C.c_uint64), ("n_too_short", C.c_uint64),
+                ("n_trimmed_mates", C.c_uint64), ("n_classes", C.c_uint64), ("n_batches", C.c_uint64),
+                ("n_read_lengths", C.c_uint32), ("em_iters", C.c_uint32), ("em_converged", C.c_uint32),
+                ("reserved", C.c_uint32), ("map_seconds", C.c_double), ("em_seconds", C.c_double),
+                ("total_seconds", C.c_double), ("map_device_ms", C.c_float), ("reserved2", C.c_float)]
+
+
 SYMBOLS = {
+    "sb_quant_default_opts": (None, [C.POINTER(sb_quant_opts)]),
+    "sb_quant_files": (C.c_int, [_P, _P, _P, C.c_uint32, _P, _P, C.POINTER(sb_quant_opts), C.c_char_p, _P,
+                                 C.POINTER(sb_quant_summary)]),
     "sb_reads_open": (_P, [_P, _P, C.c_uint32, C.c_uint32]),
     "sb_reads_next": (C.c_int64, [_P, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
     "sb_reads_close": (None, [_P]),
@@ -783,3 +801,25 @@ def read_txome_fasta(path, k=31, gencode=False, decoys=None, no_clip=False, keep
                 "n_short": int(t.n_short)}
     finally:
         lib.sb_txome_free(pt)
+
+
+def quant_files_native(index, mates1, mates2, out_dir=None, map_params=None, em_params=None, **opts):
+    """sb_quant_files: the C++ host driver (reader thread + GPU thread, salmon_b200/csrc/pipeline.cu).
+    opts: fields of sb_quant_opts.  -> (alpha[M], summary dict)."""
+    lib = load()
+    mates1 = [mates1] if isinstance(mates1, (str, bytes, os.PathLike)) else list(mates1)
+    mates2 = [mates2] if isinstance(mates2, (str, bytes, os.PathLike)) else list(mates2)
+    o = sb_quant_opts()
+    lib.sb_quant_default_opts(C.byref(o))
+    for k, v in opts.items():
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    a1 = (C.c_char_p * len(mates1))(*[os.fsencode(f) for f in mates1])
+    a2 = (C.c_char_p * len(mates2))(*[os.fsencode(f) for f in mates2])
+    alpha = np.zeros(index.n_txps)
+    sm = sb_quant_summary()
+    _check(lib.sb_quant_files(index.h, a1, a2, len(mates1), C.byref(map_params) if map_params is not None else None,
+                              C.byref(em_params) if em_params is not None else None, C.byref(o),
+                              os.fsencode(out_dir) if out_dir else None, alpha.ctypes.data, C.byref(sm)), "sb_quant_files")
+    return alpha, {k: getattr(sm, k) for k, _ in sb_quant_summary._fields_ if not k.startswith("reserved")}

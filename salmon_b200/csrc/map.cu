@@ -1018,7 +1018,7 @@ extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int d
   const uint32_t cap = p.max_read_occ;
   const size_t B = batch_cap;
   // reads per pipeline chunk: the per-chunk buffers are sized for chunk_cap; SB_MAP_CHUNK raises it for sweeps
-  size_t chunk_cap = 65536;
+  size_t chunk_cap = 131072;   // 131072: +4 % over 65536 at human scale (profiles/sweep_r1_stageA_chunk.txt)
   if (const char* e = getenv("SB_MAP_CHUNK")) { const long v = atol(e); if (v >= 1024 && v <= (1 << 24)) chunk_cap = (size_t)v; }
   c->chunk = c->chunk_cap = (uint32_t)std::min<size_t>(B, chunk_cap);
   const size_t CH = c->chunk;
@@ -1279,14 +1279,14 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
         SB_CUDA(cudaEventRecord(c->ev_seed[2 * ch + 1], st));
         k_dp_classify<4><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, L, c->fast_ok, io);
         k_dp_pair<4><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, L, io);
-        k_dp_general<4><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, io);
+        k_dp_general<4><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, c->ascii, io);
       } else {
         if (npos <= 32) k_seed_chain_w<4, 1><<<c->seed_blocks, SeedCfg<4>::WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
         else k_seed_chain_w<4, 2><<<c->seed_blocks, SeedCfg<4>::WARPS * 32, 0, st>>>(ix, p, c->pr, cn, L, so);
         SB_CUDA(cudaEventRecord(c->ev_seed[2 * ch + 1], st));
         k_dp_classify<8><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, L, c->fast_ok, io);
         k_dp_pair<8><<<c->n_sm * 2, 256, 0, st>>>(ix, p, c->pr, L, io);
-        k_dp_general<8><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, io);
+        k_dp_general<8><<<c->n_sm * 3, 256, 0, st>>>(ix, p, c->pr, dl, dr, L, c->ascii, io);
       }
       c->launches += 5;
     }

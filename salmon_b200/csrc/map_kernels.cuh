@@ -565,8 +565,13 @@ struct DpIo {
 };
 
 // byte-code form (transcripts with N, reads with N): lanes = band cells, one reference byte per row
+__device__ __forceinline__ uint8_t base_code(uint8_t c, int ascii) {   // same mapping as k_pack_reads
+  if (!ascii) return c;
+  const uint8_t u = c & 0xDFu;
+  return (u == 'A') ? 0 : (u == 'C') ? 1 : (u == 'G') ? 2 : (u == 'T') ? 3 : 4;
+}
 __device__ __forceinline__ int32_t dp_warp_bytes(const IndexView& ix, const Params& p, const uint8_t* read, uint32_t L,
-                                                 const Cand& c, uint32_t lane) {
+                                                 const Cand& c, uint32_t lane, int ascii) {
   const int32_t B = (int32_t)p.band, W = 2 * B + 1;
   const uint32_t ori = c.ori_cov >> 31;
   const int64_t tlen = (int64_t)(ix.tx_off[c.tid + 1] - ix.tx_off[c.tid]);
@@ -576,7 +581,7 @@ __device__ __forceinline__ int32_t dp_warp_bytes(const IndexView& ix, const Para
   int64_t rpos = (int64_t)c.diag_c + ((int32_t)lane - B);
   uint8_t rbase = (rpos >= 0 && rpos < tlen) ? ref[rpos] : (uint8_t)255;
   for (uint32_t i = 0; i < L; ++i) {
-    const uint8_t cc = ori ? read[L - 1 - i] : read[i];
+    const uint8_t cc = base_code(ori ? read[L - 1 - i] : read[i], ascii);
     const uint8_t rb = ori ? (uint8_t)(cc > 3 ? 4 : 3 - cc) : cc;
     const bool valid = in_band && rbase != 255;
     const int32_t Hup = __shfl_down_sync(0xffffffffu, H, 1);
@@ -825,7 +830,7 @@ k_dp_pair(IndexView ix, Params p, PackedReads pr, uint32_t L, DpIo io) {
 template <int NWR>
 __global__ void __launch_bounds__(256, 3)
 k_dp_general(IndexView ix, Params p, PackedReads pr, const uint8_t* __restrict__ left,
-             const uint8_t* __restrict__ right, uint32_t L, DpIo io) {
+             const uint8_t* __restrict__ right, uint32_t L, int ascii, DpIo io) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t n_edge = io.list_n[1], n_n = io.list_n[2];
@@ -838,7 +843,7 @@ k_dp_general(IndexView ix, Params p, PackedReads pr, const uint8_t* __restrict__
     const Cand c = mate ? io.cand_r[(size_t)r * MAXCAND + ci] : io.cand_l[(size_t)r * MAXCAND + ci];
     int32_t* out = (mate ? io.score_r : io.score_l) + (size_t)r * MAXCAND + ci;
     if (bytes) {
-      const int32_t s = dp_warp_bytes(ix, p, (mate ? right : left) + (size_t)r * L, L, c, lane);
+      const int32_t s = dp_warp_bytes(ix, p, (mate ? right : left) + (size_t)r * L, L, c, lane, ascii);
       if (lane == 0) *out = s;
       continue;
     }

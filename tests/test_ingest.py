@@ -280,3 +280,40 @@ def test_index_save_load_round_trip(tmp_path):
     open(path, "wb").write(b"not an index at all, just text padding to be long enough for a header " * 2)
     with pytest.raises(_capi.SalmonB200Error, match="bad header"):
         _capi.Index.load(path)
+
+
+def test_cli_index_and_no_gpu_failure(tmp_path):
+    """sb_salmon (C++ front end over the C ABI): `index` is host-only and runs anywhere; `quant` must fail loudly
+    without a CUDA device (no CPU fallback)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(_capi.LIB_PATH), "sb_salmon")
+    assert os.path.exists(exe), "build it with `make` (or __graft_entry__.build())"
+    rng = np.random.default_rng(13)
+    fa = tmp_path / "t.fa"
+    seqs = [rand_seq(rng, int(rng.integers(100, 600))) for _ in range(12)]
+    fa.write_text("".join(f">tx{i}|gene{i // 2}|more\n{s}\n" for i, s in enumerate(seqs)) + ">chrD\n" + rand_seq(rng, 900) + "\n")
+    (tmp_path / "decoys.txt").write_text("chrD\n")
+    idir = tmp_path / "idx"
+    r = subprocess.run([exe, "index", "-t", str(fa), "-i", str(idir), "-k", "25", "--gencode", "-d", str(tmp_path / "decoys.txt")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ix = _capi.Index.load(str(idir / "sb_index.bin"))
+    m = ix.meta()
+    assert m["k"] == 25 and m["n_txps"] == 13 and m["first_decoy"] == 12 and m["names"][0] == "tx0" and m["names"][-1] == "chrD"
+    import json
+    info = json.load(open(idir / "info.json"))
+    assert info["k"] == 25 and info["num_references"] == 13 and info["first_decoy"] == 12
+    # even k is rejected like the reference does (BuildSalmonIndex.cpp:206-211)
+    r = subprocess.run([exe, "index", "-t", str(fa), "-i", str(idir), "-k", "30"], capture_output=True, text=True)
+    assert r.returncode == 1 and "odd" in r.stderr
+    # options outside the hot path are refused, not ignored
+    r = subprocess.run([exe, "quant", "-i", str(idir), "-l", "IU", "-1", "a.fq", "-2", "b.fq", "-o", str(tmp_path / "o"), "--gcBias"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "outside the hot path" in r.stderr
+    if _capi.load().sb_device_count() == 0:
+        f1, f2 = tmp_path / "a_1.fq", tmp_path / "a_2.fq"
+        f1.write_text("@r\n" + seqs[0][:60] + "\n+\n" + "I" * 60 + "\n")
+        f2.write_text("@r\n" + seqs[0][100:160] + "\n+\n" + "I" * 60 + "\n")
+        r = subprocess.run([exe, "quant", "-i", str(idir), "-l", "IU", "-1", str(f1), "-2", str(f2), "-o", str(tmp_path / "o")],
+                           capture_output=True, text=True)
+        assert r.returncode == 1 and "no CUDA device" in r.stderr

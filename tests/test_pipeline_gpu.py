@@ -94,3 +94,54 @@ def test_quant_eqclasses_matches_oracle(tmp_path):
     np.testing.assert_allclose(got["alpha"], ref, rtol=1e-9, atol=1e-9)
     assert np.array_equal(f["eff_len"], eff)
     assert len((tmp_path / "o" / "quant.sf").read_text().splitlines()) == eq.n_txps + 1
+
+
+def test_native_driver_and_cli_match_python_pipeline(tmp_path):
+    """sb_quant_files (C++ reader thread + GPU thread) and the sb_salmon command line give the numbers of the Python
+    mirror on the same files (uniform read length: same batches in the same order -> bit-identical alphas)."""
+    import subprocess
+    from salmon_b200.quant import quant_files
+    txps, _ = synth_txome(seed=41, n_genes=120)
+    left, right, truth = synth_reads(txps, seed=45, n=20000)
+    names = [f"ENST{i:05d}" for i in range(len(txps))]
+    idx = Index(txps, names=names)
+    f1, f2 = str(tmp_path / "r_1.fq.gz"), str(tmp_path / "r_2.fq.gz")
+    write_fastq(f1, left); write_fastq(f2, right)
+    py = quant_files(idx, f1, f2, batch=8192, max_read_len=128)
+    alpha, sm = _capi.quant_files_native(idx, f1, f2, out_dir=str(tmp_path / "nat"), batch=8192, max_read_len=128,
+                                         dump_eq_weights=1, num_bootstraps=2, seed=5)
+    assert sm["n_observed"] == 20000 and sm["n_mapped"] == py["n_mapped"] and sm["n_read_lengths"] == 1
+    assert np.array_equal(alpha, py["alpha"])
+    assert (tmp_path / "nat" / "aux_info" / "bootstrap" / "names.tsv.gz").exists()
+    raw = gzip.open(tmp_path / "nat" / "aux_info" / "bootstrap" / "bootstraps.gz", "rb").read()
+    assert len(raw) == 2 * len(txps) * 8
+    # the command line: index from FASTA, quant from the files
+    fa = tmp_path / "t.fa"
+    with open(fa, "wb") as f:
+        for nm, t in zip(names, txps):
+            f.write(b">" + nm.encode() + b" x\n" + LETTERS[t].tobytes() + b"\n")
+    exe = os.path.join(os.path.dirname(_capi.LIB_PATH), "sb_salmon")
+    r = subprocess.run([exe, "index", "-t", str(fa), "-i", str(tmp_path / "idx"), "--no-clip", "--keepDuplicates"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, "quant", "-i", str(tmp_path / "idx"), "-l", "IU", "-1", f1, "-2", f2, "-o", str(tmp_path / "cli"),
+                        "--batch", "8192", "--maxReadLen", "128", "--dumpEq"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    a = (tmp_path / "nat" / "quant.sf").read_text().splitlines()
+    b = (tmp_path / "cli" / "quant.sf").read_text().splitlines()
+    assert a == b and a[1].startswith("ENST00000\t")
+    assert (tmp_path / "cli" / "aux_info" / "meta_info.json").exists()
+    # variable read lengths through the native driver: same totals as the Python mirror
+    n = 6000
+    rng = np.random.default_rng(4)
+    ll = np.full(n, 100); lr = np.full(n, 100)
+    trim = rng.random(n) < 0.5
+    ll[trim] = rng.integers(25, 101, size=int(trim.sum())); lr[trim] = rng.integers(25, 101, size=int(trim.sum()))
+    g1, g2 = str(tmp_path / "v_1.fq"), str(tmp_path / "v_2.fq")
+    write_fastq(g1, left[:n], ll, gz=False); write_fastq(g2, right[:n], lr, gz=False)
+    alpha2, sm2 = _capi.quant_files_native(idx, g1, g2, batch=4096, max_read_len=128)
+    py2 = quant_files(idx, g1, g2, batch=4096, max_read_len=128)
+    assert sm2["n_observed"] == n and sm2["n_read_lengths"] > 10 and sm2["n_too_short"] > 0
+    assert abs(alpha2.sum() - sm2["n_mapped"]) < 1e-6 * sm2["n_mapped"]
+    assert abs(int(sm2["n_mapped"]) - py2["n_mapped"]) <= 0.01 * py2["n_mapped"]     # different batch composition
+    assert np.corrcoef(alpha2, py2["alpha"])[0, 1] > 0.999
