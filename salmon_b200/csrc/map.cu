@@ -845,6 +845,14 @@ struct sb_map_ctx {
   int fast_ok = 1;
   uint32_t k1_threads = 0, seed_blocks = 0, dp_blocks = 0;
   BatchBufs b{};                     // cand/score/task buffers: one chunk; outputs: whole batch
+  // k_assign of chunk i runs on its own stream next to the seed / DP kernels of chunk i+1 (it is latency-bound at
+  // ~10 % issue utilisation, they are issue-bound): the buffers both sides touch exist twice
+  int overlap_assign = 0;
+  cudaStream_t assign_stream = nullptr;
+  cudaEvent_t ev_dp[2] = {nullptr, nullptr}, ev_asg[2] = {nullptr, nullptr};
+  uint32_t *alt_n_l = nullptr, *alt_n_r = nullptr;
+  Cand *alt_cand_l = nullptr, *alt_cand_r = nullptr;
+  int32_t *alt_score_l = nullptr, *alt_score_r = nullptr;
   uint8_t* d_in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [slot][mate]
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   PackedReads pr{};
@@ -1010,6 +1018,12 @@ extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int d
   c->n_sm = prop.multiProcessorCount;
   cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->assign_stream, cudaStreamNonBlocking);
+  for (int s = 0; s < 2; ++s) {
+    cudaEventCreateWithFlags(&c->ev_dp[s], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_asg[s], cudaEventDisableTiming);
+  }
+  if (const char* e = getenv("SB_MAP_OVERLAP")) c->overlap_assign = atoi(e) ? 1 : 0;
   cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
   for (int s = 0; s < 2; ++s) {
     cudaEventCreateWithFlags(&c->ev_in[s], cudaEventDisableTiming);
@@ -1031,6 +1045,8 @@ extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int d
   // per chunk
   A(&b.n_l, CH); A(&b.n_r, CH); A(&b.cand_l, CH * MAXCAND); A(&b.cand_r, CH * MAXCAND);
   A(&b.score_l, CH * MAXCAND); A(&b.score_r, CH * MAXCAND);
+  A(&c->alt_n_l, CH); A(&c->alt_n_r, CH); A(&c->alt_cand_l, CH * MAXCAND); A(&c->alt_cand_r, CH * MAXCAND);
+  A(&c->alt_score_l, CH * MAXCAND); A(&c->alt_score_r, CH * MAXCAND);
   A(&b.keys, (size_t)MAXSEEDS * c->k1_threads);
   A(&b.n_tasks, 4); A(&b.tasks, CH * 2 * MAXCAND);
   const size_t S = (size_t)c->k1_threads * cap;
@@ -1104,6 +1120,9 @@ extern "C" void sb_map_destroy(sb_map_ctx* c) {
                   c->d_work, c->d_work2, c->d_ids, c->d_order, c->fin.uniq, c->fin.total, c->fin.hits, c->fin.parent, c->fin.root, c->fin.root2, c->fin.ids, c->fin.memb,
                   c->fin.head, c->fin.head_scan, c->fin.start, c->fin.proj, c->fin.eff, c->fin.bound, c->fin.tmp};
   for (void* p : ptrs) cudaFree(p);
+  cudaFree(c->alt_n_l); cudaFree(c->alt_n_r); cudaFree(c->alt_cand_l); cudaFree(c->alt_cand_r); cudaFree(c->alt_score_l); cudaFree(c->alt_score_r);
+  for (int s = 0; s < 2; ++s) { if (c->ev_dp[s]) cudaEventDestroy(c->ev_dp[s]); if (c->ev_asg[s]) cudaEventDestroy(c->ev_asg[s]); }
+  if (c->assign_stream) cudaStreamDestroy(c->assign_stream);
   c->agg.free_all();
   cudaFree(c->arena.labels); cudaFree(c->arena.weights); cudaFree(c->arena.counts); cudaFree(c->arena.loff); cudaFree(c->arena.woff);
   for (cudaEvent_t e : c->ev_seed) cudaEventDestroy(e);
@@ -1124,6 +1143,7 @@ extern "C" int sb_map_set_option(sb_map_ctx* c, const char* key, int64_t value) 
     if (value && c->variant == 0) { sb::set_error("ascii_reads needs the warp kernels (variant 1)"); return SB_ERR_INVALID; }
     c->ascii = value ? 1 : 0; return SB_OK;
   }
+  if (!strcmp(key, "overlap_assign")) { c->overlap_assign = value ? 1 : 0; return SB_OK; }
   if (!strcmp(key, "chunk")) {   // reads per pipeline chunk (<= the size the context was created with)
     const uint32_t mx = c->chunk_cap;
     if (value < 1 || value > (int64_t)mx) { sb::set_error("chunk must be in 1..%u", mx); return SB_ERR_INVALID; }
@@ -1257,6 +1277,13 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
     SB_CUDA(cudaMemsetAsync(c->d_next_task, 0, 32, st));
     // outputs of this chunk inside the batch-wide arrays
     BatchBufs bc = c->b;
+    const bool ovl = c->overlap_assign && c->variant != 0;
+    const int set = (int)(ch & 1);
+    if (ovl && set) {
+      bc.n_l = c->alt_n_l; bc.n_r = c->alt_n_r; bc.cand_l = c->alt_cand_l; bc.cand_r = c->alt_cand_r;
+      bc.score_l = c->alt_score_l; bc.score_r = c->alt_score_r;
+    }
+    if (ovl && ch >= 2) SB_CUDA(cudaStreamWaitEvent(st, c->ev_asg[set], 0));   // k_assign of chunk ch-2 still reads this set
     bc.n_aln += c0; bc.tid += (size_t)c0 * cap; bc.score += (size_t)c0 * cap; bc.prob += (size_t)c0 * cap;
     bc.pos += (size_t)c0 * cap; bc.mate_pos += (size_t)c0 * cap; bc.flags += (size_t)c0 * cap; bc.flen += (size_t)c0 * cap;
     bc.label += (size_t)c0 * 2 * cap; bc.weight += (size_t)c0 * cap;
@@ -1290,15 +1317,25 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
       }
       c->launches += 5;
     }
-    {
-      k_assign_work<<<nblk(cn, 256), 256, 0, st>>>(cn, bc.n_l, bc.n_r, c->d_work, c->d_ids);
-      size_t tb = c->agg.tmp_bytes;
-      SB_CUDA(cub::DeviceRadixSort::SortPairs(c->agg.tmp, tb, c->d_work, c->d_work2, c->d_ids, c->d_order, (int)cn, 0, 8, st));
+    cudaStream_t as = st;
+    if (ovl) {   // the input staging buffers are free once the DP kernels are done; k_assign moves to its own stream
+      SB_CUDA(cudaEventRecord(c->ev_free[s], st));
+      SB_CUDA(cudaEventRecord(c->ev_dp[set], st));
+      as = c->assign_stream;
+      SB_CUDA(cudaStreamWaitEvent(as, c->ev_dp[set], 0));
     }
-    k_assign<<<T / 128, 128, 0, st>>>(ix, p, c->fld, useAux, burnedIn, cn, L, bc, onv, c0, c->d_order);
+    {
+      k_assign_work<<<nblk(cn, 256), 256, 0, as>>>(cn, bc.n_l, bc.n_r, c->d_work, c->d_ids);
+      size_t tb = c->agg.tmp_bytes;
+      SB_CUDA(cub::DeviceRadixSort::SortPairs(c->agg.tmp, tb, c->d_work, c->d_work2, c->d_ids, c->d_order, (int)cn, 0, 8, as));
+    }
+    k_assign<<<T / 128, 128, 0, as>>>(ix, p, c->fld, useAux, burnedIn, cn, L, bc, onv, c0, c->d_order);
     c->launches += 3;
-    SB_CUDA(cudaEventRecord(c->ev_free[s], st));
+    if (ovl) SB_CUDA(cudaEventRecord(c->ev_asg[set], as));
+    else SB_CUDA(cudaEventRecord(c->ev_free[s], st));
   }
+  if (c->overlap_assign && c->variant != 0)   // the batch-level kernels below read what the last k_assign launches wrote
+    for (int set = 0; set < 2 && (uint32_t)set < nch; ++set) SB_CUDA(cudaStreamWaitEvent(st, c->ev_asg[set], 0));
   // fold the batch into the online state (masses, FLD)
   if (n) {
     if (c->M) k_online_fold_mass<<<nblk(c->M, 256), 256, 0, st>>>(c->M, fm_ref, c->on.mass, c->on.mass_acc);
