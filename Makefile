@@ -12,11 +12,11 @@ CLI       := salmon_b200/sb_salmon
 all: $(LIB) $(CLI) oracle
 
 $(LIB): $(SRCS) $(HDRS)
-	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(SRCS) -ldl -lgomp -lz
+	$(NVCC) $(NVCCFLAGS) -shared -o $@.tmp $(SRCS) -ldl -lgomp -lz && mv -f $@.tmp $@
 
 # command-line front end (host C++ over the C ABI; finds the library next to itself)
 $(CLI): $(CSRC)/cli_main.cpp $(LIB) include/salmon_b200.h
-	g++ -O2 -std=c++17 -Wall -o $@ $(CSRC)/cli_main.cpp -Lsalmon_b200 -lsalmon_b200 -Wl,-rpath,'$$ORIGIN'
+	g++ -O2 -std=c++17 -Wall -o $@.tmp $(CSRC)/cli_main.cpp -Lsalmon_b200 -lsalmon_b200 -Wl,-rpath,'$$ORIGIN' && mv -f $@.tmp $@
 
 oracle:
 	$(MAKE) -C oracle

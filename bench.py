@@ -62,13 +62,23 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t_mark = index, None, [], None
+
+    def mark(self):
+        """start of the timed region: samples that arrive from now on are 'timed', earlier ones 'warm-up'"""
+        self.t_mark = time.perf_counter()
+
+    def wait_first(self, timeout=4.0):
+        """nvidia-smi needs a moment to start: block until its first line is in (so that short timed regions get samples)"""
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -76,7 +86,7 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
     def stop(self):
         if not self.proc:
@@ -87,7 +97,12 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        timed = [ln for (t, ln) in self.lines if self.t_mark is None or t >= self.t_mark]
+        window = "timed region"
+        if len(timed) < 3:      # a timed region shorter than a few sampling periods: add the warm-up steps (same kernels, same load)
+            timed = [ln for (_, ln) in self.lines]
+            window = "warm-up + timed region (timed region shorter than 3 sampling periods)"
+        for ln in timed:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -103,7 +118,7 @@ class ClockSampler:
         # samples under load = upper half of the observed clocks
         hi = sorted(sm)[len(sm) // 2:]
         return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 _CPU_BEST = {}
@@ -171,6 +186,68 @@ def stage_a_workload(rank, small=False):
     return txps, flat, left, right
 
 
+def write_fastq_pair(dirname, left, right):
+    """the step's reads as two plain 4-line FASTQ files (vectorised writer): what `sb_salmon quant -1 -2` would be given"""
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    paths = []
+    for tag, codes in (("1", left), ("2", right)):
+        n, L = codes.shape
+        rec = np.empty((n, 3 + L + 3 + L + 1), dtype=np.uint8)
+        rec[:, 0:3] = np.frombuffer(b"@r\n", dtype=np.uint8)
+        rec[:, 3:3 + L] = lut[codes]
+        rec[:, 3 + L:6 + L] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+        rec[:, 6 + L:6 + 2 * L] = ord("I")
+        rec[:, 6 + 2 * L] = 10
+        path = os.path.join(dirname, f"bench_{tag}.fq")
+        rec.tofile(path)
+        paths.append(path)
+    return paths
+
+
+def stage_a_from_files(idx, left, right, batch, ncores):
+    """row f1 measured: FASTQ files -> parser threads -> length buckets (pinned) -> sb_map_batch -> classes -> EM, through
+    sb_quant_files (the C++ driver `sb_salmon quant` calls); and the parser alone (sb_reads_next into host buffers)."""
+    import shutil
+    import tempfile
+    from salmon_b200 import _capi
+    need = 2 * left.shape[0] * (2 * left.shape[1] + 7) + (64 << 20)
+    base = None
+    if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK):
+        sv = os.statvfs("/dev/shm")
+        if sv.f_bavail * sv.f_frsize > need:
+            base = "/dev/shm"
+    d = tempfile.mkdtemp(prefix="sb_bench_", dir=base)
+    try:
+        n, L = left.shape
+        f1, f2 = write_fastq_pair(d, left, right)
+        threads = max(1, min(32, ncores - 2))
+        out = {"files": "2 plain FASTQ files in " + (base or "the temp dir"), "pairs": int(n), "parser_threads": threads}
+        bufs = (np.empty((batch, L), np.uint8), np.empty((batch, L), np.uint8), np.empty(batch, np.uint32), np.empty(batch, np.uint32))
+        best = 0.0
+        for _ in range(2):      # second pass: page cache warm, block pool filled
+            rf = _capi.ReadFiles(f1, f2, n_threads=threads)
+            t0 = time.perf_counter(); tot = 0
+            while True:
+                k = rf.next_batch(batch, L, out=bufs)[0]
+                if k == 0:
+                    break
+                tot += k
+            dt = time.perf_counter() - t0
+            rf.close()
+            best = max(best, tot / dt / 1e6)
+        out["parser_only_mreads_s"] = best
+        alpha, sm = _capi.quant_files_native(idx, f1, f2, batch=batch, max_read_len=L, threads=threads)
+        alpha, sm = _capi.quant_files_native(idx, f1, f2, batch=batch, max_read_len=L, threads=threads)
+        out.update({"files_to_classes_mreads_s": sm["n_observed"] / sm["map_seconds"] / 1e6, "map_seconds": sm["map_seconds"],
+                    "map_device_ms": sm["map_device_ms"], "em_seconds": sm["em_seconds"], "em_iters": sm["em_iters"],
+                    "n_mapped": int(sm["n_mapped"]), "api": "sb_quant_files (C ABI): reader thread + GPU thread, then sb_em_optimize"})
+        return out
+    except Exception as e:  # noqa: BLE001  (an extra measurement must not lose the bench line)
+        return {"error": repr(e)}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def stage_a_cpu(idx, p, left, right, budget_s, ncores):
     """CPU port (the product's serial forms compiled for the host, OpenMP over reads) on a bounded sample."""
     import hostmap_lib
@@ -230,13 +307,16 @@ def bench_stage_a(args, rank, world, local, dist, W, peak, peak_src, ncores):
     torch.cuda.set_device(local)
     dl = torch.from_numpy(left).cuda(); dr = torch.from_numpy(right).cuda()
     ctx.set_option("input_on_device", 1)
+    sampler = ClockSampler(local); sampler.start(); sampler.wait_first()
     barrier(); step((dl.data_ptr(), dr.data_ptr()))
+    sampler.mark()
     res_s, seed_ms_l, seed_n_l = [], [], 0
     for _ in range(args.steps):
         barrier()
         wall, dev_ms, seed_ms, seed_n, launches, res = step((dl.data_ptr(), dr.data_ptr()))
         res_s.append(wall); seed_ms_l.append(seed_ms); seed_n_l = seed_n
     barrier()
+    clocks_a = sampler.stop()
     c = res["counters"]
 
     def reduce_max(x):
@@ -271,6 +351,7 @@ def bench_stage_a(args, rank, world, local, dist, W, peak, peak_src, ncores):
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_t * 1e3,
                 "api": "sb_map_batch x batches + sb_map_finish (C ABI, pinned host buffers)"},
         "gpu_launches": int(launches),
+        "clocks": clocks_a,
         "roofline": {"bound": "hbm", "kernel": "k_seed_chain_w", "achieved": seed_achieved, "peak": peak, "unit": "GB/s",
                      "frac": seed_achieved / peak, "peak_source": peak_src, "avg_launch_ms": seed_launch_ms,
                      "fragments_per_launch": frags_per_launch,
@@ -284,7 +365,12 @@ def bench_stage_a(args, rank, world, local, dist, W, peak, peak_src, ncores):
         v, ns, cc = stage_a_cpu(idx, p, left, right, args.cpu_budget, ncores)
         out["cpu_baseline"] = {"value": v, "unit": "Mreads/s", "cores": ncores, "kind": "port",
                                "sample": f"{ns} read pairs of the same workload, same index, OpenMP over reads"}
-    ctx.close()
+        ctx.close()
+        ctx = None
+        if not args.no_files:
+            out["from_files"] = stage_a_from_files(idx, left, right, batch, ncores)
+    if ctx is not None:
+        ctx.close()
     return out
 
 
@@ -299,6 +385,7 @@ def main():
     ap.add_argument("--nccl", action="store_true", help="N>1: per-iteration ncclAllReduce instead of the fused kernel")
     ap.add_argument("--no-stage-a", action="store_true", help="skip the Stage A (mapping) measurement")
     ap.add_argument("--sa-small", action="store_true", help="Stage A on a 20x smaller transcriptome (dev)")
+    ap.add_argument("--no-files", action="store_true", help="skip the FASTQ-files -> classes measurement (row f1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -384,9 +471,10 @@ def main():
     # ---- device-resident: sb_em_run only
     ctx.upload(eq, proj, eff, uniq)
     ctx.prepare(p)
+    sampler = ClockSampler(local); sampler.start(); sampler.wait_first()
     for _ in range(W):
         ctx.flush_l2(); barrier(); ctx.run()
-    sampler = ClockSampler(local); sampler.start()
+    sampler.mark()
     run_ms, loop_ms, launches, loop_launches = [], [], 0, 0
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):

@@ -13,7 +13,9 @@
 // memchr per record), queueing blocks with a (offset, length) list of the sequence lines; sb_reads_next() hands the
 // records of a batch to an OpenMP team that translates bytes to codes straight into the caller's (pinned) buffers.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <zlib.h>
 
 #include <condition_variable>
@@ -40,11 +42,30 @@ struct CodeLut {
 };
 const CodeLut LUT;
 
-struct RecBlock {
-  std::vector<char> buf;       // raw text of whole records
+struct RecBlock {               // recycled through Stream::pool: no allocation / page faults in steady state
+  char* buf = nullptr;         // raw text of whole records
+  size_t cap = 0, len = 0;
   std::vector<uint32_t> seq;   // 2 per record: offset, length of the sequence line
   uint32_t n = 0;
+  ~RecBlock() { free(buf); }
+  bool reserve(size_t need) {
+    if (need <= cap) return true;
+    char* nb = (char*)realloc(buf, need);
+    if (!nb) return false;
+    buf = nb; cap = need;
+    return true;
+  }
 };
+
+// SB_READS_PROFILE=1: where the reader's time goes (printed by sb_reads_close)
+struct Prof {
+  double t_read = 0, t_scan = 0, t_push_wait = 0, t_alloc = 0;
+};
+inline double wall() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 struct Stream {
   std::vector<std::string> files;
@@ -52,8 +73,10 @@ struct Stream {
   std::mutex mu;
   std::condition_variable cv_put, cv_get;
   std::deque<std::unique_ptr<RecBlock>> q;
+  std::vector<std::unique_ptr<RecBlock>> pool;   // consumed blocks, reused by the splitter
   bool done = false, stop = false;
   std::string err;
+  Prof prof;
   // consumer side
   std::unique_ptr<RecBlock> cur;
   uint32_t cur_pos = 0;
@@ -116,10 +139,13 @@ size_t scan_records(const char* buf, size_t len, bool eof, RecBlock* blk, std::s
     const size_t p3 = (size_t)(nl2 - buf) + 1;
     if (p3 >= len) break;
     if (buf[p3] != '+') { err = "malformed FASTQ: third line of a record does not start with '+' (multi-line FASTQ is not supported)"; return cut; }
-    const char* nl3 = (const char*)memchr(buf + p3, '\n', len - p3);
+    const char* nl3 = (p3 + 1 < len && buf[p3 + 1] == '\n') ? buf + p3 + 1 : (const char*)memchr(buf + p3, '\n', len - p3);
     if (!nl3) break;
     const size_t q0 = (size_t)(nl3 - buf) + 1;
-    const char* nl4 = (q0 < len) ? (const char*)memchr(buf + q0, '\n', len - q0) : nullptr;
+    // the quality line is as long as the sequence line: look for its newline there first
+    const size_t raw = (size_t)(nl2 - buf) - s0;
+    const char* nl4 = (q0 + raw < len && buf[q0 + raw] == '\n') ? buf + q0 + raw
+                      : ((q0 < len) ? (const char*)memchr(buf + q0, '\n', len - q0) : nullptr);
     size_t qend, next;
     if (nl4) { qend = (size_t)(nl4 - buf); next = qend + 1; }
     else if (eof && q0 <= len) { qend = len; next = len; }
@@ -132,37 +158,125 @@ size_t scan_records(const char* buf, size_t len, bool eof, RecBlock* blk, std::s
   return cut;
 }
 
+// plain or gzip input behind one read call (gzread's transparent mode costs a copy: plain files are read() directly)
+struct Input {
+  gzFile g = nullptr;
+  FILE* f = nullptr;
+  bool open(const char* path) {
+    FILE* t = fopen(path, "rb");
+    if (!t) return false;
+    unsigned char m[2] = {0, 0};
+    const size_t k = fread(m, 1, 2, t);
+    if (k == 2 && m[0] == 0x1f && m[1] == 0x8b) {
+      fclose(t);
+      g = gzopen(path, "rb");
+      if (g) gzbuffer(g, 1u << 20);
+      return g != nullptr;
+    }
+    rewind(t);
+    setvbuf(t, nullptr, _IONBF, 0);
+    f = t;
+    return true;
+  }
+  long read(char* dst, size_t n, std::string& err) {
+    if (g) {
+      const int got = gzread(g, dst, (unsigned)n);
+      if (got < 0) { int e; err = gzerror(g, &e); }
+      return got;
+    }
+    const size_t got = fread(dst, 1, n, f);
+    if (got < n && ferror(f)) { err = "read error"; return -1; }
+    return (long)got;
+  }
+  void close() { if (g) gzclose(g); if (f) fclose(f); g = nullptr; f = nullptr; }
+};
+
+std::unique_ptr<RecBlock> take_block(Stream* s) {
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (!s->pool.empty()) {
+      std::unique_ptr<RecBlock> b = std::move(s->pool.back());
+      s->pool.pop_back();
+      b->seq.clear(); b->n = 0; b->len = 0;
+      return b;
+    }
+  }
+  return std::unique_ptr<RecBlock>(new RecBlock());
+}
+
 void split_stream(Stream* s) {
   std::string err;
   for (const std::string& path : s->files) {
-    gzFile g = gzopen(path.c_str(), "rb");
-    if (!g) { err = "cannot open " + path; break; }
-    gzbuffer(g, 1u << 20);
+    Input in;
+    if (!in.open(path.c_str())) { err = "cannot open " + path; break; }
     std::vector<char> carry;
     bool eof = false;
     while (!eof && err.empty()) {
-      std::unique_ptr<RecBlock> blk(new RecBlock());
-      blk->buf.resize(carry.size() + CHUNK);
-      if (!carry.empty()) memcpy(blk->buf.data(), carry.data(), carry.size());
-      const int got = gzread(g, blk->buf.data() + carry.size(), (unsigned)CHUNK);
-      if (got < 0) { int e; err = std::string("read error in ") + path + ": " + gzerror(g, &e); break; }
+      double t0 = wall();
+      std::unique_ptr<RecBlock> blk = take_block(s);
+      // slack for the carried-over partial record, so that recycled blocks are not re-allocated
+      if (!blk->reserve(std::max<size_t>(carry.size(), 1u << 20) + CHUNK)) { err = "out of memory"; break; }
+      if (!carry.empty()) memcpy(blk->buf, carry.data(), carry.size());
+      double t1 = wall();
+      s->prof.t_alloc += t1 - t0;
+      std::string rerr;
+      const long got = in.read(blk->buf + carry.size(), CHUNK, rerr);
+      t0 = wall();
+      s->prof.t_read += t0 - t1;
+      if (got < 0) { err = "read error in " + path + ": " + rerr; break; }
       const size_t len = carry.size() + (size_t)got;
       eof = (size_t)got < CHUNK;
-      const size_t cut = scan_records(blk->buf.data(), len, eof, blk.get(), err);
+      const size_t cut = scan_records(blk->buf, len, eof, blk.get(), err);
+      t1 = wall();
+      s->prof.t_scan += t1 - t0;
       if (!err.empty()) { err += " (" + path + ")"; break; }
-      carry.assign(blk->buf.data() + cut, blk->buf.data() + len);
-      blk->buf.resize(cut);
+      carry.assign(blk->buf + cut, blk->buf + len);
+      blk->len = cut;
       blk->n = (uint32_t)(blk->seq.size() / 2);
       if (eof) {
         for (char ch : carry)
           if (ch != '\n' && ch != '\r' && ch != ' ' && ch != '\t') { err = "truncated record at the end of " + path; break; }
       }
-      if (blk->n && err.empty() && !push_block(s, std::move(blk))) { gzclose(g); finish_stream(s, ""); return; }
+      t0 = wall();
+      const bool pushed = !(blk->n && err.empty()) || push_block(s, std::move(blk));
+      s->prof.t_push_wait += wall() - t0;
+      if (!pushed) { in.close(); finish_stream(s, ""); return; }
     }
-    gzclose(g);
+    in.close();
     if (!err.empty()) break;
   }
   finish_stream(s, err);
+}
+
+// bytes -> base codes, 32 at a time: the low nibble of A C G T U (1 3 7 4 5) indexes a code table and a table of the
+// expected upper-case letter; a byte whose upper-case form is not the expected letter is N (4).
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) void translate_avx2(const uint8_t* src, uint8_t* dst, uint32_t n) {
+  const __m256i code_tab = _mm256_setr_epi8(4, 0, 4, 1, 3, 3, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4, 4, 0, 4, 1, 3, 3, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4);
+  const __m256i chr_tab = _mm256_setr_epi8(0, 'A', 0, 'C', 'T', 'U', 0, 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 'A', 0, 'C', 'T', 'U', 0, 'G', 0, 0, 0, 0, 0, 0,
+                                           0, 0);
+  const __m256i up = _mm256_set1_epi8((char)0xDF), lo = _mm256_set1_epi8(0x0F), four = _mm256_set1_epi8(4);
+  uint32_t j = 0;
+  for (; j + 32 <= n; j += 32) {
+    const __m256i c = _mm256_loadu_si256((const __m256i*)(src + j));
+    const __m256i u = _mm256_and_si256(c, up);
+    const __m256i nib = _mm256_and_si256(c, lo);
+    const __m256i code = _mm256_shuffle_epi8(code_tab, nib);
+    const __m256i want = _mm256_shuffle_epi8(chr_tab, nib);
+    const __m256i ok = _mm256_cmpeq_epi8(u, want);
+    _mm256_storeu_si256((__m256i*)(dst + j), _mm256_blendv_epi8(four, code, ok));
+  }
+  for (; j < n; ++j) dst[j] = LUT.t[src[j]];
+}
+const bool HAVE_AVX2 = __builtin_cpu_supports("avx2");
+#else
+const bool HAVE_AVX2 = false;
+inline void translate_avx2(const uint8_t*, uint8_t*, uint32_t) {}
+#endif
+inline void translate(const uint8_t* src, uint8_t* dst, uint32_t n) {
+  if (HAVE_AVX2) { translate_avx2(src, dst, n); return; }
+  for (uint32_t j = 0; j < n; ++j) dst[j] = LUT.t[src[j]];
 }
 
 struct Task {
@@ -181,6 +295,7 @@ struct sb_reads {
   uint64_t n_delivered = 0;
   uint32_t max_len_seen = 0;
   bool failed = false;
+  double t_wait_blocks = 0, t_translate = 0;
 };
 
 extern "C" sb_reads* sb_reads_open(const char* const* files1, const char* const* files2, uint32_t n_files,
@@ -205,6 +320,13 @@ extern "C" void sb_reads_close(sb_reads* r) {
     r->st[m].cv_put.notify_all();
     if (r->st[m].th.joinable()) r->st[m].th.join();
   }
+  if (getenv("SB_READS_PROFILE")) {
+    for (int m = 0; m < r->n_streams; ++m)
+      fprintf(stderr, "sb_reads: stream %d splitter: alloc %.3f s, read/inflate %.3f s, scan %.3f s, waiting for the consumer %.3f s\n", m,
+              r->st[m].prof.t_alloc, r->st[m].prof.t_read, r->st[m].prof.t_scan, r->st[m].prof.t_push_wait);
+    fprintf(stderr, "sb_reads: consumer: waiting for blocks %.3f s, translating %.3f s, %llu records\n", r->t_wait_blocks, r->t_translate,
+            (unsigned long long)r->n_delivered);
+  }
   delete r;
 }
 
@@ -215,8 +337,9 @@ extern "C" int64_t sb_reads_next(sb_reads* r, uint32_t max_pairs, uint32_t strid
   }
   if (r->failed) { sb::set_error("sb_reads_next: the reader is in a failed state"); return SB_ERR_INVALID; }
   std::vector<Task> tasks;
-  std::vector<std::unique_ptr<RecBlock>> retired;
+  std::vector<std::pair<int, std::unique_ptr<RecBlock>>> retired;   // (stream, fully consumed block)
   uint64_t filled[2] = {0, 0};
+  const double tw0 = wall();
   for (int m = 0; m < r->n_streams; ++m) {
     Stream& s = r->st[m];
     while (filled[m] < max_pairs) {
@@ -235,7 +358,7 @@ extern "C" int64_t sb_reads_next(sb_reads* r, uint32_t max_pairs, uint32_t strid
         tasks.push_back(Task{s.cur.get(), s.cur_pos + o, std::min(2048u, take - o), filled[m] + o, m});
       s.cur_pos += take;
       filled[m] += take;
-      if (s.cur_pos == s.cur->n) retired.push_back(std::move(s.cur));
+      if (s.cur_pos == s.cur->n) retired.emplace_back(m, std::move(s.cur));
     }
   }
   if (r->n_streams == 2 && filled[0] != filled[1]) {
@@ -245,6 +368,8 @@ extern "C" int64_t sb_reads_next(sb_reads* r, uint32_t max_pairs, uint32_t strid
     return SB_ERR_INVALID;
   }
   uint32_t maxlen = 0;
+  const double tw1 = wall();
+  r->t_wait_blocks += tw1 - tw0;
   const int nt = (int)std::max<size_t>(1, std::min<size_t>(r->n_threads, tasks.size()));
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nt) reduction(max : maxlen)
   for (long ti = 0; ti < (long)tasks.size(); ++ti) {
@@ -256,11 +381,17 @@ extern "C" int64_t sb_reads_next(sb_reads* r, uint32_t max_pairs, uint32_t strid
       maxlen = std::max(maxlen, len);
       lens[t.dst + i] = len;
       const uint32_t n = std::min(len, stride);
-      const uint8_t* src = (const uint8_t*)t.blk->buf.data() + off;
+      const uint8_t* src = (const uint8_t*)t.blk->buf + off;
       uint8_t* d = out + (t.dst + i) * (size_t)stride;
-      for (uint32_t j = 0; j < n; ++j) d[j] = LUT.t[src[j]];
+      translate(src, d, n);
       if (n < stride) memset(d + n, 4, stride - n);
     }
+  }
+  r->t_translate += wall() - tw1;
+  for (auto& b : retired) {   // hand the consumed blocks back to their splitter
+    Stream& s = r->st[b.first];
+    std::lock_guard<std::mutex> lk(s.mu);
+    if (s.pool.size() < 2 * MAX_QUEUED) s.pool.push_back(std::move(b.second));
   }
   r->max_len_seen = std::max(r->max_len_seen, maxlen);
   if (maxlen > stride) {

@@ -847,7 +847,7 @@ struct sb_map_ctx {
   BatchBufs b{};                     // cand/score/task buffers: one chunk; outputs: whole batch
   // k_assign of chunk i runs on its own stream next to the seed / DP kernels of chunk i+1 (it is latency-bound at
   // ~10 % issue utilisation, they are issue-bound): the buffers both sides touch exist twice
-  int overlap_assign = 0;
+  int overlap_assign = 1;   // +2.7 % at human scale (profiles/stageA_r1_overlap_ab.txt); results bit-identical
   cudaStream_t assign_stream = nullptr;
   cudaEvent_t ev_dp[2] = {nullptr, nullptr}, ev_asg[2] = {nullptr, nullptr};
   uint32_t *alt_n_l = nullptr, *alt_n_r = nullptr;

@@ -164,28 +164,51 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
       if (n == 0) break;
       P.n_observed += (uint64_t)n;
       if (bi++ % o.shard_count != o.shard_index) continue;
-      for (int64_t i = 0; i < n && err.empty(); ++i) {
-        const uint32_t L = std::min(ll[i], lr[i]);
-        if (ll[i] != lr[i]) ++P.n_trimmed_mates;
-        if (L < mp.k) { ++P.n_too_short; continue; }   // cannot hold a k-mer: observed, never assigned
-        std::unique_ptr<Bucket>& bp = buckets[L];
-        if (!bp) {
-          bp.reset(new Bucket());
-          // the first length seen gets full-size buffers; rarer lengths smaller ones
-          const uint32_t cap = buckets.size() == 1 ? o.batch : std::max<uint32_t>(o.batch / 8, 4096);
-          if (bp->buf[0].alloc(cap, L) != SB_OK || bp->buf[1].alloc(cap, L) != SB_OK) { err = sb_last_error(); break; }
+      // rows [i0, i1) of the staging buffers -> the bucket of length L (copied by an OpenMP team when it is a run)
+      auto put_rows = [&](uint32_t L, int64_t i0, int64_t i1) {
+        while (i0 < i1 && err.empty()) {
+          std::unique_ptr<Bucket>& bp = buckets[L];
+          if (!bp) {
+            bp.reset(new Bucket());
+            // the first length seen gets full-size buffers; rarer lengths smaller ones
+            const uint32_t cap = buckets.size() == 1 ? o.batch : std::max<uint32_t>(o.batch / 8, 4096);
+            if (bp->buf[0].alloc(cap, L) != SB_OK || bp->buf[1].alloc(cap, L) != SB_OK) { err = sb_last_error(); return; }
+          }
+          HostBuf* b = &bp->buf[bp->fill];
+          if (!bp->checked) {   // first row after a flip: the GPU side must have released this buffer
+            std::unique_lock<std::mutex> lk(P.mu);
+            P.cv_free.wait(lk, [&] { return !b->busy || P.abort; });
+            if (P.abort) { err = "aborted"; return; }
+            bp->checked = true;
+          }
+          const int64_t take = std::min<int64_t>(i1 - i0, (int64_t)(b->cap - bp->cnt));
+          const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(o.threads, take / 4096));
+#pragma omp parallel for schedule(static) num_threads(nt)
+          for (int64_t q = 0; q < take; ++q) {
+            memcpy(b->left + (size_t)(bp->cnt + q) * L, sl.data() + (size_t)(i0 + q) * stride, L);
+            memcpy(b->right + (size_t)(bp->cnt + q) * L, sr.data() + (size_t)(i0 + q) * stride, L);
+          }
+          bp->cnt += (uint32_t)take;
+          i0 += take;
+          if (bp->cnt == b->cap) { b->n = bp->cnt; submit(b); bp->fill ^= 1; bp->cnt = 0; bp->checked = false; }
         }
-        HostBuf* b = &bp->buf[bp->fill];
-        if (!bp->checked) {   // first row after a flip: the GPU side must have released this buffer
-          std::unique_lock<std::mutex> lk(P.mu);
-          P.cv_free.wait(lk, [&] { return !b->busy || P.abort; });
-          if (P.abort) break;
-          bp->checked = true;
+      };
+      // runs of equal length go in one piece (the common case: the whole batch)
+      int64_t run0 = 0;
+      uint32_t runL = 0;
+      for (int64_t i = 0; i <= n && err.empty(); ++i) {
+        uint32_t L = 0;
+        if (i < n) {
+          L = std::min(ll[i], lr[i]);
+          if (ll[i] != lr[i]) ++P.n_trimmed_mates;
+          if (L < mp.k) { ++P.n_too_short; L = 0; }   // cannot hold a k-mer: observed, never assigned
         }
-        memcpy(b->left + (size_t)bp->cnt * L, sl.data() + (size_t)i * stride, L);
-        memcpy(b->right + (size_t)bp->cnt * L, sr.data() + (size_t)i * stride, L);
-        if (++bp->cnt == b->cap) { b->n = bp->cnt; submit(b); bp->fill ^= 1; bp->cnt = 0; bp->checked = false; }
+        if (i == n || L != runL) {
+          if (runL != 0 && i > run0) put_rows(runL, run0, i);
+          run0 = i; runL = L;
+        }
       }
+      if (err == "aborted") { err.clear(); break; }
       if (!err.empty()) break;
     }
     if (err.empty())
