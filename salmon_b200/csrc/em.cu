@@ -36,6 +36,8 @@ namespace sb {
 // ---------------------------------------------------------------------------
 struct KernelSet {
   const char* name;
+  int ch;            // ring chunk (columns)
+  bool dyn;          // persistent kernel takes its work from per-block unit tables (k_em_persistent_dyn)
   size_t smem;
   const void* persistent;
   const void* persistent_mgpu;
@@ -47,6 +49,8 @@ template <int CH, int MINB, int MODE>
 static KernelSet make_set(const char* name) {
   KernelSet k;
   k.name = name;
+  k.ch = CH;
+  k.dyn = false;
   k.smem = em_smem<CH>();
   k.persistent = (const void*)k_em_persistent<CH, MINB, MODE>;
   k.persistent_mgpu = (const void*)k_em_persistent_mgpu<CH, MINB, MODE>;
@@ -55,15 +59,25 @@ static KernelSet make_set(const char* name) {
   k.p2_partial = k_em_p2_partial<CH, MINB, MODE>;
   return k;
 }
+// dynamic distribution inside a block (single-GPU persistent kernel only; the other entry points are MODE 0)
+template <int CH, int MINB>
+static KernelSet make_set_dyn(const char* name) {
+  KernelSet k = make_set<CH, MINB, 0>(name);
+  k.dyn = true;
+  k.smem = em_smem_dyn<CH>();
+  k.persistent = (const void*)k_em_persistent_dyn<CH, MINB>;
+  return k;
+}
 // MODE 0: lane-per-row loop with inline epilogues (round-1 kernel); MODE 1 / 2: batched streaming (8 / 16 gathers
 // per lane in flight, epilogues after the stream), see run_phase_b.
-constexpr int N_KERNEL_SETS = 11;
+constexpr int N_KERNEL_SETS = 13;
 static const KernelSet& kernel_set(int cfg) {
   static const KernelSet sets[N_KERNEL_SETS] = {
       make_set<8, 3, 0>("ch8b3"),     make_set<16, 2, 0>("ch16b2"),   make_set<8, 4, 0>("ch8b4"),
       make_set<4, 4, 0>("ch4b4"),     make_set<4, 3, 0>("ch4b3"),     make_set<8, 2, 0>("ch8b2"),
       make_set<16, 2, 1>("ch16b2m1"), make_set<16, 2, 2>("ch16b2m2"), make_set<8, 2, 1>("ch8b2m1"),
-      make_set<8, 3, 1>("ch8b3m1"),   make_set<8, 4, 1>("ch8b4m1"),
+      make_set<8, 3, 1>("ch8b3m1"),   make_set<8, 4, 1>("ch8b4m1"),   make_set_dyn<16, 2>("ch16b2dyn"),
+      make_set_dyn<8, 3>("ch8b3dyn"),
   };
   if (cfg < 0 || cfg >= N_KERNEL_SETS) cfg = 0;
   return sets[cfg];
@@ -511,7 +525,8 @@ extern "C" sb_em_ctx* sb_em_create(int device) {
 
 static void free_sell(SellDev& m) {
   void** ptrs[] = {(void**)&m.slice_ptr, (void**)&m.width, (void**)&m.len, (void**)&m.idx,
-                   (void**)&m.w, (void**)&m.warp_begin, (void**)&m.long_rows, (void**)&m.targets};
+                   (void**)&m.w, (void**)&m.warp_begin, (void**)&m.long_rows, (void**)&m.targets,
+                   (void**)&m.units, (void**)&m.blk_unit_ptr};
   for (void** p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -762,6 +777,45 @@ static int build_sell(sb_em_ctx* c, SellDev& m, uint32_t n_rows, const uint32_t*
                                                         m.warp_begin);
   c->launches++;
   SB_CUDA(cudaStreamSynchronize(st));   // h_targets must outlive the copy
+  const KernelSet& ks = kernel_set(c->config);
+  if (ks.dyn && n_warps >= (uint32_t)(EM_THREADS / 32)) {
+    // unit tables of k_em_persistent_dyn: the slice range of every block (= of its 8 warps' balanced ranges) cut into
+    // units of whole slices with <= CH columns and <= 32 slices; a slice wider than CH is a unit of its own;
+    // zero-width slices (only long / absent rows) need no unit.  Costliest first inside a block.
+    const uint32_t wpb = EM_THREADS / 32, grid = n_warps / wpb, CHc = (uint32_t)ks.ch;
+    std::vector<uint32_t> h_sp((size_t)m.n_slices + 1), h_wb((size_t)n_warps + 1);
+    SB_CUDA(cudaMemcpy(h_sp.data(), m.slice_ptr, h_sp.size() * 4, cudaMemcpyDeviceToHost));
+    SB_CUDA(cudaMemcpy(h_wb.data(), m.warp_begin, h_wb.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint4> units;
+    std::vector<uint32_t> bptr(grid + 1, 0);
+    for (uint32_t b = 0; b < grid; ++b) {
+      const uint32_t lo = h_wb[(size_t)b * wpb], hi = h_wb[(size_t)(b + 1) * wpb];
+      const size_t first = units.size();
+      uint32_t s = lo;
+      while (s < hi) {
+        while (s < hi && h_sp[s + 1] == h_sp[s]) ++s;          // zero-width slices open no unit
+        if (s >= hi) break;
+        const uint32_t s0 = s;
+        uint32_t cols = 0;
+        while (s < hi && s - s0 < 32u) {
+          const uint32_t w = h_sp[s + 1] - h_sp[s];
+          if (cols > 0 && cols + w > CHc) break;
+          cols += w;
+          ++s;
+          if (cols >= CHc) break;                               // (also ends a unit made of one wide slice)
+        }
+        units.push_back(make_uint4(s0, s, h_sp[s0], h_sp[s]));
+      }
+      std::stable_sort(units.begin() + first, units.end(), [&](const uint4& x, const uint4& y) {
+        return (x.w - x.z) + (uint64_t)overhead * (x.y - x.x) > (y.w - y.z) + (uint64_t)overhead * (y.y - y.x);
+      });
+      bptr[b + 1] = (uint32_t)units.size();
+    }
+    SB_TRY(dev_alloc(&m.units, units.size() + 1));
+    SB_TRY(dev_alloc(&m.blk_unit_ptr, (size_t)grid + 1));
+    SB_CUDA(cudaMemcpy(m.units, units.data(), units.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(m.blk_unit_ptr, bptr.data(), bptr.size() * 4, cudaMemcpyHostToDevice));
+  }
   return SB_OK;
 }
 
@@ -986,6 +1040,7 @@ static Sell sell_view(const SellDev& m) {
   s.long_rows = m.long_rows; s.csr_idx = m.csr_idx; s.csr_w = m.csr_w;
   s.n_rows = m.n_rows; s.n_slices = m.n_slices; s.n_long = m.n_long;
   s.n_block = m.n_block;
+  s.units = m.units; s.blk_unit_ptr = m.blk_unit_ptr;
   s.keep_pct = 100;
   return s;
 }

@@ -20,6 +20,8 @@ struct SellDev {
   uint32_t* warp_begin = nullptr;
   uint32_t* long_rows = nullptr;
   uint64_t* targets = nullptr;   // optional per-warp cumulative work targets (balance_long)
+  uint4* units = nullptr;        // k_em_persistent_dyn: work units per block
+  uint32_t* blk_unit_ptr = nullptr;
   const uint32_t* csr_idx = nullptr;  // not owned
   const double* csr_w = nullptr;      // not owned
 };

@@ -47,6 +47,10 @@ struct Sell {
   const double* csr_w;
   uint32_t n_rows, n_slices, n_long;
   uint32_t n_block;            // the first n_block long rows (longest first) take the block path
+  // dynamic distribution (k_em_persistent_dyn): the slices of a block cut into units of <= CH columns (whole slices;
+  // a slice wider than CH is a unit of its own), handed out to the block's warps through a shared-memory counter
+  const uint4* units;          // {first slice, end slice, first column, end column}, per block, costliest first
+  const uint32_t* blk_unit_ptr;// [grid+1]
   uint32_t keep_pct;           // % of stream chunks loaded with L2 evict_last (rest evict_first)
 };
 
@@ -104,7 +108,7 @@ struct __align__(128) WarpRing {
 };
 constexpr int EM_WARPS = EM_THREADS / 32;
 template <int CH>
-constexpr size_t em_smem() { return sizeof(WarpRing<CH>) * EM_WARPS + EM_WARPS * RING * 8 + 40 * 8; }
+__host__ __device__ constexpr size_t em_smem() { return sizeof(WarpRing<CH>) * EM_WARPS + EM_WARPS * RING * 8 + 40 * 8; }
 
 template <int CH>
 struct WarpCtx {
@@ -646,6 +650,284 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent(const __grid
 #pragma unroll
     for (int k = 0; k < RING; ++k)
       if ((uint32_t)k < nchunks) mbar_wait(&W.bars[k], (W.phase_bits >> k) & 1u);
+  }
+}
+
+// ---- dynamic distribution inside a block (MODE 3, k_em_persistent_dyn) ---------------------------------------------
+// Round-1 timeline: the median warp finishes P1 in 6.4 us and P2 in 11 us, the slowest in 10.7 / 17.6 us, and 42 % of
+// all warp-time is spent at the two grid barriers.  The per-warp time is the latency of the warp's own instruction
+// stream, so its spread is latency noise on a static share.  Here a block's slices are cut (host side, at prepare)
+// into units of <= CH columns and the block's 8 warps take units from a shared-memory counter until none is left: the
+// static share becomes the block's, the variance averages over 8 warps x ~10 units.  A warp keeps its private ring;
+// the chunk stream it feeds is "the chunks of the units I grabbed", issued RING chunks ahead of consumption (the unit
+// after the current one is grabbed, and its bulk copies issued, while the current one is consumed; the first units of
+// the next phase before the grid barrier).  Per-row arithmetic and summation order are those of MODE 0.
+constexpr int UQ = 4;               // units in flight per warp (consumed + issued ahead), >= RING + 1
+struct __align__(16) DynWarp {
+  uint4 uq[UQ];                     // unit descriptors, ring indexed by units grabbed
+  uint32_t sp[UQ][32];              // end column of each slice of the unit
+  uint32_t cq[RING][2];             // column range of the chunk in each ring slot
+};
+template <int CH>
+__host__ __device__ constexpr size_t em_smem_dyn() { return em_smem<CH>() + sizeof(DynWarp) * EM_WARPS + 16; }
+
+struct DynState {                   // warp-uniform
+  uint32_t ki = 0, kc = 0;          // chunks issued / consumed
+  uint32_t i_col = 0, i_end = 0;    // issue side: next column, end column of the unit being issued
+  uint32_t un_in = 0, un_out = 0;   // units grabbed / taken over by the consumer
+  bool i_done = true;               // no more units in this phase
+};
+
+// issue bulk copies until RING chunks are in flight or the block has no more units
+template <int CH>
+__device__ __forceinline__ void dyn_issue(const Sell& S, WarpCtx<CH>& W, DynWarp* D, DynState& st, uint32_t* ctr,
+                                          uint32_t ub0, uint32_t ub1) {
+  const uint32_t lane = threadIdx.x & 31u;
+  while (st.ki - st.kc < (uint32_t)RING) {
+    if (st.i_col == st.i_end) {
+      if (st.i_done || st.un_in - st.un_out >= (uint32_t)UQ) break;
+      uint32_t u = 0;
+      if (lane == 0) u = ub0 + atomicAdd(ctr, 1u);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if (u >= ub1) { st.i_done = true; break; }
+      const uint4 d = __ldg(&S.units[u]);
+      const uint32_t q = st.un_in % UQ;
+      if (lane == 0) D->uq[q] = d;
+      D->sp[q][lane] = (d.x + lane < d.y) ? __ldg(&S.slice_ptr[d.x + lane + 1]) : d.w;
+      ++st.un_in;
+      st.i_col = d.z; st.i_end = d.w;
+    }
+    const uint32_t cols = min((uint32_t)CH, st.i_end - st.i_col);
+    const int slot = st.ki % RING;
+    if (lane == 0) {
+      const uint32_t c = st.i_col;
+      const bool keep = (((c / CH) * 2654435761u) >> 16) % 100u < S.keep_pct;
+      const uint64_t pol = keep ? l2_policy_evict_last() : l2_policy_evict_first();
+      D->cq[slot][0] = c; D->cq[slot][1] = c + cols;
+      mbar_arrive_expect_tx(&W.bars[slot], cols * 384u);
+      bulk_g2s_hint(W.ring->w[slot], S.w + (size_t)c * 32u, cols * 256u, &W.bars[slot], pol);
+      bulk_g2s_hint(W.ring->idx[slot], S.idx + (size_t)c * 32u, cols * 128u, &W.bars[slot], pol);
+    }
+    st.i_col += cols;
+    ++st.ki;
+  }
+  __syncwarp();
+}
+
+// start issuing for a phase (its counter, its unit range); called before the grid barrier that precedes the phase
+template <int CH>
+__device__ __forceinline__ void dyn_begin(const Sell& S, WarpCtx<CH>& W, DynWarp* D, DynState& st, uint32_t* ctr,
+                                          uint32_t ub0, uint32_t ub1) {
+  st.i_col = st.i_end = 0;
+  st.i_done = (ub0 >= ub1);
+  dyn_issue(S, W, D, st, ctr, ub0, ub1);
+}
+
+template <int PHASE, int CH>
+__device__ __forceinline__ void run_phase_dyn(const EmArgs& A, WarpCtx<CH>& W, DynWarp* D, DynState& st, uint32_t* ctr,
+                                              uint32_t ub0, uint32_t ub1, uint32_t bid, uint32_t nblk, double logNorm,
+                                              double bias, P2Acc& pa) {
+  const Sell& S = (PHASE == 1) ? A.cm : A.tm;
+  const double* gsrc = (PHASE == 1) ? A.theta : A.scale;   // rewritten by other blocks: coherent loads only
+  const bool em_nan_guard = (PHASE == 1) && !A.vbem;
+  const uint32_t lane = threadIdx.x & 31u;
+  // the unit being consumed
+  uint32_t s = 0, u_s0 = 0, u_s1 = 0, u_rem = 0, slice_end = 0, sp = 0;
+  RowOps ops;
+  ops.x0 = ops.x1 = ops.x2 = ops.x3 = 0.0;
+  ops.len = LEN_LONG;
+  double acc = 0.0;
+  auto next_slice = [&]() {
+    row_finish<PHASE>(A, s * 32u + lane, ops, acc, logNorm, bias, pa);
+    ++s;
+    acc = 0.0;
+    if (s < u_s1) {
+      slice_end = __shfl_sync(0xffffffffu, sp, (int)(s - u_s0));
+      ops = load_ops<PHASE>(A, S, s * 32u + lane);
+    }
+  };
+  for (;;) {
+    if (st.kc == st.ki) {
+      dyn_issue(S, W, D, st, ctr, ub0, ub1);
+      if (st.kc == st.ki) break;           // nothing in flight, nothing left to grab
+    }
+    const int slot = st.kc % RING;
+    mbar_wait(&W.bars[slot], (W.phase_bits >> slot) & 1u);
+    W.phase_bits ^= (1u << slot);
+    const uint32_t c0 = D->cq[slot][0], cstop = D->cq[slot][1];
+    if (u_rem == 0) {                      // this chunk opens the next unit
+      while (s < u_s1) next_slice();       // (trailing zero-width slices of the previous unit)
+      const uint32_t q = st.un_out % UQ;
+      const uint4 d = D->uq[q];
+      sp = D->sp[q][lane];
+      ++st.un_out;
+      u_s0 = d.x; u_s1 = d.y; u_rem = d.w - d.z;
+      s = u_s0;
+      slice_end = __shfl_sync(0xffffffffu, sp, 0);
+      ops = load_ops<PHASE>(A, S, s * 32u + lane);
+      acc = 0.0;
+    }
+    const uint32_t* sidx = W.ring->idx[slot] + lane;
+    const double* sw = W.ring->w[slot] + lane;
+    uint32_t col = c0;
+    while (col < cstop) {
+      while (col == slice_end && s + 1 < u_s1) next_slice();   // (possibly zero-width slices)
+      const uint32_t n = min(slice_end, cstop) - col;
+      const uint32_t l0 = col - c0;
+      uint32_t j = 0;
+      for (; j + 4 <= n; j += 4) {
+        const uint32_t o = (l0 + j) * 32u;
+        const double g0 = gsrc[sidx[o]], g1 = gsrc[sidx[o + 32]];
+        const double g2 = gsrc[sidx[o + 64]], g3 = gsrc[sidx[o + 96]];
+        double v0 = g0 * sw[o], v1 = g1 * sw[o + 32], v2 = g2 * sw[o + 64], v3 = g3 * sw[o + 96];
+        if (em_nan_guard) {
+          if (isnan(v0)) v0 = 0.0;
+          if (isnan(v1)) v1 = 0.0;
+          if (isnan(v2)) v2 = 0.0;
+          if (isnan(v3)) v3 = 0.0;
+        }
+        acc += v0; acc += v1; acc += v2; acc += v3;
+      }
+      for (; j < n; ++j) {
+        const uint32_t o = (l0 + j) * 32u;
+        double v = gsrc[sidx[o]] * sw[o];
+        if (em_nan_guard && isnan(v)) v = 0.0;
+        acc += v;
+      }
+      col += n;
+    }
+    u_rem -= cstop - c0;
+    __syncwarp();
+    ++st.kc;
+    dyn_issue(S, W, D, st, ctr, ub0, ub1);
+  }
+  while (s < u_s1) next_slice();
+  if (W.dbg && lane == 0) *W.dbg = gtime_ns();
+  // long rows exactly as in MODE 0 (static distribution)
+  for (uint32_t li = bid; li < S.n_block; li += nblk) {
+    const uint32_t r = __ldg(&S.long_rows[3 * li]);
+    const uint32_t b = __ldg(&S.long_rows[3 * li + 1]);
+    const uint32_t e = __ldg(&S.long_rows[3 * li + 2]);
+    double a = 0.0;
+    for (uint32_t k = b + threadIdx.x; k < e; k += EM_THREADS) {
+      double v = gsrc[__ldg(&S.csr_idx[k])] * __ldg(&S.csr_w[k]);
+      if (em_nan_guard && isnan(v)) v = 0.0;
+      a += v;
+    }
+    a = block_reduce<false>(a, W.scratch);
+    if (threadIdx.x == 0) {
+      RowOps o = load_ops<PHASE>(A, S, r);
+      o.len = 0;
+      row_finish<PHASE>(A, r, o, a, logNorm, bias, pa);
+    }
+    __syncthreads();
+  }
+  {
+    const uint32_t gw = bid * EM_WARPS + (threadIdx.x >> 5);
+    const uint32_t nw = nblk * EM_WARPS;
+    uint32_t cnt = 0, myrow = 0xffffffffu;
+    double myacc = 0.0;
+    auto flush = [&]() {
+      if (myrow != 0xffffffffu) {
+        RowOps o = load_ops<PHASE>(A, S, myrow);
+        o.len = 0;
+        row_finish<PHASE>(A, myrow, o, myacc, logNorm, bias, pa);
+      }
+      myrow = 0xffffffffu;
+      cnt = 0;
+    };
+    for (uint32_t li = S.n_block + gw; li < S.n_long; li += nw) {
+      const uint32_t r = __ldg(&S.long_rows[3 * li]);
+      const uint32_t b = __ldg(&S.long_rows[3 * li + 1]);
+      const uint32_t e = __ldg(&S.long_rows[3 * li + 2]);
+      double a0 = 0.0, a1 = 0.0;
+      uint32_t k = b + lane;
+      for (; k + 32 < e; k += 64) {
+        const uint32_t i0 = __ldg(&S.csr_idx[k]), i1 = __ldg(&S.csr_idx[k + 32]);
+        double v0 = gsrc[i0] * __ldg(&S.csr_w[k]);
+        double v1 = gsrc[i1] * __ldg(&S.csr_w[k + 32]);
+        if (em_nan_guard) {
+          if (isnan(v0)) v0 = 0.0;
+          if (isnan(v1)) v1 = 0.0;
+        }
+        a0 += v0;
+        a1 += v1;
+      }
+      if (k < e) {
+        double v = gsrc[__ldg(&S.csr_idx[k])] * __ldg(&S.csr_w[k]);
+        if (em_nan_guard && isnan(v)) v = 0.0;
+        a0 += v;
+      }
+      const double a = warp_sum(a0 + a1);
+      if (lane == cnt) { myacc = a; myrow = r; }
+      if (++cnt == 32) flush();
+    }
+    flush();
+  }
+}
+
+template <int CH, int MINB>
+__global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent_dyn(const __grid_constant__ EmArgs A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  WarpCtx<CH> W;
+  warp_setup(W, smem);
+  double* scratch = W.scratch;
+  DynWarp* D = reinterpret_cast<DynWarp*>(smem + em_smem<CH>()) + (threadIdx.x >> 5);
+  uint32_t* s_ctr = reinterpret_cast<uint32_t*>(smem + em_smem<CH>() + sizeof(DynWarp) * EM_WARPS);   // [0] P1, [1] P2
+  if (threadIdx.x == 0) { s_ctr[0] = 0u; s_ctr[1] = 0u; }
+  __syncthreads();
+  cg::grid_group grid = cg::this_grid();
+  const uint32_t bid = blockIdx.x, nblk = gridDim.x;
+  const uint32_t gwarp = bid * (EM_THREADS / 32) + (threadIdx.x >> 5);
+  const uint32_t u1a = __ldg(&A.cm.blk_unit_ptr[bid]), u1b = __ldg(&A.cm.blk_unit_ptr[bid + 1]);
+  const uint32_t u2a = __ldg(&A.tm.blk_unit_ptr[bid]), u2b = __ldg(&A.tm.blk_unit_ptr[bid + 1]);
+  DynState st;
+  uint32_t it = 0;
+  bool converged = false;
+  double logNorm = A.vbem ? digamma_pos(A.sum0) : 0.0;
+  dyn_begin(A.cm, W, D, st, &s_ctr[0], u1a, u1b);
+  while (it < A.min_iter || (it < A.max_iter && !converged)) {
+    const uint32_t par = it & 1u;
+    if (bid == 0 && threadIdx.x == 0) A.maxrel[par] = 0ull;
+    if (A.vbem && it > 0) lag_lognorm_warp0(A, par, nblk, scratch);  // consumed after the next barrier
+    P2Acc pa{0.0, 0.0};
+    SB_DBG(0)
+    run_phase_dyn<1, CH>(A, W, D, st, &s_ctr[0], u1a, u1b, bid, nblk, 0.0, 0.0, pa);
+    SB_DBG(1)
+    dyn_begin(A.tm, W, D, st, &s_ctr[1], u2a, u2b);   // first units of P2: their stream lands during the barrier
+    __syncthreads();                                   // every warp of the block is done taking P1 units ...
+    if (threadIdx.x == 0) s_ctr[0] = 0u;               // ... so the P1 counter can be re-armed for the next iteration
+    grid.sync();
+    SB_DBG(2)
+    if (A.vbem && it > 0) logNorm = scratch[33];
+    const double bias = (it == 0) ? A.first_bias : 0.0;
+    SB_DBG(3)
+    W.dbg = (A.dbg && it == A.dbg_it) ? &A.dbg[(size_t)gwarp * 8 + 7] : nullptr;
+    run_phase_dyn<2, CH>(A, W, D, st, &s_ctr[1], u2a, u2b, bid, nblk, logNorm, bias, pa);
+    W.dbg = nullptr;
+    SB_DBG(4)
+    dyn_begin(A.cm, W, D, st, &s_ctr[0], u1a, u1b);   // next iteration's P1 (harmless if the loop ends)
+    p2_finish(A, scratch, pa, par);
+    SB_DBG(5)
+    __syncthreads();
+    if (threadIdx.x == 0) s_ctr[1] = 0u;
+    grid.sync();
+    SB_DBG(6)
+    const double mr = __longlong_as_double((long long)__ldcg(&A.maxrel[par]));
+    converged = !(mr > A.tol);
+    ++it;
+  }
+  if (bid == 0 && threadIdx.x == 0) {
+    A.out[0] = it;
+    A.out[1] = converged ? 1u : 0u;
+    A.out[2] = (it - 1) & 1u;
+  }
+  // drain the speculative prefetch before the block (and its shared memory) retires
+  while (st.kc < st.ki) {
+    const int slot = st.kc % RING;
+    mbar_wait(&W.bars[slot], (W.phase_bits >> slot) & 1u);
+    W.phase_bits ^= (1u << slot);
+    ++st.kc;
   }
 }
 
