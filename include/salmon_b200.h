@@ -170,6 +170,13 @@ sb_reads* sb_reads_open(const char* const* files1, const char* const* files2, ui
  * files of different length, a read longer than `stride`). */
 int64_t sb_reads_next(sb_reads* r, uint32_t max_pairs, uint32_t stride, uint8_t* left, uint8_t* right,
                       uint32_t* len_left, uint32_t* len_right);
+/* Lengths of the next records without delivering them: returns how many reads (pairs) the next sb_reads_next call can
+ * deliver, up to max_pairs (fewer only at the end of the input); *uniform_len = their common length when every read of
+ * both mates has the same one, else 0 (a caller that groups reads by length then takes the usual case straight into its
+ * [n, L] buffer with stride = L).  sb_reads_skip drops the next n reads unread (another shard's batch). */
+int64_t sb_reads_peek(sb_reads* r, uint32_t max_pairs, uint32_t* uniform_len);
+int64_t sb_reads_skip(sb_reads* r, uint32_t n);
+int sb_reads_paired(const sb_reads* r);   /* 1: two mate streams, 0: single-end */
 void sb_reads_close(sb_reads* r);
 
 /* The --eqclasses input (src/util/SalmonUtils.cpp:1024-1122 readEquivCounts): N, C, N names, C lines
@@ -349,6 +356,22 @@ int sb_map_online_state(sb_map_ctx* ctx, double* mass_out, double* hist_out, dou
 int sb_map_last_alignments(sb_map_ctx* ctx, uint32_t n, uint32_t* n_aln, uint32_t* tid, int32_t* score,
                            double* prob, int32_t* pos, int32_t* mate_pos, uint8_t* flags, int32_t* flen,
                            uint32_t* label, double* weight);
+
+/* The read stream as [n, L] batches of one read length each (what sb_map_batch takes): a reader thread parses, groups
+ * the reads by length into double-buffered (page-locked, when a device is present) matrices and hands full ones to
+ * `cb` on the calling thread, so parsing overlaps whatever the callback does (sb_quant_files: sb_map_batch).  A pair
+ * whose mates differ in length goes at the shorter length (the longer mate loses its 3' end); pairs shorter than
+ * min_len are counted and dropped.  The stream is cut into global batches of `batch` records; this call delivers the
+ * batches g with g % shard_count == shard_index (multi-GPU: one process per shard).  A batch of one length -- the usual
+ * case -- is translated straight into the bucket, without staging.  cb != 0 aborts and is returned.  Single-end
+ * readers deliver right == NULL. */
+typedef int (*sb_batch_cb)(void* user, const uint8_t* left, const uint8_t* right, uint32_t n_pairs, uint32_t read_len);
+typedef struct sb_bucket_stats {
+  uint64_t n_observed, n_delivered, n_too_short, n_trimmed_mates, n_batches;
+  uint32_t n_read_lengths, reserved;
+} sb_bucket_stats;
+int sb_reads_bucketed(sb_reads* rd, uint32_t min_len, uint32_t batch, uint32_t max_read_len, uint32_t threads,
+                      uint32_t shard_index, uint32_t shard_count, sb_batch_cb cb, void* user, sb_bucket_stats* stats);
 
 /* ---- the host driver of the path (C++; salmon_b200/csrc/pipeline.cu): `salmon quant -i idx -l IU -1 .. -2 .. -o out`
  * for the hot path.  Mirrors processReadLibrary / quantifyLibrary (src/quant/SalmonQuantify.cpp:2339-2730) and

@@ -152,6 +152,10 @@ SYMBOLS = {
     "sb_reads_open": (_P, [_P, _P, C.c_uint32, C.c_uint32]),
     "sb_reads_next": (C.c_int64, [_P, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
     "sb_reads_close": (None, [_P]),
+    "sb_reads_peek": (C.c_int64, [_P, C.c_uint32, _P]),
+    "sb_reads_skip": (C.c_int64, [_P, C.c_uint32]),
+    "sb_reads_paired": (C.c_int, [_P]),
+    "sb_reads_bucketed": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P]),
     "sb_eq_file_read": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(sb_eq_file))]),
     "sb_eq_file_free": (None, [C.POINTER(sb_eq_file)]),
     "sb_bootstrap_writer_open": (_P, [C.c_char_p]),
@@ -722,6 +726,38 @@ class ReadFiles:
                                    lr.ctypes.data if self.paired else None)
         _check(n, "sb_reads_next")
         return n, left[:n], (right[:n] if self.paired else None), ll[:n], (lr[:n] if self.paired else None)
+
+    def peek(self, max_pairs):
+        """-> (n available up to max_pairs, their common read length or 0)"""
+        L = C.c_uint32(0)
+        n = _check(self.lib.sb_reads_peek(self.h, max_pairs, C.byref(L)), "sb_reads_peek")
+        return n, L.value
+
+    def skip(self, n):
+        return _check(self.lib.sb_reads_skip(self.h, n), "sb_reads_skip")
+
+    def bucketed(self, fn, min_len=31, batch=65536, max_read_len=256, threads=4, shard_index=0, shard_count=1):
+        """sb_reads_bucketed: fn(left[n, L], right[n, L] | None, L) is called for every batch of one read length (the
+        arrays are views of the library's buffers: copy what you keep).  -> stats dict."""
+        CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32)
+
+        def cb(user, lp, rp, n, L):
+            try:
+                left = np.ctypeslib.as_array(C.cast(lp, C.POINTER(C.c_uint8)), shape=(n, L))
+                right = np.ctypeslib.as_array(C.cast(rp, C.POINTER(C.c_uint8)), shape=(n, L)) if rp else None
+                r = fn(left, right, L)
+                return int(r) if r else 0
+            except Exception:  # noqa: BLE001  (an exception must not unwind through the C frames)
+                import traceback
+                traceback.print_exc()
+                return -1
+        cbo = CB(cb)
+        st = (C.c_uint64 * 6)()
+        rc = self.lib.sb_reads_bucketed(self.h, min_len, batch, max_read_len, threads, shard_index, shard_count,
+                                        C.cast(cbo, C.c_void_p), None, st)
+        _check(rc, "sb_reads_bucketed")
+        return {"n_observed": st[0], "n_delivered": st[1], "n_too_short": st[2], "n_trimmed_mates": st[3], "n_batches": st[4],
+                "n_read_lengths": st[5] & 0xffffffff}
 
     def close(self):
         if self.h:

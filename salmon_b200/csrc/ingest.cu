@@ -78,8 +78,10 @@ struct Stream {
   std::string err;
   Prof prof;
   // consumer side
-  std::unique_ptr<RecBlock> cur;
-  uint32_t cur_pos = 0;
+  std::deque<std::unique_ptr<RecBlock>> held;   // blocks taken from the queue, not yet fully delivered
+  uint32_t front_pos = 0;                        // records of held.front() already delivered
+  uint64_t held_recs = 0;                        // records in `held` still to deliver
+  bool drained = false;                          // the splitter is done and its queue is empty
 };
 
 constexpr size_t CHUNK = 8u << 20;
@@ -279,6 +281,38 @@ inline void translate(const uint8_t* src, uint8_t* dst, uint32_t n) {
   for (uint32_t j = 0; j < n; ++j) dst[j] = LUT.t[src[j]];
 }
 
+// consumer side: make sure `want` undelivered records are held (or the stream has ended)
+bool hold(Stream& s, uint64_t want, std::string& err) {
+  while (s.held_recs < want && !s.drained) {
+    std::unique_lock<std::mutex> lk(s.mu);
+    s.cv_get.wait(lk, [&] { return !s.q.empty() || s.done; });
+    if (!s.err.empty()) { err = s.err; return false; }
+    if (s.q.empty()) { s.drained = true; break; }
+    s.held_recs += s.q.front()->n;
+    s.held.push_back(std::move(s.q.front()));
+    s.q.pop_front();
+    s.cv_put.notify_one();
+  }
+  return true;
+}
+// n records have been delivered (or skipped): drop them, hand fully consumed blocks back to the splitter
+void consume(Stream& s, uint64_t n) {
+  s.held_recs -= n;
+  while (n > 0) {
+    RecBlock* b = s.held.front().get();
+    const uint64_t take = std::min<uint64_t>(n, b->n - s.front_pos);
+    s.front_pos += (uint32_t)take;
+    n -= take;
+    if (s.front_pos == b->n) {
+      std::unique_ptr<RecBlock> done = std::move(s.held.front());
+      s.held.pop_front();
+      s.front_pos = 0;
+      std::lock_guard<std::mutex> lk(s.mu);
+      if (s.pool.size() < 2 * MAX_QUEUED) s.pool.push_back(std::move(done));
+    }
+  }
+}
+
 struct Task {
   const RecBlock* blk;
   uint32_t from, cnt;
@@ -337,28 +371,22 @@ extern "C" int64_t sb_reads_next(sb_reads* r, uint32_t max_pairs, uint32_t strid
   }
   if (r->failed) { sb::set_error("sb_reads_next: the reader is in a failed state"); return SB_ERR_INVALID; }
   std::vector<Task> tasks;
-  std::vector<std::pair<int, std::unique_ptr<RecBlock>>> retired;   // (stream, fully consumed block)
   uint64_t filled[2] = {0, 0};
   const double tw0 = wall();
   for (int m = 0; m < r->n_streams; ++m) {
     Stream& s = r->st[m];
-    while (filled[m] < max_pairs) {
-      if (!s.cur) {
-        std::unique_lock<std::mutex> lk(s.mu);
-        s.cv_get.wait(lk, [&] { return !s.q.empty() || s.done; });
-        if (!s.err.empty()) { r->failed = true; sb::set_error("%s", s.err.c_str()); return SB_ERR_INVALID; }
-        if (s.q.empty()) break;   // end of the stream
-        s.cur = std::move(s.q.front());
-        s.q.pop_front();
-        s.cur_pos = 0;
-        s.cv_put.notify_one();
-      }
-      const uint32_t take = (uint32_t)std::min<uint64_t>(s.cur->n - s.cur_pos, max_pairs - filled[m]);
+    std::string err;
+    if (!hold(s, max_pairs, err)) { r->failed = true; sb::set_error("%s", err.c_str()); return SB_ERR_INVALID; }
+    size_t bi = 0;
+    uint32_t pos = s.front_pos;
+    while (filled[m] < max_pairs && bi < s.held.size()) {
+      RecBlock* b = s.held[bi].get();
+      const uint32_t take = (uint32_t)std::min<uint64_t>(b->n - pos, max_pairs - filled[m]);
       for (uint32_t o = 0; o < take; o += 2048)
-        tasks.push_back(Task{s.cur.get(), s.cur_pos + o, std::min(2048u, take - o), filled[m] + o, m});
-      s.cur_pos += take;
+        tasks.push_back(Task{b, pos + o, std::min(2048u, take - o), filled[m] + o, m});
       filled[m] += take;
-      if (s.cur_pos == s.cur->n) retired.emplace_back(m, std::move(s.cur));
+      pos += take;
+      if (pos == b->n) { ++bi; pos = 0; }
     }
   }
   if (r->n_streams == 2 && filled[0] != filled[1]) {
@@ -388,11 +416,7 @@ extern "C" int64_t sb_reads_next(sb_reads* r, uint32_t max_pairs, uint32_t strid
     }
   }
   r->t_translate += wall() - tw1;
-  for (auto& b : retired) {   // hand the consumed blocks back to their splitter
-    Stream& s = r->st[b.first];
-    std::lock_guard<std::mutex> lk(s.mu);
-    if (s.pool.size() < 2 * MAX_QUEUED) s.pool.push_back(std::move(b.second));
-  }
+  for (int m = 0; m < r->n_streams; ++m) consume(r->st[m], filled[m]);
   r->max_len_seen = std::max(r->max_len_seen, maxlen);
   if (maxlen > stride) {
     r->failed = true;
@@ -401,6 +425,62 @@ extern "C" int64_t sb_reads_next(sb_reads* r, uint32_t max_pairs, uint32_t strid
   }
   r->n_delivered += filled[0];
   return (int64_t)filled[0];
+}
+
+// Look at the lengths of the next records without delivering them: returns how many records (pairs) the next call can
+// deliver, up to max_pairs (fewer only at the end of the input), and in *uniform_len their common length when every
+// read of both mates has the same one (else 0).  Lets a caller that groups reads by length take the usual case --
+// one length -- straight into its [n, L] buffer with sb_reads_next(..., stride = L, ...).
+extern "C" int64_t sb_reads_peek(sb_reads* r, uint32_t max_pairs, uint32_t* uniform_len) {
+  if (!r) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  if (r->failed) { sb::set_error("sb_reads_peek: the reader is in a failed state"); return SB_ERR_INVALID; }
+  uint64_t n = max_pairs;
+  for (int m = 0; m < r->n_streams; ++m) {
+    std::string err;
+    if (!hold(r->st[m], max_pairs, err)) { r->failed = true; sb::set_error("%s", err.c_str()); return SB_ERR_INVALID; }
+    n = std::min<uint64_t>(n, r->st[m].held_recs);
+  }
+  if (uniform_len) {
+    uint32_t L = 0;
+    bool uni = n > 0;
+    for (int m = 0; m < r->n_streams && uni; ++m) {
+      const Stream& s = r->st[m];
+      uint64_t left = n;
+      uint32_t pos = s.front_pos;
+      for (size_t bi = 0; bi < s.held.size() && left > 0 && uni; ++bi, pos = 0) {
+        const RecBlock* b = s.held[bi].get();
+        const uint64_t take = std::min<uint64_t>(left, b->n - pos);
+        if (m == 0 && bi == 0 && take > 0) L = b->seq[2 * (size_t)pos + 1];
+        for (uint64_t i = 0; i < take; ++i)
+          if (b->seq[2 * (size_t)(pos + i) + 1] != L) { uni = false; break; }
+        left -= take;
+      }
+    }
+    *uniform_len = uni ? L : 0;
+  }
+  return (int64_t)n;
+}
+
+extern "C" int sb_reads_paired(const sb_reads* r) { return (r && r->n_streams == 2) ? 1 : 0; }
+
+// Drop the next n records (pairs) unread (another shard's batch).  Returns the number dropped.
+extern "C" int64_t sb_reads_skip(sb_reads* r, uint32_t n) {
+  if (!r) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  if (r->failed) { sb::set_error("sb_reads_skip: the reader is in a failed state"); return SB_ERR_INVALID; }
+  uint64_t k = n;
+  for (int m = 0; m < r->n_streams; ++m) {
+    std::string err;
+    if (!hold(r->st[m], n, err)) { r->failed = true; sb::set_error("%s", err.c_str()); return SB_ERR_INVALID; }
+    k = std::min<uint64_t>(k, r->st[m].held_recs);
+  }
+  if (r->n_streams == 2 && k < n && r->st[0].held_recs != r->st[1].held_recs) {
+    r->failed = true;
+    sb::set_error("the mate files hold different numbers of records (after %llu pairs)", (unsigned long long)(r->n_delivered + k));
+    return SB_ERR_INVALID;
+  }
+  for (int m = 0; m < r->n_streams; ++m) consume(r->st[m], k);
+  r->n_delivered += k;
+  return (int64_t)k;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@
 // at the shorter length (documented deviation until the kernels take per-mate lengths).
 #include <errno.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
 #include <time.h>
@@ -40,19 +41,23 @@ struct HostBuf {   // pinned [cap, L] byte matrix pair
   uint8_t* left = nullptr;
   uint8_t* right = nullptr;
   uint32_t cap = 0, L = 0, n = 0;
-  bool busy = false;   // handed to the GPU side
+  bool busy = false;   // handed to the consumer side
+  bool pinned = false;
   int alloc(uint32_t cap_, uint32_t L_) {
     cap = cap_; L = L_; n = 0;
     const size_t bytes = (size_t)cap * L;
-    if (cudaMallocHost(&left, bytes) != cudaSuccess || cudaMallocHost(&right, bytes) != cudaSuccess) {
-      sb::set_error("cannot allocate %zu bytes of pinned host memory", 2 * bytes);
-      return SB_ERR_CUDA;
-    }
+    // page-locked when a CUDA device is there (the consumer copies these to the GPU), plain memory otherwise
+    if (cudaMallocHost(&left, bytes) == cudaSuccess && cudaMallocHost(&right, bytes) == cudaSuccess) { pinned = true; return SB_OK; }
+    cudaGetLastError();
+    if (left) { cudaFreeHost(left); left = nullptr; }
+    left = (uint8_t*)malloc(bytes ? bytes : 1);
+    right = (uint8_t*)malloc(bytes ? bytes : 1);
+    if (!left || !right) { sb::set_error("cannot allocate %zu bytes of host memory", 2 * bytes); return SB_ERR_NOMEM; }
     return SB_OK;
   }
   void release() {
-    if (left) cudaFreeHost(left);
-    if (right) cudaFreeHost(right);
+    if (pinned) { if (left) cudaFreeHost(left); if (right) cudaFreeHost(right); }
+    else { free(left); free(right); }
     left = right = nullptr;
   }
 };
@@ -103,6 +108,172 @@ bool make_dirs(const std::string& path) {
 
 }  // namespace
 
+extern "C" int sb_reads_bucketed(sb_reads* rd, uint32_t min_len, uint32_t batch, uint32_t max_read_len, uint32_t threads,
+                                 uint32_t shard_index, uint32_t shard_count, sb_batch_cb cb, void* user,
+                                 sb_bucket_stats* stats) {
+  if (!rd || !cb) { sb::set_error("sb_reads_bucketed: null argument"); return SB_ERR_INVALID; }
+  if (batch < 1) batch = 1;
+  if (max_read_len < 1) { sb::set_error("sb_reads_bucketed: max_read_len must be positive"); return SB_ERR_INVALID; }
+  if (shard_count == 0 || shard_index >= shard_count) { sb::set_error("bad shard index / count"); return SB_ERR_INVALID; }
+  if (threads == 0) threads = 1;
+  const bool paired = sb_reads_paired(rd) != 0;
+  Pipe P;
+  std::map<uint32_t, std::unique_ptr<Bucket>> buckets;
+  const uint32_t stride = max_read_len;
+  // ---- reader side ---------------------------------------------------------------------------------------------
+  auto submit = [&](HostBuf* b) {   // hand a filled buffer to the consumer side
+    std::unique_lock<std::mutex> lk(P.mu);
+    b->busy = true;
+    P.jobs.push_back(Job{b});
+    P.cv_job.notify_one();
+  };
+  auto reader = [&]() {
+    std::vector<uint8_t> sl, sr;          // staging for batches of mixed lengths (allocated on first use)
+    std::vector<uint32_t> ll(batch), lr(batch);
+    std::string err;
+    // the bucket of length L with room for at least one row; nullptr on error / abort
+    auto bucket_for = [&](uint32_t L) -> Bucket* {
+      std::unique_ptr<Bucket>& bp = buckets[L];
+      if (!bp) {
+        bp.reset(new Bucket());
+        // the first length seen gets full-size buffers; rarer lengths smaller ones
+        const uint32_t cap = buckets.size() == 1 ? batch : std::max<uint32_t>(batch / 8, std::min<uint32_t>(batch, 4096));
+        if (bp->buf[0].alloc(cap, L) != SB_OK || bp->buf[1].alloc(cap, L) != SB_OK) { err = sb_last_error(); return nullptr; }
+      }
+      HostBuf* b = &bp->buf[bp->fill];
+      if (!bp->checked) {   // first row after a flip: the consumer must have released this buffer
+        std::unique_lock<std::mutex> lk(P.mu);
+        P.cv_free.wait(lk, [&] { return !b->busy || P.abort; });
+        if (P.abort) { err = "aborted"; return nullptr; }
+        bp->checked = true;
+      }
+      return bp.get();
+    };
+    auto filled = [&](Bucket* bp, uint32_t rows) {
+      HostBuf* b = &bp->buf[bp->fill];
+      bp->cnt += rows;
+      if (bp->cnt == b->cap) { b->n = bp->cnt; submit(b); bp->fill ^= 1; bp->cnt = 0; bp->checked = false; }
+    };
+    // rows [i0, i1) of the staging buffers -> the bucket of length L (copied by an OpenMP team when it is a run)
+    auto put_rows = [&](uint32_t L, int64_t i0, int64_t i1) {
+      while (i0 < i1 && err.empty()) {
+        Bucket* bp = bucket_for(L);
+        if (!bp) return;
+        HostBuf* b = &bp->buf[bp->fill];
+        const int64_t take = std::min<int64_t>(i1 - i0, (int64_t)(b->cap - bp->cnt));
+        const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(threads, take / 4096));
+#pragma omp parallel for schedule(static) num_threads(nt)
+        for (int64_t q = 0; q < take; ++q) {
+          memcpy(b->left + (size_t)(bp->cnt + q) * L, sl.data() + (size_t)(i0 + q) * stride, L);
+          if (paired) memcpy(b->right + (size_t)(bp->cnt + q) * L, sr.data() + (size_t)(i0 + q) * stride, L);
+        }
+        i0 += take;
+        filled(bp, (uint32_t)take);
+      }
+    };
+    // the read stream is cut into global batches of `batch` records; batch g belongs to shard g % shard_count
+    for (uint64_t g = 0; err.empty(); ++g) {
+      { std::lock_guard<std::mutex> lk(P.mu); if (P.abort) break; }
+      uint32_t L0 = 0;
+      int64_t n = sb_reads_peek(rd, batch, &L0);
+      if (n < 0) { err = sb_last_error(); break; }
+      if (n == 0) break;
+      P.n_observed += (uint64_t)n;
+      if (g % shard_count != shard_index) {
+        if (sb_reads_skip(rd, (uint32_t)n) != n) { err = sb_last_error(); break; }
+        continue;
+      }
+      if (L0 >= min_len && L0 > 0 && L0 <= stride) {
+        // one length (the usual case): translated straight into the bucket buffer, no staging, no copy
+        int64_t left_n = n;
+        while (left_n > 0 && err.empty()) {
+          Bucket* bp = bucket_for(L0);
+          if (!bp) break;
+          HostBuf* b = &bp->buf[bp->fill];
+          const uint32_t take = (uint32_t)std::min<int64_t>(left_n, (int64_t)(b->cap - bp->cnt));
+          const int64_t got = sb_reads_next(rd, take, L0, b->left + (size_t)bp->cnt * L0, b->right + (size_t)bp->cnt * L0,
+                                            ll.data(), lr.data());
+          if (got != (int64_t)take) { err = got < 0 ? sb_last_error() : "short read from the parser"; break; }
+          left_n -= take;
+          filled(bp, take);
+        }
+        continue;
+      }
+      if (sl.empty()) { sl.resize((size_t)batch * stride); sr.resize((size_t)batch * stride); }
+      const int64_t got = sb_reads_next(rd, (uint32_t)n, stride, sl.data(), sr.data(), ll.data(), lr.data());
+      if (got != n) { err = got < 0 ? sb_last_error() : "short read from the parser"; break; }
+      // runs of equal length go in one piece
+      int64_t run0 = 0;
+      uint32_t runL = 0;
+      for (int64_t i = 0; i <= n && err.empty(); ++i) {
+        uint32_t L = 0;
+        if (i < n) {
+          L = paired ? std::min(ll[i], lr[i]) : ll[i];
+          if (paired && ll[i] != lr[i]) ++P.n_trimmed_mates;
+          if (L < min_len || L == 0) { ++P.n_too_short; L = 0; }   // cannot hold a k-mer: observed, never delivered
+        }
+        if (i == n || L != runL) {
+          if (runL != 0 && i > run0) put_rows(runL, run0, i);
+          run0 = i; runL = L;
+        }
+      }
+    }
+    if (err == "aborted") err.clear();
+    if (err.empty())
+      for (auto& kv : buckets) {   // ascending read length
+        Bucket& bk = *kv.second;
+        if (bk.cnt > 0) { HostBuf* b = &bk.buf[bk.fill]; b->n = bk.cnt; bk.cnt = 0; submit(b); }
+      }
+    std::lock_guard<std::mutex> lk(P.mu);
+    if (!err.empty()) P.err = err;
+    P.reader_done = true;
+    P.cv_job.notify_all();
+  };
+  std::thread rt(reader);
+  // ---- consumer side (the calling thread) ------------------------------------------------------------------------
+  int rc = SB_OK;
+  std::string cb_err;
+  uint64_t n_batches = 0, n_delivered = 0;
+  for (;;) {
+    Job j{nullptr};
+    {
+      std::unique_lock<std::mutex> lk(P.mu);
+      P.cv_job.wait(lk, [&] { return !P.jobs.empty() || P.reader_done; });
+      if (P.jobs.empty()) break;
+      j = P.jobs.front();
+      P.jobs.pop_front();
+    }
+    if (rc == SB_OK) {
+      rc = cb(user, j.b->left, paired ? j.b->right : nullptr, j.b->n, j.b->L);
+      if (rc != SB_OK) {
+        cb_err = sb_last_error();
+        std::lock_guard<std::mutex> lk(P.mu);
+        P.abort = true;
+      } else {
+        ++n_batches;
+        n_delivered += j.b->n;
+      }
+    }
+    {
+      std::lock_guard<std::mutex> lk(P.mu);
+      j.b->n = 0;
+      j.b->busy = false;
+    }
+    P.cv_free.notify_all();
+  }
+  rt.join();
+  const uint32_t n_lengths = (uint32_t)buckets.size();
+  for (auto& kv : buckets) { kv.second->buf[0].release(); kv.second->buf[1].release(); }
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->n_observed = P.n_observed; stats->n_delivered = n_delivered; stats->n_too_short = P.n_too_short;
+    stats->n_trimmed_mates = P.n_trimmed_mates; stats->n_batches = n_batches; stats->n_read_lengths = n_lengths;
+  }
+  if (rc != SB_OK) { sb::set_error("%s", cb_err.c_str()); return rc > 0 ? SB_ERR_STATE : rc; }
+  if (!P.err.empty()) { sb::set_error("%s", P.err.c_str()); return SB_ERR_INVALID; }
+  return SB_OK;
+}
+
 extern "C" void sb_quant_default_opts(sb_quant_opts* o) {
   if (!o) return;
   memset(o, 0, sizeof(*o));
@@ -142,124 +313,19 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
   sb_reads* rd = sb_reads_open(mates1, mates2, n_files, o.threads);
   if (!rd) { sb_map_destroy(ctx); return SB_ERR_INVALID; }
 
-  Pipe P;
-  std::map<uint32_t, std::unique_ptr<Bucket>> buckets;
-  const uint32_t stride = o.max_read_len;
-  // ---- reader side ---------------------------------------------------------------------------------------------
-  auto submit = [&](HostBuf* b) {   // hand a filled buffer to the GPU side
-    std::unique_lock<std::mutex> lk(P.mu);
-    b->busy = true;
-    P.jobs.push_back(Job{b});
-    P.cv_job.notify_one();
+  struct MapUser { sb_map_ctx* ctx; float device_ms; } mu{ctx, 0.0f};
+  sb_batch_cb map_cb = [](void* user, const uint8_t* l, const uint8_t* r, uint32_t n, uint32_t L) -> int {
+    MapUser* u = (MapUser*)user;
+    sb_map_batch_stats st;
+    const int rc = sb_map_batch(u->ctx, l, r, n, L, &st);
+    if (rc == SB_OK) u->device_ms += st.device_ms;
+    return rc;
   };
-  auto reader = [&]() {
-    std::vector<uint8_t> sl((size_t)o.batch * stride), sr((size_t)o.batch * stride);
-    std::vector<uint32_t> ll(o.batch), lr(o.batch);
-    std::string err;
-    uint64_t bi = 0;
-    for (;;) {
-      { std::lock_guard<std::mutex> lk(P.mu); if (P.abort) break; }
-      const int64_t n = sb_reads_next(rd, o.batch, stride, sl.data(), sr.data(), ll.data(), lr.data());
-      if (n < 0) { err = sb_last_error(); break; }
-      if (n == 0) break;
-      P.n_observed += (uint64_t)n;
-      if (bi++ % o.shard_count != o.shard_index) continue;
-      // rows [i0, i1) of the staging buffers -> the bucket of length L (copied by an OpenMP team when it is a run)
-      auto put_rows = [&](uint32_t L, int64_t i0, int64_t i1) {
-        while (i0 < i1 && err.empty()) {
-          std::unique_ptr<Bucket>& bp = buckets[L];
-          if (!bp) {
-            bp.reset(new Bucket());
-            // the first length seen gets full-size buffers; rarer lengths smaller ones
-            const uint32_t cap = buckets.size() == 1 ? o.batch : std::max<uint32_t>(o.batch / 8, 4096);
-            if (bp->buf[0].alloc(cap, L) != SB_OK || bp->buf[1].alloc(cap, L) != SB_OK) { err = sb_last_error(); return; }
-          }
-          HostBuf* b = &bp->buf[bp->fill];
-          if (!bp->checked) {   // first row after a flip: the GPU side must have released this buffer
-            std::unique_lock<std::mutex> lk(P.mu);
-            P.cv_free.wait(lk, [&] { return !b->busy || P.abort; });
-            if (P.abort) { err = "aborted"; return; }
-            bp->checked = true;
-          }
-          const int64_t take = std::min<int64_t>(i1 - i0, (int64_t)(b->cap - bp->cnt));
-          const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(o.threads, take / 4096));
-#pragma omp parallel for schedule(static) num_threads(nt)
-          for (int64_t q = 0; q < take; ++q) {
-            memcpy(b->left + (size_t)(bp->cnt + q) * L, sl.data() + (size_t)(i0 + q) * stride, L);
-            memcpy(b->right + (size_t)(bp->cnt + q) * L, sr.data() + (size_t)(i0 + q) * stride, L);
-          }
-          bp->cnt += (uint32_t)take;
-          i0 += take;
-          if (bp->cnt == b->cap) { b->n = bp->cnt; submit(b); bp->fill ^= 1; bp->cnt = 0; bp->checked = false; }
-        }
-      };
-      // runs of equal length go in one piece (the common case: the whole batch)
-      int64_t run0 = 0;
-      uint32_t runL = 0;
-      for (int64_t i = 0; i <= n && err.empty(); ++i) {
-        uint32_t L = 0;
-        if (i < n) {
-          L = std::min(ll[i], lr[i]);
-          if (ll[i] != lr[i]) ++P.n_trimmed_mates;
-          if (L < mp.k) { ++P.n_too_short; L = 0; }   // cannot hold a k-mer: observed, never assigned
-        }
-        if (i == n || L != runL) {
-          if (runL != 0 && i > run0) put_rows(runL, run0, i);
-          run0 = i; runL = L;
-        }
-      }
-      if (err == "aborted") { err.clear(); break; }
-      if (!err.empty()) break;
-    }
-    if (err.empty())
-      for (auto& kv : buckets) {
-        Bucket& bk = *kv.second;
-        if (bk.cnt > 0) { HostBuf* b = &bk.buf[bk.fill]; b->n = bk.cnt; bk.cnt = 0; submit(b); }
-      }
-    std::lock_guard<std::mutex> lk(P.mu);
-    if (!err.empty()) P.err = err;
-    P.reader_done = true;
-    P.cv_job.notify_all();
-  };
-  std::thread rt(reader);
-  // ---- GPU side --------------------------------------------------------------------------------------------------
-  int rc = SB_OK;
-  std::string gpu_err;
-  uint64_t n_batches = 0;
-  float device_ms = 0;
-  for (;;) {
-    Job j{nullptr};
-    {
-      std::unique_lock<std::mutex> lk(P.mu);
-      P.cv_job.wait(lk, [&] { return !P.jobs.empty() || P.reader_done; });
-      if (P.jobs.empty()) break;
-      j = P.jobs.front();
-      P.jobs.pop_front();
-    }
-    if (rc == SB_OK) {
-      sb_map_batch_stats st;
-      rc = sb_map_batch(ctx, j.b->left, j.b->right, j.b->n, j.b->L, &st);
-      if (rc != SB_OK) {
-        gpu_err = sb_last_error();
-        std::lock_guard<std::mutex> lk(P.mu);
-        P.abort = true;
-      } else {
-        ++n_batches;
-        device_ms += st.device_ms;
-      }
-    }
-    {
-      std::lock_guard<std::mutex> lk(P.mu);
-      j.b->n = 0;
-      j.b->busy = false;
-    }
-    P.cv_free.notify_all();
-  }
-  rt.join();
+  sb_bucket_stats bs;
+  int rc = sb_reads_bucketed(rd, mp.k, o.batch, o.max_read_len, o.threads, o.shard_index, o.shard_count, map_cb, &mu, &bs);
   sb_reads_close(rd);
-  for (auto& kv : buckets) { kv.second->buf[0].release(); kv.second->buf[1].release(); }
-  if (rc == SB_OK && !P.err.empty()) { rc = SB_ERR_INVALID; gpu_err = P.err; }
-  if (rc != SB_OK) { sb_map_destroy(ctx); sb::set_error("%s", gpu_err.c_str()); return rc; }
+  if (rc != SB_OK) { sb_map_destroy(ctx); return rc; }
+  const float device_ms = mu.device_ms;
   const double t_map = now_s();
 
   // ---- classes -> EM -> outputs --------------------------------------------------------------------------------
@@ -325,9 +391,9 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
   if (alpha_out) memcpy(alpha_out, alpha.data(), (size_t)M * 8);
   if (sum) {
     memset(sum, 0, sizeof(*sum));
-    sum->n_observed = P.n_observed; sum->n_mapped = res.n_mapped; sum->n_too_short = P.n_too_short;
-    sum->n_trimmed_mates = P.n_trimmed_mates;
-    sum->n_classes = res.n_classes; sum->n_batches = n_batches; sum->n_read_lengths = (uint32_t)buckets.size();
+    sum->n_observed = bs.n_observed; sum->n_mapped = res.n_mapped; sum->n_too_short = bs.n_too_short;
+    sum->n_trimmed_mates = bs.n_trimmed_mates;
+    sum->n_classes = res.n_classes; sum->n_batches = bs.n_batches; sum->n_read_lengths = bs.n_read_lengths;
     sum->em_iters = est.iters; sum->em_converged = est.converged;
     sum->map_seconds = t_map - t0; sum->em_seconds = t_em - t_map; sum->total_seconds = now_s() - t0;
     sum->map_device_ms = device_ms;

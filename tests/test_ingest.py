@@ -317,3 +317,106 @@ def test_cli_index_and_no_gpu_failure(tmp_path):
         r = subprocess.run([exe, "quant", "-i", str(idir), "-l", "IU", "-1", str(f1), "-2", str(f2), "-o", str(tmp_path / "o")],
                            capture_output=True, text=True)
         assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+def test_peek_and_skip(tmp_path):
+    rng = np.random.default_rng(14)
+    n = 3000
+    seqs = [rand_seq(rng, 76) for _ in range(n)]
+    lens2 = np.full(n, 76)
+    lens2[1500] = 50                                   # one shorter read in the second mate file
+    f1, f2 = tmp_path / "p_1.fq", tmp_path / "p_2.fq"
+    write_text(f1, fastq_text(seqs, 1), False)
+    write_text(f2, fastq_text([s[:lens2[i]] for i, s in enumerate(seqs)], 2), True)
+    with _capi.ReadFiles(str(f1), str(f2), n_threads=2) as rf:
+        assert rf.peek(1000) == (1000, 76)             # uniform
+        assert rf.peek(1000) == (1000, 76)             # peeking delivers nothing
+        k, left, right, ll, lr = rf.next_batch(400, 76)
+        assert k == 400 and np.array_equal(left[399], encode(seqs[399]))
+        assert rf.skip(600) == 600
+        assert rf.peek(1000) == (1000, 0)              # records 1000..1999 hold the 50-base read
+        k, left, right, ll, lr = rf.next_batch(1000, 76)
+        assert k == 1000 and lr[500] == 50 and np.array_equal(left[0], encode(seqs[1000]))
+        assert np.array_equal(right[500, :50], encode(seqs[1500][:50])) and np.all(right[500, 50:] == 4)
+        assert rf.peek(5000) == (1000, 76)             # only 1000 left
+        assert rf.skip(5000) == 1000
+        assert rf.peek(10) == (0, 0) and rf.next_batch(10, 76)[0] == 0
+
+
+def _pairs_with_lengths(rng, n, uniform):
+    r1, r2 = [], []
+    for i in range(n):
+        if uniform:
+            a = b = 80
+        else:
+            a = int(rng.integers(10, 101)); b = a if rng.random() < 0.6 else int(rng.integers(10, 101))
+        r1.append(rand_seq(rng, a, "ACGTN" if i % 11 == 0 else "ACGT")); r2.append(rand_seq(rng, b))
+    return r1, r2
+
+
+@pytest.mark.parametrize("uniform", [True, False])
+def test_bucketed_batches(tmp_path, uniform):
+    """sb_reads_bucketed (the reader + length grouping of sb_quant_files, with a callback in place of sb_map_batch):
+    every pair is delivered exactly once, in a batch of its own length, at the shorter mate's length."""
+    rng = np.random.default_rng(21 + uniform)
+    n, batch, k = 7000, 1024, 31
+    r1, r2 = _pairs_with_lengths(rng, n, uniform)
+    f1, f2 = tmp_path / "b_1.fq", tmp_path / "b_2.fq.gz"
+    write_text(f1, fastq_text(r1, 1), False); write_text(f2, fastq_text(r2, 2), True)
+    got, sizes = [], []
+
+    def take(left, right, L):
+        assert left.shape == right.shape and left.shape[1] == L and 0 < left.shape[0] <= batch
+        sizes.append((L, left.shape[0]))
+        got.extend((L, left[i].tobytes(), right[i].tobytes()) for i in range(left.shape[0]))
+    with _capi.ReadFiles(str(f1), str(f2), n_threads=3) as rf:
+        st = rf.bucketed(take, min_len=k, batch=batch, max_read_len=100, threads=3)
+    want = []
+    short = trimmed = 0
+    for a, b in zip(r1, r2):
+        L = min(len(a), len(b))
+        trimmed += len(a) != len(b)
+        if L < k:
+            short += 1
+            continue
+        want.append((L, encode(a[:L]).tobytes(), encode(b[:L]).tobytes()))
+    assert st["n_observed"] == n and st["n_delivered"] == len(want) == len(got) and st["n_too_short"] == short
+    assert st["n_batches"] == len(sizes) and st["n_read_lengths"] == len({L for L, _ in sizes})
+    if uniform:
+        assert got == want and sizes == [(80, 1024)] * 6 + [(80, n - 6 * 1024)]     # order kept, no regrouping
+        assert st["n_trimmed_mates"] == 0
+    else:
+        assert sorted(got) == sorted(want) and st["n_trimmed_mates"] == trimmed
+        # inside one length the stream order is kept
+        for L in {L for L, _ in sizes}:
+            assert [g for g in got if g[0] == L] == [w for w in want if w[0] == L]
+
+
+def test_bucketed_shards_and_abort(tmp_path):
+    rng = np.random.default_rng(23)
+    n, batch = 5000, 512
+    r1, r2 = _pairs_with_lengths(rng, n, True)
+    f1, f2 = tmp_path / "s_1.fq", tmp_path / "s_2.fq"
+    write_text(f1, fastq_text(r1, 1), False); write_text(f2, fastq_text(r2, 2), False)
+    all_rows = []
+    for shard in range(3):
+        rows = []
+        with _capi.ReadFiles(str(f1), str(f2), n_threads=2) as rf:
+            st = rf.bucketed(lambda l, r, L: rows.extend(l[i].tobytes() for i in range(l.shape[0])), batch=batch,
+                             max_read_len=80, shard_index=shard, shard_count=3)
+        # global batches g = shard, shard + 3, ... of 512 records each
+        want = [encode(r1[i]).tobytes() for i in range(n) if (i // batch) % 3 == shard]
+        assert rows == want and st["n_observed"] == n and st["n_delivered"] == len(want)
+        all_rows += rows
+    assert sorted(all_rows) == sorted(encode(s).tobytes() for s in r1)
+    # a failing callback stops the stream and is reported
+    calls = []
+    with _capi.ReadFiles(str(f1), str(f2), n_threads=2) as rf:
+        with pytest.raises(_capi.SalmonB200Error):
+            rf.bucketed(lambda l, r, L: calls.append(1) or (-7 if len(calls) == 3 else 0), batch=batch, max_read_len=80)
+    assert len(calls) == 3
+    # single-end: right is None
+    with _capi.ReadFiles(str(f1), None, n_threads=2) as rf:
+        seen = []
+        st = rf.bucketed(lambda l, r, L: seen.append((r is None, l.shape[0])), batch=2048, max_read_len=80)
+    assert all(x for x, _ in seen) and sum(c for _, c in seen) == n
