@@ -420,3 +420,48 @@ def test_bucketed_shards_and_abort(tmp_path):
         seen = []
         st = rf.bucketed(lambda l, r, L: seen.append((r is None, l.shape[0])), batch=2048, max_read_len=80)
     assert all(x for x, _ in seen) and sum(c for _, c in seen) == n
+
+
+def test_parallel_splitter_adversarial_qualities(tmp_path, monkeypatch):
+    """Plain files are memory-mapped and cut at record starts found from arbitrary offsets: quality lines that begin
+    with '@' or '+' (legal Phred+33 characters) must not be taken for headers; same records as the serial splitter."""
+    monkeypatch.setenv("SB_READS_SCANNERS", "4")
+    rng = np.random.default_rng(31)
+    n = 90000
+    L = rng.integers(60, 121, size=n)
+    qual_alphabet = np.frombuffer(b"@+IIIIFF#;", dtype=np.uint8)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    recs, seqs = [], []
+    for i in range(n):
+        sq = lut[rng.integers(0, 4, size=L[i])].tobytes()
+        q = qual_alphabet[rng.integers(0, len(qual_alphabet), size=L[i])].tobytes()
+        if i % 3 == 0:
+            q = b"@" + q[1:]
+        elif i % 3 == 1:
+            q = b"+" + q[1:]
+        seqs.append(sq)
+        recs.append(b"@read%d\n%s\n+\n%s\n" % (i, sq, q))
+    f1, f2 = tmp_path / "q_1.fq", tmp_path / "q_2.fq"
+    f1.write_bytes(b"".join(recs)); f2.write_bytes(b"".join(recs[::-1]))
+    assert os.path.getsize(f1) > (16 << 20)
+    got1, got2 = [], []
+    with _capi.ReadFiles(str(f1), str(f2), n_threads=4) as rf:
+        while True:
+            k, left, right, ll, lr = rf.next_batch(20000, 120)
+            if k == 0:
+                break
+            got1 += [left[i, :ll[i]].tobytes() for i in range(k)]
+            got2 += [right[i, :lr[i]].tobytes() for i in range(k)]
+    want = [encode(s.decode()).tobytes() for s in seqs]
+    assert got1 == want and got2 == want[::-1]
+    # single-line FASTA reads through the same path
+    fa = tmp_path / "q.fa"
+    fa.write_bytes(b"".join(b">r%d\n%s\n" % (i, s) for i, s in enumerate(seqs)))
+    got = []
+    with _capi.ReadFiles(str(fa), None, n_threads=4) as rf:
+        while True:
+            k, left, right, ll, lr = rf.next_batch(30000, 120)
+            if k == 0:
+                break
+            got += [left[i, :ll[i]].tobytes() for i in range(k)]
+    assert got == want
