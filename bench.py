@@ -176,6 +176,15 @@ def stage_a_algorithmic_bytes(n_frags, read_len, c, band=15):
             + 32 * c["kept"] + 4 * c["label_entries"])
 
 
+def stage_a_traffic(frags_per_launch):
+    """DRAM bytes per seed-kernel launch from the committed ncu --set full capture (per fragment x fragments per launch)"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))["stage_a"]
+        return t["dram_bytes_per_fragment"] * frags_per_launch
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def stage_a_workload(rank, small=False):
     from salmon_b200.synth import synth_txome, synth_reads_fast, flatten_txome
     g = SA["n_genes"] // (20 if small else 1)
@@ -356,7 +365,7 @@ def bench_stage_a(args, rank, world, local, dist, W, peak, peak_src, ncores):
                      "frac": seed_achieved / peak, "peak_source": peak_src, "avg_launch_ms": seed_launch_ms,
                      "fragments_per_launch": frags_per_launch,
                      "algorithmic_bytes_per_launch": seed_bytes,
-                     "traffic": None,
+                     "traffic": stage_a_traffic(frags_per_launch),
                      "whole_stage_algorithmic_gbs": stage_a_algorithmic_bytes(n, L, c) / res_t / 1e9,
                      "note": "the kernel is latency/issue-bound (dependent hash-probe -> posting loads, warp-level sort "
                              "and scans), not bandwidth-bound: see DESIGN.md"},
