@@ -97,3 +97,12 @@ def test_sample_data_through_the_command_line(oracle, tmp_path):
     want = sorted((tuple(e["tids"][eo[c]:eo[c + 1]].tolist()), int(e["counts"][c])) for c in range(len(e["counts"])))
     assert sum(c for _, c in got) == sum(c for _, c in want) == int((m["n_aln"] > 0).sum())
     assert got == want
+
+
+def test_product_host_logic_matches_oracle_on_sample_reads(oracle):
+    """map_core.h (the per-read logic the CUDA kernels share, compiled for the host) against the oracle on the reference's
+    simulated 2x50 bp reads: alignments, scores, probabilities, labels and weights bit-exact."""
+    from test_map_host import run_both
+    names, txps, left, right, tid, flen = load_fixture()
+    run_both(oracle, txps, left[:4000], right[:4000])
+    run_both(oracle, txps, left[4000:6000], right[4000:6000], frag_counter=6_000_000)
