@@ -295,3 +295,32 @@ def test_read_length_below_context_capacity(oracle, L, cap_len):
     m = np.arange(p.max_read_occ)[None, :] < got2["n_aln"][:, None]
     assert np.array_equal(got2["tid"][m], ref2["tid"][m]) and np.array_equal(got2["score"][m], ref2["score"][m])
     ctx.close()
+
+
+def test_decoy_aware_batch_bit_exact(oracle):
+    """BASELINE configs[3] semantics on the GPU: decoys last in the index, first_decoy set -- no decoy alignment is
+    reported, fragments that map best to a decoy are dropped, everything bit-exact against the oracle."""
+    rng = np.random.default_rng(17)
+    txps, _ = synth_txome(seed=8, n_genes=40)
+    M = len(txps)
+    decoys = []
+    for g in range(6):
+        parts = [rng.integers(0, 4, size=300, dtype=np.uint8)]
+        for t in rng.choice(M, size=5, replace=False):
+            parts += [txps[t], rng.integers(0, 4, size=200, dtype=np.uint8)]
+        decoys.append(np.concatenate(parts))
+    allseq = txps + decoys
+    l1, r1, _ = synth_reads(txps, seed=18, n=2000)
+    l2, r2, _ = synth_reads(decoys, seed=19, n=1000, expressed_frac=1.0)
+    left, right = np.concatenate([l1, l2]), np.concatenate([r1, r2])
+    p = map_default_params(first_decoy=M)
+    ctx = MapContext(Index(allseq), p, batch_cap=4096, max_read_len=100)
+    st = ctx.map_batch(left, right)
+    got = ctx.last_alignments()
+    ref = oracle.map_reads(oracle.MapIndex(allseq), oracle.map_params(first_decoy=M), left, right, 0)
+    compare(got, ref, p.max_read_occ)
+    assert st.mapped == ref["counters"]["mapped"]
+    sel = np.arange(p.max_read_occ)[None, :] < got["n_aln"][:, None]
+    assert (got["tid"][sel] < M).all() and (got["n_aln"][2000:] == 0).sum() > 100
+    check_classes(ctx.finish(), oracle.eq_aggregate(ref, p.max_read_occ, True), exact_weights=True)
+    ctx.close()

@@ -89,3 +89,35 @@ def test_detmath_close_to_libm():
         for x in np.exp(rng.uniform(-700, 700, size=20000)):
             assert abs(lib.l(x) - math.log(x)) <= 2.3e-16 * max(abs(math.log(x)), 1e-300) + 1e-320
         assert lib.e(0.0) == 1.0 and lib.l(1.0) == 0.0 and lib.e(-lib.l(2.0)) == 0.5
+
+
+def test_decoys_host_logic_matches_oracle(oracle):
+    """Decoy-aware mapping (BASELINE configs[3]; updateRefMappings / filterAndCollectAlignments with firstDecoyIndex,
+    SalmonMappingUtils.hpp:225-405): decoy sequences that carry the transcripts' exons plus flanking sequence come last;
+    no alignment to a decoy is ever reported, and a fragment that maps better to a decoy than to any transcript is
+    dropped.  Host logic bit-exact against the oracle."""
+    rng = np.random.default_rng(17)
+    txps, _ = synth_txome(seed=8, n_genes=40)
+    M = len(txps)
+    # "genome" decoys: a few transcripts embedded in random flanks, and intron-like pieces that only exist in the decoy
+    decoys = []
+    for g in range(6):
+        parts = [rng.integers(0, 4, size=300, dtype=np.uint8)]
+        for t in rng.choice(M, size=5, replace=False):
+            parts += [txps[t], rng.integers(0, 4, size=200, dtype=np.uint8)]
+        decoys.append(np.concatenate(parts))
+    allseq = txps + decoys
+    l1, r1, _ = synth_reads(txps, seed=18, n=2000)
+    l2, r2, _ = synth_reads(decoys, seed=19, n=1000, expressed_frac=1.0)      # fragments that come from the decoys
+    left, right = np.concatenate([l1, l2]), np.concatenate([r1, r2])
+    got, ref = run_both(oracle, allseq, left, right, first_decoy=M)
+    na = got["n_aln"]
+    sel = np.arange(got["tid"].shape[1])[None, :] < na[:, None]
+    assert (got["tid"][sel] < M).all()                                   # decoys are never reported
+    # decoy fragments: those lying in decoy-only sequence are dropped, those inside an embedded transcript map to it
+    assert (na[2000:] == 0).sum() > 100 and (na[2000:] > 0).sum() > 100
+    assert (na[:2000] > 0).mean() > 0.9
+    # and without the decoy boundary the same reads do get decoy alignments
+    got2, _ = run_both(oracle, allseq, left, right)
+    assert (got2["tid"][np.arange(got2["tid"].shape[1])[None, :] < got2["n_aln"][:, None]] >= M).any()
+    assert got2["counters"]["mapped"] > got["counters"]["mapped"]
