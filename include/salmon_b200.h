@@ -390,7 +390,8 @@ typedef struct sb_quant_opts {
   uint32_t num_gibbs;        /* --numGibbsSamples */
   uint32_t thinning;         /* --thinningFactor (16) */
   int32_t no_gamma_draw;     /* --noGammaDraw */
-  uint32_t shard_index, shard_count;   /* this process maps the reader batches b with b % shard_count == shard_index */
+  uint32_t shard_index, shard_count;   /* must be 0 / 1: a shard alone is not a quantification (multi-GPU: sb_reads_bucketed
+                                          + the host layer's end-of-mapping reduction, salmon_b200/quant.py::quant_files) */
   uint64_t seed;
 } sb_quant_opts;
 typedef struct sb_quant_summary {

@@ -741,20 +741,23 @@ class ReadFiles:
         arrays are views of the library's buffers: copy what you keep).  -> stats dict."""
         CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32)
 
+        raised = []
+
         def cb(user, lp, rp, n, L):
             try:
                 left = np.ctypeslib.as_array(C.cast(lp, C.POINTER(C.c_uint8)), shape=(n, L))
                 right = np.ctypeslib.as_array(C.cast(rp, C.POINTER(C.c_uint8)), shape=(n, L)) if rp else None
                 r = fn(left, right, L)
                 return int(r) if r else 0
-            except Exception:  # noqa: BLE001  (an exception must not unwind through the C frames)
-                import traceback
-                traceback.print_exc()
+            except Exception as e:  # noqa: BLE001  (an exception must not unwind through the C frames)
+                raised.append(e)
                 return -1
         cbo = CB(cb)
         st = (C.c_uint64 * 6)()
         rc = self.lib.sb_reads_bucketed(self.h, min_len, batch, max_read_len, threads, shard_index, shard_count,
                                         C.cast(cbo, C.c_void_p), None, st)
+        if raised:
+            raise raised[0]              # the callback's own exception, after the reader has wound down
         _check(rc, "sb_reads_bucketed")
         return {"n_observed": st[0], "n_delivered": st[1], "n_too_short": st[2], "n_trimmed_mates": st[3], "n_batches": st[4],
                 "n_read_lengths": st[5] & 0xffffffff}

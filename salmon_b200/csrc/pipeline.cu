@@ -295,7 +295,12 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
   if (o_in) o = *o_in; else sb_quant_default_opts(&o);
   if (o.batch < 1024) o.batch = 1024;
   if (o.max_read_len < 32 || o.max_read_len > 256) { sb::set_error("max_read_len must be in 32..256"); return SB_ERR_INVALID; }
-  if (o.shard_count == 0 || o.shard_index >= o.shard_count) { sb::set_error("bad shard index / count"); return SB_ERR_INVALID; }
+  if (o.shard_count != 1 || o.shard_index != 0) {
+    // a shard's classes alone are not a quantification: multi-GPU runs reduce the end-of-mapping statistics over the
+    // ranks before the EM (salmon_b200.quant.quant_files: sb_reads_bucketed + sb_map_partial_get / sb_map_project_global)
+    sb::set_error("sb_quant_files quantifies one whole library on one GPU; shard the reads with sb_reads_bucketed and the multi-GPU host layer");
+    return SB_ERR_INVALID;
+  }
   if (o.num_bootstraps && o.num_gibbs) { sb::set_error("choose bootstraps or Gibbs samples, not both"); return SB_ERR_INVALID; }
   sb_map_params mp;
   if (mp_in) mp = *mp_in; else sb_map_default_params(&mp);

@@ -66,56 +66,6 @@ def quant_reads(index, left, right, map_params=None, em_params=None, device=0, b
                 projected_counts=inputs["projected_counts"], unique_counts=inputs["unique_counts"])
 
 
-class _LengthBuckets:
-    """sb_map_batch takes one read length per call; reads are therefore grouped by length on the host.  A pair whose
-    mates differ in length is mapped at the shorter length (the longer mate loses its 3' end) -- documented deviation,
-    the kernels take per-mate lengths in a later round.  Uniform-length input (the common case) passes straight
-    through without a copy."""
-
-    def __init__(self, ctx, batch, k):
-        self.ctx, self.batch, self.k = ctx, batch, k
-        self.pending = {}        # L -> [list of left blocks, list of right blocks, count]
-        self.too_short = 0
-        self.n_in = 0
-
-    def _flush(self, L, force=False):
-        ent = self.pending.get(L)
-        if not ent:
-            return
-        while ent[2] >= self.batch or (force and ent[2] > 0):
-            left = np.concatenate(ent[0]) if len(ent[0]) > 1 else ent[0][0]
-            right = np.concatenate(ent[1]) if len(ent[1]) > 1 else ent[1][0]
-            take = min(self.batch, left.shape[0])
-            self.ctx.map_batch(left[:take], right[:take])
-            ent[0], ent[1], ent[2] = ([left[take:]] if take < left.shape[0] else []), \
-                                     ([right[take:]] if take < right.shape[0] else []), left.shape[0] - take
-            if ent[2] == 0:
-                break
-
-    def add(self, left, right, ll, lr):
-        n = left.shape[0]
-        self.n_in += n
-        L = np.minimum(ll, lr)
-        if n and L.min() == L.max() and int(L[0]) == left.shape[1] and int(L[0]) >= self.k and not self.pending:
-            self.ctx.map_batch(left, right)      # uniform, full-width: no regrouping
-            return
-        for Lv in np.unique(L):
-            sel = np.nonzero(L == Lv)[0]
-            Lv = int(Lv)
-            if Lv < self.k:
-                self.too_short += sel.shape[0]   # cannot hold a k-mer: unmappable (counted as observed, not assigned)
-                continue
-            ent = self.pending.setdefault(Lv, [[], [], 0])
-            ent[0].append(np.ascontiguousarray(left[sel, :Lv]))
-            ent[1].append(np.ascontiguousarray(right[sel, :Lv]))
-            ent[2] += sel.shape[0]
-            self._flush(Lv)
-
-    def finish(self):
-        for L in sorted(self.pending):
-            self._flush(L, force=True)
-
-
 def _quantify(index, ctx, ep, device, dist, names, out_dir, dump_eq, dump_eq_weights, num_bootstraps=0, seed=0,
               n_observed=None):
     """Everything after mapping: finish() -> (multi-GPU reduction) -> EM -> outputs.  Shared by quant_reads-style
@@ -169,9 +119,11 @@ def _quantify(index, ctx, ep, device, dist, names, out_dir, dump_eq, dump_eq_wei
 def quant_files(index, mates1, mates2, out_dir=None, map_params=None, em_params=None, device=0, batch=262_144,
                 max_read_len=256, threads=8, dist=None, dump_eq=False, dump_eq_weights=False, num_bootstraps=0, seed=0):
     """`salmon quant -i index -l IU -1 mates1 -2 mates2 -o out_dir` for the hot path: FASTQ/FASTA(.gz) files ->
-    sb_reads_* -> sb_map_batch -> ... -> quant.sf.  index: an _capi.Index or the path of a saved one.  With
-    torch.distributed initialised every rank takes the batches b with b % world == rank (round-robin sharding of
-    the read stream)."""
+    sb_reads_bucketed -> sb_map_batch -> ... -> quant.sf.  index: an _capi.Index or the path of a saved one.  With
+    torch.distributed initialised every rank takes the global batches g with g % world == rank (round-robin sharding
+    of the read stream), the end-of-mapping statistics are reduced once and the EM all-reduces alpha.
+    A pair whose mates differ in length is mapped at the shorter length (documented deviation until the kernels take
+    per-mate lengths)."""
     if isinstance(index, (str, bytes, os.PathLike)):
         index = _capi.Index.load(index)
     mp = map_params or map_default_params()
@@ -182,33 +134,15 @@ def quant_files(index, mates1, mates2, out_dir=None, map_params=None, em_params=
     world = dist.get_world_size() if (dist is not None and dist.is_initialized()) else 1
     rank = dist.get_rank() if world > 1 else 0
     ctx = MapContext(index, mp, device=device, batch_cap=batch, max_read_len=max_read_len)
-    buckets = _LengthBuckets(ctx, batch, mp.k)
-    bufs = (np.empty((batch, max_read_len), np.uint8), np.empty((batch, max_read_len), np.uint8),
-            np.empty(batch, np.uint32), np.empty(batch, np.uint32))
-    for b in bufs[:2]:
-        _capi.pin(b)
-    n_observed = 0
-    try:
-        with _capi.ReadFiles(mates1, mates2, n_threads=threads) as rf:
-            bi = 0
-            while True:
-                n, left, right, ll, lr = rf.next_batch(batch, max_read_len, out=bufs)
-                if n == 0:
-                    break
-                n_observed += n
-                if bi % world == rank:
-                    L0 = int(ll[0])
-                    if np.all(ll == L0) and np.all(lr == L0) and L0 < max_read_len:
-                        left, right = np.ascontiguousarray(left[:, :L0]), np.ascontiguousarray(right[:, :L0])
-                        ll = lr = np.full(n, L0, np.uint32)
-                        buckets.add(left, right, ll, lr)
-                    else:
-                        buckets.add(left, right, ll, lr)
-                bi += 1
-        buckets.finish()
-    finally:
-        for b in bufs[:2]:
-            _capi.unpin(b)
+    # sb_reads_bucketed: a reader thread parses and groups the reads by length into page-locked [n, L] buffers while this
+    # thread maps the previous ones; global batches of `batch` records go round-robin to the ranks
+    def map_one(left, right, L):
+        ctx.map_batch(left, right)       # raises on error (the reader then stops and reports it)
+        return 0
+    with _capi.ReadFiles(mates1, mates2, n_threads=threads) as rf:
+        st = rf.bucketed(map_one, min_len=mp.k, batch=batch, max_read_len=max_read_len, threads=threads,
+                         shard_index=rank, shard_count=world)
+    n_observed = int(st["n_observed"])
     return _quantify(index, ctx, ep, device, dist, None, out_dir, dump_eq, dump_eq_weights, num_bootstraps, seed,
                      n_observed=n_observed)
 
