@@ -319,11 +319,11 @@ def bench_stage_a(args, rank, world, local, dist, W, peak, peak_src, ncores):
     sampler = ClockSampler(local); sampler.start(); sampler.wait_first()
     barrier(); step((dl.data_ptr(), dr.data_ptr()))
     sampler.mark()
-    res_s, seed_ms_l, seed_n_l = [], [], 0
+    res_s, seed_ms_l, seed_n_l, dev_ms_l = [], [], 0, []
     for _ in range(args.steps):
         barrier()
         wall, dev_ms, seed_ms, seed_n, launches, res = step((dl.data_ptr(), dr.data_ptr()))
-        res_s.append(wall); seed_ms_l.append(seed_ms); seed_n_l = seed_n
+        res_s.append(wall); seed_ms_l.append(seed_ms); seed_n_l = seed_n; dev_ms_l.append(dev_ms)
     barrier()
     clocks_a = sampler.stop()
     c = res["counters"]
@@ -348,7 +348,12 @@ def bench_stage_a(args, rank, world, local, dist, W, peak, peak_src, ncores):
     out = {
         "metric": "Mreads/s selective-align", "value": world * n / res_t / 1e6, "unit": "Mreads/s",
         "ms_per_step": res_t * 1e3, "higher_is_better": True, "scaling": "weak", "dtype": "u8/i32 (mapping), f64 (weights)",
-        "steps_ms_rank0": {"resident": [round(x * 1e3, 2) for x in res_s], "e2e": [round(x * 1e3, 2) for x in e2e_s]},
+        "steps_ms_rank0": {"resident": [round(x * 1e3, 2) for x in res_s], "e2e": [round(x * 1e3, 2) for x in e2e_s],
+                           "resident_device_events": [round(x, 2) for x in dev_ms_l]},
+        "timing": "value / e2e: host clock around the synchronous C-ABI calls of a step (sb_map_batch x batches + sb_map_finish), "
+                  "barrier + synchronize on both sides, max over ranks -- it contains the device time (CUDA events on the "
+                  "library's streams, resident_device_events, batches only) plus finish() and the host side of the calls, so it "
+                  "cannot overstate the rate",
         "config": {"workload": f"configs[2] shape: synth_txome(seed=44, n_genes={SA['n_genes'] // (20 if args.sa_small else 1)}) = "
                                f"{len(txps)} transcripts / {flat[1].shape[0] / 1e6:.0f} Mb / {info['n_kmers'] / 1e6:.0f} M distinct 31-mers; "
                                f"{n} synthetic 2x{L} bp IU pairs per GPU per step (0.5% substitutions, 3% unmappable), "
