@@ -179,3 +179,65 @@ def test_online_oracle_properties():
     lens = np.array([t.shape[0] for t in txps], dtype=np.float64)
     assert np.all(fin["eff_len"] >= 1.0) and np.all(fin["eff_len"] <= lens)
     assert fin["eff_len"].mean() < lens.mean() - 100          # roughly length - mean fragment length
+
+
+def test_map_oracle_vs_python_restatement_of_the_aux_model(oracle):
+    """Second, independent restatement (tests/py_ref_map.py, written from the reference source) of
+    filterAndCollectAlignments + the auxiliary-probability / label arithmetic of processMiniBatch, checked against the
+    oracle read by read: paired alignments, left / right orphans, multi-mapping reads with range-factorised labels."""
+    import py_ref_map as R
+    from salmon_b200.synth import synth_reads, synth_txome
+    txps, _ = synth_txome(seed=12, n_genes=120)
+    left, right, truth = synth_reads(txps, seed=13, n=4000, indel_rate=0.002, sub_rate=0.02)
+    rng = np.random.default_rng(2)
+    kill = rng.random(4000) < 0.15                      # make orphans: one mate becomes unmappable noise
+    right[kill] = rng.integers(0, 4, size=(int(kill.sum()), right.shape[1]), dtype=np.uint8)
+    kill2 = rng.random(4000) < 0.08
+    left[kill2 & ~kill] = rng.integers(0, 4, size=(int((kill2 & ~kill).sum()), left.shape[1]), dtype=np.uint8)
+    p = oracle.map_params()
+    m = oracle.map_reads(oracle.MapIndex(txps), p, left, right, 0)
+    tx_len = np.array([t.shape[0] for t in txps])
+    cmf = R.quirk_cmf(p.max_frag_len)
+    cap = p.max_read_occ
+    n_checked = n_multi = n_orphan = 0
+    for r in range(left.shape[0]):
+        k = R.check_read(m["n_aln"][r], m["tid"][r], m["score"][r], m["prob"][r], m["pos"][r], m["flags"][r],
+                         m["label"][r], m["weight"][r], left.shape[1], tx_len, cmf, score_exp=p.score_exp,
+                         min_aln_prob=p.min_aln_prob, range_bins=p.range_bins, max_read_occ=cap)
+        n_checked += k > 0
+        n_multi += k > 1
+        n_orphan += k > 0 and ((int(m["flags"][r][0]) >> 2) & 3) != 0
+    assert n_checked > 3000 and n_multi > 500 and n_orphan > 300, (n_checked, n_multi, n_orphan)
+
+
+def test_normalize_alphas_vs_python_restatement(oracle):
+    """normalizeAlphas + projectToPolytope restated in Python from the reference (tests/py_ref_map.py) against the
+    oracle's orc_online_finish on the state three mapped batches leave behind."""
+    import py_ref_map as R
+    from salmon_b200.synth import synth_reads, synth_txome
+    txps, _ = synth_txome(seed=14, n_genes=100)
+    left, right, _ = synth_reads(txps, seed=15, n=6000)
+    p = oracle.map_params(num_pre_burnin=1500, num_burnin=4000)
+    on = oracle.Online(oracle.MapIndex(txps), p, seed=3, mini_batch=1000)
+    outs = [on.batch(left[s:s + 2000], right[s:s + 2000]) for s in range(0, 6000, 2000)]
+    cap = p.max_read_occ
+    # classes over all batches (transcript part of the labels)
+    agg = {}
+    for m in outs:
+        for r in range(m["n_aln"].shape[0]):
+            k = int(m["n_aln"][r])
+            if k:
+                key = tuple(int(x) for x in m["tid"][r, :k])
+                agg[key] = agg.get(key, 0) + 1
+    keys = sorted(agg)
+    off = np.concatenate([[0], np.cumsum([len(k) for k in keys])]).astype(np.uint64)
+    tids = np.array([t for k in keys for t in k], dtype=np.uint32)
+    counts = np.array([agg[k] for k in keys], dtype=np.uint64)
+    st = on.state()
+    fin = on.finish(off, tids, counts)
+    proj, uniq, total = R.normalize_alphas([float(x) for x in st["mass"]], [(list(k), agg[k]) for k in keys])
+    assert np.array_equal(fin["unique_counts"], np.array(uniq, dtype=np.uint64))
+    assert np.array_equal(fin["total_counts"], np.array(total, dtype=np.uint64))
+    np.testing.assert_allclose(fin["projected_counts"], np.array(proj), rtol=1e-9, atol=1e-9)
+    assert abs(fin["projected_counts"].sum() - counts.sum()) < 1e-6 * counts.sum()
+    assert (np.array(proj) > 0).sum() > 50
