@@ -168,3 +168,23 @@ def project_to_polytope(mem, proj, uniq, total, cluster_counts):
         rounds += 1
         if rounds > 5000:
             return
+
+
+# ---- FragmentLengthDistribution prior (src/model/FragmentLengthDistribution.cpp:22-78, pmf :114-125, cmf :141-156) -----
+def fld_prior_tables(mean, sd, max_val, alpha=1.0):
+    """log pmf / log cmf over 0..max_val of the prior N(mean, sd) discretised per unit bin (bin_size 1)."""
+    def ncdf(x):
+        return 0.5 * math.erfc(-(x - mean) / (sd * math.sqrt(2.0)))
+    tot = math.log(alpha)
+    hist, tot_mass = [], LOG_0
+    for i in range(max_val + 1):
+        norm_mass = ncdf(i + 0.5) - ncdf(i - 0.5)
+        mass = LOG_EPSILON if norm_mass == 0 else tot + math.log(norm_mass)
+        hist.append(mass)
+        tot_mass = log_add(tot_mass, mass)
+    pmf = [h - tot_mass for h in hist]
+    cmf, cum = [], LOG_0
+    for h in hist:
+        cum = log_add(cum, h)
+        cmf.append(cum - tot_mass)
+    return pmf, cmf

@@ -241,3 +241,25 @@ def test_normalize_alphas_vs_python_restatement(oracle):
     np.testing.assert_allclose(fin["projected_counts"], np.array(proj), rtol=1e-9, atol=1e-9)
     assert abs(fin["projected_counts"].sum() - counts.sum()) < 1e-6 * counts.sum()
     assert (np.array(proj) > 0).sum() > 50
+
+
+def test_fld_prior_tables_vs_python_restatement(oracle):
+    """The fragment-length prior (FragmentLengthDistribution ctor, pmf, cmf) restated in Python against orc_fld_tables:
+    where the normal mass is resolvable (within ~7 sd) to 1e-9 in log space; farther out both carry the rounding noise
+    of a cdf difference near 1 (as the reference's own tables do), so only the floor is compared there."""
+    import ctypes as C
+    import py_ref_map as R
+    lib = oracle.load()
+    for mean, sd, mx in ((250.0, 25.0, 1000), (180.0, 15.0, 800), (400.0, 80.0, 1000)):
+        pmf = np.zeros(mx + 1); cmf = np.zeros(mx + 1)
+        lib.orc_fld_tables(C.c_double(mean), C.c_double(sd), C.c_uint32(mx), pmf.ctypes.data_as(C.c_void_p),
+                           cmf.ctypes.data_as(C.c_void_p))
+        rp, rc = R.fld_prior_tables(mean, sd, mx)
+        rp, rc = np.array(rp), np.array(rc)
+        core = np.abs(np.arange(mx + 1) - mean) < 7 * sd
+        np.testing.assert_allclose(pmf[core], rp[core], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(cmf[core], rc[core], rtol=0, atol=1e-9)
+        assert abs(np.exp(cmf[-1])) - 1 < 1e-9 and np.all(np.diff(cmf) >= -1e-12)     # a distribution, monotone
+        far = np.arange(mx + 1) > mean + 12 * sd          # the normal mass underflows: the LOG_EPSILON floor, exactly
+        if far.any():
+            np.testing.assert_allclose(pmf[far], rp[far], rtol=0, atol=1e-12)
