@@ -263,3 +263,32 @@ def test_fld_prior_tables_vs_python_restatement(oracle):
         far = np.arange(mx + 1) > mean + 12 * sd          # the normal mass underflows: the LOG_EPSILON floor, exactly
         if far.any():
             np.testing.assert_allclose(pmf[far], rp[far], rtol=0, atol=1e-12)
+
+
+def test_eq_aggregate_vs_python_dict(oracle):
+    """EquivalenceClassBuilder::addGroup / finish (EquivalenceClassBuilder.hpp:165-181,237-250; TGValue :114-123)
+    restated with a Python dict: count += 1 and weights[i] += w_i per fragment under the full label (transcripts ++ range
+    bins), finish() scales a class's weights to sum 1."""
+    from salmon_b200.synth import synth_reads, synth_txome
+    txps, _ = synth_txome(seed=16, n_genes=80)
+    left, right, _ = synth_reads(txps, seed=17, n=3000)
+    p = oracle.map_params()
+    m = oracle.map_reads(oracle.MapIndex(txps), p, left, right, 0)
+    cap = p.max_read_occ
+    agg = {}
+    for r in range(3000):
+        k = int(m["n_aln"][r])
+        if not k:
+            continue
+        key = tuple(int(x) for x in m["label"][r, :2 * k])
+        cnt, ws = agg.get(key, (0, [0.0] * k))
+        agg[key] = (cnt + 1, [a + float(b) for a, b in zip(ws, m["weight"][r, :k])])
+    e = oracle.eq_aggregate(m, cap, True)
+    off = e["off"].astype(np.int64)
+    assert len(e["counts"]) == len(agg)
+    for c, key in enumerate(sorted(agg)):                         # the oracle emits classes sorted by full label
+        cnt, ws = agg[key]
+        k = len(ws)
+        assert e["tids"][off[c]:off[c + 1]].tolist() == list(key[:k]) and int(e["counts"][c]) == cnt
+        tot = sum(ws)
+        np.testing.assert_allclose(e["weights"][off[c]:off[c + 1]], [w / tot for w in ws], rtol=1e-12)
