@@ -292,3 +292,43 @@ def test_eq_aggregate_vs_python_dict(oracle):
         assert e["tids"][off[c]:off[c + 1]].tolist() == list(key[:k]) and int(e["counts"][c]) == cnt
         tot = sum(ws)
         np.testing.assert_allclose(e["weights"][off[c]:off[c + 1]], [w / tot for w in ws], rtol=1e-12)
+
+
+def test_bootstrap_and_gibbs_oracle_statistics(oracle):
+    """The samplers' RNG is substituted (Philox for mt19937 / pcg32), so the oracle is pinned on what does not depend on
+    the generator: a bootstrap replicate is a multinomial resample of the class counts (every replicate draws exactly N
+    fragments, replicate means and variances per class are those of Multinomial(N, count/N),
+    CollapsedEMOptimizer.cpp:398-552), and the Gibbs chain conserves the fragments and centres on the EM estimate
+    (CollapsedGibbsSampler.cpp:317-508)."""
+    from salmon_b200._capi import default_params
+    from salmon_b200.synth import synth_eq
+    from test_sampling_gpu import boot_inputs, unique_labels
+    eq, proj, eff, uniq = synth_eq(seed=21, C=800, M=300, total_count=40_000)
+    eq = unique_labels(eq, proj, eff, uniq)
+    N = float(eq.counts.sum())
+    p_main = default_params(use_vbem=1)
+    alpha, st = oracle.em_optimize(eq, proj, eff, uniq, p_main)
+    cw, valid, valid_boot, prior, active = boot_inputs(oracle, eq, proj, eff, uniq, p_main, N)
+    p_boot = default_params(use_vbem=1, min_iter=50)
+    n_boot = 120
+    alphas, samp, rc = oracle.bootstrap(eq, cw, valid_boot, prior, active, p_boot, n_boot, 11)
+    assert rc == 0
+    assert np.all(samp.sum(axis=1) == int(N))                       # N draws per replicate
+    np.testing.assert_allclose(alphas.sum(axis=1), N, rtol=1e-6)
+    pc = eq.counts / N
+    mean, var = samp.mean(axis=0), samp.var(axis=0, ddof=1)
+    big = eq.counts >= 50
+    z = (mean[big] - eq.counts[big]) / np.sqrt(N * pc[big] * (1 - pc[big]) / n_boot)
+    assert np.abs(z).max() < 5 and abs(z.mean()) < 0.5, (np.abs(z).max(), z.mean())
+    ratio = var[big] / (N * pc[big] * (1 - pc[big]))
+    assert 0.8 < np.median(ratio) < 1.25, np.median(ratio)
+    # replicates differ from each other and scatter around the point estimate
+    assert np.abs(alphas - alphas[0]).max() > 1.0
+    hi = alpha > 200
+    assert np.all(np.abs(alphas[:, hi].mean(axis=0) - alpha[hi]) < 0.15 * alpha[hi] + 30)
+    # Gibbs: thinning 4, with and without the gamma draw
+    for no_gamma in (1, 0):
+        g = oracle.gibbs(eq, valid, eff, alpha, 1, 1, p_main.vb_prior, 40, 4, no_gamma, N, 5)
+        np.testing.assert_allclose(g.sum(axis=1), N, rtol=1e-9)
+        assert (g >= 0).all() and np.abs(g - g[0]).max() > 1.0
+        assert np.all(np.abs(g[:, hi].mean(axis=0) - alpha[hi]) < 0.2 * alpha[hi] + 30)
