@@ -121,3 +121,61 @@ def test_decoys_host_logic_matches_oracle(oracle):
     got2, _ = run_both(oracle, allseq, left, right)
     assert (got2["tid"][np.arange(got2["tid"].shape[1])[None, :] < got2["n_aln"][:, None]] >= M).any()
     assert got2["counters"]["mapped"] > got["counters"]["mapped"]
+
+
+@pytest.mark.parametrize("master_seed", [1, 4])
+def test_fuzz_host_logic_against_oracle(oracle, master_seed):
+    """Randomised parity: adversarial transcriptomes (shared blocks, homopolymers, N, short references), read lengths
+    35..125, error rates up to 5 % / 2 % indels, and random settings of stride, maxReadOcc, maxOccsPerHit, range bins,
+    hard filter, minScoreFraction, consensus fraction, k, band, first decoy, fragLenDistMax, in all three regimes of the
+    fragment counter -- the product's per-read logic stays bit-exact with the oracle."""
+    rng = np.random.default_rng(master_seed)
+    done = 0
+    for trial in range(70):
+        seed = int(rng.integers(1, 1 << 30))
+        if trial % 4 == 0:
+            txps, _ = synth_txome(seed=seed, n_genes=int(rng.integers(5, 40)))
+        else:
+            r = np.random.default_rng(seed)
+            unit = r.integers(0, 4, size=int(r.integers(60, 300)), dtype=np.uint8)
+            txps = []
+            for _ in range(int(r.integers(3, 40))):
+                parts = []
+                for _ in range(int(r.integers(1, 5))):
+                    c = r.random()
+                    if c < 0.4:
+                        parts.append(unit[: int(r.integers(31, len(unit) + 1))])
+                    elif c < 0.5:
+                        parts.append(np.full(int(r.integers(5, 60)), int(r.integers(0, 4)), dtype=np.uint8))
+                    else:
+                        parts.append(r.integers(0, 4, size=int(r.integers(10, 400)), dtype=np.uint8))
+                t = np.concatenate(parts)
+                if r.random() < 0.2:
+                    t[int(r.integers(0, len(t)))] = 4
+                txps.append(t)
+            if max(len(t) for t in txps) < 150:
+                txps.append(r.integers(0, 4, size=400, dtype=np.uint8))
+        L = int(rng.choice([35, 50, 75, 100, 125]))
+        fm = float(rng.choice([max(L + 20, 120), 250]))
+        try:
+            left, right, _ = synth_reads(txps, seed=seed + 1, n=int(rng.integers(50, 300)), read_len=L, frag_mean=fm,
+                                         frag_sd=float(rng.choice([5, 25])), sub_rate=float(rng.choice([0.0, 0.01, 0.05])),
+                                         indel_rate=float(rng.choice([0.0, 0.003, 0.02])), random_frac=0.1)
+        except Exception:  # noqa: BLE001  (the simulator refuses transcriptomes shorter than its fragments)
+            continue
+        if rng.random() < 0.3:
+            left[rng.integers(0, left.shape[0]), rng.integers(0, L)] = 4
+        over = {}
+        for key, p_use, choices in (("stride", 0.5, [1, 2, 3, 4, 7]), ("max_read_occ", 0.4, [1, 2, 5, 50]),
+                                    ("max_occs_per_hit", 0.4, [1, 3, 16, 200]), ("range_bins", 0.4, [0, 1, 8]),
+                                    ("hard_filter", 0.3, [1]), ("min_score_fraction", 0.3, [0.3, 0.8, 0.95]),
+                                    ("consensus_frac", 0.3, [0.3, 0.9, 1.0]), ("k", 0.3, [15, 21, 25]),
+                                    ("band", 0.3, [3, 8, 15]), ("max_frag_len", 0.3, [200, 400])):
+            if rng.random() < p_use:
+                v = rng.choice(choices)
+                over[key] = float(v) if isinstance(choices[0], float) else int(v)
+        if rng.random() < 0.2:
+            over["first_decoy"] = max(1, len(txps) - int(rng.integers(1, 4)))
+        run_both(oracle, txps, left, right, frag_counter=int(rng.choice([0, 0, 6000, 6_000_000])), **over)
+        done += 1
+    assert done >= 40
