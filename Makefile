@@ -11,8 +11,16 @@ CLI       := salmon_b200/sb_salmon
 
 all: $(LIB) $(CLI) oracle
 
-$(LIB): $(SRCS) $(HDRS)
-	$(NVCC) $(NVCCFLAGS) -shared -o $@.tmp $(SRCS) -ldl -lgomp -lz && mv -f $@.tmp $@
+# one object per translation unit (build/ is git-ignored), so that `make -j` compiles them side by side; the library
+# is written under a temporary name and renamed, a snapshot of the tree never sees a half-written .so
+OBJS      := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
+
+build/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) -c -o $@ $<
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@.tmp $(OBJS) -ldl -lgomp -lz && mv -f $@.tmp $@
 
 # command-line front end (host C++ over the C ABI; finds the library next to itself)
 $(CLI): $(CSRC)/cli_main.cpp $(LIB) include/salmon_b200.h
@@ -22,6 +30,6 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -f $(LIB) $(CLI); $(MAKE) -C oracle clean
+	rm -rf $(LIB) $(CLI) build; $(MAKE) -C oracle clean
 
 .PHONY: all oracle clean
