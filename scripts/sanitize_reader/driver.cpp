@@ -30,5 +30,25 @@ int main(int argc, char** argv) {
   while ((k = sb_reads_next(rd, 8192, 128, a.data(), b.data(), la.data(), lb.data())) > 0) tot += k;
   printf("next loop: %lld\n", tot);
   sb_reads_close(rd);
+  // the other file parsers of ingest.cu
+  if (argc > 4) {
+    sb_eq_file* f = nullptr;
+    if (sb_eq_file_read(argv[3], &f) != 0) { fprintf(stderr, "eq: %s\n", sb_last_error()); return 1; }
+    printf("eq file: %u transcripts, %llu classes, weights %u, missing eff %u\n", f->n_txps, (unsigned long long)f->n_classes,
+           f->has_weights, f->n_missing_eff_len);
+    sb_bootstrap_writer* w = sb_bootstrap_writer_open("/dev/null");
+    if (w) { sb_bootstrap_writer_write(w, f->eff_len, f->n_txps); sb_bootstrap_writer_close(w); }
+    sb_eq_file_free(f);
+    sb_txome* t = nullptr;
+    if (sb_txome_read_fasta(argv[4], 31, 1, nullptr, 0, 0, &t) != 0) { fprintf(stderr, "txome: %s\n", sb_last_error()); return 1; }
+    printf("txome: %u sequences, %u duplicates removed, %u clipped, %u short\n", t->n_txps, t->n_duplicates_removed, t->n_clipped,
+           t->n_short);
+    sb_txome_free(t);
+    // malformed inputs must fail cleanly
+    sb_eq_file* g = nullptr;
+    if (sb_eq_file_read(argv[4], &g) == 0) { fprintf(stderr, "a FASTA parsed as an eq file\n"); return 1; }
+    sb_txome* u = nullptr;
+    if (sb_txome_read_fasta(argv[3], 31, 0, nullptr, 0, 0, &u) == 0) { fprintf(stderr, "an eq file parsed as FASTA\n"); return 1; }
+  }
   return 0;
 }
