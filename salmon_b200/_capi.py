@@ -410,6 +410,13 @@ class EMContext:
         allh = C.create_string_buffer(b"".join(hs), 64 * len(hs))
         _check(self.lib.sb_em_peer_open(self.h, dist.get_rank(), dist.get_world_size(), allh), "sb_em_peer_open")
 
+    def peer_loopback(self, max_txps: int):
+        """the fused multi-GPU kernel on ONE GPU: the rank is its own and only peer (exercises the push / owner /
+        exchange-barrier logic without a second device)"""
+        buf = C.create_string_buffer(64)
+        _check(self.lib.sb_em_peer_handle(self.h, int(max_txps), buf), "sb_em_peer_handle")
+        _check(self.lib.sb_em_peer_open(self.h, 0, 1, buf), "sb_em_peer_open")
+
     def comm_init(self, rank: int, nranks: int, uid: bytes):
         buf = C.create_string_buffer(uid, 128)
         _check(self.lib.sb_em_comm_init(self.h, rank, nranks, buf), "sb_em_comm_init")

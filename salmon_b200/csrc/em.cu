@@ -36,48 +36,43 @@ namespace sb {
 // ---------------------------------------------------------------------------
 struct KernelSet {
   const char* name;
-  int ch;            // ring chunk (columns)
-  bool dyn;          // persistent kernel takes its work from per-block unit tables (k_em_persistent_dyn)
+  int ch, ring;      // ring chunk (columns) x chunks in flight per warp
   size_t smem;
-  const void* persistent;
-  const void* persistent_mgpu;
-  void (*p1)(EmArgs);
-  void (*p2)(EmArgs, uint32_t);
-  void (*p2_partial)(EmArgs);
+  // [0] = plain EM, [1] = VBEM (compile-time variants: the NaN guard exists in EM only, the digamma/exp epilogue in VBEM only)
+  const void* persistent[2];
+  const void* persistent_mgpu[2];
+  void (*p1[2])(EmArgs);
+  void (*p2[2])(EmArgs, uint32_t);
+  void (*p2_partial[2])(EmArgs);
 };
-template <int CH, int MINB, int MODE>
+template <int CH, int RING, int MINB, int NB>
 static KernelSet make_set(const char* name) {
   KernelSet k;
   k.name = name;
   k.ch = CH;
-  k.dyn = false;
-  k.smem = em_smem<CH>();
-  k.persistent = (const void*)k_em_persistent<CH, MINB, MODE>;
-  k.persistent_mgpu = (const void*)k_em_persistent_mgpu<CH, MINB, MODE>;
-  k.p1 = k_em_p1<CH, MINB, MODE>;
-  k.p2 = k_em_p2<CH, MINB, MODE>;
-  k.p2_partial = k_em_p2_partial<CH, MINB, MODE>;
+  k.ring = RING;
+  k.smem = em_smem<CH, RING>();
+  k.persistent[0] = (const void*)k_em_persistent<CH, RING, MINB, NB, false>;
+  k.persistent[1] = (const void*)k_em_persistent<CH, RING, MINB, NB, true>;
+  k.persistent_mgpu[0] = (const void*)k_em_persistent_mgpu<CH, RING, MINB, NB, false>;
+  k.persistent_mgpu[1] = (const void*)k_em_persistent_mgpu<CH, RING, MINB, NB, true>;
+  k.p1[0] = k_em_p1<CH, RING, MINB, NB, false>;
+  k.p1[1] = k_em_p1<CH, RING, MINB, NB, true>;
+  k.p2[0] = k_em_p2<CH, RING, MINB, NB, false>;
+  k.p2[1] = k_em_p2<CH, RING, MINB, NB, true>;
+  k.p2_partial[0] = k_em_p2_partial<CH, RING, MINB, NB, false>;
+  k.p2_partial[1] = k_em_p2_partial<CH, RING, MINB, NB, true>;
   return k;
 }
-// dynamic distribution inside a block (single-GPU persistent kernel only; the other entry points are MODE 0)
-template <int CH, int MINB>
-static KernelSet make_set_dyn(const char* name) {
-  KernelSet k = make_set<CH, MINB, 0>(name);
-  k.dyn = true;
-  k.smem = em_smem_dyn<CH>();
-  k.persistent = (const void*)k_em_persistent_dyn<CH, MINB>;
-  return k;
-}
-// MODE 0: lane-per-row loop with inline epilogues (round-1 kernel); MODE 1 / 2: batched streaming (8 / 16 gathers
-// per lane in flight, epilogues after the stream), see run_phase_b.
-constexpr int N_KERNEL_SETS = 13;
+// chunk columns x ring depth x resident blocks per SM (shared memory per block = 8 warps x CH x RING x 384 B):
+// and columns per gather batch (two batches in flight per warp):
+//   0: 8x4 b2 n8 (96 KB, 16 warps/SM)   1: 8x4 b2 n4   2: 8x3 b3 n4 (72 KB, 24 warps/SM)   3: 8x2 b4 n4 (48 KB, 32 warps/SM)
+//   4: 16x2 b2 n8 (the round-1 ring shape)
+constexpr int N_KERNEL_SETS = 5;
 static const KernelSet& kernel_set(int cfg) {
   static const KernelSet sets[N_KERNEL_SETS] = {
-      make_set<8, 3, 0>("ch8b3"),     make_set<16, 2, 0>("ch16b2"),   make_set<8, 4, 0>("ch8b4"),
-      make_set<4, 4, 0>("ch4b4"),     make_set<4, 3, 0>("ch4b3"),     make_set<8, 2, 0>("ch8b2"),
-      make_set<16, 2, 1>("ch16b2m1"), make_set<16, 2, 2>("ch16b2m2"), make_set<8, 2, 1>("ch8b2m1"),
-      make_set<8, 3, 1>("ch8b3m1"),   make_set<8, 4, 1>("ch8b4m1"),   make_set_dyn<16, 2>("ch16b2dyn"),
-      make_set_dyn<8, 3>("ch8b3dyn"),
+      make_set<8, 4, 2, 8>("ch8r4b2n8"), make_set<8, 4, 2, 4>("ch8r4b2n4"), make_set<8, 3, 3, 4>("ch8r3b3n4"),
+      make_set<8, 2, 4, 4>("ch8r2b4n4"), make_set<16, 2, 2, 8>("ch16r2b2n8"),
   };
   if (cfg < 0 || cfg >= N_KERNEL_SETS) cfg = 0;
   return sets[cfg];
@@ -374,7 +369,7 @@ __global__ void k_theta0(uint32_t n, int vbem, const double* __restrict__ alpha0
   if (vbem) {
     double logNorm = digamma_pos(sum0[0]);
     double ap = a + prior[i];
-    theta[i] = (ap > DIGAMMA_MIN) ? exp(digamma_pos(ap) - logNorm) : 0.0;
+    theta[i] = theta_of<true>(a, ap, logNorm);
   } else {
     theta[i] = a;
   }
@@ -395,13 +390,14 @@ __global__ void k_reset_maxrel(unsigned long long* maxrel, uint32_t par) { maxre
 
 // multi-GPU: per-transcript update over ALL transcripts from the all-reduced alpha'.
 // Every rank computes the same values, so every rank takes the same decisions.
+template <bool VBEM>
 __global__ void __launch_bounds__(256)
 k_em_update(const __grid_constant__ EmArgs A, const double* __restrict__ red, uint32_t M,
             uint32_t it) {
   __shared__ double scratch[32];
   const uint32_t par = it & 1u;
   double logNorm = 0.0;
-  if (A.vbem) {
+  if (VBEM) {
     if (it == 0) logNorm = digamma_pos(A.sum0);
     else logNorm = digamma_pos(sum_partials(A.sum_partial + (size_t)(par ^ 1u) * gridDim.x,
                                                  gridDim.x, 0.0, scratch));
@@ -415,7 +411,7 @@ k_em_update(const __grid_constant__ EmArgs A, const double* __restrict__ red, ui
     A.alpha[t] = na;
     const double ap = na + A.prior[t];
     sum += ap;
-    A.theta[t] = A.vbem ? ((ap > DIGAMMA_MIN) ? exp(digamma_pos(ap) - logNorm) : 0.0) : na;
+    A.theta[t] = theta_of<VBEM>(na, ap, logNorm);
   }
   double bs = block_reduce<false>(sum, scratch);
   double bm = block_reduce<true>(mx, scratch);
@@ -526,7 +522,7 @@ extern "C" sb_em_ctx* sb_em_create(int device) {
 static void free_sell(SellDev& m) {
   void** ptrs[] = {(void**)&m.slice_ptr, (void**)&m.width, (void**)&m.len, (void**)&m.idx,
                    (void**)&m.w, (void**)&m.warp_begin, (void**)&m.long_rows, (void**)&m.targets,
-                   (void**)&m.units, (void**)&m.blk_unit_ptr};
+                   };
   for (void** p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -542,7 +538,7 @@ static void free_all(sb_em_ctx* c) {
                    (void**)&c->d_valid, (void**)&c->d_scalars, (void**)&c->d_tcnt,
                    (void**)&c->d_tid_row, (void**)&c->m_off, (void**)&c->m_idx,
                    (void**)&c->m_idx_state, (void**)&c->m_w, (void**)&c->t_off, (void**)&c->t_idx,
-                   (void**)&c->t_w, (void**)&c->d_cnt, (void**)&c->d_scale, (void**)&c->d_raw1, (void**)&c->d_raw2, (void**)&c->d_ent_cls,
+                   (void**)&c->t_w, (void**)&c->d_cnt, (void**)&c->d_scale, (void**)&c->d_ent_cls,
                    (void**)&c->d_row_tid, (void**)&c->d_rank_tid, (void**)&c->d_rowperm,
                    (void**)&c->d_order, (void**)&c->d_sort_keys, (void**)&c->d_sort_vals,
                    (void**)&c->d_sort_keys2, (void**)&c->d_sort_vals2, (void**)&c->d_tmp,
@@ -596,6 +592,8 @@ extern "C" int sb_em_set_option(sb_em_ctx* c, const char* key, int64_t value) {
   } else if (!strcmp(key, "balance_long")) { c->balance_long = (int)value; c->prepared = false;
   } else if (!strcmp(key, "l2_keep_cm")) { c->keep_cm = (int)value; }
   else if (!strcmp(key, "l2_keep_tm")) { c->keep_tm = (int)value; }
+  else if (!strcmp(key, "rebalance")) { c->rebalance = (int)value; c->prepared = false; }
+  else if (!strcmp(key, "rebalance_iters")) { c->rebalance_iters = (int)value; c->prepared = false; }
   else if (!strcmp(key, "overhead_p1")) { c->ovh_p1 = (int)value; c->prepared = false; }
   else if (!strcmp(key, "overhead_p2")) { c->ovh_p2 = (int)value; c->prepared = false; }
   else { set_error("unknown option '%s'", key); return SB_ERR_INVALID; }
@@ -777,47 +775,10 @@ static int build_sell(sb_em_ctx* c, SellDev& m, uint32_t n_rows, const uint32_t*
                                                         m.warp_begin);
   c->launches++;
   SB_CUDA(cudaStreamSynchronize(st));   // h_targets must outlive the copy
-  const KernelSet& ks = kernel_set(c->config);
-  if (ks.dyn && n_warps >= (uint32_t)(EM_THREADS / 32)) {
-    // unit tables of k_em_persistent_dyn: the slice range of every block (= of its 8 warps' balanced ranges) cut into
-    // units of whole slices with <= CH columns and <= 32 slices; a slice wider than CH is a unit of its own;
-    // zero-width slices (only long / absent rows) need no unit.  Costliest first inside a block.
-    const uint32_t wpb = EM_THREADS / 32, grid = n_warps / wpb, CHc = (uint32_t)ks.ch;
-    std::vector<uint32_t> h_sp((size_t)m.n_slices + 1), h_wb((size_t)n_warps + 1);
-    SB_CUDA(cudaMemcpy(h_sp.data(), m.slice_ptr, h_sp.size() * 4, cudaMemcpyDeviceToHost));
-    SB_CUDA(cudaMemcpy(h_wb.data(), m.warp_begin, h_wb.size() * 4, cudaMemcpyDeviceToHost));
-    std::vector<uint4> units;
-    std::vector<uint32_t> bptr(grid + 1, 0);
-    for (uint32_t b = 0; b < grid; ++b) {
-      const uint32_t lo = h_wb[(size_t)b * wpb], hi = h_wb[(size_t)(b + 1) * wpb];
-      const size_t first = units.size();
-      uint32_t s = lo;
-      while (s < hi) {
-        while (s < hi && h_sp[s + 1] == h_sp[s]) ++s;          // zero-width slices open no unit
-        if (s >= hi) break;
-        const uint32_t s0 = s;
-        uint32_t cols = 0;
-        while (s < hi && s - s0 < 32u) {
-          const uint32_t w = h_sp[s + 1] - h_sp[s];
-          if (cols > 0 && cols + w > CHc) break;
-          cols += w;
-          ++s;
-          if (cols >= CHc) break;                               // (also ends a unit made of one wide slice)
-        }
-        units.push_back(make_uint4(s0, s, h_sp[s0], h_sp[s]));
-      }
-      std::stable_sort(units.begin() + first, units.end(), [&](const uint4& x, const uint4& y) {
-        return (x.w - x.z) + (uint64_t)overhead * (x.y - x.x) > (y.w - y.z) + (uint64_t)overhead * (y.y - y.x);
-      });
-      bptr[b + 1] = (uint32_t)units.size();
-    }
-    SB_TRY(dev_alloc(&m.units, units.size() + 1));
-    SB_TRY(dev_alloc(&m.blk_unit_ptr, (size_t)grid + 1));
-    SB_CUDA(cudaMemcpy(m.units, units.data(), units.size() * sizeof(uint4), cudaMemcpyHostToDevice));
-    SB_CUDA(cudaMemcpy(m.blk_unit_ptr, bptr.data(), bptr.size() * 4, cudaMemcpyHostToDevice));
-  }
   return SB_OK;
 }
+
+static int em_rebalance(sb_em_ctx* c);
 
 extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* stats) {
   if (!c || !p) { set_error("null argument"); return SB_ERR_INVALID; }
@@ -829,18 +790,21 @@ extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* s
   const uint64_t C = c->C;
   const uint32_t M = c->M;
   const uint64_t nnz = c->nnz;
-  const bool row_space = c->nranks <= 1;
+  const bool row_space = c->nranks <= 1 && !c->fused_loopback;
   SB_CUDA(cudaEventRecord(c->ev[0], st));
 
   // launch geometry first: the slice ranges are cut for this grid
   int occ = 0;
   const KernelSet& ks = kernel_set(c->config);
-  SB_CUDA(cudaFuncSetAttribute(ks.persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
-  SB_CUDA(cudaFuncSetAttribute((const void*)ks.p1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
-  SB_CUDA(cudaFuncSetAttribute((const void*)ks.p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
-  SB_CUDA(cudaFuncSetAttribute((const void*)ks.p2_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
-  SB_CUDA(cudaFuncSetAttribute(ks.persistent_mgpu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
-  SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->nranks > 1 ? ks.persistent_mgpu : ks.persistent,
+  for (int v = 0; v < 2; ++v) {
+    SB_CUDA(cudaFuncSetAttribute(ks.persistent[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
+    SB_CUDA(cudaFuncSetAttribute((const void*)ks.p1[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
+    SB_CUDA(cudaFuncSetAttribute((const void*)ks.p2[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
+    SB_CUDA(cudaFuncSetAttribute((const void*)ks.p2_partial[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
+    SB_CUDA(cudaFuncSetAttribute(ks.persistent_mgpu[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.smem));
+  }
+  const int vb = p->use_vbem ? 1 : 0;
+  SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (c->nranks > 1 || c->fused_loopback) ? ks.persistent_mgpu[vb] : ks.persistent[vb],
                                                         EM_THREADS, ks.smem));
   if (occ < 1) { set_error("persistent EM kernel does not fit on an SM"); return SB_ERR_CUDA; }
   if (c->blocks_per_sm > 0) occ = std::min(occ, c->blocks_per_sm);
@@ -930,8 +894,6 @@ extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* s
   SB_TRY(dev_alloc(&c->d_scale, (size_t)Cm + 4));
   SB_TRY(dev_alloc(&c->d_ent_cls, (size_t)nnzm));
   SB_CUDA(cudaMemsetAsync(c->d_scale, 0, ((size_t)Cm + 4) * 8, st));
-  SB_TRY(dev_alloc(&c->d_raw1, (size_t)Cm + 32));
-  SB_TRY(dev_alloc(&c->d_raw2, (size_t)M + 32));
   SB_CUDA(cudaMemcpyAsync(c->m_off + Cm, &nnzm, 4, cudaMemcpyHostToDevice, st));
   if (C) {
     k_compact<<<nblk(C, 128), 128, 0, st>>>(C, c->d_order, c->d_off, c->d_tids, c->d_cw, c->d_counts,
@@ -1016,6 +978,17 @@ extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* s
   SB_CUDA(cudaMemcpyAsync(&c->inactive_sum, d_inact, 8, cudaMemcpyDeviceToHost, st));
   SB_TRY(dev_alloc(&c->d_sum_partial, (size_t)2 * std::max<uint32_t>(c->grid, 4096)));
   SB_CUDA(cudaStreamSynchronize(st));
+  c->prepared = true;
+  // measured re-cut of the warp ranges (persistent kernels only: they carry the per-warp phase timers)
+  c->rebalance_rounds_done = 0;
+  if (c->variant == 1 && (c->nranks <= 1 || (c->peers_ready && c->M <= c->x_cap)) && p->max_iter > 0) {
+    for (int r = 0; r < c->rebalance; ++r) {
+      int rc = em_rebalance(c);
+      if (rc != SB_OK) { c->prepared = false; return rc; }
+      c->rebalance_rounds_done++;
+    }
+  }
+  const uint32_t prep_launches = c->launches;
   SB_CUDA(cudaEventRecord(c->ev[1], st));
   SB_CUDA(cudaEventSynchronize(c->ev[1]));
   float ms = 0;
@@ -1029,7 +1002,7 @@ extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* s
     stats->nnz_multi = nnzm;
     stats->n_active_txps = R;
     stats->prepare_ms = ms;
-    stats->gpu_launches = c->launches;
+    stats->gpu_launches = prep_launches;
   }
   return SB_OK;
 }
@@ -1040,7 +1013,6 @@ static Sell sell_view(const SellDev& m) {
   s.long_rows = m.long_rows; s.csr_idx = m.csr_idx; s.csr_w = m.csr_w;
   s.n_rows = m.n_rows; s.n_slices = m.n_slices; s.n_long = m.n_long;
   s.n_block = m.n_block;
-  s.units = m.units; s.blk_unit_ptr = m.blk_unit_ptr;
   s.keep_pct = 100;
   return s;
 }
@@ -1051,11 +1023,13 @@ static void fill_args(sb_em_ctx* c, EmArgs& A, bool row_space) {
   A.tm = sell_view(c->tm);
   A.cm.keep_pct = (uint32_t)c->keep_cm;
   A.tm.keep_pct = (uint32_t)c->keep_tm;
-  A.c_cnt = c->ov_cnt ? c->ov_cnt : c->d_cnt; A.scale = c->d_scale;
-  A.raw1 = c->d_raw1; A.raw2 = c->d_raw2;
+  // the bootstrap driver's overrides apply only while it is running (ov_active): the buffers outlive it, and a later
+  // optimize on the same context must not see the last replicate's resampled counts
+  const bool ov = c->ov_active;
+  A.c_cnt = (ov && c->ov_cnt) ? c->ov_cnt : c->d_cnt; A.scale = c->d_scale;
   if (row_space) {
     A.alpha = c->r_alpha; A.theta = c->r_theta; A.prior = c->r_prior;
-    A.base = c->ov_base_row ? c->ov_base_row : c->r_base;
+    A.base = (ov && c->ov_base_row) ? c->ov_base_row : c->r_base;
     A.row_tid = nullptr;
   } else {
     A.alpha = c->d_alpha; A.theta = c->d_theta; A.prior = c->d_prior; A.base = c->d_base;
@@ -1063,14 +1037,13 @@ static void fill_args(sb_em_ctx* c, EmArgs& A, bool row_space) {
   }
   A.sum_partial = c->d_sum_partial;
   A.maxrel = (unsigned long long*)(c->d_scalars + 24);
-  A.inactive_sum = c->ov_active ? c->ov_inactive_sum : c->inactive_sum;
-  A.sum0 = c->ov_active ? c->ov_sum0 : c->sum0;
-  A.min_eq_w = c->ov_active ? c->ov_min_eq_w : DBL_MIN;
-  A.first_bias = c->ov_active ? 0.0 : (c->params.use_vbem ? 0.0 : 1.0);
+  A.inactive_sum = ov ? c->ov_inactive_sum : c->inactive_sum;
+  A.sum0 = ov ? c->ov_sum0 : c->sum0;
+  A.min_eq_w = ov ? c->ov_min_eq_w : DBL_MIN;
+  A.first_bias = ov ? 0.0 : (c->params.use_vbem ? 0.0 : 1.0);
   A.tol = c->params.tol; A.min_iter = c->params.min_iter; A.max_iter = c->params.max_iter;
-  A.vbem = c->params.use_vbem;
   A.out = (uint32_t*)(c->d_scalars + 32);
-  A.dbg = c->d_dbg;
+  A.dbg = c->dbg_enabled ? c->d_dbg : nullptr;
   A.dbg_it = c->dbg_it;
 }
 
@@ -1150,13 +1123,13 @@ extern "C" int sb_em_comm_destroy(sb_em_ctx* c) {
   return SB_OK;
 }
 
-// ---- exchange blocks for the fused multi-GPU kernel (CUDA IPC over NVLink P2P) ----------------------
+// ---- exchange blocks for the fused multi-GPU kernel (CUDA IPC over NVLink P2P); layout: XchgLayout ----------
 extern "C" int sb_em_peer_handle(sb_em_ctx* c, uint32_t max_txps, void* out64) {
   if (!c || !out64 || !max_txps) { set_error("null argument"); return SB_ERR_INVALID; }
   SB_CUDA(cudaSetDevice(c->device));
   if (c->x_block && c->x_cap < max_txps) { set_error("exchange block already allocated for %u transcripts", c->x_cap); return SB_ERR_STATE; }
   if (!c->x_block) {
-    const size_t bytes = ((size_t)2 * max_txps + 64) * 8;
+    const size_t bytes = XchgLayout(max_txps, 64).bytes() + 64 * 8;   // G * ceil(M / G) <= M + 63 for every G <= 64
     SB_CUDA(cudaMalloc(&c->x_block, bytes));
     SB_CUDA(cudaMemset(c->x_block, 0, bytes));
     SB_CUDA(cudaMalloc(&c->d_xfail, 4));
@@ -1169,14 +1142,13 @@ extern "C" int sb_em_peer_handle(sb_em_ctx* c, uint32_t max_txps, void* out64) {
   return SB_OK;
 }
 
-// handles: nranks x 64 bytes (every rank's sb_em_peer_handle, all-gathered by the host layer).  The block layout
-// depends on the number of transcripts of the run: [part M | red M | flags], so M is fixed by the first run after
-// this call (max_txps of sb_em_peer_handle must be >= M).
+// handles: nranks x 64 bytes (every rank's sb_em_peer_handle, all-gathered by the host layer).  nranks == 1 is a
+// loop-back (the rank is its own and only peer): the fused kernel's exchange logic on one GPU, for tests.
 extern "C" int sb_em_peer_open(sb_em_ctx* c, int rank, int nranks, const void* handles) {
-  if (!c || !handles || nranks < 2 || nranks > 64 || rank < 0 || rank >= nranks) { set_error("bad arguments"); return SB_ERR_INVALID; }
+  if (!c || !handles || nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) { set_error("bad arguments"); return SB_ERR_INVALID; }
   if (!c->x_block) { set_error("sb_em_peer_open before sb_em_peer_handle"); return SB_ERR_STATE; }
   SB_CUDA(cudaSetDevice(c->device));
-  std::vector<double*> ptrs(nranks, nullptr);
+  std::vector<unsigned char*> ptrs(nranks, nullptr);
   for (int q = 0; q < nranks; ++q) {
     if (q == rank) { ptrs[q] = c->x_block; continue; }
     cudaIpcMemHandle_t h;
@@ -1184,40 +1156,44 @@ extern "C" int sb_em_peer_open(sb_em_ctx* c, int rank, int nranks, const void* h
     void* p = nullptr;
     cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e)); cudaGetLastError(); return SB_ERR_CUDA; }
-    ptrs[q] = (double*)p;
+    ptrs[q] = (unsigned char*)p;
     c->x_opened.push_back(p);
   }
-  if (!c->d_peers) SB_CUDA(cudaMalloc(&c->d_peers, 64 * sizeof(double*)));
-  SB_CUDA(cudaMemcpy(c->d_peers, ptrs.data(), (size_t)nranks * sizeof(double*), cudaMemcpyHostToDevice));
+  if (!c->d_peers) SB_CUDA(cudaMalloc(&c->d_peers, 64 * sizeof(unsigned char*)));
+  SB_CUDA(cudaMemcpy(c->d_peers, ptrs.data(), (size_t)nranks * sizeof(unsigned char*), cudaMemcpyHostToDevice));
   c->rank = rank; c->nranks = nranks;
   c->peers_ready = true;
+  c->fused_loopback = (nranks == 1);
+  c->prepared = false;   // the index space of the class-major matrix depends on it
   return SB_OK;
 }
 
-// Fused path: one cooperative launch per run on every rank; alpha' is all-reduced inside the kernel over the
-// peers' exchange blocks (see k_em_persistent_mgpu).
+// Fused path: one cooperative launch per run on every rank; the partial alpha' are pushed to their owners, the owners
+// push theta back, all inside the kernel over the peers' exchange blocks (see k_em_persistent_mgpu).
 static int em_run_multi_gpu_fused(sb_em_ctx* c, const KernelSet& ks, EmArgs& A, uint32_t* out,
                                   uint32_t* launches, uint32_t* loop_launches, float* loop_ms) {
   cudaStream_t st = c->stream;
   const uint32_t M = c->M;
-  // locally inactive transcripts contribute their (constant) folded singleton mass
-  SB_CUDA(cudaMemcpyAsync(c->x_block + 64, c->d_base, (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
+  const int vb = c->params.use_vbem ? 1 : 0;
+  const XchgLayout X(M, (uint32_t)c->nranks);
   SB_CUDA(cudaMemsetAsync(c->d_xfail, 0, 4, st));
-  A.part_out = c->x_block + 64;
+  A.part_out = c->d_base;           // constant share of the locally inactive transcripts, pushed once per launch
+  A.theta = reinterpret_cast<double*>(c->x_block + X.off_theta());
   A.inactive_sum = 0.0;
   A.peers = c->d_peers; A.rank = (uint32_t)c->rank; A.nranks = (uint32_t)c->nranks; A.M = M;
   A.epoch0 = c->x_epoch; A.xfail = c->d_xfail;
   void* args[] = {(void*)&A};
   SB_CUDA(cudaEventRecord(c->ev[2], st));
-  SB_CUDA(cudaLaunchCooperativeKernel(ks.persistent_mgpu, dim3(c->grid), dim3(EM_THREADS), args, ks.smem, st));
+  SB_CUDA(cudaLaunchCooperativeKernel(ks.persistent_mgpu[vb], dim3(c->grid), dim3(EM_THREADS), args, ks.smem, st));
   SB_CUDA(cudaEventRecord(c->ev[3], st));
   *launches += 1; *loop_launches += 1;
   uint32_t fail = 0;
   SB_CUDA(cudaMemcpyAsync(out, A.out, 16, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaMemcpyAsync(&fail, c->d_xfail, 4, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(c->d_alpha, c->x_block + X.off_alpha(), (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
   SB_CUDA(cudaStreamSynchronize(st));
   cudaEventElapsedTime(loop_ms, c->ev[2], c->ev[3]);
-  c->x_epoch += 2ull * out[0];
+  c->x_epoch += out[3];
   if (fail) { set_error("multi-GPU EM: a peer GPU did not reach the in-kernel barrier (rank %d of %d)", c->rank, c->nranks); return SB_ERR_NCCL; }
   return SB_OK;
 }
@@ -1227,6 +1203,7 @@ static int em_run_multi_gpu(sb_em_ctx* c, const KernelSet& ks, EmArgs& A, uint32
                             uint32_t* launches, uint32_t* loop_launches, float* loop_ms) {
   cudaStream_t st = c->stream;
   const uint32_t M = c->M;
+  const int vb = c->params.use_vbem ? 1 : 0;
   if (!c->nccl_comm) { set_error("multi-GPU EM: neither peers (sb_em_peer_open) nor NCCL (sb_em_comm_init) are set up"); return SB_ERR_STATE; }
   SB_TRY(dev_alloc(&c->d_part, (size_t)M));
   SB_TRY(dev_alloc(&c->d_part_red, (size_t)M));
@@ -1240,11 +1217,12 @@ static int em_run_multi_gpu(sb_em_ctx* c, const KernelSet& ks, EmArgs& A, uint32
   SB_CUDA(cudaEventRecord(c->ev[2], st));
   while (it < A.min_iter || (it < A.max_iter && !converged)) {
     k_reset_maxrel<<<1, 1, 0, st>>>(A.maxrel, it & 1u);
-    ks.p1<<<c->grid, EM_THREADS, ks.smem, st>>>(A);
-    ks.p2_partial<<<c->grid, EM_THREADS, ks.smem, st>>>(A);
+    ks.p1[vb]<<<c->grid, EM_THREADS, ks.smem, st>>>(A);
+    ks.p2_partial[vb]<<<c->grid, EM_THREADS, ks.smem, st>>>(A);
     SB_NCCL(g_nccl.AllReduce(c->d_part, c->d_part_red, (size_t)M, /*ncclFloat64*/ 8, /*ncclSum*/ 0,
                              c->nccl_comm, st));
-    k_em_update<<<ugrid, 256, 0, st>>>(A, c->d_part_red, M, it);
+    if (vb) k_em_update<true><<<ugrid, 256, 0, st>>>(A, c->d_part_red, M, it);
+    else k_em_update<false><<<ugrid, 256, 0, st>>>(A, c->d_part_red, M, it);
     *launches += 5; *loop_launches += 4;
     ++it;
     if (it >= A.min_iter) {
@@ -1271,19 +1249,24 @@ extern "C" int sb_em_run(sb_em_ctx* c, sb_em_stats* stats) {
   const KernelSet& ks = kernel_set(c->config);
   const uint32_t M = c->M;
   const uint32_t R = c->n_rows;
-  const bool multi_gpu = c->nranks > 1;
+  const bool multi_gpu = c->nranks > 1 || c->fused_loopback;
+  const int vb = c->params.use_vbem ? 1 : 0;
   uint32_t launches = 0;
   SB_CUDA(cudaEventRecord(c->ev[0], st));
   // restart from the prepared state
   double* d_sum0 = c->d_scalars + 16;
+  const bool fused = multi_gpu && c->peers_ready && c->M <= c->x_cap && c->variant == 1;
+  const bool ov = c->ov_active;
   if (multi_gpu) {
+    // fused path: the replicated theta lives in the rank's exchange block (the owners push into it)
+    double* theta0 = fused ? reinterpret_cast<double*>(c->x_block + XchgLayout(M, (uint32_t)c->nranks).off_theta()) : c->d_theta;
     k_theta0<<<nblk(M, 256), 256, 0, st>>>(M, c->params.use_vbem, c->d_alpha0, c->d_prior, d_sum0,
-                                            c->d_alpha, c->d_theta);
+                                            c->d_alpha, theta0);
     ++launches;
   } else if (R) {
     k_theta0<<<nblk(R, 256), 256, 0, st>>>(R, c->params.use_vbem,
-                                            c->ov_alpha0_row ? c->ov_alpha0_row : c->r_alpha0,
-                                            c->r_prior, c->ov_active ? c->d_scalars + 18 : d_sum0,
+                                            (ov && c->ov_alpha0_row) ? c->ov_alpha0_row : c->r_alpha0,
+                                            c->r_prior, ov ? c->d_scalars + 18 : d_sum0,
                                             c->r_alpha, c->r_theta);
     ++launches;
   }
@@ -1296,14 +1279,13 @@ extern "C" int sb_em_run(sb_em_ctx* c, sb_em_stats* stats) {
   if (c->params.max_iter == 0 && c->params.min_iter == 0) {
     // nothing to iterate
   } else if (multi_gpu) {
-    const bool fused = c->peers_ready && c->M <= c->x_cap && c->variant == 1;
     int r = fused ? em_run_multi_gpu_fused(c, ks, A, out, &launches, &loop_launches, &loop_ms)
                   : em_run_multi_gpu(c, ks, A, out, &launches, &loop_launches, &loop_ms);
     if (r != SB_OK) return r;
   } else if (c->variant == 1) {
     void* args[] = {(void*)&A};
     SB_CUDA(cudaEventRecord(c->ev[2], st));
-    SB_CUDA(cudaLaunchCooperativeKernel(ks.persistent, dim3(c->grid), dim3(EM_THREADS), args, ks.smem, st));
+    SB_CUDA(cudaLaunchCooperativeKernel(ks.persistent[vb], dim3(c->grid), dim3(EM_THREADS), args, ks.smem, st));
     SB_CUDA(cudaEventRecord(c->ev[3], st));
     ++launches; ++loop_launches;
     SB_CUDA(cudaMemcpyAsync(out, A.out, 16, cudaMemcpyDeviceToHost, st));
@@ -1317,8 +1299,8 @@ extern "C" int sb_em_run(sb_em_ctx* c, sb_em_stats* stats) {
     SB_CUDA(cudaEventRecord(c->ev[2], st));
     while (it < A.min_iter || (it < A.max_iter && !converged)) {
       k_reset_maxrel<<<1, 1, 0, st>>>(A.maxrel, it & 1u);
-      ks.p1<<<c->grid, EM_THREADS, ks.smem, st>>>(A);
-      ks.p2<<<c->grid, EM_THREADS, ks.smem, st>>>(A, it);
+      ks.p1[vb]<<<c->grid, EM_THREADS, ks.smem, st>>>(A);
+      ks.p2[vb]<<<c->grid, EM_THREADS, ks.smem, st>>>(A, it);
       launches += 3; loop_launches += 2;
       ++it;
       if (it >= A.min_iter) {
@@ -1347,11 +1329,11 @@ extern "C" int sb_em_run(sb_em_ctx* c, sb_em_stats* stats) {
   if (!multi_gpu) {
     // row space -> transcript space (+ inactive transcripts)
     if (out[0] > 0) {
-      double bias = (!c->ov_active && !c->params.use_vbem && out[0] == 1) ? 1.0 : 0.0;
-      k_finalize<<<nblk(M, 256), 256, 0, st>>>(M, c->d_tid_row, c->ov_base_tid ? c->ov_base_tid : c->d_base,
+      double bias = (!ov && !c->params.use_vbem && out[0] == 1) ? 1.0 : 0.0;
+      k_finalize<<<nblk(M, 256), 256, 0, st>>>(M, c->d_tid_row, (ov && c->ov_base_tid) ? c->ov_base_tid : c->d_base,
                                                 bias, c->r_alpha, c->d_alpha);
     } else {
-      SB_CUDA(cudaMemcpyAsync(c->d_alpha, c->ov_alpha0_tid ? c->ov_alpha0_tid : c->d_alpha0, (size_t)M * 8,
+      SB_CUDA(cudaMemcpyAsync(c->d_alpha, (ov && c->ov_alpha0_tid) ? c->ov_alpha0_tid : c->d_alpha0, (size_t)M * 8,
                               cudaMemcpyDeviceToDevice, st));
     }
     ++launches;
@@ -1376,6 +1358,87 @@ extern "C" int sb_em_run(sb_em_ctx* c, sb_em_stats* stats) {
     stats->loop_kernel_launches = loop_launches;
     stats->gpu_launches = launches;
   }
+  return SB_OK;
+}
+
+// Measured re-balancing (42 % of all warp time was spent waiting at the two grid barriers because the
+// static split by column count does not predict a warp's phase time).  One short instrumented run of the persistent
+// kernel accumulates, per warp, the duration of P1 and P2 and of their SELL parts (em_kernels.cuh: SB_ACC_*); the
+// slice ranges are then re-cut so that   long-row time of the warp (fixed: those rows are dealt by list position)
+// + sum over its slices of (measured time density of the warp that ran the slice x modelled slice cost)
+// is equal for all warps (water-filling).  Deterministic given the measurements; the results of the iteration do not
+// depend on the split (each row's sum is computed by one lane in a fixed order wherever the row lands).
+static int em_recut(sb_em_ctx* c, sb::SellDev& m, uint32_t overhead, const std::vector<unsigned long long>& dbg,
+                    int slot_total, int slot_sell, uint32_t n_warps) {
+  if (m.n_slices == 0 || n_warps == 0) return SB_OK;
+  std::vector<uint32_t> sp((size_t)m.n_slices + 1), wb((size_t)n_warps + 1);
+  SB_CUDA(cudaMemcpy(sp.data(), m.slice_ptr, sp.size() * 4, cudaMemcpyDeviceToHost));
+  SB_CUDA(cudaMemcpy(wb.data(), m.warp_begin, wb.size() * 4, cudaMemcpyDeviceToHost));
+  auto cost = [&](uint32_t s) { return (double)(sp[s + 1] - sp[s]) + (sp[s + 1] > sp[s] ? (double)overhead : 0.0); };
+  std::vector<double> fixed(n_warps), dens(n_warps, 0.0);
+  double sell_total = 0.0, dens_sum = 0.0, work_sum = 0.0;
+  for (uint32_t w = 0; w < n_warps; ++w) {
+    const double T = (double)dbg[(size_t)w * 8 + slot_total], Ts = std::min(T, (double)dbg[(size_t)w * 8 + slot_sell]);
+    double W = 0.0;
+    for (uint32_t s = wb[w]; s < wb[w + 1]; ++s) W += cost(s);
+    fixed[w] = T - Ts;
+    if (W > 0.0) { dens[w] = Ts / W; dens_sum += Ts; work_sum += W; }
+    sell_total += Ts;
+  }
+  if (!(sell_total > 0.0) || !(work_sum > 0.0)) return SB_OK;
+  const double dens_mean = dens_sum / work_sum;
+  // cumulative measured time over slices
+  std::vector<double> F((size_t)m.n_slices + 1, 0.0);
+  {
+    uint32_t w = 0;
+    for (uint32_t s = 0; s < m.n_slices; ++s) {
+      while (w + 1 < n_warps && s >= wb[w + 1]) ++w;
+      const double d = dens[w] > 0.0 ? 0.75 * dens[w] + 0.25 * dens_mean : dens_mean;   // damped
+      F[s + 1] = F[s] + d * cost(s);
+    }
+  }
+  const double total = F[m.n_slices];
+  // level L with sum_w max(0, L - fixed_w) = total
+  double lo = 0.0, hi = total;
+  for (double f : fixed) hi = std::max(hi, f + total);
+  for (int it = 0; it < 100; ++it) {
+    const double L = 0.5 * (lo + hi);
+    double acc = 0.0;
+    for (double f : fixed) acc += std::max(0.0, L - f);
+    if (acc < total) lo = L; else hi = L;
+  }
+  const double L = hi;
+  std::vector<uint32_t> nb((size_t)n_warps + 1);
+  double cum = 0.0;
+  uint32_t s = 0;
+  for (uint32_t w = 0; w < n_warps; ++w) {
+    nb[w] = s;
+    cum += std::max(0.0, L - fixed[w]);
+    while (s < m.n_slices && 0.5 * (F[s] + F[s + 1]) < cum) ++s;   // a slice goes to the warp that holds its midpoint
+  }
+  nb[n_warps] = m.n_slices;
+  nb[0] = 0;
+  SB_CUDA(cudaMemcpy(m.warp_begin, nb.data(), nb.size() * 4, cudaMemcpyHostToDevice));
+  return SB_OK;
+}
+
+static int em_rebalance(sb_em_ctx* c) {
+  const uint32_t n_warps = c->grid * (EM_THREADS / 32);
+  SB_TRY(dev_alloc(&c->d_dbg, (size_t)n_warps * 8));
+  SB_CUDA(cudaMemsetAsync(c->d_dbg, 0, (size_t)n_warps * 64, c->stream));
+  const sb_em_params saved = c->params;
+  const uint32_t saved_it = c->dbg_it;
+  const bool saved_en = c->dbg_enabled;
+  c->params.min_iter = c->params.max_iter = (uint32_t)std::max(2, c->rebalance_iters + 1);
+  c->dbg_it = DBG_ACCUMULATE;
+  c->dbg_enabled = true;
+  int rc = sb_em_run(c, nullptr);
+  c->params = saved; c->dbg_it = saved_it; c->dbg_enabled = saved_en;
+  if (rc != SB_OK) return rc;
+  std::vector<unsigned long long> dbg((size_t)n_warps * 8);
+  SB_CUDA(cudaMemcpy(dbg.data(), c->d_dbg, dbg.size() * 8, cudaMemcpyDeviceToHost));
+  SB_TRY(em_recut(c, c->cm, (uint32_t)c->ovh_p1, dbg, 0, 3, n_warps));
+  SB_TRY(em_recut(c, c->tm, (uint32_t)(c->params.use_vbem ? c->ovh_p2 : c->ovh_p1), dbg, 1, 4, n_warps));
   return SB_OK;
 }
 
@@ -1453,6 +1516,7 @@ extern "C" int sb_em_debug_timeline(sb_em_ctx* c, uint64_t* out, uint32_t iterat
     SB_TRY(dev_alloc(&c->d_dbg, (size_t)n_warps * 8));
     SB_CUDA(cudaMemset(c->d_dbg, 0, (size_t)n_warps * 64));
     c->dbg_it = iteration;
+    c->dbg_enabled = true;
     return (int)n_warps;
   }
   if (!c->d_dbg) { set_error("timeline not armed"); return SB_ERR_STATE; }

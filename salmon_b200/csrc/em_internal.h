@@ -20,8 +20,6 @@ struct SellDev {
   uint32_t* warp_begin = nullptr;
   uint32_t* long_rows = nullptr;
   uint64_t* targets = nullptr;   // optional per-warp cumulative work targets (balance_long)
-  uint4* units = nullptr;        // k_em_persistent_dyn: work units per block
-  uint32_t* blk_unit_ptr = nullptr;
   const uint32_t* csr_idx = nullptr;  // not owned
   const double* csr_w = nullptr;      // not owned
 };
@@ -38,7 +36,9 @@ struct sb_em_ctx {
   // options
   int variant = 1;        // 1 = persistent cooperative kernel, 0 = one launch per phase
   int blocks_per_sm = 0;  // 0 = as many as fit
-  int config = 1;         // kernel configuration (tile/threads/stages), see kernel_set()
+  int config = 0;         // kernel configuration (ring chunk x depth x resident blocks), see kernel_set()
+  int rebalance = 2;      // rounds of measured re-cutting of the warp ranges at prepare (0 = column-count model only)
+  int rebalance_iters = 8;
   int occ = 0;
   int ovh_p1 = 3, ovh_p2 = 12;
   int lmax = 96;                    // longest row kept on the lane-per-row SELL path
@@ -86,7 +86,6 @@ struct sb_em_ctx {
   uint8_t* d_valid = nullptr;
   double* d_cnt = nullptr;        // counts of compact classes (as f64)
   double* d_scale = nullptr;      // count/denom per compact class
-  double *d_raw1 = nullptr, *d_raw2 = nullptr;   // per-row sums of the batched streaming path
   uint32_t* d_ent_cls = nullptr;
   uint32_t *d_sort_keys = nullptr, *d_sort_vals = nullptr, *d_sort_keys2 = nullptr,
            *d_sort_vals2 = nullptr;
@@ -113,9 +112,10 @@ struct sb_em_ctx {
   double* d_part = nullptr;       // per-transcript partial alpha' (send)
   double* d_part_red = nullptr;   // all-reduced (recv)
   // fused path: exchange block [part M | red M | flags 64] shared with the peers through CUDA IPC
-  double* x_block = nullptr;
+  unsigned char* x_block = nullptr;
   uint32_t x_cap = 0;
-  double** d_peers = nullptr;
+  unsigned char** d_peers = nullptr;
+  bool fused_loopback = false;    // one rank that is its own peer: the fused exchange logic on one GPU (tests)
   std::vector<void*> x_opened;
   bool peers_ready = false;
   unsigned long long x_epoch = 0;
@@ -140,6 +140,8 @@ struct sb_em_ctx {
   // debug timeline
   unsigned long long* d_dbg = nullptr;
   uint32_t dbg_it = 0;
+  bool dbg_enabled = false;
+  int rebalance_rounds_done = 0;
 
   // L2 flush
   void* d_flush = nullptr;

@@ -299,7 +299,11 @@ extern "C" int sb_bootstrap(sb_em_ctx* c, const sb_em_params* p, double num_mapp
   SB_TRY(build_cdf(c, c->d_valid_boot, 0, &total));
   if (total == 0) { set_error("no fragments to resample"); return SB_ERR_INVALID; }
   const double unif = scale * (double)total;                                         // :450-453, :681
-  sb_em_params saved = c->params;
+  // restores the context on EVERY exit path (the SB_CUDA macros below return early on a CUDA error)
+  struct Restore {
+    sb_em_ctx* c; sb_em_params saved;
+    ~Restore() { c->params = saved; c->ov_active = false; }
+  } restore{c, c->params};
   c->params = *p;
   std::vector<double> alpha(M);
   int rc_out = SB_OK;
@@ -331,8 +335,6 @@ extern "C" int sb_bootstrap(sb_em_ctx* c, const sb_em_params* p, double num_mapp
     if (rc == 1) { rc_out = 1; break; }                                  // :521-525
     if (cb(alpha.data(), M, user) != 0) break;
   }
-  c->params = saved;
-  c->ov_active = false;
   return rc_out;
 }
 

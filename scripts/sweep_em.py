@@ -1,5 +1,5 @@
 """EM kernel sweep on BASELINE config 2 (dev helper): every setting is checked against the first one.
-usage: sweep_em.py iters "cfg:lmax:lwarp:balance:ovh1:ovh2:keep_cm:keep_tm:group_cm:group_tm,..." [vbem]"""
+usage: sweep_em.py iters "key=value:key=value,key=value:..." [vbem]      (settings separated by commas)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -7,16 +7,15 @@ from salmon_b200 import EMContext, default_params
 from salmon_b200.synth import synth_eq
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 300
-settings = [tuple(int(y) for y in x.split(":")) for x in sys.argv[2].split(",")]
+settings = [dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in x.split(":") if kv) for x in sys.argv[2].split(",")]
 vbem = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 eq, proj, eff, uniq = synth_eq(seed=1)
 ctx = EMContext(0)
 p = default_params(min_iter=iters, max_iter=iters, use_vbem=vbem)
 ctx.upload(eq, proj, eff, uniq)
 ref = None
-names = ["config", "lmax", "lwarp", "balance_long", "overhead_p1", "overhead_p2", "l2_keep_cm", "l2_keep_tm", "sell_group_cm", "sell_group_tm"]
 for stg in settings:
-    for k, v in zip(names, stg):
+    for k, v in stg.items():
         ctx.set_option(k, v)
     try:
         st = ctx.prepare(p)
@@ -31,5 +30,5 @@ for stg in settings:
         continue
     if ref is None:
         ref = a
-    print(f"{':'.join(map(str, stg)):40s} loop {best / iters * 1e3:7.2f} us/iter  {iters / (best / 1e3):8.0f} iters/s  "
+    print(f"{str(stg):70s} prepare {st.prepare_ms:6.2f} ms  loop {best / iters * 1e3:7.2f} us/iter  {iters / (best / 1e3):8.0f} iters/s  "
           f"maxdiff vs first {np.max(np.abs(a - ref) / np.maximum(ref, 1e-6)):.1e}", flush=True)

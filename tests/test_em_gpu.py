@@ -185,3 +185,45 @@ def test_full_size_properties(ctx, oracle):
     pc = default_params()
     alpha, stc, ok = ctx.optimize(eq, pc, proj, eff, uniq)
     assert stc.converged == 1 and stc.max_rel_diff <= 0.01
+
+
+@pytest.mark.parametrize("vbem", [1, 0])
+def test_fused_multi_gpu_kernel_loopback(oracle, vbem):
+    """k_em_persistent_mgpu on ONE GPU that is its own peer: pushes to the owner's recv rows, owner update, theta
+    broadcast, exchange barriers, final alpha all-gather -- against the oracle (the 2-GPU run is scripts/check_multigpu.py)."""
+    eq, proj, eff, uniq = synth_eq(seed=5, C=40000, M=9000, total_count=900000)
+    c = EMContext(0)
+    try:
+        c.peer_loopback(eq.n_txps)
+        for k in (1, 2, 25):
+            p = default_params(use_vbem=vbem, min_iter=k, max_iter=k)
+            alpha, st, ok = c.optimize(eq, p, proj, eff, uniq)
+            ref, rst = oracle.em_optimize(eq, proj, eff, uniq, p)
+            assert ok and st.iters == rst.iters == k
+            assert_alpha(alpha, ref)
+            assert abs(st.max_rel_diff - rst.max_rel_diff) <= 1e-9 * max(1.0, abs(rst.max_rel_diff))
+        # convergence decision taken inside the kernel from the exchanged maxima
+        p = default_params(use_vbem=vbem, min_iter=10, max_iter=400)
+        alpha, st, ok = c.optimize(eq, p, proj, eff, uniq)
+        ref, rst = oracle.em_optimize(eq, proj, eff, uniq, p)
+        assert st.iters == rst.iters and st.converged == rst.converged
+        assert_alpha(alpha, ref)
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("rebalance", [0, 3])
+def test_kernel_configurations_agree(ctx, oracle, cfg, rebalance):
+    """every ring / batch / occupancy configuration and the measured re-cut of the warp ranges give the oracle's alphas
+    (a row's sum is computed by one lane in label order wherever the row lands)"""
+    eq, proj, eff, uniq = synth_eq(seed=6, C=60000, M=15000, total_count=2_000_000)
+    p = default_params(min_iter=12, max_iter=12)
+    ctx.set_option("variant", 1); ctx.set_option("config", cfg); ctx.set_option("rebalance", rebalance)
+    try:
+        alpha, st, ok = ctx.optimize(eq, p, proj, eff, uniq)
+    finally:
+        ctx.set_option("config", 0); ctx.set_option("rebalance", 2)
+    ref, rst = oracle.em_optimize(eq, proj, eff, uniq, p)
+    assert ok and st.iters == 12
+    assert_alpha(alpha, ref)

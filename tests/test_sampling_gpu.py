@@ -96,3 +96,23 @@ def test_gibbs_gamma_posterior_mean(ctx, oracle):
     tr = np.array([oracle.tpm(s, eff) for s in ref]).mean(0) / 1e6
     assert np.max(np.abs(tg - tr)) < 1e-3
     assert np.isfinite(got).all() and (got >= 0).all()
+
+
+@pytest.mark.parametrize("vbem", [1, 0])
+def test_optimize_after_bootstrap_on_a_larger_problem(ctx, oracle, vbem):
+    """the bootstrap driver's override buffers outlive it; a later optimize on the same context --
+    here on a LARGER table -- must not see the last replicate's resampled counts / base / uniform start."""
+    eq, proj, eff, uniq = synth_eq(seed=21, C=3000, M=900, total_count=90_000)
+    p = default_params(use_vbem=vbem, min_iter=30, max_iter=30)
+    ctx.optimize(eq, p, proj, eff, uniq)
+    got, okb = ctx.bootstrap(default_params(use_vbem=vbem, min_iter=50, max_iter=200), float(eq.counts.sum()), 2, 77)
+    assert okb
+    eq2, proj2, eff2, uniq2 = synth_eq(seed=22, C=9000, M=2500, total_count=400_000)
+    alpha, st, ok = ctx.optimize(eq2, p, proj2, eff2, uniq2)
+    ref, rst = oracle.em_optimize(eq2, proj2, eff2, uniq2, p)
+    assert ok and st.iters == rst.iters == 30
+    np.testing.assert_allclose(alpha, ref, rtol=1e-9, atol=1e-9)
+    # and the staged path (run without a new prepare) on the same context
+    ctx.upload(eq2, proj2, eff2, uniq2); ctx.prepare(p); ctx.run()
+    a2, _, ok2 = ctx.download()
+    np.testing.assert_allclose(a2, ref, rtol=1e-9, atol=1e-9)
