@@ -45,34 +45,34 @@ struct KernelSet {
   void (*p2[2])(EmArgs, uint32_t);
   void (*p2_partial[2])(EmArgs);
 };
-template <int CH, int RING, int MINB, int NB>
+template <int CH, int RING, int MINB>
 static KernelSet make_set(const char* name) {
   KernelSet k;
   k.name = name;
   k.ch = CH;
   k.ring = RING;
   k.smem = em_smem<CH, RING>();
-  k.persistent[0] = (const void*)k_em_persistent<CH, RING, MINB, NB, false>;
-  k.persistent[1] = (const void*)k_em_persistent<CH, RING, MINB, NB, true>;
-  k.persistent_mgpu[0] = (const void*)k_em_persistent_mgpu<CH, RING, MINB, NB, false>;
-  k.persistent_mgpu[1] = (const void*)k_em_persistent_mgpu<CH, RING, MINB, NB, true>;
-  k.p1[0] = k_em_p1<CH, RING, MINB, NB, false>;
-  k.p1[1] = k_em_p1<CH, RING, MINB, NB, true>;
-  k.p2[0] = k_em_p2<CH, RING, MINB, NB, false>;
-  k.p2[1] = k_em_p2<CH, RING, MINB, NB, true>;
-  k.p2_partial[0] = k_em_p2_partial<CH, RING, MINB, NB, false>;
-  k.p2_partial[1] = k_em_p2_partial<CH, RING, MINB, NB, true>;
+  k.persistent[0] = (const void*)k_em_persistent<CH, RING, MINB, false>;
+  k.persistent[1] = (const void*)k_em_persistent<CH, RING, MINB, true>;
+  k.persistent_mgpu[0] = (const void*)k_em_persistent_mgpu<CH, RING, MINB, false>;
+  k.persistent_mgpu[1] = (const void*)k_em_persistent_mgpu<CH, RING, MINB, true>;
+  k.p1[0] = k_em_p1<CH, RING, MINB, false>;
+  k.p1[1] = k_em_p1<CH, RING, MINB, true>;
+  k.p2[0] = k_em_p2<CH, RING, MINB, false>;
+  k.p2[1] = k_em_p2<CH, RING, MINB, true>;
+  k.p2_partial[0] = k_em_p2_partial<CH, RING, MINB, false>;
+  k.p2_partial[1] = k_em_p2_partial<CH, RING, MINB, true>;
   return k;
 }
 // chunk columns x ring depth x resident blocks per SM (shared memory per block = 8 warps x CH x RING x 384 B):
-// and columns per gather batch (two batches in flight per warp):
-//   0: 8x4 b2 n8 (96 KB, 16 warps/SM)   1: 8x4 b2 n4   2: 8x3 b3 n4 (72 KB, 24 warps/SM)   3: 8x2 b4 n4 (48 KB, 32 warps/SM)
-//   4: 16x2 b2 n8 (the round-1 ring shape)
-constexpr int N_KERNEL_SETS = 5;
+//   0: 16x2 b2 (96 KB, 16 warps/SM)   1: 8x4 b2   2: 8x3 b3 (72 KB, 24 warps/SM)   3: 8x2 b4 (48 KB, 32 warps/SM)
+// Measured in round 2 and removed again: a ring-less kernel with block-level dynamic
+// distribution, and gathers through a shared-memory window of theta / scale.
+constexpr int N_KERNEL_SETS = 4;
 static const KernelSet& kernel_set(int cfg) {
   static const KernelSet sets[N_KERNEL_SETS] = {
-      make_set<8, 4, 2, 8>("ch8r4b2n8"), make_set<8, 4, 2, 4>("ch8r4b2n4"), make_set<8, 3, 3, 4>("ch8r3b3n4"),
-      make_set<8, 2, 4, 4>("ch8r2b4n4"), make_set<16, 2, 2, 8>("ch16r2b2n8"),
+      make_set<16, 2, 2>("ch16r2b2"), make_set<8, 4, 2>("ch8r4b2"), make_set<8, 3, 3>("ch8r3b3"),
+      make_set<8, 2, 4>("ch8r2b4"),
   };
   if (cfg < 0 || cfg >= N_KERNEL_SETS) cfg = 0;
   return sets[cfg];
@@ -289,7 +289,7 @@ __global__ void k_sell_widths(uint32_t n_rows, uint32_t n_slices, uint32_t lmax,
     }
   }
   for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
-  if (lane == 0) width[s] = len;
+  if (lane == 0) width[s] = (len + 3u) & ~3u;   // whole column groups of 4 (em_kernels.cuh: run_phase)
 }
 __global__ void k_sell_fill(uint32_t n_rows, uint32_t n_slices, const uint32_t* __restrict__ rowperm,
                             const uint32_t* __restrict__ csr_off, const uint32_t* __restrict__ csr_idx,
@@ -301,8 +301,10 @@ __global__ void k_sell_fill(uint32_t n_rows, uint32_t n_slices, const uint32_t* 
   if (s >= n_slices) return;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t row = s * 32 + lane;
-  const size_t base = (size_t)slice_ptr[s] * 32 + lane;
+  // group-of-4 layout: entry j of lane l sits at (first column * 32) + (j / 4) * 128 + l * 4 + (j % 4)
+  const size_t base = (size_t)slice_ptr[s] * 32 + (size_t)lane * 4;
   const uint32_t width = slice_ptr[s + 1] - slice_ptr[s];
+  auto pos = [&](uint32_t j) { return base + (size_t)(j >> 2) * 128 + (j & 3u); };
   uint32_t n = 0;
   if (row < n_rows) {
     const uint32_t cr = rowperm ? rowperm[row] : row;
@@ -315,15 +317,15 @@ __global__ void k_sell_fill(uint32_t n_rows, uint32_t n_slices, const uint32_t* 
     } else {
       n = e - b;
       for (uint32_t j = 0; j < n; ++j) {
-        s_idx[base + (size_t)j * 32] = csr_idx[b + j];
-        s_w[base + (size_t)j * 32] = csr_w[b + j];
+        s_idx[pos(j)] = csr_idx[b + j];
+        s_w[pos(j)] = csr_w[b + j];
       }
     }
   }
   // padding: weight 0 and a gather index that always reads 0.0 (slot one past the end)
   for (uint32_t j = n; j < width; ++j) {
-    s_idx[base + (size_t)j * 32] = pad_idx;
-    s_w[base + (size_t)j * 32] = 0.0;
+    s_idx[pos(j)] = pad_idx;
+    s_w[pos(j)] = 0.0;
   }
 }
 // contiguous, work-balanced slice ranges per warp: work(slice) = width + overhead
@@ -985,7 +987,7 @@ extern "C" int sb_em_prepare(sb_em_ctx* c, const sb_em_params* p, sb_em_stats* s
     for (int r = 0; r < c->rebalance; ++r) {
       int rc = em_rebalance(c);
       if (rc != SB_OK) { c->prepared = false; return rc; }
-      c->rebalance_rounds_done++;
+          c->rebalance_rounds_done++;
     }
   }
   const uint32_t prep_launches = c->launches;
@@ -1043,6 +1045,7 @@ static void fill_args(sb_em_ctx* c, EmArgs& A, bool row_space) {
   A.first_bias = ov ? 0.0 : (c->params.use_vbem ? 0.0 : 1.0);
   A.tol = c->params.tol; A.min_iter = c->params.min_iter; A.max_iter = c->params.max_iter;
   A.out = (uint32_t*)(c->d_scalars + 32);
+  A.lq = (unsigned int*)(c->d_scalars + 44);
   A.dbg = c->dbg_enabled ? c->d_dbg : nullptr;
   A.dbg_it = c->dbg_it;
 }
@@ -1271,6 +1274,7 @@ extern "C" int sb_em_run(sb_em_ctx* c, sb_em_stats* stats) {
     ++launches;
   }
   SB_CUDA(cudaMemsetAsync(c->d_scalars + 24, 0, 16 * 8, st));
+  SB_CUDA(cudaMemsetAsync(c->d_scalars + 44, 0, 16, st));   // long-row queues
   EmArgs A;
   fill_args(c, A, !multi_gpu);
   uint32_t out[4] = {0, 0, 0, 0};
@@ -1368,12 +1372,23 @@ extern "C" int sb_em_run(sb_em_ctx* c, sb_em_stats* stats) {
 // + sum over its slices of (measured time density of the warp that ran the slice x modelled slice cost)
 // is equal for all warps (water-filling).  Deterministic given the measurements; the results of the iteration do not
 // depend on the split (each row's sum is computed by one lane in a fixed order wherever the row lands).
-static int em_recut(sb_em_ctx* c, sb::SellDev& m, uint32_t overhead, const std::vector<unsigned long long>& dbg,
-                    int slot_total, int slot_sell, uint32_t n_warps) {
+// `unit` = warps that share one range: 1 (ring kernels: a warp owns its range) or 8 (direct kernel: a block's warps take
+// slices from the block's range dynamically; the block's time is the mean of its warps').
+static int em_recut(sb_em_ctx* c, sb::SellDev& m, uint32_t overhead, const std::vector<unsigned long long>& dbg_w,
+                    int slot_total, int slot_sell, uint32_t n_warps_all, uint32_t unit) {
+  const uint32_t n_warps = n_warps_all / unit;        // ranges
   if (m.n_slices == 0 || n_warps == 0) return SB_OK;
-  std::vector<uint32_t> sp((size_t)m.n_slices + 1), wb((size_t)n_warps + 1);
+  std::vector<uint32_t> sp((size_t)m.n_slices + 1), wb_all((size_t)n_warps_all + 1), wb((size_t)n_warps + 1);
   SB_CUDA(cudaMemcpy(sp.data(), m.slice_ptr, sp.size() * 4, cudaMemcpyDeviceToHost));
-  SB_CUDA(cudaMemcpy(wb.data(), m.warp_begin, wb.size() * 4, cudaMemcpyDeviceToHost));
+  SB_CUDA(cudaMemcpy(wb_all.data(), m.warp_begin, wb_all.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<unsigned long long> dbg((size_t)n_warps * 8, 0ull);
+  for (uint32_t r = 0; r <= n_warps; ++r) wb[r] = wb_all[(size_t)r * unit];
+  for (uint32_t r = 0; r < n_warps; ++r)
+    for (int k = 0; k < 8; ++k) {
+      unsigned long long a = 0;
+      for (uint32_t u = 0; u < unit; ++u) a += dbg_w[((size_t)r * unit + u) * 8 + k];
+      dbg[(size_t)r * 8 + k] = a / unit;
+    }
   auto cost = [&](uint32_t s) { return (double)(sp[s + 1] - sp[s]) + (sp[s + 1] > sp[s] ? (double)overhead : 0.0); };
   std::vector<double> fixed(n_warps), dens(n_warps, 0.0);
   double sell_total = 0.0, dens_sum = 0.0, work_sum = 0.0;
@@ -1381,7 +1396,7 @@ static int em_recut(sb_em_ctx* c, sb::SellDev& m, uint32_t overhead, const std::
     const double T = (double)dbg[(size_t)w * 8 + slot_total], Ts = std::min(T, (double)dbg[(size_t)w * 8 + slot_sell]);
     double W = 0.0;
     for (uint32_t s = wb[w]; s < wb[w + 1]; ++s) W += cost(s);
-    fixed[w] = T - Ts;
+    fixed[w] = 0.0 * (T - Ts);   // the long rows are taken from a global queue: every warp's tail is filled, nothing is fixed
     if (W > 0.0) { dens[w] = Ts / W; dens_sum += Ts; work_sum += W; }
     sell_total += Ts;
   }
@@ -1418,7 +1433,12 @@ static int em_recut(sb_em_ctx* c, sb::SellDev& m, uint32_t overhead, const std::
   }
   nb[n_warps] = m.n_slices;
   nb[0] = 0;
-  SB_CUDA(cudaMemcpy(m.warp_begin, nb.data(), nb.size() * 4, cudaMemcpyHostToDevice));
+  std::vector<uint32_t> nb_all((size_t)n_warps_all + 1);
+  for (uint32_t r = 0; r < n_warps; ++r)
+    for (uint32_t u = 0; u < unit; ++u)    // inside a unit the cut points only matter to the ring kernels: even split
+      nb_all[(size_t)r * unit + u] = nb[r] + (uint32_t)(((uint64_t)(nb[r + 1] - nb[r]) * u) / unit);
+  nb_all[n_warps_all] = m.n_slices;
+  SB_CUDA(cudaMemcpy(m.warp_begin, nb_all.data(), nb_all.size() * 4, cudaMemcpyHostToDevice));
   return SB_OK;
 }
 
@@ -1437,8 +1457,9 @@ static int em_rebalance(sb_em_ctx* c) {
   if (rc != SB_OK) return rc;
   std::vector<unsigned long long> dbg((size_t)n_warps * 8);
   SB_CUDA(cudaMemcpy(dbg.data(), c->d_dbg, dbg.size() * 8, cudaMemcpyDeviceToHost));
-  SB_TRY(em_recut(c, c->cm, (uint32_t)c->ovh_p1, dbg, 0, 3, n_warps));
-  SB_TRY(em_recut(c, c->tm, (uint32_t)(c->params.use_vbem ? c->ovh_p2 : c->ovh_p1), dbg, 1, 4, n_warps));
+  const uint32_t unit = 1u;
+  SB_TRY(em_recut(c, c->cm, (uint32_t)c->ovh_p1, dbg, 0, 3, n_warps, unit));
+  SB_TRY(em_recut(c, c->tm, (uint32_t)(c->params.use_vbem ? c->ovh_p2 : c->ovh_p1), dbg, 1, 4, n_warps, unit));
   return SB_OK;
 }
 

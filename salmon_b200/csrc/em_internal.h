@@ -37,7 +37,7 @@ struct sb_em_ctx {
   int variant = 1;        // 1 = persistent cooperative kernel, 0 = one launch per phase
   int blocks_per_sm = 0;  // 0 = as many as fit
   int config = 0;         // kernel configuration (ring chunk x depth x resident blocks), see kernel_set()
-  int rebalance = 2;      // rounds of measured re-cutting of the warp ranges at prepare (0 = column-count model only)
+  int rebalance = 1;      // rounds of measured re-cutting of the warp ranges at prepare (0 = column-count model only)
   int rebalance_iters = 8;
   int occ = 0;
   int ovh_p1 = 3, ovh_p2 = 12;

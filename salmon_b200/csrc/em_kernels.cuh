@@ -87,6 +87,7 @@ struct EmArgs {
   uint32_t* out;                // [0]=iters [1]=converged [2]=maxrel slot
   unsigned long long* dbg;      // optional [n_warps*8] phase timestamps (ns) of iteration dbg_it
   uint32_t dbg_it;
+  unsigned int* lq;             // [2] global long-row queues of the persistent kernels (P1, P2)
   // multi-GPU, fused exchange over peer memory (k_em_persistent_mgpu): every rank owns one exchange block (layout:
   // XchgLayout) mapped into every peer (CUDA IPC, NVLink P2P)
   unsigned char* const* peers;  // [nranks] base pointers of the exchange blocks (peers[rank] = own)
@@ -249,7 +250,7 @@ __device__ __forceinline__ void ring_issue(const Sell& S, WarpCtx<CH, RING>& W, 
     const int st = k % RING;
     // The two layouts together exceed what the L2 keeps under a cyclic sweep; pin a fixed
     // pseudo-random subset of chunks (evict_last) and let the rest stream (evict_first).
-    const bool keep = (((c / CH) * 2654435761u) >> 16) % 100u < S.keep_pct;
+    const bool keep = ((((c / CH) * 2654435761u) >> 24) * 100u >> 8) < S.keep_pct;
     const uint64_t pol = keep ? W.pol_keep : W.pol_stream;
     mbar_arrive_expect_tx(&W.bars[st], cols * 384u);
     bulk_g2s_hint(W.ring->w[st], S.w + (size_t)c * 32u, cols * 256u, &W.bars[st], pol);
@@ -275,23 +276,18 @@ __device__ __forceinline__ void ring_drain(WarpCtx<CH, RING>& W, const WarpRange
     if ((uint32_t)k < nchunks) mbar_wait(&W.bars[k], (W.phase_bits >> k) & 1u);
 }
 
-// one gather batch in flight: <= NB columns of ONE slice, inside ONE ring chunk
-template <int NB>
-struct Batch {
-  double g[NB];          // gathered state values (0 beyond n)
-  const double* w;       // this lane's weights of the batch in shared memory (stride 32)
-  RowOps ops;            // epilogue operands of the slice (loaded with its last batch)
-  uint32_t n;            // columns (warp-uniform)
-  uint32_t slice;        // slice the columns belong to
-  uint32_t chunk_done;   // 1 + index of the ring chunk this batch completes, else 0
-  bool last;             // completes its slice
-  bool valid;
-};
-
-template <int PHASE, int CH, int RING, int NB, bool VBEM, class Deliver>
+// The SELL stream of a warp.  Columns come in GROUPS of 4 (slice widths are padded to a multiple of 4; padding
+// entries have weight 0 and gather a slot that always holds 0.0): inside a group the layout is lane-major,
+//   idx[(group * 32 + lane) * 4 + j],  w[(group * 32 + lane) * 4 + j]        j = 0..3,
+// so a lane reads its four indices with ONE 16-byte shared-memory load and its four weights with two, issues the
+// four gathers together and needs no predicate and no remainder loop (round 1 / the first round-2 attempt spent
+// 10-12 instructions per column here; this is ~4).  Two groups (8 gathers) are in flight when a slice has them.
+template <int PHASE, int CH, int RING, bool VBEM, bool DYNQ, class Deliver>
 __device__ __forceinline__ void run_phase(const EmArgs& A, WarpCtx<CH, RING>& W, const WarpRange& R,
                                           uint32_t bid, uint32_t nblk, double logNorm, double bias,
                                           P2Acc& pa, Deliver&& deliver) {
+  static_assert(CH % 4 == 0, "ring chunks hold whole column groups");
+  constexpr uint32_t CHG = CH / 4;           // groups per chunk
   const Sell& S = (PHASE == 1) ? A.cm : A.tm;
   // theta / scale are rewritten by other blocks inside the persistent kernel: plain
   // coherent loads only, never ld.global.nc.
@@ -300,83 +296,74 @@ __device__ __forceinline__ void run_phase(const EmArgs& A, WarpCtx<CH, RING>& W,
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t s0 = R.s0, s1 = R.s1;
   if (s1 > s0 && R.cend > R.cbeg) {
-    const uint32_t cbeg = R.cbeg, cend = R.cend;
-    const uint32_t nchunks = (cend - cbeg + CH - 1) / CH;
-    // ---- fetch cursor (warp-uniform): next column, its chunk, its slice
-    uint32_t fcol = cbeg, fk = 0, fstop = min(cend, cbeg + (uint32_t)CH);
-    uint32_t fs = s0, sbase = s0;
-    uint32_t sp = (s0 + lane < s1) ? __ldg(&S.slice_ptr[s0 + lane + 1]) : cend;   // end columns of 32 slices
-    uint32_t f_end = __shfl_sync(0xffffffffu, sp, 0);
-    mbar_wait(&W.bars[0], W.phase_bits & 1u);
-    W.phase_bits ^= 1u;
-    auto fetch = [&](Batch<NB>& b) {
-      b.valid = false;
-      while (fcol == f_end) {                 // slice exhausted (or zero width: only long / absent rows)
-        if (++fs >= s1) return;
-        if (fs - sbase == 32u) {
-          sbase = fs;
-          sp = (fs + lane < s1) ? __ldg(&S.slice_ptr[fs + lane + 1]) : cend;
-        }
-        f_end = __shfl_sync(0xffffffffu, sp, (int)(fs - sbase));
+    const uint32_t nchunks = (R.cend - R.cbeg + CH - 1) / CH;
+    uint32_t rel = 0;                         // groups consumed so far (chunk = rel / CHG)
+    uint32_t sbase = s0;
+    uint32_t sp = (s0 + lane < s1) ? __ldg(&S.slice_ptr[s0 + lane + 1]) : R.cend;   // end columns of 32 slices
+    uint32_t col = R.cbeg;
+    auto fma4 = [&](double& acc, const uint4& i4, const double2& wa, const double2& wb,
+                    double g0, double g1, double g2, double g3) {
+      if (GUARD) {
+        const double v0 = g0 * wa.x, v1 = g1 * wa.y, v2 = g2 * wb.x, v3 = g3 * wb.y;
+        if (!isnan(v0)) acc += v0;
+        if (!isnan(v1)) acc += v1;
+        if (!isnan(v2)) acc += v2;
+        if (!isnan(v3)) acc += v3;
+      } else {
+        acc = fma(g0, wa.x, acc); acc = fma(g1, wa.y, acc); acc = fma(g2, wb.x, acc); acc = fma(g3, wb.y, acc);
       }
-      if (fcol == fstop) {                    // next ring chunk
-        ++fk;
-        const int st = fk % RING;
-        mbar_wait(&W.bars[st], (W.phase_bits >> st) & 1u);
-        W.phase_bits ^= (1u << st);
-        fstop = min(cend, cbeg + (fk + 1u) * (uint32_t)CH);
-      }
-      const uint32_t lim = min(f_end, fstop);
-      const uint32_t n = min(lim - fcol, (uint32_t)NB);
-      const uint32_t l0 = (fcol - (cbeg + fk * (uint32_t)CH)) * 32u + lane;
-      const int st = fk % RING;
-      const uint32_t* sidx = W.ring->idx[st] + l0;
-      b.w = W.ring->w[st] + l0;
-#pragma unroll
-      for (int j = 0; j < NB; ++j) b.g[j] = ((uint32_t)j < n) ? gsrc[sidx[j * 32]] : 0.0;
-      fcol += n;
-      b.n = n;
-      b.slice = fs;
-      b.last = (fcol == f_end);
-      b.chunk_done = (fcol == fstop) ? fk + 1u : 0u;
-      b.valid = true;
-      if (b.last) b.ops = load_ops<PHASE>(A, S, fs * 32u + lane);
     };
-    double acc = 0.0;
-    auto consume = [&](const Batch<NB>& c) {
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        if ((uint32_t)j < c.n) {
-          if (GUARD) {
-            const double v = c.g[j] * c.w[j * 32];
-            if (!isnan(v)) acc += v;
-          } else {
-            acc = fma(c.g[j], c.w[j * 32], acc);
+    RowOps ops_next = load_ops<PHASE>(A, S, s0 * 32u + lane);
+    for (uint32_t s = s0; s < s1; ++s) {
+      if (s - sbase == 32u) {
+        sbase = s;
+        sp = (s + lane < s1) ? __ldg(&S.slice_ptr[s + lane + 1]) : R.cend;
+      }
+      const uint32_t slice_end = __shfl_sync(0xffffffffu, sp, (int)(s - sbase));
+      uint32_t ng = (slice_end - col) >> 2;
+      col = slice_end;
+      // epilogue operands one slice ahead: the loads of slice s+1 are in flight while slice s is reduced and finished
+      const RowOps ops = ops_next;
+      if (s + 1u < s1) ops_next = load_ops<PHASE>(A, S, (s + 1u) * 32u + lane);
+      if (ng == 0) continue;                  // only long / absent rows
+      double acc = 0.0;
+      while (ng) {
+        const uint32_t within = rel % CHG;
+        const uint32_t k = rel / CHG;
+        if (within == 0) {                    // entering chunk k: hand back chunk k-1, wait for k
+          if (k > 0) {
+            __syncwarp();
+            if (k - 1u + (uint32_t)RING < nchunks) ring_issue(S, W, R, k - 1u + (uint32_t)RING);
           }
+          const int st = k % RING;
+          mbar_wait(&W.bars[st], (W.phase_bits >> st) & 1u);
+          W.phase_bits ^= (1u << st);
+        }
+        const int st = k % RING;
+        const uint32_t o = (within * 32u + lane) * 4u;
+        const uint32_t* pi = W.ring->idx[st] + o;
+        const double* pw = W.ring->w[st] + o;
+        if (ng >= 2 && within + 1u < CHG) {   // two groups of this slice in this chunk: 8 gathers in flight
+          const uint4 ia = *reinterpret_cast<const uint4*>(pi);
+          const uint4 ib = *reinterpret_cast<const uint4*>(pi + 128);
+          const double a0 = gsrc[ia.x], a1 = gsrc[ia.y], a2 = gsrc[ia.z], a3 = gsrc[ia.w];
+          const double b0 = gsrc[ib.x], b1 = gsrc[ib.y], b2 = gsrc[ib.z], b3 = gsrc[ib.w];
+          const double2 wa0 = *reinterpret_cast<const double2*>(pw), wa1 = *reinterpret_cast<const double2*>(pw + 2);
+          const double2 wb0 = *reinterpret_cast<const double2*>(pw + 128), wb1 = *reinterpret_cast<const double2*>(pw + 130);
+          fma4(acc, ia, wa0, wa1, a0, a1, a2, a3);
+          fma4(acc, ib, wb0, wb1, b0, b1, b2, b3);
+          rel += 2; ng -= 2;
+        } else {
+          const uint4 ia = *reinterpret_cast<const uint4*>(pi);
+          const double a0 = gsrc[ia.x], a1 = gsrc[ia.y], a2 = gsrc[ia.z], a3 = gsrc[ia.w];
+          const double2 wa0 = *reinterpret_cast<const double2*>(pw), wa1 = *reinterpret_cast<const double2*>(pw + 2);
+          fma4(acc, ia, wa0, wa1, a0, a1, a2, a3);
+          rel += 1; ng -= 1;
         }
       }
-      if (c.chunk_done) {                     // every lane has read the chunk: hand its slot back to the producer
-        __syncwarp();
-        const uint32_t kn = c.chunk_done - 1u + (uint32_t)RING;
-        if (kn < nchunks) ring_issue(S, W, R, kn);
-      }
-      if (c.last) {
-        row_finish<PHASE, VBEM>(A, c.slice * 32u + lane, c.ops, acc, logNorm, bias, pa, deliver);
-        acc = 0.0;
-      }
-    };
-    // two batches ping-pong: the gathers of the next batch go out before the current one is consumed
-    Batch<NB> ba, bb;
-    ba.ops.x0 = ba.ops.x1 = ba.ops.x2 = ba.ops.x3 = 0.0; ba.ops.len = LEN_LONG;
-    bb.ops = ba.ops;
-    fetch(ba);
-    while (ba.valid) {
-      fetch(bb);
-      consume(ba);
-      if (!bb.valid) break;
-      fetch(ba);
-      consume(bb);
+      row_finish<PHASE, VBEM>(A, s * 32u + lane, ops, acc, logNorm, bias, pa, deliver);
     }
+    // the last chunk's slot is not re-armed: nothing more to stream in this phase
   }
   if (W.dbg && lane == 0) *W.dbg = gtime_ns();
   if (W.dbg_acc && lane == 0) *W.dbg_acc += gtime_ns() - W.t0;
@@ -412,10 +399,15 @@ __device__ __forceinline__ void run_phase(const EmArgs& A, WarpCtx<CH, RING>& W,
     __syncthreads();
   }
   // long rows (LMAX < len <= LWARP): one warp per row, lanes stride the CSR copy with four independent gathers in
-  // flight, fixed shuffle tree.  Sorted longest-first and dealt round-robin over all warps of the grid.
+  // flight, fixed shuffle tree.  Sorted longest-first.  Persistent kernels (DYNQ): taken one at a time from a global
+  // queue by whichever warp has finished its SELL share (the next claim is in flight while a row is reduced), so the
+  // tail of a phase is filled evenly -- round 1 dealt them round-robin and the warp that drew a 1900-entry row ended
+  // the phase 6-12 us after the median.  Per-phase launches: dealt round-robin over the warps of the grid.
   {
     const uint32_t gw = bid * EM_WARPS + (threadIdx.x >> 5);
     const uint32_t nw = nblk * EM_WARPS;
+    const uint32_t n_mid = S.n_long - S.n_block;
+    unsigned int* queue = A.lq + ((PHASE == 1) ? 0 : 1);
     // lane k keeps the sum of the k-th row this warp reduced; the epilogues (digamma, exp)
     // then run lane-parallel, 32 rows at a time.
     uint32_t cnt = 0, myrow = 0xffffffffu;
@@ -429,7 +421,18 @@ __device__ __forceinline__ void run_phase(const EmArgs& A, WarpCtx<CH, RING>& W,
       myrow = 0xffffffffu;
       cnt = 0;
     };
-    for (uint32_t li = S.n_block + gw; li < S.n_long; li += nw) {
+    auto claim = [&]() -> uint32_t {
+      uint32_t q = 0;
+      if (lane == 0) q = atomicAdd(queue, 1u);
+      return q;               // lane 0's value is broadcast when it is consumed
+    };
+    uint32_t q_next = 0;
+    if (DYNQ) { if (n_mid) q_next = claim(); } else q_next = gw;
+    for (;;) {
+      uint32_t q = DYNQ ? __shfl_sync(0xffffffffu, q_next, 0) : q_next;
+      if (q >= n_mid) break;
+      if (DYNQ) q_next = claim(); else q_next = q + nw;
+      const uint32_t li = S.n_block + q;
       const uint32_t r = __ldg(&S.long_rows[3 * li]);
       const uint32_t b = __ldg(&S.long_rows[3 * li + 1]);
       const uint32_t e = __ldg(&S.long_rows[3 * li + 2]);
@@ -526,7 +529,7 @@ __device__ __forceinline__ void p2_finish(const EmArgs& A, double* scratch, P2Ac
   if (dbg_acc && (threadIdx.x & 31u) == 0) A.dbg[(size_t)gwarp * 8 + (slot)] += gtime_ns() - var;
 
 // ---- persistent cooperative kernel: the whole iteration loop, two grid barriers/iter
-template <int CH, int RING, int MINB, int NB, bool VBEM>
+template <int CH, int RING, int MINB, bool VBEM>
 __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent(const __grid_constant__ EmArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   WarpCtx<CH, RING> W;
@@ -549,18 +552,19 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent(const __grid
     P2Acc pa{0.0, 0.0};
     SB_DBG(0)
     SB_ACC_BEGIN(t1, 3)
-    run_phase<1, CH, RING, NB, VBEM>(A, W, R1, bid, nblk, 0.0, 0.0, pa, NoDeliver{});
+    run_phase<1, CH, RING, VBEM, true>(A, W, R1, bid, nblk, 0.0, 0.0, pa, NoDeliver{});
     SB_ACC_END(t1, 0)
     SB_DBG(1)
     ring_prefetch(A.tm, W, R2);   // P2's stream lands during the grid barrier
     grid.sync();
     SB_DBG(2)
+    if (bid == 0 && threadIdx.x == 0) A.lq[0] = 0u;   // P1's long-row queue: idle until the next iteration
     if (VBEM && it > 0) logNorm = scratch[33];   // written before the grid barrier above
     const double bias = (it == 0) ? A.first_bias : 0.0;  // alphasPrime starts at 1.0 (:812,:821)
     SB_DBG(3)
     SB_ACC_BEGIN(t2, 4)
     W.dbg = (A.dbg && it == A.dbg_it) ? &A.dbg[(size_t)gwarp * 8 + 7] : nullptr;
-    run_phase<2, CH, RING, NB, VBEM>(A, W, R2, bid, nblk, logNorm, bias, pa, NoDeliver{});
+    run_phase<2, CH, RING, VBEM, true>(A, W, R2, bid, nblk, logNorm, bias, pa, NoDeliver{});
     W.dbg = nullptr;
     SB_ACC_END(t2, 1)
     SB_DBG(4)
@@ -569,6 +573,7 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent(const __grid
     SB_DBG(5)
     grid.sync();
     SB_DBG(6)
+    if (bid == 0 && threadIdx.x == 0) A.lq[1] = 0u;   // P2's long-row queue
     if (dbg_acc && (threadIdx.x & 31u) == 0) A.dbg[(size_t)gwarp * 8 + 2] += 1ull;
     const double mr = __longlong_as_double((long long)__ldcg(&A.maxrel[par]));
     converged = !(mr > A.tol);
@@ -634,7 +639,7 @@ struct DeliverPush {           // fused path: into row `rank` of the owner's rec
   }
 };
 
-template <int CH, int RING, int MINB, int NB, bool VBEM>
+template <int CH, int RING, int MINB, bool VBEM>
 __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent_mgpu(const __grid_constant__ EmArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   WarpCtx<CH, RING> W;
@@ -665,15 +670,17 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent_mgpu(const _
     const bool dbg_acc = A.dbg && A.dbg_it == DBG_ACCUMULATE && it > 0;
     P2Acc pa{0.0, 0.0};
     SB_ACC_BEGIN(t1, 3)
-    run_phase<1, CH, RING, NB, VBEM>(A, W, R1, bid, nblk, 0.0, 0.0, pa, NoDeliver{});
+    run_phase<1, CH, RING, VBEM, true>(A, W, R1, bid, nblk, 0.0, 0.0, pa, NoDeliver{});
     SB_ACC_END(t1, 0)
     ring_prefetch(A.tm, W, R2);
     grid.sync();
+    if (bid == 0 && threadIdx.x == 0) A.lq[0] = 0u;
     SB_ACC_BEGIN(t2, 4)
-    run_phase<3, CH, RING, NB, VBEM>(A, W, R2, bid, nblk, 0.0, 0.0, pa, push);
+    run_phase<3, CH, RING, VBEM, true>(A, W, R2, bid, nblk, 0.0, 0.0, pa, push);
     SB_ACC_END(t2, 1)
     ring_prefetch(A.cm, W, R1);
     xgpu_barrier(grid, A, ++epoch);                            // every rank's partials have landed at their owners
+    if (bid == 0 && threadIdx.x == 0) A.lq[1] = 0u;
     if (*reinterpret_cast<volatile uint32_t*>(A.xfail)) break;
     // ---- owner phase: my slice [lo, hi)
     const double bias = (it == 0) ? A.first_bias : 0.0;
@@ -742,7 +749,7 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent_mgpu(const _
 }
 
 // ---- one launch per phase (baseline variant; also the NCCL multi-GPU building blocks)
-template <int CH, int RING, int MINB, int NB, bool VBEM>
+template <int CH, int RING, int MINB, bool VBEM>
 __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p1(const __grid_constant__ EmArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   WarpCtx<CH, RING> W;
@@ -750,9 +757,9 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p1(const __grid_constan
   P2Acc pa{0.0, 0.0};
   const WarpRange R = load_range(A.cm, blockIdx.x * (EM_THREADS / 32) + (threadIdx.x >> 5));
   ring_prefetch(A.cm, W, R);
-  run_phase<1, CH, RING, NB, VBEM>(A, W, R, blockIdx.x, gridDim.x, 0.0, 0.0, pa, NoDeliver{});
+  run_phase<1, CH, RING, VBEM, false>(A, W, R, blockIdx.x, gridDim.x, 0.0, 0.0, pa, NoDeliver{});
 }
-template <int CH, int RING, int MINB, int NB, bool VBEM>
+template <int CH, int RING, int MINB, bool VBEM>
 __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p2(const __grid_constant__ EmArgs A, uint32_t it) {
   extern __shared__ __align__(128) unsigned char smem[];
   WarpCtx<CH, RING> W;
@@ -773,10 +780,10 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p2(const __grid_constan
   P2Acc pa{0.0, 0.0};
   const WarpRange R = load_range(A.tm, blockIdx.x * (EM_THREADS / 32) + (threadIdx.x >> 5));
   ring_prefetch(A.tm, W, R);
-  run_phase<2, CH, RING, NB, VBEM>(A, W, R, blockIdx.x, gridDim.x, logNorm, bias, pa, NoDeliver{});
+  run_phase<2, CH, RING, VBEM, false>(A, W, R, blockIdx.x, gridDim.x, logNorm, bias, pa, NoDeliver{});
   p2_finish(A, scratch, pa, par);
 }
-template <int CH, int RING, int MINB, int NB, bool VBEM>
+template <int CH, int RING, int MINB, bool VBEM>
 __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p2_partial(const __grid_constant__ EmArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   WarpCtx<CH, RING> W;
@@ -784,7 +791,7 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p2_partial(const __grid
   P2Acc pa{0.0, 0.0};
   const WarpRange R = load_range(A.tm, blockIdx.x * (EM_THREADS / 32) + (threadIdx.x >> 5));
   ring_prefetch(A.tm, W, R);
-  run_phase<3, CH, RING, NB, VBEM>(A, W, R, blockIdx.x, gridDim.x, 0.0, 0.0, pa, DeliverLocal{A.part_out});
+  run_phase<3, CH, RING, VBEM, false>(A, W, R, blockIdx.x, gridDim.x, 0.0, 0.0, pa, DeliverLocal{A.part_out});
 }
 
 }  // namespace sb

@@ -7,6 +7,9 @@ from salmon_b200.synth import synth_eq
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 500000
 eq, proj, eff, uniq = synth_eq(seed=1, C=C, M=C // 2, total_count=40 * C)
 ctx = EMContext(0)
+for kv in sys.argv[2:]:
+    k, v = kv.split("=")
+    ctx.set_option(k, int(v))
 p = default_params(min_iter=60, max_iter=60)
 ctx.upload(eq, proj, eff, uniq); ctx.prepare(p)
 ctx.run()

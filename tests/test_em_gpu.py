@@ -212,7 +212,7 @@ def test_fused_multi_gpu_kernel_loopback(oracle, vbem):
         c.close()
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
 @pytest.mark.parametrize("rebalance", [0, 3])
 def test_kernel_configurations_agree(ctx, oracle, cfg, rebalance):
     """every ring / batch / occupancy configuration and the measured re-cut of the warp ranges give the oracle's alphas
@@ -223,7 +223,7 @@ def test_kernel_configurations_agree(ctx, oracle, cfg, rebalance):
     try:
         alpha, st, ok = ctx.optimize(eq, p, proj, eff, uniq)
     finally:
-        ctx.set_option("config", 0); ctx.set_option("rebalance", 2)
+        ctx.set_option("config", 0); ctx.set_option("rebalance", 1)
     ref, rst = oracle.em_optimize(eq, proj, eff, uniq, p)
     assert ok and st.iters == 12
     assert_alpha(alpha, ref)
