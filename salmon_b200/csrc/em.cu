@@ -594,6 +594,7 @@ extern "C" int sb_em_set_option(sb_em_ctx* c, const char* key, int64_t value) {
   } else if (!strcmp(key, "balance_long")) { c->balance_long = (int)value; c->prepared = false;
   } else if (!strcmp(key, "l2_keep_cm")) { c->keep_cm = (int)value; }
   else if (!strcmp(key, "l2_keep_tm")) { c->keep_tm = (int)value; }
+  else if (!strcmp(key, "push_pass")) { c->push_pass = (int)value; }
   else if (!strcmp(key, "rebalance")) { c->rebalance = (int)value; c->prepared = false; }
   else if (!strcmp(key, "rebalance_iters")) { c->rebalance_iters = (int)value; c->prepared = false; }
   else if (!strcmp(key, "overhead_p1")) { c->ovh_p1 = (int)value; c->prepared = false; }
@@ -1036,6 +1037,7 @@ static void fill_args(sb_em_ctx* c, EmArgs& A, bool row_space) {
   } else {
     A.alpha = c->d_alpha; A.theta = c->d_theta; A.prior = c->d_prior; A.base = c->d_base;
     A.row_tid = c->d_row_tid;
+    A.tid_row = c->d_tid_row;
   }
   A.sum_partial = c->d_sum_partial;
   A.maxrel = (unsigned long long*)(c->d_scalars + 24);
@@ -1180,7 +1182,12 @@ static int em_run_multi_gpu_fused(sb_em_ctx* c, const KernelSet& ks, EmArgs& A, 
   const int vb = c->params.use_vbem ? 1 : 0;
   const XchgLayout X(M, (uint32_t)c->nranks);
   SB_CUDA(cudaMemsetAsync(c->d_xfail, 0, 4, st));
-  A.part_out = c->d_base;           // constant share of the locally inactive transcripts, pushed once per launch
+  SB_TRY(dev_alloc(&c->d_part, (size_t)M));
+  // locally inactive transcripts contribute their (constant) folded singleton mass
+  SB_CUDA(cudaMemcpyAsync(c->d_part, c->d_base, (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
+  A.part_out = c->d_part;
+  A.push_pass = (c->push_pass >= 0) ? (uint32_t)c->push_pass : (c->nranks > 2 ? 1u : 0u);
+  if (c->grid > XAUX) { set_error("multi-GPU EM: grid of %u blocks exceeds the exchange block's aux area", c->grid); return SB_ERR_STATE; }
   A.theta = reinterpret_cast<double*>(c->x_block + X.off_theta());
   A.inactive_sum = 0.0;
   A.peers = c->d_peers; A.rank = (uint32_t)c->rank; A.nranks = (uint32_t)c->nranks; A.M = M;

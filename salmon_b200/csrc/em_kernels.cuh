@@ -75,6 +75,7 @@ struct EmArgs {
   // indexed by transcript id (cm.idx holds ids) and row_tid maps tm rows to ids.
   double* alpha; double* theta; const double* prior; const double* base;
   const uint32_t* row_tid;
+  const uint32_t* tid_row;      // multi-GPU: row of a transcript id (0xffffffff: locally inactive)
   double* part_out;             // multi-GPU (NCCL path): this rank's alpha' share per transcript id
   // reductions
   double* sum_partial;          // [2][grid]
@@ -92,25 +93,31 @@ struct EmArgs {
   // XchgLayout) mapped into every peer (CUDA IPC, NVLink P2P)
   unsigned char* const* peers;  // [nranks] base pointers of the exchange blocks (peers[rank] = own)
   uint32_t rank, nranks, M;
+  uint32_t push_pass;           // fused path: partials go to the owners in a coalesced pass (else from the row epilogues)
   unsigned long long epoch0;    // barrier epochs consumed by earlier launches
   uint32_t* xfail;              // set when a peer did not show up in time
 };
 
-// Exchange block of one rank (bytes from its base; S = ceil(M / G) transcripts per owner slice):
-//   flags  [64] u64     flags[q] = last epoch rank q has signalled to this rank
-//   aux    [2][64][2] f64   per parity, per source rank: {max rel diff, sum(alpha'+prior)} of its slice
-//   theta  [M + 4] f64      the replicated iteration state every rank's P1 gathers from (owners push their slice)
-//   alpha  [M] f64          final alpha, all-gathered once after the loop
-//   recv   [G][S] f64       partial alpha' of this rank's slice, one row per source rank
+// Exchange block of one rank (bytes from its base; S = ceil(M / G) transcripts per owner slice).  The per-iteration
+// traffic travels as flagged 16-byte lines {lo32, epoch, hi32, epoch} (the NCCL "LL" idea: each 8-byte half carries its
+// own flag and is written atomically, so the receiver polls the data itself and no fence or barrier orders it):
+//   flags  [64] u64            end-of-run barrier: flags[q] = last epoch rank q has signalled to this rank
+//   theta  [M + 4] f64         plain copy of the replicated state, what this rank's P1 gathers from
+//   alpha  [M] f64             final alpha, all-gathered once after the loop
+//   llth   [M] lines           theta' pushed by the owners of the other slices
+//   llaux  [G][XAUX][2] lines  per source rank, per block: {sum(alpha'+prior), max rel diff} of its share of its slice
+//   llrecv [G][S] lines        partial alpha' of this rank's slice, one row per source rank
+constexpr uint32_t XAUX = 1024;   // blocks per rank the aux area has room for
 struct XchgLayout {
   uint32_t M, G, S;
   __host__ __device__ XchgLayout(uint32_t m, uint32_t g) : M(m), G(g), S((m + g - 1) / g) {}
   __host__ __device__ size_t off_flags() const { return 0; }
-  __host__ __device__ size_t off_aux() const { return 64 * 8; }
-  __host__ __device__ size_t off_theta() const { return off_aux() + (size_t)2 * 64 * 2 * 8; }
+  __host__ __device__ size_t off_theta() const { return 64 * 8; }
   __host__ __device__ size_t off_alpha() const { return off_theta() + ((size_t)M + 4) * 8; }
-  __host__ __device__ size_t off_recv() const { return off_alpha() + (size_t)M * 8; }
-  __host__ __device__ size_t bytes() const { return off_recv() + (size_t)G * S * 8; }
+  __host__ __device__ size_t off_llth() const { return (off_alpha() + (size_t)M * 8 + 15) & ~(size_t)15; }
+  __host__ __device__ size_t off_llaux() const { return off_llth() + (size_t)M * 16; }
+  __host__ __device__ size_t off_llrecv() const { return off_llaux() + (size_t)G * XAUX * 2 * 16; }
+  __host__ __device__ size_t bytes() const { return off_llrecv() + (size_t)G * S * 16; }
 };
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -589,19 +596,19 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent(const __grid
 
 // ---- multi-GPU persistent kernel --------------------------------------------------------------------------------------
 // Classes stay sharded per rank; the state (theta) is replicated; transcript t is OWNED by rank t / S (S = ceil(M/G)).
-// One iteration:
-//   P1 (local classes, local theta replica)                                   -> grid barrier
-//   P2-partial: every locally active transcript's share of alpha' is PUSHED (remote store over NVLink) into row
-//     `rank` of its owner's recv matrix while the phase runs; locally inactive transcripts contribute their constant
-//     folded singleton mass, delivered once before the loop                    -> exchange barrier 1
-//   owner phase: rank r sums its slice over the G recv rows in rank order, applies the update (convergence terms,
-//     digamma / exp) for M/G transcripts only, keeps alpha, and pushes theta' of the slice into every rank's replica;
-//     its {max rel diff, sum(alpha'+prior)} go to every rank's aux slots      -> exchange barrier 2
-//   every rank reads the G aux pairs in rank order: identical convergence decision and logNorm everywhere.
-// Exchange barrier = system-scope fence, grid barrier, block 0 pushes the epoch into each peer's flag slot
-// (st.release.sys) and polls its own slots (ld.acquire.sys), grid barrier.  Against round 1 (partials pulled by
-// remote loads, a redundant update of all M transcripts on every rank, alpha and theta re-broadcast): no remote load is
-// on the critical path, the digamma work is 1/G per rank, and 8 bytes per transcript travel each way.
+// One iteration (three grid barriers; NO exchange barrier and no system-scope fence):
+//   P1 (local classes, local plain copy of theta)                                                    -> grid barrier
+//   P2-partial: every transcript's local share of alpha' (locally inactive ones: their constant folded singleton mass)
+//     into a local buffer                                                                              -> grid barrier
+//   push: the buffer goes to the owners as flagged lines, row `rank` of the owner's llrecv, in transcript order
+//   owner phase: rank r polls the G lines of each transcript of its slice (they arrive as the peers' P2 proceeds), sums
+//     them in rank order, applies the update (convergence terms, digamma / exp) for M/G transcripts only, keeps alpha,
+//     writes theta' into its own plain copy and pushes it as a flagged line into every peer's llth; every block pushes
+//     its {sum(alpha'+prior), max rel diff} into every rank's llaux
+//   unpack: every rank polls the llth lines of the other slices into its plain theta; block 0 polls the G x grid aux
+//     pairs and reduces them in (rank, block) order -> identical logNorm / convergence decision everywhere  -> grid barrier
+// Round 1 pulled the partials with remote loads between two exchange barriers (system fence + grid barrier + flag
+// round trip + grid barrier, every thread fencing at system scope): +41 us per iteration at N=2, +94 us at N=8.
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -613,8 +620,48 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
   asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+// flagged line: {lo32, epoch, hi32, epoch}; each 8-byte half is single-copy atomic
+__device__ __forceinline__ void ll_store(uint4* line, double v, uint32_t epoch) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"((uint32_t)b), "r"(epoch),
+               "r"((uint32_t)(b >> 32)), "r"(epoch)
+               : "memory");
+}
+__device__ __forceinline__ bool ll_try_load(const uint4* line, uint32_t epoch, double& v) {
+  uint4 q;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(line) : "memory");
+  v = __longlong_as_double((long long)(((unsigned long long)q.z << 32) | q.x));
+  return q.y == epoch && q.w == epoch;
+}
+__device__ __forceinline__ double ll_wait(const uint4* line, uint32_t epoch, uint32_t* fail);
+__device__ __forceinline__ uint4 ll_load_raw(const uint4* line) {
+  uint4 q;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(line) : "memory");
+  return q;
+}
+// value of a line whose first copy `q` is already in registers (so that a thread can put several polls in flight
+// before it looks at any of them); re-polls while the flags are stale
+__device__ __forceinline__ double ll_finish(const uint4* line, uint4 q, uint32_t epoch, uint32_t* fail) {
+  if (q.y != epoch || q.w != epoch) return ll_wait(line, epoch, fail);
+  return __longlong_as_double((long long)(((unsigned long long)q.z << 32) | q.x));
+}
+
+__device__ __forceinline__ double ll_wait(const uint4* line, uint32_t epoch, uint32_t* fail) {
+  double v;
+  if (ll_try_load(line, epoch, v)) return v;
+  const unsigned long long t0 = gtime_ns();
+  for (uint32_t spins = 0;; ++spins) {
+    __nanosleep(spins < 4 ? 100u : 400u);    // thousands of pollers: leave the L2 to the lines that are still arriving
+    if (ll_try_load(line, epoch, v)) return v;
+    if ((spins & 63u) == 63u) {
+      if (*reinterpret_cast<volatile uint32_t*>(fail)) return 0.0;
+      if (gtime_ns() - t0 > 20000000000ull) { *fail = 1u; return 0.0; }
+    }
+  }
+}
+// end-of-run barrier over all GPUs.  Only the signalling threads fence at system scope (st.release.sys): the other
+// threads' remote stores happen-before it through the gpu-scope grid barrier, and release is cumulative.
 __device__ __forceinline__ void xgpu_barrier(cg::grid_group& grid, const EmArgs& A, unsigned long long epoch) {
-  __threadfence_system();
   grid.sync();
   if (blockIdx.x == 0 && threadIdx.x < A.nranks) {
     const uint32_t q = threadIdx.x;
@@ -628,14 +675,14 @@ __device__ __forceinline__ void xgpu_barrier(cg::grid_group& grid, const EmArgs&
   grid.sync();
 }
 
-struct DeliverPush {           // fused path: into row `rank` of the owner's recv matrix
+struct DeliverPush {           // fused path: a flagged line into row `rank` of the owner's llrecv
   unsigned char* const* peers;
-  size_t off_recv;
-  uint32_t S, rank;
+  size_t off_llrecv;
+  uint32_t S, rank, epoch;
   __device__ __forceinline__ void operator()(uint32_t t, double v) const {
     const uint32_t owner = t / S;
-    double* dst = reinterpret_cast<double*>(peers[owner] + off_recv) + (size_t)rank * S + (t - owner * S);
-    st_relaxed_sys_f64(dst, v);
+    uint4* dst = reinterpret_cast<uint4*>(peers[owner] + off_llrecv) + (size_t)rank * S + (t - owner * S);
+    ll_store(dst, v, epoch);
   }
 };
 
@@ -655,81 +702,145 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent_mgpu(const _
   const XchgLayout X(M, G);
   const uint32_t S = X.S, lo = min(A.rank * S, M), hi = min(lo + S, M);
   unsigned char* const own = A.peers[A.rank];
-  const double* my_recv = reinterpret_cast<const double*>(own + X.off_recv());
-  const DeliverPush push{A.peers, X.off_recv(), S, A.rank};
-  unsigned long long epoch = A.epoch0;
+  const uint4* my_recv = reinterpret_cast<const uint4*>(own + X.off_llrecv());
+  const uint4* my_llth = reinterpret_cast<const uint4*>(own + X.off_llth());
+  const uint4* my_aux = reinterpret_cast<const uint4*>(own + X.off_llaux());
+  double* theta = A.theta;                   // = own + off_theta: the plain copy P1 gathers from
   uint32_t it = 0;
   bool converged = false;
   double logNorm = VBEM ? digamma_pos(A.sum0) : 0.0;
   ring_prefetch(A.cm, W, R1);
-  // once: the constant share of the locally INACTIVE transcripts (their folded singleton classes; 0 elsewhere) --
-  // active rows overwrite their slot in every P2-partial.  part_out holds base[t] for inactive t, 0 for active t.
-  for (uint32_t t = gtid; t < M; t += gthreads) push(t, A.part_out[t]);
   while (it < A.min_iter || (it < A.max_iter && !converged)) {
     const uint32_t par = it & 1u;
+    const uint32_t epoch = (uint32_t)(A.epoch0 + it + 1ull);
+    const DeliverPush push{A.peers, X.off_llrecv(), S, A.rank, epoch};
     const bool dbg_acc = A.dbg && A.dbg_it == DBG_ACCUMULATE && it > 0;
     P2Acc pa{0.0, 0.0};
+    SB_DBG(0)
     SB_ACC_BEGIN(t1, 3)
     run_phase<1, CH, RING, VBEM, true>(A, W, R1, bid, nblk, 0.0, 0.0, pa, NoDeliver{});
     SB_ACC_END(t1, 0)
+    SB_DBG(1)
     ring_prefetch(A.tm, W, R2);
     grid.sync();
+    SB_DBG(2)
     if (bid == 0 && threadIdx.x == 0) A.lq[0] = 0u;
     SB_ACC_BEGIN(t2, 4)
-    run_phase<3, CH, RING, VBEM, true>(A, W, R2, bid, nblk, 0.0, 0.0, pa, push);
-    SB_ACC_END(t2, 1)
-    ring_prefetch(A.cm, W, R1);
-    xgpu_barrier(grid, A, ++epoch);                            // every rank's partials have landed at their owners
-    if (bid == 0 && threadIdx.x == 0) A.lq[1] = 0u;
-    if (*reinterpret_cast<volatile uint32_t*>(A.xfail)) break;
-    // ---- owner phase: my slice [lo, hi)
+    if (A.push_pass) {
+      // this rank's share of alpha' per transcript id into the local buffer (locally inactive transcripts keep their
+      // constant folded singleton mass, written once per run by the host) ...
+      run_phase<3, CH, RING, VBEM, true>(A, W, R2, bid, nblk, 0.0, 0.0, pa, DeliverLocal{A.part_out});
+      SB_ACC_END(t2, 1)
+      SB_DBG(3)
+      ring_prefetch(A.cm, W, R1);
+      __threadfence();
+      grid.sync();
+      if (bid == 0 && threadIdx.x == 0) A.lq[1] = 0u;
+      // ... and from there to the owners in transcript order: consecutive threads write consecutive 16-byte lines,
+      // i.e. whole 512-byte runs per warp over NVLink.  Measured (scripts/timeline_mgpu.py): at N=8 the pushes from
+      // the row epilogues below -- 32 scattered remote stores per warp instruction -- cost +10 us of P2, this pass
+      // is 6 us faster per iteration; at N=2 it is the other way round (one destination: 65 vs 45 us), so the host
+      // picks the pass for more than two ranks.
+      for (uint32_t t = gtid; t < M; t += gthreads) push(t, __ldcg(&A.part_out[t]));
+    } else {
+      // straight from the row epilogues; locally inactive transcripts (constant share) first
+      for (uint32_t t = gtid; t < M; t += gthreads)
+        if (__ldg(&A.tid_row[t]) == 0xffffffffu) push(t, __ldg(&A.base[t]));
+      run_phase<3, CH, RING, VBEM, true>(A, W, R2, bid, nblk, 0.0, 0.0, pa, push);
+      SB_ACC_END(t2, 1)
+      SB_DBG(3)
+      ring_prefetch(A.cm, W, R1);
+    }
+    // ---- owner phase: my slice [lo, hi); the lines are polled as they arrive
     const double bias = (it == 0) ? A.first_bias : 0.0;
     double sum = 0.0, mx = 0.0;
     for (uint32_t t = lo + gtid; t < hi; t += gthreads) {
       double na = bias;
-      for (uint32_t q = 0; q < G; ++q) na += __ldcg(&my_recv[(size_t)q * S + (t - lo)]);
+      for (uint32_t q0 = 0; q0 < G; q0 += 8) {                 // up to 8 polls in flight, summed in rank order
+        uint4 ln[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (q0 + j < G) ln[j] = ll_load_raw(&my_recv[(size_t)(q0 + j) * S + (t - lo)]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (q0 + j < G) na += ll_finish(&my_recv[(size_t)(q0 + j) * S + (t - lo)], ln[j], epoch, A.xfail);
+      }
       const double old = A.alpha[t];
       if (na > ALPHA_CHECK_CUTOFF) mx = fmax(mx, fabs(old - na) / na);
       A.alpha[t] = na;
       const double ap = na + A.prior[t];
       sum += ap;
       const double th = theta_of<VBEM>(na, ap, logNorm);
+      theta[t] = th;
       for (uint32_t q = 0; q < G; ++q)
-        st_relaxed_sys_f64(reinterpret_cast<double*>(A.peers[q] + X.off_theta()) + t, th);
+        if (q != A.rank) ll_store(reinterpret_cast<uint4*>(A.peers[q] + X.off_llth()) + t, th, epoch);
     }
+    SB_DBG(4)
     {
       const double bs = block_reduce<false>(sum, scratch);
       const double bm = block_reduce<true>(mx, scratch);
+      if (threadIdx.x < G) {                                   // this block's pair -> every rank's aux area
+        uint4* aux = reinterpret_cast<uint4*>(A.peers[threadIdx.x] + X.off_llaux()) + ((size_t)A.rank * XAUX + bid) * 2;
+        ll_store(aux, bs, epoch);
+        ll_store(aux + 1, fmax(bm, 0.0), epoch);
+      }
+    }
+    // ---- unpack: the other slices' theta into my plain copy
+    for (uint32_t t0 = gtid; t0 < M; t0 += 4 * gthreads) {       // four polls in flight per thread
+      uint4 ln[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t t = t0 + j * gthreads;
+        if (t < M && (t < lo || t >= hi)) ln[j] = ll_load_raw(&my_llth[t]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t t = t0 + j * gthreads;
+        if (t < M && (t < lo || t >= hi)) theta[t] = ll_finish(&my_llth[t], ln[j], epoch, A.xfail);
+      }
+    }
+    SB_DBG(5)
+    if (bid == 0) {                                            // (rank, block) order: identical on every rank
+      double s2 = 0.0, m2 = 0.0;
+      for (uint32_t i0 = threadIdx.x; i0 < G * nblk; i0 += 4 * EM_THREADS) {   // four pairs in flight per thread
+        uint4 ls[4], lm[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t i = i0 + j * EM_THREADS;
+          if (i < G * nblk) {
+            const uint32_t q = i / nblk, b = i - q * nblk;
+            ls[j] = ll_load_raw(&my_aux[((size_t)q * XAUX + b) * 2]);
+            lm[j] = ll_load_raw(&my_aux[((size_t)q * XAUX + b) * 2 + 1]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t i = i0 + j * EM_THREADS;
+          if (i < G * nblk) {
+            const uint32_t q = i / nblk, b = i - q * nblk;
+            s2 += ll_finish(&my_aux[((size_t)q * XAUX + b) * 2], ls[j], epoch, A.xfail);
+            m2 = fmax(m2, ll_finish(&my_aux[((size_t)q * XAUX + b) * 2 + 1], lm[j], epoch, A.xfail));
+          }
+        }
+      }
+      s2 = block_reduce<false>(s2, scratch);
+      m2 = block_reduce<true>(m2, scratch);
       if (threadIdx.x == 0) {
-        A.sum_partial[(size_t)par * nblk + bid] = bs;
-        if (bm > 0.0) atomicMax(&A.maxrel[par], (unsigned long long)__double_as_longlong(bm));
+        A.sum_partial[par] = s2;
+        A.maxrel[par] = (unsigned long long)__double_as_longlong(m2);
       }
     }
     __threadfence();
     grid.sync();
-    if (bid == 0) {                                            // my slice's pair -> every rank's aux slot
-      const double ssum = sum_partials(A.sum_partial + (size_t)par * nblk, nblk, 0.0, scratch);
-      if (threadIdx.x < G) {
-        double* aux = reinterpret_cast<double*>(A.peers[threadIdx.x] + X.off_aux()) + ((size_t)par * 64 + A.rank) * 2;
-        st_relaxed_sys_f64(aux, __longlong_as_double((long long)__ldcg(&A.maxrel[par])));
-        st_relaxed_sys_f64(aux + 1, ssum);
-      }
-      if (threadIdx.x == 0) A.maxrel[par ^ 1u] = 0ull;         // re-arm the other slot for the next iteration
-    }
-    xgpu_barrier(grid, A, ++epoch);                            // every slice's theta / aux pair is everywhere
+    SB_DBG(6)
+    if (!A.push_pass && bid == 0 && threadIdx.x == 0) A.lq[1] = 0u;
     if (*reinterpret_cast<volatile uint32_t*>(A.xfail)) break;
     {
-      const double* aux = reinterpret_cast<const double*>(own + X.off_aux()) + (size_t)par * 64 * 2;
-      double mr = 0.0, tot = 0.0;
-      for (uint32_t q = 0; q < G; ++q) {                       // rank order: identical on every rank
-        mr = fmax(mr, __ldcg(&aux[2 * q]));
-        tot += __ldcg(&aux[2 * q + 1]);
-      }
+      const double mr = __longlong_as_double((long long)__ldcg(&A.maxrel[par]));
       converged = !(mr > A.tol);
-      if (VBEM) logNorm = digamma_pos(tot);
-      // the host reads the GLOBAL value from this iteration's slot (re-armed two iterations from now)
-      if (bid == 0 && threadIdx.x == 0) A.maxrel[par] = (unsigned long long)__double_as_longlong(mr);
+      if (VBEM) logNorm = digamma_pos(__ldcg(&A.sum_partial[par]));
     }
+    SB_DBG(7)
     if (dbg_acc && (threadIdx.x & 31u) == 0) A.dbg[(size_t)gwarp * 8 + 2] += 1ull;
     ++it;
   }
@@ -738,12 +849,12 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent_mgpu(const _
     const double a = A.alpha[t];
     for (uint32_t q = 0; q < G; ++q) st_relaxed_sys_f64(reinterpret_cast<double*>(A.peers[q] + X.off_alpha()) + t, a);
   }
-  xgpu_barrier(grid, A, ++epoch);
+  xgpu_barrier(grid, A, A.epoch0 + it + 1ull);
   if (bid == 0 && threadIdx.x == 0) {
     A.out[0] = it;
     A.out[1] = converged ? 1u : 0u;
     A.out[2] = (it - 1) & 1u;
-    A.out[3] = (uint32_t)(epoch - A.epoch0);
+    A.out[3] = it + 2u;                       // epochs consumed
   }
   ring_drain(W, R1);
 }

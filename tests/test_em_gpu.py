@@ -187,14 +187,16 @@ def test_full_size_properties(ctx, oracle):
     assert stc.converged == 1 and stc.max_rel_diff <= 0.01
 
 
+@pytest.mark.parametrize("push_pass", [0, 1])
 @pytest.mark.parametrize("vbem", [1, 0])
-def test_fused_multi_gpu_kernel_loopback(oracle, vbem):
+def test_fused_multi_gpu_kernel_loopback(oracle, vbem, push_pass):
     """k_em_persistent_mgpu on ONE GPU that is its own peer: pushes to the owner's recv rows, owner update, theta
     broadcast, exchange barriers, final alpha all-gather -- against the oracle (the 2-GPU run is scripts/check_multigpu.py)."""
     eq, proj, eff, uniq = synth_eq(seed=5, C=40000, M=9000, total_count=900000)
     c = EMContext(0)
     try:
         c.peer_loopback(eq.n_txps)
+        c.set_option("push_pass", push_pass)    # both ways of getting the partials to their owners
         for k in (1, 2, 25):
             p = default_params(use_vbem=vbem, min_iter=k, max_iter=k)
             alpha, st, ok = c.optimize(eq, p, proj, eff, uniq)
@@ -202,6 +204,7 @@ def test_fused_multi_gpu_kernel_loopback(oracle, vbem):
             assert ok and st.iters == rst.iters == k
             assert_alpha(alpha, ref)
             assert abs(st.max_rel_diff - rst.max_rel_diff) <= 1e-9 * max(1.0, abs(rst.max_rel_diff))
+
         # convergence decision taken inside the kernel from the exchanged maxima
         p = default_params(use_vbem=vbem, min_iter=10, max_iter=400)
         alpha, st, ok = c.optimize(eq, p, proj, eff, uniq)
