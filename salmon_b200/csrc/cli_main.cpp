@@ -151,6 +151,7 @@ int cmd_quant(Args& a) {
   sb_quant_default_opts(&qo);
   auto num = [&](double& d) { if (!a.value(v)) return false; d = atof(v.c_str()); return true; };
   double d = 0;
+  bool vb_prior_given = false;
   while (a.more()) {
     const std::string o = a.next();
     if (o == "-i" || o == "--index") { if (!a.value(dir)) return usage(); }
@@ -169,7 +170,7 @@ int cmd_quant(Args& a) {
     else if (o == "--noGammaDraw") qo.no_gamma_draw = 1;
     else if (o == "--useEM") ep.use_vbem = 0;
     else if (o == "--useVBOpt") ep.use_vbem = 1;
-    else if (o == "--vbPrior") { if (!num(ep.vb_prior)) return usage(); }
+    else if (o == "--vbPrior") { if (!num(ep.vb_prior)) return usage(); vb_prior_given = true; }
     else if (o == "--perNucleotidePrior") ep.per_txp_prior = 0;
     else if (o == "--perTranscriptPrior") ep.per_txp_prior = 1;
     else if (o == "--initUniform") ep.init_uniform = 1;
@@ -205,6 +206,9 @@ int cmd_quant(Args& a) {
     } else { fprintf(stderr, "sb_salmon quant: unknown option %s\n", o.c_str()); return usage(); }
   }
   if (out.empty()) return usage();
+  // --perNucleotidePrior without an explicit --vbPrior: the reference switches the default to 1e-5
+  // (src/cli/QuantOptionsUtils.cpp:569-572)
+  if (ep.use_vbem && !ep.per_txp_prior && !vb_prior_given) ep.vb_prior = 1e-5;
   if (!eqfile.empty()) return quant_eqclasses(eqfile, out, ep, qo);
   if (dir.empty()) return usage();
   if (!unmated.empty() || m1.empty() || m1.size() != m2.size()) {

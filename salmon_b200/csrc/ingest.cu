@@ -663,6 +663,7 @@ extern "C" int sb_eq_file_read(const char* path, sb_eq_file** out) {
   auto bad = [&](const char* what) { sb::set_error("%s: %s", path, what); return SB_ERR_INVALID; };
   auto get_u64 = [&](uint64_t& v) {
     if (!tk.next(b, n)) return false;
+    if (n == 0 || *b == '-' || *b == '+') return false;     // strtoull would wrap a negative number
     char* endp = nullptr;
     v = strtoull(b, &endp, 10);
     return endp == b + n;
@@ -670,6 +671,10 @@ extern "C" int sb_eq_file_read(const char* path, sb_eq_file** out) {
   uint64_t numTxps = 0, numEq = 0;
   if (!get_u64(numTxps) || !get_u64(numEq)) return bad("missing transcript / class counts");
   if (numTxps > 0xffffffffull) return bad("too many transcripts");
+  // every name / class takes at least two bytes of the file: header values beyond that are corrupt (and would make
+  // the reservations below throw through the C boundary)
+  if (numTxps > text.size() / 2 + 1 || numEq > text.size() / 2 + 1) return bad("header counts exceed the file size");
+  try {
   S->names.reserve(numTxps);
   std::unordered_map<std::string, uint32_t> nameToIndex;
   nameToIndex.reserve(numTxps * 2);
@@ -743,6 +748,13 @@ extern "C" int sb_eq_file_read(const char* path, sb_eq_file** out) {
   P.n_missing_eff_len = (uint32_t)(numTxps - n_seen);
   *out = &S.release()->pub;
   return SB_OK;
+  } catch (const std::bad_alloc&) {
+    sb::set_error("%s: out of memory", path);
+    return SB_ERR_NOMEM;
+  } catch (const std::exception& ex) {
+    sb::set_error("%s: %s", path, ex.what());
+    return SB_ERR_INVALID;
+  }
 }
 
 extern "C" void sb_eq_file_free(sb_eq_file* f) {

@@ -8,6 +8,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <sys/stat.h>
+
 #include <algorithm>
 #include <parallel/algorithm>
 #include <vector>
@@ -233,6 +235,14 @@ extern "C" sb_index* sb_index_load(const char* path) {
   if (h.n_table == 0 || (h.n_table & (h.n_table - 1)) || h.k < 3 || h.k > 31 || h.first_decoy > h.n_txps) {
     fclose(f); sb::set_error("%s: corrupt header", path); return nullptr;
   }
+  {   // the arrays the header announces must fit in the file (a corrupt count must not drive the allocations)
+    struct stat stt;
+    const uint64_t need = (uint64_t)(h.n_txps + 1ull) * 8 + h.n_codes + (uint64_t)h.n_table * sizeof(TableEntry) +
+                          (uint64_t)h.n_post * sizeof(Posting) + h.names_bytes;
+    if (fstat(fileno(f), &stt) != 0 || need > (uint64_t)stt.st_size) {
+      fclose(f); sb::set_error("%s: truncated or corrupt index (the header announces more data than the file holds)", path); return nullptr;
+    }
+  }
   sb_index* ix = new sb_index();
   ix->n_txps = h.n_txps; ix->k = h.k; ix->n_kmers = h.n_kmers; ix->first_decoy = h.first_decoy;
   bool ok = true;
@@ -255,9 +265,19 @@ extern "C" sb_index* sb_index_load(const char* path) {
       }
       if (!ix->names.empty() && ix->names.size() != h.n_txps) ok = false;
       for (auto& n : ix->names) ix->name_ptrs.push_back(n.c_str());
-      ok = ok && ix->tx_off[h.n_txps] == h.n_codes;
+      ok = ok && ix->tx_off[h.n_txps] == h.n_codes && ix->tx_off[0] == 0;
+      for (uint32_t t = 0; t < h.n_txps && ok; ++t) ok = ix->tx_off[t] <= ix->tx_off[t + 1];   // monotonic offsets
+      // every table entry points inside the posting array, every posting inside its transcript (these go to the GPU)
+      for (size_t i = 0; i < ix->table.size() && ok; ++i) {
+        const TableEntry& e = ix->table[i];
+        if (e.key != EMPTY_KEY) ok = (uint64_t)e.off + e.cnt <= ix->post.size();
+      }
+      for (size_t i = 0; i < ix->post.size() && ok; ++i) {
+        const Posting& q = ix->post[i];
+        ok = q.tid < h.n_txps && (uint64_t)(q.tpos_rc & 0x7fffffffu) + h.k <= ix->tx_off[q.tid + 1] - ix->tx_off[q.tid];
+      }
     }
-  } catch (const std::bad_alloc&) { ok = false; }
+  } catch (const std::exception&) { ok = false; }   // bad_alloc, length_error from a corrupt count
   fclose(f);
   if (!ok) { delete ix; sb::set_error("%s: truncated or corrupt index", path); return nullptr; }
   return ix;

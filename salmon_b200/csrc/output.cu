@@ -32,10 +32,11 @@ extern "C" int sb_write_quant_sf(const char* path, uint32_t n, const char* const
   sb_tpm(n, alpha, eff_len, num_mapped_frags, tpm.data());
   FILE* f = fopen(path, "w");
   if (!f) { sb::set_error("cannot open %s", path); return SB_ERR_INVALID; }
-  fprintf(f, "Name\tLength\tEffectiveLength\tTPM\tNumReads\n");
-  for (uint32_t i = 0; i < n; ++i)
-    fprintf(f, "%s\t%u\t%.*f\t%f\t%.*f\n", names[i], complete_len[i], sig_digits, eff_len[i], tpm[i], sig_digits, alpha[i]);
-  fclose(f);
+  bool ok = fprintf(f, "Name\tLength\tEffectiveLength\tTPM\tNumReads\n") > 0;
+  for (uint32_t i = 0; i < n && ok; ++i)
+    ok = fprintf(f, "%s\t%u\t%.*f\t%f\t%.*f\n", names[i], complete_len[i], sig_digits, eff_len[i], tpm[i], sig_digits, alpha[i]) > 0;
+  ok = (fclose(f) == 0) && ok;     // a full disk shows up here at the latest
+  if (!ok) { sb::set_error("write error on %s", path); return SB_ERR_INVALID; }
   return SB_OK;
 }
 
@@ -47,8 +48,18 @@ struct Sink {   // plain or gzip text sink
     if (L > 3 && !strcmp(path + L - 3, ".gz")) g = gzopen(path, "wb"); else f = fopen(path, "w");
     return f || g;
   }
-  void put(const std::string& s) { if (g) gzwrite(g, s.data(), (unsigned)s.size()); else fwrite(s.data(), 1, s.size(), f); }
-  void close() { if (g) gzclose(g); if (f) fclose(f); }
+  bool ok = true;
+  void put(const std::string& s) {
+    if (s.empty()) return;
+    if (g) ok = ok && gzwrite(g, s.data(), (unsigned)s.size()) == (int)s.size();
+    else ok = ok && fwrite(s.data(), 1, s.size(), f) == s.size();
+  }
+  bool close() {
+    if (g) ok = (gzclose(g) == Z_OK) && ok;
+    if (f) ok = (fclose(f) == 0) && ok;
+    g = nullptr; f = nullptr;
+    return ok;
+  }
 };
 }  // namespace
 
@@ -92,6 +103,6 @@ extern "C" int sb_write_eq_classes(const char* path, uint32_t n_txps, const char
       out.put(s);
     }
   }
-  out.close();
+  if (!out.close()) { sb::set_error("write error on %s", path); return SB_ERR_INVALID; }
   return SB_OK;
 }

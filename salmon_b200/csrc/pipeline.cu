@@ -390,7 +390,8 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
       std::string nm;
       for (uint32_t t = 0; t < M; ++t) { nm += names[t]; nm += (t + 1 < M) ? '\t' : '\n'; }
       gzFile g = gzopen((outs + "/aux_info/bootstrap/names.tsv.gz").c_str(), "wb");
-      if (g) { gzwrite(g, nm.data(), (unsigned)nm.size()); gzclose(g); }
+      const bool wrote = g && gzwrite(g, nm.data(), (unsigned)nm.size()) == (int)nm.size();
+      if (!g || (gzclose(g) != Z_OK) || !wrote) { sb::set_error("write error on %s/aux_info/bootstrap/names.tsv.gz", outs.c_str()); return fail(SB_ERR_INVALID); }
     }
   }
   if (alpha_out) memcpy(alpha_out, alpha.data(), (size_t)M * 8);
