@@ -344,6 +344,37 @@ int sb_map_partial_get(sb_map_ctx* ctx, sb_map_partial* out);
 int sb_map_project_global(sb_map_ctx* ctx, const sb_map_partial* global_stats, uint32_t n_ranks,
                           const uint32_t* roots_all /* n_ranks x n_txps */, sb_map_result* out);
 
+/* ---- B2: the equivalence-class builder on its own -----------------------------------------------------------------
+ * Replaces `void EquivalenceClassBuilder<TGValue>::addGroup(TranscriptGroup&&, std::vector<double>& weights)`,
+ * `bool finish()` and `eqVec()` (include/salmon/internal/quant/EquivalenceClassBuilder.hpp:237-250,165-181,210-223;
+ * callers src/quant/SalmonQuantify.cpp:855-856,2641) for a caller that forms the labels itself, and the table that
+ * `--eqclasses` reads (readEquivCounts, src/util/SalmonUtils.cpp:1024-1122).  Host buffers in, host CSR out (owned by
+ * the builder, valid until the next finish / destroy); the aggregation runs on the device (label hash -> radix sort ->
+ * segmented reduce, the kernels sb_map_batch uses for its own reads).  sb_map_batch / sb_map_finish keep doing this
+ * internally for reads mapped by the library. */
+typedef struct sb_eq_builder sb_eq_builder;
+typedef struct sb_eq_table {
+  uint64_t n_classes;
+  uint32_t n_txps, reserved;
+  const uint64_t* off;             /* [n_classes+1] into tids / weights */
+  const uint32_t* tids;            /* transcript part of every label */
+  const double* weights;           /* normalised to sum 1 per class (TGValue::normalizeAux, :114-123) */
+  const uint64_t* counts;
+  const uint32_t* n_txp_in_label;  /* [n_classes] */
+  const uint64_t* label_off;       /* [n_classes+1] into labels: the full labels (transcripts + range-factorisation bins) */
+  const uint32_t* labels;
+  uint64_t n_groups;               /* addGroup calls so far */
+} sb_eq_table;
+sb_eq_builder* sb_eq_create(uint32_t n_txps, int device);
+void sb_eq_destroy(sb_eq_builder* b);
+/* addGroup x n: label i = labels[label_off[i] .. label_off[i+1]) (transcript ids, optionally followed by as many
+ * range-factorisation bins), weights[weight_off[i] .. weight_off[i+1]) one per transcript; counts NULL = 1 each. */
+int sb_eq_add_batch(sb_eq_builder* b, uint32_t n_groups, const uint64_t* label_off, const uint32_t* labels,
+                    const uint64_t* weight_off, const double* weights, const uint64_t* counts);
+/* a finished table (e.g. sb_eq_file_read's) as one batch */
+int sb_eq_from_host(sb_eq_builder* b, const sb_eq_csr* eq);
+int sb_eq_finish(sb_eq_builder* b, sb_eq_table* out);
+
 /* Forget everything mapped so far (class tables, online state, counters) without re-allocating. */
 int sb_map_reset(sb_map_ctx* ctx);
 /* finish(): merge batch tables, normalise weights, return the CSR (feeds sb_em_optimize). */

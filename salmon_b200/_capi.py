@@ -203,6 +203,11 @@ SYMBOLS = {
     "sb_map_batch": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, C.POINTER(sb_map_batch_stats)]),
     "sb_map_finish": (C.c_int, [_P, C.POINTER(sb_map_result)]),
     "sb_map_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "sb_eq_create": (_P, [C.c_uint32, C.c_int]),
+    "sb_eq_destroy": (None, [_P]),
+    "sb_eq_add_batch": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P, _P]),
+    "sb_eq_from_host": (C.c_int, [_P, C.POINTER(sb_eq_csr)]),
+    "sb_eq_finish": (C.c_int, [_P, _P]),
     "sb_map_online_state": (C.c_int, [_P, _P, _P, _P, _P]),
     "sb_map_reset": (C.c_int, [_P]),
     "sb_tpm": (C.c_int, [C.c_uint32, _P, _P, C.c_double, _P]),
@@ -249,6 +254,57 @@ def default_params(**over) -> sb_em_params:
             raise AttributeError(k)
         setattr(p, k, v)
     return p
+
+
+class sb_eq_table(C.Structure):
+    _fields_ = [("n_classes", C.c_uint64), ("n_txps", C.c_uint32), ("reserved", C.c_uint32), ("off", C.c_void_p),
+                ("tids", C.c_void_p), ("weights", C.c_void_p), ("counts", C.c_void_p), ("n_txp_in_label", C.c_void_p),
+                ("label_off", C.c_void_p), ("labels", C.c_void_p), ("n_groups", C.c_uint64)]
+
+
+class EqBuilder:
+    """B2 seam: EquivalenceClassBuilder::addGroup / finish through the C ABI (sb_eq_*)."""
+
+    def __init__(self, n_txps: int, device: int = 0):
+        self.lib = load()
+        self.h = self.lib.sb_eq_create(int(n_txps), int(device))
+        if not self.h:
+            raise SalmonB200Error(f"sb_eq_create: {self.lib.sb_last_error().decode()}")
+        self.n_txps = n_txps
+
+    def add_batch(self, label_off, labels, weight_off, weights, counts=None):
+        label_off = np.ascontiguousarray(label_off, dtype=np.uint64); labels = np.ascontiguousarray(labels, dtype=np.uint32)
+        weight_off = np.ascontiguousarray(weight_off, dtype=np.uint64); weights = np.ascontiguousarray(weights, dtype=np.float64)
+        cp = None
+        if counts is not None:
+            counts = np.ascontiguousarray(counts, dtype=np.uint64); cp = counts.ctypes.data
+        _check(self.lib.sb_eq_add_batch(self.h, len(label_off) - 1, label_off.ctypes.data, labels.ctypes.data,
+                                        weight_off.ctypes.data, weights.ctypes.data, cp), "sb_eq_add_batch")
+
+    def from_host(self, eq):
+        st = eq.as_struct()
+        _check(self.lib.sb_eq_from_host(self.h, C.byref(st)), "sb_eq_from_host")
+
+    def finish(self):
+        t = sb_eq_table()
+        _check(self.lib.sb_eq_finish(self.h, C.byref(t)), "sb_eq_finish")
+        n = int(t.n_classes)
+
+        def arr(ptr, dt, k):
+            if k == 0:
+                return np.zeros(0, dtype=dt)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(k,)).copy()
+        off = arr(t.off, np.uint64, n + 1) if n else np.zeros(1, dtype=np.uint64)
+        loff = arr(t.label_off, np.uint64, n + 1) if n else np.zeros(1, dtype=np.uint64)
+        nnz, nl = int(off[-1]), int(loff[-1])
+        return dict(off=off, tids=arr(t.tids, np.uint32, nnz), weights=arr(t.weights, np.float64, nnz),
+                    counts=arr(t.counts, np.uint64, n), ntx=arr(t.n_txp_in_label, np.uint32, n), label_off=loff,
+                    labels=arr(t.labels, np.uint32, nl), n_groups=int(t.n_groups))
+
+    def close(self):
+        if self.h:
+            self.lib.sb_eq_destroy(self.h)
+            self.h = None
 
 
 @dataclass

@@ -1681,3 +1681,173 @@ extern "C" int sb_map_online_state(sb_map_ctx* c, double* mass_out, double* hist
   }
   return SB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// B2: the equivalence-class builder as a seam of its own.  Replaces
+//   void EquivalenceClassBuilder<TGValue>::addGroup(TranscriptGroup&&, std::vector<double>& weights)
+//   bool finish();  std::vector<std::pair<const TranscriptGroup, TGValue>>& eqVec()
+// (include/salmon/internal/quant/EquivalenceClassBuilder.hpp:237-250,165-181,210-223) for callers that produce the
+// labels themselves (e.g. the reference's own mapping loop, SalmonQuantify.cpp:855-856, or `--eqclasses`,
+// SalmonUtils.cpp:1024-1122): groups arrive in batches from the host, are hashed / sorted / reduced on the device with
+// the kernels sb_map_batch uses for its own reads, and finish() hands back the CSR sb_em_optimize takes.
+// ---------------------------------------------------------------------------------------------
+struct sb_eq_builder {
+  sb_map_ctx* c = nullptr;          // only stream, aggregation scratch and arena are used
+  uint32_t n_txps = 0;
+  uint64_t n_groups = 0;
+  // device staging of one batch
+  uint64_t cap_n = 0, cap_l = 0, cap_w = 0;
+  uint64_t *d_loff = nullptr, *d_woff = nullptr, *d_counts = nullptr;
+  uint32_t* d_labels = nullptr;
+  double* d_weights = nullptr;
+  // host result
+  std::vector<uint64_t> h_off, h_counts, h_label_off;
+  std::vector<uint32_t> h_tids, h_ntx, h_labels;
+  std::vector<double> h_w;
+};
+
+extern "C" sb_eq_builder* sb_eq_create(uint32_t n_txps, int device) {
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) { cudaGetLastError(); sb::set_error("no CUDA device available"); return nullptr; }
+  if (device < 0 || device >= n_dev) { sb::set_error("device %d out of range", device); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { sb::set_error("cudaSetDevice failed"); return nullptr; }
+  sb_eq_builder* b = new sb_eq_builder();
+  b->c = new sb_map_ctx();
+  b->c->device = device;
+  b->n_txps = n_txps;
+  if (cudaStreamCreate(&b->c->stream) != cudaSuccess) { sb::set_error("cudaStreamCreate failed"); delete b->c; delete b; return nullptr; }
+  return b;
+}
+
+extern "C" void sb_eq_destroy(sb_eq_builder* b) {
+  if (!b) return;
+  cudaSetDevice(b->c->device);
+  cudaFree(b->d_loff); cudaFree(b->d_woff); cudaFree(b->d_counts); cudaFree(b->d_labels); cudaFree(b->d_weights);
+  sb_map_destroy(b->c);
+  delete b;
+}
+
+namespace {
+__global__ void k_eq_records(uint32_t n, const uint64_t* __restrict__ loff, const uint64_t* __restrict__ woff,
+                             uint64_t* __restrict__ lstart, uint32_t* __restrict__ llen, uint64_t* __restrict__ wstart,
+                             uint32_t* __restrict__ wlen) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  lstart[i] = loff[i]; llen[i] = (uint32_t)(loff[i + 1] - loff[i]);
+  wstart[i] = woff[i]; wlen[i] = (uint32_t)(woff[i + 1] - woff[i]);
+}
+template <typename T>
+int regrow(T** p, uint64_t* cap, uint64_t need) {
+  if (need <= *cap) return SB_OK;
+  cudaFree(*p);
+  *p = nullptr;
+  const uint64_t c = std::max<uint64_t>(need + need / 2, 1024);
+  SB_CUDA(cudaMalloc(p, c * sizeof(T)));
+  *cap = c;
+  return SB_OK;
+}
+}  // namespace
+
+// n groups: label i = labels[label_off[i] .. label_off[i+1]) -- transcript ids (ascending, as TranscriptGroup holds them),
+// optionally followed by the same number of range-factorisation bins -- and weights[weight_off[i] .. weight_off[i+1])
+// (one per transcript of the label).  counts == NULL: every group counts once (addGroup); else counts[i] fragments.
+extern "C" int sb_eq_add_batch(sb_eq_builder* b, uint32_t n, const uint64_t* label_off, const uint32_t* labels,
+                               const uint64_t* weight_off, const double* weights, const uint64_t* counts) {
+  if (!b || (n && (!label_off || !labels || !weight_off || !weights))) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  if (n == 0) return SB_OK;
+  const uint64_t nl = label_off[n], nw = weight_off[n];
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint64_t ll = label_off[i + 1] - label_off[i], wl = weight_off[i + 1] - weight_off[i];
+    if (label_off[i + 1] < label_off[i] || weight_off[i + 1] < weight_off[i] || wl == 0 || (ll != wl && ll != 2 * wl)) {
+      sb::set_error("sb_eq_add_batch: group %u: label of %llu entries with %llu weights", i, (unsigned long long)ll, (unsigned long long)wl);
+      return SB_ERR_INVALID;
+    }
+    for (uint64_t j = 0; j < wl; ++j)
+      if (labels[label_off[i] + j] >= b->n_txps) { sb::set_error("sb_eq_add_batch: transcript id out of range in group %u", i); return SB_ERR_INVALID; }
+  }
+  sb_map_ctx* c = b->c;
+  SB_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  uint64_t cn = b->cap_n, cn2 = b->cap_n, cn3 = b->cap_n;
+  SB_TRY(regrow(&b->d_loff, &cn, (uint64_t)n + 1)); SB_TRY(regrow(&b->d_woff, &cn2, (uint64_t)n + 1));
+  SB_TRY(regrow(&b->d_counts, &cn3, (uint64_t)n + 1));
+  b->cap_n = std::min(cn, std::min(cn2, cn3));
+  SB_TRY(regrow(&b->d_labels, &b->cap_l, nl));
+  SB_TRY(regrow(&b->d_weights, &b->cap_w, nw));
+  SB_CUDA(cudaMemcpyAsync(b->d_loff, label_off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(b->d_woff, weight_off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(b->d_labels, labels, nl * 4, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(b->d_weights, weights, nw * 8, cudaMemcpyHostToDevice, st));
+  if (counts) SB_CUDA(cudaMemcpyAsync(b->d_counts, counts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  SB_TRY(agg_reserve(c->agg, n));
+  AggScratch& a = c->agg;
+  k_eq_records<<<nblk(n, 256), 256, 0, st>>>(n, b->d_loff, b->d_woff, a.lstart, a.llen, a.wstart, a.wlen);
+  Records R{n, a.lstart, a.llen, a.wstart, a.wlen, b->d_labels, b->d_weights, counts ? b->d_counts : nullptr};
+  EqStore s;
+  SB_TRY(aggregate(c, R, s));
+  SB_CUDA(cudaStreamSynchronize(st));       // the staging buffers are reused by the next batch
+  c->stores.push_back(s);
+  b->n_groups += n;
+  return SB_OK;
+}
+
+// --eqclasses (readEquivCounts, SalmonUtils.cpp:1024-1122): a finished table -- weights per class, counts -- as one batch
+extern "C" int sb_eq_from_host(sb_eq_builder* b, const sb_eq_csr* eq) {
+  if (!b || !eq) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  if (eq->n_txps != b->n_txps) { sb::set_error("sb_eq_from_host: transcript count mismatch"); return SB_ERR_INVALID; }
+  if (eq->n_classes >= (1ull << 31)) { sb::set_error("sb_eq_from_host: too many classes"); return SB_ERR_INVALID; }
+  return sb_eq_add_batch(b, (uint32_t)eq->n_classes, eq->off, eq->tids, eq->off, eq->weights, eq->counts);
+}
+
+// finish(): merge the batch tables (same label -> one class: counts add, weights add in batch order), normalise the
+// weights of every class to sum 1 (TGValue::normalizeAux, EquivalenceClassBuilder.hpp:114-123).
+extern "C" int sb_eq_finish(sb_eq_builder* b, sb_eq_table* out) {
+  if (!b || !out) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  sb_map_ctx* c = b->c;
+  SB_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  uint64_t n = 0;
+  for (auto& s : c->stores) n += s.n;
+  if (n >= (1ull << 31)) { sb::set_error("sb_eq_finish: too many batch classes"); return SB_ERR_INVALID; }
+  EqStore merged;
+  Arena& ar = c->arena;
+  const uint64_t mark_l = ar.n_l, mark_w = ar.n_w, mark_c = ar.n_c, mark_o = ar.n_o;
+  if (n) {
+    SB_TRY(agg_reserve(c->agg, n));
+    AggScratch& a = c->agg;
+    uint64_t i = 0;
+    for (auto& s : c->stores) {
+      if (!s.n) continue;
+      k_store_records<<<nblk(s.n, 256), 256, 0, st>>>(s.n, ar.loff + s.base_o, ar.woff + s.base_o, s.base_l, s.base_w,
+                                                      a.lstart + i, a.llen + i, a.wstart + i, a.wlen + i);
+      i += s.n;
+    }
+    Records R{(uint32_t)n, a.lstart, a.llen, a.wstart, a.wlen, ar.labels, ar.weights, ar.counts + c->stores.front().base_c};
+    SB_TRY(aggregate(c, R, merged));
+    if (merged.n) k_normalize<<<nblk(merged.n, 128), 128, 0, st>>>(merged.n, ar.woff + merged.base_o, ar.weights + merged.base_w);
+  }
+  std::vector<uint64_t> loff(merged.n + 1, 0), woff(merged.n + 1, 0);
+  b->h_counts.assign(merged.n, 0); b->h_labels.assign(merged.n_lab, 0); b->h_w.assign(merged.n_w, 0.0);
+  if (merged.n) {
+    SB_CUDA(cudaMemcpyAsync(loff.data(), ar.loff + merged.base_o, (merged.n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(woff.data(), ar.woff + merged.base_o, (merged.n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(b->h_counts.data(), ar.counts + merged.base_c, merged.n * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(b->h_labels.data(), ar.labels + merged.base_l, merged.n_lab * 4, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(b->h_w.data(), ar.weights + merged.base_w, merged.n_w * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+  }
+  b->h_off = woff; b->h_label_off = loff;
+  b->h_tids.clear(); b->h_ntx.clear();
+  b->h_tids.reserve(merged.n_w);
+  for (uint64_t q = 0; q < merged.n; ++q) {
+    const uint64_t ntx = woff[q + 1] - woff[q];
+    b->h_ntx.push_back((uint32_t)ntx);
+    for (uint64_t j = 0; j < ntx; ++j) b->h_tids.push_back(b->h_labels[loff[q] + j]);
+  }
+  ar.n_l = mark_l; ar.n_w = mark_w; ar.n_c = mark_c; ar.n_o = mark_o;   // the merged table is temporary: more batches may follow
+  out->n_classes = merged.n; out->n_txps = b->n_txps;
+  out->off = b->h_off.data(); out->tids = b->h_tids.data(); out->weights = b->h_w.data(); out->counts = b->h_counts.data();
+  out->n_txp_in_label = b->h_ntx.data(); out->label_off = b->h_label_off.data(); out->labels = b->h_labels.data();
+  out->n_groups = b->n_groups;
+  return SB_OK;
+}
