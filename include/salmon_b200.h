@@ -421,9 +421,9 @@ typedef struct sb_quant_opts {
   uint32_t num_gibbs;        /* --numGibbsSamples */
   uint32_t thinning;         /* --thinningFactor (16) */
   int32_t no_gamma_draw;     /* --noGammaDraw */
-  uint32_t shard_index, shard_count;   /* must be 0 / 1: a shard alone is not a quantification (multi-GPU: sb_reads_bucketed
-                                          + the host layer's end-of-mapping reduction, salmon_b200/quant.py::quant_files) */
+  uint32_t shard_index, shard_count;   /* rank / number of ranks of a multi-GPU run (one process per GPU); 0 / 1 on one GPU */
   uint64_t seed;
+  const void* nccl_uid;      /* shard_count > 1: the 128 bytes of rank 0's sb_nccl_unique_id(), the same on every rank */
 } sb_quant_opts;
 typedef struct sb_quant_summary {
   uint64_t n_observed, n_mapped, n_too_short, n_trimmed_mates, n_classes, n_batches;
@@ -432,10 +432,39 @@ typedef struct sb_quant_summary {
   float map_device_ms, reserved2;                  /* sum of sb_map_batch_stats.device_ms */
 } sb_quant_summary;
 void sb_quant_default_opts(sb_quant_opts* o);
-/* mp / ep / o may be NULL (defaults); out_dir may be NULL (no files); alpha_out[n_txps] may be NULL. */
+/* mp / ep / o may be NULL (defaults); out_dir may be NULL (no files); alpha_out[n_txps] may be NULL (decoy entries, the
+ * suffix of the id space, are 0: decoys are dropped before the optimiser and the writers, SalmonQuantify.cpp:2479).
+ * shard_count > 1: every rank calls this with its shard_index and the same nccl_uid; reads are sharded by global batch,
+ * the end-of-mapping statistics are reduced once, the optimiser exchanges alpha inside its kernel, rank 0 writes. */
 int sb_quant_files(sb_index* ix, const char* const* mates1, const char* const* mates2, uint32_t n_files,
                    const sb_map_params* mp, const sb_em_params* ep, const sb_quant_opts* o, const char* out_dir,
                    double* alpha_out, sb_quant_summary* summary);
+
+/* ---- host-level communicator of the multi-GPU driver (one process per GPU; NCCL underneath, loaded with dlopen) ----
+ * rank / nranks as the launcher gives them; nccl_uid128 = the 128 bytes of sb_nccl_unique_id(), made by rank 0 and
+ * handed to the other ranks by the launcher (sb_salmon: a file in the output directory; torchrun: any broadcast).
+ * In place over HOST buffers of 8-byte elements: dtype 0 = f64, 1 = u64; op 0 = sum, 2 = max, 3 = min. */
+typedef struct sb_comm sb_comm;
+sb_comm* sb_comm_create(int rank, int nranks, const void* nccl_uid128, int device);
+void sb_comm_destroy(sb_comm* comm);
+int sb_comm_rank(const sb_comm* comm);
+int sb_comm_size(const sb_comm* comm);
+int sb_comm_allreduce(sb_comm* comm, void* buf, size_t n, int dtype, int op);
+int sb_comm_allgather(sb_comm* comm, const void* send, void* recv, size_t bytes_per_rank);
+/* sb_em_peer_handle + all-gather + sb_em_peer_open on this communicator (fused multi-GPU EM) */
+int sb_em_peer_setup(sb_em_ctx* ctx, sb_comm* comm, uint32_t max_txps);
+/* End-of-mapping reduction of a sharded run, the C++ form of salmon_b200/dist.py: masses and the
+ * fragment-length histogram by log-sum-exp over the ranks (the prior counted once), counts by sum, cluster roots
+ * all-gathered, then normalizeAlphas with the global state (sb_map_project_global).  On return every rank holds the
+ * same projected counts / effective lengths / unique counts in *out; *assigned_out = fragments assigned by all ranks. */
+int sb_map_reduce_global(sb_map_ctx* ctx, sb_comm* comm, sb_map_result* out, uint64_t* assigned_out);
+
+/* `salmon quant -e` (processEqClasses, src/alignment/SalmonQuantifyAlignments.cpp:1406-1440): optimiser + samplers over a
+ * dumped class table.  shard_count > 1: every rank holds the table, the posterior samples (bootstraps / Gibbs chains,
+ * which are independent: CollapsedGibbsSampler.cpp:425-461, CollapsedEMOptimizer.cpp:670-688) are split over the ranks
+ * and gathered by rank 0 into aux_info/bootstrap/bootstraps.gz in sample order. */
+int sb_quant_eqclasses(const char* eq_path, const sb_em_params* ep, const sb_quant_opts* o, const char* out_dir,
+                       sb_quant_summary* summary);
 
 /* Tuning knobs of the mapping context: "variant" (1 = warp-cooperative kernels, 0 = serial-form kernels),
  * "fast_dp" (ungapped shortcut of the DP kernel on/off), "chunk" (reads per pipeline chunk), "input_on_device"

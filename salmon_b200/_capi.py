@@ -134,7 +134,7 @@ class sb_quant_opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("batch", C.c_uint32), ("max_read_len", C.c_uint32), ("threads", C.c_uint32),
                 ("dump_eq", C.c_int32), ("dump_eq_weights", C.c_int32), ("num_bootstraps", C.c_uint32),
                 ("num_gibbs", C.c_uint32), ("thinning", C.c_uint32), ("no_gamma_draw", C.c_int32),
-                ("shard_index", C.c_uint32), ("shard_count", C.c_uint32), ("seed", C.c_uint64)]
+                ("shard_index", C.c_uint32), ("shard_count", C.c_uint32), ("seed", C.c_uint64), ("nccl_uid", C.c_void_p)]
 
 
 class sb_quant_summary(C.Structure):
@@ -203,6 +203,15 @@ SYMBOLS = {
     "sb_map_batch": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, C.POINTER(sb_map_batch_stats)]),
     "sb_map_finish": (C.c_int, [_P, C.POINTER(sb_map_result)]),
     "sb_map_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "sb_comm_create": (_P, [C.c_int, C.c_int, _P, C.c_int]),
+    "sb_comm_destroy": (None, [_P]),
+    "sb_comm_rank": (C.c_int, [_P]),
+    "sb_comm_size": (C.c_int, [_P]),
+    "sb_comm_allreduce": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int]),
+    "sb_comm_allgather": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "sb_em_peer_setup": (C.c_int, [_P, _P, C.c_uint32]),
+    "sb_map_reduce_global": (C.c_int, [_P, _P, _P, _P]),
+    "sb_quant_eqclasses": (C.c_int, [C.c_char_p, _P, _P, C.c_char_p, _P]),
     "sb_eq_create": (_P, [C.c_uint32, C.c_int]),
     "sb_eq_destroy": (None, [_P]),
     "sb_eq_add_batch": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P, _P]),

@@ -6,7 +6,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <sys/stat.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 #include <string>
 #include <vector>
@@ -22,6 +25,8 @@ int die(const char* what) {
 
 struct Args {
   std::vector<std::string> v;
+  std::vector<std::string> all;    // the arguments as given (cmd_info.json, re-execution per rank)
+  std::string argv0;
   size_t i = 0;
   bool more() const { return i < v.size(); }
   const std::string& peek() const { return v[i]; }
@@ -109,35 +114,64 @@ int cmd_index(Args& a) {
   return 0;
 }
 
-int quant_eqclasses(const std::string& eqfile, const std::string& out, sb_em_params ep, const sb_quant_opts& qo) {
-  sb_eq_file* f = nullptr;
-  if (sb_eq_file_read(eqfile.c_str(), &f) != 0) return die("reading the equivalence classes");
-  if (!f->has_weights) { fprintf(stderr, "sb_salmon: --eqclasses needs the weights (write the file with --dumpEqWeights)\n"); return 1; }
-  // processEqClasses, src/alignment/SalmonQuantifyAlignments.cpp:1406-1440: uniform initialisation, eq-class mode
-  ep.init_uniform = 1;
-  ep.eq_class_mode = 1;
-  std::vector<double> zeros(f->n_txps, 0.0), alpha(f->n_txps, 0.0);
-  std::vector<uint64_t> uniq(f->n_txps, 0);
-  sb_eq_csr eq;
-  eq.n_classes = f->n_classes; eq.n_txps = f->n_txps; eq.off = f->off; eq.tids = f->tids; eq.weights = f->weights; eq.counts = f->counts;
-  sb_em_ctx* em = sb_em_create(qo.device);
-  if (!em) return die("creating the optimiser");
-  sb_em_stats st;
-  const int rc = sb_em_optimize(em, &eq, &ep, zeros.data(), f->eff_len, uniq.data(), alpha.data(), &st);
-  if (rc < 0) return die("optimising");
-  if (rc == 1) { fprintf(stderr, "The optimization algorithm failed (total alpha weight too small)\n"); return 1; }
-  double n_frags = 0;
-  for (uint64_t c = 0; c < f->n_classes; ++c) n_frags += (double)f->counts[c];
-  mkdir(out.c_str(), 0777);
-  std::vector<uint32_t> lens(f->n_txps);
-  for (uint32_t t = 0; t < f->n_txps; ++t) lens[t] = (uint32_t)(f->eff_len[t] < 1.0 ? 1.0 : f->eff_len[t]);
-  if (sb_write_quant_sf((out + "/quant.sf").c_str(), f->n_txps, f->names, lens.data(), f->eff_len, alpha.data(), n_frags, 3) != 0)
-    return die("writing quant.sf");
-  fprintf(stderr, "%llu classes, %u transcripts: %u iterations (%s), %.1f ms on the device\n", (unsigned long long)f->n_classes,
-          f->n_txps, st.iters, st.converged ? "converged" : "iteration limit", st.run_ms);
-  sb_em_destroy(em);
-  sb_eq_file_free(f);
+int quant_eqclasses(const std::string& eqfile, const std::string& out, const sb_em_params& ep, const sb_quant_opts& qo) {
+  sb_quant_summary sum;
+  if (sb_quant_eqclasses(eqfile.c_str(), &ep, &qo, out.c_str(), &sum) != 0) return die("quant -e");
+  if (qo.shard_index == 0)
+    fprintf(stderr, "%llu classes: %u iterations (%s) in %.2f s, total %.2f s on %u GPU(s)\n", (unsigned long long)sum.n_classes,
+            sum.em_iters, sum.em_converged ? "converged" : "iteration limit", sum.em_seconds, sum.total_seconds, qo.shard_count ? qo.shard_count : 1);
   return 0;
+}
+
+// cmd_info.json (salmon::utils::writeCmdInfo): the options as given
+void write_cmd_info(const std::string& out, const std::vector<std::string>& argv_all) {
+  FILE* f = fopen((out + "/cmd_info.json").c_str(), "w");
+  if (!f) return;
+  fprintf(f, "{\n    \"salmon_version\": \"1.11.4-sb%d\"", sb_version());
+  std::string key;
+  std::vector<std::string> vals;
+  auto flush = [&]() {
+    if (key.empty()) return;
+    fprintf(f, ",\n    \"%s\": ", key.c_str());
+    if (vals.empty()) fprintf(f, "[]");
+    else if (vals.size() == 1) fprintf(f, "\"%s\"", vals[0].c_str());
+    else { fprintf(f, "["); for (size_t i = 0; i < vals.size(); ++i) fprintf(f, "%s\"%s\"", i ? ", " : "", vals[i].c_str()); fprintf(f, "]"); }
+  };
+  for (const std::string& a : argv_all) {
+    if (a.size() > 1 && a[0] == '-' && !(a[1] >= '0' && a[1] <= '9')) {
+      flush();
+      key = a.substr(a.find_first_not_of('-'));
+      vals.clear();
+    } else if (!key.empty()) {
+      vals.push_back(a);
+    }
+  }
+  flush();
+  fprintf(f, "\n}\n");
+  fclose(f);
+}
+
+// rank 0 writes the communicator id into the output directory, the other ranks wait for it
+bool exchange_uid(const std::string& out, int rank, const std::string& tag, unsigned char* uid) {
+  const std::string path = out + "/.sb_nccl_uid_" + tag;
+  if (rank == 0) {
+    if (sb_nccl_unique_id(uid) != 0) return false;
+    const std::string tmp = path + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f || fwrite(uid, 1, 128, f) != 128) { if (f) fclose(f); return false; }
+    fclose(f);
+    return rename(tmp.c_str(), path.c_str()) == 0;
+  }
+  for (int tries = 0; tries < 6000; ++tries) {       // up to 60 s
+    FILE* f = fopen(path.c_str(), "rb");
+    if (f) {
+      const size_t n = fread(uid, 1, 128, f);
+      fclose(f);
+      if (n == 128) return true;
+    }
+    usleep(10000);
+  }
+  return false;
 }
 
 int cmd_quant(Args& a) {
@@ -152,6 +186,8 @@ int cmd_quant(Args& a) {
   auto num = [&](double& d) { if (!a.value(v)) return false; d = atof(v.c_str()); return true; };
   double d = 0;
   bool vb_prior_given = false;
+  int n_gpus = 1, my_rank = -1;
+  std::string run_tag;
   while (a.more()) {
     const std::string o = a.next();
     if (o == "-i" || o == "--index") { if (!a.value(dir)) return usage(); }
@@ -195,6 +231,9 @@ int cmd_quant(Args& a) {
     else if (o == "--numPreAuxModelSamples") { if (!num(d)) return usage(); mp.num_pre_burnin = (uint64_t)d; }
     else if (o == "--numAuxModelSamples") { if (!num(d)) return usage(); mp.num_burnin = (uint64_t)d; }
     else if (o == "--gpu") { if (!num(d)) return usage(); qo.device = (int32_t)d; }
+    else if (o == "--gpus" || o == "--numGpus") { if (!num(d)) return usage(); n_gpus = (int)d; }
+    else if (o == "--_rank") { if (!num(d)) return usage(); my_rank = (int)d; }
+    else if (o == "--_tag") { if (!a.value(run_tag)) return usage(); }
     else if (o == "--batch") { if (!num(d)) return usage(); qo.batch = (uint32_t)d; }
     else if (o == "--maxReadLen") { if (!num(d)) return usage(); qo.max_read_len = (uint32_t)d; }
     else if (o == "--seed") { if (!num(d)) return usage(); qo.seed = (uint64_t)d; mp.seed = (uint64_t)d; }
@@ -209,6 +248,44 @@ int cmd_quant(Args& a) {
   // --perNucleotidePrior without an explicit --vbPrior: the reference switches the default to 1e-5
   // (src/cli/QuantOptionsUtils.cpp:569-572)
   if (ep.use_vbem && !ep.per_txp_prior && !vb_prior_given) ep.vb_prior = 1e-5;
+  mkdir(out.c_str(), 0777);
+  // ---- multi-GPU: one process per GPU.  The parent re-executes itself once per rank; rank r uses GPU r.
+  if (n_gpus > 1 && my_rank < 0) {
+    const int have = sb_device_count();
+    if (have < n_gpus) { fprintf(stderr, "sb_salmon quant: --gpus %d but %d CUDA device(s) visible\n", n_gpus, have); return 1; }
+    char tag[64];
+    snprintf(tag, sizeof tag, "%ld_%d", (long)time(nullptr), (int)getpid());
+    std::vector<pid_t> kids;
+    for (int r = 0; r < n_gpus; ++r) {
+      pid_t pid = fork();
+      if (pid < 0) { perror("fork"); return 1; }
+      if (pid == 0) {
+        std::vector<std::string> av = a.all;
+        av.push_back("--_rank"); av.push_back(std::to_string(r));
+        av.push_back("--_tag"); av.push_back(tag);
+        std::vector<char*> cv;
+        cv.push_back(const_cast<char*>(a.argv0.c_str()));
+        cv.push_back(const_cast<char*>("quant"));
+        for (auto& x : av) cv.push_back(const_cast<char*>(x.c_str()));
+        cv.push_back(nullptr);
+        execv(a.argv0.c_str(), cv.data());
+        perror("execv");
+        _exit(127);
+      }
+      kids.push_back(pid);
+    }
+    int bad = 0;
+    for (pid_t k : kids) { int st = 0; waitpid(k, &st, 0); if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) bad = 1; }
+    unlink((out + "/.sb_nccl_uid_" + tag).c_str());
+    return bad;
+  }
+  unsigned char uid[128];
+  if (n_gpus > 1) {
+    qo.shard_index = (uint32_t)my_rank; qo.shard_count = (uint32_t)n_gpus; qo.device = my_rank;
+    if (!exchange_uid(out, my_rank, run_tag, uid)) { fprintf(stderr, "sb_salmon quant: rank %d could not obtain the communicator id\n", my_rank); return 1; }
+    qo.nccl_uid = uid;
+  }
+  if (qo.shard_index == 0) write_cmd_info(out, a.all);
   if (!eqfile.empty()) return quant_eqclasses(eqfile, out, ep, qo);
   if (dir.empty()) return usage();
   if (!unmated.empty() || m1.empty() || m1.size() != m2.size()) {
@@ -228,19 +305,14 @@ int cmd_quant(Args& a) {
   sb_quant_summary sum;
   if (sb_quant_files(ix, p1.data(), p2.data(), (uint32_t)p1.size(), &mp, &ep, &qo, out.c_str(), nullptr, &sum) != 0)
     return die("quant");
-  const double rate = sum.n_observed ? 100.0 * (double)sum.n_mapped / (double)sum.n_observed : 0.0;
-  fprintf(stderr, "%llu fragments observed, %llu mapped (%.4f%%), %llu equivalence classes; %u read lengths, %llu batches\n",
-          (unsigned long long)sum.n_observed, (unsigned long long)sum.n_mapped, rate, (unsigned long long)sum.n_classes,
-          sum.n_read_lengths, (unsigned long long)sum.n_batches);
-  fprintf(stderr, "mapping %.2f s (%.1f ms on the device, %.2f M fragments/s end to end), optimiser %u iterations in %.2f s, total %.2f s\n",
-          sum.map_seconds, sum.map_device_ms, sum.map_seconds > 0 ? (double)sum.n_observed / sum.map_seconds / 1e6 : 0.0, sum.em_iters,
-          sum.em_seconds, sum.total_seconds);
-  if (FILE* f = fopen((out + "/aux_info/meta_info.json").c_str(), "w")) {   // the fields downstream tools read (tximport: num_bootstraps ...)
-    fprintf(f, "{\n  \"salmon_version\": \"sb-%d\",\n  \"samp_type\": \"%s\",\n  \"num_bootstraps\": %u,\n  \"num_processed\": %llu,\n"
-               "  \"num_mapped\": %llu,\n  \"percent_mapped\": %.6f,\n  \"num_eq_classes\": %llu,\n  \"mapping_type\": \"mapping\"\n}\n",
-            sb_version(), qo.num_gibbs ? "gibbs" : (qo.num_bootstraps ? "bootstrap" : "none"), qo.num_gibbs ? qo.num_gibbs : qo.num_bootstraps,
-            (unsigned long long)sum.n_observed, (unsigned long long)sum.n_mapped, rate, (unsigned long long)sum.n_classes);
-    fclose(f);
+  if (qo.shard_index == 0) {
+    const double rate = sum.n_observed ? 100.0 * (double)sum.n_mapped / (double)sum.n_observed : 0.0;
+    fprintf(stderr, "%llu fragments observed, %llu mapped (%.4f%%), %llu equivalence classes%s; %u read lengths, %llu batches%s\n",
+            (unsigned long long)sum.n_observed, (unsigned long long)sum.n_mapped, rate, (unsigned long long)sum.n_classes,
+            n_gpus > 1 ? " on rank 0" : "", sum.n_read_lengths, (unsigned long long)sum.n_batches, n_gpus > 1 ? " on rank 0" : "");
+    fprintf(stderr, "mapping %.2f s (%.1f ms on the device, %.2f M fragments/s end to end, %d GPU(s)), optimiser %u iterations in %.2f s, total %.2f s\n",
+            sum.map_seconds, sum.map_device_ms, sum.map_seconds > 0 ? (double)sum.n_observed / sum.map_seconds / 1e6 : 0.0, n_gpus, sum.em_iters,
+            sum.em_seconds, sum.total_seconds);
   }
   sb_index_free(ix);
   return 0;
@@ -252,6 +324,12 @@ int main(int argc, char** argv) {
   if (argc < 2) return usage();
   Args a;
   for (int i = 2; i < argc; ++i) a.v.push_back(argv[i]);
+  a.all = a.v;
+  {   // the executable's own path, for the per-rank re-execution
+    char self[4096];
+    const ssize_t n = readlink("/proc/self/exe", self, sizeof self - 1);
+    a.argv0 = n > 0 ? std::string(self, (size_t)n) : std::string(argv[0]);
+  }
   const std::string cmd = argv[1];
   if (cmd == "index") return cmd_index(a);
   if (cmd == "quant") return cmd_quant(a);

@@ -21,6 +21,10 @@ void set_error(const char* fmt, ...);
     }                                                                          \
   } while (0)
 
+#ifndef SB_TRY
+#define SB_TRY(x) do { int _r = (x); if (_r != SB_OK) return _r; } while (0)
+#endif
+
 // ---- PTX wrappers: mbarrier + 1-D bulk (TMA) copies ------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

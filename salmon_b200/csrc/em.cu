@@ -487,7 +487,6 @@ static int dev_alloc(T** p, size_t n) {
   caps[(void**)p] = want;
   return SB_OK;
 }
-#define SB_TRY(x) do { int _r = (x); if (_r != SB_OK) return _r; } while (0)
 
 extern "C" sb_em_ctx* sb_em_create(int device) {
   int n = sb_device_count();
@@ -595,6 +594,7 @@ extern "C" int sb_em_set_option(sb_em_ctx* c, const char* key, int64_t value) {
   } else if (!strcmp(key, "l2_keep_cm")) { c->keep_cm = (int)value; }
   else if (!strcmp(key, "l2_keep_tm")) { c->keep_tm = (int)value; }
   else if (!strcmp(key, "push_pass")) { c->push_pass = (int)value; }
+  else if (!strcmp(key, "sample_offset")) { c->sample_offset = (uint32_t)value; }
   else if (!strcmp(key, "rebalance")) { c->rebalance = (int)value; c->prepared = false; }
   else if (!strcmp(key, "rebalance_iters")) { c->rebalance_iters = (int)value; c->prepared = false; }
   else if (!strcmp(key, "overhead_p1")) { c->ovh_p1 = (int)value; c->prepared = false; }
@@ -1064,6 +1064,7 @@ struct NcclFns {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -1077,9 +1078,10 @@ int nccl_load() {
   g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
   g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.CommDestroy) {
     set_error("libnccl is missing required symbols");
     return SB_ERR_NCCL;
   }
@@ -1103,6 +1105,91 @@ extern "C" int sb_nccl_unique_id(void* out128) {
   SB_NCCL(g_nccl.GetUniqueId(out128));
   return SB_OK;
 }
+// ---- host-level communicator of the C++ multi-GPU driver (one process per GPU; NCCL underneath) ---------------------
+// The once-per-run reductions at the end of mapping (M-sized vectors), the exchange of the CUDA IPC handles of the
+// fused EM kernel and the gathering of posterior samples go through it; the per-iteration exchange of the EM does not
+// (k_em_persistent_mgpu moves it inside the kernel).
+struct sb_comm {
+  int rank = 0, nranks = 1, device = 0;
+  void* nccl = nullptr;
+  cudaStream_t stream = nullptr;
+  unsigned char* d_buf = nullptr;
+  size_t cap = 0;
+};
+extern "C" sb_comm* sb_comm_create(int rank, int nranks, const void* nccl_uid128, int device) {
+  if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !nccl_uid128)) { set_error("sb_comm_create: bad arguments"); return nullptr; }
+  sb_comm* cm = new sb_comm();
+  cm->rank = rank; cm->nranks = nranks; cm->device = device;
+  if (nranks == 1) return cm;
+  if (nccl_load() != SB_OK) { delete cm; return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&cm->stream) != cudaSuccess) {
+    set_error("sb_comm_create: cannot use device %d", device); delete cm; return nullptr;
+  }
+  NcclUid u;
+  memcpy(u.b, nccl_uid128, 128);
+  const int r = g_nccl.CommInitRank(&cm->nccl, nranks, u, rank);
+  if (r != 0) {
+    set_error("ncclCommInitRank -> %d (%s)", r, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    cudaStreamDestroy(cm->stream); delete cm; return nullptr;
+  }
+  return cm;
+}
+extern "C" void sb_comm_destroy(sb_comm* cm) {
+  if (!cm) return;
+  if (cm->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(cm->nccl);
+  if (cm->d_buf) { cudaSetDevice(cm->device); cudaFree(cm->d_buf); }
+  if (cm->stream) cudaStreamDestroy(cm->stream);
+  delete cm;
+}
+extern "C" int sb_comm_rank(const sb_comm* cm) { return cm ? cm->rank : 0; }
+extern "C" int sb_comm_size(const sb_comm* cm) { return cm ? cm->nranks : 1; }
+static int comm_reserve(sb_comm* cm, size_t bytes) {
+  if (bytes <= cm->cap) return SB_OK;
+  SB_CUDA(cudaSetDevice(cm->device));
+  if (cm->d_buf) cudaFree(cm->d_buf);
+  cm->d_buf = nullptr; cm->cap = 0;
+  SB_CUDA(cudaMalloc(&cm->d_buf, bytes + 256));
+  cm->cap = bytes;
+  return SB_OK;
+}
+// in place over host buffers; dtype: 0 = f64, 1 = u64; op: 0 sum, 2 max, 3 min (ncclRedOp_t)
+extern "C" int sb_comm_allreduce(sb_comm* cm, void* buf, size_t n, int dtype, int op) {
+  if (!cm || (n && !buf)) { set_error("null argument"); return SB_ERR_INVALID; }
+  if (cm->nranks == 1 || n == 0) return SB_OK;
+  SB_TRY(comm_reserve(cm, n * 8));
+  SB_CUDA(cudaSetDevice(cm->device));
+  SB_CUDA(cudaMemcpyAsync(cm->d_buf, buf, n * 8, cudaMemcpyHostToDevice, cm->stream));
+  SB_NCCL(g_nccl.AllReduce(cm->d_buf, cm->d_buf, n, dtype == 0 ? /*ncclFloat64*/ 8 : /*ncclUint64*/ 5, op, cm->nccl, cm->stream));
+  SB_CUDA(cudaMemcpyAsync(buf, cm->d_buf, n * 8, cudaMemcpyDeviceToHost, cm->stream));
+  SB_CUDA(cudaStreamSynchronize(cm->stream));
+  return SB_OK;
+}
+// recv = nranks x bytes (rank order); host buffers
+extern "C" int sb_comm_allgather(sb_comm* cm, const void* send, void* recv, size_t bytes) {
+  if (!cm || !send || !recv) { set_error("null argument"); return SB_ERR_INVALID; }
+  if (cm->nranks == 1) { memcpy(recv, send, bytes); return SB_OK; }
+  const size_t padded = (bytes + 15) & ~(size_t)15;
+  SB_TRY(comm_reserve(cm, padded * (size_t)(cm->nranks + 1)));
+  SB_CUDA(cudaSetDevice(cm->device));
+  SB_CUDA(cudaMemcpyAsync(cm->d_buf, send, bytes, cudaMemcpyHostToDevice, cm->stream));
+  SB_NCCL(g_nccl.AllGather(cm->d_buf, cm->d_buf + padded, padded, /*ncclInt8*/ 0, cm->nccl, cm->stream));
+  std::vector<unsigned char> tmp(padded * (size_t)cm->nranks);
+  SB_CUDA(cudaMemcpyAsync(tmp.data(), cm->d_buf + padded, tmp.size(), cudaMemcpyDeviceToHost, cm->stream));
+  SB_CUDA(cudaStreamSynchronize(cm->stream));
+  for (int r = 0; r < cm->nranks; ++r) memcpy((unsigned char*)recv + (size_t)r * bytes, tmp.data() + (size_t)r * padded, bytes);
+  return SB_OK;
+}
+// the fused multi-GPU EM on this communicator: exchange the exchange blocks' CUDA IPC handles and map the peers
+extern "C" int sb_em_peer_setup(sb_em_ctx* c, sb_comm* cm, uint32_t max_txps) {
+  if (!c || !cm) { set_error("null argument"); return SB_ERR_INVALID; }
+  if (cm->nranks == 1) return SB_OK;
+  unsigned char mine[64];
+  SB_TRY(sb_em_peer_handle(c, max_txps, mine));
+  std::vector<unsigned char> all((size_t)64 * cm->nranks);
+  SB_TRY(sb_comm_allgather(cm, mine, all.data(), 64));
+  return sb_em_peer_open(c, cm->rank, cm->nranks, all.data());
+}
+
 extern "C" int sb_em_comm_init(sb_em_ctx* c, int rank, int nranks, const void* uid) {
   if (!c || !uid || nranks < 1 || rank < 0 || rank >= nranks) { set_error("bad argument"); return SB_ERR_INVALID; }
   SB_TRY(nccl_load());

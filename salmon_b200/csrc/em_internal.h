@@ -115,6 +115,7 @@ struct sb_em_ctx {
   unsigned char* x_block = nullptr;
   uint32_t x_cap = 0;
   unsigned char** d_peers = nullptr;
+  uint32_t sample_offset = 0;     // index of the first sample of this call within the whole run (samples split over GPUs)
   int push_pass = -1;             // fused path: -1 = by rank count, 0 = push from the row epilogues, 1 = coalesced pass
   bool fused_loopback = false;    // one rank that is its own peer: the fused exchange logic on one GPU (tests)
   std::vector<void*> x_opened;

@@ -918,7 +918,6 @@ struct sb_map_ctx {
   std::vector<double> h_w;
 };
 
-#define SB_TRY(x) do { int _r = (x); if (_r != SB_OK) return _r; } while (0)
 template <typename T>
 static int dmalloc(T** p, size_t n) {
   cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));

@@ -18,11 +18,13 @@
 #include <time.h>
 #include <zlib.h>
 
+#include <cmath>
 #include <condition_variable>
 #include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <random>
 #include <string>
 #include <thread>
 #include <vector>
@@ -287,6 +289,178 @@ extern "C" void sb_quant_default_opts(sb_quant_opts* o) {
   o->seed = 42;
 }
 
+namespace {
+// ---- run metadata of the drop-in contract (src/output/GZipWriter.cpp:294-640 writeMeta, ReadExperiment.inl:219-350
+// summarizeLibraryTypeCounts, MappingPipelineStages.cpp:164-173 flenDist.txt) -----------------------------------------
+struct MetaIn {
+  const sb_quant_opts* o; const sb_em_params* ep; const sb_map_params* mp;
+  uint32_t n_valid, n_decoy;
+  uint64_t n_observed, n_mapped, n_classes;
+  const std::vector<double>* fld_log;     // log histogram of the fragment-length distribution
+  const uint64_t* uniq; const uint64_t* total;
+  std::string files, start_time, end_time;
+  int n_ranks;
+};
+std::string time_string() {
+  time_t t = time(nullptr);
+  char buf[64];
+  struct tm tmv;
+  localtime_r(&t, &tmv);
+  strftime(buf, sizeof buf, "%a %b %e %H:%M:%S %Y", &tmv);
+  return buf;
+}
+bool write_text(const std::string& path, const std::string& text) {
+  FILE* f = fopen(path.c_str(), "w");
+  if (!f) return false;
+  const bool ok = fwrite(text.data(), 1, text.size(), f) == text.size();
+  return (fclose(f) == 0) && ok;
+}
+bool write_gz(const std::string& path, const void* data, size_t bytes) {
+  gzFile g = gzopen(path.c_str(), "wb");
+  if (!g) return false;
+  const bool ok = bytes == 0 || gzwrite(g, data, (unsigned)bytes) == (int)bytes;
+  return (gzclose(g) == Z_OK) && ok;
+}
+int write_run_metadata(const std::string& outs, const MetaIn& m) {
+  if (!make_dirs(outs + "/aux_info") || !make_dirs(outs + "/libParams") || !make_dirs(outs + "/logs")) {
+    sb::set_error("cannot create the output sub-directories of %s", outs.c_str());
+    return SB_ERR_INVALID;
+  }
+  // normalised pmf of the fragment-length distribution, its mean / sd (DistributionUtils.cpp:57-101)
+  const std::vector<double>& lh = *m.fld_log;
+  std::vector<double> pmf(lh.size(), 0.0);
+  double mx = -INFINITY;
+  for (double v : lh) if (std::isfinite(v)) mx = std::max(mx, v);
+  double tot = 0.0;
+  if (std::isfinite(mx)) for (size_t i = 0; i < lh.size(); ++i) { pmf[i] = std::isfinite(lh[i]) ? std::exp(lh[i] - mx) : 0.0; tot += pmf[i]; }
+  double mean = 0.0, var = 0.0;
+  if (tot > 0) for (size_t i = 0; i < pmf.size(); ++i) { pmf[i] /= tot; mean += pmf[i] * (double)i; var += pmf[i] * (double)i * (double)i; }
+  var -= mean * mean;
+  const double sd = var > 0 ? std::sqrt(var) : 0.0;
+  // aux_info/fld.gz: int32 counts of 10000 draws from the pmf (the reference seeds from random_device; here --seed)
+  std::vector<int32_t> samples(pmf.size(), 0);
+  if (tot > 0) {
+    std::mt19937 gen((uint32_t)m.o->seed);
+    std::discrete_distribution<int32_t> dist(pmf.begin(), pmf.end());
+    for (int i = 0; i < 10000; ++i) ++samples[dist(gen)];
+  }
+  bool ok = write_gz(outs + "/aux_info/fld.gz", samples.data(), samples.size() * 4);
+  {   // libParams/flenDist.txt: exp(pmf(i)), tab separated, ostream precision
+    std::string t;
+    char buf[48];
+    for (size_t i = 0; i < pmf.size(); ++i) { snprintf(buf, sizeof buf, "%g", pmf[i]); t += buf; t += (i + 1 < pmf.size()) ? "\t" : "\n"; }
+    t += "\n";
+    ok = write_text(outs + "/libParams/flenDist.txt", t) && ok;
+  }
+  {   // aux_info/ambig_info.tsv (GZipWriter.cpp:603-616)
+    std::string t = "UniqueCount\tAmbigCount\n";
+    for (uint32_t i = 0; i < m.n_valid; ++i)
+      t += std::to_string(m.uniq[i]) + "\t" + std::to_string(m.total[i] >= m.uniq[i] ? m.total[i] - m.uniq[i] : 0) + "\n";
+    ok = write_text(outs + "/aux_info/ambig_info.tsv", t) && ok;
+  }
+  const uint32_t n_samp = m.o->num_bootstraps ? m.o->num_bootstraps : m.o->num_gibbs;
+  const double pct = m.n_observed ? 100.0 * (double)m.n_mapped / (double)m.n_observed : 0.0;
+  {
+    char buf[4096];
+    snprintf(buf, sizeof buf,
+             "{\n    \"salmon_version\": \"1.11.4-sb%d\",\n    \"samp_type\": \"%s\",\n    \"opt_type\": \"%s\",\n    \"quant_errors\": [],\n"
+             "    \"num_libraries\": 1,\n    \"library_types\": [\n        \"IU\"\n    ],\n    \"frag_dist_length\": %zu,\n"
+             "    \"frag_length_mean\": %.6f,\n    \"frag_length_sd\": %.6f,\n    \"seq_bias_correct\": false,\n    \"gc_bias_correct\": false,\n"
+             "    \"num_bias_bins\": 0,\n    \"mapping_type\": \"mapping\",\n    \"keep_duplicates\": false,\n    \"num_valid_targets\": %u,\n"
+             "    \"num_decoy_targets\": %u,\n    \"num_eq_classes\": %llu,\n    \"serialized_eq_classes\": %s,\n    \"eq_class_properties\": [%s],\n"
+             "    \"length_classes\": [],\n    \"index_seq_hash\": \"\",\n    \"index_name_hash\": \"\",\n    \"num_bootstraps\": %u,\n"
+             "    \"num_processed\": %llu,\n    \"num_mapped\": %llu,\n    \"num_decoy_fragments\": 0,\n    \"num_dovetail_fragments\": 0,\n"
+             "    \"num_fragments_filtered_vm\": 0,\n    \"num_alignments_below_threshold_for_mapped_fragments_vm\": 0,\n"
+             "    \"percent_mapped\": %.6f,\n    \"call\": \"quant\",\n    \"start_time\": \"%s\",\n    \"end_time\": \"%s\",\n    \"sb_num_gpus\": %d\n}\n",
+             sb_version(), m.o->num_bootstraps ? "bootstrap" : (m.o->num_gibbs ? "gibbs" : "none"), m.ep->use_vbem ? "vb" : "em",
+             pmf.size(), mean, sd, m.n_valid, m.n_decoy, (unsigned long long)m.n_classes,
+             (m.o->dump_eq || m.o->dump_eq_weights) ? "true" : "false",
+             m.mp->range_bins ? "\n        \"range_factorized\"\n    " : "", n_samp, (unsigned long long)m.n_observed,
+             (unsigned long long)m.n_mapped, pct, m.start_time.c_str(), m.end_time.c_str(), m.n_ranks);
+    ok = write_text(outs + "/aux_info/meta_info.json", buf) && ok;
+  }
+  {   // lib_format_counts.json: the library is IU; every kept mapping is compatible with it (inward pairs, orphans)
+    char buf[2048];
+    snprintf(buf, sizeof buf,
+             "{\n    \"read_files\": \"%s\",\n    \"expected_format\": \"IU\",\n    \"compatible_fragment_ratio\": %.6f,\n"
+             "    \"num_compatible_fragments\": %llu,\n    \"num_assigned_fragments\": %llu,\n"
+             "    \"num_frags_with_concordant_consistent_mappings\": %llu,\n    \"num_frags_with_inconsistent_or_orphan_mappings\": 0,\n"
+             "    \"strand_mapping_bias\": 0.0\n}\n",
+             m.files.c_str(), m.n_mapped ? 1.0 : 0.0, (unsigned long long)m.n_mapped, (unsigned long long)m.n_mapped,
+             (unsigned long long)m.n_mapped);
+    ok = write_text(outs + "/lib_format_counts.json", buf) && ok;
+  }
+  if (!ok) { sb::set_error("write error on the run metadata under %s", outs.c_str()); return SB_ERR_INVALID; }
+  return SB_OK;
+}
+
+// posterior samples split over the ranks (chains restart independently, CollapsedGibbsSampler.cpp:425-461; bootstrap
+// replicates are independent, CollapsedEMOptimizer.cpp:670-688): rank r draws samples [lo_r, hi_r) with their own
+// counter-RNG streams, rank 0 gathers them in sample order
+struct GatherUser { std::vector<double>* buf; };
+int gather_cb(const double* sample, uint32_t n, void* user) {
+  GatherUser* g = (GatherUser*)user;
+  g->buf->insert(g->buf->end(), sample, sample + n);
+  return 0;
+}
+int run_samples(sb_em_ctx* em, const sb_em_params& ep, const sb_quant_opts& o, const double* alpha, uint32_t M, double n_mapped,
+                sb_comm* comm, const std::string& outs, const char* const* names) {
+  const uint32_t n_total = o.num_bootstraps ? o.num_bootstraps : o.num_gibbs;
+  const int G = comm ? sb_comm_size(comm) : 1, r = comm ? sb_comm_rank(comm) : 0;
+  const uint32_t lo = (uint32_t)((uint64_t)n_total * r / G), hi = (uint32_t)((uint64_t)n_total * (r + 1) / G);
+  std::vector<double> mine;
+  mine.reserve((size_t)(hi - lo) * M);
+  GatherUser gu{&mine};
+  int rc = SB_OK;
+  if (hi > lo) {
+    // the samplers key their counter RNG by (seed, sample index): a rank's share starts at index lo, so a split run
+    // draws exactly the bootstrap replicates of the one-GPU run; a Gibbs share is a chain of its own from alphasInit
+    SB_TRY(sb_em_set_option(em, "sample_offset", lo));
+    if (o.num_bootstraps) {
+      sb_em_params bp = ep;
+      bp.min_iter = 50;   // CollapsedEMOptimizer.cpp:411
+      rc = sb_bootstrap(em, &bp, n_mapped, hi - lo, o.seed, gather_cb, &gu);
+    } else {
+      rc = sb_gibbs(em, alpha, ep.use_vbem, ep.per_txp_prior, ep.vb_prior, hi - lo, o.thinning ? o.thinning : 16,
+                    o.no_gamma_draw, n_mapped, o.seed, gather_cb, &gu);
+    }
+    sb_em_set_option(em, "sample_offset", 0);
+    if (rc < 0) return rc;
+  }
+  // gather: equal-sized slots of ceil(n/G) samples
+  const uint32_t slot = (n_total + G - 1) / G;
+  std::vector<double> all;
+  if (G > 1) {
+    mine.resize((size_t)slot * M, 0.0);
+    all.resize((size_t)slot * M * G);
+    SB_TRY(sb_comm_allgather(comm, mine.data(), all.data(), (size_t)slot * M * 8));
+  }
+  if (r != 0 || outs.empty()) return SB_OK;
+  if (!make_dirs(outs + "/aux_info/bootstrap")) { sb::set_error("cannot create the bootstrap directory"); return SB_ERR_INVALID; }
+  sb_bootstrap_writer* w = sb_bootstrap_writer_open((outs + "/aux_info/bootstrap/bootstraps.gz").c_str());
+  if (!w) return SB_ERR_INVALID;
+  for (int q = 0; q < G && rc >= 0; ++q) {
+    const uint32_t qlo = (uint32_t)((uint64_t)n_total * q / G), qhi = (uint32_t)((uint64_t)n_total * (q + 1) / G);
+    const double* base = G > 1 ? all.data() + (size_t)q * slot * M : mine.data();
+    for (uint32_t k = 0; k < qhi - qlo && rc >= 0; ++k) rc = sb_bootstrap_writer_write(w, base + (size_t)k * M, M);
+  }
+  const int rc2 = sb_bootstrap_writer_close(w);
+  if (rc < 0 || rc2 < 0) return rc < 0 ? rc : rc2;
+  std::string nm;
+  for (uint32_t t = 0; t < M; ++t) { nm += names[t]; nm += (t + 1 < M) ? '\t' : '\n'; }
+  if (!write_gz(outs + "/aux_info/bootstrap/names.tsv.gz", nm.data(), nm.size())) {
+    sb::set_error("write error on %s/aux_info/bootstrap/names.tsv.gz", outs.c_str());
+    return SB_ERR_INVALID;
+  }
+  return SB_OK;
+}
+}  // namespace
+
+// `salmon quant` (mapping mode) for one library, on one GPU or -- shard_count > 1, one process per GPU -- on several:
+// processReadLibrary -> quantifyLibrary -> stageFinalizeMappingOutputs (SalmonQuantify.cpp:2340-2480,
+// pipeline/MappingPipelineStages.cpp:21-175).  Rank r maps the global batches g with g % shard_count == r and keeps
+// their classes; the end-of-mapping statistics are reduced once (sb_map_reduce_global), the EM runs over the sharded
+// classes with the per-iteration exchange inside the kernel, rank 0 writes the outputs.
 extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const char* const* mates2, uint32_t n_files,
                               const sb_map_params* mp_in, const sb_em_params* ep_in, const sb_quant_opts* o_in,
                               const char* out_dir, double* alpha_out, sb_quant_summary* sum) {
@@ -295,13 +469,20 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
   if (o_in) o = *o_in; else sb_quant_default_opts(&o);
   if (o.batch < 1024) o.batch = 1024;
   if (o.max_read_len < 32 || o.max_read_len > 256) { sb::set_error("max_read_len must be in 32..256"); return SB_ERR_INVALID; }
-  if (o.shard_count != 1 || o.shard_index != 0) {
-    // a shard's classes alone are not a quantification: multi-GPU runs reduce the end-of-mapping statistics over the
-    // ranks before the EM (salmon_b200.quant.quant_files: sb_reads_bucketed + sb_map_partial_get / sb_map_project_global)
-    sb::set_error("sb_quant_files quantifies one whole library on one GPU; shard the reads with sb_reads_bucketed and the multi-GPU host layer");
+  if (o.shard_count == 0) o.shard_count = 1;
+  if (o.shard_index >= o.shard_count) { sb::set_error("shard_index must be below shard_count"); return SB_ERR_INVALID; }
+  const bool multi = o.shard_count > 1;
+  if (multi && !o.nccl_uid) {
+    sb::set_error("sb_quant_files: a sharded run needs the communicator id (sb_quant_opts.nccl_uid, sb_nccl_unique_id of rank 0): "
+                  "a shard's classes alone are not a quantification");
     return SB_ERR_INVALID;
   }
   if (o.num_bootstraps && o.num_gibbs) { sb::set_error("choose bootstraps or Gibbs samples, not both"); return SB_ERR_INVALID; }
+  if (multi && (o.num_bootstraps || o.num_gibbs || o.dump_eq || o.dump_eq_weights)) {
+    sb::set_error("posterior samples / --dumpEq need the whole class table on one GPU: run them on one GPU, or sample from a dumped table "
+                  "with `quant -e` (which splits the samples over the GPUs)");
+    return SB_ERR_INVALID;
+  }
   sb_map_params mp;
   if (mp_in) mp = *mp_in; else sb_map_default_params(&mp);
   sb_em_params ep;
@@ -311,14 +492,26 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
   const uint32_t* complete_len = nullptr;
   sb_index_get_meta(ix, &M, &k, &first_decoy, &names, &complete_len);
   if (first_decoy < M) mp.first_decoy = (int32_t)first_decoy;
+  // decoys are dropped before normalizeAlphas / the optimiser / the writers (readExp.dropDecoyTranscripts(),
+  // SalmonQuantify.cpp:2479, ReadExperiment.hpp:120): they are the suffix of the id space and never appear in a label
+  const uint32_t Mq = first_decoy < M ? first_decoy : M;
   const double t0 = now_s();
+  const std::string start_time = time_string();
 
-  sb_map_ctx* ctx = sb_map_create(ix, &mp, o.device, o.batch, o.max_read_len);
-  if (!ctx) return SB_ERR_CUDA;
-  sb_reads* rd = sb_reads_open(mates1, mates2, n_files, o.threads);
-  if (!rd) { sb_map_destroy(ctx); return SB_ERR_INVALID; }
+  struct Scope {   // everything acquired below, released on every exit path
+    sb_map_ctx* ctx = nullptr; sb_em_ctx* em = nullptr; sb_comm* comm = nullptr; sb_reads* rd = nullptr;
+    ~Scope() { if (rd) sb_reads_close(rd); if (em) sb_em_destroy(em); if (ctx) sb_map_destroy(ctx); if (comm) sb_comm_destroy(comm); }
+  } S;
+  if (multi) {
+    S.comm = sb_comm_create((int)o.shard_index, (int)o.shard_count, o.nccl_uid, o.device);
+    if (!S.comm) return SB_ERR_NCCL;
+  }
+  S.ctx = sb_map_create(ix, &mp, o.device, o.batch, o.max_read_len);
+  if (!S.ctx) return SB_ERR_CUDA;
+  S.rd = sb_reads_open(mates1, mates2, n_files, o.threads);
+  if (!S.rd) return SB_ERR_INVALID;
 
-  struct MapUser { sb_map_ctx* ctx; float device_ms; } mu{ctx, 0.0f};
+  struct MapUser { sb_map_ctx* ctx; float device_ms; } mu{S.ctx, 0.0f};
   sb_batch_cb map_cb = [](void* user, const uint8_t* l, const uint8_t* r, uint32_t n, uint32_t L) -> int {
     MapUser* u = (MapUser*)user;
     sb_map_batch_stats st;
@@ -327,39 +520,46 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
     return rc;
   };
   sb_bucket_stats bs;
-  int rc = sb_reads_bucketed(rd, mp.k, o.batch, o.max_read_len, o.threads, o.shard_index, o.shard_count, map_cb, &mu, &bs);
-  sb_reads_close(rd);
-  if (rc != SB_OK) { sb_map_destroy(ctx); return rc; }
+  int rc = sb_reads_bucketed(S.rd, mp.k, o.batch, o.max_read_len, o.threads, o.shard_index, o.shard_count, map_cb, &mu, &bs);
+  sb_reads_close(S.rd);
+  S.rd = nullptr;
+  if (rc != SB_OK) return rc;
   const float device_ms = mu.device_ms;
   const double t_map = now_s();
 
-  // ---- classes -> EM -> outputs --------------------------------------------------------------------------------
+  // ---- classes -> (global statistics) -> EM -> outputs -----------------------------------------------------------
   sb_map_result res;
-  rc = sb_map_finish(ctx, &res);
-  if (rc != SB_OK) { sb_map_destroy(ctx); return rc; }
+  rc = sb_map_finish(S.ctx, &res);
+  if (rc != SB_OK) return rc;
+  sb_map_result glob = res;          // per-transcript inputs of the optimiser
+  uint64_t n_mapped_u = res.n_mapped, n_observed = bs.n_observed;
+  if (multi) {
+    SB_TRY(sb_map_reduce_global(S.ctx, S.comm, &glob, &n_mapped_u));
+    SB_TRY(sb_comm_allreduce(S.comm, &n_observed, 1, 1, 0));
+  }
   sb_eq_csr eq;
-  eq.n_classes = res.n_classes; eq.n_txps = M; eq.off = res.off; eq.tids = res.tids; eq.weights = res.weights; eq.counts = res.counts;
+  eq.n_classes = res.n_classes; eq.n_txps = Mq; eq.off = res.off; eq.tids = res.tids; eq.weights = res.weights; eq.counts = res.counts;
   std::vector<double> alpha(M, 0.0);
   sb_em_stats est;
   memset(&est, 0, sizeof est);
-  sb_em_ctx* em = sb_em_create(o.device);
-  if (!em) { sb_map_destroy(ctx); return SB_ERR_CUDA; }
-  rc = sb_em_optimize(em, &eq, &ep, res.projected_counts, res.eff_len, res.unique_counts, alpha.data(), &est);
-  const double n_mapped = (double)res.n_mapped;
+  S.em = sb_em_create(o.device);
+  if (!S.em) return SB_ERR_CUDA;
+  if (multi) SB_TRY(sb_em_peer_setup(S.em, S.comm, Mq));
+  rc = sb_em_optimize(S.em, &eq, &ep, glob.projected_counts, glob.eff_len, glob.unique_counts, alpha.data(), &est);
+  const double n_mapped = (double)n_mapped_u;
   std::string outs = out_dir ? out_dir : "";
-  auto fail = [&](int code) { sb_em_destroy(em); sb_map_destroy(ctx); return code; };
-  if (rc < 0) return fail(rc);
-  if (rc == 1) { sb::set_error("The optimization algorithm failed (total alpha weight too small)"); return fail(SB_ERR_STATE); }
+  if (rc < 0) return rc;
+  if (rc == 1) { sb::set_error("The optimization algorithm failed (total alpha weight too small)"); return SB_ERR_STATE; }
   const double t_em = now_s();
-  if (!outs.empty()) {
-    if (!make_dirs(outs + "/aux_info")) { sb::set_error("cannot create %s/aux_info", outs.c_str()); return fail(SB_ERR_INVALID); }
-    std::vector<std::string> gen;
-    std::vector<const char*> np;
-    if (!names) {
-      for (uint32_t t = 0; t < M; ++t) gen.push_back("t" + std::to_string(t));
-      for (auto& s : gen) np.push_back(s.c_str());
-      names = np.data();
-    }
+  std::vector<std::string> gen;
+  std::vector<const char*> np;
+  if (!names) {
+    for (uint32_t t = 0; t < M; ++t) gen.push_back("t" + std::to_string(t));
+    for (auto& sname : gen) np.push_back(sname.c_str());
+    names = np.data();
+  }
+  if (!outs.empty() && o.shard_index == 0) {
+    if (!make_dirs(outs + "/aux_info")) { sb::set_error("cannot create %s/aux_info", outs.c_str()); return SB_ERR_INVALID; }
     std::vector<uint32_t> lens;
     if (!complete_len) {
       const uint64_t* off = nullptr;
@@ -367,44 +567,151 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
       for (uint32_t t = 0; t < M; ++t) lens.push_back((uint32_t)(off[t + 1] - off[t]));
       complete_len = lens.data();
     }
-    rc = sb_write_quant_sf((outs + "/quant.sf").c_str(), M, names, complete_len, res.eff_len, alpha.data(), n_mapped, 3);
+    rc = sb_write_quant_sf((outs + "/quant.sf").c_str(), Mq, names, complete_len, glob.eff_len, alpha.data(), n_mapped, 3);
     if (rc == SB_OK && (o.dump_eq || o.dump_eq_weights))
-      rc = sb_write_eq_classes((outs + "/aux_info/eq_classes.txt.gz").c_str(), M, names, res.n_classes, res.off, res.tids,
+      rc = sb_write_eq_classes((outs + "/aux_info/eq_classes.txt.gz").c_str(), Mq, names, res.n_classes, res.off, res.tids,
                                o.dump_eq_weights ? res.weights : nullptr, res.counts);
-    if (rc != SB_OK) return fail(rc);
-    if (o.num_bootstraps || o.num_gibbs) {
-      if (!make_dirs(outs + "/aux_info/bootstrap")) { sb::set_error("cannot create the bootstrap directory"); return fail(SB_ERR_INVALID); }
-      BootUser bu{sb_bootstrap_writer_open((outs + "/aux_info/bootstrap/bootstraps.gz").c_str()), SB_OK};
-      if (!bu.w) return fail(SB_ERR_INVALID);
-      if (o.num_bootstraps) {
-        sb_em_params bp = ep;
-        bp.min_iter = 50;   // CollapsedEMOptimizer.cpp:411
-        rc = sb_bootstrap(em, &bp, n_mapped, o.num_bootstraps, o.seed, boot_cb, &bu);
-      } else {
-        rc = sb_gibbs(em, alpha.data(), ep.use_vbem, ep.per_txp_prior, ep.vb_prior, o.num_gibbs, o.thinning ? o.thinning : 16,
-                      o.no_gamma_draw, n_mapped, o.seed, boot_cb, &bu);
-      }
-      sb_bootstrap_writer_close(bu.w);
-      if (rc < 0 || bu.rc != SB_OK) return fail(rc < 0 ? rc : bu.rc);
-      // names of the columns of bootstraps.gz (GZipWriter writes names.tsv.gz next to it)
-      std::string nm;
-      for (uint32_t t = 0; t < M; ++t) { nm += names[t]; nm += (t + 1 < M) ? '\t' : '\n'; }
-      gzFile g = gzopen((outs + "/aux_info/bootstrap/names.tsv.gz").c_str(), "wb");
-      const bool wrote = g && gzwrite(g, nm.data(), (unsigned)nm.size()) == (int)nm.size();
-      if (!g || (gzclose(g) != Z_OK) || !wrote) { sb::set_error("write error on %s/aux_info/bootstrap/names.tsv.gz", outs.c_str()); return fail(SB_ERR_INVALID); }
-    }
+    if (rc != SB_OK) return rc;
+    // run metadata
+    std::vector<double> hist((size_t)mp.max_frag_len + 1, 0.0);
+    SB_TRY(sb_map_online_state(S.ctx, nullptr, hist.data(), nullptr, nullptr));
+    std::string files = "[ ";
+    for (uint32_t f = 0; f < n_files; ++f) files += std::string(f ? ", " : "") + "( " + mates1[f] + ", " + mates2[f] + " )";
+    files += " ]";
+    MetaIn mi{&o, &ep, &mp, Mq, M - Mq, n_observed, n_mapped_u, res.n_classes, &hist, glob.unique_counts, glob.total_counts,
+              files, start_time, time_string(), (int)o.shard_count};
+    SB_TRY(write_run_metadata(outs, mi));
+  }
+  if (o.num_bootstraps || o.num_gibbs) {
+    rc = run_samples(S.em, ep, o, alpha.data(), Mq, n_mapped, nullptr, o.shard_index == 0 ? outs : std::string(), names);
+    if (rc < 0) return rc;
   }
   if (alpha_out) memcpy(alpha_out, alpha.data(), (size_t)M * 8);
   if (sum) {
     memset(sum, 0, sizeof(*sum));
-    sum->n_observed = bs.n_observed; sum->n_mapped = res.n_mapped; sum->n_too_short = bs.n_too_short;
+    sum->n_observed = n_observed; sum->n_mapped = n_mapped_u; sum->n_too_short = bs.n_too_short;
     sum->n_trimmed_mates = bs.n_trimmed_mates;
     sum->n_classes = res.n_classes; sum->n_batches = bs.n_batches; sum->n_read_lengths = bs.n_read_lengths;
     sum->em_iters = est.iters; sum->em_converged = est.converged;
     sum->map_seconds = t_map - t0; sum->em_seconds = t_em - t_map; sum->total_seconds = now_s() - t0;
     sum->map_device_ms = device_ms;
   }
-  sb_em_destroy(em);
-  sb_map_destroy(ctx);
   return SB_OK;
+}
+
+// `salmon quant -e` (processEqClasses, SalmonQuantifyAlignments.cpp:1406-1440): the optimiser and the samplers over a
+// dumped class table.  With shard_count > 1 (one process per GPU, every rank holding the whole table) the posterior
+// samples are split over the ranks -- BASELINE.json configs[4] -- and gathered by rank 0.
+extern "C" int sb_quant_eqclasses(const char* eq_path, const sb_em_params* ep_in, const sb_quant_opts* o_in,
+                                  const char* out_dir, sb_quant_summary* sum) {
+  if (!eq_path) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  sb_quant_opts o;
+  if (o_in) o = *o_in; else sb_quant_default_opts(&o);
+  if (o.shard_count == 0) o.shard_count = 1;
+  const bool multi = o.shard_count > 1;
+  if (multi && !o.nccl_uid) { sb::set_error("sb_quant_eqclasses: a multi-GPU run needs sb_quant_opts.nccl_uid"); return SB_ERR_INVALID; }
+  if (o.num_bootstraps && o.num_gibbs) { sb::set_error("choose bootstraps or Gibbs samples, not both"); return SB_ERR_INVALID; }
+  sb_em_params ep;
+  if (ep_in) ep = *ep_in; else sb_em_default_params(&ep);
+  const double t0 = now_s();
+  struct Scope {
+    sb_eq_file* f = nullptr; sb_em_ctx* em = nullptr; sb_comm* comm = nullptr;
+    ~Scope() { if (em) sb_em_destroy(em); if (f) sb_eq_file_free(f); if (comm) sb_comm_destroy(comm); }
+  } S;
+  if (sb_eq_file_read(eq_path, &S.f) != SB_OK) return SB_ERR_INVALID;
+  const sb_eq_file* f = S.f;
+  if (multi) {
+    S.comm = sb_comm_create((int)o.shard_index, (int)o.shard_count, o.nccl_uid, o.device);
+    if (!S.comm) return SB_ERR_NCCL;
+  }
+  if (!f->has_weights) { sb::set_error("--eqclasses needs the weights (write the file with --dumpEqWeights)"); return SB_ERR_INVALID; }
+  const uint32_t M = f->n_txps;
+  std::vector<double> zeros(M, 0.0), alpha(M, 0.0);
+  std::vector<uint64_t> uniq(M, 0);
+  double n_frags = 0.0;
+  for (uint64_t c = 0; c < f->n_classes; ++c) n_frags += (double)f->counts[c];
+  // processEqClasses: uniform initialisation, eq-class mode (the weights of the file are the combined weights)
+  ep.init_uniform = 1;
+  ep.eq_class_mode = 1;
+  sb_eq_csr eqv;
+  eqv.n_classes = f->n_classes; eqv.n_txps = M; eqv.off = f->off; eqv.tids = f->tids; eqv.weights = f->weights; eqv.counts = f->counts;
+  S.em = sb_em_create(o.device);
+  if (!S.em) return SB_ERR_CUDA;
+  sb_em_stats st;
+  memset(&st, 0, sizeof st);
+  int rc = sb_em_optimize(S.em, &eqv, &ep, zeros.data(), f->eff_len, uniq.data(), alpha.data(), &st);
+  if (rc < 0) return rc;
+  if (rc == 1) { sb::set_error("The optimization algorithm failed (total alpha weight too small)"); return SB_ERR_STATE; }
+  const double t_em = now_s();
+  const std::string outs = out_dir ? out_dir : "";
+  if (!outs.empty() && o.shard_index == 0) {
+    if (!make_dirs(outs + "/aux_info")) { sb::set_error("cannot create %s/aux_info", outs.c_str()); return SB_ERR_INVALID; }
+    std::vector<uint32_t> lens(M);
+    for (uint32_t t = 0; t < M; ++t) lens[t] = (uint32_t)(f->eff_len[t] < 1.0 ? 1.0 : f->eff_len[t]);   // the table carries no lengths
+    SB_TRY(sb_write_quant_sf((outs + "/quant.sf").c_str(), M, f->names, lens.data(), f->eff_len, alpha.data(), n_frags, 3));
+  }
+  if (o.num_bootstraps || o.num_gibbs) {
+    rc = run_samples(S.em, ep, o, alpha.data(), M, n_frags, S.comm, o.shard_index == 0 ? outs : std::string(), f->names);
+    if (rc < 0) return rc;
+  }
+  if (sum) {
+    memset(sum, 0, sizeof(*sum));
+    sum->n_observed = (uint64_t)n_frags; sum->n_mapped = (uint64_t)n_frags; sum->n_classes = f->n_classes;
+    sum->em_iters = st.iters; sum->em_converged = st.converged;
+    sum->em_seconds = t_em - t0; sum->total_seconds = now_s() - t0;
+  }
+  return SB_OK;
+}
+
+// ---- end-of-mapping reduction of a sharded run, C++ form of salmon_b200/dist.py::reduce_partials --------------------
+extern "C" int sb_map_reduce_global(sb_map_ctx* ctx, sb_comm* comm, sb_map_result* out, uint64_t* assigned_out) {
+  if (!ctx || !comm || !out) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  sb_map_partial p;
+  SB_TRY(sb_map_partial_get(ctx, &p));
+  const int G = sb_comm_size(comm);
+  const uint32_t M = p.n_txps, nf = p.n_fld;
+  if (G == 1) {
+    if (assigned_out) *assigned_out = p.assigned;
+    return sb_map_project_global(ctx, &p, 1, p.cluster_root, out);
+  }
+  // log-sum-exp over the ranks; +inf = no mass (salmon's LOG_0); `prior` (counted by every rank) is kept once
+  auto lse = [&](const double* vals, size_t n, const double* prior, std::vector<double>& res) -> int {
+    res.assign(vals, vals + n);
+    double ref = -INFINITY;
+    for (size_t i = 0; i < n; ++i) if (std::isfinite(vals[i])) ref = std::max(ref, vals[i]);
+    SB_TRY(sb_comm_allreduce(comm, &ref, 1, 0, 2));
+    if (!std::isfinite(ref)) return SB_OK;
+    std::vector<double> lin(n);
+    for (size_t i = 0; i < n; ++i) {
+      double v = std::isfinite(vals[i]) ? std::exp(vals[i] - ref) : 0.0;
+      if (prior) v = std::max(v - std::exp(prior[i] - ref), 0.0);
+      lin[i] = v;
+    }
+    SB_TRY(sb_comm_allreduce(comm, lin.data(), n, 0, 0));
+    for (size_t i = 0; i < n; ++i) {
+      const double tot = lin[i] + (prior ? std::exp(prior[i] - ref) : 0.0);
+      res[i] = tot > 0.0 ? ref + std::log(tot) : INFINITY;
+    }
+    return SB_OK;
+  };
+  std::vector<double> mass, hist, tot1;
+  SB_TRY(lse(p.mass, M, nullptr, mass));
+  SB_TRY(lse(p.fld_hist, nf, p.fld_prior_hist, hist));
+  SB_TRY(lse(&p.fld_tot, 1, &p.fld_prior_tot, tot1));
+  std::vector<uint64_t> uniq(p.unique_counts, p.unique_counts + M), total(p.total_counts, p.total_counts + M),
+      hits(p.cluster_hits, p.cluster_hits + M);
+  SB_TRY(sb_comm_allreduce(comm, uniq.data(), M, 1, 0));
+  SB_TRY(sb_comm_allreduce(comm, total.data(), M, 1, 0));
+  SB_TRY(sb_comm_allreduce(comm, hits.data(), M, 1, 0));
+  uint64_t scal[2] = {p.fld_min, p.assigned};
+  SB_TRY(sb_comm_allreduce(comm, &scal[0], 1, 1, 3));
+  SB_TRY(sb_comm_allreduce(comm, &scal[1], 1, 1, 0));
+  std::vector<uint32_t> roots((size_t)G * std::max<uint32_t>(M, 1));
+  SB_TRY(sb_comm_allgather(comm, p.cluster_root, roots.data(), (size_t)M * 4));
+  sb_map_partial g = p;
+  g.mass = mass.data(); g.fld_hist = hist.data(); g.fld_tot = tot1[0];
+  g.unique_counts = uniq.data(); g.total_counts = total.data(); g.cluster_hits = hits.data();
+  g.fld_min = (uint32_t)scal[0]; g.assigned = scal[1];
+  if (assigned_out) *assigned_out = scal[1];
+  return sb_map_project_global(ctx, &g, (uint32_t)G, roots.data(), out);
 }

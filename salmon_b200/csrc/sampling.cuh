@@ -310,7 +310,7 @@ extern "C" int sb_bootstrap(sb_em_ctx* c, const sb_em_params* p, double num_mapp
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   for (uint32_t b = 0; b < n_boot && rc_out == SB_OK; ++b) {
     SB_CUDA(cudaMemsetAsync(c->d_samp, 0, ((size_t)Cm + M + 1) * 8, st));
-    k_boot_sample<<<c->n_sm * 8, 256, 0, st>>>(total, b, k0, k1, c->d_cdf, C, c->d_cls_map, c->d_samp,
+    k_boot_sample<<<c->n_sm * 8, 256, 0, st>>>(total, b + c->sample_offset, k0, k1, c->d_cdf, C, c->d_cls_map, c->d_samp,
                                                 c->d_samp + Cm);
     if (Cm) k_u64_to_f64<<<nblk(Cm, 256), 256, 0, st>>>(Cm, c->d_samp, c->ov_cnt);
     k_u64_to_f64<<<nblk(M, 256), 256, 0, st>>>(M, c->d_samp + Cm, c->ov_base_tid);
@@ -387,7 +387,7 @@ extern "C" int sb_gibbs(sb_em_ctx* c, const double* alphas_init, int use_vbem, i
   k_gibbs_init<<<nblk(M, 256), 256, 0, st>>>(M, c->d_active, c->d_efflens, d_init, perTxp, prior,
                                               c->d_gibbs_prior, c->d_gibbs_cnt, c->d_gibbs_mu);
   std::vector<double> out(M);
-  uint32_t round = 0;
+  uint32_t round = c->sample_offset * thinning;   // a rank's share of a split run draws from its own rounds
   for (uint32_t sid = 0; sid < n_samples; ++sid) {
     if (nchains > 1 && sid > 0 && sid % step == 0 && sid / step < nchains)   // :457-461
       k_gibbs_init<<<nblk(M, 256), 256, 0, st>>>(M, c->d_active, c->d_efflens, d_init, perTxp, prior,

@@ -19,6 +19,21 @@ from . import _capi
 from ._capi import EMContext, EqClasses, MapContext, default_params, map_default_params
 
 
+def _drop_decoys(index, inputs):
+    """readExp.dropDecoyTranscripts() (SalmonQuantify.cpp:2479, ReadExperiment.hpp:120): decoys -- the suffix of the id
+    space, never part of a label -- leave before the optimiser and the writers.  Returns (Mq, inputs cut to Mq)."""
+    M = index.n_txps
+    fd = index.meta()["first_decoy"]
+    Mq = fd if fd < M else M
+    if Mq == M:
+        return M, inputs
+    cut = dict(inputs)
+    for k in ("projected_counts", "eff_len", "unique_counts", "total_counts"):
+        if k in cut and cut[k] is not None:
+            cut[k] = np.ascontiguousarray(cut[k][:Mq])
+    return Mq, cut
+
+
 def quant_reads(index, left, right, map_params=None, em_params=None, device=0, batch=262_144, dist=None,
                 names=None, out_dir=None, dump_eq=False, dump_eq_weights=False):
     """left/right: [n, L] uint8 base codes (0..3 = ACGT, 4 = N) of THIS rank's read shard.
@@ -40,7 +55,7 @@ def quant_reads(index, left, right, map_params=None, em_params=None, device=0, b
         inputs = ctx.project_global(g, roots)
         n_mapped = g["assigned"]
     ctx.close()
-    M = index.n_txps
+    M, inputs = _drop_decoys(index, inputs)
     eq = EqClasses(M, res["off"], res["tids"], res["weights"], res["counts"])
     em = EMContext(device)
     if world > 1:
@@ -56,7 +71,8 @@ def quant_reads(index, left, right, map_params=None, em_params=None, device=0, b
         meta = index.meta()
         if names is None and meta["names"]:
             nm = meta["names"]
-        lens = meta["complete_len"] if meta["complete_len"] is not None else index.tx_lengths()
+        nm = nm[:M]
+        lens = (meta["complete_len"] if meta["complete_len"] is not None else index.tx_lengths())[:M]
         _capi.write_quant_sf(os.path.join(out_dir, "quant.sf"), nm, lens, inputs["eff_len"], alpha,
                              float(n_mapped) if n_mapped else None)
         if dump_eq or dump_eq_weights:
@@ -81,7 +97,7 @@ def _quantify(index, ctx, ep, device, dist, names, out_dir, dump_eq, dump_eq_wei
         inputs = ctx.project_global(g, roots)
         n_mapped = g["assigned"]
     ctx.close()
-    M = index.n_txps
+    M, inputs = _drop_decoys(index, inputs)
     eq = EqClasses(M, res["off"], res["tids"], res["weights"], res["counts"])
     em = EMContext(device)
     if world > 1:
@@ -98,8 +114,8 @@ def _quantify(index, ctx, ep, device, dist, names, out_dir, dump_eq, dump_eq_wei
     if out_dir is not None and rank == 0:
         os.makedirs(os.path.join(out_dir, "aux_info"), exist_ok=True)
         meta = index.meta()
-        nm = names or meta["names"] or [f"t{i}" for i in range(M)]
-        lens = meta["complete_len"] if meta["complete_len"] is not None else index.tx_lengths()
+        nm = (names or meta["names"] or [f"t{i}" for i in range(index.n_txps)])[:M]
+        lens = (meta["complete_len"] if meta["complete_len"] is not None else index.tx_lengths())[:M]
         _capi.write_quant_sf(os.path.join(out_dir, "quant.sf"), nm, lens, inputs["eff_len"], alpha,
                              float(n_mapped) if n_mapped else None)
         if dump_eq or dump_eq_weights:

@@ -467,11 +467,12 @@ def test_parallel_splitter_adversarial_qualities(tmp_path, monkeypatch):
     assert got == want
 
 
-def test_quant_files_refuses_shards_and_bad_options():
-    """argument checks of the C++ driver happen before any device work"""
+def test_quant_files_argument_checks():
+    """argument checks of the C++ driver happen before any device work (a sharded run needs the communicator id;
+    posterior samples / class dumps need the whole table on one GPU)"""
     import ctypes as C
     idx = _capi.Index([encode(rand_seq(np.random.default_rng(1), 200))], k=31)
-    for kw, msg in ((dict(shard_count=2), "one whole library"), (dict(max_read_len=1000), "max_read_len"),
-                    (dict(num_bootstraps=2, num_gibbs=2), "not both")):
+    for kw, msg in ((dict(shard_count=2), "communicator id"), (dict(shard_count=2, shard_index=2), "below shard_count"),
+                    (dict(max_read_len=1000), "max_read_len"), (dict(num_bootstraps=2, num_gibbs=2), "not both")):
         with pytest.raises(_capi.SalmonB200Error, match=msg):
             _capi.quant_files_native(idx, "a.fq", "b.fq", **kw)

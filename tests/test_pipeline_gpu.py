@@ -145,3 +145,80 @@ def test_native_driver_and_cli_match_python_pipeline(tmp_path):
     assert abs(alpha2.sum() - sm2["n_mapped"]) < 1e-6 * sm2["n_mapped"]
     assert abs(int(sm2["n_mapped"]) - py2["n_mapped"]) <= 0.01 * py2["n_mapped"]     # different batch composition
     assert np.corrcoef(alpha2, py2["alpha"])[0, 1] > 0.999
+
+
+def test_decoys_are_dropped_and_run_metadata_is_written(tmp_path):
+    """with a decoy-aware index the optimiser, quant.sf and eq_classes.txt.gz see the real targets
+    only (readExp.dropDecoyTranscripts(), SalmonQuantify.cpp:2479); plus the run-metadata files of the drop-in contract
+    (GZipWriter.cpp:294-640, ReadExperiment.inl:219-350, MappingPipelineStages.cpp:164-173)."""
+    import json
+    import subprocess
+    from salmon_b200.quant import quant_files
+    txps, _ = synth_txome(seed=47, n_genes=100)
+    n_real = len(txps) - 25                      # the last 25 references act as decoys
+    left, right, truth = synth_reads(txps, seed=48, n=15000)
+    names = [f"ENST{i:05d}" for i in range(len(txps))]
+    idx = Index(txps, names=names, first_decoy=n_real)
+    f1, f2 = str(tmp_path / "d_1.fq"), str(tmp_path / "d_2.fq")
+    write_fastq(f1, left, gz=False); write_fastq(f2, right, gz=False)
+    out = tmp_path / "out"
+    alpha, sm = _capi.quant_files_native(idx, f1, f2, out_dir=str(out), batch=8192, max_read_len=128, dump_eq_weights=1, seed=3)
+    assert np.all(alpha[n_real:] == 0.0) and abs(alpha.sum() - sm["n_mapped"]) < 1e-6 * sm["n_mapped"]
+    rows = (out / "quant.sf").read_text().splitlines()
+    assert len(rows) == n_real + 1 and rows[-1].split("\t")[0] == names[n_real - 1]
+    eqf = _capi.read_eq_classes(str(out / "aux_info" / "eq_classes.txt.gz"))
+    assert eqf["n_txps"] == n_real and int(eqf["tids"].max()) < n_real
+    py = quant_files(idx, f1, f2, batch=8192, max_read_len=128)
+    assert len(py["alpha"]) == n_real and np.array_equal(py["alpha"], alpha[:n_real])
+    # the optimiser's uniform prior is totalWeight / M with M = real targets (CollapsedEMOptimizer.cpp:803): the oracle on
+    # the same classes with n_real transcripts reproduces alpha
+    eq = _capi.EqClasses(n_real, py["classes"]["off"], py["classes"]["tids"], py["classes"]["weights"], py["classes"]["counts"])
+    ref, _ = O.em_optimize(eq, py["projected_counts"], py["eff_len"], py["unique_counts"], _capi.default_params())
+    np.testing.assert_allclose(py["alpha"], ref, rtol=1e-9, atol=1e-9)
+    # ---- run metadata
+    meta = json.loads((out / "aux_info" / "meta_info.json").read_text())
+    assert meta["num_valid_targets"] == n_real and meta["num_decoy_targets"] == 25
+    assert meta["num_processed"] == 15000 and meta["num_mapped"] == sm["n_mapped"] and meta["opt_type"] == "vb"
+    assert meta["samp_type"] == "none" and meta["mapping_type"] == "mapping" and meta["serialized_eq_classes"] is True
+    assert abs(meta["percent_mapped"] - 100.0 * sm["n_mapped"] / 15000) < 1e-4
+    fld = np.frombuffer(gzip.open(out / "aux_info" / "fld.gz", "rb").read(), dtype=np.int32)
+    assert fld.shape[0] == 1001 and int(fld.sum()) == 10000 and abs(meta["frag_length_mean"] - 250) < 25
+    assert abs(float((np.arange(1001) * fld).sum()) / 10000 - meta["frag_length_mean"]) < 5
+    pmf = np.array((out / "libParams" / "flenDist.txt").read_text().split(), dtype=float)
+    assert pmf.shape[0] == 1001 and abs(pmf.sum() - 1.0) < 1e-3
+    lfc = json.loads((out / "lib_format_counts.json").read_text())
+    assert lfc["expected_format"] == "IU" and lfc["num_assigned_fragments"] == sm["n_mapped"]
+    amb = (out / "aux_info" / "ambig_info.tsv").read_text().splitlines()
+    assert amb[0] == "UniqueCount\tAmbigCount" and len(amb) == n_real + 1
+    assert sum(int(x.split("\t")[0]) + int(x.split("\t")[1]) for x in amb[1:]) >= sm["n_mapped"]
+    # cmd_info.json comes from the command line
+    ipath = tmp_path / "idx"; ipath.mkdir()
+    idx.save(str(ipath / "sb_index.bin"))
+    exe = os.path.join(os.path.dirname(_capi.LIB_PATH), "sb_salmon")
+    r = subprocess.run([exe, "quant", "-i", str(ipath), "-l", "IU", "-1", f1, "-2", f2, "-o", str(tmp_path / "cli"),
+                        "--batch", "8192", "--maxReadLen", "128", "--seed", "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ci = json.loads((tmp_path / "cli" / "cmd_info.json").read_text())
+    assert ci["libType"] == "IU" and ci["mates1"] == f1 and ci["batch"] == "8192"
+    assert (tmp_path / "cli" / "quant.sf").read_text() == (out / "quant.sf").read_text()
+
+
+def test_cli_eqclasses_bootstraps(tmp_path):
+    """`sb_salmon quant -e` through sb_quant_eqclasses: quant.sf + bootstraps.gz, equal to the Python mirror"""
+    import subprocess
+    from salmon_b200.quant import quant_eqclasses
+    eq, proj, eff, uniq = synth_eq(seed=15, C=6000, M=1500, total_count=200000)
+    names = [f"t{i}" for i in range(eq.n_txps)]
+    path = str(tmp_path / "eq_classes.txt.gz")
+    _capi.write_eq_classes(path, names, eq.off, eq.tids, eq.counts, eq.weights)
+    exe = os.path.join(os.path.dirname(_capi.LIB_PATH), "sb_salmon")
+    r = subprocess.run([exe, "quant", "-e", path, "-o", str(tmp_path / "o"), "--numBootstraps", "4", "--seed", "11"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    py = quant_eqclasses(path, num_bootstraps=4, seed=11)
+    raw = gzip.open(tmp_path / "o" / "aux_info" / "bootstrap" / "bootstraps.gz", "rb").read()
+    boots = np.frombuffer(raw, dtype=np.float64).reshape(4, eq.n_txps)
+    assert np.array_equal(boots, py["bootstraps"])
+    rows = (tmp_path / "o" / "quant.sf").read_text().splitlines()
+    got = np.array([float(x.split("\t")[4]) for x in rows[1:]])
+    np.testing.assert_allclose(got, py["alpha"], rtol=0, atol=6e-4)     # %.3f
