@@ -137,10 +137,16 @@ void write_cmd_info(const std::string& out, const std::vector<std::string>& argv
     else if (vals.size() == 1) fprintf(f, "\"%s\"", vals[0].c_str());
     else { fprintf(f, "["); for (size_t i = 0; i < vals.size(); ++i) fprintf(f, "%s\"%s\"", i ? ", " : "", vals[i].c_str()); fprintf(f, "]"); }
   };
+  static const char* const short_names[][2] = {{"i", "index"}, {"l", "libType"}, {"1", "mates1"}, {"2", "mates2"},
+                                                {"o", "output"}, {"p", "threads"}, {"r", "unmatedReads"}, {"e", "eqclasses"},
+                                                {"d", "dumpEqWeights"}, {"q", "quiet"}};
   for (const std::string& a : argv_all) {
-    if (a.size() > 1 && a[0] == '-' && !(a[1] >= '0' && a[1] <= '9')) {
+    const bool is_opt = a.size() > 1 && a[0] == '-' && (a == "-1" || a == "-2" || !(a[1] >= '0' && a[1] <= '9'));
+    if (is_opt) {
       flush();
       key = a.substr(a.find_first_not_of('-'));
+      for (auto& sn : short_names) if (key == sn[0]) key = sn[1];
+      if (key.size() > 1 && key[0] == '_') key.clear();       // the per-rank re-execution's own options
       vals.clear();
     } else if (!key.empty()) {
       vals.push_back(a);

@@ -126,10 +126,31 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
   return t;
 }
 
+// sum of (alpha' + prior) over my rows, in units of 2^-20: integer additions commute, so the total -- and with it
+// logNorm and every later bit of the run -- does not depend on which warp took which row (dynamic long-row queue) or
+// on how the ranges were cut (measured re-balancing): runs are bit-reproducible.  (logNorm only has to be the same
+// everywhere: any common factor of theta cancels in P1/P2.)
+constexpr double SUM_FIXED = 1048576.0;
 struct P2Acc {
-  double sum;     // sum of (alpha' + prior) over my rows
+  long long isum;
   double maxrel;  // max rel diff over my rows
 };
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// all threads of the block; scratch: >= 32 doubles of shared memory; result valid in every thread
+__device__ __forceinline__ long long block_sum_ll(long long v, double* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+  v = warp_sum_ll(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = __longlong_as_double(v);
+  __syncthreads();
+  long long r = (lane < nw) ? __double_as_longlong(scratch[lane]) : 0ll;
+  return warp_sum_ll(r);
+}
 
 // Per-warp TMA ring: each warp streams ITS contiguous column range of the SELL arrays
 // through a private shared-memory ring with 1-D bulk copies (lane 0 is the producer, the
@@ -227,7 +248,7 @@ __device__ __forceinline__ void row_finish(const EmArgs& A, uint32_t row, const 
     if (na > ALPHA_CHECK_CUTOFF) pa.maxrel = fmax(pa.maxrel, fabs(o.x3 - na) / na);
     A.alpha[row] = na;
     const double ap = na + pr;
-    pa.sum += ap;
+    pa.isum += __double2ll_rn(ap * SUM_FIXED);
     A.theta[row] = theta_of<VBEM>(na, ap, logNorm);
   } else {
     const uint32_t t = (uint32_t)__double_as_longlong(o.x3);
@@ -506,19 +527,19 @@ __device__ __forceinline__ void lag_lognorm_warp0(const EmArgs& A, uint32_t par,
                                                   double* scratch) {
   if (threadIdx.x < 32) {
     const double* part = A.sum_partial + (size_t)(par ^ 1u) * nblk;
-    double acc = 0.0;
-    for (uint32_t i = threadIdx.x; i < nblk; i += 32) acc += __ldcg(&part[i]);
-    acc = warp_sum(acc);
-    if (threadIdx.x == 0) scratch[33] = digamma_pos(acc + A.inactive_sum);
+    long long acc = 0;
+    for (uint32_t i = threadIdx.x; i < nblk; i += 32) acc += __double_as_longlong(__ldcg(&part[i]));
+    acc = warp_sum_ll(acc);
+    if (threadIdx.x == 0) scratch[33] = digamma_pos((double)acc / SUM_FIXED + A.inactive_sum);
   }
 }
 
 __device__ __forceinline__ void p2_finish(const EmArgs& A, double* scratch, P2Acc& pa,
                                           uint32_t par) {
-  double bs = block_reduce<false>(pa.sum, scratch);
+  const long long bs = block_sum_ll(pa.isum, scratch);
   double bm = block_reduce<true>(pa.maxrel, scratch);
   if (threadIdx.x == 0) {
-    A.sum_partial[(size_t)par * gridDim.x + blockIdx.x] = bs;
+    A.sum_partial[(size_t)par * gridDim.x + blockIdx.x] = __longlong_as_double(bs);   // fixed point, bit pattern
     if (bm > 0.0) atomicMax(&A.maxrel[par], (unsigned long long)__double_as_longlong(bm));
   }
 }
@@ -556,7 +577,7 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent(const __grid
     const bool dbg_acc = A.dbg && A.dbg_it == DBG_ACCUMULATE && it > 0;
     if (bid == 0 && threadIdx.x == 0) A.maxrel[par] = 0ull;
     if (VBEM && it > 0) lag_lognorm_warp0(A, par, nblk, scratch);  // consumed after the next barrier
-    P2Acc pa{0.0, 0.0};
+    P2Acc pa{0ll, 0.0};
     SB_DBG(0)
     SB_ACC_BEGIN(t1, 3)
     run_phase<1, CH, RING, VBEM, true>(A, W, R1, bid, nblk, 0.0, 0.0, pa, NoDeliver{});
@@ -715,7 +736,7 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_persistent_mgpu(const _
     const uint32_t epoch = (uint32_t)(A.epoch0 + it + 1ull);
     const DeliverPush push{A.peers, X.off_llrecv(), S, A.rank, epoch};
     const bool dbg_acc = A.dbg && A.dbg_it == DBG_ACCUMULATE && it > 0;
-    P2Acc pa{0.0, 0.0};
+    P2Acc pa{0ll, 0.0};
     SB_DBG(0)
     SB_ACC_BEGIN(t1, 3)
     run_phase<1, CH, RING, VBEM, true>(A, W, R1, bid, nblk, 0.0, 0.0, pa, NoDeliver{});
@@ -865,7 +886,7 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p1(const __grid_constan
   extern __shared__ __align__(128) unsigned char smem[];
   WarpCtx<CH, RING> W;
   warp_setup(W, smem);
-  P2Acc pa{0.0, 0.0};
+  P2Acc pa{0ll, 0.0};
   const WarpRange R = load_range(A.cm, blockIdx.x * (EM_THREADS / 32) + (threadIdx.x >> 5));
   ring_prefetch(A.cm, W, R);
   run_phase<1, CH, RING, VBEM, false>(A, W, R, blockIdx.x, gridDim.x, 0.0, 0.0, pa, NoDeliver{});
@@ -888,7 +909,7 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p2(const __grid_constan
     }
   }
   const double bias = (it == 0) ? A.first_bias : 0.0;
-  P2Acc pa{0.0, 0.0};
+  P2Acc pa{0ll, 0.0};
   const WarpRange R = load_range(A.tm, blockIdx.x * (EM_THREADS / 32) + (threadIdx.x >> 5));
   ring_prefetch(A.tm, W, R);
   run_phase<2, CH, RING, VBEM, false>(A, W, R, blockIdx.x, gridDim.x, logNorm, bias, pa, NoDeliver{});
@@ -899,7 +920,7 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) k_em_p2_partial(const __grid
   extern __shared__ __align__(128) unsigned char smem[];
   WarpCtx<CH, RING> W;
   warp_setup(W, smem);
-  P2Acc pa{0.0, 0.0};
+  P2Acc pa{0ll, 0.0};
   const WarpRange R = load_range(A.tm, blockIdx.x * (EM_THREADS / 32) + (threadIdx.x >> 5));
   ring_prefetch(A.tm, W, R);
   run_phase<3, CH, RING, VBEM, false>(A, W, R, blockIdx.x, gridDim.x, 0.0, 0.0, pa, DeliverLocal{A.part_out});

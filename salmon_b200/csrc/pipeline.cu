@@ -533,10 +533,7 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
   if (rc != SB_OK) return rc;
   sb_map_result glob = res;          // per-transcript inputs of the optimiser
   uint64_t n_mapped_u = res.n_mapped, n_observed = bs.n_observed;
-  if (multi) {
-    SB_TRY(sb_map_reduce_global(S.ctx, S.comm, &glob, &n_mapped_u));
-    SB_TRY(sb_comm_allreduce(S.comm, &n_observed, 1, 1, 0));
-  }
+  if (multi) SB_TRY(sb_map_reduce_global(S.ctx, S.comm, &glob, &n_mapped_u));   // (every rank's reader sees the whole stream: n_observed is global already)
   sb_eq_csr eq;
   eq.n_classes = res.n_classes; eq.n_txps = Mq; eq.off = res.off; eq.tids = res.tids; eq.weights = res.weights; eq.counts = res.counts;
   std::vector<double> alpha(M, 0.0);

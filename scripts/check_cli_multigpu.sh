@@ -41,7 +41,10 @@ def sf(p):
 a1, t1 = sf("/tmp/mg/one/quant.sf"); aN, tN = sf("/tmp/mg/multi/quant.sf")
 m1 = json.load(open("/tmp/mg/one/aux_info/meta_info.json")); mN = json.load(open("/tmp/mg/multi/aux_info/meta_info.json"))
 r = np.corrcoef(a1, aN)[0, 1]
-ok = m1["num_mapped"] == mN["num_mapped"] and m1["num_processed"] == mN["num_processed"] and abs(a1.sum() - aN.sum()) < 1e-3 * a1.sum() and r > 0.9995
+conds = dict(mapped=m1["num_mapped"] == mN["num_mapped"], processed=m1["num_processed"] == mN["num_processed"],
+             total=abs(a1.sum() - aN.sum()) < 1e-3 * a1.sum(), corr=r > 0.9995)
+ok = all(conds.values())
+print(conds, m1["num_processed"], mN["num_processed"], a1.sum(), aN.sum())
 print(f"reads: mapped {m1['num_mapped']} vs {mN['num_mapped']} on {mN['sb_num_gpus']} GPUs, corr(NumReads) {r:.6f}, max |dTPM| {np.abs(t1 - tN).max():.3f} -> {'OK' if ok else 'FAIL'}")
 def boots(p, n):
     raw = gzip.open(p + "/aux_info/bootstrap/bootstraps.gz", "rb").read()
