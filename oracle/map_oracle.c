@@ -4,7 +4,7 @@
  */
 #include "map_oracle.h"
 #include "em_oracle.h"
-#include "../include/sb_detmath.h"
+#include "orc_math.h"
 
 #include <limits.h>
 #include <math.h>
@@ -26,12 +26,21 @@ static double logAdd(double x, double y) {
   return x + log(1 + exp(y - x));
 }
 
-/* the same function on the deterministic exp/log (per-alignment arithmetic, see sb_detmath.h) */
+int orc_math_mode_ = ORC_MATH_LIBM;
+void orc_set_math_mode(int mode) { orc_math_mode_ = mode ? ORC_MATH_FDLIBM : ORC_MATH_LIBM; }
+int orc_get_math_mode(void) { return orc_math_mode_; }
+/* test tap: exp over x[], log over y[] in the given mode */
+void orc_math_probe(int mode, uint64_t nx, const double* x, double* ex, uint64_t ny, const double* y, double* ly) {
+  for (uint64_t i = 0; i < nx; ++i) ex[i] = mode ? orc_fd_exp(x[i]) : exp(x[i]);
+  for (uint64_t i = 0; i < ny; ++i) ly[i] = mode ? orc_fd_log(y[i]) : log(y[i]);
+}
+
+/* the same function on the mode's exp/log (per-alignment arithmetic, see orc_math.h) */
 static double logAddDet(double x, double y) {
   if (fabs(x) == LOG_0) return y;
   if (fabs(y) == LOG_0) return x;
   if (y > x) { double t = x; x = y; y = t; }
-  return x + sbm_det_log(1 + sbm_det_exp(y - x));
+  return x + m_log(1 + m_exp(y - x));
 }
 
 /* ---------------------------------------------------------------- FLD tables
@@ -421,7 +430,7 @@ static int map_reads_core(const orc_index* ix, const orc_map_params* p, const fl
     for (uint32_t q = 0; q < nkept; ++q) {
       const joint_t* j = &jh[perm[q].idx];
       double v = (double)bestScore - (double)scores[perm[q].idx];
-      double estAlnProb = p->hard_filter ? -1.0 : sbm_det_exp(-p->score_exp * v);
+      double estAlnProb = p->hard_filter ? -1.0 : m_exp(-p->score_exp * v);
       if (!p->hard_filter && estAlnProb < p->min_aln_prob) continue;
       const cand_t* first = (j->status == 2) ? &rcand[j->ri] : &lc[j->li];
       aln_tid[base + na] = j->tid;
@@ -451,7 +460,7 @@ static int map_reads_core(const orc_index* ix, const orc_map_params* p, const fl
       const uint32_t status = (aln_flags[base + a] >> 2) & 3;
       const int fwd = aln_flags[base + a] & 1, mateFwd = (aln_flags[base + a] >> 1) & 1;
       const double coverage = aln_prob[base + a];
-      const double logFragCov = (coverage > 0) ? sbm_det_log(coverage) : LOG_1;          /* :602-603 */
+      const double logFragCov = (coverage > 0) ? m_log(coverage) : LOG_1;          /* :602-603 */
       int32_t flen = aln_flen[base + a];
       if (status == 0 && fwd != mateFwd) {                                       /* :629-632 fragLengthPedantic */
         int32_t pos = aln_pos[base + a], mpos = aln_mate_pos[base + a];
@@ -485,7 +494,7 @@ static int map_reads_core(const orc_index* ix, const orc_map_params* p, const fl
       auxDenom = logAddDet(auxDenom, aux[a]);
     }
     for (uint32_t a = 0; a < na; ++a) {                                            /* :818-820 */
-      weight[base + a] = sbm_det_exp(aux[a] - auxDenom);
+      weight[base + a] = m_exp(aux[a] - auxDenom);
       label[(size_t)r * 2 * cap + a] = aln_tid[base + a];
     }
     if (p->range_bins > 0) {                                                        /* :845-853 */
@@ -509,9 +518,32 @@ int orc_map_reads(const orc_index* ix, const orc_map_params* p, const uint8_t* l
                   uint32_t* label, double* weight, orc_map_counters* ctr) {
   fld_t fld;
   fld_init(&fld, p->fld_mean, p->fld_sd, p->max_frag_len);
-  int rc = map_reads_core(ix, p, &fld, frag_counter >= p->num_pre_burnin, frag_counter >= p->num_burnin, NULL, left,
-                          right, n, L, n_aln, aln_tid, aln_score, aln_prob, aln_pos, aln_mate_pos, aln_flags, aln_flen,
-                          label, weight, ctr);
+  /* reads are independent here (no online state): chunks of reads in parallel, counters summed (test-harness speed:
+   * the at-scale pinning tests map 10^6 pairs) */
+  const uint32_t CH = 2048, cap = p->max_read_occ;
+  const uint32_t nchunk = (n + CH - 1) / CH;
+  int rc = 0;
+  orc_map_counters tot;
+  memset(&tot, 0, sizeof tot);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (uint32_t c = 0; c < nchunk; ++c) {
+    const size_t o = (size_t)c * CH;
+    const uint32_t m = (uint32_t)((o + CH <= n) ? CH : n - o);
+    orc_map_counters cc;
+    memset(&cc, 0, sizeof cc);
+    int r = map_reads_core(ix, p, &fld, frag_counter >= p->num_pre_burnin, frag_counter >= p->num_burnin, NULL, left + o * L,
+                           right + o * L, m, L, n_aln + o, aln_tid + o * cap, aln_score + o * cap, aln_prob + o * cap,
+                           aln_pos + o * cap, aln_mate_pos + o * cap, aln_flags + o * cap, aln_flen + o * cap,
+                           label + o * 2 * cap, weight + o * cap, &cc);
+#pragma omp critical
+    {
+      if (r) rc = r;
+      const uint64_t* src = (const uint64_t*)&cc;
+      uint64_t* dst = (uint64_t*)&tot;
+      for (size_t i = 0; i < sizeof(orc_map_counters) / 8; ++i) dst[i] += src[i];
+    }
+  }
+  if (ctr) *ctr = tot;
   fld_free(&fld);
   return rc;
 }
@@ -618,8 +650,8 @@ orc_online* orc_online_create(const orc_index* ix, const orc_map_params* p, uint
   for (uint32_t t = 0; t < on->M; ++t) {
     const double len = (double)(ix->off[t + 1] - ix->off[t]);
     on->mass[t] = LOG_0;
-    on->prior[t] = sbm_det_log(0.005 * len);           /* Transcript(id, name, len, alpha = 0.005): priorMass_ = log(alpha*len) */
-    on->log_eff[t] = sbm_det_log(len);
+    on->prior[t] = m_log(0.005 * len);           /* Transcript(id, name, len, alpha = 0.005): priorMass_ = log(alpha*len) */
+    on->log_eff[t] = m_log(len);
   }
   fld_init(&on->fld, p->fld_mean, p->fld_sd, p->max_frag_len);
   on->min_val = p->max_frag_len;
@@ -659,9 +691,9 @@ static void online_fragment(orc_online* on, uint32_t r, uint32_t L, uint32_t na,
       flen = (p1 > p2) ? p1 - p2 : p2 - p1;
       fped[a] = flen;
     }
-    const double logRefLength = on->burned_in ? on->log_eff[ti] : sbm_det_log((double)refLen);      /* :617-623 */
+    const double logRefLength = on->burned_in ? on->log_eff[ti] : m_log((double)refLen);      /* :617-623 */
     double startPosProb = -logRefLength;                                                           /* :749-757 */
-    if (status == 0) startPosProb = ((double)flen <= refLength) ? -sbm_det_log(refLength - (double)flen + 1) : LOG_EPSILON;
+    if (status == 0) startPosProb = ((double)flen <= refLength) ? -m_log(refLength - (double)flen + 1) : LOG_EPSILON;
     const double transcriptLogCount = logAddDet(on->prior[ti], on->mass[ti]);                       /* mass(initialRound) */
     lp[a] = transcriptLogCount + aux[a] + startPosProb;                                            /* :785 */
     S = logAddDet(S, lp[a]);                                                                        /* :792 */
@@ -669,12 +701,12 @@ static void online_fragment(orc_online* on, uint32_t r, uint32_t L, uint32_t na,
   const uint64_t g = on->frags_seen + r;
   for (uint32_t a = 0; a < na; ++a) {
     const double nlp = lp[a] - S;                                                                   /* :865 */
-    on->mass_acc[tid[a]] += (uint64_t)quant40(sbm_det_exp(fmv - ref + nlp));                        /* :871-872 */
+    on->mass_acc[tid[a]] += (uint64_t)quant40(m_exp(fmv - ref + nlp));                        /* :871-872 */
     if (!on->burned_in) {                                                                           /* :974-983 */
       uint32_t rnd[4];
       orc_philox4x32((uint32_t)g, (uint32_t)(g >> 32), a, 3u, (uint32_t)on->seed, (uint32_t)(on->seed >> 32), rnd);
       const double u = (double)rnd[0] * (1.0 / 4294967296.0);
-      if (u < sbm_det_exp(nlp) && fped[a] > 0) {
+      if (u < m_exp(nlp) && fped[a] > 0) {
         /* FragmentLengthDistribution::addVal(len, logForgettingMass), :84-106; kernel = binomial(4, 0.5) */
         static const double kern_lin[5] = {1.0 / 16, 4.0 / 16, 6.0 / 16, 4.0 / 16, 1.0 / 16};
         uint64_t len = (uint64_t)fped[a];
@@ -683,7 +715,7 @@ static void online_fragment(orc_online* on, uint32_t r, uint32_t L, uint32_t na,
         int64_t off = (int64_t)len - 2;
         for (int i = 0; i < 5; ++i, ++off)
           if (off > 0 && off < (int64_t)on->nfld)
-            on->fld_acc[off] += (uint64_t)quant40(sbm_det_exp(fmv - ref + sbm_det_log(kern_lin[i])));
+            on->fld_acc[off] += (uint64_t)quant40(m_exp(fmv - ref + m_log(kern_lin[i])));
       }
     }
   }
@@ -699,7 +731,7 @@ static void online_eff_lengths(orc_online* on) {
   double sum = LOG_0;
   for (uint64_t i = minV; i <= maxV; ++i) { logPMF[i - minV] = on->fld.hist[i] - on->fld.tot; sum = logAddDet(sum, logPMF[i - minV]); }
   double* pmf = (double*)calloc(maxV + 1, sizeof(double));
-  for (uint64_t i = minV; i < maxV; ++i) pmf[i] = 100.0 * sbm_det_exp(logPMF[i - minV] - sum);
+  for (uint64_t i = minV; i < maxV; ++i) pmf[i] = 100.0 * m_exp(logPMF[i - minV] - sum);
   const uint64_t maxLen = maxV + 1;
   double* cf = (double*)calloc(maxLen, sizeof(double));
   double vals = 0.0, mult = pmf[0];
@@ -713,7 +745,7 @@ static void online_eff_lengths(orc_online* on) {
     const double c = (origLen >= (double)maxLen) ? cf[maxLen - 1] : cf[(uint64_t)origLen];
     double effLen = origLen - c;
     if (effLen < 1.0) effLen = origLen;
-    on->log_eff[t] = sbm_det_log(effLen);
+    on->log_eff[t] = m_log(effLen);
   }
   free(logPMF); free(pmf); free(cf);
 }
@@ -734,18 +766,18 @@ int orc_online_batch(orc_online* on, const uint8_t* left, const uint8_t* right, 
   /* fold the batch into the state */
   for (uint32_t t = 0; t < on->M; ++t)
     if (on->mass_acc[t]) {
-      on->mass[t] = logAddDet(on->mass[t], on->batch_ref + sbm_det_log((double)on->mass_acc[t] * (1.0 / MASS_SCALE)));
+      on->mass[t] = logAddDet(on->mass[t], on->batch_ref + m_log((double)on->mass_acc[t] * (1.0 / MASS_SCALE)));
       on->mass_acc[t] = 0;
     }
   uint64_t tot_acc = 0;
   for (uint32_t j = 0; j < nfld; ++j)
     if (on->fld_acc[j]) {
-      on->fld.hist[j] = logAddDet(on->fld.hist[j], on->batch_ref + sbm_det_log((double)on->fld_acc[j] * (1.0 / MASS_SCALE)));
+      on->fld.hist[j] = logAddDet(on->fld.hist[j], on->batch_ref + m_log((double)on->fld_acc[j] * (1.0 / MASS_SCALE)));
       tot_acc += on->fld_acc[j];
       on->fld_acc[j] = 0;
     }
   if (tot_acc) {
-    on->fld.tot = logAddDet(on->fld.tot, on->batch_ref + sbm_det_log((double)tot_acc * (1.0 / MASS_SCALE)));
+    on->fld.tot = logAddDet(on->fld.tot, on->batch_ref + m_log((double)tot_acc * (1.0 / MASS_SCALE)));
     if (on->batch_min < on->min_val) on->min_val = on->batch_min;
     for (uint32_t j = 0; j < nfld; ++j) on->fld.pmf_live[j] = on->fld.hist[j] - on->fld.tot;
   }
@@ -773,7 +805,7 @@ void orc_online_state(const orc_online* on, double* mass_out, double* hist_out, 
   if (log_eff_out) memcpy(log_eff_out, on->log_eff, on->M * sizeof(double));
   if (scalars) {
     scalars[0] = on->assigned; scalars[1] = on->frags_seen; scalars[2] = on->timestep; scalars[3] = (uint64_t)on->burned_in;
-    scalars[4] = on->min_val; scalars[5] = sbm_d2u(on->fld.tot);
+    scalars[4] = on->min_val; scalars[5] = orc_d2u(on->fld.tot);
   }
 }
 
@@ -815,13 +847,13 @@ int orc_online_finish(orc_online* on, uint64_t n_classes, const uint64_t* off, c
     if (e == b) continue;
     double clusterHits = 0.0, logClusterMass = LOG_0;
     for (uint32_t q = b; q < e; ++q) { clusterHits += hits[memb[q]]; logClusterMass = logAddDet(logClusterMass, on->mass[memb[q]]); }
-    const double logClusterCount = sbm_det_log(clusterHits);
+    const double logClusterCount = m_log(clusterHits);
     int requiresProjection = 0;
     for (uint32_t q = b; q < e; ++q) {
       const uint32_t t = memb[q];
       if (on->mass[t] == LOG_0) projected[t] = 0.0;
       else {
-        projected[t] = sbm_det_exp((on->mass[t] - logClusterMass) + logClusterCount);
+        projected[t] = m_exp((on->mass[t] - logClusterMass) + logClusterCount);
         requiresProjection |= projected[t] > (double)total[t] || projected[t] < (double)unique[t];
       }
     }
@@ -844,7 +876,7 @@ int orc_online_finish(orc_online* on, uint64_t n_classes, const uint64_t* off, c
       }
     }
   }
-  for (uint32_t t = 0; t < M; ++t) eff_len[t] = sbm_det_exp(on->log_eff[t]);   /* CollapsedEMOptimizer.cpp:782-784 */
+  for (uint32_t t = 0; t < M; ++t) eff_len[t] = m_exp(on->log_eff[t]);   /* CollapsedEMOptimizer.cpp:782-784 */
   free(parent); free(hits); free(root); free(start); free(memb); free(fill); free(bound);
   return 0;
 }

@@ -106,6 +106,12 @@ void orc_online_state(const orc_online* on, double* mass_out, double* hist_out, 
 int orc_online_finish(orc_online* on, uint64_t n_classes, const uint64_t* off, const uint32_t* tids,
                       const uint64_t* counts, double* projected, double* eff_len, uint64_t* unique, uint64_t* total);
 
+/* exp / log of the per-alignment arithmetic: 0 = the platform libm (default: what the reference calls), 1 = the
+ * fdlibm restatement of orc_math.h (bit-exact regression mode, the algorithm of the product's device code) */
+void orc_set_math_mode(int mode);
+int orc_get_math_mode(void);
+void orc_math_probe(int mode, uint64_t nx, const double* x, double* ex, uint64_t ny, const double* y, double* ly);
+
 #ifdef __cplusplus
 }
 #endif

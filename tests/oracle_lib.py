@@ -48,8 +48,30 @@ def load():
         lib = C.CDLL(LIB)
         lib.orc_digamma.restype = C.c_double
         lib.orc_digamma.argtypes = [C.c_double]
+        # The C default is the platform libm (what the reference's std::exp / std::log are).  The regression tests demand
+        # bit-exact labels / integer accumulators from the CUDA path, so the harness switches the oracle to its fdlibm
+        # restatement (oracle/orc_math.h: the ALGORITHM the device code implements); the pinning tests
+        # (tests/test_math_pinning.py, tests/test_map_gpu.py::test_gpu_vs_libm_oracle_at_scale) switch back with
+        # math_mode("libm") and account for every label that differs.
+        lib.orc_set_math_mode(1)
         _lib = lib
     return _lib
+
+
+class math_mode:
+    """with math_mode("libm"): ...  -- exp / log of the Stage A oracle for the duration of the block"""
+
+    def __init__(self, mode):
+        self.mode = {"libm": 0, "fdlibm": 1}[mode]
+
+    def __enter__(self):
+        lib = load()
+        self.prev = lib.orc_get_math_mode()
+        lib.orc_set_math_mode(self.mode)
+        return self
+
+    def __exit__(self, *a):
+        load().orc_set_math_mode(self.prev)
 
 
 def params_from(p, n_threads=0) -> orc_em_params:
