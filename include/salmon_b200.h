@@ -278,6 +278,13 @@ typedef struct sb_map_params {
   uint64_t seed;              /* stream of the stochastic FLD update (the reference seeds from random_device) */
   uint32_t mini_batch;        /* reads per forgetting-mass timestep (miniBatchSize 5000) */
   uint32_t reserved2;
+  /* join policy (pufferfish::util::MappingConstraintPolicy as salmon configures it, SalmonMappingUtils.hpp:208-220;
+   * option texts src/cli/ProgramOptionsGenerator.cpp:111-137,198-201): */
+  double pre_merge_thresh;    /* preMergeChainSubThresh 0.75: per mate and transcript, chains below this fraction of the best are dropped */
+  double post_merge_thresh;   /* postMergeChainSubThresh 0.9: per transcript, chain pairs below this fraction of the best pair are dropped */
+  double orphan_thresh;       /* orphanChainSubThresh 0.95: without a concordant pair, orphans below this fraction of the best chain are dropped */
+  int32_t allow_dovetail;     /* allowDovetail (false): dovetailing mates count as concordant */
+  int32_t allow_orphans;      /* !discardOrphansQuasi (true): orphan mappings when no pair exists */
 } sb_map_params;
 void sb_map_default_params(sb_map_params* p);
 

@@ -374,22 +374,59 @@ static int map_reads_core(const orc_index* ix, const orc_map_params* p, const fl
     n_aln[r] = 0;
     uint32_t nl = mate_candidates(ix, p, rl, L, lc, &local);
     uint32_t nr = mate_candidates(ix, p, rr, L, rcand, &local);
-    /* ---- join (library type IU: inward, unstranded) */
+    /* ---- join (library type IU: inward, unstranded) with the constraint policy salmon sets
+     *      (SalmonMappingUtils.hpp:208-220; ProgramOptionsGenerator.cpp:111-137,198-201; MAPSPEC step 4):
+     *      pre-merge filter per mate and transcript, concordant pairs, post-merge filter per transcript, pair consensus
+     *      over the read, else orphans above the orphan threshold */
     uint32_t nj = 0;
-    for (uint32_t a = 0; a < nl; ++a)
-      for (uint32_t b = 0; b < nr; ++b) {
-        if (lc[a].tid != rcand[b].tid || lc[a].ori == rcand[b].ori) continue;
-        int32_t start, end; int ok;
-        if (lc[a].ori == 0) { start = lc[a].diag_c; end = rcand[b].diag_c + (int32_t)L; ok = rcand[b].diag_c >= lc[a].diag_c; }
-        else { start = rcand[b].diag_c; end = lc[a].diag_c + (int32_t)L; ok = lc[a].diag_c >= rcand[b].diag_c; }
-        int32_t fl = end - start;
-        if (!ok || fl <= 0 || fl > (int32_t)p->max_frag_len) continue;
-        joint_t j; j.tid = lc[a].tid; j.li = (int32_t)a; j.ri = (int32_t)b; j.frag_len = fl; j.status = 0;
-        jh[nj++] = j;
+    {
+      uint8_t okl[MAXCAND], okr[MAXCAND];
+      for (uint32_t a = 0; a < nl; ++a) {                 /* best chain of this mate on the transcript of chain a */
+        uint32_t best = 0;
+        for (uint32_t q = 0; q < nl; ++q) if (lc[q].tid == lc[a].tid && lc[q].cov > best) best = lc[q].cov;
+        okl[a] = (double)lc[a].cov >= p->pre_merge_thresh * (double)best;
       }
-    if (nj == 0) {  /* orphans: lefts precede rights (SalmonQuantify.cpp:1407-1420) */
-      for (uint32_t a = 0; a < nl; ++a) { joint_t j; j.tid = lc[a].tid; j.li = (int32_t)a; j.ri = -1; j.frag_len = 0; j.status = 1; jh[nj++] = j; }
-      for (uint32_t b = 0; b < nr; ++b) { joint_t j; j.tid = rcand[b].tid; j.li = -1; j.ri = (int32_t)b; j.frag_len = 0; j.status = 2; jh[nj++] = j; }
+      for (uint32_t b = 0; b < nr; ++b) {
+        uint32_t best = 0;
+        for (uint32_t q = 0; q < nr; ++q) if (rcand[q].tid == rcand[b].tid && rcand[q].cov > best) best = rcand[q].cov;
+        okr[b] = (double)rcand[b].cov >= p->pre_merge_thresh * (double)best;
+      }
+      /* all geometrically valid pairs, left-major */
+      uint32_t npair = 0, best_all = 0;
+      for (uint32_t a = 0; a < nl; ++a)
+        for (uint32_t b = 0; b < nr; ++b) {
+          if (!okl[a] || !okr[b] || lc[a].tid != rcand[b].tid || lc[a].ori == rcand[b].ori) continue;
+          const cand_t* fw = lc[a].ori == 0 ? &lc[a] : &rcand[b];
+          const cand_t* rv = lc[a].ori == 0 ? &rcand[b] : &lc[a];
+          int32_t start = fw->diag_c, end = rv->diag_c + (int32_t)L;
+          if (rv->diag_c < fw->diag_c) {                  /* dovetail */
+            if (!p->allow_dovetail) continue;
+            start = rv->diag_c; end = fw->diag_c + (int32_t)L;
+          }
+          const int32_t fl = end - start;
+          if (fl <= 0 || fl > (int32_t)p->max_frag_len) continue;
+          joint_t j; j.tid = lc[a].tid; j.li = (int32_t)a; j.ri = (int32_t)b; j.frag_len = fl; j.status = 0;
+          jh[npair++] = j;
+          const uint32_t sc = lc[a].cov + rcand[b].cov;
+          if (sc > best_all) best_all = sc;
+        }
+      /* post-merge per transcript + consensus over the read; order kept */
+      for (uint32_t q = 0; q < npair; ++q) {
+        const uint32_t sc = lc[jh[q].li].cov + rcand[jh[q].ri].cov;
+        uint32_t best_t = 0;
+        for (uint32_t w = 0; w < npair; ++w)
+          if (jh[w].tid == jh[q].tid) { const uint32_t s2 = lc[jh[w].li].cov + rcand[jh[w].ri].cov; if (s2 > best_t) best_t = s2; }
+        if ((double)sc < p->post_merge_thresh * (double)best_t || (double)sc < p->consensus_frac * (double)best_all) { jh[q].status = 9; }
+      }
+      for (uint32_t q = 0; q < npair; ++q) if (jh[q].status == 0) jh[nj++] = jh[q];
+      if (nj == 0 && p->allow_orphans) {  /* orphans: lefts precede rights (SalmonQuantify.cpp:1407-1420) */
+        uint32_t best_c = 0;
+        for (uint32_t a = 0; a < nl; ++a) if (okl[a] && lc[a].cov > best_c) best_c = lc[a].cov;
+        for (uint32_t b = 0; b < nr; ++b) if (okr[b] && rcand[b].cov > best_c) best_c = rcand[b].cov;
+        const double thr = p->orphan_thresh * (double)best_c;
+        for (uint32_t a = 0; a < nl; ++a) if (okl[a] && (double)lc[a].cov >= thr) { joint_t j; j.tid = lc[a].tid; j.li = (int32_t)a; j.ri = -1; j.frag_len = 0; j.status = 1; jh[nj++] = j; }
+        for (uint32_t b = 0; b < nr; ++b) if (okr[b] && (double)rcand[b].cov >= thr) { joint_t j; j.tid = rcand[b].tid; j.li = -1; j.ri = (int32_t)b; j.frag_len = 0; j.status = 2; jh[nj++] = j; }
+      }
     }
     if (nj == 0 || nj > cap) continue;   /* unmapped, or more than maxReadOcc places */
     /* ---- scoring + updateRefMappings (SalmonMappingUtils.hpp:225-281) */

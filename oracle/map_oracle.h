@@ -48,6 +48,13 @@ typedef struct orc_map_params {
   double fld_mean, fld_sd;    /* 250, 25 */
   uint64_t num_pre_burnin;    /* 5000 */
   uint64_t num_burnin;        /* 5000000 */
+  /* join policy as salmon configures pufferfish's MappingConstraintPolicy (SalmonMappingUtils.hpp:208-220; option
+   * texts ProgramOptionsGenerator.cpp:111-137,198-201; defaults SalmonDefaults.hpp:28-30,46) */
+  double pre_merge_thresh;    /* 0.75 */
+  double post_merge_thresh;   /* 0.9 */
+  double orphan_thresh;       /* 0.95 */
+  int32_t allow_dovetail;     /* 0 */
+  int32_t allow_orphans;      /* 1 */
 } orc_map_params;
 
 /* per-dataset counters for the roofline accounting of SURVEY.md section 8d */

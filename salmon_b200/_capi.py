@@ -81,6 +81,8 @@ class sb_map_params(C.Structure):
         ("min_aln_prob", C.c_double), ("decoy_threshold", C.c_double), ("fld_mean", C.c_double), ("fld_sd", C.c_double),
         ("num_pre_burnin", C.c_uint64), ("num_burnin", C.c_uint64),
         ("seed", C.c_uint64), ("mini_batch", C.c_uint32), ("reserved2", C.c_uint32),
+        ("pre_merge_thresh", C.c_double), ("post_merge_thresh", C.c_double), ("orphan_thresh", C.c_double),
+        ("allow_dovetail", C.c_int32), ("allow_orphans", C.c_int32),
     ]
 
 

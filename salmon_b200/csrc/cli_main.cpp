@@ -58,7 +58,8 @@ int usage() {
           "  sb_salmon quant -i index_dir -l IU -1 r1.fq[.gz] ... -2 r2.fq[.gz] ... -o out_dir [-p threads] [--dumpEq] [--dumpEqWeights]\n"
           "                  [--numBootstraps N | --numGibbsSamples N] [--thinningFactor 16] [--noGammaDraw] [--useEM] [--vbPrior 0.01]\n"
           "                  [--perNucleotidePrior] [--maxReadOcc 200] [--maxOccsPerHit 1000] [--minScoreFraction 0.65] [--consensusSlack 0.35]\n"
-          "                  [--hardFilter] [--rangeFactorizationBins 4] [--fldMean 250] [--fldSD 25] [--fldMax 1000] [--scoreExp 1]\n"
+          "                  [--preMergeChainSubThresh 0.75] [--postMergeChainSubThresh 0.9] [--orphanChainSubThresh 0.95] [--allowDovetail]\n"
+          "                  [--discardOrphansQuasi] [--hardFilter] [--rangeFactorizationBins 4] [--fldMean 250] [--fldSD 25] [--fldMax 1000] [--scoreExp 1]\n"
           "                  [--numPreAuxModelSamples 5000] [--numAuxModelSamples 5000000] [--gpu 0] [--batch 262144] [--maxReadLen 256] [--seed 42]\n"
           "  sb_salmon quant -e eq_classes.txt[.gz] -o out_dir [--useEM] [--numBootstraps N]\n",
           sb_version());
@@ -223,6 +224,11 @@ int cmd_quant(Args& a) {
     else if (o == "--minScoreFraction") { if (!num(mp.min_score_fraction)) return usage(); }
     else if (o == "--consensusSlack") { if (!num(d)) return usage(); mp.consensus_frac = 1.0 - d; }
     else if (o == "--hardFilter") mp.hard_filter = 1;
+    else if (o == "--preMergeChainSubThresh") { if (!num(mp.pre_merge_thresh)) return usage(); }
+    else if (o == "--postMergeChainSubThresh") { if (!num(mp.post_merge_thresh)) return usage(); }
+    else if (o == "--orphanChainSubThresh") { if (!num(mp.orphan_thresh)) return usage(); }
+    else if (o == "--allowDovetail") mp.allow_dovetail = 1;
+    else if (o == "--discardOrphansQuasi") mp.allow_orphans = 0;
     else if (o == "--rangeFactorizationBins") { if (!num(d)) return usage(); mp.range_bins = (uint32_t)d; }
     else if (o == "--fldMean") { if (!num(mp.fld_mean)) return usage(); }
     else if (o == "--fldSD") { if (!num(mp.fld_sd)) return usage(); }

@@ -934,6 +934,8 @@ extern "C" void sb_map_default_params(sb_map_params* q) {
   q->score_exp = 1.0; q->min_aln_prob = 1e-5; q->decoy_threshold = 1.0; q->fld_mean = 250.0; q->fld_sd = 25.0;
   q->num_pre_burnin = 5000; q->num_burnin = 5000000;
   q->seed = 42; q->mini_batch = 5000;
+  q->pre_merge_thresh = 0.75; q->post_merge_thresh = 0.9; q->orphan_thresh = 0.95;   // SalmonDefaults.hpp:28-30
+  q->allow_dovetail = 0; q->allow_orphans = 1;                                         // :46, discardOrphansQuasi = false
 }
 
 static void build_fld_host(const Params& p, std::vector<double>& t) {
@@ -1029,6 +1031,14 @@ extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int d
   p.min_aln_prob = q->min_aln_prob; p.decoy_threshold = q->decoy_threshold; p.fld_mean = q->fld_mean; p.fld_sd = q->fld_sd;
   p.num_pre_burnin = q->num_pre_burnin; p.num_burnin = q->num_burnin;
   p.seed = q->seed; p.mini_batch = q->mini_batch ? q->mini_batch : 5000; p.reserved = 0;
+  p.pre_merge_thresh = q->pre_merge_thresh; p.post_merge_thresh = q->post_merge_thresh; p.orphan_thresh = q->orphan_thresh;
+  p.allow_dovetail = q->allow_dovetail; p.allow_orphans = q->allow_orphans;
+  if (!(p.pre_merge_thresh >= 0 && p.pre_merge_thresh <= 1) || !(p.post_merge_thresh >= 0 && p.post_merge_thresh <= 1) ||
+      !(p.orphan_thresh >= 0 && p.orphan_thresh <= 1)) {
+    sb::set_error("the chain sub-thresholds must be in [0, 1]");    // QuantOptionsUtils.cpp:234-247
+    delete c;
+    return nullptr;
+  }
   // the ungapped shortcut of k_dp_score_w needs: no cell scores above ma, gaps cost something
   c->fast_ok = (p.ma >= 0 && p.mp <= p.ma && p.go >= 0 && p.ge >= 0) ? 1 : 0;
   cudaSetDevice(device);

@@ -35,6 +35,8 @@ struct Params {
   uint64_t num_pre_burnin, num_burnin;
   uint64_t seed;
   uint32_t mini_batch, reserved;
+  double pre_merge_thresh, post_merge_thresh, orphan_thresh;   // join policy (see sb_map_params)
+  int32_t allow_dovetail, allow_orphans;
 };
 
 struct TableEntry {
@@ -314,31 +316,99 @@ struct Joint {
   uint32_t status;      // 0 paired, 1 left orphan, 2 right orphan
 };
 
-// visits joint hits in order; F(const Joint&) ; returns the number of joint hits
+// Join policy (MAPSPEC step 4; the knobs salmon sets on pufferfish's MappingConstraintPolicy,
+// SalmonMappingUtils.hpp:208-220, semantics from the option texts ProgramOptionsGenerator.cpp:111-137,198-201):
+//   (1) pre-merge: per mate and transcript, a chain with coverage < pre_merge_thresh x (best coverage of that mate on
+//       that transcript) takes no part;
+//   (2) a pair = one chain of each mate on the same transcript, opposite orientations, the forward mate not behind the
+//       reverse mate (unless allow_dovetail), 0 < fragment length <= max_frag_len; its score = sum of the coverages;
+//   (3) post-merge: per transcript, pairs with score < post_merge_thresh x (best pair score on it) are dropped;
+//   (4) consensus: pairs with score < consensus_frac x (best pair score of the read) are dropped;
+//   (5) no pair at all -> orphans, if allow_orphans: chains with coverage >= orphan_thresh x (best chain coverage of
+//       the read), lefts before rights (SalmonQuantify.cpp:1407-1420).
+// Candidate lists are sorted by (transcript, orientation, diagonal), so the chains of a transcript are one run in each.
+SB_HD uint32_t sbm_maxu(uint32_t a, uint32_t b) { return a > b ? a : b; }
+SB_HD bool pair_geometry(const Params& p, const Cand& l, const Cand& r, uint32_t L, int32_t& fl) {
+  if (l.tid != r.tid || (l.ori_cov >> 31) == (r.ori_cov >> 31)) return false;
+  const Cand& fw = ((l.ori_cov >> 31) == 0) ? l : r;      // the mate that maps forward
+  const Cand& rv = ((l.ori_cov >> 31) == 0) ? r : l;
+  int32_t start = fw.diag_c, end = rv.diag_c + (int32_t)L;
+  if (rv.diag_c < fw.diag_c) {                              // the reverse mate starts before the forward mate: dovetail
+    if (!p.allow_dovetail) return false;
+    start = rv.diag_c; end = fw.diag_c + (int32_t)L;
+  }
+  fl = end - start;
+  return fl > 0 && fl <= (int32_t)p.max_frag_len;
+}
+SB_HD uint32_t cand_cov(const Cand& c) { return c.ori_cov & 0x7fffffffu; }
+// chain c of `list` passes the pre-merge filter (1)
+SB_HD bool pre_merge_keep(const Params& p, const Cand* list, uint32_t n, uint32_t c) {
+  uint32_t best = 0;
+  for (uint32_t q = c; q < n && list[q].tid == list[c].tid; ++q) best = sbm_maxu(best, cand_cov(list[q]));
+  for (uint32_t q = c; q-- > 0 && list[q].tid == list[c].tid;) best = sbm_maxu(best, cand_cov(list[q]));
+  return (double)cand_cov(list[c]) >= p.pre_merge_thresh * (double)best;
+}
+
+// visits joint hits in order; F(const Joint&, index) ; returns the number of joint hits
 template <class F>
 SB_HD uint32_t for_each_joint(const Params& p, const Cand* lc, uint32_t nl, const Cand* rc, uint32_t nr,
                               uint32_t L, F&& f) {
-  uint32_t nj = 0;
-  for (uint32_t a = 0; a < nl; ++a)
+  // pre-merge masks
+  unsigned long long keep_l = 0, keep_r = 0;
+  for (uint32_t a = 0; a < nl; ++a) if (pre_merge_keep(p, lc, nl, a)) keep_l |= 1ull << a;
+  for (uint32_t b = 0; b < nr; ++b) if (pre_merge_keep(p, rc, nr, b)) keep_r |= 1ull << b;
+  // best pair score of the read (4)
+  uint32_t best_all = 0;
+  for (uint32_t a = 0; a < nl; ++a) {
+    if (!(keep_l >> a & 1)) continue;
     for (uint32_t b = 0; b < nr; ++b) {
-      if (lc[a].tid != rc[b].tid || (lc[a].ori_cov >> 31) == (rc[b].ori_cov >> 31)) continue;
-      int32_t start, end;
-      bool ok;
-      if ((lc[a].ori_cov >> 31) == 0) { start = lc[a].diag_c; end = rc[b].diag_c + (int32_t)L; ok = rc[b].diag_c >= lc[a].diag_c; }
-      else { start = rc[b].diag_c; end = lc[a].diag_c + (int32_t)L; ok = lc[a].diag_c >= rc[b].diag_c; }
-      const int32_t fl = end - start;
-      if (!ok || fl <= 0 || fl > (int32_t)p.max_frag_len) continue;
-      Joint j;
-      j.tid = lc[a].tid; j.li = (int32_t)a; j.ri = (int32_t)b; j.frag_len = fl; j.status = 0;
-      f(j, nj);
-      ++nj;
+      int32_t fl;
+      if ((keep_r >> b & 1) && pair_geometry(p, lc[a], rc[b], L, fl)) best_all = sbm_maxu(best_all, cand_cov(lc[a]) + cand_cov(rc[b]));
     }
-  if (nj == 0) {
+  }
+  uint32_t nj = 0;
+  if (best_all > 0) {
+    uint32_t a0 = 0;
+    while (a0 < nl) {                       // runs of one transcript in the left list
+      uint32_t a1 = a0;
+      while (a1 < nl && lc[a1].tid == lc[a0].tid) ++a1;
+      uint32_t best_t = 0;                  // best pair score on this transcript (3)
+      for (uint32_t a = a0; a < a1; ++a) {
+        if (!(keep_l >> a & 1)) continue;
+        for (uint32_t b = 0; b < nr; ++b) {
+          int32_t fl;
+          if ((keep_r >> b & 1) && pair_geometry(p, lc[a], rc[b], L, fl)) best_t = sbm_maxu(best_t, cand_cov(lc[a]) + cand_cov(rc[b]));
+        }
+      }
+      if (best_t > 0)
+        for (uint32_t a = a0; a < a1; ++a) {
+          if (!(keep_l >> a & 1)) continue;
+          for (uint32_t b = 0; b < nr; ++b) {
+            int32_t fl;
+            if (!(keep_r >> b & 1) || !pair_geometry(p, lc[a], rc[b], L, fl)) continue;
+            const double sc = (double)(cand_cov(lc[a]) + cand_cov(rc[b]));
+            if (sc < p.post_merge_thresh * (double)best_t || sc < p.consensus_frac * (double)best_all) continue;
+            Joint j;
+            j.tid = lc[a].tid; j.li = (int32_t)a; j.ri = (int32_t)b; j.frag_len = fl; j.status = 0;
+            f(j, nj);
+            ++nj;
+          }
+        }
+      a0 = a1;
+    }
+  }
+  if (nj == 0 && p.allow_orphans) {
+    uint32_t best_c = 0;
+    for (uint32_t a = 0; a < nl; ++a) if (keep_l >> a & 1) best_c = sbm_maxu(best_c, cand_cov(lc[a]));
+    for (uint32_t b = 0; b < nr; ++b) if (keep_r >> b & 1) best_c = sbm_maxu(best_c, cand_cov(rc[b]));
+    const double thr = p.orphan_thresh * (double)best_c;
     for (uint32_t a = 0; a < nl; ++a) {
+      if (!(keep_l >> a & 1) || (double)cand_cov(lc[a]) < thr) continue;
       Joint j; j.tid = lc[a].tid; j.li = (int32_t)a; j.ri = -1; j.frag_len = 0; j.status = 1;
       f(j, nj); ++nj;
     }
     for (uint32_t b = 0; b < nr; ++b) {
+      if (!(keep_r >> b & 1) || (double)cand_cov(rc[b]) < thr) continue;
       Joint j; j.tid = rc[b].tid; j.li = -1; j.ri = (int32_t)b; j.frag_len = 0; j.status = 2;
       f(j, nj); ++nj;
     }

@@ -475,26 +475,74 @@ k_seed_chain_w(IndexView ix, Params p, PackedReads pr, uint32_t n, uint32_t L, S
     const uint32_t nl = ncand[0], nr = ncand[1];
     const uint64_t* cl = s_cand[wib][0];
     const uint64_t* cr = s_cand[wib][1];
-    // ---- joint hits (IU): which candidates take part in one
+    // ---- joint hits (IU) under the join policy of map_core.h::for_each_joint (the same five rules, lanes = left
+    //      candidates): which candidates take part in a joint hit (they need a DP score), and how many joint hits
+    __syncwarp();
+    uint32_t* s_best = reinterpret_cast<uint32_t*>(s_keys[wib]);     // [64] best pair score per left candidate (scratch:
+                                                                     // the seed keys are not needed any more)
+    // (1) pre-merge masks
+    bool kl[2] = {false, false}, kr[2] = {false, false};
+#pragma unroll
+    for (int rd = 0; rd < 2; ++rd) {
+      const uint32_t a = lane + 32u * rd;
+      if (a < nl) {
+        uint32_t best = 0;
+        for (uint32_t q = 0; q < nl; ++q) if (cwd_tid(cl[q]) == cwd_tid(cl[a])) best = max(best, cw_cov(cl[q]));
+        kl[rd] = (double)cw_cov(cl[a]) >= p.pre_merge_thresh * (double)best;
+      }
+      if (a < nr) {
+        uint32_t best = 0;
+        for (uint32_t q = 0; q < nr; ++q) if (cwd_tid(cr[q]) == cwd_tid(cr[a])) best = max(best, cw_cov(cr[q]));
+        kr[rd] = (double)cw_cov(cr[a]) >= p.pre_merge_thresh * (double)best;
+      }
+    }
+    const unsigned long long keep_l = (unsigned long long)__ballot_sync(0xffffffffu, kl[0]) |
+                                      ((unsigned long long)__ballot_sync(0xffffffffu, kl[1]) << 32);
+    const unsigned long long keep_r = (unsigned long long)__ballot_sync(0xffffffffu, kr[0]) |
+                                      ((unsigned long long)__ballot_sync(0xffffffffu, kr[1]) << 32);
+    auto geometry = [&](uint64_t wa, uint64_t wb) -> bool {          // (2) a concordant pair?
+      if (cwd_tid(wa) != cwd_tid(wb) || cwd_ori(wa) == cwd_ori(wb)) return false;
+      const int32_t dfw = cwd_ori(wa) == 0 ? cwd_diag(wa) : cwd_diag(wb);
+      const int32_t drv = cwd_ori(wa) == 0 ? cwd_diag(wb) : cwd_diag(wa);
+      int32_t start = dfw, end = drv + (int32_t)L;
+      if (drv < dfw) {
+        if (!p.allow_dovetail) return false;
+        start = drv; end = dfw + (int32_t)L;
+      }
+      const int32_t fl = end - start;
+      return fl > 0 && fl <= (int32_t)p.max_frag_len;
+    };
+    // best pair score per left candidate, of the read
+    uint32_t my_best[2] = {0, 0};
+#pragma unroll
+    for (int rd = 0; rd < 2; ++rd) {
+      const uint32_t a = lane + 32u * rd;
+      if (a < nl && ((keep_l >> a) & 1ull)) {
+        const uint64_t wa = cl[a];
+        for (uint32_t b = 0; b < nr; ++b)
+          if (((keep_r >> b) & 1ull) && geometry(wa, cr[b])) my_best[rd] = max(my_best[rd], cw_cov(wa) + cw_cov(cr[b]));
+      }
+      if (a < 64u) s_best[a] = my_best[rd];
+    }
+    uint32_t best_all = max(my_best[0], my_best[1]);
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) best_all = max(best_all, __shfl_xor_sync(0xffffffffu, best_all, sft));
+    __syncwarp();
+    // (3) + (4): count the surviving pairs, mark their candidates
     uint32_t my_cnt = 0;
     unsigned long long my_used_r = 0ull;
     bool used_a[2] = {false, false};
 #pragma unroll
     for (int rd = 0; rd < 2; ++rd) {
       const uint32_t a = lane + 32u * rd;
-      if (a < nl) {
+      if (a < nl && my_best[rd] > 0) {
         const uint64_t wa = cl[a];
-        const int32_t da = cwd_diag(wa);
+        uint32_t best_t = 0;                                         // best pair score on this transcript
+        for (uint32_t q = 0; q < nl; ++q) if (cwd_tid(cl[q]) == cwd_tid(wa)) best_t = max(best_t, s_best[q]);
         for (uint32_t b = 0; b < nr; ++b) {
-          const uint64_t wb = cr[b];
-          if (cwd_tid(wa) != cwd_tid(wb) || cwd_ori(wa) == cwd_ori(wb)) continue;
-          const int32_t db = cwd_diag(wb);
-          int32_t start, end;
-          bool ok;
-          if (cwd_ori(wa) == 0) { start = da; end = db + (int32_t)L; ok = db >= da; }
-          else { start = db; end = da + (int32_t)L; ok = da >= db; }
-          const int32_t fl = end - start;
-          if (!ok || fl <= 0 || fl > (int32_t)p.max_frag_len) continue;
+          if (!((keep_r >> b) & 1ull) || !geometry(wa, cr[b])) continue;
+          const double sc = (double)(cw_cov(wa) + cw_cov(cr[b]));
+          if (sc < p.post_merge_thresh * (double)best_t || sc < p.consensus_frac * (double)best_all) continue;
           ++my_cnt;
           my_used_r |= 1ull << b;
           used_a[rd] = true;
@@ -510,11 +558,29 @@ k_seed_chain_w(IndexView ix, Params p, PackedReads pr, uint32_t n, uint32_t L, S
       nj += __shfl_xor_sync(0xffffffffu, nj, s);
       used_r |= __shfl_xor_sync(0xffffffffu, used_r, s);
     }
-    if (nj == 0) {   // orphans
-      nj = nl + nr;
-      used_l = nl >= 64 ? ~0ull : ((1ull << nl) - 1);
-      used_r = nr >= 64 ? ~0ull : ((1ull << nr) - 1);
+    if (nj == 0 && p.allow_orphans) {   // (5) orphans above the orphan threshold
+      uint32_t best_c = 0;
+#pragma unroll
+      for (int rd = 0; rd < 2; ++rd) {
+        const uint32_t a = lane + 32u * rd;
+        if (a < nl && ((keep_l >> a) & 1ull)) best_c = max(best_c, cw_cov(cl[a]));
+        if (a < nr && ((keep_r >> a) & 1ull)) best_c = max(best_c, cw_cov(cr[a]));
+      }
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) best_c = max(best_c, __shfl_xor_sync(0xffffffffu, best_c, sft));
+      const double thr = p.orphan_thresh * (double)best_c;
+      bool ol[2], orr[2];
+#pragma unroll
+      for (int rd = 0; rd < 2; ++rd) {
+        const uint32_t a = lane + 32u * rd;
+        ol[rd] = a < nl && ((keep_l >> a) & 1ull) && (double)cw_cov(cl[a]) >= thr;
+        orr[rd] = a < nr && ((keep_r >> a) & 1ull) && (double)cw_cov(cr[a]) >= thr;
+      }
+      used_l = (unsigned long long)__ballot_sync(0xffffffffu, ol[0]) | ((unsigned long long)__ballot_sync(0xffffffffu, ol[1]) << 32);
+      used_r = (unsigned long long)__ballot_sync(0xffffffffu, orr[0]) | ((unsigned long long)__ballot_sync(0xffffffffu, orr[1]) << 32);
+      nj = (uint32_t)(__popcll(used_l) + __popcll(used_r));
     }
+    __syncwarp();      // s_best lives in the key scratch of the next read's seeds
     // ---- write the candidates and the DP tasks
     for (uint32_t a = lane; a < nl; a += 32) {
       Cand c; c.tid = cwd_tid(cl[a]); c.diag_c = cwd_diag(cl[a]); c.ori_cov = (cwd_ori(cl[a]) << 31) | cw_cov(cl[a]);

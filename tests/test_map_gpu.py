@@ -375,3 +375,22 @@ def test_gpu_vs_oracle_at_bench_scale(oracle):
     assert len(flips) <= 0.02 * n, len(flips)
     print(f"bench-scale parity: {n} pairs, {len(res['counts'])} classes, {int((got_naln > 1).sum())} multi-mapping reads; "
           f"labels on the platform libm differ on {len(flips)} reads (exact bin boundaries)")
+
+
+def test_join_policy_knobs_gpu_vs_oracle(oracle):
+    """the warp kernels' lane-parallel form of the join policy (preMerge / postMerge / orphan thresholds, allowDovetail,
+    discardOrphans) against the oracle: alignments, labels bit-exact for every knob setting"""
+    from test_map_host import JOIN_VARIANTS, join_reads
+    txps, left, right = join_reads()
+    idx = Index(txps)
+    oix = oracle.MapIndex(txps)
+    for over in JOIN_VARIANTS:
+        p = map_default_params(**over)
+        for variant in (1, 0):
+            ctx = MapContext(idx, p, batch_cap=8192, max_read_len=100)
+            ctx.set_option("variant", variant)
+            ctx.map_batch(left, right)
+            got = ctx.last_alignments()
+            ctx.close()
+            ref = oracle.map_reads(oix, oracle.map_params(**over), left, right, 0)
+            compare(got, ref, p.max_read_occ)

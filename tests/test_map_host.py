@@ -179,3 +179,63 @@ def test_fuzz_host_logic_against_oracle(oracle, master_seed):
         run_both(oracle, txps, left, right, frag_counter=int(rng.choice([0, 0, 6000, 6_000_000])), **over)
         done += 1
     assert done >= 40
+
+
+JOIN_VARIANTS = [dict(), dict(allow_dovetail=1), dict(allow_orphans=0), dict(pre_merge_thresh=1.0, post_merge_thresh=1.0, orphan_thresh=1.0),
+                 dict(pre_merge_thresh=0.0, post_merge_thresh=0.0, orphan_thresh=0.0, consensus_frac=0.3),
+                 dict(post_merge_thresh=0.5, orphan_thresh=0.6, allow_dovetail=1)]
+
+
+def join_reads(seed=71, n=6000):
+    """reads that exercise the join policy: normal pairs, pairs whose mates dovetail (fragment shorter than a read), and
+    pairs with one unmappable mate (orphans)"""
+    txps, _ = synth_txome(seed=seed, n_genes=120)
+    left, right, truth = synth_reads(txps, seed=seed + 1, n=n, indel_rate=0.001)
+    rng = np.random.default_rng(seed + 2)
+    L = left.shape[1]
+    comp = np.array([3, 2, 1, 0, 4], dtype=np.uint8)
+    for i in rng.choice(n, n // 6, replace=False):          # dovetail: the right mate starts upstream of the left mate
+        t = txps[int(rng.integers(len(txps)))]
+        if len(t) < L + 40:
+            continue
+        s = int(rng.integers(20, len(t) - L - 10))
+        left[i] = t[s:s + L]
+        right[i] = comp[t[s - 15:s - 15 + L][::-1]]
+    for i in rng.choice(n, n // 8, replace=False):          # orphan: one mate is noise
+        (left if rng.random() < 0.5 else right)[i] = rng.integers(0, 4, L).astype(np.uint8)
+    return txps, left, right
+
+
+@pytest.mark.parametrize("over", JOIN_VARIANTS)
+def test_join_policy_knobs_host_logic_vs_oracle(oracle, over):
+    """MAPSPEC step 4 with the knobs salmon exposes (preMerge / postMerge / orphan chain sub-thresholds, allowDovetail,
+    discardOrphans; SalmonMappingUtils.hpp:208-220): the product's per-read logic against the oracle's independent
+    restatement, plus what each knob must do."""
+    txps, left, right = join_reads()
+    got, ref = run_both(oracle, txps, left, right, **over)
+    status = (got["flags"] >> 2) & 3
+    valid = np.arange(got["flags"].shape[1])[None, :] < got["n_aln"][:, None]
+    n_orphan_reads = int(((status != 0) & valid).any(axis=1).sum())
+    if over.get("allow_orphans", 1) == 0:
+        assert n_orphan_reads == 0
+    else:
+        assert n_orphan_reads > 100
+    test_join_policy_knobs_host_logic_vs_oracle.mapped[tuple(sorted(over.items()))] = int((got["n_aln"] > 0).sum())
+
+
+test_join_policy_knobs_host_logic_vs_oracle.mapped = {}
+
+
+def test_join_policy_monotonicity(oracle):
+    """dovetails only map as pairs when allowed; discarding orphans only loses reads; looser thresholds only add alignments"""
+    txps, left, right = join_reads()
+    oix = oracle.MapIndex(txps)
+    run = lambda **o: oracle.map_reads(oix, oracle.map_params(**o), left, right, 0)
+    base, dove, noorph = run(), run(allow_dovetail=1), run(allow_orphans=0)
+    loose = run(pre_merge_thresh=0.0, post_merge_thresh=0.0, orphan_thresh=0.0)
+    strict = run(pre_merge_thresh=1.0, post_merge_thresh=1.0, orphan_thresh=1.0)
+    paired = lambda m: int((((m["flags"] >> 2) & 3) == 0)[np.arange(m["flags"].shape[1])[None, :] < m["n_aln"][:, None]].sum())
+    assert paired(dove) > paired(base) + 300                 # the planted dovetails become concordant pairs
+    assert (noorph["n_aln"] > 0).sum() < (base["n_aln"] > 0).sum() - 300
+    assert int(loose["n_aln"].sum()) >= int(base["n_aln"].sum()) >= int(strict["n_aln"].sum())
+    assert int(loose["n_aln"].sum()) > int(strict["n_aln"].sum())
