@@ -19,6 +19,14 @@ from . import _capi
 from ._capi import EMContext, EqClasses, MapContext, default_params, map_default_params
 
 
+def _boot_params(ep):
+    """the bootstrap replicates run with at least 50 iterations (CollapsedEMOptimizer.cpp:411), like sb_quant_files"""
+    import copy
+    bp = copy.copy(ep)
+    bp.min_iter = 50
+    return bp
+
+
 def _drop_decoys(index, inputs):
     """readExp.dropDecoyTranscripts() (SalmonQuantify.cpp:2479, ReadExperiment.hpp:120): decoys -- the suffix of the id
     space, never part of a label -- leave before the optimiser and the writers.  Returns (Mq, inputs cut to Mq)."""
@@ -108,7 +116,7 @@ def _quantify(index, ctx, ep, device, dist, names, out_dir, dump_eq, dump_eq_wei
         raise _capi.SalmonB200Error("The optimization algorithm failed (total alpha weight too small)")
     boots = None
     if num_bootstraps > 0 and world == 1:
-        boots, _ = em.bootstrap(ep, float(n_mapped), num_bootstraps, seed)
+        boots, _ = em.bootstrap(_boot_params(ep), float(n_mapped), num_bootstraps, seed)
     em.close()
     tpm = _capi.tpm(alpha, inputs["eff_len"], float(n_mapped) if n_mapped else None)
     if out_dir is not None and rank == 0:
@@ -186,7 +194,7 @@ def quant_eqclasses(eq_path, out_dir=None, em_params=None, device=0, num_bootstr
     n_frags = float(f["counts"].sum())
     boots = None
     if num_bootstraps > 0:
-        boots, _ = em.bootstrap(ep, n_frags, num_bootstraps, seed)
+        boots, _ = em.bootstrap(_boot_params(ep), n_frags, num_bootstraps, seed)
     em.close()
     tpm = _capi.tpm(alpha, f["eff_len"], n_frags)
     if out_dir is not None:
