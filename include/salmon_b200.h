@@ -285,7 +285,18 @@ typedef struct sb_map_params {
   double orphan_thresh;       /* orphanChainSubThresh 0.95: without a concordant pair, orphans below this fraction of the best chain are dropped */
   int32_t allow_dovetail;     /* allowDovetail (false): dovetailing mates count as concordant */
   int32_t allow_orphans;      /* !discardOrphansQuasi (true): orphan mappings when no pair exists */
+  /* expected library format (LibraryFormat, -l): SB_LIB_IU / ISF / ISR (paired-end, inward) or SB_LIB_U / SF / SR
+   * (single-end: sb_map_batch with right == NULL).  Mappings that are not compatible with it are ignored
+   * (incompatPrior = 0 -> ignoreIncompat, SalmonQuantify.cpp:1467-1521,2141-2150; rules src/util/SalmonUtils.cpp:138-298) */
+  int32_t lib_type;
+  int32_t reserved3;
 } sb_map_params;
+#define SB_LIB_IU 0
+#define SB_LIB_ISF 1
+#define SB_LIB_ISR 2
+#define SB_LIB_U 3
+#define SB_LIB_SF 4
+#define SB_LIB_SR 5
 void sb_map_default_params(sb_map_params* p);
 
 typedef struct sb_map_batch_stats {
@@ -314,6 +325,10 @@ typedef struct sb_map_result {   /* host CSR owned by the context, valid until d
   const double* eff_len;           /* exp(cachedLogEffectiveLength) (CollapsedEMOptimizer.cpp:782-784) */
   const uint64_t* unique_counts;   /* Transcript::uniqueCount() */
   const uint64_t* total_counts;    /* Transcript::totalCount() */
+  /* fragments that showed each observed format among their kept mappings (ReadLibrary::libTypeCounts,
+   * SalmonQuantify.cpp:765,1000-1002): [0] ISF (pair, left mate forward), [1] ISR, [2] SF (orphan / single-end read
+   * mapped forward), [3] SR; [4..7] reserved */
+  uint64_t lib_format_counts[8];
 } sb_map_result;
 
 typedef struct sb_map_ctx sb_map_ctx;

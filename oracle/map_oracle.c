@@ -374,7 +374,8 @@ static int map_reads_core(const orc_index* ix, const orc_map_params* p, const fl
     n_aln[r] = 0;
     uint32_t nl = mate_candidates(ix, p, rl, L, lc, &local);
     uint32_t nr = mate_candidates(ix, p, rr, L, rcand, &local);
-    /* ---- join (library type IU: inward, unstranded) with the constraint policy salmon sets
+    /* ---- join (inward pairs; single-end libraries arrive with an all-N second mate, i.e. left orphans only, and the
+     *      orphan threshold does not apply to them: joinReadsAndFilterSingle) with the constraint policy salmon sets
      *      (SalmonMappingUtils.hpp:208-220; ProgramOptionsGenerator.cpp:111-137,198-201; MAPSPEC step 4):
      *      pre-merge filter per mate and transcript, concordant pairs, post-merge filter per transcript, pair consensus
      *      over the read, else orphans above the orphan threshold */
@@ -423,7 +424,7 @@ static int map_reads_core(const orc_index* ix, const orc_map_params* p, const fl
         uint32_t best_c = 0;
         for (uint32_t a = 0; a < nl; ++a) if (okl[a] && lc[a].cov > best_c) best_c = lc[a].cov;
         for (uint32_t b = 0; b < nr; ++b) if (okr[b] && rcand[b].cov > best_c) best_c = rcand[b].cov;
-        const double thr = p->orphan_thresh * (double)best_c;
+        const double thr = (p->lib_type >= 3 ? 0.0 : p->orphan_thresh) * (double)best_c;
         for (uint32_t a = 0; a < nl; ++a) if (okl[a] && (double)lc[a].cov >= thr) { joint_t j; j.tid = lc[a].tid; j.li = (int32_t)a; j.ri = -1; j.frag_len = 0; j.status = 1; jh[nj++] = j; }
         for (uint32_t b = 0; b < nr; ++b) if (okr[b] && (double)rcand[b].cov >= thr) { joint_t j; j.tid = rcand[b].tid; j.li = -1; j.ri = (int32_t)b; j.frag_len = 0; j.status = 2; jh[nj++] = j; }
       }
@@ -439,6 +440,26 @@ static int map_reads_core(const orc_index* ix, const orc_map_params* p, const fl
       if (jh[h].ri >= 0) { int32_t s = dp_score(ix, p, rr, L, rcand[jh[h].ri].ori, jh[h].tid, rcand[jh[h].ri].diag_c); local.candidates++; if (s <= NEG_SCORE) bad = 1; total += s; maxPossible += p->ma * (int32_t)L; }
       int32_t hitScore = (!bad && (double)total >= p->min_score_fraction * (double)maxPossible) ? total : invalidScore;
       scores[h] = hitScore;
+      {
+        /* compatibility with the expected library format (SalmonQuantify.cpp:1467-1517 paired-end, :2141-2147
+         * single-end; salmon::utils::compatibleHit, SalmonUtils.cpp:193-298); incompatible mappings are skipped
+         * (ignoreIncompat, :1519-1521) */
+        const int isOrphan = jh[h].status != 0;
+        const int isLeft = jh[h].status != 2;
+        const int leftFw = jh[h].li >= 0 && lc[jh[h].li].ori == 0;
+        const int rightFw = jh[h].ri >= 0 && rcand[jh[h].ri].ori == 0;
+        int isCompat;
+        switch (p->lib_type) {
+          case 0: isCompat = isOrphan ? 1 : (leftFw != rightFw); break;                         /* IU */
+          case 1: isCompat = isOrphan ? ((isLeft && leftFw) || (!isLeft && !rightFw)) : (leftFw && !rightFw); break;   /* ISF: SA */
+          case 2: isCompat = isOrphan ? ((isLeft && !leftFw) || (!isLeft && rightFw)) : (!leftFw && rightFw); break;   /* ISR: AS */
+          case 3: isCompat = 1; break;                                                          /* U */
+          case 4: isCompat = leftFw; break;                                                     /* SF */
+          case 5: isCompat = !leftFw; break;                                                    /* SR */
+          default: isCompat = 1;
+        }
+        if (!isCompat) { scores[h] = invalidScore; continue; }
+      }
       const int isDecoy = (int32_t)jh[h].tid >= p->first_decoy;
       const double decoyCutoff = (double)(int32_t)(p->decoy_threshold * (double)bestDecoyScore);
       if (isDecoy) { if (hitScore > bestDecoyScore) bestDecoyScore = hitScore; continue; }

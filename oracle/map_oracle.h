@@ -55,6 +55,8 @@ typedef struct orc_map_params {
   double orphan_thresh;       /* 0.95 */
   int32_t allow_dovetail;     /* 0 */
   int32_t allow_orphans;      /* 1 */
+  int32_t lib_type;           /* expected library format: 0 IU, 1 ISF, 2 ISR (paired-end, inward); 3 U, 4 SF, 5 SR (single-end) */
+  int32_t reserved3;
 } orc_map_params;
 
 /* per-dataset counters for the roofline accounting of SURVEY.md section 8d */

@@ -82,7 +82,7 @@ class sb_map_params(C.Structure):
         ("num_pre_burnin", C.c_uint64), ("num_burnin", C.c_uint64),
         ("seed", C.c_uint64), ("mini_batch", C.c_uint32), ("reserved2", C.c_uint32),
         ("pre_merge_thresh", C.c_double), ("post_merge_thresh", C.c_double), ("orphan_thresh", C.c_double),
-        ("allow_dovetail", C.c_int32), ("allow_orphans", C.c_int32),
+        ("allow_dovetail", C.c_int32), ("allow_orphans", C.c_int32), ("lib_type", C.c_int32), ("reserved3", C.c_int32),
     ]
 
 
@@ -102,7 +102,7 @@ class sb_map_result(C.Structure):
         [(k, C.c_uint64) for k in ("n_mapped", "lookups", "postings", "seeds", "candidates", "kept", "label_entries")] + \
         [("n_txps", C.c_uint32), ("reserved", C.c_uint32), ("projected_counts", C.POINTER(C.c_double)),
          ("eff_len", C.POINTER(C.c_double)), ("unique_counts", C.POINTER(C.c_uint64)),
-         ("total_counts", C.POINTER(C.c_uint64))]
+         ("total_counts", C.POINTER(C.c_uint64)), ("lib_format_counts", C.c_uint64 * 8)]
 
 
 # every symbol include/salmon_b200.h declares: (name, restype, argtypes)
@@ -624,12 +624,16 @@ class MapContext:
             raise SalmonB200Error("sb_map_create failed: " + self.lib.sb_last_error().decode())
         self.last_n = 0
 
-    def map_batch(self, left, right) -> sb_map_batch_stats:
+    def map_batch(self, left, right=None) -> sb_map_batch_stats:
+        """right=None: single-end reads (library types U / SF / SR)"""
         left = np.ascontiguousarray(left, dtype=np.uint8)
-        right = np.ascontiguousarray(right, dtype=np.uint8)
         n, L = left.shape
+        rp = None
+        if right is not None:
+            right = np.ascontiguousarray(right, dtype=np.uint8)
+            rp = right.ctypes.data
         st = sb_map_batch_stats()
-        _check(self.lib.sb_map_batch(self.h, left.ctypes.data, right.ctypes.data, n, L, C.byref(st)), "sb_map_batch")
+        _check(self.lib.sb_map_batch(self.h, left.ctypes.data, rp, n, L, C.byref(st)), "sb_map_batch")
         self.last_n = n
         return st
 
@@ -706,6 +710,7 @@ class MapContext:
         for k, dt in (("projected_counts", np.float64), ("eff_len", np.float64), ("unique_counts", np.uint64),
                       ("total_counts", np.uint64)):
             out[k] = np.ctypeslib.as_array(getattr(r, k), shape=(M,)).copy() if M else np.zeros(0, dt)
+        out["lib_format_counts"] = dict(zip(("ISF", "ISR", "SF", "SR"), [int(x) for x in r.lib_format_counts[:4]]))
         return out
 
     def online_state(self):
@@ -921,7 +926,8 @@ def quant_files_native(index, mates1, mates2, out_dir=None, map_params=None, em_
     opts: fields of sb_quant_opts.  -> (alpha[M], summary dict)."""
     lib = load()
     mates1 = [mates1] if isinstance(mates1, (str, bytes, os.PathLike)) else list(mates1)
-    mates2 = [mates2] if isinstance(mates2, (str, bytes, os.PathLike)) else list(mates2)
+    if mates2 is not None:
+        mates2 = [mates2] if isinstance(mates2, (str, bytes, os.PathLike)) else list(mates2)
     o = sb_quant_opts()
     lib.sb_quant_default_opts(C.byref(o))
     for k, v in opts.items():
@@ -929,7 +935,7 @@ def quant_files_native(index, mates1, mates2, out_dir=None, map_params=None, em_
             raise AttributeError(k)
         setattr(o, k, v)
     a1 = (C.c_char_p * len(mates1))(*[os.fsencode(f) for f in mates1])
-    a2 = (C.c_char_p * len(mates2))(*[os.fsencode(f) for f in mates2])
+    a2 = (C.c_char_p * len(mates2))(*[os.fsencode(f) for f in mates2]) if mates2 is not None else None   # None: single-end
     alpha = np.zeros(index.n_txps)
     sm = sb_quant_summary()
     _check(lib.sb_quant_files(index.h, a1, a2, len(mates1), C.byref(map_params) if map_params is not None else None,

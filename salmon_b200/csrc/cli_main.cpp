@@ -55,7 +55,8 @@ int usage() {
   fprintf(stderr,
           "sb_salmon (salmon-b200 %d): B200-native hot path of salmon\n"
           "  sb_salmon index -t transcripts.fa[.gz] -i index_dir [-k 31] [--gencode] [-d decoys.txt] [--keepDuplicates] [--no-clip]\n"
-          "  sb_salmon quant -i index_dir -l IU -1 r1.fq[.gz] ... -2 r2.fq[.gz] ... -o out_dir [-p threads] [--dumpEq] [--dumpEqWeights]\n"
+          "  sb_salmon quant -i index_dir -l IU|ISF|ISR -1 r1.fq[.gz] ... -2 r2.fq[.gz] ... | -l U|SF|SR -r reads.fq[.gz] ...  -o out_dir [--gpus N]\n"
+          "                  [-p threads] [--dumpEq] [--dumpEqWeights]\n"
           "                  [--numBootstraps N | --numGibbsSamples N] [--thinningFactor 16] [--noGammaDraw] [--useEM] [--vbPrior 0.01]\n"
           "                  [--perNucleotidePrior] [--maxReadOcc 200] [--maxOccsPerHit 1000] [--minScoreFraction 0.65] [--consensusSlack 0.35]\n"
           "                  [--preMergeChainSubThresh 0.75] [--postMergeChainSubThresh 0.9] [--orphanChainSubThresh 0.95] [--allowDovetail]\n"
@@ -192,7 +193,7 @@ int cmd_quant(Args& a) {
   sb_quant_default_opts(&qo);
   auto num = [&](double& d) { if (!a.value(v)) return false; d = atof(v.c_str()); return true; };
   double d = 0;
-  bool vb_prior_given = false;
+  bool vb_prior_given = false, pre_merge_given = false;
   int n_gpus = 1, my_rank = -1;
   std::string run_tag;
   while (a.more()) {
@@ -224,7 +225,7 @@ int cmd_quant(Args& a) {
     else if (o == "--minScoreFraction") { if (!num(mp.min_score_fraction)) return usage(); }
     else if (o == "--consensusSlack") { if (!num(d)) return usage(); mp.consensus_frac = 1.0 - d; }
     else if (o == "--hardFilter") mp.hard_filter = 1;
-    else if (o == "--preMergeChainSubThresh") { if (!num(mp.pre_merge_thresh)) return usage(); }
+    else if (o == "--preMergeChainSubThresh") { if (!num(mp.pre_merge_thresh)) return usage(); pre_merge_given = true; }
     else if (o == "--postMergeChainSubThresh") { if (!num(mp.post_merge_thresh)) return usage(); }
     else if (o == "--orphanChainSubThresh") { if (!num(mp.orphan_thresh)) return usage(); }
     else if (o == "--allowDovetail") mp.allow_dovetail = 1;
@@ -300,22 +301,31 @@ int cmd_quant(Args& a) {
   if (qo.shard_index == 0) write_cmd_info(out, a.all);
   if (!eqfile.empty()) return quant_eqclasses(eqfile, out, ep, qo);
   if (dir.empty()) return usage();
-  if (!unmated.empty() || m1.empty() || m1.size() != m2.size()) {
-    fprintf(stderr, "sb_salmon quant: paired-end input (-1 / -2, the same number of files) is what this build maps; single-end "
-                    "reads (-r) are not supported yet\n");
+  // library type (-l): IU / ISF / ISR for mate files, U / SF / SR for unmated reads; A = the unstranded type of the input
+  static const struct { const char* name; int id; } lib_names[] = {{"IU", SB_LIB_IU}, {"ISF", SB_LIB_ISF}, {"ISR", SB_LIB_ISR},
+                                                                   {"U", SB_LIB_U}, {"SF", SB_LIB_SF}, {"SR", SB_LIB_SR}};
+  const bool se_input = !unmated.empty();
+  if (se_input ? (!m1.empty() || !m2.empty()) : (m1.empty() || m1.size() != m2.size())) {
+    fprintf(stderr, "sb_salmon quant: give either mate files (-1 / -2, the same number of each) or unmated reads (-r)\n");
     return 1;
   }
-  if (lib != "A" && lib != "IU") {
-    fprintf(stderr, "sb_salmon quant: library type %s: only IU (or A, taken as IU) is supported\n", lib.c_str());
+  int lib_id = -1;
+  if (lib == "A") lib_id = se_input ? SB_LIB_U : SB_LIB_IU;      // (automatic detection is not implemented: the unstranded type)
+  for (auto& ln : lib_names) if (lib == ln.name) lib_id = ln.id;
+  if (lib_id < 0 || (lib_id >= SB_LIB_U) != se_input) {
+    fprintf(stderr, "sb_salmon quant: library type %s does not fit the input (IU / ISF / ISR with -1 -2, U / SF / SR with -r; "
+                    "outward and same-strand types are not supported)\n", lib.c_str());
     return 1;
   }
+  mp.lib_type = lib_id;
+  if (se_input && !pre_merge_given) mp.pre_merge_thresh = 1.0;    // single-end default (QuantOptionsUtils.cpp:215-218)
   sb_index* ix = sb_index_load((dir + "/sb_index.bin").c_str());
   if (!ix) return die("loading the index");
   std::vector<const char*> p1, p2;
-  for (auto& s : m1) p1.push_back(s.c_str());
+  for (auto& s : (se_input ? unmated : m1)) p1.push_back(s.c_str());
   for (auto& s : m2) p2.push_back(s.c_str());
   sb_quant_summary sum;
-  if (sb_quant_files(ix, p1.data(), p2.data(), (uint32_t)p1.size(), &mp, &ep, &qo, out.c_str(), nullptr, &sum) != 0)
+  if (sb_quant_files(ix, p1.data(), se_input ? nullptr : p2.data(), (uint32_t)p1.size(), &mp, &ep, &qo, out.c_str(), nullptr, &sum) != 0)
     return die("quant");
   if (qo.shard_index == 0) {
     const double rate = sum.n_observed ? 100.0 * (double)sum.n_mapped / (double)sum.n_observed : 0.0;

@@ -334,6 +334,7 @@ __device__ __forceinline__ void add_counters(Counters* g, const Counters& c) {
   if (c.kept) atomicAdd(&g->kept, c.kept);
   if (c.label_entries) atomicAdd(&g->label_entries, c.label_entries);
   if (c.mapped) atomicAdd(&g->mapped, c.mapped);
+  for (int i = 0; i < 4; ++i) if (c.lib_mask_sum[i]) atomicAdd(&g->lib_mask_sum[i], c.lib_mask_sum[i]);
 }
 
 // K1: one thread per read pair -- seeds, chains, candidates, DP task list
@@ -908,6 +909,7 @@ struct sb_map_ctx {
   std::vector<EqStore> stores;
   uint64_t frag_counter = 0;     // fragments assigned so far (batched semantics)
   Counters totals{};
+  uint8_t* d_dummy_mate = nullptr;     // single-end libraries: the absent second mate (N codes)
   uint64_t full_dp_total = 0;
   uint32_t launches = 0;
   float last_ms = 0;
@@ -1033,6 +1035,8 @@ extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int d
   p.seed = q->seed; p.mini_batch = q->mini_batch ? q->mini_batch : 5000; p.reserved = 0;
   p.pre_merge_thresh = q->pre_merge_thresh; p.post_merge_thresh = q->post_merge_thresh; p.orphan_thresh = q->orphan_thresh;
   p.allow_dovetail = q->allow_dovetail; p.allow_orphans = q->allow_orphans;
+  p.lib_type = q->lib_type; p.reserved3 = 0;
+  if (p.lib_type < 0 || p.lib_type > 5) { sb::set_error("unsupported library type %d (IU, ISF, ISR, U, SF, SR)", p.lib_type); delete c; return nullptr; }
   if (!(p.pre_merge_thresh >= 0 && p.pre_merge_thresh <= 1) || !(p.post_merge_thresh >= 0 && p.post_merge_thresh <= 1) ||
       !(p.orphan_thresh >= 0 && p.orphan_thresh <= 1)) {
     sb::set_error("the chain sub-thresholds must be in [0, 1]");    // QuantOptionsUtils.cpp:234-247
@@ -1149,6 +1153,7 @@ extern "C" void sb_map_destroy(sb_map_ctx* c) {
                   c->d_work, c->d_work2, c->d_ids, c->d_order, c->fin.uniq, c->fin.total, c->fin.hits, c->fin.parent, c->fin.root, c->fin.root2, c->fin.ids, c->fin.memb,
                   c->fin.head, c->fin.head_scan, c->fin.start, c->fin.proj, c->fin.eff, c->fin.bound, c->fin.tmp};
   for (void* p : ptrs) cudaFree(p);
+  cudaFree(c->d_dummy_mate);
   cudaFree(c->alt_n_l); cudaFree(c->alt_n_r); cudaFree(c->alt_cand_l); cudaFree(c->alt_cand_r); cudaFree(c->alt_score_l); cudaFree(c->alt_score_r);
   for (int s = 0; s < 2; ++s) { if (c->ev_dp[s]) cudaEventDestroy(c->ev_dp[s]); if (c->ev_asg[s]) cudaEventDestroy(c->ev_asg[s]); }
   if (c->assign_stream) cudaStreamDestroy(c->assign_stream);
@@ -1170,7 +1175,9 @@ extern "C" int sb_map_set_option(sb_map_ctx* c, const char* key, int64_t value) 
   if (!strcmp(key, "input_on_device")) { c->input_dev = value ? 1 : 0; return SB_OK; }
   if (!strcmp(key, "ascii_reads")) {
     if (value && c->variant == 0) { sb::set_error("ascii_reads needs the warp kernels (variant 1)"); return SB_ERR_INVALID; }
-    c->ascii = value ? 1 : 0; return SB_OK;
+    c->ascii = value ? 1 : 0;
+    if (c->d_dummy_mate) { cudaFree(c->d_dummy_mate); c->d_dummy_mate = nullptr; }   // its N codes depend on the encoding
+    return SB_OK;
   }
   if (!strcmp(key, "overlap_assign")) { c->overlap_assign = value ? 1 : 0; return SB_OK; }
   if (!strcmp(key, "chunk")) {   // reads per pipeline chunk (<= the size the context was created with)
@@ -1251,10 +1258,24 @@ static int aggregate(sb_map_ctx* c, Records R, EqStore& out) {
 
 extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* right, uint32_t n, uint32_t L,
                             sb_map_batch_stats* stats) {
-  if (!c || (n && (!left || !right))) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  if (!c || (n && !left)) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  const bool single_end = c->p.lib_type >= 3;
+  if (n && single_end != (right == nullptr)) {
+    sb::set_error(single_end ? "single-end library type: sb_map_batch takes right == NULL" : "paired-end library type: both mates are needed");
+    return SB_ERR_INVALID;
+  }
   if (n > c->batch_cap || L > c->read_len_cap || L < c->p.k) { sb::set_error("batch larger than the context was created for"); return SB_ERR_INVALID; }
   SB_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream, cs = c->copy_stream;
+  if (single_end) {
+    // single-end reads (processReads SE, SalmonQuantify.cpp:1880-2325) travel through the paired kernels with an absent
+    // second mate: a device buffer of N codes -- no k-mer, no seed, no candidate -- so every mapping is a left "orphan",
+    // which is exactly how the auxiliary model treats a single-end read (getAmbigFragLengthProb, :642-650 / :2186-2200)
+    if (!c->d_dummy_mate) {
+      SB_CUDA(cudaMalloc(&c->d_dummy_mate, (size_t)c->batch_cap * c->read_len_cap));
+      SB_CUDA(cudaMemset(c->d_dummy_mate, c->ascii ? 'N' : 4, (size_t)c->batch_cap * c->read_len_cap));
+    }
+  }
   BatchBufs b = c->b;
   const Params& p = c->p;
   const uint32_t cap = p.max_read_occ;
@@ -1294,13 +1315,14 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
     const uint8_t* dl = c->d_in[s][0];
     const uint8_t* dr = c->d_in[s][1];
     if (c->input_dev) {
-      dl = left + (size_t)c0 * L; dr = right + (size_t)c0 * L;
+      dl = left + (size_t)c0 * L; dr = single_end ? c->d_dummy_mate : right + (size_t)c0 * L;
     } else {
       if (ch >= 2) SB_CUDA(cudaStreamWaitEvent(cs, c->ev_free[s], 0));
       SB_CUDA(cudaMemcpyAsync(c->d_in[s][0], left + (size_t)c0 * L, (size_t)cn * L, cudaMemcpyHostToDevice, cs));
-      SB_CUDA(cudaMemcpyAsync(c->d_in[s][1], right + (size_t)c0 * L, (size_t)cn * L, cudaMemcpyHostToDevice, cs));
+      if (!single_end) SB_CUDA(cudaMemcpyAsync(c->d_in[s][1], right + (size_t)c0 * L, (size_t)cn * L, cudaMemcpyHostToDevice, cs));
       SB_CUDA(cudaEventRecord(c->ev_in[s], cs));
       SB_CUDA(cudaStreamWaitEvent(st, c->ev_in[s], 0));
+      if (single_end) dr = c->d_dummy_mate;
     }
     SB_CUDA(cudaMemsetAsync(c->b.n_tasks, 0, 16, st));
     SB_CUDA(cudaMemsetAsync(c->d_next_task, 0, 32, st));
@@ -1405,6 +1427,7 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
   c->totals.lookups += h.lookups; c->totals.postings += h.postings; c->totals.seeds += h.seeds;
   c->totals.candidates += h.candidates; c->totals.kept += h.kept; c->totals.label_entries += h.label_entries;
   c->totals.mapped += h.mapped;
+  for (int i = 0; i < 4; ++i) c->totals.lib_mask_sum[i] += h.lib_mask_sum[i];
   if (stats) {
     stats->n_pairs = n; stats->mapped = h.mapped; stats->lookups = h.lookups; stats->postings = h.postings;
     stats->seeds = h.seeds; stats->candidates = h.candidates; stats->kept = h.kept; stats->label_entries = h.label_entries;
@@ -1563,6 +1586,8 @@ extern "C" int sb_map_finish(sb_map_ctx* c, sb_map_result* out) {
   out->off = c->h_off.data(); out->tids = c->h_tids.data(); out->weights = c->h_w.data();
   out->counts = c->h_counts.data(); out->bins = binned ? c->h_bins.data() : nullptr;
   out->n_mapped = c->totals.mapped;
+  memset(out->lib_format_counts, 0, sizeof(out->lib_format_counts));
+  for (int i = 0; i < 4; ++i) out->lib_format_counts[i] = c->totals.lib_mask_sum[i];
   out->lookups = c->totals.lookups; out->postings = c->totals.postings; out->seeds = c->totals.seeds;
   out->candidates = c->totals.candidates; out->kept = c->totals.kept; out->label_entries = c->totals.label_entries;
   out->n_txps = c->M;

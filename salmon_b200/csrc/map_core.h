@@ -37,6 +37,7 @@ struct Params {
   uint32_t mini_batch, reserved;
   double pre_merge_thresh, post_merge_thresh, orphan_thresh;   // join policy (see sb_map_params)
   int32_t allow_dovetail, allow_orphans;
+  int32_t lib_type, reserved3;      // expected library format (SB_LIB_*)
 };
 
 struct TableEntry {
@@ -79,6 +80,7 @@ struct Cand {
 
 struct Counters {
   unsigned long long lookups, postings, seeds, candidates, kept, label_entries, mapped;
+  unsigned long long lib_mask_sum[4];   // fragments that showed ISF / ISR / SF / SR among their kept mappings
 };
 
 SB_HD uint64_t mix64(uint64_t x) {
@@ -328,6 +330,20 @@ struct Joint {
 //       the read), lefts before rights (SalmonQuantify.cpp:1407-1420).
 // Candidate lists are sorted by (transcript, orientation, diagonal), so the chains of a transcript are one run in each.
 SB_HD uint32_t sbm_maxu(uint32_t a, uint32_t b) { return a > b ? a : b; }
+// Is a joint hit compatible with the expected library format?  (SalmonQuantify.cpp:1467-1517 for paired-end libraries,
+// :2141-2147 single-end; = salmon::utils::isCompatible, src/util/SalmonUtils.cpp:138-298.)  status: 0 pair, 1 left
+// orphan, 2 right orphan; first_fw: the (left, or for a right orphan the right) mate maps forward.
+SB_HD bool lib_compatible(int32_t lib_type, uint32_t status, bool left_fw, bool right_fw) {
+  switch (lib_type) {
+    case 0: return status != 0 || left_fw != right_fw;                    // IU: orphans always, pairs on opposite strands
+    case 1: return status == 0 ? (left_fw && !right_fw) : (status == 1 ? left_fw : !right_fw);   // ISF (strandedness SA)
+    case 2: return status == 0 ? (!left_fw && right_fw) : (status == 1 ? !left_fw : right_fw);   // ISR (AS)
+    case 3: return true;                                                  // U
+    case 4: return left_fw;                                               // SF
+    case 5: return !left_fw;                                              // SR
+    default: return true;
+  }
+}
 SB_HD bool pair_geometry(const Params& p, const Cand& l, const Cand& r, uint32_t L, int32_t& fl) {
   if (l.tid != r.tid || (l.ori_cov >> 31) == (r.ori_cov >> 31)) return false;
   const Cand& fw = ((l.ori_cov >> 31) == 0) ? l : r;      // the mate that maps forward
@@ -401,7 +417,7 @@ SB_HD uint32_t for_each_joint(const Params& p, const Cand* lc, uint32_t nl, cons
     uint32_t best_c = 0;
     for (uint32_t a = 0; a < nl; ++a) if (keep_l >> a & 1) best_c = sbm_maxu(best_c, cand_cov(lc[a]));
     for (uint32_t b = 0; b < nr; ++b) if (keep_r >> b & 1) best_c = sbm_maxu(best_c, cand_cov(rc[b]));
-    const double thr = p.orphan_thresh * (double)best_c;
+    const double thr = (p.lib_type >= 3 ? 0.0 : p.orphan_thresh) * (double)best_c;   // single-end: consensus filter only (joinReadsAndFilterSingle)
     for (uint32_t a = 0; a < nl; ++a) {
       if (!(keep_l >> a & 1) || (double)cand_cov(lc[a]) < thr) continue;
       Joint j; j.tid = lc[a].tid; j.li = (int32_t)a; j.ri = -1; j.frag_len = 0; j.status = 1;
@@ -566,6 +582,11 @@ SB_HD void assign_read(const IndexView& ix, const Params& p, const FldView& fld,
     if (jh[h].ri >= 0) { const int32_t s = score_r[jh[h].ri]; if (s <= NEG_SCORE) bad = true; tot += s; maxPossible += p.ma * (int32_t)L; }
     const int32_t hitScore = (!bad && (double)tot >= p.min_score_fraction * (double)maxPossible) ? tot : INVALID_SCORE;
     sc[h] = hitScore;
+    {   // mappings incompatible with the library format are ignored (ignoreIncompat, SalmonQuantify.cpp:1519-1521)
+      const bool lfw = jh[h].li >= 0 && (lc[jh[h].li].ori_cov >> 31) == 0;
+      const bool rfw = jh[h].ri >= 0 && (rcd[jh[h].ri].ori_cov >> 31) == 0;
+      if (!lib_compatible(p.lib_type, jh[h].status, lfw, rfw)) { sc[h] = INVALID_SCORE; continue; }
+    }
     const bool isDecoy = (int32_t)jh[h].tid >= p.first_decoy;
     const double decoyCutoff = (double)(int32_t)(p.decoy_threshold * (double)bestDecoyScore);
     if (isDecoy) { if (hitScore > bestDecoyScore) bestDecoyScore = hitScore; continue; }
@@ -614,6 +635,15 @@ SB_HD void assign_read(const IndexView& ix, const Params& p, const FldView& fld,
   ctr.kept += na;
   if (na == 0) return;
   ctr.mapped++;
+  {   // observed formats of this fragment (libTypeCountsPerFrag, SalmonQuantify.cpp:765,1000-1002): bit 0 ISF, 1 ISR, 2 SF, 3 SR
+    uint32_t m = 0;
+    for (uint32_t a = 0; a < na; ++a) {
+      const uint32_t st = (o.flags[a] >> 2) & 3;
+      const bool fw = (o.flags[a] & 1) != 0;
+      m |= st == 0 ? (fw ? 1u : 2u) : (fw ? 4u : 8u);
+    }
+    ctr.lib_mask_sum[0] += m & 1u; ctr.lib_mask_sum[1] += (m >> 1) & 1u; ctr.lib_mask_sum[2] += (m >> 2) & 1u; ctr.lib_mask_sum[3] += (m >> 3) & 1u;
+  }
   ctr.label_entries += na;
   // ---- SalmonQuantify.cpp:599-857 (state frozen per batch); aux kept in o.weight until normalised
   double auxDenom = log0(), sumLp = log0();

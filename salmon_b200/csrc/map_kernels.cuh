@@ -460,6 +460,7 @@ k_seed_chain_w(IndexView ix, Params p, PackedReads pr, uint32_t n, uint32_t L, S
   uint64_t* gkeys = o.overflow_keys + (size_t)warp * MAXSEEDS;
   Counters ctr;
   ctr.lookups = ctr.postings = ctr.seeds = ctr.candidates = ctr.kept = ctr.label_entries = ctr.mapped = 0;
+  ctr.lib_mask_sum[0] = ctr.lib_mask_sum[1] = ctr.lib_mask_sum[2] = ctr.lib_mask_sum[3] = 0;
   for (uint32_t r = warp; r < n; r += nwarps) {
     uint32_t ncand[2];
 #pragma unroll 1
@@ -568,7 +569,7 @@ k_seed_chain_w(IndexView ix, Params p, PackedReads pr, uint32_t n, uint32_t L, S
       }
 #pragma unroll
       for (int sft = 16; sft > 0; sft >>= 1) best_c = max(best_c, __shfl_xor_sync(0xffffffffu, best_c, sft));
-      const double thr = p.orphan_thresh * (double)best_c;
+      const double thr = (p.lib_type >= 3 ? 0.0 : p.orphan_thresh) * (double)best_c;
       bool ol[2], orr[2];
 #pragma unroll
       for (int rd = 0; rd < 2; ++rd) {

@@ -300,6 +300,7 @@ struct MetaIn {
   const uint64_t* uniq; const uint64_t* total;
   std::string files, start_time, end_time;
   int n_ranks;
+  uint64_t lib_counts[4];     // fragments that showed ISF / ISR / SF / SR among their kept mappings
 };
 std::string time_string() {
   time_t t = time(nullptr);
@@ -364,7 +365,7 @@ int write_run_metadata(const std::string& outs, const MetaIn& m) {
     char buf[4096];
     snprintf(buf, sizeof buf,
              "{\n    \"salmon_version\": \"1.11.4-sb%d\",\n    \"samp_type\": \"%s\",\n    \"opt_type\": \"%s\",\n    \"quant_errors\": [],\n"
-             "    \"num_libraries\": 1,\n    \"library_types\": [\n        \"IU\"\n    ],\n    \"frag_dist_length\": %zu,\n"
+             "    \"num_libraries\": 1,\n    \"library_types\": [\n        \"%s\"\n    ],\n    \"frag_dist_length\": %zu,\n"
              "    \"frag_length_mean\": %.6f,\n    \"frag_length_sd\": %.6f,\n    \"seq_bias_correct\": false,\n    \"gc_bias_correct\": false,\n"
              "    \"num_bias_bins\": 0,\n    \"mapping_type\": \"mapping\",\n    \"keep_duplicates\": false,\n    \"num_valid_targets\": %u,\n"
              "    \"num_decoy_targets\": %u,\n    \"num_eq_classes\": %llu,\n    \"serialized_eq_classes\": %s,\n    \"eq_class_properties\": [%s],\n"
@@ -373,21 +374,34 @@ int write_run_metadata(const std::string& outs, const MetaIn& m) {
              "    \"num_fragments_filtered_vm\": 0,\n    \"num_alignments_below_threshold_for_mapped_fragments_vm\": 0,\n"
              "    \"percent_mapped\": %.6f,\n    \"call\": \"quant\",\n    \"start_time\": \"%s\",\n    \"end_time\": \"%s\",\n    \"sb_num_gpus\": %d\n}\n",
              sb_version(), m.o->num_bootstraps ? "bootstrap" : (m.o->num_gibbs ? "gibbs" : "none"), m.ep->use_vbem ? "vb" : "em",
+             (m.mp->lib_type >= 0 && m.mp->lib_type <= 5) ? (const char* const[]){"IU", "ISF", "ISR", "U", "SF", "SR"}[m.mp->lib_type] : "IU",
              pmf.size(), mean, sd, m.n_valid, m.n_decoy, (unsigned long long)m.n_classes,
              (m.o->dump_eq || m.o->dump_eq_weights) ? "true" : "false",
              m.mp->range_bins ? "\n        \"range_factorized\"\n    " : "", n_samp, (unsigned long long)m.n_observed,
              (unsigned long long)m.n_mapped, pct, m.start_time.c_str(), m.end_time.c_str(), m.n_ranks);
     ok = write_text(outs + "/aux_info/meta_info.json", buf) && ok;
   }
-  {   // lib_format_counts.json: the library is IU; every kept mapping is compatible with it (inward pairs, orphans)
+  {   // lib_format_counts.json (ReadExperiment.inl:219-350): every kept mapping is compatible with the expected format
+      // (incompatible ones are ignored while mapping), so compatible = assigned; the per-format counts are what the
+      // fragments showed; strand_mapping_bias = first strand variant / both, as summarizeLibraryTypeCounts computes it
+    static const char* const lib_names[] = {"IU", "ISF", "ISR", "U", "SF", "SR"};
+    const int lt = m.mp->lib_type;
+    const bool pe = lt < 3;
+    const uint64_t f1 = pe ? m.lib_counts[0] : m.lib_counts[2], f2 = pe ? m.lib_counts[1] : m.lib_counts[3];
+    const bool unstranded = lt == 0 || lt == 3;
+    const uint64_t agree = unstranded ? f1 + f2 : ((lt == 1 || lt == 4) ? f1 : f2);
+    const uint64_t other = pe ? m.lib_counts[2] + m.lib_counts[3] : 0;          // orphans of a paired-end library
+    const double ratio = (f1 + f2) ? (double)f1 / (double)(f1 + f2) : 0.0;
     char buf[2048];
     snprintf(buf, sizeof buf,
-             "{\n    \"read_files\": \"%s\",\n    \"expected_format\": \"IU\",\n    \"compatible_fragment_ratio\": %.6f,\n"
+             "{\n    \"read_files\": \"%s\",\n    \"expected_format\": \"%s\",\n    \"compatible_fragment_ratio\": %.6f,\n"
              "    \"num_compatible_fragments\": %llu,\n    \"num_assigned_fragments\": %llu,\n"
-             "    \"num_frags_with_concordant_consistent_mappings\": %llu,\n    \"num_frags_with_inconsistent_or_orphan_mappings\": 0,\n"
-             "    \"strand_mapping_bias\": 0.0\n}\n",
-             m.files.c_str(), m.n_mapped ? 1.0 : 0.0, (unsigned long long)m.n_mapped, (unsigned long long)m.n_mapped,
-             (unsigned long long)m.n_mapped);
+             "    \"num_frags_with_concordant_consistent_mappings\": %llu,\n    \"num_frags_with_inconsistent_or_orphan_mappings\": %llu,\n"
+             "    \"strand_mapping_bias\": %.6f,\n    \"ISF\": %llu,\n    \"ISR\": %llu,\n    \"SF\": %llu,\n    \"SR\": %llu\n}\n",
+             m.files.c_str(), lib_names[lt < 0 || lt > 5 ? 0 : lt], m.n_mapped ? 1.0 : 0.0, (unsigned long long)m.n_mapped,
+             (unsigned long long)m.n_mapped, (unsigned long long)agree, (unsigned long long)other, ratio,
+             (unsigned long long)m.lib_counts[0], (unsigned long long)m.lib_counts[1], (unsigned long long)m.lib_counts[2],
+             (unsigned long long)m.lib_counts[3]);
     ok = write_text(outs + "/lib_format_counts.json", buf) && ok;
   }
   if (!ok) { sb::set_error("write error on the run metadata under %s", outs.c_str()); return SB_ERR_INVALID; }
@@ -464,7 +478,7 @@ int run_samples(sb_em_ctx* em, const sb_em_params& ep, const sb_quant_opts& o, c
 extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const char* const* mates2, uint32_t n_files,
                               const sb_map_params* mp_in, const sb_em_params* ep_in, const sb_quant_opts* o_in,
                               const char* out_dir, double* alpha_out, sb_quant_summary* sum) {
-  if (!ix || !mates1 || !mates2 || !n_files) { sb::set_error("sb_quant_files: null argument (paired-end input only)"); return SB_ERR_INVALID; }
+  if (!ix || !mates1 || !n_files) { sb::set_error("sb_quant_files: null argument"); return SB_ERR_INVALID; }
   sb_quant_opts o;
   if (o_in) o = *o_in; else sb_quant_default_opts(&o);
   if (o.batch < 1024) o.batch = 1024;
@@ -487,6 +501,13 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
   if (mp_in) mp = *mp_in; else sb_map_default_params(&mp);
   sb_em_params ep;
   if (ep_in) ep = *ep_in; else sb_em_default_params(&ep);
+  // single-end libraries (-r, library types U / SF / SR) come with mates2 == NULL
+  const bool single_end = mp.lib_type >= SB_LIB_U;
+  if (single_end != (mates2 == nullptr)) {
+    sb::set_error(single_end ? "a single-end library type takes unmated reads only (mates2 == NULL)"
+                             : "a paired-end library type needs both mate files");
+    return SB_ERR_INVALID;
+  }
   uint32_t M = 0, k = 0, first_decoy = 0;
   const char* const* names = nullptr;
   const uint32_t* complete_len = nullptr;
@@ -573,10 +594,13 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
     std::vector<double> hist((size_t)mp.max_frag_len + 1, 0.0);
     SB_TRY(sb_map_online_state(S.ctx, nullptr, hist.data(), nullptr, nullptr));
     std::string files = "[ ";
-    for (uint32_t f = 0; f < n_files; ++f) files += std::string(f ? ", " : "") + "( " + mates1[f] + ", " + mates2[f] + " )";
+    for (uint32_t f = 0; f < n_files; ++f)
+      files += std::string(f ? ", " : "") + (mates2 ? std::string("( ") + mates1[f] + ", " + mates2[f] + " )" : std::string(mates1[f]));
     files += " ]";
+    uint64_t libc[4] = {res.lib_format_counts[0], res.lib_format_counts[1], res.lib_format_counts[2], res.lib_format_counts[3]};
+    if (multi) SB_TRY(sb_comm_allreduce(S.comm, libc, 4, 1, 0));
     MetaIn mi{&o, &ep, &mp, Mq, M - Mq, n_observed, n_mapped_u, res.n_classes, &hist, glob.unique_counts, glob.total_counts,
-              files, start_time, time_string(), (int)o.shard_count};
+              files, start_time, time_string(), (int)o.shard_count, {libc[0], libc[1], libc[2], libc[3]}};
     SB_TRY(write_run_metadata(outs, mi));
   }
   if (o.num_bootstraps || o.num_gibbs) {

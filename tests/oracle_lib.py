@@ -187,7 +187,7 @@ class orc_map_params(C.Structure):
         ("min_aln_prob", C.c_double), ("decoy_threshold", C.c_double), ("fld_mean", C.c_double), ("fld_sd", C.c_double),
         ("num_pre_burnin", C.c_uint64), ("num_burnin", C.c_uint64),
         ("pre_merge_thresh", C.c_double), ("post_merge_thresh", C.c_double), ("orphan_thresh", C.c_double),
-        ("allow_dovetail", C.c_int32), ("allow_orphans", C.c_int32),
+        ("allow_dovetail", C.c_int32), ("allow_orphans", C.c_int32), ("lib_type", C.c_int32), ("reserved3", C.c_int32),
     ]
 
 
@@ -202,7 +202,7 @@ MAP_DEFAULTS = dict(k=31, stride=4, max_occs_per_hit=1000, max_read_occ=200, max
                     range_bins=4, ma=2, mp=-4, go=6, ge=2, hard_filter=0, first_decoy=2**31 - 1, consensus_frac=0.65,
                     min_score_fraction=0.65, score_exp=1.0, min_aln_prob=1e-5, decoy_threshold=1.0, fld_mean=250.0,
                     fld_sd=25.0, num_pre_burnin=5000, num_burnin=5000000, pre_merge_thresh=0.75, post_merge_thresh=0.9,
-                    orphan_thresh=0.95, allow_dovetail=0, allow_orphans=1)
+                    orphan_thresh=0.95, allow_dovetail=0, allow_orphans=1, lib_type=0)
 
 
 def map_params(**over):

@@ -394,3 +394,41 @@ def test_join_policy_knobs_gpu_vs_oracle(oracle):
             ctx.close()
             ref = oracle.map_reads(oix, oracle.map_params(**over), left, right, 0)
             compare(got, ref, p.max_read_occ)
+
+
+def test_library_types_and_single_end_gpu_vs_oracle(oracle):
+    """row a1: expected library formats IU / ISF / ISR (paired) and U / SF / SR (single-end reads: sb_map_batch with
+    right = None) on the CUDA path against the oracle -- alignments and labels bit-exact, class tables equal; the
+    per-format fragment counts against a recount from the alignments"""
+    from test_map_host import LIB, stranded_reads
+    txps, left, right, flip = stranded_reads()
+    idx = Index(txps)
+    oix = oracle.MapIndex(txps)
+    absent = np.full_like(right, 4)
+    for lib, se in (("IU", False), ("ISF", False), ("ISR", False), ("U", True), ("SF", True), ("SR", True)):
+        over = dict(lib_type=LIB[lib])
+        if se:
+            over["pre_merge_thresh"] = 1.0
+        p = map_default_params(**over)
+        ctx = MapContext(idx, p, batch_cap=8192, max_read_len=100)
+        ctx.map_batch(left, None if se else right)
+        got = ctx.last_alignments()
+        res = ctx.finish()
+        ctx.close()
+        ref = oracle.map_reads(oix, oracle.map_params(**over), left, absent if se else right, 0)
+        compare(got, ref, p.max_read_occ)
+        check_classes(res, oracle.eq_aggregate(ref, p.max_read_occ, True))
+        # observed formats per fragment (SalmonQuantify.cpp:765,1000-1002)
+        cap = p.max_read_occ
+        valid = np.arange(cap)[None, :] < got["n_aln"][:, None]
+        st = (got["flags"] >> 2) & 3; fw = (got["flags"] & 1) == 1
+        want = dict(ISF=int((valid & (st == 0) & fw).any(axis=1).sum()), ISR=int((valid & (st == 0) & ~fw).any(axis=1).sum()),
+                    SF=int((valid & (st != 0) & fw).any(axis=1).sum()), SR=int((valid & (st != 0) & ~fw).any(axis=1).sum()))
+        assert res["lib_format_counts"] == want, (lib, res["lib_format_counts"], want)
+        if se:
+            assert want["ISF"] == want["ISR"] == 0
+    # a paired type without the second mate (and the reverse) is refused
+    ctx = MapContext(idx, map_default_params(), batch_cap=64, max_read_len=100)
+    with pytest.raises(Exception, match="both mates"):
+        ctx.map_batch(left[:8], None)
+    ctx.close()

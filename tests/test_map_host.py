@@ -239,3 +239,59 @@ def test_join_policy_monotonicity(oracle):
     assert (noorph["n_aln"] > 0).sum() < (base["n_aln"] > 0).sum() - 300
     assert int(loose["n_aln"].sum()) >= int(base["n_aln"].sum()) >= int(strict["n_aln"].sum())
     assert int(loose["n_aln"].sum()) > int(strict["n_aln"].sum())
+
+
+LIB = dict(IU=0, ISF=1, ISR=2, U=3, SF=4, SR=5)
+
+
+def stranded_reads(seed=81, n=5000, flip_frac=0.4):
+    """pairs drawn as synth_reads draws them (the fragment's first mate is the left one, i.e. ISF-like when the fragment
+    is on the forward strand) with a known fraction of pairs swapped (left <-> right), which flips their strandedness"""
+    txps, _ = synth_txome(seed=seed, n_genes=100)
+    left, right, truth = synth_reads(txps, seed=seed + 1, n=n)
+    rng = np.random.default_rng(seed + 2)
+    flip = rng.random(n) < flip_frac
+    l2, r2 = left.copy(), right.copy()
+    l2[flip], r2[flip] = right[flip], left[flip]
+    return txps, l2, r2, flip
+
+
+@pytest.mark.parametrize("lib", ["IU", "ISF", "ISR"])
+def test_paired_library_types_host_logic_vs_oracle(oracle, lib):
+    """expected library format (row a1): mappings incompatible with it are ignored (SalmonQuantify.cpp:1467-1521;
+    salmon::utils::compatibleHit, SalmonUtils.cpp:193-298) -- product logic vs the oracle, and what the types mean"""
+    txps, left, right, flip = stranded_reads()
+    got, ref = run_both(oracle, txps, left, right, lib_type=LIB[lib])
+    cap = got["flags"].shape[1]
+    valid = np.arange(cap)[None, :] < got["n_aln"][:, None]
+    st = (got["flags"] >> 2) & 3
+    lfw = (got["flags"] & 1) == 1
+    pair = valid & (st == 0)
+    if lib == "ISF":
+        assert lfw[pair].all()
+    if lib == "ISR":
+        assert (~lfw[pair]).all()
+    test_paired_library_types_host_logic_vs_oracle.mapped[lib] = int((got["n_aln"] > 0).sum())
+    m = test_paired_library_types_host_logic_vs_oracle.mapped
+    if len(m) == 3:       # a stranded type keeps one orientation: together they cover what IU maps
+        assert m["ISF"] < m["IU"] and m["ISR"] < m["IU"] and m["ISF"] + m["ISR"] >= m["IU"]
+
+
+test_paired_library_types_host_logic_vs_oracle.mapped = {}
+
+
+@pytest.mark.parametrize("lib", ["U", "SF", "SR"])
+def test_single_end_library_types_host_logic_vs_oracle(oracle, lib):
+    """single-end reads = pairs whose second mate is absent (all N): every mapping is a left orphan; SF / SR keep one strand"""
+    txps, left, right, flip = stranded_reads(seed=91)
+    absent = np.full_like(right, 4)
+    got, ref = run_both(oracle, txps, left, absent, lib_type=LIB[lib], pre_merge_thresh=1.0)
+    cap = got["flags"].shape[1]
+    valid = np.arange(cap)[None, :] < got["n_aln"][:, None]
+    assert ((((got["flags"] >> 2) & 3) == 1) | ~valid).all()
+    fw = (got["flags"] & 1) == 1
+    if lib == "SF":
+        assert fw[valid].all()
+    if lib == "SR":
+        assert (~fw[valid]).all()
+    assert (got["n_aln"] > 0).sum() > (1500 if lib != "U" else 4000)

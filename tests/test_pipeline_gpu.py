@@ -222,3 +222,37 @@ def test_cli_eqclasses_bootstraps(tmp_path):
     rows = (tmp_path / "o" / "quant.sf").read_text().splitlines()
     got = np.array([float(x.split("\t")[4]) for x in rows[1:]])
     np.testing.assert_allclose(got, py["alpha"], rtol=0, atol=6e-4)     # %.3f
+
+
+def test_cli_single_end_and_stranded_libraries(tmp_path):
+    """`sb_salmon quant -l SF -r reads.fq` and `-l ISF -1 -2`: quant.sf, lib_format_counts.json with the observed formats"""
+    import json
+    import subprocess
+    txps, _ = synth_txome(seed=49, n_genes=100)
+    left, right, truth = synth_reads(txps, seed=50, n=12000)
+    names = [f"ENST{i:05d}" for i in range(len(txps))]
+    idx = Index(txps, names=names)
+    ipath = tmp_path / "idx"; ipath.mkdir()
+    idx.save(str(ipath / "sb_index.bin"))
+    f1, f2 = str(tmp_path / "s_1.fq"), str(tmp_path / "s_2.fq")
+    write_fastq(f1, left, gz=False); write_fastq(f2, right, gz=False)
+    exe = os.path.join(os.path.dirname(_capi.LIB_PATH), "sb_salmon")
+    runs = {}
+    for tag, args in (("U", ["-l", "U", "-r", f1]), ("SF", ["-l", "SF", "-r", f1]), ("SR", ["-l", "SR", "-r", f1]),
+                      ("IU", ["-l", "IU", "-1", f1, "-2", f2]), ("ISF", ["-l", "ISF", "-1", f1, "-2", f2])):
+        out = tmp_path / tag
+        r = subprocess.run([exe, "quant", "-i", str(ipath)] + args + ["-o", str(out), "--batch", "4096", "--maxReadLen", "128"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        lfc = json.loads((out / "lib_format_counts.json").read_text())
+        meta = json.loads((out / "aux_info" / "meta_info.json").read_text())
+        assert lfc["expected_format"] == tag and meta["library_types"] == [tag]
+        rows = (out / "quant.sf").read_text().splitlines()
+        assert len(rows) == len(txps) + 1
+        runs[tag] = (lfc, meta["num_mapped"])
+    assert runs["U"][1] == runs["SF"][1] + runs["SR"][1] or runs["U"][1] <= runs["SF"][1] + runs["SR"][1]
+    assert runs["SF"][0]["SR"] == 0 and runs["SR"][0]["SF"] == 0 and runs["U"][0]["ISF"] == 0
+    assert runs["ISF"][0]["ISR"] == 0 and runs["IU"][0]["ISF"] + runs["IU"][0]["ISR"] > 0
+    assert 0 < runs["ISF"][1] < runs["IU"][1]
+    r = subprocess.run([exe, "quant", "-i", str(ipath), "-l", "SF", "-1", f1, "-2", f2, "-o", str(tmp_path / "bad")], capture_output=True, text=True)
+    assert r.returncode != 0 and "does not fit the input" in r.stderr
