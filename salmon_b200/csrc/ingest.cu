@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "pgzip.h"
 
 namespace {
 
@@ -49,7 +50,8 @@ struct RecBlock {               // recycled through Stream::pool: no allocation 
   size_t cap = 0, len = 0;
   std::vector<uint32_t> seq;   // 2 per record: offset, length of the sequence line
   uint32_t n = 0;
-  bool borrowed = false;       // buf points into a memory-mapped file (parallel splitter): not ours to free or reuse
+  bool borrowed = false;       // buf points into a memory-mapped file or an inflated piece: not ours to free or reuse
+  std::shared_ptr<void> keep;  // (inflated piece: released with the last block that points into it)
   ~RecBlock() { if (!borrowed) free(buf); }
   bool reserve(size_t need) {
     if (need <= cap) return true;
@@ -79,6 +81,7 @@ struct Stream {
   std::vector<std::unique_ptr<RecBlock>> pool;   // consumed blocks, reused by the splitter
   std::vector<std::pair<void*, size_t>> maps;     // memory-mapped plain files (unmapped by sb_reads_close)
   int scanners = 1;                               // plain files: threads that cut sub-ranges of a wave in parallel
+  int inflaters = 1;                              // gzip files: inflate threads (pgzip.h); 1 = zlib's gzread
   bool done = false, stop = false;
   std::string err;
   Prof prof;
@@ -319,6 +322,127 @@ bool split_mapped(Stream* s, const std::string& path, std::string& err) {
   return true;
 }
 
+// Cut [buf, buf+len) -- text that starts at a record start -- into whole records with up to `scanners` threads and queue
+// the blocks in order (they point into buf; `keep` keeps it alive).  eof: nothing follows this text.  Returns the bytes
+// consumed (the rest is the beginning of a record that continues in the next piece).
+size_t scan_wave(Stream* s, const std::shared_ptr<void>& keep, const char* buf, size_t len, bool eof, bool fasta,
+                 const std::string& path, std::string& err) {
+  const int W = std::max(1, std::min(s->scanners, (int)(len >> 20) + 1));
+  std::vector<size_t> b(1, 0);
+  for (int i = 1; i < W; ++i) {
+    const size_t q = next_record_start(buf, len / W * i, len, fasta);
+    if (q > b.back() && q < len) b.push_back(q);
+  }
+  b.push_back(len);
+  const int nr = (int)b.size() - 1;
+  std::vector<std::unique_ptr<RecBlock>> blks(nr);
+  std::vector<std::string> errs(nr);
+  std::vector<size_t> cuts(nr, 0);
+  for (int i = 0; i < nr; ++i) { blks[i].reset(new RecBlock()); blks[i]->borrowed = true; blks[i]->keep = keep; }
+#pragma omp parallel for schedule(static, 1) num_threads(nr)
+  for (int i = 0; i < nr; ++i) {
+    RecBlock* k = blks[i].get();
+    k->buf = const_cast<char*>(buf + b[i]);
+    k->len = b[i + 1] - b[i];
+    k->seq.reserve(2 * (k->len / 200 + 16));
+    const bool last = i == nr - 1;
+    cuts[i] = scan_records(k->buf, k->len, last ? eof : true, k, errs[i]);
+    if (errs[i].empty() && cuts[i] != k->len && (!last || eof)) {
+      for (size_t x = cuts[i]; x < k->len; ++x)
+        if (k->buf[x] != '\n' && k->buf[x] != '\r' && k->buf[x] != ' ' && k->buf[x] != '\t') {
+          errs[i] = last ? "truncated record at the end of " + path : "malformed record (" + path + ")";
+          break;
+        }
+    }
+    k->n = (uint32_t)(k->seq.size() / 2);
+  }
+  for (int i = 0; i < nr; ++i) {
+    if (!errs[i].empty()) { err = errs[i]; if (err.find(path) == std::string::npos) err += " (" + path + ")"; return 0; }
+    if (!blks[i]->n) continue;
+    const double t0 = wall();
+    const bool pushed = push_block(s, std::move(blks[i]));
+    s->prof.t_push_wait += wall() - t0;
+    if (!pushed) { err = "stopped"; return 0; }
+  }
+  return b[nr - 1] + cuts[nr - 1];
+}
+
+// ---- gzip files: inflated by several threads (pgzip.h), cut like the mapped plain files -------------------------------
+// returns false (and leaves the file to the serial gzread path) when the file cannot be mapped or is not gzip
+bool split_gz_parallel(Stream* s, const std::string& path, std::string& err) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  struct stat stt;
+  if (fstat(fileno(f), &stt) != 0 || !S_ISREG(stt.st_mode) || stt.st_size == 0) { fclose(f); return false; }
+  const size_t flen = (size_t)stt.st_size;
+  void* mp = mmap(nullptr, flen, PROT_READ, MAP_PRIVATE, fileno(f), 0);
+  fclose(f);
+  if (mp == MAP_FAILED) return false;
+  madvise(mp, flen, MADV_SEQUENTIAL);
+  struct Unmap { void* p; size_t n; ~Unmap() { munmap(p, n); } } unmap{mp, flen};
+  sb::pgz::ParallelGz pg((const uint8_t*)mp, flen, s->inflaters);
+  std::string perr;
+  if (!pg.start(perr)) return false;
+  std::vector<char> carry;
+  bool first = true, fasta = false;
+  sb::pgz::Piece pc;
+  for (;;) {
+    double t0 = wall();
+    const bool more = pg.next(pc, perr);
+    s->prof.t_read += wall() - t0;
+    if (!more) break;
+    std::shared_ptr<void> keep = pc.keep;
+    char* data = (char*)pc.data;
+    size_t len = pc.len;
+    if (!carry.empty()) {
+      if (carry.size() <= sb::pgz::HEAD) {             // the piece's head room takes the carried partial record
+        data -= carry.size();
+        memcpy(data, carry.data(), carry.size());
+        len += carry.size();
+      } else {
+        char* nb = (char*)malloc(carry.size() + len);
+        if (!nb) { err = "out of memory"; return true; }
+        memcpy(nb, carry.data(), carry.size());
+        memcpy(nb + carry.size(), pc.data, len);
+        keep = std::shared_ptr<void>(nb, free);
+        data = nb;
+        len += carry.size();
+      }
+      carry.clear();
+    }
+    if (first) {
+      size_t p0 = 0;
+      while (p0 < len && (data[p0] == '\n' || data[p0] == '\r')) ++p0;
+      if (p0 == len) continue;                           // only blank lines so far
+      if (data[p0] != '@' && data[p0] != '>') { err = "malformed read file: record does not start with '@' or '>' (" + path + ")"; return true; }
+      fasta = data[p0] == '>';
+      data += p0; len -= p0;
+      first = false;
+    }
+    t0 = wall();
+    const size_t used = scan_wave(s, keep, data, len, false, fasta, path, err);
+    s->prof.t_scan += wall() - t0;
+    if (!err.empty()) return true;
+    carry.assign(data + used, data + len);
+  }
+  if (!perr.empty()) { err = "read error in " + path + ": " + perr; return true; }
+  if (!carry.empty()) {                                  // the last record(s): nothing follows
+    char* nb = (char*)malloc(carry.size());
+    if (!nb) { err = "out of memory"; return true; }
+    memcpy(nb, carry.data(), carry.size());
+    std::shared_ptr<void> keep(nb, free);
+    if (first) {
+      size_t p0 = 0;
+      while (p0 < carry.size() && (nb[p0] == '\n' || nb[p0] == '\r')) ++p0;
+      if (p0 == carry.size()) return true;
+      if (nb[p0] != '@' && nb[p0] != '>') { err = "malformed read file: record does not start with '@' or '>' (" + path + ")"; return true; }
+      fasta = nb[p0] == '>';
+    }
+    scan_wave(s, keep, nb, carry.size(), true, fasta, path, err);
+  }
+  return true;
+}
+
 void split_stream(Stream* s) {
   std::string err;
   for (const std::string& path : s->files) {
@@ -326,6 +450,14 @@ void split_stream(Stream* s) {
     if (!in.open(path.c_str())) { err = "cannot open " + path; break; }
     if (in.f && s->scanners > 0) {   // plain file: mapped and cut in parallel (falls through when it cannot be mapped)
       if (split_mapped(s, path, err)) {
+        in.close();
+        if (err == "stopped") { finish_stream(s, ""); return; }
+        if (!err.empty()) break;
+        continue;
+      }
+    }
+    if (in.g && s->inflaters > 1) {   // gzip file: inflated by several threads (falls through when it cannot be mapped)
+      if (split_gz_parallel(s, path, err)) {
         in.close();
         if (err == "stopped") { finish_stream(s, ""); return; }
         if (!err.empty()) break;
@@ -467,7 +599,10 @@ extern "C" sb_reads* sb_reads_open(const char* const* files1, const char* const*
   // plain files are cut by several scanner threads per stream (SB_READS_SCANNERS overrides; 0 = serial splitter)
   int scanners = (int)std::max<uint32_t>(1, std::min<uint32_t>(8, r->n_threads / 4));
   if (const char* e = getenv("SB_READS_SCANNERS")) scanners = atoi(e);
-  for (int m = 0; m < r->n_streams; ++m) r->st[m].scanners = scanners;
+  // gzip files: inflate threads per stream (SB_READS_INFLATERS overrides; 1 = zlib's gzread on the splitter thread)
+  int inflaters = (int)std::max<uint32_t>(1, std::min<uint32_t>(32, r->n_threads / (uint32_t)r->n_streams));
+  if (const char* e = getenv("SB_READS_INFLATERS")) inflaters = std::max(1, atoi(e));
+  for (int m = 0; m < r->n_streams; ++m) { r->st[m].scanners = scanners; r->st[m].inflaters = inflaters; }
   for (int m = 0; m < r->n_streams; ++m) r->st[m].th = std::thread(split_stream, &r->st[m]);
   return r;
 }

@@ -7,6 +7,7 @@
 #include <cub/cub.cuh>
 #include <math.h>
 #include <string.h>
+#include <time.h>
 
 #include <sys/stat.h>
 
@@ -868,6 +869,7 @@ struct sb_map_ctx {
   BatchBufs b{};                     // cand/score/task buffers: one chunk; outputs: whole batch
   // k_assign of chunk i runs on its own stream next to the seed / DP kernels of chunk i+1 (it is latency-bound at
   // ~10 % issue utilisation, they are issue-bound): the buffers both sides touch exist twice
+  int profile = 0;          // SB_MAP_PROFILE: per-batch host / device times on stderr
   int overlap_assign = 1;   // +2.7 % at human scale (profiles/stageA_r1_overlap_ab.txt); results bit-identical
   cudaStream_t assign_stream = nullptr;
   cudaEvent_t ev_dp[2] = {nullptr, nullptr}, ev_asg[2] = {nullptr, nullptr};
@@ -1006,6 +1008,12 @@ static int agg_reserve(AggScratch& a, uint64_t n) {
   return SB_OK;
 }
 
+static inline double wall_s() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
 extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int device, uint32_t batch_cap,
                                      uint32_t max_read_len) {
   if (!ix || !q) { sb::set_error("null argument"); return nullptr; }
@@ -1057,6 +1065,7 @@ extern "C" sb_map_ctx* sb_map_create(sb_index* ix, const sb_map_params* q, int d
     cudaEventCreateWithFlags(&c->ev_asg[s], cudaEventDisableTiming);
   }
   if (const char* e = getenv("SB_MAP_OVERLAP")) c->overlap_assign = atoi(e) ? 1 : 0;
+  c->profile = getenv("SB_MAP_PROFILE") ? 1 : 0;
   cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
   for (int s = 0; s < 2; ++s) {
     cudaEventCreateWithFlags(&c->ev_in[s], cudaEventDisableTiming);
@@ -1266,6 +1275,8 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
   }
   if (n > c->batch_cap || L > c->read_len_cap || L < c->p.k) { sb::set_error("batch larger than the context was created for"); return SB_ERR_INVALID; }
   SB_CUDA(cudaSetDevice(c->device));
+  const double t_begin = wall_s();
+  double t_agg = t_begin;
   cudaStream_t st = c->stream, cs = c->copy_stream;
   if (single_end) {
     // single-end reads (processReads SE, SalmonQuantify.cpp:1880-2325) travel through the paired kernels with an absent
@@ -1403,6 +1414,7 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
     // reads without alignments have empty labels: they all hash alike and form one "empty"
     // class; aggregate() keeps it and finish() drops it.
     Records R{n, a.lstart, a.llen, a.wstart, a.wlen, b.label, b.weight, nullptr};
+    t_agg = wall_s();
     SB_TRY(aggregate(c, R, es));
     c->stores.push_back(es);
   }
@@ -1411,8 +1423,14 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
   SB_CUDA(cudaMemcpyAsync(&h, b.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaMemcpyAsync(&full_dp, c->d_full_dp, 8, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaEventRecord(c->ev1, st));
+  const double t_enq = wall_s();
   SB_CUDA(cudaEventSynchronize(c->ev1));
   cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+  if (c->profile) {
+    const double t_end = wall_s();
+    fprintf(stderr, "sb_map_batch: n %u host enqueue %.2f ms (aggregate %.2f ms), final wait %.2f ms, device %.2f ms\n", n,
+            (t_enq - t_begin) * 1e3, (t_enq - t_agg) * 1e3, (t_end - t_enq) * 1e3, c->last_ms);
+  }
   c->frag_counter += h.mapped;
   c->frags_seen += n;
   c->timestep += nsteps;

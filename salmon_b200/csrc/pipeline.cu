@@ -236,17 +236,22 @@ extern "C" int sb_reads_bucketed(sb_reads* rd, uint32_t min_len, uint32_t batch,
   int rc = SB_OK;
   std::string cb_err;
   uint64_t n_batches = 0, n_delivered = 0;
+  double t_wait_job = 0, t_cb = 0;
   for (;;) {
     Job j{nullptr};
     {
+      const double tw = now_s();
       std::unique_lock<std::mutex> lk(P.mu);
       P.cv_job.wait(lk, [&] { return !P.jobs.empty() || P.reader_done; });
+      t_wait_job += now_s() - tw;
       if (P.jobs.empty()) break;
       j = P.jobs.front();
       P.jobs.pop_front();
     }
     if (rc == SB_OK) {
+      const double tc = now_s();
       rc = cb(user, j.b->left, paired ? j.b->right : nullptr, j.b->n, j.b->L);
+      t_cb += now_s() - tc;
       if (rc != SB_OK) {
         cb_err = sb_last_error();
         std::lock_guard<std::mutex> lk(P.mu);
@@ -264,6 +269,9 @@ extern "C" int sb_reads_bucketed(sb_reads* rd, uint32_t min_len, uint32_t batch,
     P.cv_free.notify_all();
   }
   rt.join();
+  if (getenv("SB_READS_PROFILE"))
+    fprintf(stderr, "sb_reads_bucketed: consumer waited %.3f s for batches, spent %.3f s in the callback (%llu batches)\n", t_wait_job, t_cb,
+            (unsigned long long)n_batches);
   const uint32_t n_lengths = (uint32_t)buckets.size();
   for (auto& kv : buckets) { kv.second->buf[0].release(); kv.second->buf[1].release(); }
   if (stats) {
@@ -529,6 +537,7 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
   }
   S.ctx = sb_map_create(ix, &mp, o.device, o.batch, o.max_read_len);
   if (!S.ctx) return SB_ERR_CUDA;
+  if (getenv("SB_READS_PROFILE")) fprintf(stderr, "sb_quant_files: sb_map_create %.3f s\n", now_s() - t0);
   S.rd = sb_reads_open(mates1, mates2, n_files, o.threads);
   if (!S.rd) return SB_ERR_INVALID;
 

@@ -31,7 +31,15 @@ for fh in f: fh.close()
 print(f"reads: {n} pairs written in {time.time()-t0:.0f} s", flush=True)
 PY
 ls -la $D
-/usr/bin/time -v salmon_b200/sb_salmon quant -i $D/idx -l IU -1 $D/r_1.fq -2 $D/r_2.fq -o $D/out -p 32 --maxReadLen 128 > gpurun_out/config2_run.txt 2>&1 || true
-grep -E "fragments observed|mapping |Elapsed|Maximum resident" gpurun_out/config2_run.txt
+python - <<PY > gpurun_out/config2_run.txt 2>&1 || true
+import subprocess, time, resource
+t0 = time.time()
+r = subprocess.run("salmon_b200/sb_salmon quant -i $D/idx -l IU -1 $D/r_1.fq -2 $D/r_2.fq -o $D/out -p 32 --maxReadLen 128".split(),
+                   stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+print(r.stdout)
+ru = resource.getrusage(resource.RUSAGE_CHILDREN)
+print(f"exit {r.returncode}  Elapsed wall {time.time() - t0:.2f} s  user {ru.ru_utime:.1f} s  sys {ru.ru_stime:.1f} s  Maximum resident {ru.ru_maxrss / 1024:.0f} MiB")
+PY
+tail -30 gpurun_out/config2_run.txt
 head -3 $D/out/quant.sf; wc -l $D/out/quant.sf; cat $D/out/aux_info/meta_info.json | head -40 > gpurun_out/config2_meta_info.json
 rm -rf $D

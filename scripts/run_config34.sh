@@ -45,10 +45,11 @@ _capi.write_eq_classes("$D/eq.txt.gz", [f"t{i}" for i in range(eq.n_txps)], eq.o
 print(f"classes: {eq.n_classes} classes / {eq.n_txps} transcripts written, {time.time()-t0:.0f} s", flush=True)
 PY
 EXE=salmon_b200/sb_salmon
+tm() { local t0=$(date +%s.%N); "$@"; local rc=$?; echo "$(python -c "import time; print(round(time.time() - $t0, 2))") s wall"; return $rc; }
 echo "== configs[3]: $N GPUs, read-sharded"; $EXE quant -i $D/idx -l IU -1 $D/r_1.fq -2 $D/r_2.fq -o $D/c3_multi -p 8 --maxReadLen 160 --gpus $N 2>&1 | grep -v NCCL | tail -2
 echo "== configs[3]: 1 GPU";  $EXE quant -i $D/idx -l IU -1 $D/r_1.fq -2 $D/r_2.fq -o $D/c3_one -p 32 --maxReadLen 160 2>&1 | tail -2
-echo "== configs[4]: 100 Gibbs samples, $N GPUs"; /usr/bin/time -f "%e s wall" $EXE quant -e $D/eq.txt.gz -o $D/c4_multi --numGibbsSamples 100 --seed 5 --gpus $N 2>&1 | grep -v NCCL | tail -2
-echo "== configs[4]: 100 Gibbs samples, 1 GPU"; /usr/bin/time -f "%e s wall" $EXE quant -e $D/eq.txt.gz -o $D/c4_one --numGibbsSamples 100 --seed 5 2>&1 | tail -2
+echo "== configs[4]: 100 Gibbs samples, $N GPUs"; tm $EXE quant -e $D/eq.txt.gz -o $D/c4_multi --numGibbsSamples 100 --seed 5 --gpus $N 2>&1 | grep -v NCCL | tail -2
+echo "== configs[4]: 100 Gibbs samples, 1 GPU"; tm $EXE quant -e $D/eq.txt.gz -o $D/c4_one --numGibbsSamples 100 --seed 5 2>&1 | tail -2
 python - <<PY
 import gzip, json, numpy as np
 D = "$D"
