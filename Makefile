@@ -24,7 +24,7 @@ $(LIB): $(OBJS)
 
 # command-line front end (host C++ over the C ABI; finds the library next to itself)
 $(CLI): $(CSRC)/cli_main.cpp $(LIB) include/salmon_b200.h
-	g++ -O2 -std=c++17 -Wall -o $@.tmp $(CSRC)/cli_main.cpp -Lsalmon_b200 -lsalmon_b200 -Wl,-rpath,'$$ORIGIN' && mv -f $@.tmp $@
+	g++ -O2 -std=c++17 -Wall -o $@.tmp $(CSRC)/cli_main.cpp -Lsalmon_b200 -lsalmon_b200 -lpthread -Wl,-rpath,'$$ORIGIN' && mv -f $@.tmp $@
 
 oracle:
 	$(MAKE) -C oracle

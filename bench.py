@@ -290,6 +290,50 @@ def write_fastq_pair(dirname, left, right):
     return paths
 
 
+def stage_a_from_gz(idx, f1, f2, n, L, batch, threads, bufs, max_pairs=1_000_000):
+    """the first max_pairs records of the two FASTQ files through `gzip -1`, then parser-only and sb_quant_files; idx None
+    (CPU-only check of this function): the parser rate alone"""
+    import subprocess
+    from salmon_b200 import _capi
+    k = min(n, max_pairs)
+    rec = 2 * L + 7
+    gz = [p + ".gz" for p in (f1, f2)]
+    procs = []
+    for src, dst in zip((f1, f2), gz):
+        fo = open(dst, "wb")
+        ph = subprocess.Popen(["head", "-c", str(k * rec), src], stdout=subprocess.PIPE)
+        pg = subprocess.Popen(["gzip", "-1"], stdin=ph.stdout, stdout=fo)
+        ph.stdout.close()
+        procs.append((ph, pg, fo))
+    for ph, pg, fo in procs:
+        pg.wait(); ph.wait(); fo.close()
+        if pg.returncode != 0:
+            raise RuntimeError("gzip failed")
+    out = {"files": "the first %d pairs, gzip -1" % k, "pairs": int(k), "parser_threads": threads,
+           "gz_bytes": int(sum(os.path.getsize(g) for g in gz))}
+    best = 0.0
+    for _ in range(2):
+        rf = _capi.ReadFiles(gz[0], gz[1], n_threads=threads)
+        t0 = time.perf_counter(); tot = 0
+        while True:
+            got = rf.next_batch(batch, L, out=bufs)[0]
+            if got == 0:
+                break
+            tot += got
+        dt = time.perf_counter() - t0
+        rf.close()
+        if tot != k:
+            raise RuntimeError(f"the parser delivered {tot} of {k} pairs")
+        best = max(best, tot / dt / 1e6)
+    out["parser_only_mreads_s"] = best
+    if idx is not None:
+        alpha, sm = _capi.quant_files_native(idx, gz[0], gz[1], batch=batch, max_read_len=L, threads=threads)
+        alpha, sm = _capi.quant_files_native(idx, gz[0], gz[1], batch=batch, max_read_len=L, threads=threads)
+        out.update({"files_to_classes_mreads_s": sm["n_observed"] / sm["map_seconds"] / 1e6, "map_seconds": sm["map_seconds"],
+                    "map_device_ms": sm["map_device_ms"], "n_mapped": int(sm["n_mapped"])})
+    return out
+
+
 def stage_a_from_files(idx, left, right, batch, ncores):
     """row f1 measured: FASTQ files -> parser threads -> length buckets (pinned) -> sb_map_batch -> classes -> EM, through
     sb_quant_files (the C++ driver `sb_salmon quant` calls); and the parser alone (sb_reads_next into host buffers)."""
@@ -327,6 +371,10 @@ def stage_a_from_files(idx, left, right, batch, ncores):
         out.update({"files_to_classes_mreads_s": sm["n_observed"] / sm["map_seconds"] / 1e6, "map_seconds": sm["map_seconds"],
                     "map_device_ms": sm["map_device_ms"], "em_seconds": sm["em_seconds"], "em_iters": sm["em_iters"],
                     "n_mapped": int(sm["n_mapped"]), "api": "sb_quant_files (C ABI): reader thread + GPU thread, then sb_em_optimize"})
+        try:    # the same reads as .fastq.gz (what real data looks like): parallel inflate (csrc/pgzip.h)
+            out["gz"] = stage_a_from_gz(idx, f1, f2, n, L, batch, threads, bufs)
+        except Exception as e:  # noqa: BLE001
+            out["gz"] = {"error": repr(e)}
         return out
     except Exception as e:  # noqa: BLE001  (an extra measurement must not lose the bench line)
         return {"error": repr(e)}

@@ -245,6 +245,10 @@ int sb_index_get_meta(const sb_index* ix, uint32_t* n_txps, uint32_t* k, uint32_
  * (that source is absent from the reference tree). */
 int sb_index_save(const sb_index* ix, const char* path);
 sb_index* sb_index_load(const char* path);
+
+/* Creates the CUDA context of `device` (this takes seconds on a large GPU).  Optional: a front end calls it from a
+ * thread of its own while it loads the index from disk, so that the two overlap (sb_salmon does). */
+int sb_device_init(int device);
 /* out4 = {distinct k-mers, postings, table capacity, bytes} */
 int sb_index_info(const sb_index* ix, uint64_t* out4);
 /* Raw views of the index arrays (for serialisation): table = {u64 key, u32 first posting, u32 count}

@@ -93,13 +93,24 @@ struct Stream {
 };
 
 constexpr size_t CHUNK = 8u << 20;
-constexpr size_t MAX_QUEUED = 8;
+constexpr size_t MAX_QUEUED = 8;            // blocks of the serial splitter (each owns CHUNK bytes)
+constexpr size_t MAX_QUEUED_BORROWED = 96;  // blocks that point into a mapping / an inflated piece
 
 bool push_block(Stream* s, std::unique_ptr<RecBlock> b) {
   std::unique_lock<std::mutex> lk(s->mu);
   s->cv_put.wait(lk, [&] { return s->q.size() < MAX_QUEUED || s->stop; });
   if (s->stop) return false;
   s->q.push_back(std::move(b));
+  s->cv_get.notify_one();
+  return true;
+}
+// the blocks of one wave at once: one lock, one wake-up (a thread hand-over costs far more than a block's scan)
+bool push_blocks(Stream* s, std::vector<std::unique_ptr<RecBlock>>& bs) {
+  std::unique_lock<std::mutex> lk(s->mu);
+  s->cv_put.wait(lk, [&] { return s->q.size() < MAX_QUEUED_BORROWED || s->stop; });
+  if (s->stop) return false;
+  for (auto& b : bs)
+    if (b && b->n) s->q.push_back(std::move(b));
   s->cv_get.notify_one();
   return true;
 }
@@ -309,11 +320,11 @@ bool split_mapped(Stream* s, const std::string& path, std::string& err) {
       k->n = (uint32_t)(k->seq.size() / 2);
     }
     s->prof.t_scan += wall() - t0;
-    for (int i = 0; i < nr && err.empty(); ++i) {
-      if (!errs[i].empty()) { err = errs[i]; if (err.find(path) == std::string::npos) err += " (" + path + ")"; break; }
-      if (!blks[i]->n) continue;
+    for (int i = 0; i < nr && err.empty(); ++i)
+      if (!errs[i].empty()) { err = errs[i]; if (err.find(path) == std::string::npos) err += " (" + path + ")"; }
+    if (err.empty()) {
       t0 = wall();
-      const bool pushed = push_block(s, std::move(blks[i]));
+      const bool pushed = push_blocks(s, blks);
       s->prof.t_push_wait += wall() - t0;
       if (!pushed) { err = "stopped"; break; }
     }
@@ -327,7 +338,7 @@ bool split_mapped(Stream* s, const std::string& path, std::string& err) {
 // consumed (the rest is the beginning of a record that continues in the next piece).
 size_t scan_wave(Stream* s, const std::shared_ptr<void>& keep, const char* buf, size_t len, bool eof, bool fasta,
                  const std::string& path, std::string& err) {
-  const int W = std::max(1, std::min(s->scanners, (int)(len >> 20) + 1));
+  const int W = std::max(1, std::min(s->scanners, (int)(len >> 21) + 1));
   std::vector<size_t> b(1, 0);
   for (int i = 1; i < W; ++i) {
     const size_t q = next_record_start(buf, len / W * i, len, fasta);
@@ -356,14 +367,12 @@ size_t scan_wave(Stream* s, const std::shared_ptr<void>& keep, const char* buf, 
     }
     k->n = (uint32_t)(k->seq.size() / 2);
   }
-  for (int i = 0; i < nr; ++i) {
+  for (int i = 0; i < nr; ++i)
     if (!errs[i].empty()) { err = errs[i]; if (err.find(path) == std::string::npos) err += " (" + path + ")"; return 0; }
-    if (!blks[i]->n) continue;
-    const double t0 = wall();
-    const bool pushed = push_block(s, std::move(blks[i]));
-    s->prof.t_push_wait += wall() - t0;
-    if (!pushed) { err = "stopped"; return 0; }
-  }
+  const double t0 = wall();
+  const bool pushed = push_blocks(s, blks);
+  s->prof.t_push_wait += wall() - t0;
+  if (!pushed) { err = "stopped"; return 0; }
   return b[nr - 1] + cuts[nr - 1];
 }
 
@@ -700,11 +709,13 @@ extern "C" int64_t sb_reads_peek(sb_reads* r, uint32_t max_pairs, uint32_t* unif
   if (!r) { sb::set_error("null argument"); return SB_ERR_INVALID; }
   if (r->failed) { sb::set_error("sb_reads_peek: the reader is in a failed state"); return SB_ERR_INVALID; }
   uint64_t n = max_pairs;
+  const double tw0 = wall();
   for (int m = 0; m < r->n_streams; ++m) {
     std::string err;
     if (!hold(r->st[m], max_pairs, err)) { r->failed = true; sb::set_error("%s", err.c_str()); return SB_ERR_INVALID; }
     n = std::min<uint64_t>(n, r->st[m].held_recs);
   }
+  r->t_wait_blocks += wall() - tw0;
   if (uniform_len) {
     uint32_t L = 0;
     bool uni = n > 0;

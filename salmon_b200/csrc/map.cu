@@ -10,6 +10,7 @@
 #include <time.h>
 
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <parallel/algorithm>
@@ -23,16 +24,32 @@
 
 using namespace sbmap;
 
+// std::vector without the zero fill of resize(): the big index arrays are overwritten right away (by parallel preads on
+// load), and first-touch by one thread costs seconds at human scale
+template <class T>
+struct NoInit {
+  using value_type = T;
+  NoInit() = default;
+  template <class U> NoInit(const NoInit<U>&) {}
+  T* allocate(size_t n) { T* p = (T*)malloc(n * sizeof(T)); if (!p) throw std::bad_alloc(); return p; }
+  void deallocate(T* p, size_t) { free(p); }
+  template <class U> void construct(U* p) { ::new ((void*)p) U; }                                   // default-init: no store
+  template <class U, class A0, class... A> void construct(U* p, A0&& a0, A&&... a) { ::new ((void*)p) U(std::forward<A0>(a0), std::forward<A>(a)...); }
+  template <class U> bool operator==(const NoInit<U>&) const { return true; }
+  template <class U> bool operator!=(const NoInit<U>&) const { return false; }
+};
+template <class T> using BigVec = std::vector<T, NoInit<T>>;
+
 // ---------------------------------------------------------------------------------------------
 // index (host build)
 // ---------------------------------------------------------------------------------------------
 struct sb_index {
   uint32_t n_txps = 0, k = 0;
   std::vector<uint64_t> tx_off;
-  std::vector<uint8_t> codes;
-  std::vector<TableEntry> table;
-  std::vector<Posting> post;
-  std::vector<uint64_t> packed;     // 2-bit packed codes with PACK_GUARD_BASES of guard on both sides
+  BigVec<uint8_t> codes;
+  BigVec<TableEntry> table;
+  BigVec<Posting> post;
+  BigVec<uint64_t> packed;     // 2-bit packed codes with PACK_GUARD_BASES of guard on both sides
   std::vector<uint8_t> tx_has_n;
   uint64_t n_kmers = 0;
   // what `salmon quant` needs besides the sequence: names, lengths before clipping, first decoy (optional)
@@ -251,10 +268,36 @@ extern "C" sb_index* sb_index_load(const char* path) {
     ix->tx_off.resize((size_t)h.n_txps + 1); ix->codes.resize(h.n_codes); ix->table.resize(h.n_table);
     ix->post.resize(h.n_post); ix->packed.resize(h.n_packed); ix->tx_has_n.resize(std::max<uint32_t>(h.n_txps, 1));
     std::string names(h.names_bytes, '\0');
-    ok = rd(f, ix->tx_off.data(), ix->tx_off.size()) && rd(f, ix->codes.data(), ix->codes.size()) &&
-         rd(f, ix->table.data(), ix->table.size()) && rd(f, ix->post.data(), ix->post.size()) &&
-         rd(f, ix->packed.data(), ix->packed.size()) && rd(f, ix->tx_has_n.data(), ix->tx_has_n.size()) &&
-         rd(f, &names[0], names.size());
+    // the big arrays: read by a team of threads (pread on disjoint slices; each thread first-touches what it reads)
+    ok = rd(f, ix->tx_off.data(), ix->tx_off.size());
+    if (ok) {
+      const int fd = fileno(f);
+      off_t pos = ftello(f);
+      struct Part { void* dst; size_t bytes; off_t off; };
+      Part parts[4] = {{ix->codes.data(), ix->codes.size(), 0}, {ix->table.data(), ix->table.size() * sizeof(TableEntry), 0},
+                       {ix->post.data(), ix->post.size() * sizeof(Posting), 0}, {ix->packed.data(), ix->packed.size() * 8, 0}};
+      struct Slice { char* dst; size_t bytes; off_t off; };
+      std::vector<Slice> slices;
+      constexpr size_t SL = (size_t)16 << 20;
+      for (Part& pt : parts) {
+        pt.off = pos;
+        for (size_t o = 0; o < pt.bytes; o += SL) slices.push_back(Slice{(char*)pt.dst + o, std::min(SL, pt.bytes - o), pos + (off_t)o});
+        pos += (off_t)pt.bytes;
+      }
+      int bad = 0;
+      const int nt = (int)std::max<size_t>(1, std::min<size_t>(16, slices.size()));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt) reduction(| : bad)
+      for (long i = 0; i < (long)slices.size(); ++i) {
+        size_t done = 0;
+        while (done < slices[i].bytes) {
+          const ssize_t got = pread(fd, slices[i].dst + done, slices[i].bytes - done, slices[i].off + (off_t)done);
+          if (got <= 0) { bad = 1; break; }
+          done += (size_t)got;
+        }
+      }
+      ok = !bad && fseeko(f, pos, SEEK_SET) == 0;
+    }
+    ok = ok && rd(f, ix->tx_has_n.data(), ix->tx_has_n.size()) && rd(f, &names[0], names.size());
     if (ok && has_len) { ix->complete_len.resize(h.n_txps); ok = rd(f, ix->complete_len.data(), ix->complete_len.size()); }
     if (ok) {
       size_t b = 0;
@@ -269,19 +312,74 @@ extern "C" sb_index* sb_index_load(const char* path) {
       ok = ok && ix->tx_off[h.n_txps] == h.n_codes && ix->tx_off[0] == 0;
       for (uint32_t t = 0; t < h.n_txps && ok; ++t) ok = ix->tx_off[t] <= ix->tx_off[t + 1];   // monotonic offsets
       // every table entry points inside the posting array, every posting inside its transcript (these go to the GPU)
-      for (size_t i = 0; i < ix->table.size() && ok; ++i) {
-        const TableEntry& e = ix->table[i];
-        if (e.key != EMPTY_KEY) ok = (uint64_t)e.off + e.cnt <= ix->post.size();
-      }
-      for (size_t i = 0; i < ix->post.size() && ok; ++i) {
-        const Posting& q = ix->post[i];
-        ok = q.tid < h.n_txps && (uint64_t)(q.tpos_rc & 0x7fffffffu) + h.k <= ix->tx_off[q.tid + 1] - ix->tx_off[q.tid];
+      if (ok) {
+        int bad = 0;
+        const TableEntry* tb = ix->table.data();
+        const Posting* po = ix->post.data();
+        const uint64_t* txo = ix->tx_off.data();
+        const size_t nt_ = ix->table.size(), np_ = ix->post.size();
+#pragma omp parallel for schedule(static) num_threads(16) reduction(| : bad)
+        for (long i = 0; i < (long)nt_; ++i)
+          if (tb[i].key != EMPTY_KEY && (uint64_t)tb[i].off + tb[i].cnt > np_) bad = 1;
+#pragma omp parallel for schedule(static) num_threads(16) reduction(| : bad)
+        for (long i = 0; i < (long)np_; ++i) {
+          const Posting& q = po[i];
+          if (q.tid >= h.n_txps || (uint64_t)(q.tpos_rc & 0x7fffffffu) + h.k > txo[q.tid + 1] - txo[q.tid]) bad = 1;
+        }
+        ok = !bad;
       }
     }
   } catch (const std::exception&) { ok = false; }   // bad_alloc, length_error from a corrupt count
   fclose(f);
   if (!ok) { delete ix; sb::set_error("%s: truncated or corrupt index", path); return nullptr; }
   return ix;
+}
+
+// host (pageable) -> device for the index arrays: slices are copied into two page-locked staging buffers by a team of
+// threads while the previous slice is on the wire
+static int upload_big(void* dst, const void* src, size_t bytes) {
+  constexpr size_t SL = (size_t)64 << 20;
+  if (bytes < 2 * SL) { SB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return SB_OK; }
+  char* stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaStream_t st = nullptr;
+  int rc = SB_OK;
+  if (cudaMallocHost(&stage[0], SL) != cudaSuccess || cudaMallocHost(&stage[1], SL) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    rc = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? SB_OK : SB_ERR_CUDA;   // plain copy instead
+  } else {
+    int b = 0;
+    for (size_t o = 0; o < bytes && rc == SB_OK; o += SL, b ^= 1) {
+      const size_t n = std::min(SL, bytes - o);
+      if (o >= 2 * SL && cudaEventSynchronize(ev[b]) != cudaSuccess) { rc = SB_ERR_CUDA; break; }
+      const char* sp = (const char*)src + o;
+      char* dp = stage[b];
+#pragma omp parallel for schedule(static) num_threads(8)
+      for (long q = 0; q < (long)((n + (1 << 20) - 1) >> 20); ++q) {
+        const size_t a = (size_t)q << 20;
+        memcpy(dp + a, sp + a, std::min<size_t>((size_t)1 << 20, n - a));
+      }
+      if (cudaMemcpyAsync((char*)dst + o, dp, n, cudaMemcpyHostToDevice, st) != cudaSuccess || cudaEventRecord(ev[b], st) != cudaSuccess) rc = SB_ERR_CUDA;
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = SB_ERR_CUDA;
+  }
+  if (rc != SB_OK) sb::set_error("index upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (stage[0]) cudaFreeHost(stage[0]);
+  if (stage[1]) cudaFreeHost(stage[1]);
+  if (ev[0]) cudaEventDestroy(ev[0]);
+  if (ev[1]) cudaEventDestroy(ev[1]);
+  if (st) cudaStreamDestroy(st);
+  return rc;
+}
+
+// Creates the CUDA context of `device` (seconds on a large GPU): a front end calls this from a thread of its own while
+// it loads the index from disk, so that the two overlap.
+extern "C" int sb_device_init(int device) {
+  SB_CUDA(cudaSetDevice(device));
+  SB_CUDA(cudaFree(nullptr));
+  return SB_OK;
 }
 
 static int index_to_device(sb_index* ix, int device) {
@@ -293,12 +391,12 @@ static int index_to_device(sb_index* ix, int device) {
   SB_CUDA(cudaMalloc(&ix->d_table, ix->table.size() * sizeof(TableEntry)));
   SB_CUDA(cudaMalloc(&ix->d_post, std::max<size_t>(ix->post.size(), 1) * sizeof(Posting)));
   SB_CUDA(cudaMemcpy(ix->d_tx_off, ix->tx_off.data(), ix->tx_off.size() * 8, cudaMemcpyHostToDevice));
-  SB_CUDA(cudaMemcpy(ix->d_codes, ix->codes.data(), ix->codes.size(), cudaMemcpyHostToDevice));
-  SB_CUDA(cudaMemcpy(ix->d_table, ix->table.data(), ix->table.size() * sizeof(TableEntry), cudaMemcpyHostToDevice));
-  SB_CUDA(cudaMemcpy(ix->d_post, ix->post.data(), ix->post.size() * sizeof(Posting), cudaMemcpyHostToDevice));
+  SB_TRY(upload_big(ix->d_codes, ix->codes.data(), ix->codes.size()));
+  SB_TRY(upload_big(ix->d_table, ix->table.data(), ix->table.size() * sizeof(TableEntry)));
+  SB_TRY(upload_big(ix->d_post, ix->post.data(), ix->post.size() * sizeof(Posting)));
   SB_CUDA(cudaMalloc(&ix->d_packed, ix->packed.size() * 8));
   SB_CUDA(cudaMalloc(&ix->d_tx_has_n, ix->tx_has_n.size()));
-  SB_CUDA(cudaMemcpy(ix->d_packed, ix->packed.data(), ix->packed.size() * 8, cudaMemcpyHostToDevice));
+  SB_TRY(upload_big(ix->d_packed, ix->packed.data(), ix->packed.size() * 8));
   SB_CUDA(cudaMemcpy(ix->d_tx_has_n, ix->tx_has_n.data(), ix->tx_has_n.size(), cudaMemcpyHostToDevice));
   ix->device = device;
   return SB_OK;

@@ -310,7 +310,35 @@ struct MemberEnd {     // a gzip member ended inside this chunk
   uint64_t len8;
   uint32_t crc_stored, isize_stored;
 };
+// Recycled buffers: a chunk's text buffers are tens of MB; malloc would mmap / munmap (and page-fault) each of them,
+// which serialises the inflate threads in the kernel.
+struct BufPool {
+  std::mutex mu;
+  std::vector<std::pair<void*, size_t>> v;
+  size_t max_keep = 8;
+  void* get(size_t bytes, size_t* cap) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (size_t i = v.size(); i-- > 0;)
+        if (v[i].second >= bytes) { void* p = v[i].first; *cap = v[i].second; v.erase(v.begin() + (long)i); return p; }
+      if (v.size() >= max_keep) { free(v.front().first); v.erase(v.begin()); }   // too small for the asker: make room
+    }
+    *cap = bytes;
+    return malloc(bytes);
+  }
+  void put(void* p, size_t cap) {
+    if (!p) return;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (v.size() < max_keep) { v.emplace_back(p, cap); return; }
+    }
+    free(p);
+  }
+  ~BufPool() { for (auto& e : v) free(e.first); }
+};
+
 struct ChunkOut {
+  std::shared_ptr<BufPool> pool;
   uint16_t* s16 = nullptr;      // malloc'ed leading part with markers (m16 symbols; none when the window was known)
   size_t m16 = 0, cap16 = 0;
   uint8_t* buf8 = nullptr;      // malloc'ed: HEAD bytes of head room, then n8 bytes of text
@@ -325,9 +353,13 @@ struct ChunkOut {
   // marker replacement (a second task, once the window before the chunk is known)
   std::unique_ptr<uint8_t[]> win_in;   // the window before the chunk
   size_t win_in_n = 0;
-  uint8_t* text16 = nullptr;           // malloc'ed: HEAD + m16 bytes, the marker part as text
+  uint8_t* text16 = nullptr;           // HEAD + m16 bytes, the marker part as text
+  size_t cap_text16 = 0;
   uint32_t crc16 = 0;
-  ~ChunkOut() { free(s16); free(buf8); free(text16); }
+  ~ChunkOut() {
+    if (pool) { pool->put(s16, cap16 * 2); pool->put(buf8, HEAD + cap8); pool->put(text16, cap_text16); }
+    else { free(s16); free(buf8); free(text16); }
+  }
 };
 
 struct Piece {                   // what the consumer gets: `len` bytes at `data`, HEAD writable bytes in front of it
@@ -356,13 +388,19 @@ struct Decoder {
   size_t valid_back = 0;       // how far before byte 0 a reference may reach (wrapping arithmetic, see the member start)
   size_t seg_start = 0;        // byte-mode text of the current member starts here
   std::string err;
-  ~Decoder() { free(s16); free(out); }
+  BufPool* pool = nullptr;
+  ~Decoder() {
+    if (pool) { pool->put(s16, cap16 * 2); pool->put(out, HEAD + cap); }
+    else { free(s16); free(out); }
+  }
 
   bool grow8(size_t need) {
     if (n + need <= cap) return true;
     size_t nc = cap ? cap * 2 : (size_t)1 << 22;
     while (nc < n + need) nc *= 2;
-    uint8_t* q = (uint8_t*)realloc(out, HEAD + nc);
+    uint8_t* q;
+    if (!out && pool) { size_t got = 0; q = (uint8_t*)pool->get(HEAD + nc, &got); if (q) nc = got - HEAD; }
+    else q = (uint8_t*)realloc(out, HEAD + nc);
     if (!q) { err = "out of memory"; return false; }
     out = q; cap = nc;
     return true;
@@ -371,7 +409,9 @@ struct Decoder {
     if (m + need <= cap16) return true;
     size_t nc = cap16 ? cap16 * 2 : (size_t)1 << 21;
     while (nc < m + need) nc *= 2;
-    uint16_t* q = (uint16_t*)realloc(s16, nc * 2);
+    uint16_t* q;
+    if (!s16 && pool) { size_t got = 0; q = (uint16_t*)pool->get(nc * 2, &got); if (q) nc = got / 2; }
+    else q = (uint16_t*)realloc(s16, nc * 2);
     if (!q) { err = "out of memory"; return false; }
     s16 = q; cap16 = nc;
     return true;
@@ -496,7 +536,9 @@ class ParallelGz {
  public:
   // data/len: the whole compressed file (memory mapped by the caller, must outlive this object)
   ParallelGz(const uint8_t* data, size_t len, int threads, size_t chunk_bytes = (size_t)2 << 20)
-      : d_(data), len_(len), T_(threads < 1 ? 1 : threads), C_(chunk_bytes < 1024 ? 1024 : chunk_bytes) {}
+      : d_(data), len_(len), T_(threads < 1 ? 1 : threads), C_(chunk_bytes < 1024 ? 1024 : chunk_bytes), pool_(new BufPool()) {
+    pool_->max_keep = (size_t)T_ * 4 + 8;
+  }
   ~ParallelGz() { stop(); }
 
   // false: not a gzip file (err says why)
@@ -625,6 +667,7 @@ class ParallelGz {
   size_t len_;
   int T_;
   size_t C_;
+  std::shared_ptr<BufPool> pool_;
   bool bgzf_ = false;
   uint64_t first_bit_ = 0;
   size_t nchunks_ = 0;
@@ -726,39 +769,31 @@ class ParallelGz {
   // in file order: member checks, then the chunk's text becomes pieces
   bool deliver_chunk(ChunkOut& co, std::string& err) {
     if (bgzf_) {
-      if (co.n8) {
-        Piece p;
-        uint8_t* b = co.buf8;
-        co.buf8 = nullptr;
-        p.keep = std::shared_ptr<void>(b, free);
-        p.data = b + HEAD; p.len = co.n8;
-        pending_.push_back(std::move(p));
-      }
+      if (co.n8) pending_.push_back(make_piece(co.buf8, HEAD + co.cap8, co.n8));
       return true;
     }
     if (co.m16) {
       crc_run_ = (uint32_t)crc32_combine(crc_run_, co.crc16, (z_off_t)co.m16);
       len_run_ += co.m16;
-      Piece p;
-      uint8_t* b = co.text16;
-      co.text16 = nullptr;
-      p.keep = std::shared_ptr<void>(b, free);
-      p.data = b + HEAD; p.len = co.m16;
-      pending_.push_back(std::move(p));
+      pending_.push_back(make_piece(co.text16, co.cap_text16, co.m16));
     }
     for (const MemberEnd& me : co.ends)
       if (!member_end(me, err)) return false;
     crc_run_ = (uint32_t)crc32_combine(crc_run_, co.tail_crc8, (z_off_t)co.tail_len8);
     len_run_ += co.tail_len8;
-    if (co.n8) {
-      Piece p;
-      uint8_t* b = co.buf8;
-      co.buf8 = nullptr;
-      p.keep = std::shared_ptr<void>(b, free);
-      p.data = b + HEAD; p.len = co.n8;
-      pending_.push_back(std::move(p));
-    }
+    if (co.n8) pending_.push_back(make_piece(co.buf8, HEAD + co.cap8, co.n8));
     return true;
+  }
+
+  // hands a chunk buffer over to the consumer; it returns to the pool with the last reference
+  Piece make_piece(uint8_t*& buf, size_t cap_bytes, size_t len) {
+    Piece p;
+    uint8_t* b = buf;
+    buf = nullptr;
+    std::shared_ptr<BufPool> pool = pool_;
+    p.keep = std::shared_ptr<void>(b, [pool, cap_bytes](void* q) { pool->put(q, cap_bytes); });
+    p.data = b + HEAD; p.len = len;
+    return p;
   }
 
   // the first block start of chunk j (searched once, by whoever asks first)
@@ -794,11 +829,11 @@ class ParallelGz {
       const uint64_t c0 = cpu_ns();
       if (is_resolve) {
         ChunkOut& co = *out_[i];
-        co.text16 = (uint8_t*)malloc(HEAD + co.m16);
+        co.text16 = (uint8_t*)pool_->get(HEAD + co.m16, &co.cap_text16);
         if (!co.text16) co.err = "out of memory";
         else if (!resolve(co.s16, co.m16, co.win_in.get(), co.win_in_n, co.text16 + HEAD)) co.err = "corrupt gzip data (reference before the start of the member)";
         else co.crc16 = crc_of(co.text16 + HEAD, co.m16);
-        free(co.s16); co.s16 = nullptr;
+        pool_->put(co.s16, co.cap16 * 2); co.s16 = nullptr;
         co.win_in.reset();
         worker_ns_ += cpu_ns() - c0;
         { std::lock_guard<std::mutex> lk(mu_); done_[i].store(2); }
@@ -806,6 +841,7 @@ class ParallelGz {
         continue;
       }
       std::unique_ptr<ChunkOut> co(new ChunkOut());
+      co->pool = pool_;
       if (bgzf_) inflate_bgzf(i, *co);
       else decode_chunk(i, *co, *tab, *scratch);
       worker_ns_ += cpu_ns() - c0;
@@ -826,9 +862,10 @@ class ParallelGz {
     z_stream zs;
     memset(&zs, 0, sizeof zs);
     if (inflateInit2(&zs, -15) != Z_OK) { co.err = "zlib: inflateInit2 failed"; return; }
-    size_t cap = (b - a) * 4 + 65536, n = 0;
-    uint8_t* out = (uint8_t*)malloc(HEAD + cap);
+    size_t cap = (b - a) * 4 + 65536, n = 0, got = 0;
+    uint8_t* out = (uint8_t*)pool_->get(HEAD + cap, &got);
     if (!out) { co.err = "out of memory"; inflateEnd(&zs); return; }
+    cap = got - HEAD;
     size_t off = a;
     while (off < b) {
       uint32_t sz = 0;
@@ -863,6 +900,7 @@ class ParallelGz {
     co.next = i + 1;
     if (s == NONE) return;                 // nothing found here: the predecessor decodes through this range
     Decoder D;
+    D.pool = pool_.get();
     D.br.init(d_, d_ + len_, s);
     D.markers = i != 0;
     if (D.markers) { if (!D.grow16((size_t)C_ * 5)) { co.err = D.err; return; } }

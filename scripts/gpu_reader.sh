@@ -18,8 +18,15 @@ for tag, codes in (("1", left), ("2", right)):
     rec.tofile(f"$D/r_{tag}.fq")
 PY
 nproc; lscpu | grep -E "Model name|Socket|NUMA node\(s\)|Thread"
-export SB_READS_PROFILE=1 SB_MAP_PROFILE=1
-Q="salmon_b200/sb_salmon quant -i $D/idx -l IU -1 $D/r_1.fq -2 $D/r_2.fq -o $D/out --maxReadLen 128"
-echo "== p32"; $Q -p 32 2>&1 | grep -E "sb_reads|sb_quant|mapping|sb_map_batch" | head -40
-echo "== p32 again"; $Q -p 32 2>&1 | grep -E "sb_reads|sb_quant|mapping|sb_map_batch" | tail -22
-rm -rf $D
+export SB_READS_PROFILE=1
+gzip -1 -c $D/r_1.fq > $D/g_1.fq.gz & gzip -1 -c $D/r_2.fq > $D/g_2.fq.gz; wait
+Q="salmon_b200/sb_salmon quant -i $D/idx -l IU -o $D/out --maxReadLen 128"
+G="sb_reads|sb_quant|mapping|index loaded|done "
+echo "== plain p32"; $Q -1 $D/r_1.fq -2 $D/r_2.fq -p 32 2>&1 | grep -E "$G"
+echo "== plain p32 again"; $Q -1 $D/r_1.fq -2 $D/r_2.fq -p 32 2>&1 | grep -E "$G"
+echo "== gz p32"; $Q -1 $D/g_1.fq.gz -2 $D/g_2.fq.gz -p 32 2>&1 | grep -E "$G"
+echo "== gz p64"; $Q -1 $D/g_1.fq.gz -2 $D/g_2.fq.gz -p 64 2>&1 | grep -E "$G"
+echo "== gz p32 one inflate thread per file"; SB_READS_INFLATERS=1 $Q -1 $D/g_1.fq.gz -2 $D/g_2.fq.gz -p 32 2>&1 | grep -E "$G"
+echo "== reader only, gz, p32"; python scripts/bench_reader.py 4000000 100 32 gz 2>&1 | tail -4
+echo "== reader only, gz, p64"; python scripts/bench_reader.py 4000000 100 64 gz 2>&1 | tail -4
+rm -rf $D /dev/shm/rb

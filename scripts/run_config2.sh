@@ -42,4 +42,16 @@ print(f"exit {r.returncode}  Elapsed wall {time.time() - t0:.2f} s  user {ru.ru_
 PY
 tail -30 gpurun_out/config2_run.txt
 head -3 $D/out/quant.sf; wc -l $D/out/quant.sf; cat $D/out/aux_info/meta_info.json | head -40 > gpurun_out/config2_meta_info.json
+if [ -n "$GZ" ]; then
+  # the same reads as .fastq.gz (the first $GZ pairs): parallel inflate (pgzip.h) against one zlib thread per file
+  head -n $((GZ * 4)) $D/r_1.fq | gzip -1 > $D/g_1.fq.gz &
+  head -n $((GZ * 4)) $D/r_2.fq | gzip -1 > $D/g_2.fq.gz
+  wait
+  ls -la $D/*.gz
+  for INF in "" 1; do
+    echo "== .fastq.gz, SB_READS_INFLATERS=${INF:-default}"
+    SB_READS_PROFILE=1 env ${INF:+SB_READS_INFLATERS=$INF} salmon_b200/sb_salmon quant -i $D/idx -l IU -1 $D/g_1.fq.gz -2 $D/g_2.fq.gz -o $D/outg$INF -p 32 --maxReadLen 128 2>&1 | grep -E "sb_reads|sb_quant|mapping|index loaded|observed" | tee -a gpurun_out/config2_gz.txt
+  done
+  cmp $D/outg/quant.sf $D/outg1/quant.sf && echo "quant.sf identical for both inflate paths" | tee -a gpurun_out/config2_gz.txt
+fi
 rm -rf $D

@@ -20,7 +20,7 @@ n_real = len(txps)
 rng = np.random.default_rng(99)
 decoys = []
 for c in range(24):
-    chrom = rng.integers(0, 4, size=4_000_000, dtype=np.uint8)
+    chrom = rng.integers(0, 4, size=${DECOY_LEN:-2000000}, dtype=np.uint8)
     for _ in range(400):
         t = txps[int(rng.integers(n_real))]
         a = int(rng.integers(0, max(1, len(t) - 300))); piece = t[a:a + 300]
@@ -46,10 +46,10 @@ print(f"classes: {eq.n_classes} classes / {eq.n_txps} transcripts written, {time
 PY
 EXE=salmon_b200/sb_salmon
 tm() { local t0=$(date +%s.%N); "$@"; local rc=$?; echo "$(python -c "import time; print(round(time.time() - $t0, 2))") s wall"; return $rc; }
-echo "== configs[3]: $N GPUs, read-sharded"; $EXE quant -i $D/idx -l IU -1 $D/r_1.fq -2 $D/r_2.fq -o $D/c3_multi -p 8 --maxReadLen 160 --gpus $N 2>&1 | grep -v NCCL | tail -2
-echo "== configs[3]: 1 GPU";  $EXE quant -i $D/idx -l IU -1 $D/r_1.fq -2 $D/r_2.fq -o $D/c3_one -p 32 --maxReadLen 160 2>&1 | tail -2
-echo "== configs[4]: 100 Gibbs samples, $N GPUs"; tm $EXE quant -e $D/eq.txt.gz -o $D/c4_multi --numGibbsSamples 100 --seed 5 --gpus $N 2>&1 | grep -v NCCL | tail -2
-echo "== configs[4]: 100 Gibbs samples, 1 GPU"; tm $EXE quant -e $D/eq.txt.gz -o $D/c4_one --numGibbsSamples 100 --seed 5 2>&1 | tail -2
+echo "== configs[3]: $N GPUs, read-sharded"; timeout 90 $EXE quant -i $D/idx -l IU -1 $D/r_1.fq -2 $D/r_2.fq -o $D/c3_multi -p 8 --maxReadLen 160 --gpus $N 2>&1 | grep -v NCCL | tail -4
+echo "== configs[3]: 1 GPU";  timeout 90 $EXE quant -i $D/idx -l IU -1 $D/r_1.fq -2 $D/r_2.fq -o $D/c3_one -p 32 --maxReadLen 160 2>&1 | tail -4
+echo "== configs[4]: 100 Gibbs samples, $N GPUs"; tm timeout 90 $EXE quant -e $D/eq.txt.gz -o $D/c4_multi --numGibbsSamples 100 --seed 5 --gpus $N 2>&1 | grep -v NCCL | tail -4
+echo "== configs[4]: 100 Gibbs samples, 1 GPU"; tm timeout 90 $EXE quant -e $D/eq.txt.gz -o $D/c4_one --numGibbsSamples 100 --seed 5 2>&1 | tail -4
 python - <<PY
 import gzip, json, numpy as np
 D = "$D"
