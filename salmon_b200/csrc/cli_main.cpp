@@ -3,6 +3,7 @@
 // src/index/BuildSalmonIndex.cpp:72-124).  No logic of its own: argument parsing, then sb_txome_read_fasta +
 // sb_index_build + sb_index_save, or sb_index_load + sb_quant_files, or sb_eq_file_read + sb_em_optimize.
 // Options outside the hot path (bias models, alignment mode, SAM output, ...) are rejected with a message.
+#include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -23,6 +24,14 @@ static double now_wall() {
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 static const double T_PROCESS_START = now_wall();
+
+// the per-rank child processes of `quant --gpus N`: a signal that ends the parent ends them too
+static pid_t g_kids[64];
+static volatile sig_atomic_t g_n_kids = 0;
+static void forward_signal(int sig) {
+  for (int i = 0; i < g_n_kids; ++i) if (g_kids[i] > 0) kill(g_kids[i], SIGTERM);
+  _exit(128 + sig);
+}
 
 namespace {
 
@@ -294,9 +303,31 @@ int cmd_quant(Args& a) {
         _exit(127);
       }
       kids.push_back(pid);
+      if (g_n_kids < 64) { g_kids[g_n_kids] = pid; g_n_kids = g_n_kids + 1; }
     }
+    signal(SIGTERM, forward_signal);
+    signal(SIGINT, forward_signal);
+    // a rank that fails leaves the others waiting in a collective: the first failure ends the run for all of them
     int bad = 0;
-    for (pid_t k : kids) { int st = 0; waitpid(k, &st, 0); if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) bad = 1; }
+    size_t left = kids.size();
+    while (left > 0) {
+      int st = 0;
+      const pid_t k = wait(&st);
+      if (k < 0) break;
+      bool ours = false;
+      for (size_t i = 0; i < kids.size(); ++i)
+        if (kids[i] == k) { ours = true; kids[i] = -1; }
+      if (!ours) continue;
+      --left;
+      if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) {
+        if (!bad) {
+          fprintf(stderr, "sb_salmon quant: a rank failed (%s %d); stopping the other ranks\n", WIFEXITED(st) ? "exit code" : "signal",
+                  WIFEXITED(st) ? WEXITSTATUS(st) : WTERMSIG(st));
+          for (pid_t o : kids) if (o > 0) kill(o, SIGTERM);
+        }
+        bad = 1;
+      }
+    }
     unlink((out + "/.sb_nccl_uid_" + tag).c_str());
     return bad;
   }

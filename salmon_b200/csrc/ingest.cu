@@ -763,7 +763,32 @@ extern "C" int64_t sb_reads_skip(sb_reads* r, uint32_t n) {
 // --eqclasses reader
 // ---------------------------------------------------------------------------------------------------------------------
 namespace {
+// a whole text file (plain or gzip) into memory; a regular gzip file of some size is inflated by several threads
 bool slurp(const char* path, std::string& out, std::string& err) {
+  {
+    FILE* f = fopen(path, "rb");
+    struct stat stt;
+    if (f && fstat(fileno(f), &stt) == 0 && S_ISREG(stt.st_mode) && stt.st_size > (8 << 20)) {
+      const size_t flen = (size_t)stt.st_size;
+      void* mp = mmap(nullptr, flen, PROT_READ, MAP_PRIVATE, fileno(f), 0);
+      if (mp != MAP_FAILED) {
+        bool handled = false, ok = true;
+        {
+          sb::pgz::ParallelGz pg((const uint8_t*)mp, flen, 8);
+          std::string perr;
+          if (pg.start(perr)) {     // (not gzip: the plain path below reads it)
+            handled = true;
+            sb::pgz::Piece pc;
+            while (pg.next(pc, perr)) out.append((const char*)pc.data, pc.len);
+            if (!perr.empty()) { err = std::string("read error in ") + path + ": " + perr; ok = false; }
+          }
+        }
+        munmap(mp, flen);
+        if (handled) { fclose(f); return ok; }
+      }
+    }
+    if (f) fclose(f);
+  }
   gzFile g = gzopen(path, "rb");
   if (!g) { err = std::string("cannot open ") + path; return false; }
   gzbuffer(g, 1u << 20);
@@ -910,18 +935,27 @@ extern "C" void sb_eq_file_free(sb_eq_file* f) {
 // ---------------------------------------------------------------------------------------------------------------------
 // bootstraps.gz
 // ---------------------------------------------------------------------------------------------------------------------
+// bootstraps.gz is one gzip member, as the reference writes it (zstr::ofstream at level 6, GZipWriter.cpp:774-783), but
+// deflated by a team of threads the way pigz does it: every 128 KiB slice of a sample is a raw deflate stream of its own that
+// ends on a byte boundary (Z_SYNC_FLUSH), the slices are written back to back, the member's CRC is combined from the
+// slices' CRCs.  (One zlib thread writes ~40 MB/s of doubles: 100 samples at human scale took longer than sampling them.)
 struct sb_bootstrap_writer {
-  gzFile g = nullptr;
+  FILE* f = nullptr;
   std::mutex mu;
   uint64_t n_written = 0;
+  uint32_t crc = 0;
+  uint64_t total = 0;
+  bool failed = false;
 };
 
 extern "C" sb_bootstrap_writer* sb_bootstrap_writer_open(const char* path) {
   if (!path) { sb::set_error("null argument"); return nullptr; }
-  gzFile g = gzopen(path, "wb6");   // zstr::ofstream(..., level 6), GZipWriter.cpp:774-776
-  if (!g) { sb::set_error("cannot open %s", path); return nullptr; }
+  FILE* f = fopen(path, "wb");
+  if (!f) { sb::set_error("cannot open %s", path); return nullptr; }
+  static const unsigned char hdr[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 3};   // deflate, no name / time, OS = Unix
+  if (fwrite(hdr, 1, 10, f) != 10) { fclose(f); sb::set_error("write error (bootstraps)"); return nullptr; }
   sb_bootstrap_writer* w = new sb_bootstrap_writer();
-  w->g = g;
+  w->f = f;
   return w;
 }
 
@@ -930,21 +964,53 @@ extern "C" sb_bootstrap_writer* sb_bootstrap_writer_open(const char* path) {
 extern "C" int sb_bootstrap_writer_write(sb_bootstrap_writer* w, const double* sample, uint32_t n) {
   if (!w || !sample) { sb::set_error("null argument"); return SB_ERR_INVALID; }
   std::lock_guard<std::mutex> lk(w->mu);
+  if (w->failed) { sb::set_error("write error (bootstraps)"); return SB_ERR_INVALID; }
   const size_t bytes = (size_t)n * sizeof(double);
-  size_t done = 0;
-  while (done < bytes) {
-    const unsigned part = (unsigned)std::min<size_t>(bytes - done, 1u << 30);
-    if (gzwrite(w->g, (const char*)sample + done, part) != (int)part) { sb::set_error("write error (bootstraps)"); return SB_ERR_INVALID; }
-    done += part;
+  constexpr size_t SLICE = (size_t)128 << 10;   // (pigz's block size)
+  const long ns = (long)((bytes + SLICE - 1) / SLICE);
+  std::vector<std::vector<unsigned char>> outs((size_t)ns);
+  std::vector<uint32_t> crcs((size_t)ns, 0);
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads((int)std::max<long>(1, std::min<long>(8, ns))) reduction(| : bad)
+  for (long i = 0; i < ns; ++i) {
+    const unsigned char* src = (const unsigned char*)sample + (size_t)i * SLICE;
+    const size_t len = std::min(SLICE, bytes - (size_t)i * SLICE);
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad = 1; continue; }
+    outs[(size_t)i].resize(deflateBound(&zs, (uLong)len) + 64);
+    zs.next_in = const_cast<Bytef*>(src); zs.avail_in = (uInt)len;
+    zs.next_out = outs[(size_t)i].data(); zs.avail_out = (uInt)outs[(size_t)i].size();
+    const int rc = deflate(&zs, Z_SYNC_FLUSH);
+    if (rc != Z_OK || zs.avail_in != 0 || zs.avail_out == 0) bad = 1;
+    outs[(size_t)i].resize(outs[(size_t)i].size() - zs.avail_out);
+    deflateEnd(&zs);
+    crcs[(size_t)i] = (uint32_t)crc32(0, src, (uInt)len);
+  }
+  if (bad) { w->failed = true; sb::set_error("deflate failed (bootstraps)"); return SB_ERR_INVALID; }
+  for (long i = 0; i < ns; ++i) {
+    if (fwrite(outs[(size_t)i].data(), 1, outs[(size_t)i].size(), w->f) != outs[(size_t)i].size()) {
+      w->failed = true; sb::set_error("write error (bootstraps)"); return SB_ERR_INVALID;
+    }
+    const size_t len = std::min(SLICE, bytes - (size_t)i * SLICE);
+    w->crc = (uint32_t)crc32_combine(w->crc, crcs[(size_t)i], (z_off_t)len);
+    w->total += len;
   }
   ++w->n_written;
   return SB_OK;
 }
 
+// returns the number of samples written, or a negative code when the file could not be completed
 extern "C" int64_t sb_bootstrap_writer_close(sb_bootstrap_writer* w) {
   if (!w) return 0;
-  const int64_t n = (int64_t)w->n_written;
-  gzclose(w->g);
+  int64_t n = (int64_t)w->n_written;
+  // the final (empty, fixed-code) block, then CRC-32 and the length modulo 2^32
+  unsigned char tail[10] = {0x03, 0x00, 0, 0, 0, 0, 0, 0, 0, 0};
+  const uint32_t c = w->crc, l = (uint32_t)w->total;
+  for (int i = 0; i < 4; ++i) { tail[2 + i] = (unsigned char)(c >> (8 * i)); tail[6 + i] = (unsigned char)(l >> (8 * i)); }
+  bool ok = !w->failed && fwrite(tail, 1, 10, w->f) == 10;
+  ok = (fclose(w->f) == 0) && ok;
+  if (!ok) { sb::set_error("write error (bootstraps)"); n = SB_ERR_INVALID; }
   delete w;
   return n;
 }
@@ -1033,6 +1099,22 @@ extern "C" int sb_txome_read_fasta(const char* path, uint32_t k, int gencode, co
       }
       if (dup) { ++n_dup; continue; }
       cand.push_back((uint32_t)S->names.size());
+    }
+    // a decoy longer than the index's per-reference limit (2^21 - 1 bases; chromosomes are 100x that) is stored as
+    // overlapping pieces: a decoy only matters as "the best hit of a read is in a decoy" (SalmonMappingUtils.hpp:
+    // 268-283), and with an overlap above the longest read every read that lies in the chromosome lies in one piece
+    constexpr size_t PIECE = 2000000, OVERLAP = 1024;
+    if (is_decoy && seq.size() > PIECE) {
+      size_t part = 0;
+      for (size_t a = 0; a < seq.size(); a += PIECE - OVERLAP, ++part) {
+        const size_t b = std::min(seq.size(), a + PIECE);
+        S->names.push_back(name + ":" + std::to_string(part));
+        S->complete_len.push_back((uint32_t)(b - a));
+        S->codes.insert(S->codes.end(), seq.begin() + (long)a, seq.begin() + (long)b);
+        S->seq_off.push_back(S->codes.size());
+        if (b == seq.size()) break;
+      }
+      continue;
     }
     S->names.push_back(std::move(name));
     S->complete_len.push_back(complete);

@@ -209,6 +209,22 @@ def test_bootstrap_writer_format(tmp_path):
     raw = gzip.open(path, "rb").read()
     got = np.frombuffer(raw, dtype=np.float64).reshape(7, 123)   # tximport / fishpond read it exactly like this
     assert np.array_equal(got, np.stack(samples))
+    # samples of several deflate slices (the writer compresses 128 KiB slices in parallel), sparse like real counts;
+    # one gzip member with a valid CRC / length (gzip.open checks both), also for an empty file
+    import subprocess
+    path2 = str(tmp_path / "big.gz")
+    w = _capi.BootstrapWriter(path2)
+    big = [np.where(rng.random(300_001) < 0.3, rng.random(300_001) * 1000, 0.0) for _ in range(3)]
+    for smp in big:
+        w.write(smp)
+    assert w.close() == 3
+    raw = gzip.open(path2, "rb").read()
+    assert np.array_equal(np.frombuffer(raw, dtype=np.float64).reshape(3, 300_001), np.stack(big))
+    assert subprocess.run(["gzip", "-t", path2]).returncode == 0
+    assert raw[:0] == b"" and open(path2, "rb").read(3) == b"\x1f\x8b\x08"
+    path3 = str(tmp_path / "none.gz")
+    w = _capi.BootstrapWriter(path3)
+    assert w.close() == 0 and gzip.open(path3, "rb").read() == b"" and subprocess.run(["gzip", "-t", path3]).returncode == 0
 
 
 def test_txome_fasta_options(tmp_path):
@@ -243,6 +259,36 @@ def test_txome_fasta_options(tmp_path):
     dec.write_text("ENST1|ENSG1|x\n")
     with pytest.raises(_capi.SalmonB200Error, match="decoys must come last"):
         _capi.read_txome_fasta(str(fa), k=31, decoys=str(dec))
+
+
+def test_long_decoys_are_split_into_overlapping_pieces(tmp_path):
+    """chromosome-sized decoys exceed the index's per-reference limit (2^21 - 1 bases): they are stored as pieces of 2 Mb
+    that overlap by 1024 bases, so every window of up to 1025 bases of the chromosome lies inside one piece"""
+    rng = np.random.default_rng(13)
+    tx = rand_seq(rng, 400)
+    chrom = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 4_500_000)].tobytes().decode()
+    small = rand_seq(rng, 1000)
+    fa = tmp_path / "g.fa"
+    with open(fa, "w") as f:
+        f.write(f">tx0\n{tx}\n>chrBig\n")
+        for i in range(0, len(chrom), 80):
+            f.write(chrom[i:i + 80] + "\n")
+        f.write(f">chrSmall\n{small}\n")
+    dec = tmp_path / "d.txt"
+    dec.write_text("chrBig\nchrSmall\n")
+    t = _capi.read_txome_fasta(str(fa), k=31, decoys=str(dec))
+    assert t["names"] == ["tx0", "chrBig:0", "chrBig:1", "chrBig:2", "chrSmall"] and t["first_decoy"] == 1
+    lens = [len(x) for x in t["seqs"]]
+    assert max(lens) < (1 << 21)
+    full = encode(chrom)
+    starts = [0, 2_000_000 - 1024, 2 * (2_000_000 - 1024)]
+    for piece, a in zip(t["seqs"][1:4], starts):
+        assert np.array_equal(piece, full[a:a + len(piece)])
+    assert starts[2] + lens[3] == len(chrom) and lens[1] == lens[2] == 2_000_000
+    assert list(t["complete_len"][1:4]) == lens[1:4]
+    # the pieces build (the limit applies per reference)
+    idx = _capi.Index(t["seqs"], names=t["names"], first_decoy=t["first_decoy"])
+    assert idx.n_txps == 5
 
 
 def test_index_save_load_round_trip(tmp_path):

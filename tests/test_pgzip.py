@@ -220,3 +220,24 @@ def test_reader_gz_errors(tmp_path, monkeypatch):
     with _capi.ReadFiles(str(f), None, n_threads=8) as rf:
         with pytest.raises(_capi.SalmonB200Error, match="exceeds"):
             rf.next_batch(100, 256)
+
+
+def test_eq_file_through_parallel_inflate(tmp_path):
+    """whole-file readers (--eqclasses input, transcript FASTA) inflate regular gzip files above 8 MB with pgzip.h"""
+    from salmon_b200.synth import synth_eq
+    eq, proj, eff, uniq = synth_eq(seed=2, C=300000, M=80000, total_count=3_000_000)
+    p = tmp_path / "eq.txt.gz"
+    names = [f"t{i}" for i in range(eq.n_txps)]
+    _capi.write_eq_classes(str(p), names, eq.off, eq.tids, eq.counts, eq.weights)
+    assert os.path.getsize(p) > (8 << 20)
+    got = _capi.read_eq_classes(str(p))
+    plain = tmp_path / "eq.txt"
+    plain.write_bytes(gzip.open(p, "rb").read())
+    want = _capi.read_eq_classes(str(plain))
+    assert got.keys() == want.keys()
+    for k in got:
+        a, b = got[k], want[k]
+        if isinstance(a, np.ndarray):
+            assert np.array_equal(a, b), k
+        else:
+            assert a == b, k
