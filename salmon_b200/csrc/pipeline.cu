@@ -585,6 +585,9 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
     for (auto& sname : gen) np.push_back(sname.c_str());
     names = np.data();
   }
+  // (a collective: every rank takes part, whether it writes the outputs or not)
+  uint64_t libc[4] = {res.lib_format_counts[0], res.lib_format_counts[1], res.lib_format_counts[2], res.lib_format_counts[3]};
+  if (multi) SB_TRY(sb_comm_allreduce(S.comm, libc, 4, 1, 0));
   if (!outs.empty() && o.shard_index == 0) {
     if (!make_dirs(outs + "/aux_info")) { sb::set_error("cannot create %s/aux_info", outs.c_str()); return SB_ERR_INVALID; }
     std::vector<uint32_t> lens;
@@ -606,8 +609,6 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
     for (uint32_t f = 0; f < n_files; ++f)
       files += std::string(f ? ", " : "") + (mates2 ? std::string("( ") + mates1[f] + ", " + mates2[f] + " )" : std::string(mates1[f]));
     files += " ]";
-    uint64_t libc[4] = {res.lib_format_counts[0], res.lib_format_counts[1], res.lib_format_counts[2], res.lib_format_counts[3]};
-    if (multi) SB_TRY(sb_comm_allreduce(S.comm, libc, 4, 1, 0));
     MetaIn mi{&o, &ep, &mp, Mq, M - Mq, n_observed, n_mapped_u, res.n_classes, &hist, glob.unique_counts, glob.total_counts,
               files, start_time, time_string(), (int)o.shard_count, {libc[0], libc[1], libc[2], libc[3]}};
     SB_TRY(write_run_metadata(outs, mi));

@@ -47,3 +47,20 @@ def test_no_cpu_fallback_without_gpu():
         pytest.skip("a GPU is present")
     with pytest.raises(_capi.SalmonB200Error, match="no CUDA device"):
         _capi.EMContext(0)
+
+
+def test_no_collective_inside_rank_conditional_blocks():
+    """a collective that only one rank reaches hangs the run (that happened: an all-reduce inside the rank-0 output block
+    of sb_quant_files): in the C++ multi-GPU driver no sb_comm_all* call may sit inside an `if (... shard_index == 0 ...)`
+    or `if (r != 0 ...)` block"""
+    import re
+    src = open(os.path.join(ROOT, "salmon_b200", "csrc", "pipeline.cu")).read()
+    bad = []
+    for m in re.finditer(r"if \([^\n]*(shard_index [!=]= 0|\br [!=]= 0|rank [!=]= 0)[^\n]*\) \{", src):
+        depth, i = 1, m.end()
+        while depth and i < len(src):
+            depth += {"{": 1, "}": -1}.get(src[i], 0)
+            i += 1
+        if "sb_comm_all" in src[m.end():i]:
+            bad.append(src[m.start():m.end()])
+    assert not bad, bad
