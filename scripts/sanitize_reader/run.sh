@@ -35,6 +35,7 @@ NV="nvcc -O1 -g -std=c++17 -gencode arch=compute_100a,code=sm_100a"
 $NV -Xcompiler -fsanitize=thread -Xcompiler -Wno-unknown-pragmas -o "$W/tsan" $SRC -lz -ltsan
 $NV -Xcompiler -fsanitize=address -Xcompiler -fsanitize=undefined -Xcompiler -fopenmp -o "$W/asan" $SRC -lgomp -lz -lasan -lubsan
 echo "== tsan"; TSAN_OPTIONS=halt_on_error=1 "$W/tsan" "$W/t_1.fq" "$W/t_2.fq"
+echo "== tsan gzip (parallel inflate)"; TSAN_OPTIONS=halt_on_error=1 SB_READS_INFLATERS=4 "$W/tsan" "$W/t_1.fq.gz" "$W/t_2.fq.gz"
 echo "== asan plain"; ASAN_OPTIONS=detect_leaks=1:protect_shadow_gap=0 "$W/asan" "$W/t_1.fq" "$W/t_2.fq" "$W/eq.txt" "$W/t.fa"
-echo "== asan gzip"; ASAN_OPTIONS=detect_leaks=1:protect_shadow_gap=0 "$W/asan" "$W/t_1.fq.gz" "$W/t_2.fq.gz"
+echo "== asan gzip"; SB_READS_INFLATERS=4 ASAN_OPTIONS=detect_leaks=1:protect_shadow_gap=0 "$W/asan" "$W/t_1.fq.gz" "$W/t_2.fq.gz"
 rm -rf "$W"; echo "sanitizers clean"

@@ -18,3 +18,16 @@ extern "C" int sb_gibbs(sb_em_ctx*, const double*, int, int, double, uint32_t, u
 extern "C" int sb_write_quant_sf(const char*, uint32_t, const char* const*, const uint32_t*, const double*, const double*, double, int) { return -1; }
 extern "C" int sb_write_eq_classes(const char*, uint32_t, const char* const*, uint64_t, const uint64_t*, const uint32_t*, const double*, const uint64_t*) { return -1; }
 extern "C" int sb_index_host_arrays(const sb_index*, const uint64_t**, const uint8_t**, const void**, uint64_t*, const void**, uint64_t*) { return -1; }
+// (round 2 entry points)
+extern "C" int sb_version(void) { return 0; }
+extern "C" int sb_map_partial_get(sb_map_ctx*, sb_map_partial*) { return -1; }
+extern "C" int sb_map_project_global(sb_map_ctx*, const sb_map_partial*, uint32_t, const uint32_t*, sb_map_result*) { return -1; }
+extern "C" int sb_map_online_state(sb_map_ctx*, double*, double*, double*, uint64_t*) { return -1; }
+extern "C" sb_comm* sb_comm_create(int, int, const void*, int) { return nullptr; }
+extern "C" void sb_comm_destroy(sb_comm*) {}
+extern "C" int sb_comm_rank(const sb_comm*) { return 0; }
+extern "C" int sb_comm_size(const sb_comm*) { return 1; }
+extern "C" int sb_comm_allreduce(sb_comm*, void*, size_t, int, int) { return -1; }
+extern "C" int sb_comm_allgather(sb_comm*, const void*, void*, size_t) { return -1; }
+extern "C" int sb_em_peer_setup(sb_em_ctx*, sb_comm*, uint32_t) { return -1; }
+extern "C" int sb_em_set_option(sb_em_ctx*, const char*, int64_t) { return -1; }
