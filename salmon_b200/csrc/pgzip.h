@@ -23,6 +23,9 @@
 #include <string.h>
 #include <time.h>
 #include <zlib.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -368,8 +371,74 @@ struct Piece {                   // what the consumer gets: `len` bytes at `data
   size_t len = 0;
 };
 
+#if defined(__x86_64__)
+// CRC-32 (the gzip polynomial, reflected) by carry-less multiplication: 64 bytes per step are folded into four 128-bit
+// accumulators, then reduced (Gopal et al., "Fast CRC Computation for Generic Polynomials Using PCLMULQDQ Instruction",
+// Intel 2009; the constants are the published ones for this polynomial).  `crc` is the running register value
+// (zlib's crc32 value, inverted); len >= 64 and a multiple of 16.  Checked against zlib's crc32 in tests/test_pgzip.py.
+__attribute__((target("sse4.2,pclmul"))) inline uint32_t crc32_fold(const uint8_t* buf, size_t len, uint32_t crc) {
+  alignas(16) static const uint64_t k1k2[2] = {0x0154442bd4ull, 0x01c6e41596ull};
+  alignas(16) static const uint64_t k3k4[2] = {0x01751997d0ull, 0x00ccaa009eull};
+  alignas(16) static const uint64_t k5k0[2] = {0x0163cd6124ull, 0x0000000000ull};
+  alignas(16) static const uint64_t poly[2] = {0x01db710641ull, 0x01f7011641ull};
+  __m128i x0, x1, x2, x3, x4, x5, x6, x7, x8, y5, y6, y7, y8;
+  x1 = _mm_loadu_si128((const __m128i*)(buf + 0x00));
+  x2 = _mm_loadu_si128((const __m128i*)(buf + 0x10));
+  x3 = _mm_loadu_si128((const __m128i*)(buf + 0x20));
+  x4 = _mm_loadu_si128((const __m128i*)(buf + 0x30));
+  x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)crc));
+  x0 = _mm_load_si128((const __m128i*)k1k2);
+  buf += 64; len -= 64;
+  while (len >= 64) {
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
+    x7 = _mm_clmulepi64_si128(x3, x0, 0x00); x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
+    x3 = _mm_clmulepi64_si128(x3, x0, 0x11); x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
+    y5 = _mm_loadu_si128((const __m128i*)(buf + 0x00)); y6 = _mm_loadu_si128((const __m128i*)(buf + 0x10));
+    y7 = _mm_loadu_si128((const __m128i*)(buf + 0x20)); y8 = _mm_loadu_si128((const __m128i*)(buf + 0x30));
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), y5); x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), y6);
+    x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), y7); x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), y8);
+    buf += 64; len -= 64;
+  }
+  x0 = _mm_load_si128((const __m128i*)k3k4);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
+  while (len >= 16) {
+    x2 = _mm_loadu_si128((const __m128i*)buf);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+    buf += 16; len -= 16;
+  }
+  x2 = _mm_clmulepi64_si128(x1, x0, 0x10);
+  x3 = _mm_setr_epi32(~0, 0, ~0, 0);
+  x1 = _mm_srli_si128(x1, 8);
+  x1 = _mm_xor_si128(x1, x2);
+  x0 = _mm_loadl_epi64((const __m128i*)k5k0);
+  x2 = _mm_srli_si128(x1, 4);
+  x1 = _mm_and_si128(x1, x3);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  x0 = _mm_load_si128((const __m128i*)poly);
+  x2 = _mm_and_si128(x1, x3);
+  x2 = _mm_clmulepi64_si128(x2, x0, 0x10);
+  x2 = _mm_and_si128(x2, x3);
+  x2 = _mm_clmulepi64_si128(x2, x0, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+#endif
+
+// zlib's crc32 value of [p, p + n)
 inline uint32_t crc_of(const uint8_t* p, uint64_t n) {
   uint32_t c = 0;
+#if defined(__x86_64__)
+  static const bool have_clmul = __builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.2");
+  if (have_clmul && n >= 64) {
+    const uint64_t body = n & ~(uint64_t)15;
+    c = ~crc32_fold(p, (size_t)body, ~c);
+    p += body; n -= body;
+  }
+#endif
   while (n) { const uInt k = (uInt)std::min<uint64_t>(n, (uint64_t)1 << 30); c = (uint32_t)crc32(c, p, k); p += k; n -= k; }
   return c;
 }
@@ -429,8 +498,110 @@ struct Decoder {
     return true;
   }
 
+  // one block's symbols; 0 = end of block, -1 = error.  The fast loop keeps the bit buffer in registers and never checks
+  // for the end of the input (it leaves while 16 bytes are still unread); the careful loop below finishes the block.
   template <bool MARK>
-  int codes(const Ent* lt, const Ent* dt) {   // one block's symbols; 0 = end of block, -1 = error
+  int codes(const Ent* lt, const Ent* dt) {
+    uint64_t buf = br.buf;
+    int cnt = br.cnt;
+    const uint8_t* p = br.p;
+    const uint8_t* const in_end = br.end;
+    int status = 2;   // 2 = go on in the careful loop
+#define PGZ_REFILL() do { uint64_t v_; memcpy(&v_, p, 8); buf |= v_ << cnt; p += (63 - cnt) >> 3; cnt |= 56; } while (0)
+#define PGZ_DROP(nb) do { buf >>= (nb); cnt -= (nb); } while (0)
+    while (in_end - p >= 16 && !br.overrun) {
+      if (MARK) { if (m + 264 > cap16) { if (!grow16(264)) { status = -1; break; } } }
+      else { if (n + 264 > cap) { if (!grow8(264)) { status = -1; break; } } }
+      PGZ_REFILL();
+      Ent e = lt[buf & ((1u << LIT_BITS) - 1)];
+      for (int r = 0; r < 3 && (e.opx >> 4) == OP_LIT; ++r) {
+        PGZ_DROP(e.len);
+        if (MARK) s16[m++] = e.val; else out[HEAD + n++] = (uint8_t)e.val;
+        e = lt[buf & ((1u << LIT_BITS) - 1)];
+      }
+      if ((e.opx >> 4) == OP_LIT) continue;
+      if (cnt < 48) PGZ_REFILL();
+      if ((e.opx >> 4) == OP_LINK) {
+        const int sb = e.opx & 15;
+        e = lt[e.val + ((buf >> LIT_BITS) & ((1u << sb) - 1))];
+        PGZ_DROP(LIT_BITS);
+      }
+      const uint32_t op = e.opx >> 4;
+      PGZ_DROP(e.len);
+      if (op == OP_LIT) {
+        if (MARK) s16[m++] = e.val; else out[HEAD + n++] = (uint8_t)e.val;
+        continue;
+      }
+      if (op == OP_EOB) { status = 0; break; }
+      if (op != OP_BASE) { err = "invalid literal/length code"; status = -1; break; }
+      const int lxb = e.opx & 15;
+      uint32_t len = e.val + (uint32_t)(buf & ((1u << lxb) - 1));
+      PGZ_DROP(lxb);
+      if (cnt < 32) PGZ_REFILL();
+      Ent d = dt[buf & ((1u << DIST_BITS) - 1)];
+      if ((d.opx >> 4) == OP_LINK) {
+        const int sb = d.opx & 15;
+        d = dt[d.val + ((buf >> DIST_BITS) & ((1u << sb) - 1))];
+        PGZ_DROP(DIST_BITS);
+      }
+      if ((d.opx >> 4) != OP_BASE) { err = "invalid distance code"; status = -1; break; }
+      PGZ_DROP(d.len);
+      const int dxb = d.opx & 15;
+      const uint32_t dist = d.val + (uint32_t)(buf & ((1u << dxb) - 1));
+      PGZ_DROP(dxb);
+      if (!copy_match<MARK>(len, dist)) { status = -1; break; }
+    }
+#undef PGZ_REFILL
+#undef PGZ_DROP
+    br.buf = buf; br.cnt = cnt; br.p = p;
+    if (status != 2) return status;
+    return codes_careful<MARK>(lt, dt);
+  }
+
+  template <bool MARK>
+  inline bool copy_match(uint32_t len, uint32_t dist) {
+    if (MARK) {
+      uint16_t* w = s16;
+      uint32_t seen = 0;
+      if (dist > m) {                      // reaches into the unknown window
+        const size_t before = dist - m;    // how far before the chunk's first byte
+        if (before > WSIZE) { err = "distance too far back"; return false; }
+        size_t widx = WSIZE - before;      // window index of the first byte
+        while (len && widx < WSIZE) { w[m++] = (uint16_t)(0x8000u + widx++); --len; seen = 0x8000u; }
+      }
+      // (the rest, if any, continues at the chunk's own symbols)
+      const uint16_t* src = w + (m - dist);
+      uint16_t* dst = w + m;
+      if (dist >= 8) {
+        // 8 symbols at a time; writes up to 7 symbols past the end (room is reserved by the callers)
+        for (uint32_t k = 0; k < len; k += 8) {
+          uint64_t a, b;
+          memcpy(&a, src + k, 8); memcpy(&b, src + k + 4, 8);
+          memcpy(dst + k, &a, 8); memcpy(dst + k + 4, &b, 8);
+          seen |= (uint32_t)((a | b) >> 32) | (uint32_t)(a | b);
+        }
+        // symbols past `len` may have contributed to `seen`: a false "marker seen" only delays the switch to bytes
+        seen = (seen | (seen >> 16)) & 0x8000u;
+      } else {
+        for (uint32_t k = 0; k < len; ++k) { const uint16_t sy = src[k]; dst[k] = sy; seen |= sy; }
+      }
+      m += len;
+      if (seen & 0x8000u) last_marker = m;
+    } else {
+      if (dist > n + valid_back) { err = "invalid distance too far back"; return false; }
+      uint8_t* w = out + HEAD + n;
+      const uint8_t* src = w - dist;
+      if (dist >= 16) {
+        for (uint32_t k = 0; k < len; k += 16) memcpy(w + k, src + k, 16);   // up to 15 bytes past the end (reserved)
+      } else if (dist >= len) memcpy(w, src, len);
+      else for (uint32_t k = 0; k < len; ++k) w[k] = src[k];
+      n += len;
+    }
+    return true;
+  }
+
+  template <bool MARK>
+  int codes_careful(const Ent* lt, const Ent* dt) {
     for (;;) {
       if (MARK) { if (m + 264 > cap16 && !grow16(264)) return -1; }
       else { if (n + 264 > cap && !grow8(264)) return -1; }
@@ -472,43 +643,7 @@ struct Decoder {
       const uint32_t dist = d.val + br.peek(d.opx & 15);
       br.consume(d.opx & 15);
       if (br.overrun) { err = "unexpected end of the compressed data"; return -1; }
-      if (MARK) {
-        uint16_t* w = s16;
-        uint32_t seen = 0;
-        if (dist > m) {                      // reaches into the unknown window
-          const size_t before = dist - m;    // how far before the chunk's first byte
-          if (before > WSIZE) { err = "distance too far back"; return -1; }
-          size_t widx = WSIZE - before;      // window index of the first byte
-          while (len && widx < WSIZE) { w[m++] = (uint16_t)(0x8000u + widx++); --len; seen = 0x8000u; }
-        }
-        // (the rest, if any, continues at the chunk's own symbols)
-        const uint16_t* src = w + (m - dist);
-        uint16_t* dst = w + m;
-        if (dist >= 8) {
-          // 8 symbols at a time; writes up to 7 symbols past the end (room is reserved above)
-          for (uint32_t k = 0; k < len; k += 8) {
-            uint64_t a, b;
-            memcpy(&a, src + k, 8); memcpy(&b, src + k + 4, 8);
-            memcpy(dst + k, &a, 8); memcpy(dst + k + 4, &b, 8);
-            seen |= (uint32_t)((a | b) >> 32) | (uint32_t)(a | b);
-          }
-          // symbols past `len` may have contributed to `seen`: a false "marker seen" only delays the switch to bytes
-          seen = (seen | (seen >> 16)) & 0x8000u;
-        } else {
-          for (uint32_t k = 0; k < len; ++k) { const uint16_t sy = src[k]; dst[k] = sy; seen |= sy; }
-        }
-        m += len;
-        if (seen & 0x8000u) last_marker = m;
-      } else {
-        if (dist > n + valid_back) { err = "invalid distance too far back"; return -1; }
-        uint8_t* w = out + HEAD + n;
-        const uint8_t* src = w - dist;
-        if (dist >= 16) {
-          for (uint32_t k = 0; k < len; k += 16) memcpy(w + k, src + k, 16);   // up to 15 bytes past the end (reserved)
-        } else if (dist >= len) memcpy(w, src, len);
-        else for (uint32_t k = 0; k < len; ++k) w[k] = src[k];
-        n += len;
-      }
+      if (!copy_match<MARK>(len, dist)) return -1;
     }
   }
 
@@ -660,6 +795,7 @@ class ParallelGz {
   // where the time went (thread CPU seconds): the workers' decode, the consumer's serial part
   double worker_cpu_s() const { return (double)worker_ns_.load() * 1e-9; }
   double consumer_cpu_s() const { return (double)consumer_ns_ * 1e-9; }
+  double resolve_cpu_s() const { return (double)resolve_ns_.load() * 1e-9; }   // (part of worker_cpu_s)
   uint64_t marker_symbols() const { return n16_total_; }
 
  private:
@@ -692,7 +828,7 @@ class ParallelGz {
   size_t win_n_ = 0;
   uint32_t crc_run_ = 0;          // CRC / length of the current member's text delivered so far
   uint64_t len_run_ = 0;
-  std::atomic<uint64_t> worker_ns_{0};
+  std::atomic<uint64_t> worker_ns_{0}, resolve_ns_{0};
   uint64_t consumer_ns_ = 0, n16_total_ = 0;
   static uint64_t cpu_ns() {
     timespec ts;
@@ -714,7 +850,7 @@ class ParallelGz {
     win_n_ += n;
   }
 
-  static bool resolve(const uint16_t* s, size_t m, const uint8_t* win, size_t win_n, uint8_t* t) {
+  static bool resolve_scalar(const uint16_t* s, size_t m, const uint8_t* win, size_t win_n, uint8_t* t) {
     for (size_t i = 0; i < m; ++i) {
       const uint16_t v = s[i];
       if (v & 0x8000u) {
@@ -724,6 +860,30 @@ class ParallelGz {
       } else t[i] = (uint8_t)v;
     }
     return true;
+  }
+#if defined(__x86_64__)
+  // 32 symbols at a time: groups without a marker (most of a FASTQ record's sequence and quality lines) are narrowed
+  // with one pack, the others go through the scalar loop
+  __attribute__((target("avx2"))) static bool resolve_avx2(const uint16_t* s, size_t m, const uint8_t* win, size_t win_n, uint8_t* t) {
+    size_t i = 0;
+    for (; i + 32 <= m; i += 32) {
+      const __m256i a = _mm256_loadu_si256((const __m256i*)(s + i)), b = _mm256_loadu_si256((const __m256i*)(s + i + 16));
+      if (_mm256_movemask_epi8(_mm256_or_si256(a, b)) & 0xAAAAAAAA) {
+        if (!resolve_scalar(s + i, 32, win, win_n, t + i)) return false;
+      } else {
+        const __m256i p = _mm256_permute4x64_epi64(_mm256_packus_epi16(a, b), 0xD8);
+        _mm256_storeu_si256((__m256i*)(t + i), p);
+      }
+    }
+    return resolve_scalar(s + i, m - i, win, win_n, t + i);
+  }
+#endif
+  static bool resolve(const uint16_t* s, size_t m, const uint8_t* win, size_t win_n, uint8_t* t) {
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) return resolve_avx2(s, m, win, win_n, t);
+#endif
+    return resolve_scalar(s, m, win, win_n, t);
   }
 
   // serial, cheap: the window after this chunk; the marker replacement itself becomes a task
@@ -836,6 +996,7 @@ class ParallelGz {
         pool_->put(co.s16, co.cap16 * 2); co.s16 = nullptr;
         co.win_in.reset();
         worker_ns_ += cpu_ns() - c0;
+        resolve_ns_ += cpu_ns() - c0;
         { std::lock_guard<std::mutex> lk(mu_); done_[i].store(2); }
         cv_done_.notify_all();
         continue;
