@@ -506,7 +506,10 @@ def bench_stage_a(args, rank, world, local, dist, W, peak, peak_src, ncores):
     if world == 1:
         v, ns, cc = stage_a_cpu(idx, p, left, right, args.cpu_budget, ncores)
         out["cpu_baseline"] = {"value": v, "unit": "Mreads/s", "cores": ncores, "kind": "port",
-                               "sample": f"{ns} read pairs of the same workload, same index, OpenMP over reads"}
+                               "sample": f"{ns} read pairs of the same workload, same index, OpenMP over reads",
+                               "note": "NOT a credible reference baseline: the product's serial forms compiled for the host over the "
+                                       "product's hash index, an order of magnitude below salmon's per-core rate; reported for "
+                                       "completeness, no speed-up is claimed from it (DESIGN.md section 6)"}
         ctx.close()
         ctx = None
         if not args.no_files:
@@ -579,7 +582,8 @@ def main():
             v, ns, cc = stage_a_cpu(idx, map_default_params(), left, right, max(4.0, min(args.cpu_budget, 20.0)), ncores)
             line["stage_a"] = {"metric": "Mreads/s selective-align", "value": v, "unit": "Mreads/s", "impl": "reference",
                                "cpu_baseline": {"value": v, "unit": "Mreads/s", "cores": ncores, "kind": "port",
-                                                "sample": f"{ns} read pairs, {len(txps)} transcripts, OpenMP over reads"}}
+                                                "sample": f"{ns} read pairs, {len(txps)} transcripts, OpenMP over reads",
+                                                "note": "NOT a credible reference baseline (see DESIGN.md section 6)"}}
         print(json.dumps(line))
         return 0
 
