@@ -330,6 +330,13 @@ static int32_t dp_score(const orc_index* ix, const orc_map_params* p, const uint
   return best;
 }
 
+/* test hook: the DP score of one read against one reference of an index (tests/test_dp_vs_edlib.py pins the recurrence
+ * against the reference tree's own edlib build, oracle/_ref/libedlib_ref.so) */
+int32_t orc_dp_score(const orc_index* ix, const orc_map_params* p, const uint8_t* read, uint32_t L, uint32_t ori,
+                     uint32_t tid, int32_t diag_c) {
+  return dp_score(ix, p, read, L, ori, tid, diag_c);
+}
+
 /* ---------------------------------------------------------------- joint hits */
 typedef struct {
   uint32_t tid; int32_t li, ri;   /* candidate indices, -1 if absent */

@@ -121,6 +121,11 @@ void orc_set_math_mode(int mode);
 int orc_get_math_mode(void);
 void orc_math_probe(int mode, uint64_t nx, const double* x, double* ex, uint64_t ny, const double* y, double* ly);
 
+/* test hook: banded affine glocal DP score of one read on reference `tid` around diagonal `diag_c` (read base i faces
+ * reference position diag_c + i); ori 1 = the read's reverse complement */
+int32_t orc_dp_score(const orc_index* ix, const orc_map_params* p, const uint8_t* read, uint32_t L, uint32_t ori,
+                     uint32_t tid, int32_t diag_c);
+
 #ifdef __cplusplus
 }
 #endif
