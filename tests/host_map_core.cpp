@@ -128,3 +128,12 @@ extern "C" int hmc_map_throughput(uint32_t n_txps, uint32_t k, const uint64_t* t
   for (int i = 0; i < 7; ++i) counters7[i] = tot[i];
   return 0;
 }
+
+// the product's serial DP form on one reference (tests/test_dp_vs_edlib.py)
+extern "C" int32_t hmc_dp_score(const uint64_t* tx_off, const uint8_t* codes, const Params* p, const uint8_t* read, uint32_t L,
+                                uint32_t ori, uint32_t tid, int32_t diag_c) {
+  IndexView ix;
+  memset(&ix, 0, sizeof ix);
+  ix.n_txps = tid + 1; ix.tx_off = tx_off; ix.codes = codes;
+  return dp_score_serial(ix, *p, read, L, ori, tid, diag_c);
+}

@@ -112,3 +112,58 @@ def test_default_scores_bound_by_edit_distance():
         assert p.ma * L - d * worst_per_edit <= score <= p.ma * L - (0 if d == 0 else min(-p.mp + p.ma, p.ge)), (trial, score, d, L)
         if d == 0:
             assert score == p.ma * L
+
+
+def test_product_serial_dp_equals_edlib_and_oracle():
+    """the product's serial DP form (map_core.h dp_score_serial, compiled for the host -- the form the warp kernel is
+    checked against on the GPU): unit costs against edlib, default scoring against the oracle, same cases"""
+    import hostmap_lib
+    from salmon_b200._capi import map_default_params
+    hw = _edlib()
+    hl = hostmap_lib.build()
+    hl.hmc_dp_score.restype = C.c_int32
+    ol = O.load()
+    ol.orc_dp_score.restype = C.c_int32
+    rng = np.random.default_rng(47)
+    ref = rng.integers(0, 4, 5000, dtype=np.uint8)
+    off = np.array([0, len(ref)], dtype=np.uint64)
+    ix = O.MapIndex([ref])
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+    pu, pd = map_default_params(ma=0, mp=-1, go=0, ge=1), map_default_params()
+    ou, od = O.map_params(ma=0, mp=-1, go=0, ge=1), O.map_params(ma=pd.ma, mp=pd.mp, go=pd.go, ge=pd.ge)
+    B = pu.band
+    assert B == ou.band
+
+    def prod(p, q, L, ori, diag):
+        return hl.hmc_dp_score(off.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p), C.byref(p), q.ctypes.data_as(C.c_void_p),
+                               C.c_uint32(L), C.c_uint32(ori), C.c_uint32(0), C.c_int32(diag))
+
+    def orc(p, q, L, ori, diag):
+        return ol.orc_dp_score(C.c_void_p(ix.h.value), C.byref(p), q.ctypes.data_as(C.c_void_p), C.c_uint32(L), C.c_uint32(ori),
+                               C.c_uint32(0), C.c_int32(diag))
+    for trial in range(1200):
+        L = int(rng.integers(40, 151))
+        start = int(rng.integers(100, len(ref) - 400))
+        read = _mutate(rng, ref[start:start + L + 8], int(rng.integers(0, 5)))[:L]
+        if trial % 9 == 0:
+            read[int(rng.integers(0, L))] = 4                               # an N in the read mismatches everything
+        ori = trial & 1
+        q = np.ascontiguousarray(read if not ori else np.where(read[::-1] > 3, 4, 3 - read[::-1]).astype(np.uint8))
+        diag = start + int(rng.integers(-3, 4))
+        assert prod(pd, q, L, ori, diag) == orc(od, q, L, ori, diag), trial
+        su = prod(pu, q, L, ori, diag)
+        assert su == orc(ou, q, L, ori, diag), trial
+        if trial % 9 != 0:
+            d = hw(letters[read].tobytes(), letters[ref[max(0, diag - B): diag + L + B]].tobytes())
+            assert su == -d, (trial, su, d)
+    # reads that hang over either end of the reference: the DP and edlib on the clipped window agree on what is left
+    for trial in range(200):
+        L = 100
+        over = int(rng.integers(1, 12))
+        if trial & 1:
+            read = np.concatenate([rng.integers(0, 4, over, dtype=np.uint8), ref[:L - over]]); diag = -over
+        else:
+            read = np.concatenate([ref[len(ref) - (L - over):], rng.integers(0, 4, over, dtype=np.uint8)]); diag = len(ref) - (L - over)
+        q = np.ascontiguousarray(read)
+        assert prod(pd, q, L, 0, diag) == orc(od, q, L, 0, diag), trial
+        assert prod(pu, q, L, 0, diag) == orc(ou, q, L, 0, diag), trial
