@@ -516,6 +516,16 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
                              : "a paired-end library type needs both mate files");
     return SB_ERR_INVALID;
   }
+  if (multi && (o.num_bootstraps || o.num_gibbs)) {
+    // the samplers resample a whole class table; with the reads sharded every rank holds only its share of the classes
+    sb::set_error("posterior samples are not drawn from read-sharded classes: map on one GPU with --dumpEqWeights, then "
+                  "`quant -e <out>/aux_info/eq_classes.txt.gz --numBootstraps/--numGibbsSamples N --gpus G` (the samples are split over the GPUs)");
+    return SB_ERR_INVALID;
+  }
+  if (multi && (o.dump_eq || o.dump_eq_weights)) {
+    sb::set_error("--dumpEq / --dumpEqWeights need a one-GPU run: with the reads sharded every rank holds only the classes of its own reads");
+    return SB_ERR_INVALID;
+  }
   uint32_t M = 0, k = 0, first_decoy = 0;
   const char* const* names = nullptr;
   const uint32_t* complete_len = nullptr;
