@@ -295,6 +295,11 @@ typedef struct sb_map_params {
   int32_t lib_type;
   int32_t reserved3;
 } sb_map_params;
+/* Only sb_quant_files takes these two: the library type is detected from the first 50 000 fragments that show a
+ * strand, as LibraryTypeDetector does (include/salmon/internal/model/LibraryTypeDetector.hpp:34-140): until then every
+ * mapping counts as compatible, afterwards the detected type applies (checked after every batch). */
+#define SB_LIB_AUTO_PAIRED 6
+#define SB_LIB_AUTO_SINGLE 7
 #define SB_LIB_IU 0
 #define SB_LIB_ISF 1
 #define SB_LIB_ISR 2
@@ -498,6 +503,16 @@ int sb_quant_eqclasses(const char* eq_path, const sb_em_params* ep, const sb_qua
  * are sequence characters A/C/G/T/N as the reference's parser delivers them, klibpp::KSeq::seq, instead of base
  * codes).  Results are identical for every setting. */
 int sb_map_set_option(sb_map_ctx* ctx, const char* key, int64_t value);
+
+/* "lib_type" is also a key of sb_map_set_option: the expected library format of the batches that follow (inside the
+ * family the context was created with: IU / ISF / ISR or U / SF / SR).
+ * sb_map_lib_counts: fragments mapped so far that showed the formats {ISF, ISR, SF, SR} among their kept mappings
+ * (cumulative over the batches; no device work).
+ * sb_detect_lib_type: LibraryTypeDetector::mostLikelyType for the inward / unmated formats this library maps --
+ * fraction of sense-strand fragments below 0.3 -> ISR (SR), below 0.7 -> IU (U), else ISF (SF); -1 when no fragment
+ * has shown a strand yet. */
+int sb_map_lib_counts(const sb_map_ctx* ctx, uint64_t out4[4]);
+int sb_detect_lib_type(int paired, const uint64_t counts4[4]);
 
 /* Debug: per-warp phase timestamps (ns) of one iteration of the last persistent run:
  * out[n_warps*8] = {P1 start, P1 end, barrier1 end, P2 start, P2 end, reduce end, barrier2 end, -}.

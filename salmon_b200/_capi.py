@@ -158,6 +158,8 @@ SYMBOLS = {
     "sb_reads_skip": (C.c_int64, [_P, C.c_uint32]),
     "sb_reads_paired": (C.c_int, [_P]),
     "sb_device_init": (C.c_int, [C.c_int]),
+    "sb_map_lib_counts": (C.c_int, [_P, _P]),
+    "sb_detect_lib_type": (C.c_int, [C.c_int, _P]),
     "sb_reads_bucketed": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P]),
     "sb_eq_file_read": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(sb_eq_file))]),
     "sb_eq_file_free": (None, [C.POINTER(sb_eq_file)]),

@@ -349,9 +349,9 @@ int cmd_quant(Args& a) {
     return 1;
   }
   int lib_id = -1;
-  if (lib == "A") lib_id = se_input ? SB_LIB_U : SB_LIB_IU;      // (automatic detection is not implemented: the unstranded type)
+  if (lib == "A") lib_id = se_input ? SB_LIB_AUTO_SINGLE : SB_LIB_AUTO_PAIRED;   // detected from the first 50 000 stranded fragments
   for (auto& ln : lib_names) if (lib == ln.name) lib_id = ln.id;
-  if (lib_id < 0 || (lib_id >= SB_LIB_U) != se_input) {
+  if (lib_id < 0 || ((lib_id >= SB_LIB_U && lib_id != SB_LIB_AUTO_PAIRED) != se_input)) {
     fprintf(stderr, "sb_salmon quant: library type %s does not fit the input (IU / ISF / ISR with -1 -2, U / SF / SR with -r; "
                     "outward and same-strand types are not supported)\n", lib.c_str());
     return 1;

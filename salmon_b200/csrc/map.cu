@@ -1287,6 +1287,14 @@ extern "C" int sb_map_set_option(sb_map_ctx* c, const char* key, int64_t value) 
     return SB_OK;
   }
   if (!strcmp(key, "overlap_assign")) { c->overlap_assign = value ? 1 : 0; return SB_OK; }
+  if (!strcmp(key, "lib_type")) {   // the expected format of the batches that follow, inside the context's family
+    if (value < 0 || value > 5 || (value >= 3) != (c->p.lib_type >= 3)) {
+      sb::set_error("lib_type %lld does not fit this context (paired-end: 0..2, single-end: 3..5)", (long long)value);
+      return SB_ERR_INVALID;
+    }
+    c->p.lib_type = (int32_t)value;
+    return SB_OK;
+  }
   if (!strcmp(key, "chunk")) {   // reads per pipeline chunk (<= the size the context was created with)
     const uint32_t mx = c->chunk_cap;
     if (value < 1 || value > (int64_t)mx) { sb::set_error("chunk must be in 1..%u", mx); return SB_ERR_INVALID; }
@@ -1560,6 +1568,24 @@ extern "C" int sb_map_batch(sb_map_ctx* c, const uint8_t* left, const uint8_t* r
       }
   }
   return SB_OK;
+}
+
+extern "C" int sb_map_lib_counts(const sb_map_ctx* c, uint64_t out4[4]) {
+  if (!c || !out4) { sb::set_error("null argument"); return SB_ERR_INVALID; }
+  for (int i = 0; i < 4; ++i) out4[i] = c->totals.lib_mask_sum[i];
+  return SB_OK;
+}
+
+// LibraryTypeDetector::mostLikelyType (LibraryTypeDetector.hpp:34-140) for the formats this library maps (inward
+// pairs, unmated reads): the fraction of sense-strand fragments decides
+extern "C" int sb_detect_lib_type(int paired, const uint64_t counts4[4]) {
+  if (!counts4) return -1;
+  const uint64_t nf = paired ? counts4[0] : counts4[2], nr = paired ? counts4[1] : counts4[3];
+  if (nf + nr == 0) return -1;
+  const double ratio = (double)nf / (double)(nf + nr);
+  if (ratio < 0.3) return paired ? SB_LIB_ISR : SB_LIB_SR;
+  if (ratio < 0.7) return paired ? SB_LIB_IU : SB_LIB_U;
+  return paired ? SB_LIB_ISF : SB_LIB_SF;
 }
 
 // debug / parity tap: per-read alignments of the LAST batch (arrays sized n*cap, label n*2*cap)

@@ -509,21 +509,18 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
   if (mp_in) mp = *mp_in; else sb_map_default_params(&mp);
   sb_em_params ep;
   if (ep_in) ep = *ep_in; else sb_em_default_params(&ep);
+  // -l A: start unstranded (nothing is incompatible before the type is known, SalmonQuantify.cpp:496-501), decide from
+  // the first 50 000 fragments that show a strand, checked after every batch
+  bool auto_lib = false;
+  if (mp.lib_type == SB_LIB_AUTO_PAIRED || mp.lib_type == SB_LIB_AUTO_SINGLE) {
+    auto_lib = !multi;   // (with the reads sharded the ranks would decide at different points: the run stays unstranded)
+    mp.lib_type = mp.lib_type == SB_LIB_AUTO_PAIRED ? SB_LIB_IU : SB_LIB_U;
+  }
   // single-end libraries (-r, library types U / SF / SR) come with mates2 == NULL
   const bool single_end = mp.lib_type >= SB_LIB_U;
   if (single_end != (mates2 == nullptr)) {
     sb::set_error(single_end ? "a single-end library type takes unmated reads only (mates2 == NULL)"
                              : "a paired-end library type needs both mate files");
-    return SB_ERR_INVALID;
-  }
-  if (multi && (o.num_bootstraps || o.num_gibbs)) {
-    // the samplers resample a whole class table; with the reads sharded every rank holds only its share of the classes
-    sb::set_error("posterior samples are not drawn from read-sharded classes: map on one GPU with --dumpEqWeights, then "
-                  "`quant -e <out>/aux_info/eq_classes.txt.gz --numBootstraps/--numGibbsSamples N --gpus G` (the samples are split over the GPUs)");
-    return SB_ERR_INVALID;
-  }
-  if (multi && (o.dump_eq || o.dump_eq_weights)) {
-    sb::set_error("--dumpEq / --dumpEqWeights need a one-GPU run: with the reads sharded every rank holds only the classes of its own reads");
     return SB_ERR_INVALID;
   }
   uint32_t M = 0, k = 0, first_decoy = 0;
@@ -551,12 +548,25 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
   S.rd = sb_reads_open(mates1, mates2, n_files, o.threads);
   if (!S.rd) return SB_ERR_INVALID;
 
-  struct MapUser { sb_map_ctx* ctx; float device_ms; } mu{S.ctx, 0.0f};
+  struct MapUser { sb_map_ctx* ctx; float device_ms; bool detect; bool paired; int detected; uint64_t at_fragment, seen; } mu{
+      S.ctx, 0.0f, auto_lib, !single_end, -1, 0, 0};
   sb_batch_cb map_cb = [](void* user, const uint8_t* l, const uint8_t* r, uint32_t n, uint32_t L) -> int {
     MapUser* u = (MapUser*)user;
     sb_map_batch_stats st;
-    const int rc = sb_map_batch(u->ctx, l, r, n, L, &st);
-    if (rc == SB_OK) u->device_ms += st.device_ms;
+    int rc = sb_map_batch(u->ctx, l, r, n, L, &st);
+    if (rc != SB_OK) return rc;
+    u->device_ms += st.device_ms;
+    u->seen += n;
+    if (u->detect) {
+      uint64_t c4[4];
+      rc = sb_map_lib_counts(u->ctx, c4);
+      if (rc == SB_OK && (u->paired ? c4[0] + c4[1] : c4[2] + c4[3]) >= 50000) {   // numSamplesNeeded_, LibraryTypeDetector.hpp:171
+        u->detected = sb_detect_lib_type(u->paired ? 1 : 0, c4);
+        u->at_fragment = u->seen;
+        u->detect = false;
+        if (u->detected >= 0) rc = sb_map_set_option(u->ctx, "lib_type", u->detected);
+      }
+    }
     return rc;
   };
   sb_bucket_stats bs;
@@ -566,6 +576,16 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
   if (rc != SB_OK) return rc;
   const float device_ms = mu.device_ms;
   const double t_map = now_s();
+  if (auto_lib && o.shard_index == 0) {
+    static const char* const nm[6] = {"IU", "ISF", "ISR", "U", "SF", "SR"};
+    if (mu.detected >= 0) {
+      mp.lib_type = mu.detected;       // what the run metadata reports as the expected format
+      fprintf(stderr, "Automatically detected most likely library type as %s (after %llu fragments)\n", nm[mu.detected],
+              (unsigned long long)mu.at_fragment);
+    } else {
+      fprintf(stderr, "library type not detected (fewer than 50000 stranded fragments): the run stayed %s\n", nm[mp.lib_type]);
+    }
+  }
 
   // ---- classes -> (global statistics) -> EM -> outputs -----------------------------------------------------------
   sb_map_result res;

@@ -64,3 +64,21 @@ def test_no_collective_inside_rank_conditional_blocks():
         if "sb_comm_all" in src[m.end():i]:
             bad.append(src[m.start():m.end()])
     assert not bad, bad
+
+
+def test_library_type_detection_rule():
+    """sb_detect_lib_type restates LibraryTypeDetector::mostLikelyType (LibraryTypeDetector.hpp:34-140) for inward pairs
+    and unmated reads: sense fraction < 0.3 -> antisense type, < 0.7 -> unstranded, else sense; nothing seen -> -1"""
+    import ctypes as C
+    from salmon_b200 import _capi
+    lib = _capi.load()
+    IU, ISF, ISR, U, SF, SR = range(6)
+
+    def det(paired, isf, isr, sf, sr):
+        a = (C.c_uint64 * 4)(isf, isr, sf, sr)
+        return lib.sb_detect_lib_type(1 if paired else 0, a)
+    assert det(True, 0, 0, 5, 5) == -1 and det(False, 7, 7, 0, 0) == -1
+    assert det(True, 29, 71, 0, 0) == ISR and det(True, 30, 70, 0, 0) == IU and det(True, 69, 31, 0, 0) == IU
+    assert det(True, 70, 30, 0, 0) == ISF and det(True, 100, 0, 0, 0) == ISF and det(True, 0, 9, 0, 0) == ISR
+    assert det(False, 0, 0, 29, 71) == SR and det(False, 0, 0, 50, 50) == U and det(False, 0, 0, 70, 30) == SF
+    assert lib.sb_detect_lib_type(1, None) == -1
