@@ -196,8 +196,9 @@ int sb_eq_file_read(const char* path, sb_eq_file** out);
 void sb_eq_file_free(sb_eq_file* f);
 
 /* aux_info/bootstrap/bootstraps.gz (src/output/GZipWriter.cpp:765-789 writeBootstrap): every sample is n raw doubles
- * appended to one gzip stream (level 6); write() may be called from several threads (the sb_bootstrap / sb_gibbs
- * callback).  close() returns the number of samples written. */
+ * appended to one gzip member (level 6, deflated in 128 KiB slices by a thread team the way pigz does it); write() may
+ * be called from several threads (the sb_bootstrap / sb_gibbs callback).  close() returns the number of samples written,
+ * or a negative code when the file could not be completed (full disk). */
 typedef struct sb_bootstrap_writer sb_bootstrap_writer;
 sb_bootstrap_writer* sb_bootstrap_writer_open(const char* path);
 int sb_bootstrap_writer_write(sb_bootstrap_writer* w, const double* sample, uint32_t n);
