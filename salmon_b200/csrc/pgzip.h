@@ -178,9 +178,27 @@ inline int build_table(Ent* tab, int primary, const uint8_t* lens, int n, int ki
   return left > 0 ? 1 : 0;
 }
 
+constexpr int PAIR_BITS = 12;
 struct Tables {
   Ent lit[LIT_TAB];
   Ent dist[DIST_TAB];
+  // two literals per look-up (FASTQ text is mostly literals: bases in 2-3 bits, qualities in 4-6): indexed by the next
+  // PAIR_BITS bits; low 16 bits = first literal | second << 8, bits 16-19 = code bits of both, bits 20-21 = how many
+  // literals (0: the window does not start with a directly coded literal -- the general path decodes it)
+  uint32_t pair[1 << PAIR_BITS];
+  void build_pairs() {
+    for (uint32_t w = 0; w < (1u << PAIR_BITS); ++w) {
+      const Ent a = lit[w & ((1u << LIT_BITS) - 1)];
+      uint32_t v = 0;
+      if ((a.opx >> 4) == OP_LIT && a.len <= LIT_BITS) {
+        v = a.val | ((uint32_t)a.len << 16) | (1u << 20);
+        const Ent b = lit[(w >> a.len) & ((1u << LIT_BITS) - 1)];
+        if ((b.opx >> 4) == OP_LIT && a.len + b.len <= PAIR_BITS)
+          v = a.val | ((uint32_t)b.val << 8) | ((uint32_t)(a.len + b.len) << 16) | (2u << 20);
+      }
+      pair[w] = v;
+    }
+  }
 };
 
 // the fixed code of BTYPE 1 (RFC 1951 3.2.6)
@@ -196,6 +214,7 @@ inline const Tables& fixed_tables() {
     uint8_t d[32];
     for (int i = 0; i < 32; ++i) d[i] = 5;
     build_table(t->dist, DIST_BITS, d, 32, 2);
+    t->build_pairs();
     return t;
   }();
   return *T;
@@ -203,7 +222,7 @@ inline const Tables& fixed_tables() {
 
 // the header of a dynamic block (after the 3 block bits): 0 = tables built, -1 = not a valid header (zlib's rules:
 // inflate.c / inftrees.c -- the code-length code must be complete; the other two complete or a single 1-bit code)
-inline int read_dynamic_header(BitReader& br, Tables& T) {
+inline int read_dynamic_header(BitReader& br, Tables& T, bool pairs = false) {
   br.refill();
   const uint32_t nlen = br.get(5) + 257, ndist = br.get(5) + 1, ncode = br.get(4) + 4;
   if (nlen > 286 || ndist > 30) return -1;
@@ -239,6 +258,7 @@ inline int read_dynamic_header(BitReader& br, Tables& T) {
   r = build_table(T.dist, DIST_BITS, lens + nlen, (int)ndist, 2);
   if (r < 0) return -1;
   if (r == 1) { int mx = 0; for (uint32_t k = 0; k < ndist; ++k) mx = lens[nlen + k] > mx ? lens[nlen + k] : mx; if (mx != 1) return -1; }
+  if (pairs) T.build_pairs();
   return 0;
 }
 
@@ -322,8 +342,10 @@ struct BufPool {
   void* get(size_t bytes, size_t* cap) {
     {
       std::lock_guard<std::mutex> lk(mu);
-      for (size_t i = v.size(); i-- > 0;)
-        if (v[i].second >= bytes) { void* p = v[i].first; *cap = v[i].second; v.erase(v.begin() + (long)i); return p; }
+      size_t best = v.size();     // best fit: the marker buffers are twice the size of the text buffers
+      for (size_t i = 0; i < v.size(); ++i)
+        if (v[i].second >= bytes && (best == v.size() || v[i].second < v[best].second)) best = i;
+      if (best < v.size()) { void* p = v[best].first; *cap = v[best].second; v.erase(v.begin() + (long)best); return p; }
       if (v.size() >= max_keep) { free(v.front().first); v.erase(v.begin()); }   // too small for the asker: make room
     }
     *cap = bytes;
@@ -501,7 +523,7 @@ struct Decoder {
   // one block's symbols; 0 = end of block, -1 = error.  The fast loop keeps the bit buffer in registers and never checks
   // for the end of the input (it leaves while 16 bytes are still unread); the careful loop below finishes the block.
   template <bool MARK>
-  int codes(const Ent* lt, const Ent* dt) {
+  int codes(const Ent* lt, const Ent* dt, const uint32_t* pt) {
     uint64_t buf = br.buf;
     int cnt = br.cnt;
     const uint8_t* p = br.p;
@@ -513,13 +535,20 @@ struct Decoder {
       if (MARK) { if (m + 264 > cap16) { if (!grow16(264)) { status = -1; break; } } }
       else { if (n + 264 > cap) { if (!grow8(264)) { status = -1; break; } } }
       PGZ_REFILL();
-      Ent e = lt[buf & ((1u << LIT_BITS) - 1)];
-      for (int r = 0; r < 3 && (e.opx >> 4) == OP_LIT; ++r) {
-        PGZ_DROP(e.len);
-        if (MARK) s16[m++] = e.val; else out[HEAD + n++] = (uint8_t)e.val;
-        e = lt[buf & ((1u << LIT_BITS) - 1)];
+      // up to four look-ups of two literals each per refill (4 x PAIR_BITS = 48 of the 56 bits)
+      {
+        bool more = true;
+        for (int r = 0; r < 4; ++r) {
+          const uint32_t v = pt[buf & ((1u << PAIR_BITS) - 1)];
+          const uint32_t k = v >> 20;
+          if (k == 0) { more = false; break; }
+          if (MARK) { s16[m] = (uint16_t)(v & 0xff); s16[m + 1] = (uint16_t)((v >> 8) & 0xff); m += k; }
+          else { out[HEAD + n] = (uint8_t)v; out[HEAD + n + 1] = (uint8_t)(v >> 8); n += k; }
+          PGZ_DROP((v >> 16) & 15);
+        }
+        if (more) continue;
       }
-      if ((e.opx >> 4) == OP_LIT) continue;
+      Ent e = lt[buf & ((1u << LIT_BITS) - 1)];
       if (cnt < 48) PGZ_REFILL();
       if ((e.opx >> 4) == OP_LINK) {
         const int sb = e.opx & 15;
@@ -555,7 +584,7 @@ struct Decoder {
 #undef PGZ_DROP
     br.buf = buf; br.cnt = cnt; br.p = p;
     if (status != 2) return status;
-    return codes_careful<MARK>(lt, dt);
+    return codes_careful<MARK>(lt, dt);   // (the careful loop needs no pair table)
   }
 
   template <bool MARK>
@@ -868,11 +897,24 @@ class ParallelGz {
     size_t i = 0;
     for (; i + 32 <= m; i += 32) {
       const __m256i a = _mm256_loadu_si256((const __m256i*)(s + i)), b = _mm256_loadu_si256((const __m256i*)(s + i + 16));
-      if (_mm256_movemask_epi8(_mm256_or_si256(a, b)) & 0xAAAAAAAA) {
-        if (!resolve_scalar(s + i, 32, win, win_n, t + i)) return false;
-      } else {
-        const __m256i p = _mm256_permute4x64_epi64(_mm256_packus_epi16(a, b), 0xD8);
-        _mm256_storeu_si256((__m256i*)(t + i), p);
+      // narrow all 32 (a marker saturates to 255), then put the window byte where a marker was: the cost follows the
+      // number of markers, not the number of groups that hold one (in FASTQ every record's name carries a few)
+      const __m256i p = _mm256_permute4x64_epi64(_mm256_packus_epi16(a, b), 0xD8);
+      _mm256_storeu_si256((__m256i*)(t + i), p);
+      uint32_t ma = (uint32_t)_mm256_movemask_epi8(a) & 0xAAAAAAAAu, mb = (uint32_t)_mm256_movemask_epi8(b) & 0xAAAAAAAAu;
+      while (ma) {
+        const int j = __builtin_ctz(ma) >> 1;
+        ma &= ma - 1;
+        const size_t back = WSIZE - (s[i + j] & 0x7fffu);
+        if (back > win_n) return false;
+        t[i + j] = win[win_n - back];
+      }
+      while (mb) {
+        const int j = 16 + (__builtin_ctz(mb) >> 1);
+        mb &= mb - 1;
+        const size_t back = WSIZE - (s[i + j] & 0x7fffu);
+        if (back > win_n) return false;
+        t[i + j] = win[win_n - back];
       }
     }
     return resolve_scalar(s + i, m - i, win, win_n, t + i);
@@ -1093,10 +1135,10 @@ class ParallelGz {
       const uint32_t type = hdr >> 1;
       int rc = 0;
       if (type == 0) rc = D.stored();
-      else if (type == 1) { const Tables& F = fixed_tables(); rc = D.markers ? D.codes<true>(F.lit, F.dist) : D.codes<false>(F.lit, F.dist); }
+      else if (type == 1) { const Tables& F = fixed_tables(); rc = D.markers ? D.codes<true>(F.lit, F.dist, F.pair) : D.codes<false>(F.lit, F.dist, F.pair); }
       else if (type == 2) {
-        if (read_dynamic_header(D.br, tab) != 0) { D.err = "invalid dynamic block header"; rc = -1; }
-        else rc = D.markers ? D.codes<true>(tab.lit, tab.dist) : D.codes<false>(tab.lit, tab.dist);
+        if (read_dynamic_header(D.br, tab, true) != 0) { D.err = "invalid dynamic block header"; rc = -1; }
+        else rc = D.markers ? D.codes<true>(tab.lit, tab.dist, tab.pair) : D.codes<false>(tab.lit, tab.dist, tab.pair);
       } else { D.err = "invalid block type"; rc = -1; }
       if (rc != 0 || D.br.overrun) {
         co.err = "corrupt gzip data: " + (D.err.empty() ? std::string("unexpected end of the compressed data") : D.err);
