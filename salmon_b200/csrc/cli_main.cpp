@@ -12,6 +12,7 @@
 #include <sys/wait.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <string>
 #include <thread>
 #include <vector>
@@ -210,7 +211,7 @@ int cmd_quant(Args& a) {
   sb_quant_default_opts(&qo);
   auto num = [&](double& d) { if (!a.value(v)) return false; d = atof(v.c_str()); return true; };
   double d = 0;
-  bool vb_prior_given = false, pre_merge_given = false;
+  bool vb_prior_given = false, pre_merge_given = false, threads_given = false;
   int n_gpus = 1, my_rank = -1;
   std::string run_tag;
   while (a.more()) {
@@ -222,7 +223,7 @@ int cmd_quant(Args& a) {
     else if (o == "-2" || o == "--mates2") a.list(m2);
     else if (o == "-r" || o == "--unmatedReads") a.list(unmated);
     else if (o == "-e" || o == "--eqclasses") { if (!a.value(eqfile)) return usage(); }
-    else if (o == "-p" || o == "--threads") { if (!num(d)) return usage(); qo.threads = (uint32_t)d; }
+    else if (o == "-p" || o == "--threads") { if (!num(d)) return usage(); qo.threads = (uint32_t)d; threads_given = true; }
     else if (o == "--dumpEq") qo.dump_eq = 1;
     else if (o == "-d" || o == "--dumpEqWeights") qo.dump_eq_weights = 1;
     else if (o == "--numBootstraps") { if (!num(d)) return usage(); qo.num_bootstraps = (uint32_t)d; }
@@ -275,6 +276,10 @@ int cmd_quant(Args& a) {
     } else { fprintf(stderr, "sb_salmon quant: unknown option %s\n", o.c_str()); return usage(); }
   }
   if (out.empty()) return usage();
+  if (!threads_given) {   // host threads for the reader (inflate, scan, translate): half the hardware threads, 32 at most
+    const unsigned hw = std::thread::hardware_concurrency();
+    qo.threads = std::max(2u, std::min(32u, hw / 2));
+  }
   // --perNucleotidePrior without an explicit --vbPrior: the reference switches the default to 1e-5
   // (src/cli/QuantOptionsUtils.cpp:569-572)
   if (ep.use_vbem && !ep.per_txp_prior && !vb_prior_given) ep.vb_prior = 1e-5;
