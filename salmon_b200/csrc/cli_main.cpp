@@ -278,7 +278,7 @@ int cmd_quant(Args& a) {
   if (out.empty()) return usage();
   if (!threads_given) {   // host threads for the reader (inflate, scan, translate): half the hardware threads, 32 at most
     const unsigned hw = std::thread::hardware_concurrency();
-    qo.threads = std::max(2u, std::min(32u, hw / 2));
+    qo.threads = std::max(2u, std::min(32u, hw / 2 / (unsigned)std::max(1, n_gpus)));   // (per rank)
   }
   // --perNucleotidePrior without an explicit --vbPrior: the reference switches the default to 1e-5
   // (src/cli/QuantOptionsUtils.cpp:569-572)
