@@ -88,3 +88,28 @@ def test_product_host_logic_vs_libm_oracle():
     assert len(flips) <= 0.02 * len(got["n_aln"]), len(flips)
     for k in ("lookups", "postings", "seeds", "kept", "label_entries", "mapped"):
         assert got["counters"][k] == ref["counters"][k], k
+
+
+def test_oracle_digamma_vs_reference_tree_eigen():
+    """the oracle's digamma (checker of the fused VBEM transform) against the digamma the reference tree itself vendors
+    (Eigen's Cephes-derived implementation, compiled by oracle/build_ref.sh from the headers under /root/reference through
+    a five-line shim; boost::math::digamma, which salmon calls, is not in the tree).  Skipped when oracle/_ref is absent."""
+    import ctypes as C
+    import os
+    import numpy as np
+    import pytest
+    import oracle_lib as O
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libeigen_digamma_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libeigen_digamma_ref.so not built (needs /root/reference)")
+    lib = C.CDLL(so)
+    rng = np.random.default_rng(11)
+    x = np.concatenate([10.0 ** rng.uniform(-10, 9, 40000), np.linspace(0.01, 40.0, 20000), rng.uniform(1.3, 1.6, 5000)])
+    ref = np.empty_like(x)
+    lib.ref_eigen_digamma(C.c_ulong(len(x)), x.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p))
+    mine = np.array([O.digamma(v) for v in x])
+    err = np.abs(mine - ref)
+    # relative where digamma is not near its root (x0 = 1.4616...), absolute there
+    far = np.abs(ref) > 1e-2
+    assert np.all(err[far] <= 2e-13 * np.abs(ref[far])), float((err[far] / np.abs(ref[far])).max())
+    assert np.all(err[~far] <= 1e-14), float(err[~far].max())
