@@ -461,7 +461,9 @@ typedef struct sb_quant_summary {
   uint64_t n_observed, n_mapped, n_too_short, n_trimmed_mates, n_classes, n_batches;
   uint32_t n_read_lengths, em_iters, em_converged, reserved;
   double map_seconds, em_seconds, total_seconds;   /* wall clock */
-  float map_device_ms, reserved2;                  /* sum of sb_map_batch_stats.device_ms */
+  float map_device_ms;                             /* sum of sb_map_batch_stats.device_ms */
+  float map_setup_ms;                              /* the part of map_seconds before the first read is parsed: sb_map_create
+                                                      (workspace allocation, index upload if not resident) + opening the files */
 } sb_quant_summary;
 void sb_quant_default_opts(sb_quant_opts* o);
 /* mp / ep / o may be NULL (defaults); out_dir may be NULL (no files); alpha_out[n_txps] may be NULL (decoy entries, the

@@ -144,7 +144,7 @@ class sb_quant_summary(C.Structure):
                 ("n_trimmed_mates", C.c_uint64), ("n_classes", C.c_uint64), ("n_batches", C.c_uint64),
                 ("n_read_lengths", C.c_uint32), ("em_iters", C.c_uint32), ("em_converged", C.c_uint32),
                 ("reserved", C.c_uint32), ("map_seconds", C.c_double), ("em_seconds", C.c_double),
-                ("total_seconds", C.c_double), ("map_device_ms", C.c_float), ("reserved2", C.c_float)]
+                ("total_seconds", C.c_double), ("map_device_ms", C.c_float), ("map_setup_ms", C.c_float)]
 
 
 SYMBOLS = {

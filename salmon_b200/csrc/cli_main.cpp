@@ -383,9 +383,9 @@ int cmd_quant(Args& a) {
     fprintf(stderr, "%llu fragments observed, %llu mapped (%.4f%%), %llu equivalence classes%s; %u read lengths, %llu batches%s\n",
             (unsigned long long)sum.n_observed, (unsigned long long)sum.n_mapped, rate, (unsigned long long)sum.n_classes,
             n_gpus > 1 ? " on rank 0" : "", sum.n_read_lengths, (unsigned long long)sum.n_batches, n_gpus > 1 ? " on rank 0" : "");
-    fprintf(stderr, "mapping %.2f s (%.1f ms on the device, %.2f M fragments/s end to end, %d GPU(s)), optimiser %u iterations in %.2f s, total %.2f s\n",
+    fprintf(stderr, "mapping %.2f s (%.1f ms on the device, %.2f M fragments/s end to end, %d GPU(s)), optimiser %u iterations in %.2f s, total %.2f s; mapping set-up %.2f s\n",
             sum.map_seconds, sum.map_device_ms, sum.map_seconds > 0 ? (double)sum.n_observed / sum.map_seconds / 1e6 : 0.0, n_gpus, sum.em_iters,
-            sum.em_seconds, sum.total_seconds);
+            sum.em_seconds, sum.total_seconds, (double)sum.map_setup_ms * 1e-3);
   }
   if (qo.shard_index == 0) fprintf(stderr, "done %.2f s after the process started\n", now_wall() - T_PROCESS_START);
   // the outputs are written and closed: leave without tearing down 10+ GB of host and device state piece by piece

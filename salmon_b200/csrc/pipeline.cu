@@ -547,6 +547,7 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
   if (getenv("SB_READS_PROFILE")) fprintf(stderr, "sb_quant_files: sb_map_create %.3f s\n", now_s() - t0);
   S.rd = sb_reads_open(mates1, mates2, n_files, o.threads);
   if (!S.rd) return SB_ERR_INVALID;
+  const double t_setup = now_s();
 
   struct MapUser { sb_map_ctx* ctx; float device_ms; bool detect; bool paired; int detected; uint64_t at_fragment, seen; } mu{
       S.ctx, 0.0f, auto_lib, !single_end, -1, 0, 0};
@@ -656,6 +657,7 @@ extern "C" int sb_quant_files(sb_index* ix, const char* const* mates1, const cha
     sum->em_iters = est.iters; sum->em_converged = est.converged;
     sum->map_seconds = t_map - t0; sum->em_seconds = t_em - t_map; sum->total_seconds = now_s() - t0;
     sum->map_device_ms = device_ms;
+    sum->map_setup_ms = (float)((t_setup - t0) * 1e3);
   }
   return SB_OK;
 }
