@@ -522,3 +522,21 @@ def test_quant_files_argument_checks():
                     (dict(max_read_len=1000), "max_read_len"), (dict(num_bootstraps=2, num_gibbs=2), "not both")):
         with pytest.raises(_capi.SalmonB200Error, match=msg):
             _capi.quant_files_native(idx, "a.fq", "b.fq", **kw)
+
+
+def test_quant_files_auto_library_type_arguments():
+    """SB_LIB_AUTO_PAIRED / SB_LIB_AUTO_SINGLE (-l A) are resolved to their unstranded family before the mate-file check;
+    without a GPU the call then fails loudly at sb_map_create (the library has no CPU path)"""
+    idx = _capi.Index([encode(rand_seq(np.random.default_rng(2), 300))], k=31)
+    auto_pe, auto_se = _capi.map_default_params(lib_type=6), _capi.map_default_params(lib_type=7)
+    with pytest.raises(_capi.SalmonB200Error, match="needs both mate files"):
+        _capi.quant_files_native(idx, "a.fq", None, map_params=auto_pe)
+    with pytest.raises(_capi.SalmonB200Error, match="unmated reads only"):
+        _capi.quant_files_native(idx, "a.fq", "b.fq", map_params=auto_se)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(_capi.SalmonB200Error, match="no CUDA device"):
+            _capi.quant_files_native(idx, "a.fq", "b.fq", map_params=auto_pe)
+    # the context itself takes the six concrete types only
+    with pytest.raises(_capi.SalmonB200Error):
+        _capi.MapContext(idx, _capi.map_default_params(lib_type=6), device=0, batch_cap=1024, max_read_len=128)
